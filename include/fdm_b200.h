@@ -1,0 +1,207 @@
+/*
+ * fdm_b200.h -- C ABI of the B200-native force-density equilibrium hot path.
+ *
+ * Drop-in boundary for the equilibrium path of arpastrana/jax_fdm.  Every entry point
+ * names the reference interface it replaces (file:line under src/jax_fdm/equilibrium/).
+ * The reference has no FFI of its own (it is pure Python/JAX); these are the functions a
+ * `jax.ffi` / ctypes binding on the reference side would bind.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, int return codes (0 = OK, negative = error; text via
+ *     fdm_last_error(), thread-local).  No torch / JAX types in any signature.
+ *   - all `double*` / `int*` arguments named d_* are DEVICE pointers owned by the caller;
+ *     h_* are HOST pointers.  Arrays are row-major, FP64 values (the reference fixes
+ *     float64 at import, src/jax_fdm/__init__.py:62-72).
+ *   - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     allocates nothing, never synchronises, and is CUDA-graph capturable -- except where a
+ *     function says otherwise.  Scratch memory is caller-provided (fdm_workspace_bytes).
+ *   - batch: B independent designs sharing one topology (the `vmap(model, in_axes=(0, None))`
+ *     of visualization/plotters/loss_plotter.py:98-103).  Per-array batch strides are in
+ *     ELEMENTS; stride 0 means "shared by all designs".
+ */
+#ifndef FDM_B200_H
+#define FDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fdm_plan fdm_plan;
+
+/* ---- error codes ------------------------------------------------------------------ */
+enum {
+  FDM_OK = 0,
+  FDM_ERR_INVALID = -1,        /* bad argument / size                                   */
+  FDM_ERR_CUDA = -2,           /* CUDA runtime error (text in fdm_last_error)           */
+  FDM_ERR_MULTI_EDGE = -3,     /* parallel edges or self loops: reference index_array is ill-defined
+                                  (structures.py:248-288 sums e+1 over duplicates)      */
+  FDM_ERR_NO_SUPPORT = -4,     /* no fixed node / no edge (fdm.py:491-522 asserts)      */
+  FDM_ERR_UNSUPPORTED = -5,    /* configuration outside this build (e.g. band too wide) */
+  FDM_ERR_WORKSPACE = -6       /* workspace too small                                   */
+};
+
+/* device-side solve status, written to info[FDM_INFO_STATUS] */
+enum {
+  FDM_STATUS_OK = 0,
+  FDM_STATUS_NOT_CONVERGED = 1,
+  FDM_STATUS_INDEFINITE = 2,   /* mixed-sign diagonal / pivot: K neither SPD nor -SPD   */
+  FDM_STATUS_BREAKDOWN = 3     /* non-finite scalar met in the iteration                */
+};
+
+/* layout of the per-solve info record (doubles), one record per design of the batch */
+enum {
+  FDM_INFO_STATUS = 0,
+  FDM_INFO_ITERS = 1,
+  FDM_INFO_RELRES = 2,         /* max over rhs of ||r|| / ||b|| (recurrence residual)   */
+  FDM_INFO_SIGN = 3,           /* +1: K SPD, -1: -K SPD                                 */
+  FDM_INFO_STRIDE = 8
+};
+
+/* ---- plan: topology -> static device arrays ----------------------------------------
+ * Replaces Graph.__init__/_edges_indexed (structures/graphs.py:44-97, done by the caller:
+ * `h_edges` are already node INDICES), connectivity_matrix (graphs.py:176-211),
+ * EquilibriumStructure.__init__ + _indices_* (structures/structures.py:53-69, 152-188) and
+ * EquilibriumStructureSparse.__init__ (structures.py:213-350: index_array, diag_indices, diags).
+ * Host work + uploads; synchronous; the only call that allocates device memory.
+ *   h_edges    (E,2) int64  tail, head node index
+ *   h_supports (N)   int64  0 = free, nonzero = fixed
+ */
+int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes,
+                    const int64_t* h_supports, int device, fdm_plan** out);
+void fdm_plan_destroy(fdm_plan* plan);
+
+/* host-only variant (no CUDA calls): builds every topology array but uploads nothing.
+ * Used by CPU tests of the index maps; compute calls on such a plan return FDM_ERR_INVALID. */
+int fdm_plan_create_host(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes,
+                         const int64_t* h_supports, fdm_plan** out);
+
+enum {
+  FDM_SIZE_NODES = 0, FDM_SIZE_EDGES = 1, FDM_SIZE_FREE = 2, FDM_SIZE_FIXED = 3,
+  FDM_SIZE_NNZ = 4,            /* stored entries of K = Nf + 2 * (#free-free edges)     */
+  FDM_SIZE_DIAGS_NNZ = 5,      /* stored entries of `diags`                             */
+  FDM_SIZE_HALF_BANDWIDTH = 6, /* of K after the plan's band ordering (batched Cholesky) */
+  FDM_SIZE_NUM_PARTS = 7       /* aggregates of the two-level preconditioner            */
+};
+int64_t fdm_plan_size(const fdm_plan* plan, int which);
+
+/* Topology arrays as the reference defines them; copied to a HOST
+ * buffer of `capacity` bytes.  Returns bytes written or a negative error.  dtypes follow the
+ * reference (int64 index maps; index_array.indices/indptr int32 as scipy yields them). */
+enum {
+  FDM_ARR_INDICES_FREE = 0,      /* (Nf)   int64  structures.py:152-161                  */
+  FDM_ARR_INDICES_FIXED = 1,     /* (Ns)   int64  structures.py:163-172                  */
+  FDM_ARR_INDICES_FREEFIXED = 2, /* (N)    int64  structures.py:174-188                  */
+  FDM_ARR_INDEX_DATA = 3,        /* (nnz)  int64  index_array.data   structures.py:248-288 */
+  FDM_ARR_INDEX_INDICES = 4,     /* (nnz)  int32  index_array.indices                    */
+  FDM_ARR_INDEX_INDPTR = 5,      /* (Nf+1) int32  index_array.indptr                     */
+  FDM_ARR_DIAG_INDICES = 6,      /* (Nf)   int64  structures.py:290-314                  */
+  FDM_ARR_DIAGS_INDPTR = 7,      /* (Nf+1) int32  diags (BCSR Nf x E) structures.py:316-350 */
+  FDM_ARR_DIAGS_INDICES = 8,     /* (dnnz) int32                                         */
+  FDM_ARR_BAND_PERM = 9,         /* (Nf)   int32  free index -> band-ordered index       */
+  FDM_ARR_PART_OF_ROW = 10       /* (Nf)   int32  free index -> aggregate id             */
+};
+int64_t fdm_plan_get_array(const fdm_plan* plan, int which, void* h_out, int64_t capacity);
+
+/* ---- K1: assembly --------------------------------------------------------------------
+ * Replaces EquilibriumModelSparse.stiffness_matrix (models.py:1037-1079):
+ *     K.data[k] = -q[index_array.data[k]-1],  K.data[diag_indices] = diags @ q
+ * and load_matrix / residual_fixed_matrix (models.py:828-856, 949-976):
+ *     rhs = loads[indices_free] - C_f^T (q * (C_s xyz_fixed)).
+ *   d_q (B,E)  d_xyz_fixed (B|1,Ns,3)  d_loads (B|1,N,3)  ->  d_Kdata (B,nnz)  d_rhs (B,Nf,3)
+ * d_Kdata or d_rhs may be NULL to skip that half.
+ */
+int fdm_assemble(const fdm_plan* plan, const double* d_q, const double* d_xyz_fixed,
+                 const double* d_loads, double* d_Kdata, double* d_rhs, int64_t batch,
+                 int64_t q_stride, int64_t xyz_fixed_stride, int64_t loads_stride, void* stream);
+
+/* ---- K2: the 3-rhs solve ---------------------------------------------------------------
+ * Replaces sparse_solve / spsolve_cpu / spsolve_gpu_ravel (sparse.py:207-230, 130-159, 54-84):
+ * x = K^{-1} rhs with K given by its CSC data array on the plan's pattern (K symmetric).
+ * Also serves the adjoint solve lam = K^{-1} g of sparse_solve_bwd (sparse.py:296).
+ */
+enum {
+  FDM_SOLVER_AUTO = 0,
+  FDM_SOLVER_PCG = 1,            /* Jacobi-PCG, one kernel per phase (any size)          */
+  FDM_SOLVER_PCG_PERSISTENT = 2, /* two-level PCG, one cooperative kernel, K and vectors
+                                    resident in shared memory (meshes that fit)          */
+  FDM_SOLVER_CHOLESKY_BATCHED = 3 /* one CTA per design, banded LL^T in shared memory     */
+};
+
+typedef struct fdm_solve_opts {
+  int32_t solver;       /* FDM_SOLVER_*                                                   */
+  int32_t max_iters;    /* PCG; <=0 -> default 20000                                     */
+  double tol;           /* PCG: stop when ||r|| <= tol * ||b|| for every rhs; <=0 -> 1e-12 */
+  int32_t check_every;  /* multi-kernel PCG: host polls convergence every this many iterations
+                           (synchronises the stream; not graph-capturable); <=0 -> 50    */
+  int32_t reuse_factor; /* Cholesky: nonzero -> d_ws already holds the factor of this K (adjoint
+                           solve after the forward solve, tmax>1 iterations): skip refactoring */
+} fdm_solve_opts;
+
+size_t fdm_workspace_bytes(const fdm_plan* plan, int64_t batch, int32_t solver);
+
+int fdm_solve(const fdm_plan* plan, const double* d_Kdata, const double* d_rhs, double* d_x,
+              double* d_info /* (B, FDM_INFO_STRIDE) or NULL */, void* d_ws, size_t ws_bytes,
+              int64_t batch, const fdm_solve_opts* opts, void* stream);
+
+/* ---- SpMM: Y = K X, X (Nf,3) -----------------------------------------------------------
+ * Replaces `K @ xyz_free` (models.py:1012) and `A @ xk` (sparse.py:301). */
+int fdm_spmm(const fdm_plan* plan, const double* d_Kdata, const double* d_X, double* d_Y,
+             int64_t batch, void* stream);
+
+/* ---- positions ---------------------------------------------------------------------------
+ * Replaces nodes_positions (models.py:195-220): xyz = concat(x_free, xyz_fixed)[indices_freefixed]
+ * and, with transpose != 0, its VJP: x_free_bar = xyz_bar[indices_free], xyz_fixed_bar = xyz_bar[indices_fixed].
+ */
+int fdm_positions(const fdm_plan* plan, double* d_x_free, double* d_xyz_fixed, double* d_xyz,
+                  int64_t batch, int64_t xyz_fixed_stride, int transpose, void* stream);
+
+/* ---- K4: equilibrium state and its VJP ---------------------------------------------------
+ * Replaces equilibrium_state (models.py:753-794): vectors = C xyz, lengths = |vectors|,
+ * residuals = loads - C^T (q * vectors), forces = q * lengths.  Any output may be NULL.
+ */
+int fdm_state(const fdm_plan* plan, const double* d_q, const double* d_xyz, const double* d_loads,
+              double* d_vectors /*(B,E,3)*/, double* d_lengths /*(B,E)*/, double* d_forces /*(B,E)*/,
+              double* d_residuals /*(B,N,3)*/, int64_t batch, int64_t q_stride,
+              int64_t loads_stride, void* stream);
+
+/* VJP of fdm_state (JAX autodiff of models.py:780-794).  Input cotangents may be NULL (= 0).
+ * Outputs are OVERWRITTEN: q_bar (B,E), xyz_bar (B,N,3), loads_bar (B,N,3) [loads_bar =
+ * loads_cot + residuals_cot].  A zero-length edge with nonzero length/force cotangent gives
+ * NaN, like jnp.linalg.norm's gradient. */
+int fdm_state_vjp(const fdm_plan* plan, const double* d_q, const double* d_xyz,
+                  const double* d_xyz_cot, const double* d_residuals_cot,
+                  const double* d_lengths_cot, const double* d_forces_cot,
+                  const double* d_loads_cot, const double* d_vectors_cot,
+                  double* d_q_bar, double* d_xyz_bar, double* d_loads_bar,
+                  int64_t batch, int64_t q_stride, void* stream);
+
+/* ---- K3: gradients of the implicit solve ---------------------------------------------------
+ * Replaces the tail of sparse_solve_bwd (sparse.py:299-308) plus the autodiff transposes of
+ * stiffness_matrix (models.py:1069-1077) and load_matrix (models.py:856, 973-976), given the
+ * adjoint solution lam = K^{-1} g:
+ *     q_bar_e        (+)= -(lam_head - lam_tail) . (xyz_head - xyz_tail)     (lam = 0 on supports)
+ *     loads_bar[free] (+)= lam
+ *     xyz_fixed_bar_s (+)= sum_{e=(s,j), j free} q_e lam_j
+ * accumulate != 0 adds to what the output buffers hold (direct terms from fdm_state_vjp /
+ * fdm_positions(transpose)); accumulate == 0 overwrites (loads_bar rows of supports <- 0).
+ */
+int fdm_adjoint_grads(const fdm_plan* plan, const double* d_q, const double* d_xyz,
+                      const double* d_lam, double* d_q_bar, double* d_loads_bar,
+                      double* d_xyz_fixed_bar, int64_t batch, int64_t q_stride, int accumulate,
+                      void* stream);
+
+/* ---- helper used by the benchmark's loss (above the path; kept here so the timed region
+ * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */
+int fdm_loss_sqdist(const double* d_x, const double* d_x0, double* d_g, double* d_loss,
+                    int64_t n_per_design, int64_t batch, int64_t x0_stride, void* stream);
+
+const char* fdm_last_error(void);
+const char* fdm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDM_B200_H */

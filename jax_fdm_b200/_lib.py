@@ -1,0 +1,100 @@
+"""
+ctypes binding of the C ABI in include/fdm_b200.h (libfdm_b200.so, built in-tree by
+`__graft_entry__.build()` / `python -m jax_fdm_b200.build`).
+
+There is no fallback: if the shared library is missing, import of any compute entry
+point raises.  The CPU oracle under oracle/ is never imported from here.
+"""
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libfdm_b200.so")
+
+# ---- constants mirrored from include/fdm_b200.h ----
+FDM_OK = 0
+ERRORS = {-1: "INVALID", -2: "CUDA", -3: "MULTI_EDGE", -4: "NO_SUPPORT", -5: "UNSUPPORTED", -6: "WORKSPACE"}
+STATUS_OK, STATUS_NOT_CONVERGED, STATUS_INDEFINITE, STATUS_BREAKDOWN = 0, 1, 2, 3
+INFO_STATUS, INFO_ITERS, INFO_RELRES, INFO_SIGN, INFO_STRIDE = 0, 1, 2, 3, 8
+SIZE_NODES, SIZE_EDGES, SIZE_FREE, SIZE_FIXED, SIZE_NNZ, SIZE_DIAGS_NNZ, SIZE_HBW, SIZE_PARTS = range(8)
+(ARR_INDICES_FREE, ARR_INDICES_FIXED, ARR_INDICES_FREEFIXED, ARR_INDEX_DATA, ARR_INDEX_INDICES,
+ ARR_INDEX_INDPTR, ARR_DIAG_INDICES, ARR_DIAGS_INDPTR, ARR_DIAGS_INDICES, ARR_BAND_PERM,
+ ARR_PART_OF_ROW) = range(11)
+SOLVER_AUTO, SOLVER_PCG, SOLVER_PCG_PERSISTENT, SOLVER_CHOLESKY_BATCHED = 0, 1, 2, 3
+SOLVERS = {"auto": 0, "pcg": 1, "pcg_persistent": 2, "cholesky": 3}
+
+EXPORTS = [
+    "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",
+    "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_spmm",
+    "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_adjoint_grads", "fdm_loss_sqdist",
+    "fdm_last_error", "fdm_version",
+]
+
+
+class SolveOpts(C.Structure):
+    _fields_ = [("solver", C.c_int32), ("max_iters", C.c_int32), ("tol", C.c_double),
+                ("check_every", C.c_int32), ("reuse_factor", C.c_int32)]
+
+
+class FdmError(RuntimeError):
+    def __init__(self, code, text):
+        self.code = code
+        super().__init__(f"fdm_b200 error {code} ({ERRORS.get(code, '?')}): {text}")
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+            "There is no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
+    L.fdm_plan_create.argtypes = [vp, i64, i64, vp, C.c_int, C.POINTER(vp)]
+    L.fdm_plan_create.restype = C.c_int
+    L.fdm_plan_create_host.argtypes = [vp, i64, i64, vp, C.POINTER(vp)]
+    L.fdm_plan_create_host.restype = C.c_int
+    L.fdm_plan_destroy.argtypes = [vp]
+    L.fdm_plan_destroy.restype = None
+    L.fdm_plan_size.argtypes = [vp, C.c_int]
+    L.fdm_plan_size.restype = i64
+    L.fdm_plan_get_array.argtypes = [vp, C.c_int, vp, i64]
+    L.fdm_plan_get_array.restype = i64
+    L.fdm_assemble.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, vp]
+    L.fdm_assemble.restype = C.c_int
+    L.fdm_workspace_bytes.argtypes = [vp, i64, i32]
+    L.fdm_workspace_bytes.restype = sz
+    L.fdm_solve.argtypes = [vp, vp, vp, vp, vp, vp, sz, i64, C.POINTER(SolveOpts), vp]
+    L.fdm_solve.restype = C.c_int
+    L.fdm_spmm.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.fdm_spmm.restype = C.c_int
+    L.fdm_positions.argtypes = [vp, vp, vp, vp, i64, i64, C.c_int, vp]
+    L.fdm_positions.restype = C.c_int
+    L.fdm_state.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.fdm_state.restype = C.c_int
+    L.fdm_state_vjp.argtypes = [vp] + [vp] * 8 + [vp] * 3 + [i64, i64, vp]
+    L.fdm_state_vjp.restype = C.c_int
+    L.fdm_adjoint_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
+    L.fdm_adjoint_grads.restype = C.c_int
+    L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
+    L.fdm_loss_sqdist.restype = C.c_int
+    L.fdm_last_error.argtypes = []
+    L.fdm_last_error.restype = C.c_char_p
+    L.fdm_version.argtypes = []
+    L.fdm_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != FDM_OK:
+        raise FdmError(rc, lib().fdm_last_error().decode())

@@ -1,0 +1,290 @@
+// C ABI (include/fdm_b200.h): plan lifetime, array getters, argument checks, dispatch.
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+
+#include "launch.h"
+
+namespace {
+
+template <class T>
+int upload(const std::vector<T>& h, T** d, size_t slack_bytes = 16) {
+  *d = nullptr;
+  const size_t bytes = h.size() * sizeof(T);
+  FDM_CUDA(cudaMalloc((void**)d, bytes + slack_bytes));
+  if (bytes) FDM_CUDA(cudaMemcpy(*d, h.data(), bytes, cudaMemcpyHostToDevice));
+  FDM_CUDA(cudaMemset((char*)*d + bytes, 0, slack_bytes));
+  return FDM_OK;
+}
+
+void free_device(fdm_plan* p) {
+  DeviceArrays& d = p->d;
+  void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
+                  d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
+                  d.band_iperm, d.band_kidx};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  d = DeviceArrays();
+}
+
+int build_host(fdm_plan* p, const int64_t* edges, int64_t E, int64_t N, const int64_t* supports,
+               int num_parts) {
+  int rc = fdm_build_topology(*p, edges, E, N, supports);
+  if (rc != FDM_OK) return rc;
+  fdm_build_band_order(*p);
+  fdm_build_partition(*p, num_parts);
+  return FDM_OK;
+}
+
+template <class T>
+int64_t copy_out(const std::vector<T>& v, void* out, int64_t cap) {
+  const int64_t bytes = (int64_t)(v.size() * sizeof(T));
+  if (!out || cap < bytes) {
+    fdm_set_error("fdm_plan_get_array: buffer too small (need " + std::to_string(bytes) + " bytes)");
+    return FDM_ERR_INVALID;
+  }
+  if (bytes) std::memcpy(out, v.data(), (size_t)bytes);
+  return bytes;
+}
+
+inline bool ready(const fdm_plan* p, const char* who) {
+  if (!p || !p->on_device) {
+    fdm_set_error(std::string(who) + ": plan is null or host-only");
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fdm_version(void) { return "fdm_b200 0.1 (sm_100a)"; }
+
+int fdm_plan_create_host(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes,
+                         const int64_t* h_supports, fdm_plan** out) {
+  if (!out) return FDM_ERR_INVALID;
+  *out = nullptr;
+  fdm_plan* p = new (std::nothrow) fdm_plan();
+  if (!p) return FDM_ERR_INVALID;
+  int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, 148);
+  if (rc != FDM_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return FDM_OK;
+}
+
+int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes,
+                    const int64_t* h_supports, int device, fdm_plan** out) {
+  if (!out) return FDM_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  FDM_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) {
+    fdm_set_error("fdm_plan_create: no such CUDA device " + std::to_string(device));
+    return FDM_ERR_CUDA;
+  }
+  FDM_CUDA(cudaSetDevice(device));
+  int sms = 0;
+  FDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  fdm_plan* p = new (std::nothrow) fdm_plan();
+  if (!p) return FDM_ERR_INVALID;
+  p->device = device;
+  p->sm_count = sms;
+  int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, sms);
+  if (rc == FDM_OK) {
+    DeviceArrays& d = p->d;
+    int (*steps[])(fdm_plan*) = {
+        [](fdm_plan* q) { return upload(q->node_slot, &q->d.node_slot); },
+        [](fdm_plan* q) { return upload(q->edge_nodes, &q->d.edge_nodes); },
+        [](fdm_plan* q) { return upload(q->ninc_ptr, &q->d.ninc_ptr); },
+        [](fdm_plan* q) { return upload(q->ninc_edge, &q->d.ninc_edge); },
+        [](fdm_plan* q) { return upload(q->ninc_other, &q->d.ninc_other); },
+        [](fdm_plan* q) { return upload(q->free_node, &q->d.free_node); },
+        [](fdm_plan* q) { return upload(q->fixed_node, &q->d.fixed_node); },
+        [](fdm_plan* q) { return upload(q->index_indptr, &q->d.rowptr); },
+        [](fdm_plan* q) { return upload(q->index_indices, &q->d.colidx); },
+        [](fdm_plan* q) { return upload(q->entry_edge, &q->d.entry_edge); },
+        [](fdm_plan* q) { return upload(q->diag_pos, &q->d.diag_pos); },
+        [](fdm_plan* q) { return upload(q->band_perm, &q->d.band_perm); },
+        [](fdm_plan* q) { return upload(q->band_iperm, &q->d.band_iperm); },
+        [](fdm_plan* q) { return upload(q->band_kidx, &q->d.band_kidx); },
+    };
+    (void)d;
+    for (auto f : steps) {
+      rc = f(p);
+      if (rc != FDM_OK) break;
+    }
+  }
+  if (rc != FDM_OK) {
+    free_device(p);
+    delete p;
+    return rc;
+  }
+  p->on_device = true;
+  *out = p;
+  return FDM_OK;
+}
+
+void fdm_plan_destroy(fdm_plan* plan) {
+  if (!plan) return;
+  if (plan->on_device) {
+    cudaSetDevice(plan->device);
+    pcg2_destroy(plan);
+    free_device(plan);
+  }
+  delete plan;
+}
+
+int64_t fdm_plan_size(const fdm_plan* p, int which) {
+  if (!p) return FDM_ERR_INVALID;
+  switch (which) {
+    case FDM_SIZE_NODES: return p->N;
+    case FDM_SIZE_EDGES: return p->E;
+    case FDM_SIZE_FREE: return p->Nf;
+    case FDM_SIZE_FIXED: return p->Ns;
+    case FDM_SIZE_NNZ: return p->nnz;
+    case FDM_SIZE_DIAGS_NNZ: return p->dnnz;
+    case FDM_SIZE_HALF_BANDWIDTH: return p->hbw;
+    case FDM_SIZE_NUM_PARTS: return p->num_parts;
+  }
+  return FDM_ERR_INVALID;
+}
+
+int64_t fdm_plan_get_array(const fdm_plan* p, int which, void* h_out, int64_t capacity) {
+  if (!p) return FDM_ERR_INVALID;
+  switch (which) {
+    case FDM_ARR_INDICES_FREE: return copy_out(p->indices_free, h_out, capacity);
+    case FDM_ARR_INDICES_FIXED: return copy_out(p->indices_fixed, h_out, capacity);
+    case FDM_ARR_INDICES_FREEFIXED: return copy_out(p->indices_freefixed, h_out, capacity);
+    case FDM_ARR_INDEX_DATA: return copy_out(p->index_data, h_out, capacity);
+    case FDM_ARR_INDEX_INDICES: return copy_out(p->index_indices, h_out, capacity);
+    case FDM_ARR_INDEX_INDPTR: return copy_out(p->index_indptr, h_out, capacity);
+    case FDM_ARR_DIAG_INDICES: return copy_out(p->diag_indices, h_out, capacity);
+    case FDM_ARR_DIAGS_INDPTR: return copy_out(p->diags_indptr, h_out, capacity);
+    case FDM_ARR_DIAGS_INDICES: return copy_out(p->diags_indices, h_out, capacity);
+    case FDM_ARR_BAND_PERM: return copy_out(p->band_perm, h_out, capacity);
+    case FDM_ARR_PART_OF_ROW: return copy_out(p->part_of_row, h_out, capacity);
+  }
+  fdm_set_error("fdm_plan_get_array: unknown array id");
+  return FDM_ERR_INVALID;
+}
+
+int fdm_assemble(const fdm_plan* p, const double* q, const double* xs, const double* loads,
+                 double* Kdata, double* rhs, int64_t batch, int64_t qs, int64_t xss, int64_t ls,
+                 void* stream) {
+  if (!ready(p, "fdm_assemble")) return FDM_ERR_INVALID;
+  if (!q || batch <= 0 || (rhs && (!xs || !loads)) || (!Kdata && !rhs)) {
+    fdm_set_error("fdm_assemble: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_assemble(p, q, xs, loads, Kdata, rhs, batch, qs, xss, ls, (cudaStream_t)stream);
+}
+
+static int pick_solver(const fdm_plan* p, int64_t batch, int32_t want) {
+  if (want != FDM_SOLVER_AUTO) return want;
+  if (chol_supported(p) && (batch > 1 || !pcg2_supported(p))) return FDM_SOLVER_CHOLESKY_BATCHED;
+  if (pcg2_supported(p)) return FDM_SOLVER_PCG_PERSISTENT;
+  return FDM_SOLVER_PCG;
+}
+
+size_t fdm_workspace_bytes(const fdm_plan* p, int64_t batch, int32_t solver) {
+  if (!p || batch <= 0) return 0;
+  switch (pick_solver(p, batch, solver)) {
+    case FDM_SOLVER_PCG: return pcg_workspace_bytes(p);
+    case FDM_SOLVER_PCG_PERSISTENT: return pcg2_workspace_bytes(p);
+    case FDM_SOLVER_CHOLESKY_BATCHED: return chol_workspace_bytes(p, batch);
+  }
+  return 0;
+}
+
+int fdm_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
+              void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts* opts, void* stream) {
+  if (!ready(p, "fdm_solve")) return FDM_ERR_INVALID;
+  if (!Kdata || !rhs || !x || batch <= 0 || (!ws && ws_bytes)) {
+    fdm_set_error("fdm_solve: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  fdm_solve_opts o;
+  std::memset(&o, 0, sizeof(o));
+  if (opts) o = *opts;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (pick_solver(p, batch, o.solver)) {
+    case FDM_SOLVER_PCG: return pcg_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
+    case FDM_SOLVER_PCG_PERSISTENT: return pcg2_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
+    case FDM_SOLVER_CHOLESKY_BATCHED: return chol_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
+  }
+  fdm_set_error("fdm_solve: unknown solver id");
+  return FDM_ERR_INVALID;
+}
+
+int fdm_spmm(const fdm_plan* p, const double* Kdata, const double* X, double* Y, int64_t batch,
+             void* stream) {
+  if (!ready(p, "fdm_spmm")) return FDM_ERR_INVALID;
+  if (!Kdata || !X || !Y || batch <= 0) {
+    fdm_set_error("fdm_spmm: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_spmm(p, Kdata, X, Y, batch, (cudaStream_t)stream);
+}
+
+int fdm_positions(const fdm_plan* p, double* xf, double* xs, double* xyz, int64_t batch, int64_t xss,
+                  int transpose, void* stream) {
+  if (!ready(p, "fdm_positions")) return FDM_ERR_INVALID;
+  if (!xyz || batch <= 0 || (!transpose && (!xf || !xs))) {
+    fdm_set_error("fdm_positions: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_positions(p, xf, xs, xyz, batch, xss, transpose, (cudaStream_t)stream);
+}
+
+int fdm_state(const fdm_plan* p, const double* q, const double* xyz, const double* loads,
+              double* vectors, double* lengths, double* forces, double* residuals, int64_t batch,
+              int64_t qs, int64_t ls, void* stream) {
+  if (!ready(p, "fdm_state")) return FDM_ERR_INVALID;
+  if (!q || !xyz || batch <= 0 || (residuals && !loads)) {
+    fdm_set_error("fdm_state: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_state(p, q, xyz, loads, vectors, lengths, forces, residuals, batch, qs, ls,
+                      (cudaStream_t)stream);
+}
+
+int fdm_state_vjp(const fdm_plan* p, const double* q, const double* xyz, const double* xyz_cot,
+                  const double* rbar, const double* lbar, const double* fbar, const double* loads_cot,
+                  const double* vbar, double* q_bar, double* xyz_bar, double* loads_bar,
+                  int64_t batch, int64_t qs, void* stream) {
+  if (!ready(p, "fdm_state_vjp")) return FDM_ERR_INVALID;
+  if (!q || !xyz || batch <= 0) {
+    fdm_set_error("fdm_state_vjp: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_state_vjp(p, q, xyz, xyz_cot, rbar, lbar, fbar, loads_cot, vbar, q_bar, xyz_bar,
+                          loads_bar, batch, qs, (cudaStream_t)stream);
+}
+
+int fdm_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, const double* lam,
+                      double* q_bar, double* loads_bar, double* xs_bar, int64_t batch, int64_t qs,
+                      int accumulate, void* stream) {
+  if (!ready(p, "fdm_adjoint_grads")) return FDM_ERR_INVALID;
+  if (!q || !xyz || !lam || batch <= 0) {
+    fdm_set_error("fdm_adjoint_grads: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_adjoint_grads(p, q, xyz, lam, q_bar, loads_bar, xs_bar, batch, qs, accumulate,
+                              (cudaStream_t)stream);
+}
+
+int fdm_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
+                    int64_t batch, int64_t x0_stride, void* stream) {
+  if (!x || !x0 || n <= 0 || batch <= 0) {
+    fdm_set_error("fdm_loss_sqdist: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_loss_sqdist(x, x0, g, loss, n, batch, x0_stride, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// K1 (assembly), positions, K4 (state + VJP), K3 (adjoint gradients), loss helper.
+// All HBM-bound gather/segmented-sum kernels: FP64 values, int32 indices, one design per
+// blockIdx.y.  Every sum runs over a precomputed incidence list in ascending edge id, so
+// results are deterministic and independent of the launch geometry.
+#include <cuda_runtime.h>
+
+#include "plan.h"
+#include "launch.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ double3 ld3(const double* __restrict__ p, int64_t row) {
+  const double* q = p + 3 * row;
+  return make_double3(__ldg(q), __ldg(q + 1), __ldg(q + 2));
+}
+__device__ __forceinline__ void st3(double* p, int64_t row, double3 v) {
+  double* q = p + 3 * row;
+  q[0] = v.x; q[1] = v.y; q[2] = v.z;
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: K.data and rhs.   models.py:1064-1079, 828-856, 949-976
+//   thread t < nnz : off-diagonal entry t        K.data[t] = -q[entry_edge[t]]
+//   thread t < Nf  : row t                        K.data[diag_pos[t]] = sum_inc q_e   (ascending e)
+//                                                 rhs[t] = loads[node] + sum_{e to support s} q_e xyz_fixed[s]
+// Algorithmic bytes per design: 16E + 12nnz + 52Nf + 24Ns.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+assemble_kernel(int nnz, int Nf, int N, int Ns,
+                const int32_t* __restrict__ entry_edge, const int32_t* __restrict__ diag_pos,
+                const int32_t* __restrict__ free_node, const int32_t* __restrict__ node_slot,
+                const int32_t* __restrict__ ninc_ptr, const int32_t* __restrict__ ninc_edge,
+                const int32_t* __restrict__ ninc_other,
+                const double* __restrict__ q, const double* __restrict__ xs,
+                const double* __restrict__ loads, double* __restrict__ Kdata,
+                double* __restrict__ rhs, int64_t q_stride, int64_t xs_stride, int64_t loads_stride) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  q += b * q_stride;
+  if (Kdata) {
+    Kdata += b * (int64_t)nnz;
+    if (t < nnz) {
+      const int e = __ldg(entry_edge + t);
+      if (e >= 0) Kdata[t] = -__ldg(q + e);
+    }
+  }
+  if (t < Nf) {
+    const int n = __ldg(free_node + t);
+    const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
+    double diag = 0.0;
+    double3 acc = make_double3(0.0, 0.0, 0.0);
+    const double* xsb = xs ? xs + b * xs_stride : nullptr;
+    for (int k = k0; k < k1; ++k) {
+      const double qe = __ldg(q + (__ldg(ninc_edge + k) >> 1));
+      diag += qe;
+      if (rhs) {
+        const int slot = __ldg(node_slot + __ldg(ninc_other + k));
+        if (slot < 0) {
+          const double3 x = ld3(xsb, -slot - 1);
+          acc.x += qe * x.x; acc.y += qe * x.y; acc.z += qe * x.z;
+        }
+      }
+    }
+    if (Kdata) Kdata[__ldg(diag_pos + t)] = diag;
+    if (rhs) {
+      const double3 p = ld3(loads + b * loads_stride, n);
+      st3(rhs + b * (int64_t)Nf * 3, t, make_double3(p.x + acc.x, p.y + acc.y, p.z + acc.z));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// positions  (models.py:195-220)  and transpose
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+positions_kernel(int N, int Nf, int Ns, const int32_t* __restrict__ node_slot,
+                 double* __restrict__ x_free, double* __restrict__ xs, double* __restrict__ xyz,
+                 int64_t xs_stride, int transpose) {
+  const int64_t b = blockIdx.y;
+  const int n = blockIdx.x * kThreads + threadIdx.x;
+  if (n >= N) return;
+  const int slot = __ldg(node_slot + n);
+  double* xf = x_free ? x_free + b * (int64_t)Nf * 3 : nullptr;
+  double* xsb = xs ? xs + b * xs_stride : nullptr;
+  double* xb = xyz + b * (int64_t)N * 3;
+  if (!transpose) {
+    st3(xb, n, slot >= 0 ? ld3(xf, slot) : ld3(xsb, -slot - 1));
+  } else {
+    const double3 v = ld3(xb, n);
+    if (slot >= 0) { if (xf) st3(xf, slot, v); }
+    else if (xsb) st3(xsb, -slot - 1, v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 forward: equilibrium_state (models.py:753-794).  Bytes per design: 56E + 72N.
+//   thread t < E: vectors, lengths, forces       thread t < N: residuals
+// residual_n = loads_n - sum_inc q_e (xyz_n - xyz_other)   (sign of C^T folds into the difference)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+state_kernel(int E, int N, const int32_t* __restrict__ edge_nodes,
+             const int32_t* __restrict__ ninc_ptr, const int32_t* __restrict__ ninc_edge,
+             const int32_t* __restrict__ ninc_other,
+             const double* __restrict__ q, const double* __restrict__ xyz,
+             const double* __restrict__ loads, double* __restrict__ vectors,
+             double* __restrict__ lengths, double* __restrict__ forces,
+             double* __restrict__ residuals, int64_t q_stride, int64_t loads_stride) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  q += b * q_stride;
+  xyz += b * (int64_t)N * 3;
+  if (t < E && (vectors || lengths || forces)) {
+    const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + t);
+    const double3 a = ld3(xyz, th.x), c = ld3(xyz, th.y);
+    const double3 v = make_double3(c.x - a.x, c.y - a.y, c.z - a.z);
+    if (vectors) st3(vectors + b * (int64_t)E * 3, t, v);
+    if (lengths || forces) {
+      const double len = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+      if (lengths) lengths[b * (int64_t)E + t] = len;
+      if (forces) forces[b * (int64_t)E + t] = __ldg(q + t) * len;
+    }
+  }
+  if (t < N && residuals) {
+    const double3 xn = ld3(xyz, t);
+    double3 r = ld3(loads + b * loads_stride, t);
+    const int k0 = __ldg(ninc_ptr + t), k1 = __ldg(ninc_ptr + t + 1);
+    for (int k = k0; k < k1; ++k) {
+      const double qe = __ldg(q + (__ldg(ninc_edge + k) >> 1));
+      const double3 xo = ld3(xyz, __ldg(ninc_other + k));
+      r.x -= qe * (xn.x - xo.x); r.y -= qe * (xn.y - xo.y); r.z -= qe * (xn.z - xo.z);
+    }
+    st3(residuals + b * (int64_t)N * 3, t, r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K4 reverse (autodiff transpose of models.py:780-794; SURVEY.md Appendix B "direct" terms)
+//   per edge e=(t,h):  v = x_h - x_t, l = |v|, Crb = rbar_h - rbar_t
+//       q_bar_e  = fbar_e * l - Crb . v
+//       vtot_e   = vbar_e + (lbar_e + q_e fbar_e) v / l - q_e Crb
+//   per node n:        xyz_bar_n = xyz_cot_n + sum_inc (+vtot_e if n is head, -vtot_e if tail)
+//                      loads_bar_n = loads_cot_n + rbar_n
+// Node threads recompute vtot of their incident edges, so no (E,3) temporary and no atomics.
+// ---------------------------------------------------------------------------------------
+struct EdgeCot {
+  const double *rbar, *lbar, *fbar, *vbar;
+};
+
+__device__ __forceinline__ double3 edge_vtot(const EdgeCot& c, int e, int t, int h,
+                                             const double* __restrict__ xyz, double qe,
+                                             double* qbar_out) {
+  const double3 a = ld3(xyz, t), d = ld3(xyz, h);
+  const double3 v = make_double3(d.x - a.x, d.y - a.y, d.z - a.z);
+  double3 crb = make_double3(0.0, 0.0, 0.0);
+  if (c.rbar) {
+    const double3 rt = ld3(c.rbar, t), rh = ld3(c.rbar, h);
+    crb = make_double3(rh.x - rt.x, rh.y - rt.y, rh.z - rt.z);
+  }
+  double3 vt = c.vbar ? ld3(c.vbar, e) : make_double3(0.0, 0.0, 0.0);
+  vt.x -= qe * crb.x; vt.y -= qe * crb.y; vt.z -= qe * crb.z;
+  const double fb = c.fbar ? __ldg(c.fbar + e) : 0.0;
+  const double ltot = (c.lbar ? __ldg(c.lbar + e) : 0.0) + qe * fb;
+  double len = 0.0;
+  if (ltot != 0.0 || (qbar_out && fb != 0.0)) len = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+  if (ltot != 0.0) {
+    const double s = ltot / len;  // len == 0 -> NaN, as jnp.linalg.norm's gradient
+    vt.x += s * v.x; vt.y += s * v.y; vt.z += s * v.z;
+  }
+  if (qbar_out) *qbar_out = fb * len - (crb.x * v.x + crb.y * v.y + crb.z * v.z);
+  return vt;
+}
+
+__global__ void __launch_bounds__(kThreads)
+state_vjp_kernel(int E, int N, const int32_t* __restrict__ edge_nodes,
+                 const int32_t* __restrict__ ninc_ptr, const int32_t* __restrict__ ninc_edge,
+                 const int32_t* __restrict__ ninc_other,
+                 const double* __restrict__ q, const double* __restrict__ xyz,
+                 const double* __restrict__ xyz_cot, const double* __restrict__ rbar,
+                 const double* __restrict__ lbar, const double* __restrict__ fbar,
+                 const double* __restrict__ loads_cot, const double* __restrict__ vbar,
+                 double* __restrict__ q_bar, double* __restrict__ xyz_bar,
+                 double* __restrict__ loads_bar, int64_t q_stride) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  q += b * q_stride;
+  xyz += b * (int64_t)N * 3;
+  EdgeCot c;
+  c.rbar = rbar ? rbar + b * (int64_t)N * 3 : nullptr;
+  c.lbar = lbar ? lbar + b * (int64_t)E : nullptr;
+  c.fbar = fbar ? fbar + b * (int64_t)E : nullptr;
+  c.vbar = vbar ? vbar + b * (int64_t)E * 3 : nullptr;
+  if (t < E && q_bar) {
+    const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + t);
+    double qb;
+    edge_vtot(c, t, th.x, th.y, xyz, __ldg(q + t), &qb);
+    q_bar[b * (int64_t)E + t] = qb;
+  }
+  if (t < N) {
+    if (xyz_bar) {
+      double3 acc = xyz_cot ? ld3(xyz_cot + b * (int64_t)N * 3, t) : make_double3(0.0, 0.0, 0.0);
+      if (c.rbar || c.lbar || c.fbar || c.vbar) {
+        const int k0 = __ldg(ninc_ptr + t), k1 = __ldg(ninc_ptr + t + 1);
+        for (int k = k0; k < k1; ++k) {
+          const int code = __ldg(ninc_edge + k);
+          const int e = code >> 1, o = __ldg(ninc_other + k);
+          const bool is_head = code & 1;
+          const double3 vt = edge_vtot(c, e, is_head ? o : t, is_head ? t : o, xyz, __ldg(q + e), nullptr);
+          const double s = is_head ? 1.0 : -1.0;
+          acc.x += s * vt.x; acc.y += s * vt.y; acc.z += s * vt.z;
+        }
+      }
+      st3(xyz_bar + b * (int64_t)N * 3, t, acc);
+    }
+    if (loads_bar) {
+      double3 l = loads_cot ? ld3(loads_cot + b * (int64_t)N * 3, t) : make_double3(0.0, 0.0, 0.0);
+      if (c.rbar) { const double3 r = ld3(c.rbar, t); l.x += r.x; l.y += r.y; l.z += r.z; }
+      st3(loads_bar + b * (int64_t)N * 3, t, l);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: gradients of the implicit solve (sparse.py:299-308 + transposes of models.py:1069-1077,
+// 856, 973-976).  Bytes per design: 24E + 24Nf + 48N + 24Ns.
+//   thread t < E: q_bar_e (+)= -(lam_h - lam_t).(x_h - x_t), lam = 0 on supports
+//   thread t < N: free  -> loads_bar_n (+)= lam[slot]
+//                 fixed -> xyz_fixed_bar_s (+)= sum_{inc, other free} q_e lam[other]; loads_bar_n (+)= 0
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+adjoint_grads_kernel(int E, int N, int Nf, int Ns, const int32_t* __restrict__ edge_nodes,
+                     const int32_t* __restrict__ node_slot, const int32_t* __restrict__ ninc_ptr,
+                     const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
+                     const double* __restrict__ q, const double* __restrict__ xyz,
+                     const double* __restrict__ lam, double* __restrict__ q_bar,
+                     double* __restrict__ loads_bar, double* __restrict__ xs_bar,
+                     int64_t q_stride, int accumulate) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  q += b * q_stride;
+  xyz += b * (int64_t)N * 3;
+  lam += b * (int64_t)Nf * 3;
+  const double3 zero = make_double3(0.0, 0.0, 0.0);
+  if (t < E && q_bar) {
+    const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + t);
+    const int st = __ldg(node_slot + th.x), sh = __ldg(node_slot + th.y);
+    const double3 lt = st >= 0 ? ld3(lam, st) : zero, lh = sh >= 0 ? ld3(lam, sh) : zero;
+    const double3 a = ld3(xyz, th.x), c = ld3(xyz, th.y);
+    const double g = -((lh.x - lt.x) * (c.x - a.x) + (lh.y - lt.y) * (c.y - a.y) + (lh.z - lt.z) * (c.z - a.z));
+    double* out = q_bar + b * (int64_t)E + t;
+    *out = accumulate ? *out + g : g;
+  }
+  if (t < N) {
+    const int slot = __ldg(node_slot + t);
+    if (slot >= 0) {
+      if (loads_bar) {
+        double* out = loads_bar + (b * (int64_t)N + t) * 3;
+        const double3 l = ld3(lam, slot);
+        if (accumulate) { out[0] += l.x; out[1] += l.y; out[2] += l.z; }
+        else { out[0] = l.x; out[1] = l.y; out[2] = l.z; }
+      }
+    } else {
+      if (loads_bar && !accumulate) st3(loads_bar + b * (int64_t)N * 3, t, zero);
+      if (xs_bar) {
+        double3 acc = zero;
+        const int k0 = __ldg(ninc_ptr + t), k1 = __ldg(ninc_ptr + t + 1);
+        for (int k = k0; k < k1; ++k) {
+          const int so = __ldg(node_slot + __ldg(ninc_other + k));
+          if (so >= 0) {
+            const double qe = __ldg(q + (__ldg(ninc_edge + k) >> 1));
+            const double3 l = ld3(lam, so);
+            acc.x += qe * l.x; acc.y += qe * l.y; acc.z += qe * l.z;
+          }
+        }
+        double* out = xs_bar + (b * (int64_t)Ns + (-slot - 1)) * 3;
+        if (accumulate) { out[0] += acc.x; out[1] += acc.y; out[2] += acc.z; }
+        else { out[0] = acc.x; out[1] = acc.y; out[2] = acc.z; }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// loss helper: g = x - x0, loss_b = 0.5 sum g^2   (one CTA per design, fixed-order reduction)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+loss_sqdist_kernel(const double* __restrict__ x, const double* __restrict__ x0,
+                   double* __restrict__ g, double* __restrict__ loss, int64_t n, int64_t x0_stride) {
+  const int64_t b = blockIdx.x;
+  x += b * n;
+  x0 += b * x0_stride;
+  if (g) g += b * n;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = x[i] - __ldg(x0 + i);
+    if (g) g[i] = d;
+    acc += d * d;
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0 && loss) loss[b] = 0.5 * acc;
+  }
+}
+
+inline dim3 grid_for(int64_t work, int64_t batch) {
+  return dim3((unsigned)((work + kThreads - 1) / kThreads), (unsigned)batch, 1);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const double* loads,
+                    double* Kdata, double* rhs, int64_t batch, int64_t qs, int64_t xss, int64_t ls,
+                    cudaStream_t st) {
+  const int64_t work = std::max<int64_t>(Kdata ? p->nnz : 0, p->Nf);
+  const DeviceArrays& d = p->d;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    assemble_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
+        (int)p->nnz, (int)p->Nf, (int)p->N, (int)p->Ns, d.entry_edge, d.diag_pos, d.free_node,
+        d.node_slot, d.ninc_ptr, d.ninc_edge, d.ninc_other, q + b0 * qs,
+        xs ? xs + b0 * xss : nullptr, loads ? loads + b0 * ls : nullptr,
+        Kdata ? Kdata + b0 * p->nnz : nullptr, rhs ? rhs + b0 * p->Nf * 3 : nullptr, qs, xss, ls);
+  }
+  return fdm_check_launch("assemble");
+}
+
+int launch_positions(const fdm_plan* p, double* xf, double* xs, double* xyz, int64_t batch,
+                     int64_t xss, int transpose, cudaStream_t st) {
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    positions_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
+        (int)p->N, (int)p->Nf, (int)p->Ns, p->d.node_slot, xf ? xf + b0 * p->Nf * 3 : nullptr,
+        xs ? xs + b0 * xss : nullptr, xyz + b0 * p->N * 3, xss, transpose);
+  }
+  return fdm_check_launch("positions");
+}
+
+int launch_state(const fdm_plan* p, const double* q, const double* xyz, const double* loads,
+                 double* vectors, double* lengths, double* forces, double* residuals,
+                 int64_t batch, int64_t qs, int64_t ls, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  const int64_t work = std::max(p->E, p->N);
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    state_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
+        (int)p->E, (int)p->N, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, q + b0 * qs,
+        xyz + b0 * p->N * 3, loads ? loads + b0 * ls : nullptr,
+        vectors ? vectors + b0 * p->E * 3 : nullptr, lengths ? lengths + b0 * p->E : nullptr,
+        forces ? forces + b0 * p->E : nullptr, residuals ? residuals + b0 * p->N * 3 : nullptr, qs, ls);
+  }
+  return fdm_check_launch("state");
+}
+
+int launch_state_vjp(const fdm_plan* p, const double* q, const double* xyz, const double* xyz_cot,
+                     const double* rbar, const double* lbar, const double* fbar,
+                     const double* loads_cot, const double* vbar, double* q_bar, double* xyz_bar,
+                     double* loads_bar, int64_t batch, int64_t qs, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  const int64_t work = std::max(p->E, p->N);
+  const int64_t N3 = p->N * 3, E = p->E;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    state_vjp_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
+        (int)p->E, (int)p->N, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, q + b0 * qs,
+        xyz + b0 * N3, xyz_cot ? xyz_cot + b0 * N3 : nullptr, rbar ? rbar + b0 * N3 : nullptr,
+        lbar ? lbar + b0 * E : nullptr, fbar ? fbar + b0 * E : nullptr,
+        loads_cot ? loads_cot + b0 * N3 : nullptr, vbar ? vbar + b0 * E * 3 : nullptr,
+        q_bar ? q_bar + b0 * E : nullptr, xyz_bar ? xyz_bar + b0 * N3 : nullptr,
+        loads_bar ? loads_bar + b0 * N3 : nullptr, qs);
+  }
+  return fdm_check_launch("state_vjp");
+}
+
+int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, const double* lam,
+                         double* q_bar, double* loads_bar, double* xs_bar, int64_t batch, int64_t qs,
+                         int accumulate, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  const int64_t work = std::max(p->E, p->N);
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    adjoint_grads_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
+        (int)p->E, (int)p->N, (int)p->Nf, (int)p->Ns, d.edge_nodes, d.node_slot, d.ninc_ptr,
+        d.ninc_edge, d.ninc_other, q + b0 * qs, xyz + b0 * p->N * 3, lam + b0 * p->Nf * 3,
+        q_bar ? q_bar + b0 * p->E : nullptr, loads_bar ? loads_bar + b0 * p->N * 3 : nullptr,
+        xs_bar ? xs_bar + b0 * p->Ns * 3 : nullptr, qs, accumulate);
+  }
+  return fdm_check_launch("adjoint_grads");
+}
+
+int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
+                       int64_t batch, int64_t x0_stride, cudaStream_t st) {
+  const int threads = n >= 1024 ? 1024 : (int)std::max<int64_t>(32, ((n + 31) / 32) * 32);
+  loss_sqdist_kernel<<<(unsigned)batch, threads, 0, st>>>(x, x0, g, loss, n, x0_stride);
+  return fdm_check_launch("loss_sqdist");
+}

@@ -1,0 +1,73 @@
+// Launcher declarations shared between the kernel translation units and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <string>
+
+#include "plan.h"
+
+// gridDim.y carries the design index; chunk batches larger than its limit.
+#define FDM_BATCH_LOOP(batch, b0, nb)                                                          \
+  for (int64_t b0 = 0, nb = 0;                                                                 \
+       b0 < (batch) && ((nb = std::min<int64_t>((int64_t)(batch) - b0, 65535)), true); b0 += nb)
+
+inline int fdm_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fdm_set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return FDM_ERR_CUDA;
+  }
+  return FDM_OK;
+}
+
+#define FDM_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      fdm_set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                      \
+      return FDM_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+// kernels_basic.cu
+int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const double* loads,
+                    double* Kdata, double* rhs, int64_t batch, int64_t qs, int64_t xss, int64_t ls,
+                    cudaStream_t st);
+int launch_positions(const fdm_plan* p, double* xf, double* xs, double* xyz, int64_t batch,
+                     int64_t xss, int transpose, cudaStream_t st);
+int launch_state(const fdm_plan* p, const double* q, const double* xyz, const double* loads,
+                 double* vectors, double* lengths, double* forces, double* residuals,
+                 int64_t batch, int64_t qs, int64_t ls, cudaStream_t st);
+int launch_state_vjp(const fdm_plan* p, const double* q, const double* xyz, const double* xyz_cot,
+                     const double* rbar, const double* lbar, const double* fbar,
+                     const double* loads_cot, const double* vbar, double* q_bar, double* xyz_bar,
+                     double* loads_bar, int64_t batch, int64_t qs, cudaStream_t st);
+int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, const double* lam,
+                         double* q_bar, double* loads_bar, double* xs_bar, int64_t batch, int64_t qs,
+                         int accumulate, cudaStream_t st);
+int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
+                       int64_t batch, int64_t x0_stride, cudaStream_t st);
+
+// spmm.cu
+int launch_spmm(const fdm_plan* p, const double* Kdata, const double* X, double* Y, int64_t batch,
+                cudaStream_t st);
+
+// solver_pcg.cu  (multi-kernel Jacobi-PCG, any size)
+size_t pcg_workspace_bytes(const fdm_plan* p);
+int pcg_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
+              void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
+
+// solver_chol.cu  (batched band Cholesky)
+size_t chol_workspace_bytes(const fdm_plan* p, int64_t batch);
+bool chol_supported(const fdm_plan* p);
+int chol_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
+               void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
+
+// solver_pcg2.cu  (persistent two-level PCG)
+size_t pcg2_workspace_bytes(const fdm_plan* p);
+bool pcg2_supported(const fdm_plan* p);
+int pcg2_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
+               void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
+void pcg2_destroy(fdm_plan* p);

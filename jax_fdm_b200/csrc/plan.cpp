@@ -1,0 +1,350 @@
+// Host-side plan construction: topology -> static index arrays.
+//
+// Reproduces, without scipy, the arrays the reference derives once per topology
+// (reference file:line under src/jax_fdm/equilibrium/structures/):
+//   graphs.py:176-211          signed incidence C (implicit here: edge_nodes + incidence lists)
+//   structures.py:152-188      indices_free / indices_fixed / indices_freefixed
+//   structures.py:248-288      index_array (CSC, sorted indices, explicit 0 on the diagonal)
+//   structures.py:290-314      diag_indices
+//   structures.py:316-350      diags (per free node: incident edge ids, ascending)
+// plus two orderings the reference does not have: a bandwidth-reducing permutation for the
+// batched band Cholesky and a partition of the free nodes into compact aggregates for the
+// two-level PCG.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <queue>
+
+static thread_local std::string g_err;
+void fdm_set_error(const std::string& msg) { g_err = msg; }
+extern "C" const char* fdm_last_error(void) { return g_err.c_str(); }
+
+int fdm_build_topology(fdm_plan& p, const int64_t* edges, int64_t E, int64_t N,
+                       const int64_t* supports) {
+  if (!edges || !supports || E <= 0 || N <= 0) {
+    fdm_set_error("plan: need at least one edge and one node");
+    return E <= 0 ? FDM_ERR_NO_SUPPORT : FDM_ERR_INVALID;
+  }
+  if (E >= (int64_t(1) << 30) || N >= (int64_t(1) << 31) - 1) {
+    fdm_set_error("plan: E must be < 2^30 and N < 2^31-1");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  p.N = N;
+  p.E = E;
+
+  // ---- free / fixed maps (structures.py:152-188) ----
+  p.node_slot.assign(N, 0);
+  p.indices_free.clear();
+  p.indices_fixed.clear();
+  for (int64_t n = 0; n < N; ++n) {
+    if (supports[n] == 0) {
+      p.node_slot[n] = (int32_t)p.indices_free.size();
+      p.indices_free.push_back(n);
+    } else {
+      p.node_slot[n] = -(int32_t)p.indices_fixed.size() - 1;
+      p.indices_fixed.push_back(n);
+    }
+  }
+  p.Nf = (int64_t)p.indices_free.size();
+  p.Ns = (int64_t)p.indices_fixed.size();
+  if (p.Ns == 0) {
+    fdm_set_error("plan: structure has no supports (fdm.py:491-522 asserts at least one)");
+    return FDM_ERR_NO_SUPPORT;
+  }
+  if (p.Nf == 0) {
+    fdm_set_error("plan: structure has no free nodes");
+    return FDM_ERR_INVALID;
+  }
+  // indices_freefixed = argsort(concat(free, fixed)): position of node n in the stacked order
+  p.indices_freefixed.assign(N, 0);
+  for (int64_t i = 0; i < p.Nf; ++i) p.indices_freefixed[p.indices_free[i]] = i;
+  for (int64_t s = 0; s < p.Ns; ++s) p.indices_freefixed[p.indices_fixed[s]] = p.Nf + s;
+  p.free_node.resize(p.Nf);
+  p.fixed_node.resize(p.Ns);
+  for (int64_t i = 0; i < p.Nf; ++i) p.free_node[i] = (int32_t)p.indices_free[i];
+  for (int64_t s = 0; s < p.Ns; ++s) p.fixed_node[s] = (int32_t)p.indices_fixed[s];
+
+  // ---- edges and node incidence lists (graphs.py:176-211 in list form) ----
+  p.edge_nodes.resize(2 * E);
+  p.ninc_ptr.assign(N + 1, 0);
+  for (int64_t e = 0; e < E; ++e) {
+    int64_t t = edges[2 * e], h = edges[2 * e + 1];
+    if (t < 0 || h < 0 || t >= N || h >= N) {
+      fdm_set_error("plan: edge endpoint out of range");
+      return FDM_ERR_INVALID;
+    }
+    if (t == h) {
+      fdm_set_error("plan: self loop (edge " + std::to_string(e) + ")");
+      return FDM_ERR_MULTI_EDGE;
+    }
+    p.edge_nodes[2 * e] = (int32_t)t;
+    p.edge_nodes[2 * e + 1] = (int32_t)h;
+    p.ninc_ptr[t + 1]++;
+    p.ninc_ptr[h + 1]++;
+  }
+  for (int64_t n = 0; n < N; ++n) p.ninc_ptr[n + 1] += p.ninc_ptr[n];
+  p.ninc_edge.resize(2 * E);
+  p.ninc_other.resize(2 * E);
+  {
+    std::vector<int32_t> fill(p.ninc_ptr.begin(), p.ninc_ptr.end() - 1);
+    for (int64_t e = 0; e < E; ++e) {  // ascending e => each list is ascending in edge id
+      int32_t t = p.edge_nodes[2 * e], h = p.edge_nodes[2 * e + 1];
+      p.ninc_edge[fill[t]] = (int32_t)(e << 1);
+      p.ninc_other[fill[t]++] = h;
+      p.ninc_edge[fill[h]] = (int32_t)((e << 1) | 1);
+      p.ninc_other[fill[h]++] = t;
+    }
+  }
+
+  // ---- diags (structures.py:316-350): per free node, incident edges ascending ----
+  p.diags_indptr.assign(p.Nf + 1, 0);
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    int64_t n = p.indices_free[i];
+    p.diags_indptr[i + 1] = p.diags_indptr[i] + (p.ninc_ptr[n + 1] - p.ninc_ptr[n]);
+  }
+  p.dnnz = p.diags_indptr[p.Nf];
+  p.diags_indices.resize(p.dnnz);
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    int64_t n = p.indices_free[i];
+    int32_t o = p.diags_indptr[i];
+    for (int32_t k = p.ninc_ptr[n]; k < p.ninc_ptr[n + 1]; ++k)
+      p.diags_indices[o++] = p.ninc_edge[k] >> 1;
+  }
+
+  // ---- index_array (structures.py:248-288), diag_indices (:290-314) ----
+  // column i (== row i, the pattern is symmetric) holds, sorted by row index, the diagonal with
+  // label 0 and every free neighbour j with label e+1 of the connecting edge.
+  p.index_indptr.assign(p.Nf + 1, 0);
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    int64_t n = p.indices_free[i];
+    int32_t cnt = 1;
+    for (int32_t k = p.ninc_ptr[n]; k < p.ninc_ptr[n + 1]; ++k)
+      if (p.node_slot[p.ninc_other[k]] >= 0) ++cnt;
+    p.index_indptr[i + 1] = p.index_indptr[i] + cnt;
+  }
+  p.nnz = p.index_indptr[p.Nf];
+  if (p.nnz >= (int64_t(1) << 31) - 1) {
+    fdm_set_error("plan: nnz must be < 2^31-1");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  p.index_indices.resize(p.nnz);
+  p.index_data.resize(p.nnz);
+  p.entry_edge.resize(p.nnz);
+  p.diag_indices.resize(p.Nf);
+  p.diag_pos.resize(p.Nf);
+  std::vector<std::pair<int32_t, int32_t>> row;
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    int64_t n = p.indices_free[i];
+    row.clear();
+    row.emplace_back((int32_t)i, -1);
+    for (int32_t k = p.ninc_ptr[n]; k < p.ninc_ptr[n + 1]; ++k) {
+      int32_t j = p.node_slot[p.ninc_other[k]];
+      if (j >= 0) row.emplace_back(j, p.ninc_edge[k] >> 1);
+    }
+    std::sort(row.begin(), row.end());
+    int32_t o = p.index_indptr[i];
+    for (size_t r = 0; r < row.size(); ++r) {
+      if (r > 0 && row[r].first == row[r - 1].first) {
+        fdm_set_error("plan: parallel edges between the same pair of nodes (edge " +
+                      std::to_string(row[r].second) + ")");
+        return FDM_ERR_MULTI_EDGE;
+      }
+      p.index_indices[o + r] = row[r].first;
+      p.entry_edge[o + r] = row[r].second;
+      p.index_data[o + r] = (int64_t)row[r].second + 1;  // e+1 off-diagonal, 0 on the diagonal
+      if (row[r].first == (int32_t)i) {
+        p.diag_indices[i] = o + (int64_t)r;
+        p.diag_pos[i] = o + (int32_t)r;
+      }
+    }
+  }
+  // parallel edges with a support at one end do not show in the free-free pattern; catch them too
+  {
+    std::vector<int32_t> seen;
+    for (int64_t n = 0; n < N; ++n) {
+      seen.assign(p.ninc_other.begin() + p.ninc_ptr[n], p.ninc_other.begin() + p.ninc_ptr[n + 1]);
+      std::sort(seen.begin(), seen.end());
+      if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {
+        fdm_set_error("plan: parallel edges at node " + std::to_string(n));
+        return FDM_ERR_MULTI_EDGE;
+      }
+    }
+  }
+  return FDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// graph helpers on the free-node adjacency (K's pattern without the diagonal)
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Adj {
+  const fdm_plan& p;
+  explicit Adj(const fdm_plan& pl) : p(pl) {}
+  template <class F>
+  void for_each(int32_t i, F f) const {
+    for (int32_t k = p.index_indptr[i]; k < p.index_indptr[i + 1]; ++k) {
+      int32_t j = p.index_indices[k];
+      if (j != i) f(j);
+    }
+  }
+  int32_t degree(int32_t i) const { return p.index_indptr[i + 1] - p.index_indptr[i] - 1; }
+};
+
+// BFS restricted to nodes with mask[v] == tag; returns visitation order, fills level[].
+void bfs(const Adj& g, int32_t start, const std::vector<int32_t>& mask, int32_t tag,
+         std::vector<int32_t>& level, std::vector<int32_t>& order, bool sort_by_degree) {
+  order.clear();
+  order.push_back(start);
+  level[start] = 0;
+  std::vector<int32_t> nb;
+  for (size_t head = 0; head < order.size(); ++head) {
+    int32_t v = order[head];
+    nb.clear();
+    g.for_each(v, [&](int32_t w) {
+      if (mask[w] == tag && level[w] < 0) {
+        level[w] = level[v] + 1;
+        nb.push_back(w);
+      }
+    });
+    if (sort_by_degree)
+      std::sort(nb.begin(), nb.end(), [&](int32_t a, int32_t b) {
+        int32_t da = g.degree(a), db = g.degree(b);
+        return da != db ? da < db : a < b;
+      });
+    order.insert(order.end(), nb.begin(), nb.end());
+  }
+}
+
+// pseudo-peripheral node of the component of `seed` inside {mask == tag}
+int32_t pseudo_peripheral(const Adj& g, int32_t seed, const std::vector<int32_t>& mask, int32_t tag,
+                          std::vector<int32_t>& level, std::vector<int32_t>& order) {
+  int32_t cur = seed, ecc = -1;
+  for (int it = 0; it < 8; ++it) {
+    bfs(g, cur, mask, tag, level, order, false);
+    int32_t last = order.back(), e = level[last];
+    // among the deepest level pick the smallest degree
+    for (auto v : order)
+      if (level[v] == e && g.degree(v) < g.degree(last)) last = v;
+    for (auto v : order) level[v] = -1;
+    if (e <= ecc) break;
+    ecc = e;
+    cur = last;
+  }
+  return cur;
+}
+
+int32_t bandwidth_of(const fdm_plan& p, const std::vector<int32_t>& perm) {
+  int32_t bw = 0;
+  for (int64_t i = 0; i < p.Nf; ++i)
+    for (int32_t k = p.index_indptr[i]; k < p.index_indptr[i + 1]; ++k)
+      bw = std::max(bw, std::abs(perm[i] - perm[p.index_indices[k]]));
+  return bw;
+}
+
+}  // namespace
+
+// Reverse Cuthill-McKee over every component; keep the natural order when it is at least as good.
+void fdm_build_band_order(fdm_plan& p) {
+  const int32_t n = (int32_t)p.Nf;
+  Adj g(p);
+  std::vector<int32_t> mask(n, 0), level(n, -1), order, cm;
+  cm.reserve(n);
+  for (int32_t s = 0; s < n; ++s) {
+    if (mask[s] != 0) continue;
+    int32_t start = pseudo_peripheral(g, s, mask, 0, level, order);
+    bfs(g, start, mask, 0, level, order, true);
+    for (auto v : order) {
+      mask[v] = 1;
+      level[v] = -1;
+      cm.push_back(v);
+    }
+  }
+  std::vector<int32_t> rcm_perm(n), nat(n);
+  for (int32_t k = 0; k < n; ++k) rcm_perm[cm[n - 1 - k]] = k;
+  std::iota(nat.begin(), nat.end(), 0);
+  int32_t bw_nat = bandwidth_of(p, nat), bw_rcm = bandwidth_of(p, rcm_perm);
+  if (bw_rcm < bw_nat) {
+    p.band_perm = rcm_perm;
+    p.hbw = bw_rcm;
+  } else {
+    p.band_perm = nat;
+    p.hbw = bw_nat;
+  }
+  p.band_iperm.resize(n);
+  for (int32_t i = 0; i < n; ++i) p.band_iperm[p.band_perm[i]] = i;
+  // band_kidx[j*(hbw+1) + d]: where A(j+d, j) (band order, lower triangle) sits in K.data; -1 = zero.
+  // Built only when the band is narrow enough to be useful (<= 255); wider => iterative solvers.
+  p.band_kidx.clear();
+  if (p.hbw <= 255 && (int64_t)n * (p.hbw + 1) < (int64_t(1) << 28)) {
+    const int32_t w = p.hbw + 1;
+    p.band_kidx.assign((size_t)n * w, -1);
+    for (int32_t i = 0; i < n; ++i) {
+      int32_t r = p.band_perm[i];
+      for (int32_t k = p.index_indptr[i]; k < p.index_indptr[i + 1]; ++k) {
+        int32_t c = p.band_perm[p.index_indices[k]];
+        if (c <= r) p.band_kidx[(size_t)c * w + (r - c)] = k;
+      }
+    }
+  }
+}
+
+// Recursive graph bisection into `num_parts` aggregates of (almost) equal size.  Each split
+// orders the subset by BFS from a pseudo-peripheral node and cuts the order proportionally, so
+// cuts run across the long direction of the subset and aggregates stay compact.
+void fdm_build_partition(fdm_plan& p, int num_parts) {
+  const int32_t n = (int32_t)p.Nf;
+  num_parts = std::max(1, std::min(num_parts, n));
+  p.num_parts = num_parts;
+  p.part_of_row.assign(n, 0);
+  if (num_parts == 1) return;
+  Adj g(p);
+  std::vector<int32_t> mask(n, 0), level(n, -1), order, comp;
+  struct Job { std::vector<int32_t> nodes; int32_t first_part, parts; };
+  std::vector<Job> stack;
+  {
+    Job j;
+    j.nodes.resize(n);
+    std::iota(j.nodes.begin(), j.nodes.end(), 0);
+    j.first_part = 0;
+    j.parts = num_parts;
+    stack.push_back(std::move(j));
+  }
+  int32_t tag = 0;
+  while (!stack.empty()) {
+    Job job = std::move(stack.back());
+    stack.pop_back();
+    if (job.parts == 1) {
+      for (auto v : job.nodes) p.part_of_row[v] = job.first_part;
+      continue;
+    }
+    ++tag;
+    for (auto v : job.nodes) mask[v] = tag;
+    // BFS order over all components of the subset
+    comp.clear();
+    for (auto s : job.nodes) {
+      if (mask[s] != tag) continue;
+      int32_t start = pseudo_peripheral(g, s, mask, tag, level, order);
+      bfs(g, start, mask, tag, level, order, false);
+      // order within a BFS level by (level, id) is already deterministic
+      for (auto v : order) {
+        mask[v] = -tag;  // visited marker
+        level[v] = -1;
+        comp.push_back(v);
+      }
+    }
+    int32_t pl = job.parts / 2, pr = job.parts - pl;
+    size_t cut = (size_t)((int64_t)comp.size() * pl / job.parts);
+    Job a, b;
+    a.nodes.assign(comp.begin(), comp.begin() + cut);
+    b.nodes.assign(comp.begin() + cut, comp.end());
+    a.first_part = job.first_part;
+    a.parts = pl;
+    b.first_part = job.first_part + pl;
+    b.parts = pr;
+    stack.push_back(std::move(a));
+    stack.push_back(std::move(b));
+  }
+}

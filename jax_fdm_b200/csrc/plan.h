@@ -1,0 +1,62 @@
+// Internal plan layout shared by the host builder (plan.cpp) and the kernel launchers.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/fdm_b200.h"
+
+struct DeviceArrays {
+  // topology, node order
+  int32_t* node_slot = nullptr;    // (N)  >=0: free index, <0: -(fixed index)-1
+  int32_t* edge_nodes = nullptr;   // (E,2) tail, head
+  int32_t* ninc_ptr = nullptr;     // (N+1) incidence lists of every node
+  int32_t* ninc_edge = nullptr;    // (2E)  (edge << 1) | is_head, ascending edge id per node
+  int32_t* ninc_other = nullptr;   // (2E)  other endpoint (node id)
+  int32_t* free_node = nullptr;    // (Nf)  node id of each free index   (= indices_free)
+  int32_t* fixed_node = nullptr;   // (Ns)  node id of each fixed index  (= indices_fixed)
+  // CSR/CSC pattern of K in the reference's order (symmetric pattern)
+  int32_t* rowptr = nullptr;       // (Nf+1) = index_array.indptr
+  int32_t* colidx = nullptr;       // (nnz)  = index_array.indices
+  int32_t* entry_edge = nullptr;   // (nnz)  = index_array.data - 1   (-1 on the diagonal)
+  int32_t* diag_pos = nullptr;     // (Nf)   = diag_indices
+  // band ordering (batched Cholesky)
+  int32_t* band_perm = nullptr;    // (Nf) free index -> band position
+  int32_t* band_iperm = nullptr;   // (Nf) band position -> free index
+  int32_t* band_kidx = nullptr;    // (Nf, hbw+1) column-oriented: [j*(hbw+1)+d] = position in K.data of A(j+d, j), -1 = zero
+  // two-level persistent PCG (solver_pcg_persistent.cu); built lazily by the host
+  void* pcg2 = nullptr;
+};
+
+struct fdm_plan {
+  int64_t N = 0, E = 0, Nf = 0, Ns = 0, nnz = 0, dnnz = 0;
+  int device = -1;
+  bool on_device = false;
+  int sm_count = 0;
+
+  // reference-typed host arrays
+  std::vector<int64_t> indices_free, indices_fixed, indices_freefixed, index_data, diag_indices;
+  std::vector<int32_t> index_indices, index_indptr, diags_indptr, diags_indices;
+
+  // kernel-side host arrays
+  std::vector<int32_t> node_slot, edge_nodes, ninc_ptr, ninc_edge, ninc_other;
+  std::vector<int32_t> free_node, fixed_node, entry_edge, diag_pos;
+
+  // band ordering
+  std::vector<int32_t> band_perm, band_iperm, band_kidx;
+  int32_t hbw = 0;
+
+  // aggregates for the two-level preconditioner
+  std::vector<int32_t> part_of_row;  // (Nf) free index -> aggregate
+  int32_t num_parts = 0;
+
+  DeviceArrays d;
+};
+
+// error text (thread-local), shared by all translation units
+void fdm_set_error(const std::string& msg);
+
+// host builders (plan.cpp)
+int fdm_build_topology(fdm_plan& p, const int64_t* edges, int64_t E, int64_t N, const int64_t* supports);
+void fdm_build_band_order(fdm_plan& p);
+void fdm_build_partition(fdm_plan& p, int num_parts);

@@ -1,0 +1,254 @@
+"""
+Thin wrappers that launch the C-ABI entry points on torch CUDA tensors (device memory and
+streams only -- no torch math on this path).  Every function accepts an optional leading
+batch axis (B designs sharing the structure) and runs on torch's current stream.
+"""
+
+import ctypes as C
+
+import torch
+
+from .. import _lib as L
+
+F64 = torch.float64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _chk(t, name, shape_tail):
+    if t.dtype != F64 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a float64 CUDA tensor, got {t.dtype} on {t.device}")
+    if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise ValueError(f"{name}: trailing shape {tuple(t.shape)} != {tuple(shape_tail)}")
+    return t.contiguous()
+
+
+def _batch_of(t, base_ndim):
+    """(batch, stride_in_elements, is_batched) for a tensor whose unbatched rank is base_ndim."""
+    if t.dim() == base_ndim:
+        return 1, 0, False
+    if t.dim() == base_ndim + 1:
+        per = 1
+        for s in t.shape[1:]:
+            per *= s
+        return int(t.shape[0]), per, True
+    raise ValueError(f"unexpected rank {t.dim()}")
+
+
+def _resolve_batch(*pairs):
+    """pairs of (tensor, base_ndim) -> common batch size B (1 if none batched) and batched flag."""
+    B, batched = 1, False
+    for t, nd in pairs:
+        if t is None:
+            continue
+        b, _, isb = _batch_of(t, nd)
+        if isb:
+            if batched and b != B:
+                raise ValueError("inconsistent batch sizes")
+            B, batched = b, True
+    return B, batched
+
+
+def _stride(t, base_ndim):
+    b, per, isb = _batch_of(t, base_ndim)
+    return per if isb else 0
+
+
+def assemble(structure, q, xyz_fixed=None, loads=None, want_K=True, want_rhs=True):
+    """K1 -> (Kdata (B?,nnz), rhs (B?,Nf,3)); models.py:1064-1079, 828-856, 949-976."""
+    s = structure
+    E, Ns, N, Nf, nnz = s.num_edges, s.num_supports, s.num_nodes, s.num_free, s.nnz
+    q = _chk(q, "q", (E,))
+    if want_rhs:
+        xyz_fixed = _chk(xyz_fixed, "xyz_fixed", (Ns, 3))
+        loads = _chk(loads, "loads", (N, 3))
+    B, batched = _resolve_batch((q, 1), (xyz_fixed if want_rhs else None, 2), (loads if want_rhs else None, 2))
+    lead = (B,) if batched else ()
+    K = torch.empty(lead + (nnz,), dtype=F64, device=q.device) if want_K else None
+    rhs = torch.empty(lead + (Nf, 3), dtype=F64, device=q.device) if want_rhs else None
+    if batched and q.dim() == 1:
+        q = q.expand(B, E).contiguous()
+    L.check(L.lib().fdm_assemble(s.plan, _ptr(q), _ptr(xyz_fixed if want_rhs else None),
+                                 _ptr(loads if want_rhs else None), _ptr(K), _ptr(rhs), B, E,
+                                 _stride(xyz_fixed, 2) if want_rhs else 0,
+                                 _stride(loads, 2) if want_rhs else 0, _stream()))
+    return K, rhs
+
+
+class Workspace:
+    """Caller-owned scratch for fdm_solve, cached per (structure, batch, solver)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, structure, batch, solver, device):
+        need = int(L.lib().fdm_workspace_bytes(structure.plan, batch, solver))
+        if self.buf is None or self.buf.numel() < need or self.buf.device != device:
+            self.buf = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
+        return self.buf, need
+
+
+def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_factor=False,
+          workspace=None, return_info=False, check_every=0):
+    """K2: x = K^{-1} rhs (sparse.py:207-230 / 296).  Kdata (B?,nnz), rhs (B?,Nf,3)."""
+    s = structure
+    Nf, nnz = s.num_free, s.nnz
+    Kdata = _chk(Kdata, "Kdata", (nnz,))
+    rhs = _chk(rhs, "rhs", (Nf, 3))
+    B, batched = _resolve_batch((Kdata, 1), (rhs, 2))
+    if batched:
+        if Kdata.dim() == 1:
+            Kdata = Kdata.expand(B, nnz).contiguous()
+        if rhs.dim() == 2:
+            rhs = rhs.expand(B, Nf, 3).contiguous()
+    x = torch.empty_like(rhs)
+    info = torch.zeros((B, L.INFO_STRIDE), dtype=F64, device=rhs.device)
+    sid = L.SOLVERS[solver] if isinstance(solver, str) else int(solver)
+    ws = workspace if workspace is not None else Workspace()
+    buf, need = ws.get(s, B, sid, rhs.device)
+    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)))
+    L.check(L.lib().fdm_solve(s.plan, _ptr(Kdata), _ptr(rhs), _ptr(x), _ptr(info), _ptr(buf),
+                              buf.numel(), B, C.byref(opts), _stream()))
+    return (x, info) if return_info else x
+
+
+def spmm(structure, Kdata, X):
+    """Y = K X (models.py:1012, sparse.py:301)."""
+    s = structure
+    Kdata = _chk(Kdata, "Kdata", (s.nnz,))
+    X = _chk(X, "X", (s.num_free, 3))
+    B, batched = _resolve_batch((Kdata, 1), (X, 2))
+    if batched:
+        if Kdata.dim() == 1:
+            Kdata = Kdata.expand(B, s.nnz).contiguous()
+        if X.dim() == 2:
+            X = X.expand(B, s.num_free, 3).contiguous()
+    Y = torch.empty_like(X)
+    L.check(L.lib().fdm_spmm(s.plan, _ptr(Kdata), _ptr(X), _ptr(Y), B, _stream()))
+    return Y
+
+
+def positions(structure, x_free, xyz_fixed):
+    """xyz = concat(x_free, xyz_fixed)[indices_freefixed] (models.py:195-220)."""
+    s = structure
+    x_free = _chk(x_free, "x_free", (s.num_free, 3))
+    xyz_fixed = _chk(xyz_fixed, "xyz_fixed", (s.num_supports, 3))
+    B, batched = _resolve_batch((x_free, 2), (xyz_fixed, 2))
+    if batched and x_free.dim() == 2:
+        x_free = x_free.expand(B, s.num_free, 3).contiguous()
+    lead = (B,) if batched else ()
+    xyz = torch.empty(lead + (s.num_nodes, 3), dtype=F64, device=x_free.device)
+    L.check(L.lib().fdm_positions(s.plan, _ptr(x_free), _ptr(xyz_fixed), _ptr(xyz), B,
+                                  _stride(xyz_fixed, 2), 0, _stream()))
+    return xyz
+
+
+def positions_vjp(structure, xyz_bar):
+    """x_free_bar = xyz_bar[indices_free], xyz_fixed_bar = xyz_bar[indices_fixed]."""
+    s = structure
+    xyz_bar = _chk(xyz_bar, "xyz_bar", (s.num_nodes, 3))
+    B, batched = _resolve_batch((xyz_bar, 2))
+    lead = (B,) if batched else ()
+    xf = torch.empty(lead + (s.num_free, 3), dtype=F64, device=xyz_bar.device)
+    xs = torch.empty(lead + (s.num_supports, 3), dtype=F64, device=xyz_bar.device)
+    L.check(L.lib().fdm_positions(s.plan, _ptr(xf), _ptr(xs), _ptr(xyz_bar), B,
+                                  s.num_supports * 3, 1, _stream()))
+    return xf, xs
+
+
+def state(structure, q, xyz, loads):
+    """K4 -> vectors (E,3), lengths (E,1), forces (E,1), residuals (N,3) (models.py:753-794)."""
+    s = structure
+    E, N = s.num_edges, s.num_nodes
+    q = _chk(q, "q", (E,))
+    xyz = _chk(xyz, "xyz", (N, 3))
+    loads = _chk(loads, "loads", (N, 3))
+    B, batched = _resolve_batch((q, 1), (xyz, 2), (loads, 2))
+    if batched and xyz.dim() == 2:
+        xyz = xyz.expand(B, N, 3).contiguous()
+    if batched and q.dim() == 1:
+        q = q.expand(B, E).contiguous()
+    lead = (B,) if batched else ()
+    dev = q.device
+    vectors = torch.empty(lead + (E, 3), dtype=F64, device=dev)
+    lengths = torch.empty(lead + (E, 1), dtype=F64, device=dev)
+    forces = torch.empty(lead + (E, 1), dtype=F64, device=dev)
+    residuals = torch.empty(lead + (N, 3), dtype=F64, device=dev)
+    L.check(L.lib().fdm_state(s.plan, _ptr(q), _ptr(xyz), _ptr(loads), _ptr(vectors), _ptr(lengths),
+                              _ptr(forces), _ptr(residuals), B, E, _stride(loads, 2), _stream()))
+    return vectors, lengths, forces, residuals
+
+
+def state_vjp(structure, q, xyz, xyz_cot=None, residuals_cot=None, lengths_cot=None,
+              forces_cot=None, loads_cot=None, vectors_cot=None):
+    """VJP of `state` -> (q_bar, xyz_bar, loads_bar)."""
+    s = structure
+    E, N = s.num_edges, s.num_nodes
+    q = _chk(q, "q", (E,))
+    xyz = _chk(xyz, "xyz", (N, 3))
+    cots = [xyz_cot, residuals_cot, lengths_cot, forces_cot, loads_cot, vectors_cot]
+    tails = [(N, 3), (N, 3), (E, 1), (E, 1), (N, 3), (E, 3)]
+    cots = [None if c is None else _chk(c, "cot", t) for c, t in zip(cots, tails)]
+    B, batched = _resolve_batch((q, 1), (xyz, 2))
+    if batched and q.dim() == 1:
+        q = q.expand(B, E).contiguous()
+    if batched:
+        cots = [None if c is None else (c if c.dim() == 3 else c.expand((B,) + tuple(c.shape)).contiguous())
+                for c in cots]
+    lead = (B,) if batched else ()
+    dev = q.device
+    q_bar = torch.empty(lead + (E,), dtype=F64, device=dev)
+    xyz_bar = torch.empty(lead + (N, 3), dtype=F64, device=dev)
+    loads_bar = torch.empty(lead + (N, 3), dtype=F64, device=dev)
+    L.check(L.lib().fdm_state_vjp(s.plan, _ptr(q), _ptr(xyz), *[_ptr(c) for c in cots],
+                                  _ptr(q_bar), _ptr(xyz_bar), _ptr(loads_bar), B, E, _stream()))
+    return q_bar, xyz_bar, loads_bar
+
+
+def adjoint_grads(structure, q, xyz, lam, q_bar=None, loads_bar=None, xyz_fixed_bar=None):
+    """
+    K3: gradients of the implicit solve (see include/fdm_b200.h).  When output buffers are
+    given they are accumulated into (direct terms + implicit terms); otherwise fresh.
+    """
+    s = structure
+    E, N, Nf, Ns = s.num_edges, s.num_nodes, s.num_free, s.num_supports
+    q = _chk(q, "q", (E,))
+    xyz = _chk(xyz, "xyz", (N, 3))
+    lam = _chk(lam, "lam", (Nf, 3))
+    B, batched = _resolve_batch((q, 1), (xyz, 2), (lam, 2))
+    if batched and q.dim() == 1:
+        q = q.expand(B, E).contiguous()
+    lead = (B,) if batched else ()
+    dev = q.device
+    acc = q_bar is not None or loads_bar is not None or xyz_fixed_bar is not None
+    if acc:
+        q_bar = torch.zeros(lead + (E,), dtype=F64, device=dev) if q_bar is None else q_bar.contiguous()
+        loads_bar = torch.zeros(lead + (N, 3), dtype=F64, device=dev) if loads_bar is None else loads_bar.contiguous()
+        xyz_fixed_bar = torch.zeros(lead + (Ns, 3), dtype=F64, device=dev) if xyz_fixed_bar is None else xyz_fixed_bar.contiguous()
+    else:
+        q_bar = torch.empty(lead + (E,), dtype=F64, device=dev)
+        loads_bar = torch.empty(lead + (N, 3), dtype=F64, device=dev)
+        xyz_fixed_bar = torch.empty(lead + (Ns, 3), dtype=F64, device=dev)
+    L.check(L.lib().fdm_adjoint_grads(s.plan, _ptr(q), _ptr(xyz), _ptr(lam), _ptr(q_bar),
+                                      _ptr(loads_bar), _ptr(xyz_fixed_bar), B, E, int(acc), _stream()))
+    return q_bar, loads_bar, xyz_fixed_bar
+
+
+def loss_sqdist(x, x0):
+    """loss_b = 0.5 * sum (x - x0)^2 per design, g = x - x0 (benchmark loss)."""
+    x = x.contiguous()
+    batched = x.dim() == 3
+    B = x.shape[0] if batched else 1
+    n = x[0].numel() if batched else x.numel()
+    x0 = x0.contiguous()
+    x0s = n if (x0.dim() == 3) else 0
+    g = torch.empty_like(x)
+    loss = torch.empty((B,), dtype=F64, device=x.device)
+    L.check(L.lib().fdm_loss_sqdist(_ptr(x), _ptr(x0), _ptr(g), _ptr(loss), n, B, x0s, _stream()))
+    return loss, g

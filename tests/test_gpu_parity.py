@@ -1,0 +1,241 @@
+"""
+GPU parity tests: the CUDA path, called through the C ABI (jax_fdm_b200.equilibrium.ops ->
+ctypes -> libfdm_b200.so), against the CPU oracle on the same seeded inputs and against the
+golden fixtures produced by the reference's own code.
+
+Tolerances (BASELINE.json north_star): bit-exact for index maps and for K.data (a gather and an
+ordered sum); <= 1e-10 relative on positions / residual; <= 1e-8 on gradients.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from jax_fdm_b200 import datasets  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["arch10", "readme10", "cablenet12", "pillow30", "olympia", "stuttgart21", "liew_dome", "random40"]
+POS_RTOL = 1e-10
+GRAD_RTOL = 1e-8
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=dev())
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+
+
+@pytest.fixture(scope="module")
+def eq():
+    import jax_fdm_b200.equilibrium as e
+    return e
+
+
+def make(eq, g):
+    s = eq.EquilibriumStructureSparse(g["nodes"], g["edges"], g["supports"], device=0)
+    so = oracle.build_structure(g["nodes"], g["edges"], g["supports"])
+    return s, so
+
+
+def solvers_for(s):
+    out = ["pcg"]
+    if s.num_free * (s.half_bandwidth + 1 + 3) * 8 <= 227 * 1024 - 256:
+        out.append("cholesky")
+    return out
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_assemble_bit_exact_and_rhs(eq, name):
+    g = load(name)
+    s, so = make(eq, g)
+    K, rhs = eq.ops.assemble(s, T(g["q"]), T(g["xyz_fixed"]), T(g["loads"]))
+    assert np.array_equal(N(K), g["ref_K_data"])                      # vs the reference's own output
+    assert np.array_equal(N(K), oracle.stiffness_matrix_sparse(g["q"], so).data)
+    np.testing.assert_allclose(N(rhs), g["ref_P"], rtol=0, atol=1e-13 * max(1, np.abs(g["ref_P"]).max()))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_solve_and_state(eq, name):
+    g = load(name)
+    s, so = make(eq, g)
+    q, xs, p = T(g["q"]), T(g["xyz_fixed"]), T(g["loads"])
+    K, rhs = eq.ops.assemble(s, q, xs, p)
+    for solver in solvers_for(s):
+        x, info = eq.ops.solve(s, K, rhs, solver=solver, tol=1e-13, return_info=True)
+        info = N(info)[0]
+        assert info[0] == 0, (solver, info)
+        assert relerr(N(x), g["ref_x_free"]) <= POS_RTOL, solver
+        # residual of the linear system, relative
+        r = oracle.stiffness_matrix_sparse(g["q"], so) @ N(x) - g["ref_P"]
+        assert np.abs(r).max() <= POS_RTOL * max(np.abs(g["ref_P"]).max(), np.abs(g["ref_K_data"]).max() * np.abs(N(x)).max())
+    xyz = eq.ops.positions(s, x, xs)
+    assert relerr(N(xyz), g["ref_state_xyz"]) <= POS_RTOL
+    v, l, f, r = eq.ops.state(s, q, xyz, p)
+    scale = max(1.0, np.abs(g["ref_state_xyz"]).max())
+    for mine, ref in [(v, "vectors"), (l, "lengths"), (f, "forces"), (r, "residuals")]:
+        refa = g[f"ref_state_{ref}"]
+        assert N(mine).shape == refa.shape
+        np.testing.assert_allclose(N(mine), refa, rtol=1e-9, atol=1e-9 * scale * max(1, np.abs(g["q"]).max()), err_msg=ref)
+
+
+@pytest.mark.parametrize("name", ["readme10", "liew_dome", "random40"])
+def test_spmm(eq, name):
+    g = load(name)
+    s, so = make(eq, g)
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(s.num_free, 3))
+    Y = eq.ops.spmm(s, T(g["ref_K_data"]), T(X))
+    ref = oracle.stiffness_matrix_sparse(g["q"], so) @ X
+    assert relerr(N(Y), ref) <= 1e-14
+
+
+@pytest.mark.parametrize("name", ["cablenet12", "random40", "arch10", "pillow30"])
+def test_state_vjp_and_adjoint_grads(eq, name):
+    g = load(name)
+    s, so = make(eq, g)
+    rng = np.random.default_rng(5)
+    st0, xf = oracle.forward(g["q"], g["xyz_fixed"], g["loads"], so)
+    w = {f: rng.normal(size=st0[f].shape) for f in st0}
+    ref = oracle.forward_adjoint(g["q"], g["xyz_fixed"], g["loads"], so, lambda st, x: w)
+    # K4 reverse
+    qb_o, xb_o, pb_o = oracle.equilibrium_state_vjp(g["q"], st0["xyz"], so, w)
+    qb, xb, pb = eq.ops.state_vjp(s, T(g["q"]), T(st0["xyz"]), xyz_cot=T(w["xyz"]),
+                                  residuals_cot=T(w["residuals"]), lengths_cot=T(w["lengths"]),
+                                  forces_cot=T(w["forces"]), loads_cot=T(w["loads"]),
+                                  vectors_cot=T(w["vectors"]))
+    assert relerr(N(qb), qb_o) <= 1e-12 and relerr(N(xb), xb_o) <= 1e-12 and relerr(N(pb), pb_o) <= 1e-13
+    # positions transpose + adjoint solve + K3, accumulated on top of the direct terms
+    gfree, xsb = eq.ops.positions_vjp(s, xb)
+    K, _ = eq.ops.assemble(s, T(g["q"]), want_rhs=False)
+    lam = eq.ops.solve(s, K, gfree, solver="pcg", tol=1e-14)
+    assert relerr(N(lam), ref["lam"]) <= POS_RTOL
+    qb2, pb2, xsb2 = eq.ops.adjoint_grads(s, T(g["q"]), T(st0["xyz"]), lam, q_bar=qb, loads_bar=pb,
+                                          xyz_fixed_bar=xsb)
+    assert relerr(N(qb2), ref["q_bar"]) <= GRAD_RTOL
+    assert relerr(N(pb2), ref["loads_bar"]) <= GRAD_RTOL
+    assert relerr(N(xsb2), ref["xyz_fixed_bar"]) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("name,fused", [("cablenet12", True), ("cablenet12", False), ("random40", True),
+                                        ("random40", False), ("liew_dome", True), ("pillow30", True)])
+def test_model_autograd_matches_oracle(eq, name, fused):
+    g = load(name)
+    s, so = make(eq, g)
+    rng = np.random.default_rng(11)
+    st0, _ = oracle.forward(g["q"], g["xyz_fixed"], g["loads"], so)
+    w = {f: rng.normal(size=st0[f].shape) for f in st0}
+    ref = oracle.forward_adjoint(g["q"], g["xyz_fixed"], g["loads"], so, lambda st, x: w)
+
+    q = T(g["q"]).requires_grad_(True)
+    xs = T(g["xyz_fixed"]).requires_grad_(True)
+    p = T(g["loads"]).requires_grad_(True)
+    model = eq.EquilibriumModelSparse(tmax=1, solver="pcg", tol=1e-14)
+    if fused:
+        state = model(eq.EquilibriumParametersState(q, xs, eq.LoadState(p)), s)
+    else:  # method-by-method route, as user code composing the reference's methods would
+        xf = model.nodes_free_positions(q, xs, p, s, fused=False)
+        xyz = model.nodes_positions(xf, xs, s)
+        state = model.equilibrium_state(q, xyz, p, s)
+    for f in state._fields:
+        np.testing.assert_allclose(N(getattr(state, f)), ref["state"][f], rtol=1e-9,
+                                   atol=1e-9 * max(1, np.abs(ref["state"]["xyz"]).max()), err_msg=f)
+    loss = sum((T(w[f]) * getattr(state, f)).sum() for f in state._fields)
+    loss.backward()
+    assert relerr(N(q.grad), ref["q_bar"]) <= GRAD_RTOL
+    assert relerr(N(xs.grad), ref["xyz_fixed_bar"]) <= GRAD_RTOL
+    assert relerr(N(p.grad), ref["loads_bar"]) <= GRAD_RTOL
+
+
+def test_batched_pillow_designs(eq):
+    """Config 5 shape at small batch: B designs, one topology, compression (K = -SPD)."""
+    prob = datasets.pillow_problem(30)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    B = 6
+    qb = datasets.pillow_batch_q(prob.edges.shape[0], 0, B)
+    q, xs, p = T(qb), T(prob.xyz_fixed), T(prob.loads)
+    K, rhs = eq.ops.assemble(s, q, xs, p)
+    ws = eq.ops.Workspace()
+    x, info = eq.ops.solve(s, K, rhs, solver="cholesky", workspace=ws, return_info=True)
+    assert np.all(N(info)[:, 0] == 0) and np.all(N(info)[:, 3] == -1.0)
+    x0 = T(prob.xyz0[so.indices_free])
+    loss, gcot = eq.ops.loss_sqdist(x, x0)
+    lam = eq.ops.solve(s, K, gcot, solver="cholesky", workspace=ws, reuse_factor=True)
+    xyz = eq.ops.positions(s, x, xs)
+    qbar, pbar, xsbar = eq.ops.adjoint_grads(s, q, xyz, lam)
+    for b in range(B):
+        w = {"xyz": np.zeros((so.num_nodes, 3))}
+        def cot(st, xf, b=b):
+            c = np.zeros((so.num_nodes, 3))
+            c[so.indices_free] = xf - prob.xyz0[so.indices_free]
+            return {"xyz": c}
+        ref = oracle.forward_adjoint(qb[b], prob.xyz_fixed, prob.loads, so, cot)
+        assert relerr(N(x[b]), ref["x_free"]) <= POS_RTOL
+        assert abs(float(loss[b]) - 0.5 * np.sum((ref["x_free"] - prob.xyz0[so.indices_free]) ** 2)) <= 1e-10 * float(loss[b])
+        assert relerr(N(qbar[b]), ref["q_bar"]) <= GRAD_RTOL
+        assert relerr(N(pbar[b]), ref["loads_bar"]) <= GRAD_RTOL
+        assert relerr(N(xsbar[b]), ref["xyz_fixed_bar"]) <= GRAD_RTOL
+
+
+def test_cablenet200_full_size_properties(eq):
+    """Config 4 at full size: residual, symmetry of the adjoint identity, CPU oracle agreement."""
+    prob = datasets.cablenet_problem(200)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    q, xs, p = T(prob.q), T(prob.xyz_fixed), T(prob.loads)
+    K, rhs = eq.ops.assemble(s, q, xs, p)
+    Ko = oracle.stiffness_matrix_sparse(prob.q, so)
+    assert np.array_equal(N(K), Ko.data)
+    x, info = eq.ops.solve(s, K, rhs, solver="auto", tol=1e-12, return_info=True)
+    assert N(info)[0, 0] == 0
+    r = Ko @ N(x) - N(rhs)
+    assert np.linalg.norm(r) <= POS_RTOL * np.linalg.norm(N(rhs))
+    xo = oracle.sparse_solve(Ko, N(rhs))
+    assert relerr(N(x), xo) <= POS_RTOL
+    # adjoint identity  <g, K^-1 b> == <K^-1 g, b>
+    gcot = T(np.random.default_rng(1).normal(size=(s.num_free, 3)))
+    lam = eq.ops.solve(s, K, gcot, solver="auto", tol=1e-12)
+    lhs = float((gcot * x).sum())
+    rhs_ = float((lam * rhs).sum())
+    assert abs(lhs - rhs_) <= 1e-9 * abs(lhs)
+    # gradient vs oracle
+    xyz = eq.ops.positions(s, x, xs)
+    qbar, pbar, xsbar = eq.ops.adjoint_grads(s, q, xyz, lam)
+    lam_o = oracle.sparse_solve(Ko, N(gcot))
+    full = np.zeros((so.num_nodes, 3)); full[so.indices_free] = lam_o
+    xyz_o = oracle.nodes_positions(xo, prob.xyz_fixed, so)
+    t, h = so.edges_indexed[:, 0], so.edges_indexed[:, 1]
+    qbar_o = -np.sum((full[h] - full[t]) * (xyz_o[h] - xyz_o[t]), axis=1)
+    assert relerr(N(qbar), qbar_o) <= GRAD_RTOL
+
+
+def test_zero_rhs_column_and_errors(eq):
+    g = load("arch10")      # y column of rhs is identically zero
+    s, so = make(eq, g)
+    K, rhs = eq.ops.assemble(s, T(g["q"]), T(g["xyz_fixed"]), T(g["loads"]))
+    assert float(rhs[:, 1].abs().max()) == 0.0
+    x = eq.ops.solve(s, K, rhs, solver="pcg")
+    assert torch.isfinite(x).all() and float(x[:, 1].abs().max()) == 0.0
+    with pytest.raises(TypeError):
+        eq.ops.solve(s, K.float(), rhs)
+    with pytest.raises(ValueError):
+        eq.ops.solve(s, K[:-1], rhs)

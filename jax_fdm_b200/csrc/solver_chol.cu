@@ -128,7 +128,7 @@ size_t smem_bytes(const fdm_plan* p) {
 }  // namespace
 
 bool chol_supported(const fdm_plan* p) {
-  return !p->band_kidx.empty() && smem_bytes(p) <= 227 * 1024 - 256;
+  return !p->band_kidx.empty() && smem_bytes(p) <= 227 * 1024 - 1024;
 }
 
 size_t chol_workspace_bytes(const fdm_plan* p, int64_t batch) {
@@ -146,12 +146,8 @@ int chol_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double
     fdm_set_error("chol_solve: workspace too small");
     return FDM_ERR_WORKSPACE;
   }
-  static thread_local int configured_dev = -1;
   const size_t smem = smem_bytes(p);
-  if (configured_dev != p->device) {
-    FDM_CUDA(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured_dev = p->device;
-  }
+  FDM_CUDA(cudaFuncSetAttribute(chol_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CholArgs A;
   A.n = (int)p->Nf;
   A.W = p->hbw + 1;

@@ -117,8 +117,12 @@ spmm_tma_kernel(int Nf, const int32_t* __restrict__ rowptr, const int32_t* __res
       mbar_wait(&s_bar, phase);
       phase ^= 1;
     }
-    for (int r = row_lo + sub; r < row_hi; r += kSubs) {
-      const int a = s_rp[r] - kbeg, e = s_rp[r + 1] - kbeg;
+    // uniform trip count across the warp (sub-warps of one warp own different rows and the
+    // reduction below uses full-warp shuffles)
+    for (int rb = row_lo; rb < row_hi; rb += kSubs) {
+      const int r = rb + sub;
+      const bool active = r < row_hi;
+      const int a = active ? s_rp[r] - kbeg : 0, e = active ? s_rp[r + 1] - kbeg : 0;
       double ax = 0.0, ay = 0.0, az = 0.0;
       for (int k = a + lane; k < e; k += kLanesPerRow) {
         double v;
@@ -134,7 +138,7 @@ spmm_tma_kernel(int Nf, const int32_t* __restrict__ rowptr, const int32_t* __res
         ay += __shfl_xor_sync(0xffffffffu, ay, o);
         az += __shfl_xor_sync(0xffffffffu, az, o);
       }
-      if (lane == 0) {
+      if (active && lane == 0) {
         double* y = Y + 3 * (int64_t)(r0 + r);
         y[0] = ax; y[1] = ay; y[2] = az;
       }

@@ -58,7 +58,7 @@ def make(eq, g):
 
 def solvers_for(s):
     out = ["pcg"]
-    if s.num_free * (s.half_bandwidth + 1 + 3) * 8 <= 227 * 1024 - 256:
+    if s.num_free * (s.half_bandwidth + 1 + 3) * 8 <= 227 * 1024 - 1024:
         out.append("cholesky")
     return out
 

@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""
+bench.py -- forward+adjoint FDM solves/s (BASELINE.json metric).
+
+Headline workload (config.workload): BASELINE config 5 -- a batch of 4096 synthetic 30x30
+pillow designs (841 free nodes, 1860 edges each, q_b = -2 + 0.1 (U-0.5), seed b), forward
+solve + adjoint + gradients of L_b = 1/2||x_free - x_free0||^2, batch sharded over the N
+ranks (strong scaling: the global batch is fixed), loss all-reduced with NCCL at N > 1.
+A "step" is one pass over the whole batch.  The same JSON line carries `single_mesh`:
+BASELINE config 4 (200x200 cable-net, one design) in ms per forward+adjoint solve.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun ... bench.py --gpus N ...          (N > 1: one rank per GPU)
+
+Timing: W >= 3 warm-up steps; every timed step is bracketed by CUDA events on the launching
+stream; an L2 flush (write of a 256 MiB buffer) runs between timed steps, outside the events;
+barrier + synchronize on both sides of the timed region; max over ranks.
+`--impl reference` times the CPU restatement of the reference path (oracle/: scipy SuperLU
+forward + adjoint, exactly what sparse.py:147-149, 296 run) on the host cores -- jax is not
+installable in this image, so the oracle port is the reference arm.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fwd+adjoint FDM solves/sec"
+UNIT = "solves/s"
+PILLOW_NX = 30
+GLOBAL_BATCH = 4096
+CABLENET_NX = 200
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/fdm_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU restatement of the reference path (oracle) -- cpu_baseline leg and --impl reference
+# --------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(kind, nx):
+    import oracle
+    from jax_fdm_b200 import datasets
+    prob = datasets.pillow_problem(nx) if kind == "pillow" else datasets.cablenet_problem(nx)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    _CPU.update(prob=prob, so=so, oracle=oracle, datasets=datasets,
+                x0=prob.xyz0[so.indices_free])
+
+
+def _cpu_one(b):
+    """forward + adjoint of design b on one core: 2 SuperLU spsolves + closed-form gradients."""
+    o, prob, so = _CPU["oracle"], _CPU["prob"], _CPU["so"]
+    if b is None:
+        q = prob.q
+    else:
+        q = _CPU["datasets"].pillow_batch_q(prob.edges.shape[0], b, 1)[0]
+    x0 = _CPU["x0"]
+
+    def cot(st, xf):
+        c = np.zeros_like(st["xyz"])
+        c[so.indices_free] = xf - x0
+        return {"xyz": c}
+
+    out = o.forward_adjoint(q, prob.xyz_fixed, prob.loads, so, cot)
+    return float(0.5 * np.sum((out["x_free"] - x0) ** 2))
+
+
+def cpu_time_designs(designs, procs):
+    """seconds to run `designs` pillow designs with `procs` worker processes."""
+    if procs <= 1:
+        _cpu_init("pillow", PILLOW_NX)
+        _cpu_one(0)
+        t = time.perf_counter()
+        for b in designs:
+            _cpu_one(b)
+        return time.perf_counter() - t
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs, initializer=_cpu_init, initargs=("pillow", PILLOW_NX)) as pool:
+        pool.map(_cpu_one, range(procs))                       # warm every worker
+        t = time.perf_counter()
+        pool.map(_cpu_one, list(designs), chunksize=max(1, len(designs) // (4 * procs)))
+        return time.perf_counter() - t
+
+
+def cpu_time_cablenet(reps):
+    _cpu_init("cablenet", CABLENET_NX)
+    _cpu_one(None)
+    t = time.perf_counter()
+    for _ in range(reps):
+        _cpu_one(None)
+    return (time.perf_counter() - t) / reps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = len(os.sched_getaffinity(0))
+    sample = min(GLOBAL_BATCH, max(cores * 8, 256))
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt = cpu_time_designs(range(sample), cores)
+        if i >= args.warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    value = sample / per_step
+    ms_cable = cpu_time_cablenet(2) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3 * GLOBAL_BATCH / sample,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{GLOBAL_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} (841 free nodes) fwd+adjoint",
+                   "global_batch": GLOBAL_BATCH, "timed_sample_designs": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {GLOBAL_BATCH} designs per step, one process per core; "
+                                   "numpy/scipy restatement of the reference CPU path (SuperLU fwd + adjoint)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "single_mesh": {"workload": f"cable-net {CABLENET_NX}x{CABLENET_NX}", "ms_per_solve": ms_cable,
+                        "solves_per_s": 1e3 / ms_cable, "cores": 1},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# ours
+# --------------------------------------------------------------------------------------------
+def timed_steps(fn, stream, steps, flush, dist=None):
+    """per-step CUDA-event times (ms) of fn() on `stream`, L2 flushed between steps."""
+    import torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s0, s1 in ev:
+        flush()
+        stream.synchronize()
+        s0.record(stream)
+        fn()
+        s1.record(stream)
+    stream.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from jax_fdm_b200 import datasets
+    from jax_fdm_b200 import _lib as L
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200.pipeline import ForwardAdjoint
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    assert GLOBAL_BATCH % world == 0
+    B = GLOBAL_BATCH // world
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    # ---------------- headline: batched pillow designs ----------------
+    prob = datasets.pillow_problem(PILLOW_NX)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=local)
+    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local)
+    qb = datasets.pillow_batch_q(prob.edges.shape[0], rank * B, B)
+    x0 = prob.xyz0[s.indices_free]
+    pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        with torch.cuda.stream(pipe.stream):
+            flush_buf.fill_(1)
+
+    total = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def step_dev():
+        pipe.step()
+        if world > 1:
+            with torch.cuda.stream(pipe.stream):
+                torch.sum(pipe.loss, dim=0, keepdim=True, out=total)
+                dist.all_reduce(total)
+
+    def step_e2e():
+        pipe()
+        if world > 1:
+            with torch.cuda.stream(pipe.stream):
+                torch.sum(pipe.loss, dim=0, keepdim=True, out=total)
+                dist.all_reduce(total)
+            pipe.stream.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    t_dev = timed_steps(step_dev, pipe.stream, steps, flush)
+    barrier()
+    wall = time.perf_counter() - wall0
+    # end to end: pinned host q in, loss + q_bar out, every step
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t_e2e = []
+    for _ in range(steps):
+        flush()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        step_e2e()
+        torch.cuda.synchronize(dev)
+        t_e2e.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # the dominant kernel alone (forward factor+solve), for the roofline
+    lib = L.lib()
+    import ctypes as C
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def solve_only():
+        L.check(lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws),
+                              pipe.ws.numel(), B, C.byref(pipe.opts_f), C.c_void_p(pipe.stream.cuda_stream)))
+    t_kernel = timed_steps(solve_only, pipe.stream, steps, flush)
+
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sum_dev = reduce_max(sum(t_dev))
+    sum_e2e = reduce_max(sum(t_e2e))
+    ker_ms = reduce_max(float(np.mean(t_kernel)))
+    status_ok = bool((pipe.info_f[:, 0] == 0).all().item() and (pipe.info_a[:, 0] == 0).all().item())
+
+    # ---------------- second workload: one 200x200 cable-net (rank 0 only) ----------------
+    single = None
+    if rank == 0:
+        cprob = datasets.cablenet_problem(CABLENET_NX)
+        cs = eq.EquilibriumStructureSparse(cprob.nodes, cprob.edges, cprob.supports, device=local)
+        cpipe = ForwardAdjoint(cs, batch=1, solver="auto", tol=1e-12, device=local)
+        cpipe.set_inputs(cprob.q[None], cprob.xyz_fixed, cprob.loads, cprob.xyz0[cs.indices_free])
+        for _ in range(3):
+            cpipe.step()
+        cpipe.stream.synchronize()
+        k = max(3, min(steps, 10))
+        tc = timed_steps(cpipe.step, cpipe.stream, k, flush)
+        inf_f, inf_a = cpipe.info_f.cpu().numpy()[0], cpipe.info_a.cpu().numpy()[0]
+        single = {"workload": f"cable-net {CABLENET_NX}x{CABLENET_NX}, 4 corners fixed, q~U[0.5,2], fwd+adjoint",
+                  "ms_per_solve": float(np.mean(tc)), "solves_per_s": 1e3 / float(np.mean(tc)),
+                  "solver": "two-level PCG (persistent)" if cpipe.capturable else "Jacobi-PCG (multi-kernel)",
+                  "iters_fwd": int(inf_f[1]), "iters_adj": int(inf_a[1]),
+                  "relres_fwd": float(inf_f[2]), "relres_adj": float(inf_a[2]),
+                  "status": [int(inf_f[0]), int(inf_a[0])]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, hbm_src = peaks()
+    nnz, nf = s.nnz, s.num_free
+    alg_bytes = (8 * nnz + 24 * nf + 24 * nf) * B            # K.data + rhs in, x out, per launch
+    achieved = alg_bytes / (ker_ms * 1e-3) / 1e9
+    ms_per_step = sum_dev / steps
+    value = GLOBAL_BATCH / (ms_per_step * 1e-3)
+    e2e_value = GLOBAL_BATCH / (sum_e2e / steps * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{GLOBAL_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} (841 free nodes, 1860 edges) "
+                               "forward + adjoint + gradients, batch sharded over ranks",
+                   "global_batch": GLOBAL_BATCH, "per_gpu_batch": B, "solver": "batched band Cholesky",
+                   "l2": "flushed between timed steps (256 MiB write, outside the events)",
+                   "parallelism": f"batch-sharded x{world}" + (", loss all-reduce (NCCL)" if world > 1 else "")},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes * world,
+                "d2h_bytes_per_step": pipe.d2h_bytes * world, "ms_per_step": sum_e2e / steps},
+        "gpu_launches": pipe.launches_per_step * steps,
+        "roofline": {"kernel": "batched band Cholesky factor+solve (forward)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": None, "peak_source": hbm_src, "kernel_ms": ker_ms,
+                     "algorithmic_bytes_per_launch": alg_bytes},
+        "wall_s_timed_region": wall, "solve_status_ok": status_ok,
+        "single_mesh": single,
+    }
+    if world == 1:
+        os.environ.setdefault("OMP_NUM_THREADS", "1")
+        sample = 512
+        dt = cpu_time_designs(range(sample), 1)
+        line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": f"{sample} of {GLOBAL_BATCH} designs, sequential on one core "
+                                          "(scipy SuperLU is single-threaded); numpy/scipy restatement of "
+                                          "sparse.py:147-149,296",
+                                "host_cores_available": len(os.sched_getaffinity(0))}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

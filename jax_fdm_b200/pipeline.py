@@ -1,0 +1,136 @@
+"""
+`ForwardAdjoint`: the device pipeline behind `value_and_grad(loss)(params)` for a batch of B
+designs on one structure -- what `jit(value_and_grad(loss_fn))` is to the reference
+(optimization/optimizers/optimizer.py:365-370), with the quadratic benchmark loss of
+SURVEY.md §8d:  L_b = 1/2 ||x_free_b - x_free0||^2.
+
+All buffers are allocated once; one step is a fixed sequence of this library's kernels
+(K1 assemble -> K2 solve -> positions -> K4 state -> loss/cotangent -> K2 adjoint solve ->
+K3 gradients) launched through the C ABI on one stream, optionally replayed as a CUDA graph.
+`step()` runs on device-resident inputs; `__call__` is the end-to-end call: host (pinned)
+parameters in, host loss and gradients out.
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+F64 = torch.float64
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class ForwardAdjoint:
+    def __init__(self, structure, batch=1, solver="auto", tol=1e-12, max_iters=0, with_state=True,
+                 use_graph=True, device=None):
+        s = self.s = structure
+        self.B = B = int(batch)
+        self.dev = dev = torch.device("cuda", s.device if device is None else device)
+        self.lib = L.lib()
+        self.with_state = with_state
+        E, N, Nf, Ns, nnz = s.num_edges, s.num_nodes, s.num_free, s.num_supports, s.nnz
+        z = lambda *shape: torch.zeros(shape, dtype=F64, device=dev)
+        # inputs
+        self.q, self.xyz_fixed, self.loads, self.x0 = z(B, E), z(Ns, 3), z(N, 3), z(Nf, 3)
+        # forward
+        self.K, self.rhs, self.x, self.xyz = z(B, nnz), z(B, Nf, 3), z(B, Nf, 3), z(B, N, 3)
+        if with_state:
+            self.vectors, self.lengths, self.forces, self.residuals = z(B, E, 3), z(B, E), z(B, E), z(B, N, 3)
+        # reverse
+        self.g, self.lam, self.loss = z(B, Nf, 3), z(B, Nf, 3), z(B)
+        self.q_bar, self.loads_bar, self.xs_bar = z(B, E), z(B, N, 3), z(B, Ns, 3)
+        self.info_f, self.info_a = z(B, L.INFO_STRIDE), z(B, L.INFO_STRIDE)
+        self.loss_sum = z(1)
+        self.solver_id = L.SOLVERS[solver]
+        need = int(self.lib.fdm_workspace_bytes(s.plan, B, self.solver_id))
+        self.ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+        self.opts_f = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, 0)
+        reuse = 1 if (solver == "cholesky" or (solver == "auto" and self._auto_is_cholesky())) else 0
+        self.opts_a = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, reuse)
+        self.capturable = not (solver == "pcg" or (solver == "auto" and self._auto_is_multikernel()))
+        self.graph = None
+        self.use_graph = use_graph and self.capturable
+        self.stream = torch.cuda.Stream(device=dev)
+        # pinned host staging for the end-to-end call
+        self.h_q = torch.zeros((B, E), dtype=F64).pin_memory()
+        self.h_loss = torch.zeros((B,), dtype=F64).pin_memory()
+        self.h_q_bar = torch.zeros((B, E), dtype=F64).pin_memory()
+        self.launches_per_step = 0
+
+    def _auto_is_cholesky(self):
+        s = self.s
+        return s.num_free * (s.half_bandwidth + 4) * 8 <= 227 * 1024 - 1024 and self.B > 1
+
+    def _auto_is_multikernel(self):
+        return not self._auto_is_cholesky() and int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_PCG_PERSISTENT)) == 0
+
+    # ------------------------------------------------------------------------------
+    def set_inputs(self, q, xyz_fixed, loads, x0):
+        T = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64))
+        self.q.copy_(T(q).reshape(self.B, -1))
+        self.xyz_fixed.copy_(T(xyz_fixed))
+        self.loads.copy_(T(loads))
+        self.x0.copy_(T(x0))
+        self.h_q.copy_(T(q).reshape(self.B, -1))
+        torch.cuda.synchronize(self.dev)
+
+    def _launch(self, st):
+        """The kernel sequence of one forward+adjoint step on stream `st` (a raw cudaStream_t)."""
+        s, lib, B = self.s, self.lib, self.B
+        E, N, Nf, Ns = s.num_edges, s.num_nodes, s.num_free, s.num_supports
+        ck = L.check
+        n = 0
+        ck(lib.fdm_assemble(s.plan, _p(self.q), _p(self.xyz_fixed), _p(self.loads), _p(self.K),
+                            _p(self.rhs), B, E, 0, 0, st)); n += 1
+        ck(lib.fdm_solve(s.plan, _p(self.K), _p(self.rhs), _p(self.x), _p(self.info_f), _p(self.ws),
+                         self.ws.numel(), B, C.byref(self.opts_f), st)); n += 1
+        ck(lib.fdm_positions(s.plan, _p(self.x), _p(self.xyz_fixed), _p(self.xyz), B, 0, 0, st)); n += 1
+        if self.with_state:
+            ck(lib.fdm_state(s.plan, _p(self.q), _p(self.xyz), _p(self.loads), _p(self.vectors),
+                             _p(self.lengths), _p(self.forces), _p(self.residuals), B, E, 0, st)); n += 1
+        ck(lib.fdm_loss_sqdist(_p(self.x), _p(self.x0), _p(self.g), _p(self.loss), Nf * 3, B, 0, st)); n += 1
+        ck(lib.fdm_solve(s.plan, _p(self.K), _p(self.g), _p(self.lam), _p(self.info_a), _p(self.ws),
+                         self.ws.numel(), B, C.byref(self.opts_a), st)); n += 1
+        ck(lib.fdm_adjoint_grads(s.plan, _p(self.q), _p(self.xyz), _p(self.lam), _p(self.q_bar),
+                                 _p(self.loads_bar), _p(self.xs_bar), B, E, 0, st)); n += 1
+        self.launches_per_step = n
+        return n
+
+    def step(self):
+        """One forward+adjoint on device-resident inputs, asynchronous on self.stream."""
+        with torch.cuda.stream(self.stream):
+            if self.use_graph:
+                if self.graph is None:
+                    self._launch(C.c_void_p(self.stream.cuda_stream))      # warm-up outside capture
+                    self.stream.synchronize()
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph, stream=self.stream):
+                        self._launch(C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                self.graph.replay()
+            else:
+                self._launch(C.c_void_p(self.stream.cuda_stream))
+
+    def __call__(self, q_host=None):
+        """End to end: pinned host q -> device, step, loss and q_bar back to pinned host."""
+        src = self.h_q if q_host is None else q_host
+        with torch.cuda.stream(self.stream):
+            self.q.copy_(src, non_blocking=True)
+        self.step()
+        with torch.cuda.stream(self.stream):
+            self.h_loss.copy_(self.loss, non_blocking=True)
+            self.h_q_bar.copy_(self.q_bar, non_blocking=True)
+        self.stream.synchronize()
+        return self.h_loss, self.h_q_bar
+
+    @property
+    def h2d_bytes(self):
+        return self.h_q.numel() * 8
+
+    @property
+    def d2h_bytes(self):
+        return (self.h_loss.numel() + self.h_q_bar.numel()) * 8

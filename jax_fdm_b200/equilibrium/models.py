@@ -129,9 +129,8 @@ class _FusedFreePositions(torch.autograd.Function):
     def backward(ctx, g):
         q, xyz_fixed, x, K = ctx.saved_tensors
         s = ctx.structure
-        reuse = ctx.opts.get("solver", "auto") in ("cholesky",) or \
-            (ctx.opts.get("solver", "auto") == "auto" and x.dim() == 3)
-        lam = ops.solve(s, K, g.contiguous(), workspace=ctx.ws, reuse_factor=reuse, **ctx.opts)
+        # same K, same workspace: the Cholesky factor / coarse inverse of the forward solve is reused
+        lam = ops.solve(s, K, g.contiguous(), workspace=ctx.ws, reuse_factor=True, **ctx.opts)
         xyz = ops.positions(s, x, xyz_fixed)
         qbar, pbar, xsbar = ops.adjoint_grads(s, q, xyz, lam)
         return qbar, xsbar, pbar, None, None

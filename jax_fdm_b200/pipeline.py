@@ -50,8 +50,8 @@ class ForwardAdjoint:
         need = int(self.lib.fdm_workspace_bytes(s.plan, B, self.solver_id))
         self.ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
         self.opts_f = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, 0)
-        reuse = 1 if (solver == "cholesky" or (solver == "auto" and self._auto_is_cholesky())) else 0
-        self.opts_a = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, reuse)
+        # the adjoint system has the same K: reuse the Cholesky factor / coarse inverse left in ws
+        self.opts_a = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, 1)
         self.capturable = not (solver == "pcg" or (solver == "auto" and self._auto_is_multikernel()))
         self.graph = None
         self.use_graph = use_graph and self.capturable

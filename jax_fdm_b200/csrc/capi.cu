@@ -1,6 +1,7 @@
 // C ABI (include/fdm_b200.h): plan lifetime, array getters, argument checks, dispatch.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -22,7 +23,7 @@ void free_device(fdm_plan* p) {
   DeviceArrays& d = p->d;
   void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
-                  d.band_iperm, d.band_kidx};
+                  d.band_iperm, d.band_kidx, d.band_rowkidx};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   d = DeviceArrays();
@@ -94,7 +95,9 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
   if (!p) return FDM_ERR_INVALID;
   p->device = device;
   p->sm_count = sms;
-  int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, sms);
+  int parts = sms;
+  if (const char* e = std::getenv("FDM_PCG2_PARTS")) parts = std::max(2, std::min(sms, std::atoi(e)));
+  int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, parts);
   if (rc == FDM_OK) {
     DeviceArrays& d = p->d;
     int (*steps[])(fdm_plan*) = {
@@ -112,6 +115,7 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->band_perm, &q->d.band_perm); },
         [](fdm_plan* q) { return upload(q->band_iperm, &q->d.band_iperm); },
         [](fdm_plan* q) { return upload(q->band_kidx, &q->d.band_kidx); },
+        [](fdm_plan* q) { return upload(q->band_rowkidx, &q->d.band_rowkidx); },
     };
     (void)d;
     for (auto f : steps) {

@@ -65,6 +65,12 @@ bool chol_supported(const fdm_plan* p);
 int chol_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
                void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
 
+// solver_chol_warp.cu  (batched band Cholesky, one warp per design, hbw <= 31)
+bool chol_warp_supported(const fdm_plan* p);
+size_t chol_warp_workspace_bytes(const fdm_plan* p, int64_t batch);
+int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
+                    void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
+
 // solver_pcg2.cu  (persistent two-level PCG)
 size_t pcg2_workspace_bytes(const fdm_plan* p);
 bool pcg2_supported(const fdm_plan* p);

@@ -289,6 +289,22 @@ void fdm_build_band_order(fdm_plan& p) {
       }
     }
   }
+  // band_rowkidx[R*32 + t]: where A(R, R-t) sits in K.data (t = 0..31), for the warp-per-design
+  // Cholesky (hbw <= 31).  Rows are padded to (ceil(n/32)+1)*32 with identity rows:
+  // -1 = structural zero (or column < 0), -2 = one (diagonal of a padding row).
+  p.band_rowkidx.clear();
+  if (p.hbw <= 31) {
+    const int64_t rows = ((int64_t)(n + 31) / 32 + 1) * 32;
+    p.band_rowkidx.assign((size_t)rows * 32, -1);
+    for (int64_t r = n; r < rows; ++r) p.band_rowkidx[(size_t)r * 32] = -2;
+    for (int32_t i = 0; i < n; ++i) {
+      int32_t r = p.band_perm[i];
+      for (int32_t k = p.index_indptr[i]; k < p.index_indptr[i + 1]; ++k) {
+        int32_t c = p.band_perm[p.index_indices[k]];
+        if (c <= r) p.band_rowkidx[(size_t)r * 32 + (r - c)] = k;
+      }
+    }
+  }
 }
 
 // Partition of the free nodes into `num_parts` compact aggregates: farthest-point seeding on

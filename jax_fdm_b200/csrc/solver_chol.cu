@@ -127,17 +127,24 @@ size_t smem_bytes(const fdm_plan* p) {
 
 }  // namespace
 
-bool chol_supported(const fdm_plan* p) {
+static bool chol_cta_supported(const fdm_plan* p) {
   return !p->band_kidx.empty() && smem_bytes(p) <= 227 * 1024 - 1024;
 }
 
+bool chol_supported(const fdm_plan* p) { return chol_warp_supported(p) || chol_cta_supported(p); }
+
 size_t chol_workspace_bytes(const fdm_plan* p, int64_t batch) {
+  if (chol_warp_supported(p)) return chol_warp_workspace_bytes(p, batch);
+  if (!chol_cta_supported(p)) return 0;
   return (size_t)batch * ((size_t)p->Nf * (p->hbw + 1) + 8) * sizeof(double);
 }
 
 int chol_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
                void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st) {
-  if (!chol_supported(p)) {
+  // narrow bands (hbw <= 31): one warp per design, any n.  Wider bands that still fit one
+  // CTA's shared memory: one CTA per design (below).
+  if (chol_warp_supported(p)) return chol_warp_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
+  if (!chol_cta_supported(p)) {
     fdm_set_error("chol_solve: band (n=" + std::to_string(p->Nf) + ", hbw=" + std::to_string(p->hbw) +
                   ") does not fit in shared memory");
     return FDM_ERR_UNSUPPORTED;

@@ -27,10 +27,17 @@
 
 #include "launch.h"
 
+// -DFDM_PCG2_PROFILE: CTA 0 accumulates clock64() per phase and writes the totals after the info
+// record (info must then have room for 10 doubles); off in the shipped build.
+#ifdef FDM_PCG2_PROFILE
+#define PROF(...) __VA_ARGS__
+#else
+#define PROF(...)
+#endif
+
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kWarps = kThreads / 32;
 constexpr int kMaxRowsPerThread = 4;
 constexpr int kVals = 8;               // doubles per CTA record in every exchange
 
@@ -141,45 +148,60 @@ __global__ void __launch_bounds__(1024) pcg2_setup_kernel(Pcg2Args a, size_t xwo
 // ------------------------------------------------------------------------------------------
 // the solver
 // ------------------------------------------------------------------------------------------
-struct Red {
-  double v[kVals];
-};
-
-// block-wide sum of kVals doubles; result valid in threads 0..kVals-1 (thread k holds value k)
-__device__ __forceinline__ double block_reduce_vals(const Red& mine, double* s_red /*[kWarps][kVals]*/) {
+// Block partial sums -> this CTA's record.  Every thread t < nact has stored its V partials in
+// s_part[k*kThreads + t]; warp k < V sums column k in a fixed order and its lane 0 publishes it.
+__device__ __forceinline__ void reduce_publish(const double* s_part, int nact, int V, uint64_t* myrec,
+                                               uint32_t tag) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int k = 0; k < kVals; ++k) {
-    double v = mine.v[k];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_red[warp * kVals + k] = v;
-  }
-  __syncthreads();
-  double out = 0.0;
-  if (threadIdx.x < kVals) {
-    for (int w = 0; w < kWarps; ++w) out += s_red[w * kVals + threadIdx.x];
-  }
-  return out;
-}
-
-// publish this CTA's record (thread k < kVals holds value k) and gather every CTA's record
-__device__ __forceinline__ void exchange(uint64_t* buf, double myval, uint32_t tag, int P,
-                                         double* s_gather /*[P][kVals]*/) {
-  if (threadIdx.x < kVals) ll_store(buf + ((size_t)blockIdx.x * kVals + threadIdx.x) * 2, myval, tag);
-  for (int i = threadIdx.x; i < P * kVals; i += kThreads) s_gather[i] = ll_load(buf + (size_t)i * 2, tag);
-  __syncthreads();
-}
-
-// sum over CTAs of column k (k < 3 handled by warp k), fixed order => identical in every CTA.
-// result broadcast through s_out[k]
-__device__ __forceinline__ void reduce_columns(const double* s_gather, int P, int col0, double* s_out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp < 3) {
+  if (warp < V) {
     double v = 0.0;
-    for (int c = lane; c < P; c += 32) v += s_gather[c * kVals + col0 + warp];
+    for (int i = lane; i < nact; i += 32) v += s_part[warp * kThreads + i];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) s_out[warp] = v;
+    if (lane == 0) ll_store(myrec + warp * 2, v, tag);
   }
+}
+
+// One warp gathers value `col` of every CTA's record (lane l takes CTAs l, l+32, ...), optionally
+// keeps the individual values in shared memory, and returns their sum (same fixed order in every
+// CTA => bitwise identical everywhere).  P <= 32 * kMaxPer.
+constexpr int kMaxPer = 5;
+__device__ __forceinline__ double poll_column(const uint64_t* buf, int V, int col, uint32_t tag, int P,
+                                              double* store, int sstride, int soff) {
+  const int lane = threadIdx.x & 31;
+  double v[kMaxPer];
+  unsigned pending = 0;
+#pragma unroll
+  for (int j = 0; j < kMaxPer; ++j) {
+    v[j] = 0.0;
+    if (lane + 32 * j < P) pending |= 1u << j;
+  }
+  while (pending) {
+    uint64_t w0[kMaxPer], w1[kMaxPer];
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {     // all outstanding loads in flight together
+      if (pending & (1u << j)) {
+        const uint64_t* slot = buf + ((size_t)(lane + 32 * j) * V + col) * 2;
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[j]), "=l"(w1[j]) : "l"(slot));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j) {
+      if ((pending & (1u << j)) && (uint32_t)(w0[j] >> 32) == tag && (uint32_t)(w1[j] >> 32) == tag) {
+        v[j] = __longlong_as_double((long long)((w0[j] & 0xffffffffull) | (w1[j] << 32)));
+        pending &= ~(1u << j);
+      }
+    }
+  }
+  if (store) {
+#pragma unroll
+    for (int j = 0; j < kMaxPer; ++j)
+      if (lane + 32 * j < P) store[(lane + 32 * j) * sstride + soff] = v[j];
+  }
+  double sum = v[0];
+#pragma unroll
+  for (int j = 1; j < kMaxPer; ++j) sum += v[j];
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  return sum;
 }
 
 template <int R>
@@ -190,17 +212,18 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
   const int r0 = d.row_off[c], n = d.row_off[c + 1] - r0;
   const int e0 = d.ent_off[c], ne = d.ent_off[c + 1] - e0;
   const int h0 = d.halo_off[c], nh = d.halo_off[c + 1] - h0;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nact = min(kThreads, ((min(n, kThreads) + 31) >> 5) << 5);   // threads that own rows
 
   // ---- shared memory carve-up (sizes from the host: nmax, emax, hmax) ----
   unsigned char* sp = smem_raw;
   auto take = [&](size_t bytes) { unsigned char* p = sp; sp += (bytes + 15) & ~size_t(15); return p; };
   double* s_val = (double*)take(sizeof(double) * d.emax);
   double* s_p = (double*)take(sizeof(double) * 3 * (d.nmax + d.hmax));   // [rhs][own | halo]
-  double* s_gather = (double*)take(sizeof(double) * P * kVals);
+  double* s_part = (double*)take(sizeof(double) * kVals * kThreads);     // per-thread partials
   double* s_rc = (double*)take(sizeof(double) * P * 3);                  // coarse residual [P][3]
+  double* s_cap = (double*)take(sizeof(double) * P * 3);                 // gathered P^T A p [P][3]
   double* s_ainv = (double*)take(sizeof(double) * P);                    // row c of Ac^-1
-  double* s_red = (double*)take(sizeof(double) * kWarps * kVals);
   double* s_sc = (double*)take(sizeof(double) * 32);                     // scalars
   int32_t* s_rowptr = (int32_t*)take(sizeof(int32_t) * (d.nmax + 1));
   int32_t* s_halo_src = (int32_t*)take(sizeof(int32_t) * d.hmax);
@@ -216,12 +239,13 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
   for (int i = tid; i < nh; i += kThreads) s_halo_src[i] = d.halo_src[h0 + i];
   for (int i = tid; i < P; i += kThreads) s_ainv[i] = a.ainv[(size_t)c * P + i];
   for (int i = tid; i < 3 * pstride; i += kThreads) s_p[i] = 0.0;
+  for (int i = tid; i < 3 * P; i += kThreads) s_cap[i] = 0.0;
 
   double x[R][3], r[R][3], w[R][3], dinv[R], diag[R];
   int expslot[R];
-  Red acc;
+  double acc[kVals];
 #pragma unroll
-  for (int k = 0; k < kVals; ++k) acc.v[k] = 0.0;
+  for (int k = 0; k < kVals; ++k) acc[k] = 0.0;
 #pragma unroll
   for (int j = 0; j < R; ++j) {
     const int row = tid + j * kThreads;
@@ -237,51 +261,57 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         r[j][q] = a.rhs[3 * (size_t)gi + q];
-        acc.v[q] += r[j][q];                 // P^T r (own aggregate)
-        acc.v[3 + q] += r[j][q] * r[j][q];   // <b,b>
+        acc[q] += r[j][q];                 // P^T r (own aggregate)
+        acc[3 + q] += r[j][q] * r[j][q];   // <b,b>
       }
-      acc.v[6] += diag[j] > 0.0 ? 1.0 : 0.0;
-      acc.v[7] += diag[j] < 0.0 ? 1.0 : 0.0;
+      acc[6] += diag[j] > 0.0 ? 1.0 : 0.0;
+      acc[7] += diag[j] < 0.0 ? 1.0 : 0.0;
     }
+  }
+  if (tid < nact) {
+#pragma unroll
+    for (int k = 0; k < kVals; ++k) s_part[k * kThreads + tid] = acc[k];
   }
   __syncthreads();
 
   // ---- exchange S: coarse residual of r0 = b, ||b||^2, sign census ----
-  {
-    const double v = block_reduce_vals(acc, s_red);
-    exchange(a.xS, v, 1u, P, s_gather);
+  reduce_publish(s_part, nact, 8, a.xS + (size_t)c * 8 * 2, 1u);
+  if (warp < 8) {
+    const double sum = poll_column(a.xS, 8, warp, 1u, P, warp < 3 ? s_rc : nullptr, 3, warp);
+    if (lane == 0) s_sc[warp] = sum;          // [3..5] = bb, [6] = npos, [7] = nneg
   }
-  for (int i = tid; i < P * 3; i += kThreads) s_rc[i] = s_gather[(i / 3) * kVals + (i % 3)];
-  reduce_columns(s_gather, P, 3, s_sc + 0);    // bb[3]      -> s_sc[0..2]
-  reduce_columns(s_gather, P, 5, s_sc + 24);   // cols 5,6,7: (bb_z again), npos, nneg -> s_sc[24..26]
   __syncthreads();
-  const double bb0 = s_sc[0], bb1 = s_sc[1], bb2 = s_sc[2];
-  const bool indefinite = s_sc[25] > 0.0 && s_sc[26] > 0.0;
-  const double sign = s_sc[26] > 0.0 && s_sc[25] == 0.0 ? -1.0 : 1.0;
+  const double bb0 = s_sc[3], bb1 = s_sc[4], bb2 = s_sc[5];
+  const bool indefinite = s_sc[6] > 0.0 && s_sc[7] > 0.0;
+  const double sign = s_sc[7] > 0.0 && s_sc[6] == 0.0 ? -1.0 : 1.0;
 
-  double rz_old[3] = {0.0, 0.0, 0.0};
+  double rz_old[3] = {0.0, 0.0, 0.0}, alpha[3] = {0.0, 0.0, 0.0};
   double rr[3] = {bb0, bb1, bb2};
   int it = 0;
+  PROF(long long tB = 0, tA = 0, tH = 0, tC = 0, tM = 0, t0, t1; const long long tstart = clock64();)
   int status = indefinite ? FDM_STATUS_INDEFINITE : FDM_STATUS_OK;
-  bool converged = (bb0 == 0.0 && bb1 == 0.0 && bb2 == 0.0);
+  const bool zero_rhs = (bb0 == 0.0 && bb1 == 0.0 && bb2 == 0.0);
 
-  while (!converged) {
+  while (!zero_rhs) {
     const uint32_t tag = (uint32_t)it + 1u;
-    // ---- coarse solve for the own aggregate: yc = Ainv[c,:] . rc ----
-    {
-      const int warp = tid >> 5, lane = tid & 31;
-      if (warp < 3) {
-        double v = 0.0;
-        for (int j = lane; j < P; j += 32) v += s_ainv[j] * s_rc[j * 3 + warp];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) s_sc[4 + warp] = v;
+    PROF(t0 = clock64();)
+    // ---- coarse residual recurrence + coarse solve for the own aggregate (warps 0..2) ----
+    //      rc -= alpha * (P^T A p);  yc = Ainv[c,:] . rc
+    if (warp < 3) {
+      double v = 0.0;
+      for (int j = lane; j < P; j += 32) {
+        const double nv = s_rc[j * 3 + warp] - alpha[warp] * s_cap[j * 3 + warp];
+        s_rc[j * 3 + warp] = nv;
+        v += s_ainv[j] * nv;
       }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_sc[8 + warp] = v;
     }
     __syncthreads();
-    const double yc[3] = {s_sc[4], s_sc[5], s_sc[6]};
+    const double yc[3] = {s_sc[8], s_sc[9], s_sc[10]};
     // ---- z = D^-1 r + yc ; partial <r,z>, <r,r> ; export boundary z ----
 #pragma unroll
-    for (int k = 0; k < kVals; ++k) acc.v[k] = 0.0;
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int row = tid + j * kThreads;
@@ -290,8 +320,8 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
         for (int q = 0; q < 3; ++q) {
           const double z = dinv[j] * r[j][q] + yc[q];
           w[j][q] = z;
-          acc.v[q] += r[j][q] * z;
-          acc.v[3 + q] += r[j][q] * r[j][q];
+          acc[q] += r[j][q] * z;
+          acc[3 + q] += r[j][q] * r[j][q];
         }
         if (expslot[j] >= 0) {
           uint64_t* e = a.xE + (size_t)expslot[j] * 6;
@@ -299,21 +329,27 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
         }
       }
     }
-    {
-      const double v = block_reduce_vals(acc, s_red);
-      exchange(a.xB, v, tag, P, s_gather);
+    if (tid < nact) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_part[k * kThreads + tid] = acc[k];
     }
-    reduce_columns(s_gather, P, 0, s_sc + 8);    // rz_new -> s_sc[8..10]
-    reduce_columns(s_gather, P, 3, s_sc + 12);   // rr     -> s_sc[12..14]
     __syncthreads();
+    PROF(t1 = clock64(); tC += t1 - t0; t0 = t1;)
+    reduce_publish(s_part, nact, 6, a.xB + (size_t)c * 6 * 2, tag);
+    if (warp < 6) {
+      const double sum = poll_column(a.xB, 6, warp, tag, P, nullptr, 0, 0);
+      if (lane == 0) s_sc[12 + warp] = sum;   // [12..14] = <r,z>, [15..17] = <r,r>
+    }
+    __syncthreads();
+    PROF(t1 = clock64(); tB += t1 - t0; t0 = t1;)
     double rz_new[3], beta[3];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      rz_new[q] = s_sc[8 + q];
-      rr[q] = s_sc[12 + q];
+      rz_new[q] = s_sc[12 + q];
+      rr[q] = s_sc[15 + q];
       beta[q] = (it > 0 && rz_old[q] != 0.0) ? rz_new[q] / rz_old[q] : 0.0;
     }
-    if (rr[0] <= a.tol2 * bb0 && rr[1] <= a.tol2 * bb1 && rr[2] <= a.tol2 * bb2) { converged = true; break; }
+    if (rr[0] <= a.tol2 * bb0 && rr[1] <= a.tol2 * bb1 && rr[2] <= a.tol2 * bb2) break;
     if (!(isfinite(rz_new[0]) && isfinite(rz_new[1]) && isfinite(rz_new[2]))) { status = FDM_STATUS_BREAKDOWN; break; }
     if (it >= a.max_iters) { status = FDM_STATUS_NOT_CONVERGED; break; }
     // ---- p = z + beta p on own rows and halo ----
@@ -332,9 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
       *pp = z + beta[q] * (*pp);
     }
     __syncthreads();
+    PROF(t1 = clock64(); tH += t1 - t0; t0 = t1;)
     // ---- w = A p (own rows), partial <p,Ap>, own coarse sum of Ap ----
 #pragma unroll
-    for (int k = 0; k < kVals; ++k) acc.v[k] = 0.0;
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int row = tid + j * kThreads;
@@ -349,24 +386,30 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
           a0 += v * s_p[cidx]; a1 += v * s_p[pstride + cidx]; a2 += v * s_p[2 * pstride + cidx];
         }
         w[j][0] = a0; w[j][1] = a1; w[j][2] = a2;
-        acc.v[0] += p0 * a0; acc.v[1] += p1 * a1; acc.v[2] += p2 * a2;
-        acc.v[3] += a0; acc.v[4] += a1; acc.v[5] += a2;
+        acc[0] += p0 * a0; acc[1] += p1 * a1; acc[2] += p2 * a2;
+        acc[3] += a0; acc[4] += a1; acc[5] += a2;
       }
     }
-    {
-      const double v = block_reduce_vals(acc, s_red);
-      exchange(a.xA, v, tag, P, s_gather);
+    if (tid < nact) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_part[k * kThreads + tid] = acc[k];
     }
-    reduce_columns(s_gather, P, 0, s_sc + 16);   // pAp -> s_sc[16..18]
     __syncthreads();
-    double alpha[3];
+    PROF(t1 = clock64(); tM += t1 - t0; t0 = t1;)
+    reduce_publish(s_part, nact, 6, a.xA + (size_t)c * 6 * 2, tag);
+    if (warp < 6) {
+      const double sum = poll_column(a.xA, 6, warp, tag, P, warp >= 3 ? s_cap : nullptr, 3, warp - 3);
+      if (lane == 0) s_sc[18 + warp] = sum;   // [18..20] = <p,Ap>
+    }
+    __syncthreads();
+    PROF(t1 = clock64(); tA += t1 - t0; t0 = t1;)
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const double pap = s_sc[16 + q];
+      const double pap = s_sc[18 + q];
       alpha[q] = pap != 0.0 ? rz_new[q] / pap : 0.0;
       rz_old[q] = rz_new[q];
     }
-    // ---- x += alpha p ; r -= alpha A p ; coarse residual recurrence ----
+    // ---- x += alpha p ; r -= alpha A p  (coarse recurrence happens at the top of the loop) ----
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int row = tid + j * kThreads;
@@ -378,11 +421,6 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
         }
       }
     }
-    for (int i = tid; i < P * 3; i += kThreads) {
-      const int cc = i / 3, q = i - 3 * cc;
-      s_rc[i] -= alpha[q] * s_gather[cc * kVals + 3 + q];
-    }
-    __syncthreads();
     ++it;
   }
 
@@ -405,6 +443,9 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
     a.info[FDM_INFO_ITERS] = (double)it;
     a.info[FDM_INFO_RELRES] = rel;
     a.info[FDM_INFO_SIGN] = sign;
+    // phase cycle totals of CTA 0 (diagnostics build only): coarse+z, exchange B, p/halo, SpMV, exchange A, total
+    PROF(a.info[4] = (double)tC; a.info[5] = (double)tB; a.info[6] = (double)tH; a.info[7] = (double)tM;
+         a.info[8] = (double)tA; a.info[9] = (double)(clock64() - tstart);)
   }
 }
 
@@ -429,8 +470,8 @@ int up(Pcg2Host* h, const std::vector<T>& v, T** out) {
 
 size_t pcg2_smem(int P, int nmax, int emax, int hmax) {
   auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
-  return al(8 * (size_t)emax) + al(8 * 3 * (size_t)(nmax + hmax)) + al(8 * (size_t)P * kVals) +
-         al(8 * (size_t)P * 3) + al(8 * (size_t)P) + al(8 * kWarps * kVals) + al(8 * 32) +
+  return al(8 * (size_t)emax) + al(8 * 3 * (size_t)(nmax + hmax)) + al(8 * (size_t)kVals * kThreads) +
+         al(8 * (size_t)P * 3) * 2 + al(8 * (size_t)P) + al(8 * 32) +
          al(4 * (size_t)(nmax + 1)) + al(4 * (size_t)hmax) + al(2 * (size_t)emax);
 }
 
@@ -551,7 +592,7 @@ int pcg2_build(fdm_plan* p) {
 bool shape_ok(const fdm_plan* p) {
   // P CTAs must be co-resident (one per SM) and the worst aggregate must fit shared memory.
   // Estimate before building: rows/part <= kThreads*kMaxRowsPerThread, dense coarse inverse fits one CTA.
-  if (p->num_parts < 2 || p->num_parts > p->sm_count) return false;
+  if (p->num_parts < 2 || p->num_parts > p->sm_count || p->num_parts > 32 * kMaxPer) return false;
   if ((size_t)p->num_parts * p->num_parts * 8 > 200 * 1024) return false;
   return true;
 }

@@ -63,8 +63,10 @@ class ForwardAdjoint:
         self.launches_per_step = 0
 
     def _auto_is_cholesky(self):
-        s = self.s
-        return s.num_free * (s.half_bandwidth + 4) * 8 <= 227 * 1024 - 1024 and self.B > 1
+        # mirrors pick_solver() in csrc/capi.cu: batches go to the band Cholesky when the plan supports it
+        has_chol = int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_CHOLESKY_BATCHED)) > 0
+        has_pcg2 = int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_PCG_PERSISTENT)) > 0
+        return has_chol and (self.B > 1 or not has_pcg2)
 
     def _auto_is_multikernel(self):
         return not self._auto_is_cholesky() and int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_PCG_PERSISTENT)) == 0

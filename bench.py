@@ -4,10 +4,12 @@ bench.py -- forward+adjoint FDM solves/s (BASELINE.json metric).
 
 Headline workload (config.workload): BASELINE config 5 -- a batch of 4096 synthetic 30x30
 pillow designs (841 free nodes, 1860 edges each, q_b = -2 + 0.1 (U-0.5), seed b), forward
-solve + adjoint + gradients of L_b = 1/2||x_free - x_free0||^2, batch sharded over the N
-ranks (strong scaling: the global batch is fixed), loss all-reduced with NCCL at N > 1.
-A "step" is one pass over the whole batch.  The same JSON line carries `single_mesh`:
-BASELINE config 4 (200x200 cable-net, one design) in ms per forward+adjoint solve.
+solve + adjoint + gradients of L_b = 1/2||x_free - x_free0||^2.  Designs are independent, so
+at N GPUs every rank owns 4096 designs (weak scaling, no data-path collective) and the scalar
+loss is all-reduced with NCCL; `config5_fixed_global_batch` additionally reports the fixed
+4096-design batch cut over the N ranks.  A "step" is one pass over a rank's batch.  The same
+JSON line carries `kernels` (every kernel of the step timed alone against the HBM roofline)
+and `single_mesh`: BASELINE config 4 (200x200 cable-net, one design), ms per forward+adjoint.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun ... bench.py --gpus N ...          (N > 1: one rank per GPU)
@@ -36,8 +38,14 @@ if ROOT not in sys.path:
 METRIC = "fwd+adjoint FDM solves/sec"
 UNIT = "solves/s"
 PILLOW_NX = 30
-GLOBAL_BATCH = 4096
+PER_GPU_BATCH = 4096          # designs per GPU (weak scaling); N=1 is BASELINE config 5
+CONFIG5_BATCH = 4096          # BASELINE config 5's fixed global batch (reported beside the headline at N > 1)
+GLOBAL_BATCH = PER_GPU_BATCH  # the CPU arm times a bounded sample of one GPU's share
 CABLENET_NX = 200
+E2E_CHUNKS = 4
+# dram__bytes_read.sum + dram__bytes_write.sum of the forward Cholesky launch (B = 4096), from
+# profiles/r01b_chol_warp_v1_ncu.txt; null until a capture of the current kernel exists
+NCU_TRAFFIC_CHOL_FWD = 2.333e9
 
 
 def peaks():
@@ -165,7 +173,7 @@ def run_reference(args):
         return
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     cores = len(os.sched_getaffinity(0))
-    sample = min(GLOBAL_BATCH, max(cores * 8, 256))
+    sample = min(GLOBAL_BATCH, max(cores * 64, 512))
     times = []
     for i in range(args.warmup + args.steps):
         dt = cpu_time_designs(range(sample), cores)
@@ -177,10 +185,12 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3 * GLOBAL_BATCH / sample,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{GLOBAL_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} (841 free nodes) fwd+adjoint",
-                   "global_batch": GLOBAL_BATCH, "timed_sample_designs": sample},
+        "config": {"workload": f"{GLOBAL_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} designs (841 free nodes, 1860 edges, "
+                               "q_b = -2 + 0.1(U-0.5) seed b): forward solve + adjoint solve + gradients on the host "
+                               "cores (rank 0 only; the reference has no multi-device path)",
+                   "per_gpu_batch": GLOBAL_BATCH, "timed_sample_designs": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} of {GLOBAL_BATCH} designs per step, one process per core; "
                                    "numpy/scipy restatement of the reference CPU path (SuperLU fwd + adjoint)"},
@@ -208,14 +218,57 @@ def timed_steps(fn, stream, steps, flush, dist=None):
     return [a.elapsed_time(b) for a, b in ev]
 
 
+def kernel_table(pipe, s, B, steps, flush, hbm):
+    """Each C-ABI call of the step timed alone (CUDA events on pipe.stream, L2 flushed before every
+    launch): algorithmic bytes per launch, time, achieved GB/s and fraction of the measured HBM peak."""
+    import ctypes as C
+    from jax_fdm_b200 import _lib as L
+    lib = L.lib()
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(pipe.stream.cuda_stream)
+    E, N, Nf, Ns, nnz = s.num_edges, s.num_nodes, s.num_free, s.num_supports, s.nnz
+    fac = 8 * 1024 * ((Nf + 31) // 32)                       # factor columns, 32 doubles each, rows padded to 32
+    Y = pipe.rhs.clone()
+    calls = [
+        ("assemble (K1)", 8 * E + 8 * nnz + 24 * Nf,
+         lambda: lib.fdm_assemble(s.plan, P(pipe.q), P(pipe.xyz_fixed), P(pipe.loads), P(pipe.K), P(pipe.rhs), B, E, 0, 0, st)),
+        ("band Cholesky factor+solve (K2b, forward)", 8 * nnz + 48 * Nf + fac,
+         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
+                               C.byref(pipe.opts_f), st)),
+        ("positions", 24 * Nf + 24 * N,
+         lambda: lib.fdm_positions(s.plan, P(pipe.x), P(pipe.xyz_fixed), P(pipe.xyz), B, 0, 0, st)),
+        ("state (K4)", 8 * E + 24 * N + 40 * E + 24 * N,
+         lambda: lib.fdm_state(s.plan, P(pipe.q), P(pipe.xyz), P(pipe.loads), P(pipe.vectors), P(pipe.lengths),
+                               P(pipe.forces), P(pipe.residuals), B, E, 0, st)),
+        ("loss + cotangent", 48 * Nf + 8,
+         lambda: lib.fdm_loss_sqdist(P(pipe.x), P(pipe.x0), P(pipe.g), P(pipe.loss), Nf * 3, B, 0, st)),
+        ("band Cholesky solve with stored factor (K3 adjoint solve)", fac + 48 * Nf,
+         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.g), P(pipe.lam), P(pipe.info_a), P(pipe.ws), pipe.ws.numel(), B,
+                               C.byref(pipe.opts_a), st)),
+        ("adjoint gradients (K3)", 8 * E + 24 * N + 24 * Nf + 8 * E + 24 * N + 24 * Ns,
+         lambda: lib.fdm_adjoint_grads(s.plan, P(pipe.q), P(pipe.xyz), P(pipe.lam), P(pipe.q_bar), P(pipe.loads_bar),
+                                       P(pipe.xs_bar), B, E, 0, st)),
+        ("SpMM K X (3 rhs)", 8 * nnz + 48 * Nf,
+         lambda: lib.fdm_spmm(s.plan, P(pipe.K), P(pipe.x), P(Y), B, st)),
+    ]
+    out = []
+    for name, per_design, fn in calls:
+        ts = timed_steps(lambda: L.check(fn()), pipe.stream, steps, flush)
+        ms = float(np.mean(ts))
+        gbs = per_design * B / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "ms": ms, "algorithmic_bytes_per_launch": per_design * B,
+                    "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / hbm})
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from jax_fdm_b200 import datasets
-    from jax_fdm_b200 import _lib as L
     import jax_fdm_b200.equilibrium as eq
-    from jax_fdm_b200.pipeline import ForwardAdjoint
+    from jax_fdm_b200.distributed import shard_range, total_loss
+    from jax_fdm_b200.pipeline import ChunkedForwardAdjoint, ForwardAdjoint
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,17 +279,20 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    assert GLOBAL_BATCH % world == 0
-    B = GLOBAL_BATCH // world
+    B = PER_GPU_BATCH                                    # weak scaling: every rank owns 4096 designs
     steps, warmup = args.steps, max(3, args.warmup)
+    hbm, hbm_src = peaks()
 
     # ---------------- headline: batched pillow designs ----------------
     prob = datasets.pillow_problem(PILLOW_NX)
     s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=local)
-    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local)
-    qb = datasets.pillow_batch_q(prob.edges.shape[0], rank * B, B)
+    lo, hi = shard_range(B * world, rank, world)
+    qb = datasets.pillow_batch_q(prob.edges.shape[0], lo, hi - lo)
     x0 = prob.xyz0[s.indices_free]
+    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local)
     pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+    e2e_pipe = ChunkedForwardAdjoint(s, B, chunks=E2E_CHUNKS, solver="cholesky", device=local)
+    e2e_pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def flush():
@@ -245,19 +301,20 @@ def run_ours(args):
 
     total = torch.zeros(1, dtype=torch.float64, device=dev)
 
+    def reduce_loss(p):
+        if world > 1:
+            with torch.cuda.stream(p.stream):
+                total_loss(p.loss, out=total)             # local sum + one 8-byte NCCL all-reduce
+
     def step_dev():
         pipe.step()
-        if world > 1:
-            with torch.cuda.stream(pipe.stream):
-                torch.sum(pipe.loss, dim=0, keepdim=True, out=total)
-                dist.all_reduce(total)
+        reduce_loss(pipe)
 
     def step_e2e():
-        pipe()
+        e2e_pipe()
         if world > 1:
             with torch.cuda.stream(pipe.stream):
-                torch.sum(pipe.loss, dim=0, keepdim=True, out=total)
-                dist.all_reduce(total)
+                total_loss(e2e_pipe.loss, out=total)
             pipe.stream.synchronize()
 
     def barrier():
@@ -278,7 +335,7 @@ def run_ours(args):
     barrier()
     wall = time.perf_counter() - wall0
     # end to end: pinned host q in, loss + q_bar out, every step
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
     barrier()
     t_e2e = []
@@ -292,16 +349,6 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # the dominant kernel alone (forward factor+solve), for the roofline
-    lib = L.lib()
-    import ctypes as C
-    P = lambda t: C.c_void_p(t.data_ptr())
-
-    def solve_only():
-        L.check(lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws),
-                              pipe.ws.numel(), B, C.byref(pipe.opts_f), C.c_void_p(pipe.stream.cuda_stream)))
-    t_kernel = timed_steps(solve_only, pipe.stream, steps, flush)
-
     def reduce_max(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
@@ -310,8 +357,31 @@ def run_ours(args):
 
     sum_dev = reduce_max(sum(t_dev))
     sum_e2e = reduce_max(sum(t_e2e))
-    ker_ms = reduce_max(float(np.mean(t_kernel)))
     status_ok = bool((pipe.info_f[:, 0] == 0).all().item() and (pipe.info_a[:, 0] == 0).all().item())
+
+    # every kernel of the step alone, for the roofline table (rank 0's numbers are reported)
+    kernels = kernel_table(pipe, s, B, max(3, min(steps, 10)), flush, hbm)
+
+    # BASELINE config 5 exactly (fixed global batch 4096 cut over the ranks), strong scaling, N > 1 only
+    fixed = None
+    if world > 1:
+        lo5, hi5 = shard_range(CONFIG5_BATCH, rank, world)
+        p5 = ForwardAdjoint(s, batch=hi5 - lo5, solver="cholesky", device=local)
+        p5.set_inputs(datasets.pillow_batch_q(prob.edges.shape[0], lo5, hi5 - lo5), prob.xyz_fixed, prob.loads, x0)
+
+        def step5():
+            p5.step()
+            reduce_loss(p5)
+        for _ in range(warmup):
+            step5()
+        barrier()
+
+        def flush5():
+            with torch.cuda.stream(p5.stream):
+                flush_buf.fill_(1)
+        t5 = reduce_max(sum(timed_steps(step5, p5.stream, steps, flush5)))
+        fixed = {"workload": f"{CONFIG5_BATCH} designs in total, {hi5 - lo5} per GPU", "scaling": "strong",
+                 "ms_per_step": t5 / steps, "value": CONFIG5_BATCH / (t5 / steps * 1e-3), "unit": UNIT}
 
     # ---------------- second workload: one 200x200 cable-net (rank 0 only) ----------------
     single = None
@@ -324,7 +394,11 @@ def run_ours(args):
             cpipe.step()
         cpipe.stream.synchronize()
         k = max(3, min(steps, 10))
-        tc = timed_steps(cpipe.step, cpipe.stream, k, flush)
+
+        def cflush():
+            with torch.cuda.stream(cpipe.stream):
+                flush_buf.fill_(1)
+        tc = timed_steps(cpipe.step, cpipe.stream, k, cflush)
         inf_f, inf_a = cpipe.info_f.cpu().numpy()[0], cpipe.info_a.cpu().numpy()[0]
         single = {"workload": f"cable-net {CABLENET_NX}x{CABLENET_NX}, 4 corners fixed, q~U[0.5,2], fwd+adjoint",
                   "ms_per_solve": float(np.mean(tc)), "solves_per_s": 1e3 / float(np.mean(tc)),
@@ -338,43 +412,47 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    hbm, hbm_src = peaks()
-    nnz, nf = s.nnz, s.num_free
-    alg_bytes = (8 * nnz + 24 * nf + 24 * nf) * B            # K.data + rhs in, x out, per launch
-    achieved = alg_bytes / (ker_ms * 1e-3) / 1e9
+    dom = kernels[1]
     ms_per_step = sum_dev / steps
-    value = GLOBAL_BATCH / (ms_per_step * 1e-3)
-    e2e_value = GLOBAL_BATCH / (sum_e2e / steps * 1e-3)
+    value = B * world / (ms_per_step * 1e-3)
+    e2e_value = B * world / (sum_e2e / steps * 1e-3)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{GLOBAL_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} (841 free nodes, 1860 edges) "
-                               "forward + adjoint + gradients, batch sharded over ranks",
-                   "global_batch": GLOBAL_BATCH, "per_gpu_batch": B, "solver": "batched band Cholesky",
+        "config": {"workload": f"{B} x pillow {PILLOW_NX}x{PILLOW_NX} designs per GPU (841 free nodes, 1860 edges, "
+                               "q_b = -2 + 0.1(U-0.5) seed b): forward solve + state + loss + adjoint solve + gradients; "
+                               "BASELINE config 5 at N=1",
+                   "per_gpu_batch": B, "global_batch": B * world, "solver": "batched band Cholesky, one warp per design",
                    "l2": "flushed between timed steps (256 MiB write, outside the events)",
-                   "parallelism": f"batch-sharded x{world}" + (", loss all-reduce (NCCL)" if world > 1 else "")},
+                   "parallelism": f"designs sharded x{world}, no data-path collective"
+                                  + (", 8-byte loss all-reduce (NCCL) per step" if world > 1 else "")},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes * world,
-                "d2h_bytes_per_step": pipe.d2h_bytes * world, "ms_per_step": sum_e2e / steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_pipe.h2d_bytes * world,
+                "d2h_bytes_per_step": e2e_pipe.d2h_bytes * world, "ms_per_step": sum_e2e / steps,
+                "how": f"pinned host q -> device, step, loss + q_bar -> pinned host, {E2E_CHUNKS} chunks on "
+                       "separate streams so copies overlap kernels; host wall clock, synchronised both sides"},
         "gpu_launches": pipe.launches_per_step * steps,
-        "roofline": {"kernel": "batched band Cholesky factor+solve (forward)", "bound": "hbm",
-                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": None, "peak_source": hbm_src, "kernel_ms": ker_ms,
-                     "algorithmic_bytes_per_launch": alg_bytes},
+        "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm,
+                     "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm, "traffic": NCU_TRAFFIC_CHOL_FWD,
+                     "peak_source": hbm_src, "kernel_ms": dom["ms"],
+                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                     "share_of_step": dom["ms"] / ms_per_step},
+        "kernels": kernels,
         "wall_s_timed_region": wall, "solve_status_ok": status_ok,
         "single_mesh": single,
     }
+    if fixed:
+        line["config5_fixed_global_batch"] = fixed
     if world == 1:
         os.environ.setdefault("OMP_NUM_THREADS", "1")
-        sample = 512
-        dt = cpu_time_designs(range(sample), 1)
-        line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": f"{sample} of {GLOBAL_BATCH} designs, sequential on one core "
-                                          "(scipy SuperLU is single-threaded); numpy/scipy restatement of "
-                                          "sparse.py:147-149,296",
-                                "host_cores_available": len(os.sched_getaffinity(0))}
+        sample = 2048
+        cores = len(os.sched_getaffinity(0))
+        dt = cpu_time_designs(range(sample), cores)
+        line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{sample} of {B} designs, one process per core (scipy SuperLU is "
+                                          "single-threaded); numpy/scipy restatement of sparse.py:147-149,296"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

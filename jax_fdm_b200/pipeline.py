@@ -119,6 +119,12 @@ class ForwardAdjoint:
 
     def __call__(self, q_host=None):
         """End to end: pinned host q -> device, step, loss and q_bar back to pinned host."""
+        self.enqueue_e2e(q_host)
+        self.stream.synchronize()
+        return self.h_loss, self.h_q_bar
+
+    def enqueue_e2e(self, q_host=None):
+        """Asynchronous end-to-end pass on self.stream: H2D q, step, D2H loss and q_bar (no sync)."""
         src = self.h_q if q_host is None else q_host
         with torch.cuda.stream(self.stream):
             self.q.copy_(src, non_blocking=True)
@@ -126,8 +132,6 @@ class ForwardAdjoint:
         with torch.cuda.stream(self.stream):
             self.h_loss.copy_(self.loss, non_blocking=True)
             self.h_q_bar.copy_(self.q_bar, non_blocking=True)
-        self.stream.synchronize()
-        return self.h_loss, self.h_q_bar
 
     @property
     def h2d_bytes(self):
@@ -136,3 +140,52 @@ class ForwardAdjoint:
     @property
     def d2h_bytes(self):
         return (self.h_loss.numel() + self.h_q_bar.numel()) * 8
+
+
+class ChunkedForwardAdjoint:
+    """
+    The end-to-end call for large batches: the batch is cut into `chunks` contiguous slices,
+    each with its own ForwardAdjoint (own stream, buffers, CUDA graph), so the host->device copy
+    of one slice, the kernels of another and the device->host copy of a third overlap on the
+    copy engines and the SMs.  Results land in per-chunk pinned buffers; `__call__` returns
+    them concatenated (views of one pinned allocation each).
+    """
+
+    def __init__(self, structure, batch, chunks=4, **kw):
+        chunks = max(1, min(int(chunks), int(batch)))
+        sizes = [batch // chunks + (1 if i < batch % chunks else 0) for i in range(chunks)]
+        self.offsets = [sum(sizes[:i]) for i in range(chunks)]
+        self.parts = [ForwardAdjoint(structure, batch=b, **kw) for b in sizes]
+        self.B = int(batch)
+
+    def set_inputs(self, q, xyz_fixed, loads, x0):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(self.B, -1)
+        for off, part in zip(self.offsets, self.parts):
+            part.set_inputs(q[off:off + part.B], xyz_fixed, loads, x0)
+
+    def __call__(self, q_host=None):
+        for off, part in zip(self.offsets, self.parts):
+            part.enqueue_e2e(None if q_host is None else q_host[off:off + part.B])
+        for part in self.parts:
+            part.stream.synchronize()
+        return [p.h_loss for p in self.parts], [p.h_q_bar for p in self.parts]
+
+    def synchronize(self):
+        for part in self.parts:
+            part.stream.synchronize()
+
+    @property
+    def loss(self):
+        return torch.cat([p.loss for p in self.parts])
+
+    @property
+    def h2d_bytes(self):
+        return sum(p.h2d_bytes for p in self.parts)
+
+    @property
+    def d2h_bytes(self):
+        return sum(p.d2h_bytes for p in self.parts)
+
+    @property
+    def launches_per_step(self):
+        return sum(p.launches_per_step for p in self.parts)

@@ -407,10 +407,11 @@ def run_ours(args):
                   "relres_fwd": float(inf_f[2]), "relres_adj": float(inf_a[2]),
                   "status": [int(inf_f[0]), int(inf_a[0])]}
 
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     dom = kernels[1]
     ms_per_step = sum_dev / steps
@@ -453,9 +454,22 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{sample} of {B} designs, one process per core (scipy SuperLU is "
                                           "single-threaded); numpy/scipy restatement of sparse.py:147-149,296"}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
+class _StdoutToStderr:
+    """Library banners (NCCL prints its version on stdout) must not pollute the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -468,7 +482,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        with _StdoutToStderr():
+            line = run_ours(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@ void free_device(fdm_plan* p) {
   DeviceArrays& d = p->d;
   void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
-                  d.band_iperm, d.band_kidx, d.band_rowkidx};
+                  d.band_iperm, d.band_kidx, d.band_rowkidx, d.diags_ptr, d.diags_idx, d.sup_mask};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   d = DeviceArrays();
@@ -116,6 +116,9 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->band_iperm, &q->d.band_iperm); },
         [](fdm_plan* q) { return upload(q->band_kidx, &q->d.band_kidx); },
         [](fdm_plan* q) { return upload(q->band_rowkidx, &q->d.band_rowkidx); },
+        [](fdm_plan* q) { return upload(q->diags_indptr, &q->d.diags_ptr); },
+        [](fdm_plan* q) { return upload(q->diags_indices, &q->d.diags_idx); },
+        [](fdm_plan* q) { return upload(q->sup_mask, &q->d.sup_mask); },
     };
     (void)d;
     for (auto f : steps) {

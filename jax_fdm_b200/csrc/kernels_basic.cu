@@ -22,52 +22,104 @@ __device__ __forceinline__ void st3(double* p, int64_t row, double3 v) {
 
 // ---------------------------------------------------------------------------------------
 // K1: K.data and rhs.   models.py:1064-1079, 828-856, 949-976
-//   thread t < nnz : off-diagonal entry t        K.data[t] = -q[entry_edge[t]]
-//   thread t < Nf  : row t                        K.data[diag_pos[t]] = sum_inc q_e   (ascending e)
-//                                                 rhs[t] = loads[node] + sum_{e to support s} q_e xyz_fixed[s]
+// One CTA owns kAsmRows consecutive free rows, i.e. ONE CONTIGUOUS slice [k0, k1) of K.data:
+//   phase 1  thread per stored entry  : s_val[k] = -q[entry_edge[k]]            (off-diagonal)
+//   phase 2  thread per row           : s_val[diag] = sum_inc q_e  over `diags` (ascending edge id, the
+//                                       order of the reference's BCSR product, structures.py:316-350)
+//                                       s_rhs[row] = loads[node] (+ sum_{e to support s} q_e x_s for the
+//                                       rows flagged in sup_mask: they walk the node's incidence list)
+//   phase 3  coalesced stores of the staged slice of K.data and of rhs (every line written once, full width)
+// Index streams (entry_edge, diags, rowptr, free_node) are read once, coalesced; q is gathered.
 // Algorithmic bytes per design: 16E + 12nnz + 52Nf + 24Ns.
 // ---------------------------------------------------------------------------------------
+constexpr int kAsmRows = 256;
+constexpr int kAsmCap = 2560;   // staged entries per tile (20 KB); tiles with more fall back to direct stores
+
 __global__ void __launch_bounds__(kThreads)
 assemble_kernel(int nnz, int Nf, int N, int Ns,
-                const int32_t* __restrict__ entry_edge, const int32_t* __restrict__ diag_pos,
-                const int32_t* __restrict__ free_node, const int32_t* __restrict__ node_slot,
+                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ entry_edge,
+                const int32_t* __restrict__ diag_pos, const int32_t* __restrict__ free_node,
+                const int32_t* __restrict__ diags_ptr, const int32_t* __restrict__ diags_idx,
+                const uint32_t* __restrict__ sup_mask, const int32_t* __restrict__ node_slot,
                 const int32_t* __restrict__ ninc_ptr, const int32_t* __restrict__ ninc_edge,
                 const int32_t* __restrict__ ninc_other,
                 const double* __restrict__ q, const double* __restrict__ xs,
                 const double* __restrict__ loads, double* __restrict__ Kdata,
                 double* __restrict__ rhs, int64_t q_stride, int64_t xs_stride, int64_t loads_stride) {
+  __shared__ __align__(16) double s_val[kAsmCap];
+  __shared__ __align__(16) double s_rhs[kAsmRows * 3];
   const int64_t b = blockIdx.y;
-  const int t = blockIdx.x * kThreads + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * kAsmRows, r1 = min(Nf, r0 + kAsmRows);
+  const int k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1), cnt = k1 - k0;
+  const bool staged = cnt <= kAsmCap;
   q += b * q_stride;
-  if (Kdata) {
-    Kdata += b * (int64_t)nnz;
-    if (t < nnz) {
-      const int e = __ldg(entry_edge + t);
-      if (e >= 0) Kdata[t] = -__ldg(q + e);
-    }
-  }
-  if (t < Nf) {
-    const int n = __ldg(free_node + t);
-    const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
-    double diag = 0.0;
-    double3 acc = make_double3(0.0, 0.0, 0.0);
-    const double* xsb = xs ? xs + b * xs_stride : nullptr;
-    for (int k = k0; k < k1; ++k) {
-      const double qe = __ldg(q + (__ldg(ninc_edge + k) >> 1));
-      diag += qe;
-      if (rhs) {
-        const int slot = __ldg(node_slot + __ldg(ninc_other + k));
-        if (slot < 0) {
-          const double3 x = ld3(xsb, -slot - 1);
-          acc.x += qe * x.x; acc.y += qe * x.y; acc.z += qe * x.z;
+  double* Kd = Kdata ? Kdata + b * (int64_t)nnz : nullptr;
+  if (Kd) {
+    // four entries per trip so that the index loads, then the q gathers, are in flight together
+    for (int kb = tid; kb < cnt; kb += 4 * kThreads) {
+      int e[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kb + u * kThreads;
+        e[u] = k < cnt ? __ldg(entry_edge + k0 + k) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = e[u] >= 0 ? -__ldg(q + e[u]) : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kb + u * kThreads;
+        if (e[u] >= 0) {
+          if (staged) s_val[k] = v[u]; else Kd[k0 + k] = v[u];
         }
       }
     }
-    if (Kdata) Kdata[__ldg(diag_pos + t)] = diag;
-    if (rhs) {
-      const double3 p = ld3(loads + b * loads_stride, n);
-      st3(rhs + b * (int64_t)Nf * 3, t, make_double3(p.x + acc.x, p.y + acc.y, p.z + acc.z));
+  }
+  const int t = r0 + tid;
+  if (t < r1) {
+    if (Kd) {
+      double diag = 0.0;
+      const int d0 = __ldg(diags_ptr + t), d1 = __ldg(diags_ptr + t + 1);
+      for (int k = d0; k < d1; k += 4) {   // same ascending order of additions, gathers issued four at a time
+        int ed[4];
+        double qv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) ed[u] = k + u < d1 ? __ldg(diags_idx + k + u) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qv[u] = ed[u] >= 0 ? __ldg(q + ed[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (ed[u] >= 0) diag += qv[u];
+      }
+      const int dp = __ldg(diag_pos + t);
+      if (staged) s_val[dp - k0] = diag; else Kd[dp] = diag;
     }
+    if (rhs) {
+      const int n = __ldg(free_node + t);
+      double3 acc = make_double3(0.0, 0.0, 0.0);
+      if ((__ldg(sup_mask + (t >> 5)) >> (t & 31)) & 1u) {
+        const double* xsb = xs + b * xs_stride;
+        const int i0 = __ldg(ninc_ptr + n), i1 = __ldg(ninc_ptr + n + 1);
+        for (int k = i0; k < i1; ++k) {
+          const int slot = __ldg(node_slot + __ldg(ninc_other + k));
+          if (slot < 0) {
+            const double qe = __ldg(q + (__ldg(ninc_edge + k) >> 1));
+            const double3 x = ld3(xsb, -slot - 1);
+            acc.x += qe * x.x; acc.y += qe * x.y; acc.z += qe * x.z;
+          }
+        }
+      }
+      const double3 p = ld3(loads + b * loads_stride, n);
+      s_rhs[3 * tid] = p.x + acc.x; s_rhs[3 * tid + 1] = p.y + acc.y; s_rhs[3 * tid + 2] = p.z + acc.z;
+    }
+  }
+  __syncthreads();
+  if (Kd && staged)
+    for (int k = tid; k < cnt; k += kThreads) Kd[k0 + k] = s_val[k];
+  if (rhs) {
+    double* out = rhs + (b * (int64_t)Nf + r0) * 3;
+    for (int i = tid; i < (r1 - r0) * 3; i += kThreads) out[i] = s_rhs[i];
   }
 }
 
@@ -320,12 +372,12 @@ inline dim3 grid_for(int64_t work, int64_t batch) {
 int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const double* loads,
                     double* Kdata, double* rhs, int64_t batch, int64_t qs, int64_t xss, int64_t ls,
                     cudaStream_t st) {
-  const int64_t work = std::max<int64_t>(Kdata ? p->nnz : 0, p->Nf);
   const DeviceArrays& d = p->d;
+  const unsigned tiles = (unsigned)((p->Nf + kAsmRows - 1) / kAsmRows);
   FDM_BATCH_LOOP(batch, b0, nb) {
-    assemble_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
-        (int)p->nnz, (int)p->Nf, (int)p->N, (int)p->Ns, d.entry_edge, d.diag_pos, d.free_node,
-        d.node_slot, d.ninc_ptr, d.ninc_edge, d.ninc_other, q + b0 * qs,
+    assemble_kernel<<<dim3(tiles, (unsigned)nb), kThreads, 0, st>>>(
+        (int)p->nnz, (int)p->Nf, (int)p->N, (int)p->Ns, d.rowptr, d.entry_edge, d.diag_pos, d.free_node,
+        d.diags_ptr, d.diags_idx, d.sup_mask, d.node_slot, d.ninc_ptr, d.ninc_edge, d.ninc_other, q + b0 * qs,
         xs ? xs + b0 * xss : nullptr, loads ? loads + b0 * ls : nullptr,
         Kdata ? Kdata + b0 * p->nnz : nullptr, rhs ? rhs + b0 * p->Nf * 3 : nullptr, qs, xss, ls);
   }

@@ -113,6 +113,17 @@ int fdm_build_topology(fdm_plan& p, const int64_t* edges, int64_t E, int64_t N,
       p.diags_indices[o++] = p.ninc_edge[k] >> 1;
   }
 
+  // ---- sup_mask: free rows with at least one support neighbour (they carry a load-term sum) ----
+  p.sup_mask.assign((size_t)(p.Nf + 31) / 32, 0u);
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    int64_t n = p.indices_free[i];
+    for (int32_t k = p.ninc_ptr[n]; k < p.ninc_ptr[n + 1]; ++k)
+      if (p.node_slot[p.ninc_other[k]] < 0) {
+        p.sup_mask[(size_t)i >> 5] |= 1u << (i & 31);
+        break;
+      }
+  }
+
   // ---- index_array (structures.py:248-288), diag_indices (:290-314) ----
   // column i (== row i, the pattern is symmetric) holds, sorted by row index, the diagonal with
   // label 0 and every free neighbour j with label e+1 of the connecting edge.

@@ -20,6 +20,9 @@ struct DeviceArrays {
   int32_t* colidx = nullptr;       // (nnz)  = index_array.indices
   int32_t* entry_edge = nullptr;   // (nnz)  = index_array.data - 1   (-1 on the diagonal)
   int32_t* diag_pos = nullptr;     // (Nf)   = diag_indices
+  int32_t* diags_ptr = nullptr;    // (Nf+1) = diags.indptr  (per free row: incident edges, ascending id)
+  int32_t* diags_idx = nullptr;    // (dnnz) = diags.indices
+  uint32_t* sup_mask = nullptr;    // (ceil(Nf/32)) bit r set: free row r has a support neighbour
   // band ordering (batched Cholesky)
   int32_t* band_perm = nullptr;    // (Nf) free index -> band position
   int32_t* band_iperm = nullptr;   // (Nf) band position -> free index
@@ -42,6 +45,7 @@ struct fdm_plan {
   // kernel-side host arrays
   std::vector<int32_t> node_slot, edge_nodes, ninc_ptr, ninc_edge, ninc_other;
   std::vector<int32_t> free_node, fixed_node, entry_edge, diag_pos;
+  std::vector<uint32_t> sup_mask;
 
   // band ordering
   std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx;

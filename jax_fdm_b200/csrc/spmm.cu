@@ -5,10 +5,11 @@
 // (values 8 B + column index 4 B per entry; contiguous in memory because rows are) is staged
 // into shared memory with two TMA bulk copies (cp.async.bulk.shared::cluster.global, SASS
 // UBLKCP) signalled through one mbarrier, so the 12 B/nnz stream is read with full-width
-// coalesced transactions regardless of row length.  Rows are then processed by sub-warps
-// of kLanesPerRow lanes: each lane takes entries of its row from shared memory, gathers the
-// three coordinates of X[col] through the read-only path (X is L2-resident for every size in
-// BASELINE.json), and the partial sums are combined with shuffles.
+// coalesced transactions regardless of row length.  Rows are then processed one per thread:
+// the thread walks its row's entries in shared memory in ascending order (the summation order
+// of a sequential CSR product, hence deterministic), gathers the three coordinates of X[col]
+// through the read-only path (neighbouring rows share columns, so the gathers hit L1/L2), and
+// the results leave through a shared-memory tile so that Y is written with full-width stores.
 // Algorithmic bytes: 12 nnz + 52 Nf.
 #include <cuda_runtime.h>
 
@@ -17,9 +18,8 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kLanesPerRow = 4;                       // mean row length is ~5 on quad grids
-constexpr int kRowsPerCta = 512;                      // rows per CTA tile
-constexpr int kMaxTileNnz = 3072;                     // staged entries per stage (36 KB of the 48 KB static limit)
+constexpr int kRowsPerCta = 256;                      // rows per CTA tile (one per thread)
+constexpr int kMaxTileNnz = 1536;                     // staged entries per stage (18 KB; with the Y tile 25 KB => 8 CTAs per SM)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -63,6 +63,7 @@ spmm_tma_kernel(int Nf, const int32_t* __restrict__ rowptr, const int32_t* __res
   __shared__ __align__(16) int32_t s_col[kMaxTileNnz + 4];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_rp[kRowsPerCta + 1];
+  __shared__ __align__(16) double s_y[kRowsPerCta * 3];
 
   const int64_t b = blockIdx.y;
   Kdata += b * nnz;
@@ -77,10 +78,6 @@ spmm_tma_kernel(int Nf, const int32_t* __restrict__ rowptr, const int32_t* __res
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-
-  const int sub = threadIdx.x / kLanesPerRow;            // sub-warp id in the CTA
-  const int lane = threadIdx.x % kLanesPerRow;
-  constexpr int kSubs = kThreads / kLanesPerRow;
 
   uint32_t phase = 0;
   int row_lo = 0;                                         // local row where the current stage starts
@@ -117,31 +114,37 @@ spmm_tma_kernel(int Nf, const int32_t* __restrict__ rowptr, const int32_t* __res
       mbar_wait(&s_bar, phase);
       phase ^= 1;
     }
-    // uniform trip count across the warp (sub-warps of one warp own different rows and the
-    // reduction below uses full-warp shuffles)
-    for (int rb = row_lo; rb < row_hi; rb += kSubs) {
-      const int r = rb + sub;
-      const bool active = r < row_hi;
-      const int a = active ? s_rp[r] - kbeg : 0, e = active ? s_rp[r + 1] - kbeg : 0;
+    for (int r = row_lo + threadIdx.x; r < row_hi; r += kThreads) {
+      const int a = s_rp[r] - kbeg, e = s_rp[r + 1] - kbeg;
       double ax = 0.0, ay = 0.0, az = 0.0;
-      for (int k = a + lane; k < e; k += kLanesPerRow) {
-        double v;
-        int c;
-        if (tma_ok) { v = s_val[voff + k]; c = s_col[coff + k]; }
-        else { v = __ldg(Kdata + kbeg + k); c = __ldg(colidx + kbeg + k); }
-        const double* x = X + 3 * (int64_t)c;
-        ax += v * __ldg(x); ay += v * __ldg(x + 1); az += v * __ldg(x + 2);
-      }
+      // four entries per trip: all twelve gathers are issued before the first FMA needs one
+      // (entries past the row end are clamped to the row's first column with a zero value)
+      for (int k = a; k < e; k += 4) {
+        double v[4], x0[4], x1[4], x2[4];
+        int c[4];
 #pragma unroll
-      for (int o = kLanesPerRow / 2; o > 0; o >>= 1) {
-        ax += __shfl_xor_sync(0xffffffffu, ax, o);
-        ay += __shfl_xor_sync(0xffffffffu, ay, o);
-        az += __shfl_xor_sync(0xffffffffu, az, o);
+        for (int u = 0; u < 4; ++u) {
+          const bool in = k + u < e;
+          const int kk = in ? k + u : a;
+          if (tma_ok) { v[u] = s_val[voff + kk]; c[u] = s_col[coff + kk]; }
+          else { v[u] = __ldg(Kdata + kbeg + kk); c[u] = __ldg(colidx + kbeg + kk); }
+          if (!in) v[u] = 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const double* x = X + 3 * (int64_t)c[u];
+          x0[u] = __ldg(x); x1[u] = __ldg(x + 1); x2[u] = __ldg(x + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { ax += v[u] * x0[u]; ay += v[u] * x1[u]; az += v[u] * x2[u]; }
       }
-      if (active && lane == 0) {
-        double* y = Y + 3 * (int64_t)(r0 + r);
-        y[0] = ax; y[1] = ay; y[2] = az;
-      }
+      double* y = s_y + 3 * (r - row_lo);
+      y[0] = ax; y[1] = ay; y[2] = az;
+    }
+    __syncthreads();
+    {
+      double* out = Y + 3 * (int64_t)(r0 + row_lo);
+      for (int i = threadIdx.x; i < 3 * (row_hi - row_lo); i += kThreads) out[i] = s_y[i];
     }
     __syncthreads();                                      // staging buffers are reused
     row_lo = row_hi;

@@ -3,23 +3,37 @@
 // batches of small designs that share one topology, and the adjoint solve of
 // sparse_solve_bwd (sparse.py:296) with the factor reused instead of recomputed.
 //
-// Layout.  Band order = plan.band_perm.  Lane (R & 31) owns row R of the lower triangle while R
-// is inside the 32-row window [j, j+32) of the right-looking factorisation; the row lives in 32
-// REGISTERS, slot (C & 31) holding A(R, C).  Step j:
-//     piv  = A(j,j)                    shuffle from lane j&31
-//     l    = A(R,j) / sqrt(piv)        every lane, own register (exactly 0 outside the band)
-//     A(R, j+k) -= l_R * l_{j+k}       k = 1..KMAX: l_{j+k} is a shared-memory BROADCAST (one
-//                                      wavefront per pair), the accumulator never leaves registers
-// so a step costs ~KMAX FP64 FMAs and KMAX/2 uniform LDS.128 per lane -- no matrix traffic through
-// shared memory.  The updates with j+k > R fall into slots of columns that are already
-// eliminated (dead) and are overwritten when the lane takes row R+32, whose 32 slots are read
-// from a staged shared-memory block (filled once per 32 steps from K.data through the
-// row-oriented index table plan.band_rowkidx).  The three right-hand sides ride along as three
-// more registers per lane (forward substitution fused into the factorisation).
+// Two kernels:
 //
-// The factor goes to the workspace column by column (fac[j][d] = L(j+d, j), d = 1..31, and
-// fac[j][0] = 1/L(j,j)): one coalesced 256-byte store per step.  The backward substitution and
-// the adjoint's forward substitution read it back in 32x32 blocks staged in shared memory.
+// chol_factor_kernel  factorisation + fused forward substitution.  Band order = plan.band_perm.
+//   Lane (R & 31) owns row R of the lower triangle while R is inside the 32-row window [j, j+32)
+//   of the right-looking factorisation; the row lives in 32 REGISTERS, slot (C & 31) holding
+//   A(R, C).  Step j:
+//       piv  = A(j,j)                    shuffle from lane j&31
+//       l    = A(R,j) / sqrt(piv)        every lane, own register (exactly 0 outside the band)
+//       A(R, j+k) -= l_R * l_{j+k}       k = 1..KMAX: l_{j+k} is a shared-memory BROADCAST, the
+//                                        accumulator never leaves registers
+//   The updates with j+k > R fall into slots of columns that are already eliminated (dead) and
+//   are overwritten when the lane takes row R+32, whose 32 slots are read from a staged
+//   shared-memory block (filled once per 32 steps from K.data through plan.band_rowkidx).  The
+//   three right-hand sides ride along as three more registers per lane.
+//   The factor goes to the workspace column by column (fac[j][d] = L(j+d, j), d = 1..31), one
+//   coalesced 256-byte store per step.  Columns are grouped in eights; the 8x8 diagonal block of
+//   every group is stored INVERTED (fac[8k+b][a-b] = inv(L_kk)(a,b), hence fac[j][0] = 1/L(j,j)).
+//   Inside its 32-double record, column j is rotated by 5*(j&3) slots (FROT): a 32-column block is
+//   then one contiguous 8 KB that a single TMA bulk copy drops into shared memory, and the tile
+//   fragment reads of the substitution kernel (4 columns x 8 rows per access) hit 16 distinct banks.
+//
+// chol_subst_kernel   substitutions with the stored factor, as dependency-free 8x8 tile products
+//       forward   z_k = inv(L_kk) g_k ;  g_{k+i} -= L_{k+i,k} z_k           (i = 1..NBL)
+//       backward  x_k = inv(L_kk)^T (z_k - sum_i L_{k+i,k}^T x_{k+i})
+//   on the FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA); the three right-hand sides are
+//   columns 0..2 of an 8-wide tile.  The factor streams through shared memory in 32-column blocks,
+//   double buffered: one 8 KB TMA bulk copy (cp.async.bulk, SASS UBLKCP) per block, completion on
+//   an mbarrier, so the next block is in flight while this one is used.
+//   The forward solve runs it backward-only (its forward substitution is fused in the factor
+//   kernel); the adjoint solve (opts.reuse_factor) runs forward then backward.
+//
 // Rows are padded to a multiple of 32 with identity rows, so there is no tail code.
 // sigma = sign of the first diagonal entry; the factor is of sigma*K (all q<0 => K = -SPD).
 #include <cuda_runtime.h>
@@ -28,12 +42,10 @@
 
 namespace {
 
-constexpr int kWarps = 8;  // designs per CTA
-constexpr int kThreads = kWarps * 32;
-constexpr int kFS = 34;    // row stride (doubles) of the staged 32x32 block: 16-byte aligned rows, conflict-free columns
-constexpr int kSL = 40;    // doubles per broadcast buffer: [1..32] l, [34..36] solved rhs entries
-constexpr int kWarpSmem = 32 * kFS + 2 * kSL;
+constexpr int kFS = 34;    // row stride (doubles) of a staged 32x32 block: 16-byte aligned rows, conflict-free columns
 constexpr unsigned kFull = 0xffffffffu;
+// slot of L(j+d, j) inside the 32-double record of factor column j
+#define FROT(j, d) (((d) + 5 * ((j) & 3)) & 31)
 
 struct WArgs {
   int n, bw, nblk;
@@ -46,200 +58,389 @@ struct WArgs {
   double* ws;              // (B, ws_stride)
   int64_t ws_stride;       // nblk*1024 (factor) + nblk*128 (intermediate rhs) + 8 (sigma, bad)
   int64_t nnz, batch;
-  int reuse;
+  int forward;             // subst kernel: run the forward substitution on `rhs` first
 };
 
+// ===========================================================================================
+// factorisation + fused forward substitution
+// ===========================================================================================
+constexpr int kFacWarps = 8;  // designs per CTA
+constexpr int kFacThreads = kFacWarps * 32;
+constexpr int kSL = 40;       // doubles per broadcast buffer: [1..32] l, [34..36] solved rhs entries
+constexpr int kFacWarpSmem = 32 * kFS + 2 * kSL + 64;  // staged rows + 2 broadcast buffers + 8x8 diagonal block
+
 template <int KMAX>
-__global__ void __launch_bounds__(kThreads, 2) chol_warp_kernel(WArgs A) {
+__global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * kWarps + warp;
+  const int64_t b = (int64_t)blockIdx.x * kFacWarps + warp;
   if (b >= A.batch) return;  // warps are independent: no block-level barrier anywhere below
-  double* fs = smem + warp * kWarpSmem;
+  double* fs = smem + warp * kFacWarpSmem;
   double* sl = fs + 32 * kFS;
+  double* Lb = sl + 2 * kSL;
   const int n = A.n, nblk = A.nblk;
   const double* Kd = A.Kdata + b * A.nnz;
   const double* rhs = A.rhs + b * (int64_t)n * 3;
   double* fac = A.ws + b * A.ws_stride;
   double* ysol = fac + (int64_t)nblk * 1024;
   double* meta = ysol + (int64_t)nblk * 128;
-  double sigma;
   int bad = 0;
+  const double sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
 
   auto load_rhs = [&](int R, double (&out)[3]) {
     if (R < n) {
-      const int g = __ldg(A.iperm + R);
-      out[0] = sigma * rhs[3 * g];
-      out[1] = sigma * rhs[3 * g + 1];
-      out[2] = sigma * rhs[3 * g + 2];
+      const int gi = __ldg(A.iperm + R);
+      out[0] = sigma * rhs[3 * gi];
+      out[1] = sigma * rhs[3 * gi + 1];
+      out[2] = sigma * rhs[3 * gi + 2];
     } else {
       out[0] = out[1] = out[2] = 0.0;
     }
   };
-  // fs[r][c] = fac[j0 + r][c]
-  auto stage_fac = [&](int j0) {
-    const double* src = fac + (int64_t)j0 * 32 + lane;
+  // fs[r][s] = sigma * A(R0 + r, C) for the column C = s (mod 32) of the 32 columns ending at row R0 + r
+  auto stage_rows = [&](int R0) {
+    const int32_t* idxp = A.rowkidx + (int64_t)R0 * 32;
 #pragma unroll 8
-    for (int r = 0; r < 32; ++r) fs[r * kFS + lane] = src[r * 32];
+    for (int r = 0; r < 32; ++r) {
+      const int idx = __ldg(idxp + r * 32 + ((r - lane) & 31));
+      double v = 0.0;
+      if (idx >= 0) v = sigma * __ldg(Kd + idx);
+      else if (idx == -2) v = 1.0;
+      fs[r * kFS + lane] = v;
+    }
   };
-
-  if (!A.reuse) {
-    // ------------------------------------------------------------------ factor + forward substitution
-    sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
-    // fs[r][s] = sigma * A(R0 + r, C) for the column C = s (mod 32) of the 32 columns ending at row R0 + r
-    auto stage_rows = [&](int R0) {
-      const int32_t* idxp = A.rowkidx + (int64_t)R0 * 32;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int idx = __ldg(idxp + r * 32 + ((r - lane) & 31));
-        double v = 0.0;
-        if (idx >= 0) v = sigma * __ldg(Kd + idx);
-        else if (idx == -2) v = 1.0;
-        fs[r * kFS + lane] = v;
-      }
-    };
-    double a[32], y[3], yn[3];
-    stage_rows(0);
+  double a[32], y[3], yn[3];
+  stage_rows(0);
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < 32; s += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(fs + lane * kFS + s);
+    a[s] = v.x;
+    a[s + 1] = v.y;
+  }
+  load_rhs(lane, y);
+  // per-lane constants of the unrolled step body (everything else is an immediate)
+  double* const Lbrow = Lb + (lane & 7) * 8;         // row (lane & 7) of the 8x8 diagonal block
+  const double* const fsrow0 = fs;                   // staged rows, indexed by the compile-time step
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * 32;
+    double* const fb = fac + (int64_t)j0 * 32;       // factor records of this block's 32 columns
+    double* const yb = ysol + (int64_t)j0 * 4;
+    __syncwarp();  // every lane has consumed the previous staged block
+    stage_rows(j0 + 32);
+    load_rhs(j0 + 32 + lane, yn);
     __syncwarp();
 #pragma unroll
-    for (int s = 0; s < 32; s += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(fs + lane * kFS + s);
-      a[s] = v.x;
-      a[s + 1] = v.y;
-    }
-    load_rhs(lane, y);
-    for (int jb = 0; jb < nblk; ++jb) {
-      const int j0 = jb * 32;
-      __syncwarp();  // every lane has consumed the previous staged block
-      stage_rows(j0 + 32);
-      load_rhs(j0 + 32 + lane, yn);
+    for (int p = 0; p < 32; ++p) {
+      const unsigned du = (unsigned)(lane - p);      // unwrapped row offset: du < 32 <=> lane >= p
+      const int delta = du & 31;
+      double* buf = sl + (p & 1) * kSL;
+      const double piv = __shfl_sync(kFull, a[p], p);
+      bad |= !(piv > 0.0);
+      const double inv = rsqrt(piv);
+      const double l = a[p] * inv;
+      // factor record of column j (rotated, see FROT); the entries that belong to the 8x8 diagonal
+      // block of this column group are overwritten with the block inverse at the end of the group
+      fb[p * 32 + ((lane + ((5 * (p & 3) - p) & 31)) & 31)] = l;
+      if (du <= (unsigned)(7 - (p & 7))) Lbrow[p & 7] = l;   // same group, on or below the diagonal
+      buf[delta + 1] = l;
+      if (delta == 0) {
+        const double y0 = y[0] * inv, y1 = y[1] * inv, y2 = y[2] * inv;
+        buf[34] = y0; buf[35] = y1; buf[36] = y2;
+        yb[p * 4] = y0; yb[p * 4 + 1] = y1; yb[p * 4 + 2] = y2;
+        Lbrow[p & 7] = inv;                          // the diagonal of the block holds 1/L(j,j)
+      }
       __syncwarp();
 #pragma unroll
-      for (int p = 0; p < 32; ++p) {
-        const int j = j0 + p;
-        const int delta = (lane - p) & 31;
-        double* buf = sl + (p & 1) * kSL;
-        const double piv = __shfl_sync(kFull, a[p], p);
-        bad |= !(piv > 0.0);
-        const double inv = rsqrt(piv);
-        const double l = a[p] * inv;
-        fac[(int64_t)j * 32 + delta] = delta == 0 ? inv : l;
-        buf[delta + 1] = l;
-        if (delta == 0) {
-          const double y0 = y[0] * inv, y1 = y[1] * inv, y2 = y[2] * inv;
-          buf[34] = y0; buf[35] = y1; buf[36] = y2;
-          double* yo = ysol + (int64_t)j * 4;
-          yo[0] = y0; yo[1] = y1; yo[2] = y2;
+      for (int k = 1; k <= KMAX; k += 2) {
+        const double2 lc = *reinterpret_cast<const double2*>(buf + k + 1);
+        a[(p + k) & 31] = fma(-l, lc.x, a[(p + k) & 31]);
+        if (k + 1 <= KMAX) a[(p + k + 1) & 31] = fma(-l, lc.y, a[(p + k + 1) & 31]);
+      }
+      {
+        const double2 t = *reinterpret_cast<const double2*>(buf + 34);
+        const double t2 = buf[36];
+        y[0] = fma(-l, t.x, y[0]);
+        y[1] = fma(-l, t.y, y[1]);
+        y[2] = fma(-l, t2, y[2]);
+      }
+      if (delta == 0) {  // row j is done: this lane takes row j + 32
+#pragma unroll
+        for (int s = 0; s < 32; s += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(fsrow0 + p * kFS + s);
+          a[s] = v.x;
+          a[s + 1] = v.y;
+        }
+        y[0] = yn[0]; y[1] = yn[1]; y[2] = yn[2];
+      }
+      if ((p & 7) == 7) {
+        // invert the 8x8 lower-triangular diagonal block of this group: lane b (mod 8) solves
+        // L X(:,b) = e_b by forward substitution; Lb holds L(a,c) below and 1/L(a,a) on the diagonal.
+        __syncwarp();
+        const int bcol = lane & 7;
+        double X[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int c = 0; c + 1 < r; c += 2) {
+            const double2 lv = *reinterpret_cast<const double2*>(Lb + r * 8 + c);
+            sacc = fma(lv.x, X[c], sacc);
+            sacc = fma(lv.y, X[c + 1], sacc);
+          }
+          if (r & 1) sacc = fma(Lb[r * 8 + r - 1], X[r - 1], sacc);
+          const double dinv = Lb[r * 8 + r];
+          X[r] = r < bcol ? 0.0 : (r == bcol ? dinv : -sacc * dinv);
+        }
+        if (lane < 8) {
+          double* fo = fb + (p - 7 + bcol) * 32;
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (r >= bcol) fo[FROT(bcol, r - bcol)] = X[r];
         }
         __syncwarp();
-#pragma unroll
-        for (int k = 1; k <= KMAX; k += 2) {
-          const double2 lc = *reinterpret_cast<const double2*>(buf + k + 1);
-          a[(p + k) & 31] = fma(-l, lc.x, a[(p + k) & 31]);
-          if (k + 1 <= KMAX) a[(p + k + 1) & 31] = fma(-l, lc.y, a[(p + k + 1) & 31]);
-        }
-        {
-          const double2 t = *reinterpret_cast<const double2*>(buf + 34);
-          const double t2 = buf[36];
-          y[0] = fma(-l, t.x, y[0]);
-          y[1] = fma(-l, t.y, y[1]);
-          y[2] = fma(-l, t2, y[2]);
-        }
-        if (delta == 0) {  // row j is done: this lane takes row j + 32
-#pragma unroll
-          for (int s = 0; s < 32; s += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(fs + p * kFS + s);
-            a[s] = v.x;
-            a[s + 1] = v.y;
-          }
-          y[0] = yn[0]; y[1] = yn[1]; y[2] = yn[2];
-        }
-      }
-    }
-    if (lane == 0) {
-      meta[0] = sigma;
-      meta[1] = (double)bad;
-    }
-  } else {
-    // ------------------------------------------------------------------ forward substitution with the stored factor
-    sigma = meta[0];
-    bad = meta[1] != 0.0;
-    double acc[3], yn[3];
-    load_rhs(lane, acc);
-    for (int jb = 0; jb < nblk; ++jb) {
-      const int j0 = jb * 32;
-      __syncwarp();
-      stage_fac(j0);
-      load_rhs(j0 + 32 + lane, yn);
-      __syncwarp();
-#pragma unroll
-      for (int p = 0; p < 32; ++p) {
-        const int delta = (lane - p) & 31;
-        const double inv = fs[p * kFS];
-        const double lv = fs[p * kFS + delta];
-        const double z0 = __shfl_sync(kFull, acc[0] * inv, p);
-        const double z1 = __shfl_sync(kFull, acc[1] * inv, p);
-        const double z2 = __shfl_sync(kFull, acc[2] * inv, p);
-        if (delta == 0) {
-          double* yo = ysol + (int64_t)(j0 + p) * 4;
-          yo[0] = z0; yo[1] = z1; yo[2] = z2;
-          acc[0] = yn[0]; acc[1] = yn[1]; acc[2] = yn[2];
-        } else {
-          acc[0] = fma(-lv, z0, acc[0]);
-          acc[1] = fma(-lv, z1, acc[1]);
-          acc[2] = fma(-lv, z2, acc[2]);
-        }
       }
     }
   }
+  if (lane == 0) {
+    meta[0] = sigma;
+    meta[1] = (double)bad;
+  }
+}
 
-  // -------------------------------------------------------------------- backward substitution  L^T x = y
-  double xprev[3] = {0.0, 0.0, 0.0};
-  for (int jb = nblk - 1; jb >= 0; --jb) {
-    const int j0 = jb * 32;
-    __syncwarp();  // orders this warp's factor / ysol stores before the loads below, and protects fs
-    stage_fac(j0);
-    double acc[3];
-    {
-      const double* yi = ysol + (int64_t)(j0 + lane) * 4;
-      acc[0] = yi[0]; acc[1] = yi[1]; acc[2] = yi[2];
+// ===========================================================================================
+// substitutions with the stored factor
+// ===========================================================================================
+constexpr int kSubWarps = 11;  // designs per CTA; one CTA per SM (214 KB of shared memory)
+constexpr int kSubThreads = kSubWarps * 32;
+constexpr int kSS = 32;        // staged factor blocks are verbatim copies of global memory
+constexpr int kSubWarpSmem = 2 * 32 * kSS + 6 * 64 + 2;  // 2 staged blocks, 2 transposition tiles, ring of 4 solution tiles, 2 mbarriers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(phase)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor pipe.  Lane (g = lane>>2, m = lane&3) holds
+// A[g][m], B[m][g] and D[g][2m], D[g][2m+1].
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+template <int NBL>  // column group k reaches row groups k+1 .. k+NBL
+__global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kSubWarps + warp;
+  if (b >= A.batch) return;
+  double* fsb = smem + warp * kSubWarpSmem;   // two staged blocks
+  double* zt1 = fsb + 2 * 32 * kSS;
+  double* zt2 = zt1 + 64;
+  double* xt = zt2 + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xt + 4 * 64);
+  const int g = lane >> 2, m = lane & 3;
+  const int n = A.n, nblk = A.nblk;
+  const double* rhs = A.rhs + b * (int64_t)n * 3;
+  double* fac = A.ws + b * A.ws_stride;
+  double* ysol = fac + (int64_t)nblk * 1024;
+  const double* meta = ysol + (int64_t)nblk * 128;
+  const double sigma = meta[0];
+  const bool bad = meta[1] != 0.0;
+
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = lane; i < 4 * 64; i += 32) xt[i] = 0.0;
+  __syncwarp();
+
+  // visit v = 0 .. nvis-1: forward pass over blocks 0..nblk-1 (if A.forward), then backward pass nblk-1..0
+  const int nfwd = A.forward ? nblk : 0;
+  const int nvis = nfwd + nblk;
+  auto block_of = [&](int v) { return v < nfwd ? v : nblk - 1 - (v - nfwd); };
+  auto issue = [&](int v) {  // one 8 KB bulk copy: the 32 factor columns of block_of(v) into buffer v&1
+    if (lane == 0) {
+      uint64_t* bar = bars + (v & 1);
+      mbar_expect_tx(bar, 32 * 256);
+      tma_load_1d(fsb + (v & 1) * 32 * kSS, fac + (int64_t)block_of(v) * 1024, 32 * 256, bar);
     }
-    __syncwarp();
-    const double* row = fs + lane * kFS;  // column j0+lane of L: row[d] = L(j0+lane+d, j0+lane)
-    const double myinv = row[0];
-    // rows of the block above: x_i for i = j0+32 .. j0+31+KMAX, held by lane i-j0-32 in xprev
+  };
+  uint32_t phases = 0u;   // bit i: parity the next wait on barrier i expects
+  issue(0);
+
+  // forward-pass state: T[i] = rows of group k+i of the running right-hand side, 8x8 tile (columns 0..2
+  // used) in the accumulator layout of the FP64 mma: lane (g, m) holds row g, columns 2m and 2m+1.
+  auto load_tile = [&](int R, double (&t)[2]) {
+    t[0] = 0.0; t[1] = 0.0;
+    if (R < n && m < 2) {
+      const int gi = __ldg(A.iperm + R);
+      t[0] = sigma * rhs[3 * gi + 2 * m];
+      if (m == 0) t[1] = sigma * rhs[3 * gi + 1];
+    }
+  };
+  double T[NBL + 1][2];
 #pragma unroll
-    for (int ii = KMAX; ii >= 1; --ii) {
-      const double x0 = __shfl_sync(kFull, xprev[0], ii - 1);
-      const double x1 = __shfl_sync(kFull, xprev[1], ii - 1);
-      const double x2 = __shfl_sync(kFull, xprev[2], ii - 1);
-      if (lane >= ii) {
-        const double lv = row[31 + ii - lane];
-        acc[0] = fma(-lv, x0, acc[0]);
-        acc[1] = fma(-lv, x1, acc[1]);
-        acc[2] = fma(-lv, x2, acc[2]);
+  for (int i = 0; i <= NBL; ++i) {
+    T[i][0] = 0.0; T[i][1] = 0.0;
+    if (nfwd) load_tile(8 * i + g, T[i]);
+  }
+  // Global operands of a visit are fetched ahead so that no load sits on a warp's critical path:
+  // band-to-free row indices two visits ahead (Qn -> Q -> Qc), values one visit ahead (P -> C).
+  // Forward visit: the four row groups that enter the window.  Backward visit: the four groups
+  // of z it starts from (and the row indices for storing x).
+  double P[4][2], C[4][2];
+  int Qn[4], Q[4], Qc[4];
+  auto rows_of = [&](int v, int kb) {
+    const int r0 = block_of(v) * 32 + 8 * kb + g;
+    return v < nfwd ? r0 + 8 * (NBL + 1) : r0;
+  };
+  auto fetch_idx = [&](int v) {
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const int R = rows_of(v, kb);
+      Qn[kb] = R < n ? __ldg(A.iperm + R) : -1;
+    }
+  };
+  auto fetch_val = [&](int v) {   // uses Q = row indices of visit v
+    if (v < nfwd) {
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        P[kb][0] = 0.0; P[kb][1] = 0.0;
+        if (Q[kb] >= 0 && m < 2) {
+          P[kb][0] = rhs[3 * Q[kb] + 2 * m];            // scaled by sigma where consumed: no use here, no stall
+          if (m == 0) P[kb][1] = rhs[3 * Q[kb] + 1];
+        }
+      }
+    } else {
+      const int r0 = block_of(v) * 32;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        P[kb][0] = 0.0; P[kb][1] = 0.0;
+        if (m < 2) {
+          const double2 zv = *reinterpret_cast<const double2*>(ysol + (int64_t)(r0 + 8 * kb + g) * 4 + 2 * m);
+          P[kb][0] = zv.x;
+          if (m == 0) P[kb][1] = zv.y;
+        }
       }
     }
-    double xf[3] = {0.0, 0.0, 0.0};
+  };
+  fetch_idx(0);
 #pragma unroll
-    for (int r = 31; r >= 0; --r) {
-      const double x0 = __shfl_sync(kFull, acc[0] * myinv, r);
-      const double x1 = __shfl_sync(kFull, acc[1] * myinv, r);
-      const double x2 = __shfl_sync(kFull, acc[2] * myinv, r);
-      if (lane < r) {
-        const double lv = row[r - lane];
-        acc[0] = fma(-lv, x0, acc[0]);
-        acc[1] = fma(-lv, x1, acc[1]);
-        acc[2] = fma(-lv, x2, acc[2]);
-      } else if (lane == r) {
-        xf[0] = x0; xf[1] = x1; xf[2] = x2;
-      }
+  for (int kb = 0; kb < 4; ++kb) Q[kb] = Qn[kb];
+  fetch_val(0);
+  if (nvis > 1) fetch_idx(1);
+
+  for (int v = 0; v < nvis; ++v) {
+    const int jb = block_of(v), j0 = jb * 32;
+    __syncwarp();                      // every lane is done with buffer (v+1)&1 (used at visit v-1)
+    if (v + 1 < nvis) issue(v + 1);
+    mbar_wait(bars + (v & 1), (phases >> (v & 1)) & 1u);
+    phases ^= 1u << (v & 1);
+    const double* fs = fsb + (v & 1) * 32 * kSS;
+    const int rm = 5 * m, rg = 5 * (g & 3);   // record rotation of the columns this lane reads (forward / backward)
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const double sc = v < nfwd ? sigma : 1.0;
+      C[kb][0] = P[kb][0] * sc; C[kb][1] = P[kb][1] * sc; Qc[kb] = Q[kb]; Q[kb] = Qn[kb];
     }
-    xprev[0] = xf[0]; xprev[1] = xf[1]; xprev[2] = xf[2];
-    const int R = j0 + lane;
-    if (R < n) {
-      double* xo = A.x + (b * (int64_t)n + __ldg(A.iperm + R)) * 3;
-      xo[0] = xf[0]; xo[1] = xf[1]; xo[2] = xf[2];
+    if (v + 1 < nvis && v + 1 != nfwd) fetch_val(v + 1);
+    if (v + 2 < nvis) fetch_idx(v + 2);
+    if (v < nfwd) {
+      // ---------------------------------------------------------------- forward: L z = sigma g
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const int cb = 8 * kb;
+        // z_k = inv(L_kk) T[0]
+        *reinterpret_cast<double2*>(zt1 + g * 8 + 2 * m) = make_double2(T[0][0], T[0][1]);
+        __syncwarp();
+        double z0 = 0.0, z1 = 0.0;
+        {
+          const double b0 = zt1[m * 8 + g], b1 = zt1[(4 + m) * 8 + g];
+          const double a0 = g >= m ? fs[(cb + m) * kSS + ((g - m + rm) & 31)] : 0.0;
+          const double a1 = g >= 4 + m ? fs[(cb + 4 + m) * kSS + ((g - 4 - m + rm) & 31)] : 0.0;
+          dmma(z0, z1, a0, b0);
+          dmma(z0, z1, a1, b1);
+        }
+        if (m < 2) *reinterpret_cast<double2*>(ysol + (int64_t)(j0 + cb + g) * 4 + 2 * m) = make_double2(z0, z1);
+        // T[i] -= L_{k+i,k} z_k
+        *reinterpret_cast<double2*>(zt2 + g * 8 + 2 * m) = make_double2(z0, z1);
+        __syncwarp();
+        const double nb0 = -zt2[m * 8 + g], nb1 = -zt2[(4 + m) * 8 + g];
+#pragma unroll
+        for (int i = 1; i <= NBL; ++i) {
+          const int d0 = 8 * i + g - m, d1 = d0 - 4;
+          const double a0 = d0 <= 31 ? fs[(cb + m) * kSS + ((d0 + rm) & 31)] : 0.0;
+          const double a1 = d1 <= 31 ? fs[(cb + 4 + m) * kSS + ((d1 + rm) & 31)] : 0.0;
+          dmma(T[i][0], T[i][1], a0, nb0);
+          dmma(T[i][0], T[i][1], a1, nb1);
+        }
+#pragma unroll
+        for (int i = 0; i < NBL; ++i) { T[i][0] = T[i + 1][0]; T[i][1] = T[i + 1][1]; }
+        T[NBL][0] = C[kb][0]; T[NBL][1] = C[kb][1];   // rows of group k+NBL+1 enter the window
+      }
+      if (v + 1 == nfwd) {   // the first backward visit starts from z written during this visit
+        __syncwarp();
+        fetch_val(v + 1);
+      }
+    } else {
+      // ---------------------------------------------------------------- backward: L^T x = z
+#pragma unroll
+      for (int kb = 3; kb >= 0; --kb) {
+        const int cb = 8 * kb;
+        double acc0 = C[kb][0], acc1 = C[kb][1], acd0 = 0.0, acd1 = 0.0;   // two chains of tensor ops
+        // acc -= L_{k+i,k}^T x_{k+i}: A[g][kk] = L(8(k+i)+kk, 8k+g), B[kk][nn] = x_{k+i}(kk, nn)
+#pragma unroll
+        for (int i = 1; i <= NBL; ++i) {
+          const double* xs = xt + ((kb + i) & 3) * 64;
+          const int d0 = 8 * i + m - g, d1 = d0 + 4;
+          const double a0 = d0 <= 31 ? fs[(cb + g) * kSS + ((d0 + rg) & 31)] : 0.0;
+          const double a1 = d1 <= 31 ? fs[(cb + g) * kSS + ((d1 + rg) & 31)] : 0.0;
+          dmma(acc0, acc1, a0, -xs[m * 8 + g]);
+          dmma(acd0, acd1, a1, -xs[(4 + m) * 8 + g]);
+        }
+        acc0 += acd0; acc1 += acd1;
+        // x_k = inv(L_kk)^T acc: A[g][kk] = inv(L_kk)(kk, g)
+        *reinterpret_cast<double2*>(zt1 + g * 8 + 2 * m) = make_double2(acc0, acc1);
+        __syncwarp();
+        double x0 = 0.0, x1 = 0.0;
+        {
+          const double b0 = zt1[m * 8 + g], b1 = zt1[(4 + m) * 8 + g];
+          const double a0 = m >= g ? fs[(cb + g) * kSS + ((m - g + rg) & 31)] : 0.0;
+          const double a1 = 4 + m >= g ? fs[(cb + g) * kSS + ((4 + m - g + rg) & 31)] : 0.0;
+          dmma(x0, x1, a0, b0);
+          dmma(x0, x1, a1, b1);
+        }
+        *reinterpret_cast<double2*>(xt + (kb & 3) * 64 + g * 8 + 2 * m) = make_double2(x0, x1);
+        if (Qc[kb] >= 0 && m < 2) {
+          double* xo = A.x + (b * (int64_t)n + Qc[kb]) * 3 + 2 * m;
+          xo[0] = x0;
+          if (m == 0) xo[1] = x1;
+        }
+        __syncwarp();
+      }
     }
   }
   if (A.info && lane == 0) {
@@ -288,15 +489,20 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.ws_stride = ws_stride_of(p);
   A.nnz = p->nnz;
   A.batch = batch;
-  A.reuse = o.reuse_factor;
-  void (*kern)(WArgs) = nullptr;
-  if (p->hbw <= 7) kern = chol_warp_kernel<7>;
-  else if (p->hbw <= 15) kern = chol_warp_kernel<15>;
-  else if (p->hbw <= 23) kern = chol_warp_kernel<23>;
-  else kern = chol_warp_kernel<31>;
-  const size_t smem = (size_t)kWarps * kWarpSmem * sizeof(double);
-  FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const unsigned grid = (unsigned)((batch + kWarps - 1) / kWarps);
-  kern<<<grid, kThreads, smem, st>>>(A);
+  A.forward = o.reuse_factor ? 1 : 0;
+  void (*fkern)(WArgs) = nullptr;
+  void (*skern)(WArgs) = nullptr;
+  if (p->hbw <= 7) { fkern = chol_factor_kernel<7>; skern = chol_subst_kernel<1>; }
+  else if (p->hbw <= 15) { fkern = chol_factor_kernel<15>; skern = chol_subst_kernel<2>; }
+  else if (p->hbw <= 23) { fkern = chol_factor_kernel<23>; skern = chol_subst_kernel<3>; }
+  else { fkern = chol_factor_kernel<31>; skern = chol_subst_kernel<4>; }
+  if (!o.reuse_factor) {
+    const size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
+    FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+  }
+  const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
+  FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  skern<<<(unsigned)((batch + kSubWarps - 1) / kSubWarps), kSubThreads, smem, st>>>(A);
   return fdm_check_launch("chol_warp_solve");
 }

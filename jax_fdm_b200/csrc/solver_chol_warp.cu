@@ -38,6 +38,8 @@
 // sigma = sign of the first diagonal entry; the factor is of sigma*K (all q<0 => K = -SPD).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "launch.h"
 
 namespace {
@@ -61,13 +63,62 @@ struct WArgs {
   int forward;             // subst kernel: run the forward substitution on `rhs` first
 };
 
+// 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~22 bits) + two Newton steps in
+// FP64 (relative error ~1e-16).  No special-case path: a non-positive pivot is reported through `bad`.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+
+// -------------------------------------------------------------------------------------------
+// After the factorisation: replace the 8x8 lower-triangular diagonal block of every group of 8
+// columns by its inverse, in place (the diagonal slots already hold 1/L(j,j)).  Eight lanes per
+// block: lane c solves L X(:,c) = e_c by forward substitution with the block in registers.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chol_invdiag_kernel(WArgs A) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = A.nblk * 4;
+  const int64_t item = t >> 3;            // (design, group)
+  const int c = (int)(t & 7);
+  const bool live = item < A.batch * groups;
+  double* fb = nullptr;
+  double Lr[8][8];
+  if (live) {
+    const int64_t b = item / groups;
+    const int grp = (int)(item - b * groups);
+    fb = A.ws + b * A.ws_stride + (int64_t)grp * 8 * 32;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k <= r; ++k) Lr[r][k] = fb[k * 32 + FROT(k, r - k)];   // L(r,k) below, 1/L(r,r) on the diagonal
+  }
+  __syncwarp();                            // every lane of the block has read it before anyone overwrites
+  if (!live) return;
+  double X[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) sacc = fma(Lr[r][k], X[k], sacc);   // X[k] = 0 for k < c
+    X[r] = Lr[r][r] * ((r == c ? 1.0 : 0.0) - sacc);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r >= c) fb[c * 32 + FROT(c, r - c)] = X[r];
+}
+
 // ===========================================================================================
 // factorisation + fused forward substitution
 // ===========================================================================================
 constexpr int kFacWarps = 8;  // designs per CTA
 constexpr int kFacThreads = kFacWarps * 32;
 constexpr int kSL = 40;       // doubles per broadcast buffer: [1..32] l, [34..36] solved rhs entries
-constexpr int kFacWarpSmem = 32 * kFS + 2 * kSL + 64;  // staged rows + 2 broadcast buffers + 8x8 diagonal block
+constexpr int kFacWarpSmem = 32 * kFS + 2 * kSL;       // staged rows + 2 broadcast buffers
 
 template <int KMAX>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
@@ -77,7 +128,6 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
   if (b >= A.batch) return;  // warps are independent: no block-level barrier anywhere below
   double* fs = smem + warp * kFacWarpSmem;
   double* sl = fs + 32 * kFS;
-  double* Lb = sl + 2 * kSL;
   const int n = A.n, nblk = A.nblk;
   const double* Kd = A.Kdata + b * A.nnz;
   const double* rhs = A.rhs + b * (int64_t)n * 3;
@@ -120,7 +170,6 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
   }
   load_rhs(lane, y);
   // per-lane constants of the unrolled step body (everything else is an immediate)
-  double* const Lbrow = Lb + (lane & 7) * 8;         // row (lane & 7) of the 8x8 diagonal block
   const double* const fsrow0 = fs;                   // staged rows, indexed by the compile-time step
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * 32;
@@ -132,23 +181,20 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
     __syncwarp();
 #pragma unroll
     for (int p = 0; p < 32; ++p) {
-      const unsigned du = (unsigned)(lane - p);      // unwrapped row offset: du < 32 <=> lane >= p
-      const int delta = du & 31;
+      const int delta = (lane - p) & 31;
       double* buf = sl + (p & 1) * kSL;
       const double piv = __shfl_sync(kFull, a[p], p);
       bad |= !(piv > 0.0);
       const double inv = rsqrt(piv);
       const double l = a[p] * inv;
-      // factor record of column j (rotated, see FROT); the entries that belong to the 8x8 diagonal
-      // block of this column group are overwritten with the block inverse at the end of the group
-      fb[p * 32 + ((lane + ((5 * (p & 3) - p) & 31)) & 31)] = l;
-      if (du <= (unsigned)(7 - (p & 7))) Lbrow[p & 7] = l;   // same group, on or below the diagonal
+      // factor record of column j (rotated, see FROT), 1/L(j,j) in the diagonal slot; the 8x8 diagonal
+      // blocks are inverted afterwards by chol_invdiag_kernel
+      fb[p * 32 + ((lane + ((5 * (p & 3) - p) & 31)) & 31)] = delta == 0 ? inv : l;
       buf[delta + 1] = l;
       if (delta == 0) {
         const double y0 = y[0] * inv, y1 = y[1] * inv, y2 = y[2] * inv;
         buf[34] = y0; buf[35] = y1; buf[36] = y2;
         yb[p * 4] = y0; yb[p * 4 + 1] = y1; yb[p * 4 + 2] = y2;
-        Lbrow[p & 7] = inv;                          // the diagonal of the block holds 1/L(j,j)
       }
       __syncwarp();
 #pragma unroll
@@ -173,33 +219,170 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
         }
         y[0] = yn[0]; y[1] = yn[1]; y[2] = yn[2];
       }
-      if ((p & 7) == 7) {
-        // invert the 8x8 lower-triangular diagonal block of this group: lane b (mod 8) solves
-        // L X(:,b) = e_b by forward substitution; Lb holds L(a,c) below and 1/L(a,a) on the diagonal.
-        __syncwarp();
-        const int bcol = lane & 7;
-        double X[8];
+    }
+  }
+  if (lane == 0) {
+    meta[0] = sigma;
+    meta[1] = (double)bad;
+  }
+}
+
+// ===========================================================================================
+// factorisation + fused forward substitution, FP64 tensor-core trailing updates (hbw <= 30)
+//
+// The 32x32 trailing window (rows / columns j..j+31, slot = index & 31, full symmetric storage) lives
+// in REGISTERS as 4x4 tiles of 8x8 in the accumulator layout of mma.sync.m8n8k4.f64: lane
+// (g = lane>>2, m = lane&3) holds rows 8tr+g, columns 8tc+2m and 8tc+2m+1 of every tile.  Columns
+// are eliminated two at a time:
+//   1. the two panel columns go through shared memory to a lanes = rows layout; two pivots
+//      (shuffle, rsqrt), the 1x1 update between them, the two columns of L            [FP64 FMA pipe]
+//   2. forward substitution of the three right-hand sides with those two columns
+//   3. the factor records (rotated, see FROT) and the 8x8 diagonal block of the column group
+//   4. the panel goes back through shared memory as mma A/B fragments (k = 2 of 4 used) and the
+//      whole window gets W -= L_panel L_panel^T as 16 independent DMMAs             [FP64 tensor pipe]
+//   5. the two retired rows and columns are refilled with rows j+32, j+33 from the staged block
+// Out-of-band entries of the window stay exactly zero (an update needs both factors non-zero).
+// ===========================================================================================
+constexpr int kMS = 36;                                  // staged row: 32 column slots + 3 right-hand sides + pad
+constexpr int kMmaWarpSmem = 32 * kMS + 64;              // staged rows + panel exchange
+
+__device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * kFacWarps + warp;
+  if (b >= A.batch) return;
+  double* fs = smem + warp * kMmaWarpSmem;
+  double* Pn = fs + 32 * kMS;
+  const int g = lane >> 2, m = lane & 3;
+  const int n = A.n, nblk = A.nblk;
+  const double* Kd = A.Kdata + b * A.nnz;
+  const double* rhs = A.rhs + b * (int64_t)n * 3;
+  double* fac = A.ws + b * A.ws_stride;
+  double* ysol = fac + (int64_t)nblk * 1024;
+  double* meta = ysol + (int64_t)nblk * 128;
+  int bad = 0;
+  const double sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
+
+  // fs[r][s] = sigma * A(R0 + r, C), C = the column with slot s among the 32 ending at row R0 + r;
+  // fs[r][32..34] = sigma * rhs(R0 + r)
+  auto stage_rows = [&](int R0) {
+    const int32_t* idxp = A.rowkidx + (int64_t)R0 * 32;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const int idx = __ldg(idxp + r * 32 + ((r - lane) & 31));
+      double v = 0.0;
+      if (idx >= 0) v = sigma * __ldg(Kd + idx);
+      else if (idx == -2) v = 1.0;
+      fs[r * kMS + lane] = v;
+    }
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    if (R0 + lane < n) {
+      const int gi = __ldg(A.iperm + R0 + lane);
+      r0 = sigma * rhs[3 * gi]; r1 = sigma * rhs[3 * gi + 1]; r2 = sigma * rhs[3 * gi + 2];
+    }
+    fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
+  };
+
+  double W[4][4][2], y[3];
+  stage_rows(0);
+  __syncwarp();
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          double sacc = 0.0;
+  for (int tr = 0; tr < 4; ++tr)
 #pragma unroll
-          for (int c = 0; c + 1 < r; c += 2) {
-            const double2 lv = *reinterpret_cast<const double2*>(Lb + r * 8 + c);
-            sacc = fma(lv.x, X[c], sacc);
-            sacc = fma(lv.y, X[c + 1], sacc);
-          }
-          if (r & 1) sacc = fma(Lb[r * 8 + r - 1], X[r - 1], sacc);
-          const double dinv = Lb[r * 8 + r];
-          X[r] = r < bcol ? 0.0 : (r == bcol ? dinv : -sacc * dinv);
-        }
-        if (lane < 8) {
-          double* fo = fb + (p - 7 + bcol) * 32;
+    for (int tc = 0; tc < 4; ++tc)
 #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (r >= bcol) fo[FROT(bcol, r - bcol)] = X[r];
-        }
-        __syncwarp();
+      for (int e = 0; e < 2; ++e) {
+        const int R = 8 * tr + g, C = 8 * tc + 2 * m + e;
+        W[tr][tc][e] = C <= R ? fs[R * kMS + C] : fs[C * kMS + R];
       }
+  y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34];
+
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * 32;
+    double* const fb = fac + (int64_t)j0 * 32;
+    double* const yb = ysol + (int64_t)j0 * 4;
+    __syncwarp();
+    stage_rows(j0 + 32);
+    __syncwarp();
+#pragma unroll
+    for (int p2 = 0; p2 < 16; ++p2) {
+      const int s0 = 2 * p2;            // slots (= columns of this block) of the panel: s0, s0 + 1
+      const int tc0 = p2 >> 2, m0 = p2 & 3;
+      // ---- 1. panel columns -> lanes = rows
+      __syncwarp();                                      // the previous panel's fragment reads of Pn are done
+      if (m == m0) {
+#pragma unroll
+        for (int tr = 0; tr < 4; ++tr)
+          *reinterpret_cast<double2*>(Pn + (8 * tr + g) * 2) = make_double2(W[tr][tc0][0], W[tr][tc0][1]);
+      }
+      __syncwarp();
+      const double2 v = *reinterpret_cast<const double2*>(Pn + 2 * lane);
+      const int d0 = (lane - s0) & 31;                 // row of this lane = j0 + s0 + d0
+      const double piv0 = __shfl_sync(kFull, v.x, s0);
+      const double inv0 = rsqrt_nr(piv0);
+      const double l0 = v.x * inv0;
+      const double c10 = __shfl_sync(kFull, l0, s0 + 1);
+      const double t1 = fma(-l0, c10, v.y);
+      const double piv1 = __shfl_sync(kFull, t1, s0 + 1);
+      const double inv1 = rsqrt_nr(piv1);
+      const double l1 = t1 * inv1;
+      bad |= !(piv0 > 0.0) | !(piv1 > 0.0);
+      // ---- 2. right-hand sides
+      const double ya0 = __shfl_sync(kFull, y[0] * inv0, s0);
+      const double ya1 = __shfl_sync(kFull, y[1] * inv0, s0);
+      const double ya2 = __shfl_sync(kFull, y[2] * inv0, s0);
+      y[0] = fma(-l0, ya0, y[0]); y[1] = fma(-l0, ya1, y[1]); y[2] = fma(-l0, ya2, y[2]);
+      const double yc0 = __shfl_sync(kFull, y[0] * inv1, s0 + 1);
+      const double yc1 = __shfl_sync(kFull, y[1] * inv1, s0 + 1);
+      const double yc2 = __shfl_sync(kFull, y[2] * inv1, s0 + 1);
+      y[0] = fma(-l1, yc0, y[0]); y[1] = fma(-l1, yc1, y[1]); y[2] = fma(-l1, yc2, y[2]);
+      if (lane == s0) { yb[s0 * 4] = ya0; yb[s0 * 4 + 1] = ya1; yb[s0 * 4 + 2] = ya2; }
+      if (lane == s0 + 1) { yb[s0 * 4 + 4] = yc0; yb[s0 * 4 + 5] = yc1; yb[s0 * 4 + 6] = yc2; }
+      // ---- 3. factor records and the diagonal block of the column group
+      // (the diagonal slot holds 1/L(j,j); chol_invdiag_kernel turns the 8x8 diagonal blocks into
+      //  their inverses afterwards)
+      fb[s0 * 32 + FROT(s0, d0)] = d0 == 0 ? inv0 : l0;
+      fb[(s0 + 1) * 32 + FROT(s0 + 1, (d0 - 1) & 31)] = d0 == 0 ? 0.0 : (d0 == 1 ? inv1 : l1);
+      // ---- 4. W -= L_panel L_panel^T on the tensor pipe (k = 2 of 4 used)
+      *reinterpret_cast<double2*>(Pn + 2 * lane) = make_double2(l0, l1);
+      __syncwarp();
+      double af[4], nf[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        af[t] = m < 2 ? Pn[(8 * t + g) * 2 + m] : 0.0;
+        nf[t] = -af[t];
+      }
+#pragma unroll
+      for (int tr = 0; tr < 4; ++tr)
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc) dmma_f(W[tr][tc][0], W[tr][tc][1], nf[tr], af[tc]);
+      // ---- 5. rows / columns j+32, j+33 enter at slots s0, s0+1
+      if ((g >> 1) == m0) {                              // tile row tc0, rows s0 + (g & 1)
+        const double* fr = fs + (s0 + (g & 1)) * kMS;
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc) {
+          const double2 w = *reinterpret_cast<const double2*>(fr + 8 * tc + 2 * m);
+          W[tc0][tc][0] = w.x;
+          W[tc0][tc][1] = w.y;
+        }
+        if (m == m0 && (g & 1) == 0) W[tc0][tc0][1] = fs[(s0 + 1) * kMS + s0];   // (s0, s0+1) mirrors (s0+1, s0)
+      }
+      if (m == m0) {                                     // tile column tc0, columns s0, s0 + 1
+#pragma unroll
+        for (int tr = 0; tr < 4; ++tr) {
+          if (!(tr == tc0 && (g >> 1) == m0)) {
+            W[tr][tc0][0] = fs[s0 * kMS + 8 * tr + g];
+            W[tr][tc0][1] = fs[(s0 + 1) * kMS + 8 * tr + g];
+          }
+        }
+      }
+      if ((lane >> 1) == p2) { y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34]; }
     }
   }
   if (lane == 0) {
@@ -497,9 +680,16 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   else if (p->hbw <= 23) { fkern = chol_factor_kernel<23>; skern = chol_subst_kernel<3>; }
   else { fkern = chol_factor_kernel<31>; skern = chol_subst_kernel<4>; }
   if (!o.reuse_factor) {
-    const size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
+    static const bool force_simt = std::getenv("FDM_CHOL_SIMT") != nullptr;   // A/B switch for profiling
+    size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
+    if (p->hbw <= 30 && !force_simt) {
+      fkern = chol_factor_mma_kernel;
+      smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
+    }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+    const int64_t items = batch * A.nblk * 4 * 8;
+    chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
   }
   const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
   FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

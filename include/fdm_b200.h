@@ -193,6 +193,23 @@ int fdm_adjoint_grads(const fdm_plan* plan, const double* d_q, const double* d_x
                       double* d_xyz_fixed_bar, int64_t batch, int64_t q_stride, int accumulate,
                       void* stream);
 
+/* ---- shape-dependent loads (tmax > 1) -------------------------------------------------------
+ * Replaces nodes_load with non-scalar edge loads in the global frame (models.py:290-344,
+ * loads.py:296-331, 407-465): line loads scaled by the edge length, half to each end node:
+ *     loads_out_n = loads_nodes_n + 1/2 sum_{e incident to n} edges_load_e |x_head - x_tail|
+ *   d_xyz (B,N,3)  d_loads_nodes (B|1,N,3)  d_edges_load (B|1,E,3)  ->  d_loads_out (B,N,3)
+ */
+int fdm_edge_loads(const fdm_plan* plan, const double* d_xyz, const double* d_loads_nodes,
+                   const double* d_edges_load, double* d_loads_out, int64_t batch,
+                   int64_t loads_stride, int64_t edges_load_stride, void* stream);
+
+/* VJP of fdm_edge_loads at the cotangent d_cot (B,N,3) of loads_out.  Outputs are OVERWRITTEN and
+ * any of them may be NULL:  xyz_bar (B,N,3) [through the edge lengths; a zero-length edge gives
+ * NaN like jnp.linalg.norm], edges_load_bar (B,E,3);  loads_nodes_bar is d_cot itself. */
+int fdm_edge_loads_vjp(const fdm_plan* plan, const double* d_xyz, const double* d_edges_load,
+                       const double* d_cot, double* d_xyz_bar, double* d_edges_load_bar,
+                       int64_t batch, int64_t edges_load_stride, void* stream);
+
 /* ---- helper used by the benchmark's loss (above the path; kept here so the timed region
  * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */
 int fdm_loss_sqdist(const double* d_x, const double* d_x0, double* d_g, double* d_loss,

@@ -285,6 +285,26 @@ int fdm_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, con
                               (cudaStream_t)stream);
 }
 
+int fdm_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
+                   double* loads_out, int64_t batch, int64_t ls, int64_t es, void* stream) {
+  if (!ready(p, "fdm_edge_loads")) return FDM_ERR_INVALID;
+  if (!xyz || !loads_nodes || !edges_load || !loads_out || batch <= 0) {
+    fdm_set_error("fdm_edge_loads: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_edge_loads(p, xyz, loads_nodes, edges_load, loads_out, batch, ls, es, (cudaStream_t)stream);
+}
+
+int fdm_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges_load, const double* cot,
+                       double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, void* stream) {
+  if (!ready(p, "fdm_edge_loads_vjp")) return FDM_ERR_INVALID;
+  if (!xyz || !edges_load || !cot || batch <= 0) {
+    fdm_set_error("fdm_edge_loads_vjp: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_edge_loads_vjp(p, xyz, edges_load, cot, xyz_bar, edges_load_bar, batch, es, (cudaStream_t)stream);
+}
+
 int fdm_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                     int64_t batch, int64_t x0_stride, void* stream) {
   if (!x || !x0 || n <= 0 || batch <= 0) {

@@ -334,6 +334,74 @@ adjoint_grads_kernel(int E, int N, int Nf, int Ns, const int32_t* __restrict__ e
 }
 
 // ---------------------------------------------------------------------------------------
+// shape-dependent loads: tributary edge line loads in the global frame (loads.py:296-331, 407-465)
+//   forward, thread per node:  out_n = loads_n + 1/2 sum_inc w_e |x_h - x_t|      (ascending edge id)
+//   reverse, thread per edge:  w_bar_e = 1/2 |v_e| (c_t + c_h)
+//            thread per node:  xyz_bar_n = sum_inc (+-) 1/2 (w_e . (c_t + c_h)) v_e / |v_e|
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+edge_loads_kernel(int N, int E, const int32_t* __restrict__ ninc_ptr, const int32_t* __restrict__ ninc_edge,
+                  const int32_t* __restrict__ ninc_other, const double* __restrict__ xyz,
+                  const double* __restrict__ loads_nodes, const double* __restrict__ edges_load,
+                  double* __restrict__ out, int64_t ls, int64_t es) {
+  const int64_t b = blockIdx.y;
+  const int n = blockIdx.x * kThreads + threadIdx.x;
+  if (n >= N) return;
+  xyz += b * (int64_t)N * 3;
+  edges_load += b * es;
+  double3 acc = make_double3(0.0, 0.0, 0.0);
+  const double3 xn = ld3(xyz, n);
+  const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
+  for (int k = k0; k < k1; ++k) {
+    const int e = __ldg(ninc_edge + k) >> 1;
+    const double3 xo = ld3(xyz, __ldg(ninc_other + k));
+    const double dx = xo.x - xn.x, dy = xo.y - xn.y, dz = xo.z - xn.z;
+    const double len = sqrt(dx * dx + dy * dy + dz * dz);
+    const double3 w = ld3(edges_load, e);
+    acc.x += w.x * len; acc.y += w.y * len; acc.z += w.z * len;
+  }
+  const double3 p = ld3(loads_nodes + b * ls, n);
+  st3(out + b * (int64_t)N * 3, n, make_double3(p.x + 0.5 * acc.x, p.y + 0.5 * acc.y, p.z + 0.5 * acc.z));
+}
+
+__global__ void __launch_bounds__(kThreads)
+edge_loads_vjp_kernel(int N, int E, const int32_t* __restrict__ edge_nodes, const int32_t* __restrict__ ninc_ptr,
+                      const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
+                      const double* __restrict__ xyz, const double* __restrict__ edges_load,
+                      const double* __restrict__ cot, double* __restrict__ xyz_bar,
+                      double* __restrict__ edges_load_bar, int64_t es) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  xyz += b * (int64_t)N * 3;
+  cot += b * (int64_t)N * 3;
+  edges_load += b * es;
+  if (t < E && edges_load_bar) {
+    const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + t);
+    const double3 a = ld3(xyz, th.x), c = ld3(xyz, th.y);
+    const double dx = c.x - a.x, dy = c.y - a.y, dz = c.z - a.z;
+    const double h = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
+    const double3 ct = ld3(cot, th.x), ch = ld3(cot, th.y);
+    st3(edges_load_bar + b * (int64_t)E * 3, t, make_double3(h * (ct.x + ch.x), h * (ct.y + ch.y), h * (ct.z + ch.z)));
+  }
+  if (t < N && xyz_bar) {
+    double3 acc = make_double3(0.0, 0.0, 0.0);
+    const double3 xn = ld3(xyz, t), cn = ld3(cot, t);
+    const int k0 = __ldg(ninc_ptr + t), k1 = __ldg(ninc_ptr + t + 1);
+    for (int k = k0; k < k1; ++k) {
+      const int e = __ldg(ninc_edge + k) >> 1, o = __ldg(ninc_other + k);
+      const double3 xo = ld3(xyz, o), co = ld3(cot, o);
+      const double3 w = ld3(edges_load, e);
+      // d len / d x_n = (x_n - x_o) / len, whichever end n is
+      const double dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z;
+      const double len = sqrt(dx * dx + dy * dy + dz * dz);
+      const double s = 0.5 * (w.x * (cn.x + co.x) + w.y * (cn.y + co.y) + w.z * (cn.z + co.z)) / len;
+      acc.x += s * dx; acc.y += s * dy; acc.z += s * dz;
+    }
+    st3(xyz_bar + b * (int64_t)N * 3, t, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // loss helper: g = x - x0, loss_b = 0.5 sum g^2   (one CTA per design, fixed-order reduction)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -441,6 +509,30 @@ int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, 
         xs_bar ? xs_bar + b0 * p->Ns * 3 : nullptr, qs, accumulate);
   }
   return fdm_check_launch("adjoint_grads");
+}
+
+int launch_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
+                      double* loads_out, int64_t batch, int64_t ls, int64_t es, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    edge_loads_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
+        (int)p->N, (int)p->E, d.ninc_ptr, d.ninc_edge, d.ninc_other, xyz + b0 * p->N * 3, loads_nodes + b0 * ls,
+        edges_load + b0 * es, loads_out + b0 * p->N * 3, ls, es);
+  }
+  return fdm_check_launch("edge_loads");
+}
+
+int launch_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges_load, const double* cot,
+                          double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  const int64_t work = std::max(p->E, p->N);
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    edge_loads_vjp_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
+        (int)p->N, (int)p->E, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, xyz + b0 * p->N * 3,
+        edges_load + b0 * es, cot + b0 * p->N * 3, xyz_bar ? xyz_bar + b0 * p->N * 3 : nullptr,
+        edges_load_bar ? edges_load_bar + b0 * p->E * 3 : nullptr, es);
+  }
+  return fdm_check_launch("edge_loads_vjp");
 }
 
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,

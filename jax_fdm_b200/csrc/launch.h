@@ -47,6 +47,10 @@ int launch_state_vjp(const fdm_plan* p, const double* q, const double* xyz, cons
 int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, const double* lam,
                          double* q_bar, double* loads_bar, double* xs_bar, int64_t batch, int64_t qs,
                          int accumulate, cudaStream_t st);
+int launch_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
+                      double* loads_out, int64_t batch, int64_t ls, int64_t es, cudaStream_t st);
+int launch_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges_load, const double* cot,
+                          double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, cudaStream_t st);
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                        int64_t batch, int64_t x0_stride, cudaStream_t st);
 

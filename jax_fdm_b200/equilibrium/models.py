@@ -13,6 +13,7 @@ Both give the same numbers; tests compare them.
 import torch
 
 from . import ops
+from .solvers import fixed_point_bwd_adjoint, solver_fixedpoint_implicit, solver_forward
 from .sparse import CSC, sparse_solve
 from .states import EquilibriumParametersState, EquilibriumState, LoadState
 
@@ -136,10 +137,85 @@ class _FusedFreePositions(torch.autograd.Function):
         return qbar, xsbar, pbar, None, None
 
 
+class _NodesLoad(torch.autograd.Function):
+    """nodes_load with tributary edge loads in the global frame (models.py:290-344, loads.py:296-331)."""
+
+    @staticmethod
+    def forward(ctx, xyz, loads_nodes, edges_load, structure):
+        ctx.structure = structure
+        ctx.save_for_backward(xyz, edges_load)
+        return ops.edge_loads(structure, xyz, loads_nodes, edges_load)
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz, edges_load = ctx.saved_tensors
+        xb, eb = ops.edge_loads_vjp(ctx.structure, xyz, edges_load, g.contiguous(),
+                                    want_xyz=ctx.needs_input_grad[0], want_edges=ctx.needs_input_grad[2])
+        return xb, g, eb, None
+
+
+class _FixedPoint(torch.autograd.Function):
+    """
+    x* = K(q)^{-1} P(x*),  P(x) = nodes_load(xyz(x))[free] - R_fixed(q, x_s): the fixed-point
+    equilibrium of models.py:512-618 as ONE node.  Forward = solver_forward with a single
+    factorisation of K reused by every iteration; backward = the implicit adjoint of
+    fixed_point.py:501-604 with the same factor:  w - J_P^T K^{-1} w = x_bar,  lam = K^{-1} w,
+    then the cotangents of f(theta, x*) = K^{-1} P(theta, x*) at w.
+    """
+
+    @staticmethod
+    def forward(ctx, q, xyz_fixed, loads_nodes, edges_load, x_init, structure, opts, config):
+        s = structure
+        K, rhs0 = ops.assemble(s, q, xyz_fixed, torch.zeros_like(loads_nodes))     # rhs0 = -R_fixed
+        ws = ops.Workspace()
+        first = [True]
+
+        def solve_fn(b):
+            x = ops.solve(s, K, b.contiguous(), workspace=ws, reuse_factor=not first[0], **opts)
+            first[0] = False
+            return x
+
+        free = torch.as_tensor(s.indices_free, device=q.device)
+
+        def f(_, x):
+            xyz = ops.positions(s, x, xyz_fixed)
+            loads = ops.edge_loads(s, xyz, loads_nodes, edges_load)
+            return solve_fn(loads.index_select(-2, free) + rhs0)
+
+        x = solver_fixedpoint_implicit(config.get("solver"), config, f, None, x_init)
+        ctx.structure, ctx.solve_fn, ctx.free = s, solve_fn, free
+        ctx.save_for_backward(q, xyz_fixed, edges_load, x)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        q, xyz_fixed, edges_load, x = ctx.saved_tensors
+        s, solve_fn, free = ctx.structure, ctx.solve_fn, ctx.free
+        xyz = ops.positions(s, x, xyz_fixed)
+
+        def scatter_free(lam):
+            c = torch.zeros(lam.shape[:-2] + (s.num_nodes, 3), dtype=lam.dtype, device=lam.device)
+            c.index_copy_(-2, free, lam)
+            return c
+
+        def loads_vjp_x(lam):                       # J_P^T lam, free rows
+            xb, _ = ops.edge_loads_vjp(s, xyz, edges_load, scatter_free(lam), want_edges=False)
+            return xb.index_select(-2, free)
+
+        w, lam = fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, g.contiguous())
+        # cotangents of f(theta, x*) at w: K and R_fixed terms (K3), then the load terms
+        qbar, pbar, xsbar = ops.adjoint_grads(s, q, xyz, lam)
+        xb, ebar = ops.edge_loads_vjp(s, xyz, edges_load, pbar)
+        fixed = torch.as_tensor(s.indices_fixed, device=q.device)
+        xsbar = xsbar + xb.index_select(-2, fixed)  # edge lengths at the supports depend on x_s
+        return qbar, xsbar, pbar, ebar, None, None, None, None
+
+
 class EquilibriumModel:
     """
-    FDM model (models.py:47-91).  Only `tmax=1` (one linear FDM step with nodal loads) runs on
-    the device path in this build; `tmax>1` raises NotImplementedError.
+    FDM model (models.py:47-91).  `tmax=1`: one linear FDM step with nodal loads.  `tmax>1`: the
+    fixed-point iteration for shape-dependent loads (edge line loads in the global frame) with the
+    implicit adjoint; face loads and local (follower) frames raise NotImplementedError.
     The dense variant assembles the same K and solves with the same kernels: the "dense" vs
     "sparse" split of the reference is a storage choice, not different arithmetic.
     """
@@ -195,11 +271,32 @@ class EquilibriumModel:
         return self.nodes_equilibrium(q, xyz_fixed, loads_nodes, structure)
 
     def nodes_load(self, xyz, load_state, structure):
+        """models.py:290-344: nodal loads plus tributary edge loads when an (E,3) edge load is present."""
         nodes_load, edges_load, faces_load = load_state
-        for extra in (edges_load, faces_load):
-            if isinstance(extra, torch.Tensor) and extra.numel() > 1:
-                raise NotImplementedError("edge/face tributary loads are outside this build (SURVEY.md §8f)")
+        if isinstance(faces_load, torch.Tensor) and faces_load.numel() > 1:
+            raise NotImplementedError("face tributary loads are outside this build (SURVEY.md §8f)")
+        if isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1:
+            if self.is_load_local:
+                raise NotImplementedError("local (follower) edge loads are outside this build (SURVEY.md §8f)")
+            return _NodesLoad.apply(xyz, nodes_load, edges_load, structure)
         return nodes_load
+
+    def equilibrium_iterative_xyz(self, q, xyz_fixed, load_state, structure, xyz_free_init=None, tmax=100,
+                                  eta=1e-6, solver=None, implicit_diff=True, verbose=False):
+        """models.py:512-618."""
+        if not implicit_diff:
+            raise NotImplementedError("unrolled differentiation of the fixed point is not built; use implicit_diff=True")
+        if xyz_free_init is None:
+            xyz_free_init = self.equilibrium(q, xyz_fixed, load_state.nodes, structure)
+        edges_load = load_state.edges
+        if not (isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1):
+            edges_load = torch.zeros((structure.num_edges, 3), dtype=q.dtype, device=q.device)
+        if isinstance(load_state.faces, torch.Tensor) and load_state.faces.numel() > 1:
+            raise NotImplementedError("face tributary loads are outside this build (SURVEY.md §8f)")
+        config = {"tmax": tmax, "eta": eta, "verbose": verbose, "solver": solver or self.itersolve_fn}
+        self.last_solver_config = config
+        return _FixedPoint.apply(q, xyz_fixed, load_state.nodes, edges_load, xyz_free_init.detach(), structure,
+                                 self.solve_opts, config)
 
     def equilibrium_state(self, q, xyz, loads_nodes, structure):
         vectors, lengths, forces, residuals = _State.apply(q, xyz, loads_nodes, structure)
@@ -210,9 +307,13 @@ class EquilibriumModel:
         q, xyz_fixed, load_state = params
         if not isinstance(load_state, LoadState):
             load_state = LoadState(load_state)
-        if self.tmax > 1:
-            raise NotImplementedError("tmax > 1 (shape-dependent loads) is outside this build; use tmax=1")
         xyz_free = self.equilibrium(q, xyz_fixed, load_state.nodes, structure)
+        if self.tmax > 1:                                  # models.py:449-465
+            if self.iterload_fn is not None:
+                load_state = self.iterload_fn(load_state)
+            xyz_free = self.equilibrium_iterative_xyz(q, xyz_fixed, load_state, structure, xyz_free_init=xyz_free,
+                                                      tmax=self.tmax, eta=self.eta, solver=self.itersolve_fn,
+                                                      implicit_diff=self.implicit_diff, verbose=self.verbose)
         xyz = self.nodes_positions(xyz_free, xyz_fixed, structure)
         load_nodes = self.nodes_load(xyz, load_state, structure)
         return self.equilibrium_state(q, xyz, load_nodes, structure)

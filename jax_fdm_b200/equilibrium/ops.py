@@ -240,6 +240,44 @@ def adjoint_grads(structure, q, xyz, lam, q_bar=None, loads_bar=None, xyz_fixed_
     return q_bar, loads_bar, xyz_fixed_bar
 
 
+def edge_loads(structure, xyz, loads_nodes, edges_load):
+    """nodes_load with tributary edge line loads, global frame (models.py:290-344, loads.py:296-331, 407-465)."""
+    s = structure
+    E, N = s.num_edges, s.num_nodes
+    xyz = _chk(xyz, "xyz", (N, 3))
+    loads_nodes = _chk(loads_nodes, "loads_nodes", (N, 3))
+    edges_load = _chk(edges_load, "edges_load", (E, 3))
+    B, batched = _resolve_batch((xyz, 2), (loads_nodes, 2), (edges_load, 2))
+    if batched and xyz.dim() == 2:
+        xyz = xyz.expand(B, N, 3).contiguous()
+    out = torch.empty(((B,) if batched else ()) + (N, 3), dtype=F64, device=xyz.device)
+    L.check(L.lib().fdm_edge_loads(s.plan, _ptr(xyz), _ptr(loads_nodes), _ptr(edges_load), _ptr(out), B,
+                                   _stride(loads_nodes, 2), _stride(edges_load, 2), _stream()))
+    return out
+
+
+def edge_loads_vjp(structure, xyz, edges_load, cot, want_xyz=True, want_edges=True):
+    """VJP of `edge_loads` -> (xyz_bar, edges_load_bar); the cotangent of loads_nodes is `cot` itself."""
+    s = structure
+    E, N = s.num_edges, s.num_nodes
+    xyz = _chk(xyz, "xyz", (N, 3))
+    edges_load = _chk(edges_load, "edges_load", (E, 3))
+    cot = _chk(cot, "cot", (N, 3))
+    B, batched = _resolve_batch((xyz, 2), (cot, 2))
+    if batched and xyz.dim() == 2:
+        xyz = xyz.expand(B, N, 3).contiguous()
+    if batched and cot.dim() == 2:
+        cot = cot.expand(B, N, 3).contiguous()
+    lead = (B,) if batched else ()
+    xyz_bar = torch.empty(lead + (N, 3), dtype=F64, device=xyz.device) if want_xyz else None
+    e_bar = torch.empty(lead + (E, 3), dtype=F64, device=xyz.device) if want_edges else None
+    L.check(L.lib().fdm_edge_loads_vjp(s.plan, _ptr(xyz), _ptr(edges_load), _ptr(cot), _ptr(xyz_bar), _ptr(e_bar), B,
+                                       _stride(edges_load, 2), _stream()))
+    if e_bar is not None and batched and edges_load.dim() == 2:
+        e_bar = e_bar.sum(0)            # one edge load shared by the batch: its cotangent sums over designs
+    return xyz_bar, e_bar
+
+
 def loss_sqdist(x, x0):
     """loss_b = 0.5 * sum (x - x0)^2 per design, g = x - x0 (benchmark loss)."""
     x = x.contiguous()

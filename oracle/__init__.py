@@ -38,4 +38,6 @@ from .model import (  # noqa: F401
     sparse_solve_bwd,
     forward,
     forward_adjoint,
+    nodes_load_edges,
+    fixed_point_forward,
 )

@@ -196,3 +196,44 @@ def forward_adjoint(q, xyz_fixed, loads, s, cot_fn):
 
     return dict(state=state, x_free=xf, lam=lam, q_bar=qbar,
                 xyz_fixed_bar=xsbar, loads_bar=pbar)
+
+
+# ----------------------------------------------------------------------------
+# shape-dependent loads and the fixed-point equilibrium (tmax > 1)
+# ----------------------------------------------------------------------------
+
+def nodes_load_edges(xyz, loads_nodes, edges_load, s):
+    """
+    models.py:290-344 with loads.py:296-331, 407-465 (global frame): line loads times edge length,
+    half to each end node, added to the nodal loads.
+    """
+    ei = s.edges_indexed
+    lengths = np.linalg.norm(xyz[ei[:, 1]] - xyz[ei[:, 0]], axis=1, keepdims=True)
+    total = np.asarray(edges_load, dtype=np.float64) * lengths
+    out = np.array(loads_nodes, dtype=np.float64, copy=True)
+    np.add.at(out, ei[:, 0], 0.5 * total)
+    np.add.at(out, ei[:, 1], 0.5 * total)
+    return out
+
+
+def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=1e-6):
+    """
+    models.py:410-478, 512-618 + fixed_point.py:139-198: one linear step with the nodal loads, then
+    x <- K^{-1} (nodes_load(xyz(x))[free] - R_fixed) until the mean nodal move <= eta or tmax steps.
+    Returns (x_free, steps).  The reference re-solves with SuperLU every iteration; so does this.
+    """
+    K = stiffness_matrix_sparse(q, s)
+    r_fixed = residual_fixed_matrix(q, xyz_fixed, s)
+
+    def f(x):
+        xyz = nodes_positions(x, xyz_fixed, s)
+        p = nodes_load_edges(xyz, loads_nodes, edges_load, s)[s.indices_free, :] - r_fixed
+        return sparse_solve(K, p)
+
+    x_prev = sparse_solve(K, np.asarray(loads_nodes)[s.indices_free, :] - r_fixed)
+    x = f(x_prev)
+    steps = 0
+    while steps < tmax and np.mean(np.linalg.norm(x_prev - x, axis=1)) > eta:
+        x_prev, x = x, f(x)
+        steps += 1
+    return x, steps

@@ -1,0 +1,111 @@
+"""
+tmax > 1 on the GPU: fixed-point equilibrium with shape-dependent (tributary edge) loads and its
+implicit adjoint, against the CPU oracle (models.py:410-478, 512-618; fixed_point.py:139-240,
+501-604; loads.py:296-331, 407-465).
+
+Forward parity: <= 1e-10 relative on x* (both iterate to a tight eta).  Gradient parity: the
+reference pins its implicit adjoint against unrolled AD at 1e-7 (tests/test_taylor_convergence.py:
+265-304); JAX cannot run here, so the implicit gradients are checked against central finite
+differences of the ORACLE's forward solve at 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from jax_fdm_b200 import datasets  # noqa: E402
+
+
+def T(a, grad=False):
+    t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=torch.device("cuda", 0))
+    return t.requires_grad_(True) if grad else t
+
+
+def problem(nx=6, seed=5):
+    prob = datasets.cablenet_problem(nx, seed=seed)
+    rng = np.random.default_rng(seed)
+    E = prob.edges.shape[0]
+    edges_load = np.zeros((E, 3))
+    edges_load[:, 2] = -0.05 * rng.uniform(0.5, 1.5, size=E)       # self-weight-like line load
+    edges_load[:, 0] = 0.01 * rng.standard_normal(E)
+    return prob, edges_load
+
+
+def oracle_loss(q, xs, loads, eload, so, x0):
+    x, steps = oracle.fixed_point_forward(q, xs, loads, eload, so, tmax=200, eta=1e-13)
+    xyz = oracle.nodes_positions(x, xs, so)
+    ei = so.edges_indexed
+    lengths = np.linalg.norm(xyz[ei[:, 1]] - xyz[ei[:, 0]], axis=1)
+    return 0.5 * np.sum((xyz - x0) ** 2) + 0.1 * np.sum(lengths ** 2), x, steps
+
+
+@pytest.mark.parametrize("solver", ["cholesky", "pcg"])
+def test_fixed_point_forward_and_implicit_gradients(solver):
+    import jax_fdm_b200.equilibrium as eq
+
+    prob, eload = problem()
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    x0 = prob.xyz0
+
+    q, xs, p, w = T(prob.q, True), T(prob.xyz_fixed, True), T(prob.loads, True), T(eload, True)
+    model = eq.EquilibriumModelSparse(tmax=200, eta=1e-13, solver=solver, tol=1e-14)
+    state = model(eq.EquilibriumParametersState(q, xs, eq.LoadState(p, w, 0.0)), s)
+    loss = 0.5 * ((state.xyz - T(x0)) ** 2).sum() + 0.1 * (state.lengths ** 2).sum()
+    loss.backward()
+
+    ref_loss, x_ref, steps = oracle_loss(prob.q, prob.xyz_fixed, prob.loads, eload, so, x0)
+    assert 1 < steps < 200, "the oracle's fixed point must converge in a few iterations"
+    assert model.last_solver_config["steps"] > 1
+    xf = state.xyz.detach().cpu().numpy()[so.indices_free]
+    assert np.abs(xf - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
+    assert abs(loss.item() - ref_loss) <= 1e-10 * abs(ref_loss)
+    # loads reported by the state include the tributary edge loads at the converged geometry
+    xyz_ref = oracle.nodes_positions(x_ref, prob.xyz_fixed, so)
+    loads_ref = oracle.nodes_load_edges(xyz_ref, prob.loads, eload, so)
+    assert np.abs(state.loads.detach().cpu().numpy() - loads_ref).max() <= 1e-10 * np.abs(loads_ref).max()
+
+    rng = np.random.default_rng(0)
+
+    def fd(arr, make_args, n_probe=6, eps=1e-6):
+        out = []
+        flat_idx = rng.choice(arr.size, size=min(n_probe, arr.size), replace=False)
+        for k in flat_idx:
+            d = np.zeros(arr.size)
+            d[k] = eps * max(1.0, abs(arr.flat[k]))
+            d = d.reshape(arr.shape)
+            lp = oracle_loss(*make_args(arr + d), so, x0)[0]
+            lm = oracle_loss(*make_args(arr - d), so, x0)[0]
+            out.append((k, (lp - lm) / (2 * d.flat[k])))
+        return out
+
+    checks = [
+        (q.grad, prob.q, lambda a: (a, prob.xyz_fixed, prob.loads, eload)),
+        (xs.grad, prob.xyz_fixed, lambda a: (prob.q, a, prob.loads, eload)),
+        (p.grad, prob.loads, lambda a: (prob.q, prob.xyz_fixed, a, eload)),
+        (w.grad, eload, lambda a: (prob.q, prob.xyz_fixed, prob.loads, a)),
+    ]
+    for grad, arr, mk in checks:
+        gnp = grad.cpu().numpy()
+        scale = np.abs(gnp).max()
+        for k, ref in fd(arr, mk):
+            assert abs(gnp.flat[k] - ref) <= 1e-6 * scale + 1e-9, (k, gnp.flat[k], ref)
+
+
+def test_tmax1_ignores_edge_loads_in_the_solve_but_reports_them():
+    """models.py:447, 475-478: with tmax = 1 edge loads do not enter the solve
+    but are added to the reported loads / residuals."""
+    import jax_fdm_b200.equilibrium as eq
+
+    prob, eload = problem()
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    model = eq.EquilibriumModelSparse(tmax=1)
+    st = model(eq.EquilibriumParametersState(T(prob.q), T(prob.xyz_fixed), eq.LoadState(T(prob.loads), T(eload), 0.0)), s)
+    _, xf = oracle.forward(prob.q, prob.xyz_fixed, prob.loads, so)
+    xyz = oracle.nodes_positions(xf, prob.xyz_fixed, so)
+    assert np.abs(st.xyz.cpu().numpy() - xyz).max() <= 1e-10 * np.abs(xyz).max()
+    loads_ref = oracle.nodes_load_edges(xyz, prob.loads, eload, so)
+    assert np.abs(st.loads.cpu().numpy() - loads_ref).max() <= 1e-12 * np.abs(loads_ref).max()

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libfdm_b200.so")
+# FDM_B200_LIB: alternative build of the same library (e.g. the -DFDM_PCG2_PROFILE diagnostics build)
+LIB_PATH = os.environ.get("FDM_B200_LIB") or os.path.join(HERE, "lib", "libfdm_b200.so")
 
 # ---- constants mirrored from include/fdm_b200.h ----
 FDM_OK = 0

@@ -1,0 +1,98 @@
+"""
+Batched band Cholesky across the shapes its kernels specialise on (solver_chol_warp.cu /
+solver_chol.cu): half bandwidth 1 .. 31 (FP64 tensor-core factor kernel up to 30, register
+rank-1 kernel at 31, one template per 8 of bandwidth for the substitution kernel), orders that
+are / are not multiples of 32 and smaller than one window, batch sizes that do not fill a CTA,
+forward solve + adjoint solve with the stored factor, K = +SPD and K = -SPD, and the
+one-CTA-per-design kernel for bands wider than 31.  Checked against the CPU oracle (SuperLU).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from jax_fdm_b200 import datasets  # noqa: E402
+
+
+def T(a):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=torch.device("cuda", 0))
+
+
+def strip_problem(nx, ny, sign, seed):
+    """nx x ny quads, all boundary vertices fixed -> (nx-1)(ny-1) free nodes, half bandwidth min(nx,ny)-1."""
+    m = datasets.meshgrid(nx, ny=ny)
+    w = nx + 1
+    i, j = np.divmod(np.arange(m.nodes.size), w)
+    supports = ((i == 0) | (i == ny) | (j == 0) | (j == nx)).astype(np.int64)
+    rng = np.random.default_rng(seed)
+    q = sign * rng.uniform(0.5, 2.0, size=m.edges.shape[0])
+    xyz = m.xyz.copy()
+    xyz[:, 2] = 0.3 * np.sin(xyz[:, 0]) * np.cos(xyz[:, 1])
+    loads = np.zeros_like(xyz)
+    loads[:, 2] = -0.1
+    loads[:, 0] = 0.02
+    return m, supports, q, xyz[np.flatnonzero(supports)], loads
+
+
+@pytest.mark.parametrize("nx,ny,batch,sign", [
+    (3, 2, 1, 1.0),      # 2 free nodes, hbw 1
+    (9, 4, 3, -1.0),     # hbw 3   (subst template 1)
+    (40, 9, 5, 1.0),     # hbw 8   (template 2), n = 312
+    (33, 17, 9, -1.0),   # hbw 16  (template 3), n = 512 = 16 * 32
+    (12, 25, 2, 1.0),    # hbw 11, n = 264
+    (31, 40, 11, 1.0),   # hbw 30  (largest tensor-core case)
+    (32, 34, 4, -1.0),   # hbw 31  (rank-1 register kernel)
+])
+def test_band_cholesky_forward_and_stored_factor(nx, ny, batch, sign):
+    import jax_fdm_b200.equilibrium as eq
+
+    m, supports, q, xs, loads = strip_problem(nx, ny, sign, seed=nx * 100 + ny)
+    s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
+    so = oracle.build_structure(m.nodes, m.edges, supports)
+    assert s.half_bandwidth == min(nx, ny) - 1
+    rng = np.random.default_rng(7)
+    qb = q[None, :] * rng.uniform(0.8, 1.25, size=(batch, q.size))
+    K, rhs = eq.ops.assemble(s, T(qb), T(xs), T(loads))
+    ws = eq.ops.Workspace()
+    x, info = eq.ops.solve(s, K, rhs, solver="cholesky", return_info=True, workspace=ws)
+    assert (info[:, 0] == 0).all() and (info[:, 3] == sign).all()
+    g = rng.standard_normal((batch, s.num_free, 3))
+    lam = eq.ops.solve(s, K, T(g), solver="cholesky", workspace=ws, reuse_factor=True)
+    for b in range(batch):
+        Kb = oracle.stiffness_matrix_sparse(qb[b], so)
+        xo = oracle.sparse_solve(Kb, oracle.load_matrix(qb[b], xs, loads, so))
+        lo = oracle.sparse_solve(Kb, g[b])
+        assert np.abs(x[b].cpu().numpy() - xo).max() <= 1e-10 * np.abs(xo).max()
+        assert np.abs(lam[b].cpu().numpy() - lo).max() <= 1e-10 * np.abs(lo).max()
+
+
+def test_indefinite_design_is_flagged_not_solved():
+    import jax_fdm_b200.equilibrium as eq
+
+    m, supports, q, xs, loads = strip_problem(9, 6, 1.0, seed=3)
+    s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
+    qb = np.stack([q, q * np.where(np.arange(q.size) % 2, -1.0, 1.0), q])
+    K, rhs = eq.ops.assemble(s, T(qb), T(xs), T(loads))
+    _, info = eq.ops.solve(s, K, rhs, solver="cholesky", return_info=True)
+    st = info[:, 0].cpu().numpy()
+    assert st[0] == 0 and st[2] == 0 and st[1] == 2        # FDM_STATUS_INDEFINITE for the mixed-sign design only
+
+
+def test_band_too_wide_is_refused_and_auto_uses_pcg():
+    """hbw = 32, n = 1024: neither band kernel applies (295 KB of band > shared memory): the Cholesky
+    solver returns FDM_ERR_UNSUPPORTED and the automatic choice is an iterative solver."""
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200._lib import FdmError
+
+    m, supports, q, xs, loads = strip_problem(33, 33, 1.0, seed=1)
+    s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
+    so = oracle.build_structure(m.nodes, m.edges, supports)
+    K, rhs = eq.ops.assemble(s, T(q), T(xs), T(loads))
+    with pytest.raises(FdmError) as e:
+        eq.ops.solve(s, K, rhs, solver="cholesky")
+    assert e.value.code == -5
+    x, info = eq.ops.solve(s, K, rhs, solver="auto", tol=1e-13, return_info=True)
+    xo = oracle.sparse_solve(oracle.stiffness_matrix_sparse(q, so), oracle.load_matrix(q, xs, loads, so))
+    assert info[0, 0] == 0 and np.abs(x.cpu().numpy() - xo).max() <= 1e-10 * np.abs(xo).max()

@@ -441,7 +441,8 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
                      "share_of_step": dom["ms"] / ms_per_step},
         "kernels": kernels,
-        "wall_s_timed_region": wall, "solve_status_ok": status_ok,
+        "wall_s_timed_region": wall,
+        "solve_status_ok": status_ok and (single is None or single["status"] == [0, 0]),
         "single_mesh": single,
     }
     if fixed:

@@ -69,7 +69,7 @@ int fdm_plan_create_host(const int64_t* h_edges, int64_t num_edges, int64_t num_
   *out = nullptr;
   fdm_plan* p = new (std::nothrow) fdm_plan();
   if (!p) return FDM_ERR_INVALID;
-  int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, 144);
+  int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, 148);
   if (rc != FDM_OK) {
     delete p;
     return rc;
@@ -95,8 +95,8 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
   if (!p) return FDM_ERR_INVALID;
   p->device = device;
   p->sm_count = sms;
-  int parts = sms > 16 ? sms - 4 : sms;   // the persistent PCG keeps 4 SMs for its coarse-problem CTAs
-  if (const char* e = std::getenv("FDM_PCG2_PARTS")) parts = std::max(2, std::min(sms - 4, std::atoi(e)));
+  int parts = sms;
+  if (const char* e = std::getenv("FDM_PCG2_PARTS")) parts = std::max(2, std::min(sms, std::atoi(e)));
   int rc = build_host(p, h_edges, num_edges, num_nodes, h_supports, parts);
   if (rc == FDM_OK) {
     DeviceArrays& d = p->d;

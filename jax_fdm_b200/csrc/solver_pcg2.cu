@@ -11,19 +11,10 @@
 //
 // Preconditioner: M^-1 = D^-1 + P Ac^-1 P^T  (Jacobi + piecewise-constant coarse correction,
 // Ac = P^T K P is PxP, inverted once per K by a small kernel and reused by the adjoint solve).
-// The iteration is the Chronopoulos-Gear form of PCG (mathematically the same iterates): with
-// z = M^-1 r and w = K z,   gamma = <r,z>, delta = <w,z>,  beta = gamma/gamma_old,
-// alpha = gamma / (delta - beta gamma / alpha_old),  p = z + beta p,  s = w + beta s (= K p),
-// x += alpha p,  r -= alpha s.  Both inner products are taken at the same point, and the coarse
-// residual P^T r is carried by recurrence (P^T s = P^T w + beta P^T s_old, P^T r -= alpha P^T s).
-//
-// Roles: P WORKER CTAs own the aggregates; kRoots ROOT CTAs (no rows) own the coarse problem.
-// Per iteration a worker publishes ONE record { <r,z>_c, <w,z>_c, <r,r>_c, (P^T w)_c } (12 doubles)
-// and reads ONE mailbox { alpha, beta, the coarse correction yc of its aggregate, flag }; a root
-// reads the P records, forms the scalars, advances the coarse residual and multiplies its rows of
-// Ac^-1 into it.  Traffic per iteration is ~P*(192+160) bytes per root instead of P^2 records when
-// every CTA gathered everything -- on 148 SMs that all-gather alone cost ~10k cycles per iteration
-// in L2 request traffic.  The boundary values of z go neighbour to neighbour before the SpMV.
+// The coarse residual P^T r is carried by recurrence (P^T r -= alpha P^T A p), so one CG
+// iteration needs exactly two grid-wide exchanges:
+//   A: all-gather { <p,Ap>_c [3],  (P^T A p)_c [3] }                      -> alpha, coarse residual
+//   B: all-gather { <r,z>_c [3], <r,r>_c [3] } + boundary values of z     -> beta, halo of p
 // Exchanges are flag-in-data ("LL"): every double travels as two 8-byte words {32 payload bits,
 // 32-bit tag}; readers poll the words themselves, so an exchange costs one L2 round trip with
 // no fence, no atomic and no separate barrier.  All CTAs reduce the gathered partials in the
@@ -37,7 +28,7 @@
 #include "launch.h"
 
 // -DFDM_PCG2_PROFILE: CTA 0 accumulates clock64() per phase and writes the totals after the info
-// record (slots 4..7: coarse solve + z, halo hand-over, SpMV, all-gather); off in the shipped build.
+// record (slots 4..7: coarse+z, exchange B, halo+SpMV, exchange A); off in the shipped build.
 #ifdef FDM_PCG2_PROFILE
 #define PROF(...) __VA_ARGS__
 #else
@@ -48,10 +39,7 @@ namespace {
 
 constexpr int kThreads = 512;
 constexpr int kMaxRowsPerThread = 4;
-constexpr int kVals = 12;              // doubles per worker record
-constexpr int kMail = 12;              // LL slots per mailbox: alpha[3] beta[3] yc[3] flag, 2 spare
-constexpr int kRoots = 4;              // CTAs that own the coarse problem
-enum { F_CONTINUE = 0, F_CONVERGED = 1, F_MAXIT = 2, F_BREAKDOWN = 3, F_ZERO = 4 };
+constexpr int kVals = 8;               // doubles per CTA record in every exchange
 
 struct Pcg2Device {
   int P = 0, nmax = 0, emax = 0, hmax = 0, xmax = 0, rows_per_thread = 1;
@@ -79,10 +67,10 @@ struct Pcg2Args {
   double* x;
   double* info;
   double* ainv;          // (P,P) workspace
-  uint64_t* xS;          // (P, 8) LL slots: start-up records
-  uint64_t* xR;          // (2, P, kVals) LL slots: iteration records, double buffered by parity
-  uint64_t* xM;          // (P, kMail) LL slots: mailboxes root -> worker
-  uint64_t* xE;          // (total_exports, 3) LL slots: boundary values of z
+  uint64_t* xS;          // (P, kVals, 2) LL words
+  uint64_t* xA;
+  uint64_t* xB;
+  uint64_t* xE;          // (total_exports, 3, 2) LL words
   double tol2;
   int max_iters;
 };
@@ -110,7 +98,7 @@ __device__ __forceinline__ double ll_load(const uint64_t* slot, uint32_t tag) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) pcg2_setup_kernel(Pcg2Args a, size_t xwords) {
   if (blockIdx.x > 0) {
-    // exchange buffers are contiguous: xS | xR | xM | xE
+    // exchange buffers are contiguous: xS | xA | xB | xE
     const size_t per = (xwords + gridDim.x - 2) / (gridDim.x - 1);
     const size_t lo = (size_t)(blockIdx.x - 1) * per, hi = min(xwords, lo + per);
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) a.xS[i] = 0ull;
@@ -216,130 +204,11 @@ __device__ __forceinline__ double poll_column(const uint64_t* buf, int V, int co
   return sum;
 }
 
-// ------------------------------------------------------------------------------------------
-// root CTA: scalars, coarse residual recurrence, coarse solve for its workers
-// ------------------------------------------------------------------------------------------
-__device__ void pcg2_root(const Pcg2Args& a, unsigned char* smem_raw) {
-  const Pcg2Device& d = a.d;
-  const int P = d.P, root = blockIdx.x - P;
-  const int w0 = (int)((long long)root * P / kRoots), w1 = (int)((long long)(root + 1) * P / kRoots), nown = w1 - w0;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  double* s_ainv = (double*)smem_raw;                 // rows w0..w1 of Ac^-1   [nown][P]
-  double* s_rc = s_ainv + (size_t)nown * P;           // P^T r                   [P][3]
-  double* s_cs = s_rc + 3 * P;                        // P^T s                   [P][3]
-  double* s_cw = s_cs + 3 * P;                        // gathered P^T w          [P][3]
-  double* s_yc = s_cw + 3 * P;                        // coarse corrections      [nown][3]
-  double* s_sc = s_yc + 3 * nown;                     // scalars                 [32]
-  for (int i = tid; i < nown * P; i += kThreads) s_ainv[i] = a.ainv[(size_t)w0 * P + i];
-  for (int i = tid; i < 3 * P; i += kThreads) { s_cs[i] = 0.0; s_cw[i] = 0.0; }
-
-  // yc[w][q] = Ainv[w,:] . rc[:,q] for the own workers; four threads per dot product
-  auto coarse_solve = [&]() {
-    for (int idx = tid; idx < ((nown * 12 + 31) & ~31); idx += kThreads) {
-      const int wl = idx / 12, q = (idx >> 2) % 3, seg = idx & 3;
-      double v = 0.0;
-      if (wl < nown) {
-        const int j0 = seg * ((P + 3) >> 2), j1 = min(P, j0 + ((P + 3) >> 2));
-        const double* ar = s_ainv + (size_t)wl * P;
-        for (int j = j0; j < j1; ++j) v += ar[j] * s_rc[j * 3 + q];
-      }
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
-      if (wl < nown && seg == 0) s_yc[wl * 3 + q] = v;
-    }
-  };
-
-  // ---- start-up: coarse residual of r0 = b, ||b||^2, sign census ----
-  if (warp < 8) {
-    const double sum = poll_column(a.xS, 8, warp, 1u, P, warp < 3 ? s_rc : nullptr, 3, warp);
-    if (lane == 0) s_sc[warp] = sum;          // [3..5] = bb, [6] = npos, [7] = nneg
-  }
-  __syncthreads();
-  const double bb0 = s_sc[3], bb1 = s_sc[4], bb2 = s_sc[5];
-  const bool indefinite = s_sc[6] > 0.0 && s_sc[7] > 0.0;
-  const double sign = s_sc[7] > 0.0 && s_sc[6] == 0.0 ? -1.0 : 1.0;
-  const bool zero_rhs = (bb0 == 0.0 && bb1 == 0.0 && bb2 == 0.0);
-  coarse_solve();
-  __syncthreads();
-  for (int t = tid; t < nown * 4; t += kThreads) {
-    const int wl = t >> 2, f = t & 3;
-    const double v = f < 3 ? s_yc[wl * 3 + f] : (zero_rhs ? (double)F_ZERO : (double)F_CONTINUE);
-    ll_store(a.xM + ((size_t)(w0 + wl) * kMail + 6 + f) * 2, v, 1u);
-  }
-
-  double gam_old[3] = {0.0, 0.0, 0.0}, alpha_old[3] = {0.0, 0.0, 0.0};
-  double rr[3] = {bb0, bb1, bb2};
-  int it = 0;
-  int status = indefinite ? FDM_STATUS_INDEFINITE : FDM_STATUS_OK;
-  while (!zero_rhs) {
-    const uint32_t tag = (uint32_t)it + 1u;
-    const uint64_t* xRb = a.xR + (size_t)(it & 1) * P * kVals * 2;
-    __syncthreads();                          // s_sc / s_cw of the previous iteration are consumed
-    if (warp < kVals) {
-      const double sum = poll_column(xRb, kVals, warp, tag, P, warp >= 9 ? s_cw : nullptr, 3, warp - 9);
-      if (lane == 0) s_sc[12 + warp] = sum;   // [12..14] = <r,z>, [15..17] = <w,z>, [18..20] = <r,r>
-    }
-    __syncthreads();
-    double gam[3], beta[3] = {0.0, 0.0, 0.0}, alpha[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { gam[q] = s_sc[12 + q]; rr[q] = s_sc[18 + q]; }
-    int flag = F_CONTINUE;
-    if (rr[0] <= a.tol2 * bb0 && rr[1] <= a.tol2 * bb1 && rr[2] <= a.tol2 * bb2) flag = F_CONVERGED;
-    else if (!(isfinite(gam[0]) && isfinite(gam[1]) && isfinite(gam[2]))) { flag = F_BREAKDOWN; status = FDM_STATUS_BREAKDOWN; }
-    else if (it >= a.max_iters) { flag = F_MAXIT; status = FDM_STATUS_NOT_CONVERGED; }
-    if (flag == F_CONTINUE) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double del = s_sc[15 + q];
-        beta[q] = (it > 0 && gam_old[q] != 0.0) ? gam[q] / gam_old[q] : 0.0;
-        const double den = del - ((it > 0 && alpha_old[q] != 0.0) ? beta[q] * gam[q] / alpha_old[q] : 0.0);
-        alpha[q] = den != 0.0 ? gam[q] / den : 0.0;
-        gam_old[q] = gam[q];
-        alpha_old[q] = alpha[q];
-      }
-      // coarse recurrences: P^T s = P^T w + beta P^T s ; P^T r -= alpha P^T s
-      for (int i = tid; i < 3 * P; i += kThreads) {
-        const int q = i % 3;
-        const double cs = s_cw[i] + beta[q] * s_cs[i];
-        s_cs[i] = cs;
-        s_rc[i] -= alpha[q] * cs;
-      }
-      __syncthreads();
-      coarse_solve();
-      __syncthreads();
-    }
-    for (int t = tid; t < nown * 10; t += kThreads) {
-      const int wl = t / 10, f = t - 10 * wl;
-      const double v = f < 3 ? alpha[f] : (f < 6 ? beta[f - 3] : (f < 9 ? s_yc[wl * 3 + f - 6] : (double)flag));
-      ll_store(a.xM + ((size_t)(w0 + wl) * kMail + f) * 2, v, tag + 1u);
-    }
-    if (flag != F_CONTINUE) break;
-    ++it;
-  }
-  if (root == 0 && tid == 0 && a.info) {
-    double rel = 0.0;
-    const double bb[3] = {bb0, bb1, bb2};
-    for (int q = 0; q < 3; ++q)
-      if (bb[q] > 0.0) rel = fmax(rel, sqrt(rr[q] / bb[q]));
-    a.info[FDM_INFO_STATUS] = (double)status;
-    a.info[FDM_INFO_ITERS] = (double)it;
-    a.info[FDM_INFO_RELRES] = rel;
-    a.info[FDM_INFO_SIGN] = sign;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// the solver: CTAs 0..P-1 are workers, P..P+kRoots-1 roots
-// ------------------------------------------------------------------------------------------
 template <int R>
 __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Pcg2Device& d = a.d;
   const int c = blockIdx.x, P = d.P;
-  if (c >= P) {
-    pcg2_root(a, smem_raw);
-    return;
-  }
   const int r0 = d.row_off[c], n = d.row_off[c + 1] - r0;
   const int e0 = d.ent_off[c], ne = d.ent_off[c + 1] - e0;
   const int h0 = d.halo_off[c], nh = d.halo_off[c + 1] - h0;
@@ -350,9 +219,12 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
   unsigned char* sp = smem_raw;
   auto take = [&](size_t bytes) { unsigned char* p = sp; sp += (bytes + 15) & ~size_t(15); return p; };
   double* s_val = (double*)take(sizeof(double) * d.emax);
-  double* s_z = (double*)take(sizeof(double) * 3 * (d.nmax + d.hmax));   // [rhs][own | halo]
+  double* s_p = (double*)take(sizeof(double) * 3 * (d.nmax + d.hmax));   // [rhs][own | halo]
   double* s_part = (double*)take(sizeof(double) * kVals * kThreads);     // per-thread partials
-  double* s_sc = (double*)take(sizeof(double) * 32);                     // mailbox contents
+  double* s_rc = (double*)take(sizeof(double) * P * 3);                  // coarse residual [P][3]
+  double* s_cap = (double*)take(sizeof(double) * P * 3);                 // gathered P^T A p [P][3]
+  double* s_ainv = (double*)take(sizeof(double) * P);                    // row c of Ac^-1
+  double* s_sc = (double*)take(sizeof(double) * 32);                     // scalars
   int32_t* s_rowptr = (int32_t*)take(sizeof(int32_t) * (d.nmax + 1));
   int32_t* s_halo_src = (int32_t*)take(sizeof(int32_t) * d.hmax);
   uint16_t* s_col = (uint16_t*)take(sizeof(uint16_t) * d.emax);
@@ -365,9 +237,11 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
     s_val[i] = __ldg(a.Kdata + __ldg(d.lkidx + e0 + i));
   }
   for (int i = tid; i < nh; i += kThreads) s_halo_src[i] = d.halo_src[h0 + i];
-  for (int i = tid; i < 3 * pstride; i += kThreads) s_z[i] = 0.0;
+  for (int i = tid; i < P; i += kThreads) s_ainv[i] = a.ainv[(size_t)c * P + i];
+  for (int i = tid; i < 3 * pstride; i += kThreads) s_p[i] = 0.0;
+  for (int i = tid; i < 3 * P; i += kThreads) s_cap[i] = 0.0;
 
-  double x[R][3], r[R][3], w[R][3], pv[R][3], sv[R][3], dinv[R], diag[R];
+  double x[R][3], r[R][3], w[R][3], dinv[R], diag[R];
   int expslot[R];
   double acc[kVals];
 #pragma unroll
@@ -378,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
     expslot[j] = -1;
     dinv[j] = 0.0; diag[j] = 0.0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) { x[j][q] = 0.0; r[j][q] = 0.0; w[j][q] = 0.0; pv[j][q] = 0.0; sv[j][q] = 0.0; }
+    for (int q = 0; q < 3; ++q) { x[j][q] = 0.0; r[j][q] = 0.0; w[j][q] = 0.0; }
     if (row < n) {
       const int gi = d.rows[r0 + row];
       diag[j] = __ldg(a.Kdata + __ldg(d.dkidx + r0 + row));
@@ -396,94 +270,154 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
   }
   if (tid < nact) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s_part[k * kThreads + tid] = acc[k];
+    for (int k = 0; k < kVals; ++k) s_part[k * kThreads + tid] = acc[k];
   }
   __syncthreads();
-  // ---- start-up record to the roots; their reply carries the first coarse correction ----
-  reduce_publish(s_part, nact, 8, a.xS + (size_t)c * 8 * 2, 1u);
-  if (warp == 0 && lane < 4) s_sc[6 + lane] = ll_load(a.xM + ((size_t)c * kMail + 6 + lane) * 2, 1u);
-  __syncthreads();
-  double yc[3] = {s_sc[6], s_sc[7], s_sc[8]};
-  const bool zero_rhs = (int)s_sc[9] == F_ZERO;
 
+  // ---- exchange S: coarse residual of r0 = b, ||b||^2, sign census ----
+  reduce_publish(s_part, nact, 8, a.xS + (size_t)c * 8 * 2, 1u);
+  if (warp < 8) {
+    const double sum = poll_column(a.xS, 8, warp, 1u, P, warp < 3 ? s_rc : nullptr, 3, warp);
+    if (lane == 0) s_sc[warp] = sum;          // [3..5] = bb, [6] = npos, [7] = nneg
+  }
+  __syncthreads();
+  const double bb0 = s_sc[3], bb1 = s_sc[4], bb2 = s_sc[5];
+  const bool indefinite = s_sc[6] > 0.0 && s_sc[7] > 0.0;
+  const double sign = s_sc[7] > 0.0 && s_sc[6] == 0.0 ? -1.0 : 1.0;
+
+  double rz_old[3] = {0.0, 0.0, 0.0}, alpha[3] = {0.0, 0.0, 0.0};
+  double rr[3] = {bb0, bb1, bb2};
   int it = 0;
-  PROF(long long tB = 0, tA = 0, tH = 0, tC = 0, tM = 0, t0, t1;)
+  PROF(long long tB = 0, tA = 0, tH = 0, tC = 0, tM = 0, t0, t1; const long long tstart = clock64();)
+  int status = indefinite ? FDM_STATUS_INDEFINITE : FDM_STATUS_OK;
+  const bool zero_rhs = (bb0 == 0.0 && bb1 == 0.0 && bb2 == 0.0);
+
   while (!zero_rhs) {
     const uint32_t tag = (uint32_t)it + 1u;
-    uint64_t* xRb = a.xR + (size_t)(it & 1) * P * kVals * 2;
     PROF(t0 = clock64();)
-    // ---- z = D^-1 r + yc on own rows; hand the boundary values to the neighbours ----
+    // ---- coarse residual recurrence + coarse solve for the own aggregate (warps 0..2) ----
+    //      rc -= alpha * (P^T A p);  yc = Ainv[c,:] . rc
+    if (warp < 3) {
+      double v = 0.0;
+      for (int j = lane; j < P; j += 32) {
+        const double nv = s_rc[j * 3 + warp] - alpha[warp] * s_cap[j * 3 + warp];
+        s_rc[j * 3 + warp] = nv;
+        v += s_ainv[j] * nv;
+      }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_sc[8 + warp] = v;
+    }
+    __syncthreads();
+    const double yc[3] = {s_sc[8], s_sc[9], s_sc[10]};
+    // ---- z = D^-1 r + yc ; partial <r,z>, <r,r> ; export boundary z ----
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int row = tid + j * kThreads;
       if (row < n) {
-        double z[3];
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          z[q] = dinv[j] * r[j][q] + yc[q];
-          s_z[q * pstride + row] = z[q];
+          const double z = dinv[j] * r[j][q] + yc[q];
+          w[j][q] = z;
+          acc[q] += r[j][q] * z;
+          acc[3 + q] += r[j][q] * r[j][q];
         }
         if (expslot[j] >= 0) {
           uint64_t* e = a.xE + (size_t)expslot[j] * 6;
-          ll_store(e, z[0], tag); ll_store(e + 2, z[1], tag); ll_store(e + 4, z[2], tag);
+          ll_store(e, w[j][0], tag); ll_store(e + 2, w[j][1], tag); ll_store(e + 4, w[j][2], tag);
         }
       }
     }
-    PROF(t1 = clock64(); tC += t1 - t0; t0 = t1;)
-    for (int i = tid; i < nh * 3; i += kThreads) {
-      const int h = i / 3, q = i - 3 * h;
-      s_z[q * pstride + d.nmax + h] = ll_load(a.xE + (size_t)s_halo_src[h] * 6 + 2 * q, tag);
+    if (tid < nact) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s_part[k * kThreads + tid] = acc[k];
     }
     __syncthreads();
-    PROF(t1 = clock64(); tH += t1 - t0; t0 = t1;)
-    // ---- w = K z (own rows); partial <r,z>, <w,z>, <r,r>, own coarse sum of w ----
+    PROF(t1 = clock64(); tC += t1 - t0; t0 = t1;)
+    reduce_publish(s_part, nact, 6, a.xB + (size_t)c * 6 * 2, tag);
+    if (warp < 6) {
+      const double sum = poll_column(a.xB, 6, warp, tag, P, nullptr, 0, 0);
+      if (lane == 0) s_sc[12 + warp] = sum;   // [12..14] = <r,z>, [15..17] = <r,r>
+    }
+    __syncthreads();
+    PROF(t1 = clock64(); tB += t1 - t0; t0 = t1;)
+    double rz_new[3], beta[3];
 #pragma unroll
-    for (int k = 0; k < kVals; ++k) acc[k] = 0.0;
+    for (int q = 0; q < 3; ++q) {
+      rz_new[q] = s_sc[12 + q];
+      rr[q] = s_sc[15 + q];
+      beta[q] = (it > 0 && rz_old[q] != 0.0) ? rz_new[q] / rz_old[q] : 0.0;
+    }
+    if (rr[0] <= a.tol2 * bb0 && rr[1] <= a.tol2 * bb1 && rr[2] <= a.tol2 * bb2) break;
+    if (!(isfinite(rz_new[0]) && isfinite(rz_new[1]) && isfinite(rz_new[2]))) { status = FDM_STATUS_BREAKDOWN; break; }
+    if (it >= a.max_iters) { status = FDM_STATUS_NOT_CONVERGED; break; }
+    // ---- p = z + beta p on own rows and halo ----
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int row = tid + j * kThreads;
       if (row < n) {
-        const double z0 = s_z[row], z1 = s_z[pstride + row], z2 = s_z[2 * pstride + row];
-        double a0 = diag[j] * z0, a1 = diag[j] * z1, a2 = diag[j] * z2;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s_p[q * pstride + row] = w[j][q] + beta[q] * s_p[q * pstride + row];
+      }
+    }
+    for (int i = tid; i < nh * 3; i += kThreads) {
+      const int h = i / 3, q = i - 3 * h;
+      const double z = ll_load(a.xE + (size_t)s_halo_src[h] * 6 + 2 * q, tag);
+      double* pp = s_p + q * pstride + d.nmax + h;
+      *pp = z + beta[q] * (*pp);
+    }
+    __syncthreads();
+    PROF(t1 = clock64(); tH += t1 - t0; t0 = t1;)
+    // ---- w = A p (own rows), partial <p,Ap>, own coarse sum of Ap ----
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] = 0.0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int row = tid + j * kThreads;
+      if (row < n) {
+        const double p0 = s_p[row], p1 = s_p[pstride + row], p2 = s_p[2 * pstride + row];
+        double a0 = diag[j] * p0, a1 = diag[j] * p1, a2 = diag[j] * p2;
         const int k0 = s_rowptr[row], k1 = s_rowptr[row + 1];
         for (int k = k0; k < k1; ++k) {
           const double v = s_val[k];
           int cidx = s_col[k];
           cidx = cidx < n ? cidx : d.nmax + (cidx - n);
-          a0 += v * s_z[cidx]; a1 += v * s_z[pstride + cidx]; a2 += v * s_z[2 * pstride + cidx];
+          a0 += v * s_p[cidx]; a1 += v * s_p[pstride + cidx]; a2 += v * s_p[2 * pstride + cidx];
         }
         w[j][0] = a0; w[j][1] = a1; w[j][2] = a2;
-        acc[0] += r[j][0] * z0; acc[1] += r[j][1] * z1; acc[2] += r[j][2] * z2;
-        acc[3] += a0 * z0; acc[4] += a1 * z1; acc[5] += a2 * z2;
-        acc[6] += r[j][0] * r[j][0]; acc[7] += r[j][1] * r[j][1]; acc[8] += r[j][2] * r[j][2];
-        acc[9] += a0; acc[10] += a1; acc[11] += a2;
+        acc[0] += p0 * a0; acc[1] += p1 * a1; acc[2] += p2 * a2;
+        acc[3] += a0; acc[4] += a1; acc[5] += a2;
       }
     }
     if (tid < nact) {
 #pragma unroll
-      for (int k = 0; k < kVals; ++k) s_part[k * kThreads + tid] = acc[k];
+      for (int k = 0; k < 6; ++k) s_part[k * kThreads + tid] = acc[k];
     }
     __syncthreads();
     PROF(t1 = clock64(); tM += t1 - t0; t0 = t1;)
-    // ---- record to the roots, mailbox back ----
-    reduce_publish(s_part, nact, kVals, xRb + (size_t)c * kVals * 2, tag);
-    if (warp == 0 && lane < 10) s_sc[lane] = ll_load(a.xM + ((size_t)c * kMail + lane) * 2, tag + 1u);
+    reduce_publish(s_part, nact, 6, a.xA + (size_t)c * 6 * 2, tag);
+    if (warp < 6) {
+      const double sum = poll_column(a.xA, 6, warp, tag, P, warp >= 3 ? s_cap : nullptr, 3, warp - 3);
+      if (lane == 0) s_sc[18 + warp] = sum;   // [18..20] = <p,Ap>
+    }
     __syncthreads();
     PROF(t1 = clock64(); tA += t1 - t0; t0 = t1;)
-    if ((int)s_sc[9] != F_CONTINUE) break;
-    const double alpha[3] = {s_sc[0], s_sc[1], s_sc[2]}, beta[3] = {s_sc[3], s_sc[4], s_sc[5]};
-    yc[0] = s_sc[6]; yc[1] = s_sc[7]; yc[2] = s_sc[8];
-    // ---- p = z + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ----
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double pap = s_sc[18 + q];
+      alpha[q] = pap != 0.0 ? rz_new[q] / pap : 0.0;
+      rz_old[q] = rz_new[q];
+    }
+    // ---- x += alpha p ; r -= alpha A p  (coarse recurrence happens at the top of the loop) ----
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int row = tid + j * kThreads;
       if (row < n) {
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          pv[j][q] = s_z[q * pstride + row] + beta[q] * pv[j][q];
-          sv[j][q] = w[j][q] + beta[q] * sv[j][q];
-          x[j][q] += alpha[q] * pv[j][q];
-          r[j][q] -= alpha[q] * sv[j][q];
+          x[j][q] += alpha[q] * s_p[q * pstride + row];
+          r[j][q] -= alpha[q] * w[j][q];
         }
       }
     }
@@ -500,7 +434,19 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
       for (int q = 0; q < 3; ++q) a.x[3 * (size_t)gi + q] = x[j][q];
     }
   }
-  PROF(if (c == 0 && tid == 0 && a.info) { a.info[4] = (double)tC; a.info[5] = (double)tH; a.info[6] = (double)tM; a.info[7] = (double)tA; (void)tB; })
+  if (c == 0 && tid == 0 && a.info) {
+    double rel = 0.0;
+    const double bb[3] = {bb0, bb1, bb2};
+    for (int q = 0; q < 3; ++q)
+      if (bb[q] > 0.0) rel = fmax(rel, sqrt(rr[q] / bb[q]));
+    a.info[FDM_INFO_STATUS] = (double)status;
+    a.info[FDM_INFO_ITERS] = (double)it;
+    a.info[FDM_INFO_RELRES] = rel;
+    a.info[FDM_INFO_SIGN] = sign;
+    // phase cycle totals of CTA 0 (diagnostics build only): coarse+z, exchange B, p/halo, SpMV, exchange A, total
+    PROF(a.info[4] = (double)tC; a.info[5] = (double)tB; a.info[6] = (double)(tH + tM); a.info[7] = (double)tA;
+         (void)tstart;)
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,11 +470,9 @@ int up(Pcg2Host* h, const std::vector<T>& v, T** out) {
 
 size_t pcg2_smem(int P, int nmax, int emax, int hmax) {
   auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
-  const size_t worker = al(8 * (size_t)emax) + al(8 * 3 * (size_t)(nmax + hmax)) + al(8 * (size_t)kVals * kThreads) +
-                        al(8 * 32) + al(4 * (size_t)(nmax + 1)) + al(4 * (size_t)hmax) + al(2 * (size_t)emax);
-  const size_t nown = (size_t)(P + kRoots - 1) / kRoots;
-  const size_t root = 8 * (nown * P + 9 * (size_t)P + 3 * nown + 32) + 64;
-  return std::max(worker, root);
+  return al(8 * (size_t)emax) + al(8 * 3 * (size_t)(nmax + hmax)) + al(8 * (size_t)kVals * kThreads) +
+         al(8 * (size_t)P * 3) * 2 + al(8 * (size_t)P) + al(8 * 32) +
+         al(4 * (size_t)(nmax + 1)) + al(4 * (size_t)hmax) + al(2 * (size_t)emax);
 }
 
 // Build (once per plan) the per-aggregate local CSR, halo and export maps.
@@ -640,7 +584,7 @@ int pcg2_build(fdm_plan* p) {
     delete H;
     return rc;
   }
-  H->xwords = ((size_t)P * (8 + 2 * kVals + kMail) + (size_t)D.total_exports * 3) * 2;
+  H->xwords = ((size_t)3 * P * kVals + (size_t)D.total_exports * 3) * 2;
   p->d.pcg2 = H;
   return FDM_OK;
 }
@@ -648,7 +592,7 @@ int pcg2_build(fdm_plan* p) {
 bool shape_ok(const fdm_plan* p) {
   // P CTAs must be co-resident (one per SM) and the worst aggregate must fit shared memory.
   // Estimate before building: rows/part <= kThreads*kMaxRowsPerThread, dense coarse inverse fits one CTA.
-  if (p->num_parts < 2 || p->num_parts + kRoots > p->sm_count || p->num_parts > 32 * kMaxPer) return false;
+  if (p->num_parts < 2 || p->num_parts > p->sm_count || p->num_parts > 32 * kMaxPer) return false;
   if ((size_t)p->num_parts * p->num_parts * 8 > 200 * 1024) return false;
   return true;
 }
@@ -707,9 +651,9 @@ int pcg2_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double
   a.d = D;
   a.ainv = (double*)((char*)ws + ainv_off);
   a.xS = (uint64_t*)((char*)ws + x_off);
-  a.xR = a.xS + (size_t)P * 8 * 2;
-  a.xM = a.xR + (size_t)2 * P * kVals * 2;
-  a.xE = a.xM + (size_t)P * kMail * 2;
+  a.xA = a.xS + (size_t)P * kVals * 2;
+  a.xB = a.xA + (size_t)P * kVals * 2;
+  a.xE = a.xB + (size_t)P * kVals * 2;
   const double tol = o.tol > 0 ? o.tol : 1e-12;
   a.tol2 = tol * tol;
   a.max_iters = o.max_iters > 0 ? o.max_iters : 20000;
@@ -735,7 +679,7 @@ int pcg2_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double
       FDM_CUDA(cudaMemsetAsync(a.xS, 0, H->xwords * 8, st));
     }
     void* args[] = {&a};
-    FDM_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(P + kRoots), dim3(kThreads), args, D.smem_bytes, st));
+    FDM_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(P), dim3(kThreads), args, D.smem_bytes, st));
   }
   return fdm_check_launch("pcg2_solve");
 }

@@ -228,6 +228,34 @@ def test_cablenet200_full_size_properties(eq):
     assert relerr(N(qbar), qbar_o) <= GRAD_RTOL
 
 
+def test_cablenet200_pipeline_forward_and_adjoint_converge(eq):
+    """Config 4 through the benchmark's device pipeline: both solves of the persistent PCG (the adjoint
+    reuses the coarse inverse) must CONVERGE to 1e-12 in a few hundred iterations, and q_bar must match
+    the CPU oracle."""
+    from jax_fdm_b200.pipeline import ForwardAdjoint
+
+    prob = datasets.cablenet_problem(200)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    pipe = ForwardAdjoint(s, batch=1, solver="auto", tol=1e-12, device=0)
+    x0 = prob.xyz0[s.indices_free]
+    pipe.set_inputs(prob.q[None], prob.xyz_fixed, prob.loads, x0)
+    pipe.step()
+    pipe.stream.synchronize()
+    for info in (N(pipe.info_f)[0], N(pipe.info_a)[0]):
+        assert info[0] == 0, f"solve status {info[0]}"
+        assert 0 < info[1] < 2000 and info[2] <= 1e-12
+
+    def cot(st, xf):
+        c = np.zeros_like(st["xyz"])
+        c[so.indices_free] = xf - x0
+        return {"xyz": c}
+
+    ref = oracle.forward_adjoint(prob.q, prob.xyz_fixed, prob.loads, so, cot)
+    assert relerr(N(pipe.x)[0], ref["x_free"]) <= POS_RTOL
+    assert relerr(N(pipe.q_bar)[0], ref["q_bar"]) <= GRAD_RTOL
+
+
 def test_zero_rhs_column_and_errors(eq):
     g = load("arch10")      # y column of rhs is identically zero
     s, so = make(eq, g)

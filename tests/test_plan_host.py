@@ -52,7 +52,7 @@ def test_plan_arrays_bit_exact_vs_reference(name):
     rows = np.repeat(np.arange(s.num_free), np.diff(ia.indptr))
     assert np.abs(bp[rows] - bp[ia.indices]).max() == s.half_bandwidth
     part = s.part_of_row
-    assert part.min() == 0 and part.max() == min(144, s.num_free) - 1   # 148 SMs minus the 4 coarse-problem CTAs
+    assert part.min() == 0 and part.max() == min(148, s.num_free) - 1
     assert np.bincount(part).min() >= 1
 
 

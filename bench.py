@@ -359,6 +359,20 @@ def run_ours(args):
     sum_e2e = reduce_max(sum(t_e2e))
     status_ok = bool((pipe.info_f[:, 0] == 0).all().item() and (pipe.info_a[:, 0] == 0).all().item())
 
+    # diagnostic at N > 1: the same steps without the loss all-reduce (what the collective + the lock-step
+    # it imposes on the ranks cost), and the spread of the per-rank times
+    scaling_diag = None
+    if world > 1:
+        barrier()
+        t_local = timed_steps(pipe.step, pipe.stream, steps, flush)
+        barrier()
+        mine = torch.tensor([sum(t_dev) / steps, sum(t_local) / steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = torch.stack(allr).cpu().numpy()
+        scaling_diag = {"ms_per_step_with_allreduce_per_rank": [float(v) for v in per_rank[:, 0]],
+                        "ms_per_step_without_allreduce_per_rank": [float(v) for v in per_rank[:, 1]]}
+
     # every kernel of the step alone, for the roofline table (rank 0's numbers are reported)
     kernels = kernel_table(pipe, s, B, max(3, min(steps, 10)), flush, hbm)
 
@@ -447,6 +461,8 @@ def run_ours(args):
     }
     if fixed:
         line["config5_fixed_global_batch"] = fixed
+    if scaling_diag:
+        line["scaling_diagnostic"] = scaling_diag
     if world == 1:
         os.environ.setdefault("OMP_NUM_THREADS", "1")
         sample = 2048

@@ -146,6 +146,16 @@ int fdm_solve(const fdm_plan* plan, const double* d_Kdata, const double* d_rhs, 
               double* d_info /* (B, FDM_INFO_STRIDE) or NULL */, void* d_ws, size_t ws_bytes,
               int64_t batch, const fdm_solve_opts* opts, void* stream);
 
+/* K1 + K2 in one call: x = K(q)^{-1} (loads_f - C_f^T Q C_s xyz_fixed), i.e. nodes_free_positions
+ * (models.py:222-256), without materialising K.data or the right-hand side.  Available where the
+ * batched band Cholesky assembles its rows from q in place (half bandwidth <= 30); otherwise returns
+ * FDM_ERR_UNSUPPORTED and the caller uses fdm_assemble + fdm_solve.  The factor left in d_ws serves
+ * later fdm_solve calls with opts.reuse_factor (the adjoint solve). */
+int fdm_solve_from_q(const fdm_plan* plan, const double* d_q, const double* d_xyz_fixed,
+                     const double* d_loads, double* d_x, double* d_info, void* d_ws, size_t ws_bytes,
+                     int64_t batch, int64_t q_stride, int64_t xyz_fixed_stride, int64_t loads_stride,
+                     const fdm_solve_opts* opts, void* stream);
+
 /* ---- SpMM: Y = K X, X (Nf,3) -----------------------------------------------------------
  * Replaces `K @ xyz_free` (models.py:1012) and `A @ xk` (sparse.py:301). */
 int fdm_spmm(const fdm_plan* plan, const double* d_Kdata, const double* d_X, double* d_Y,

@@ -27,7 +27,7 @@ SOLVERS = {"auto": 0, "pcg": 1, "pcg_persistent": 2, "cholesky": 3}
 
 EXPORTS = [
     "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",
-    "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_spmm",
+    "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_solve_from_q", "fdm_spmm",
     "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_adjoint_grads", "fdm_edge_loads",
     "fdm_edge_loads_vjp", "fdm_loss_sqdist",
     "fdm_last_error", "fdm_version",
@@ -77,6 +77,8 @@ def lib():
     L.fdm_workspace_bytes.restype = sz
     L.fdm_solve.argtypes = [vp, vp, vp, vp, vp, vp, sz, i64, C.POINTER(SolveOpts), vp]
     L.fdm_solve.restype = C.c_int
+    L.fdm_solve_from_q.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, i64, i64, i64, i64, C.POINTER(SolveOpts), vp]
+    L.fdm_solve_from_q.restype = C.c_int
     L.fdm_spmm.argtypes = [vp, vp, vp, vp, i64, vp]
     L.fdm_spmm.restype = C.c_int
     L.fdm_positions.argtypes = [vp, vp, vp, vp, i64, i64, C.c_int, vp]

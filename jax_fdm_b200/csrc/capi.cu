@@ -23,7 +23,7 @@ void free_device(fdm_plan* p) {
   DeviceArrays& d = p->d;
   void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
-                  d.band_iperm, d.band_kidx, d.band_rowkidx, d.diags_ptr, d.diags_idx, d.sup_mask};
+                  d.band_iperm, d.band_kidx, d.band_rowkidx, d.band_rowedge, d.diags_ptr, d.diags_idx, d.sup_mask};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   d = DeviceArrays();
@@ -116,6 +116,7 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->band_iperm, &q->d.band_iperm); },
         [](fdm_plan* q) { return upload(q->band_kidx, &q->d.band_kidx); },
         [](fdm_plan* q) { return upload(q->band_rowkidx, &q->d.band_rowkidx); },
+        [](fdm_plan* q) { return upload(q->band_rowedge, &q->d.band_rowedge); },
         [](fdm_plan* q) { return upload(q->diags_indptr, &q->d.diags_ptr); },
         [](fdm_plan* q) { return upload(q->diags_indices, &q->d.diags_idx); },
         [](fdm_plan* q) { return upload(q->sup_mask, &q->d.sup_mask); },
@@ -226,6 +227,29 @@ int fdm_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double*
   }
   fdm_set_error("fdm_solve: unknown solver id");
   return FDM_ERR_INVALID;
+}
+
+int fdm_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
+                     double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss, int64_t ls,
+                     const fdm_solve_opts* opts, void* stream) {
+  if (!ready(p, "fdm_solve_from_q")) return FDM_ERR_INVALID;
+  if (!q || !xs || !loads || !x || batch <= 0 || (!ws && ws_bytes)) {
+    fdm_set_error("fdm_solve_from_q: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  fdm_solve_opts o;
+  std::memset(&o, 0, sizeof(o));
+  if (opts) o = *opts;
+  if (o.reuse_factor) {
+    fdm_set_error("fdm_solve_from_q: reuse_factor needs a right-hand side, call fdm_solve");
+    return FDM_ERR_INVALID;
+  }
+  if (pick_solver(p, batch, o.solver) != FDM_SOLVER_CHOLESKY_BATCHED || !chol_warp_from_q_supported(p)) {
+    fdm_set_error("fdm_solve_from_q: only the warp-per-design band Cholesky (hbw <= 30) assembles in place; "
+                  "call fdm_assemble + fdm_solve");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  return chol_warp_solve_from_q(p, q, xs, loads, x, info, ws, ws_bytes, batch, qs, xss, ls, (cudaStream_t)stream);
 }
 
 int fdm_spmm(const fdm_plan* p, const double* Kdata, const double* X, double* Y, int64_t batch,

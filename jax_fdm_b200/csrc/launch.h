@@ -75,6 +75,11 @@ size_t chol_warp_workspace_bytes(const fdm_plan* p, int64_t batch);
 int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
                     void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
 
+bool chol_warp_from_q_supported(const fdm_plan* p);
+int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
+                           double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss,
+                           int64_t ls, cudaStream_t st);
+
 // solver_pcg2.cu  (persistent two-level PCG)
 size_t pcg2_workspace_bytes(const fdm_plan* p);
 bool pcg2_supported(const fdm_plan* p);

@@ -304,6 +304,7 @@ void fdm_build_band_order(fdm_plan& p) {
   // Cholesky (hbw <= 31).  Rows are padded to (ceil(n/32)+1)*32 with identity rows:
   // -1 = structural zero (or column < 0), -2 = one (diagonal of a padding row).
   p.band_rowkidx.clear();
+  p.band_rowedge.clear();
   if (p.hbw <= 31) {
     const int64_t rows = ((int64_t)(n + 31) / 32 + 1) * 32;
     p.band_rowkidx.assign((size_t)rows * 32, -1);
@@ -314,6 +315,13 @@ void fdm_build_band_order(fdm_plan& p) {
         int32_t c = p.band_perm[p.index_indices[k]];
         if (c <= r) p.band_rowkidx[(size_t)r * 32 + (r - c)] = k;
       }
+    }
+    // same table in terms of q: edge id of the off-diagonal entry, -3 = diagonal (sum over `diags`),
+    // -1 / -2 as above.  Lets the batched factorisation assemble its rows straight from q.
+    p.band_rowedge.assign(p.band_rowkidx.size(), -1);
+    for (size_t i = 0; i < p.band_rowkidx.size(); ++i) {
+      const int32_t k = p.band_rowkidx[i];
+      p.band_rowedge[i] = k >= 0 ? (p.entry_edge[k] >= 0 ? p.entry_edge[k] : -3) : k;
     }
   }
 }

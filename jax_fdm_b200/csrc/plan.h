@@ -28,6 +28,7 @@ struct DeviceArrays {
   int32_t* band_iperm = nullptr;   // (Nf) band position -> free index
   int32_t* band_kidx = nullptr;    // (Nf, hbw+1) column-oriented: [j*(hbw+1)+d] = position in K.data of A(j+d, j), -1 = zero
   int32_t* band_rowkidx = nullptr; // ((ceil(Nf/32)+1)*32, 32) row-oriented: [R*32+t] = position of A(R, R-t), -1 zero, -2 one
+  int32_t* band_rowedge = nullptr; // same shape: edge id of the entry, -3 diagonal, -1 zero, -2 one
   // two-level persistent PCG (solver_pcg_persistent.cu); built lazily by the host
   void* pcg2 = nullptr;
 };
@@ -48,7 +49,7 @@ struct fdm_plan {
   std::vector<uint32_t> sup_mask;
 
   // band ordering
-  std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx;
+  std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx, band_rowedge;
   int32_t hbw = 0;
 
   // aggregates for the two-level preconditioner

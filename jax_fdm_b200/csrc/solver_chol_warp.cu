@@ -61,6 +61,13 @@ struct WArgs {
   int64_t ws_stride;       // nblk*1024 (factor) + nblk*128 (intermediate rhs) + 8 (sigma, bad)
   int64_t nnz, batch;
   int forward;             // subst kernel: run the forward substitution on `rhs` first
+  // in-place assembly (chol_factor_mma_kernel<true>): K and the load term straight from q
+  const double* q;         // (B, E)
+  const double* xs;        // (B|1, Ns, 3)
+  const double* loads;     // (B|1, N, 3)
+  int64_t q_stride, xs_stride, loads_stride;
+  const int32_t *rowedge, *diags_ptr, *diags_idx, *free_node, *node_slot, *ninc_ptr, *ninc_edge, *ninc_other;
+  const uint32_t* sup_mask;
 };
 
 // 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~22 bits) + two Newton steps in
@@ -252,6 +259,7 @@ __device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double 
                : "d"(a), "d"(b));
 }
 
+template <bool FROM_Q>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,32 +269,81 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
   double* Pn = fs + 32 * kMS;
   const int g = lane >> 2, m = lane & 3;
   const int n = A.n, nblk = A.nblk;
-  const double* Kd = A.Kdata + b * A.nnz;
-  const double* rhs = A.rhs + b * (int64_t)n * 3;
+  const double* Kd = FROM_Q ? nullptr : A.Kdata + b * A.nnz;
+  const double* rhs = FROM_Q ? nullptr : A.rhs + b * (int64_t)n * 3;
+  const double* q = FROM_Q ? A.q + b * A.q_stride : nullptr;
   double* fac = A.ws + b * A.ws_stride;
   double* ysol = fac + (int64_t)nblk * 1024;
   double* meta = ysol + (int64_t)nblk * 128;
   int bad = 0;
-  const double sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
+
+  // K(i,i) = sum of q over the incident edges of free row f, in ascending edge id (the order of the
+  // reference's `diags @ q`, structures.py:316-350 -- same additions as assemble_kernel)
+  auto diag_of = [&](int f) {
+    double dsum = 0.0;
+    const int k0 = __ldg(A.diags_ptr + f), k1 = __ldg(A.diags_ptr + f + 1);
+    for (int k = k0; k < k1; ++k) dsum += __ldg(q + __ldg(A.diags_idx + k));
+    return dsum;
+  };
+  double sigma;
+  if (FROM_Q) sigma = diag_of(__ldg(A.iperm)) < 0.0 ? -1.0 : 1.0;
+  else sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
 
   // fs[r][s] = sigma * A(R0 + r, C), C = the column with slot s among the 32 ending at row R0 + r;
   // fs[r][32..34] = sigma * rhs(R0 + r)
   auto stage_rows = [&](int R0) {
-    const int32_t* idxp = A.rowkidx + (int64_t)R0 * 32;
+    if (!FROM_Q) {
+      const int32_t* idxp = A.rowkidx + (int64_t)R0 * 32;
 #pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const int idx = __ldg(idxp + r * 32 + ((r - lane) & 31));
-      double v = 0.0;
-      if (idx >= 0) v = sigma * __ldg(Kd + idx);
-      else if (idx == -2) v = 1.0;
-      fs[r * kMS + lane] = v;
+      for (int r = 0; r < 32; ++r) {
+        const int idx = __ldg(idxp + r * 32 + ((r - lane) & 31));
+        double v = 0.0;
+        if (idx >= 0) v = sigma * __ldg(Kd + idx);
+        else if (idx == -2) v = 1.0;
+        fs[r * kMS + lane] = v;
+      }
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+      if (R0 + lane < n) {
+        const int gi = __ldg(A.iperm + R0 + lane);
+        r0 = sigma * rhs[3 * gi]; r1 = sigma * rhs[3 * gi + 1]; r2 = sigma * rhs[3 * gi + 2];
+      }
+      fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
+    } else {
+      // assembly in place (models.py:1064-1079, 828-856, 949-976): off-diagonals -q[e], then lane r finishes
+      // row R0 + r: its diagonal and its load term loads_f + sum_{e to support s} q_e x_s
+      const int32_t* idxp = A.rowedge + (int64_t)R0 * 32;
+      const double nsig = -sigma;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int e = __ldg(idxp + r * 32 + ((r - lane) & 31));
+        double v = 0.0;
+        if (e >= 0) v = nsig * __ldg(q + e);
+        else if (e == -2) v = 1.0;
+        fs[r * kMS + lane] = v;
+      }
+      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+      if (R0 + lane < n) {
+        const int f = __ldg(A.iperm + R0 + lane);
+        fs[lane * kMS + lane] = sigma * diag_of(f);          // slot of column R0 + lane is lane
+        const int node = __ldg(A.free_node + f);
+        double3 acc = make_double3(0.0, 0.0, 0.0);
+        if ((__ldg(A.sup_mask + (f >> 5)) >> (f & 31)) & 1u) {
+          const double* xsb = A.xs + b * A.xs_stride;
+          const int i0 = __ldg(A.ninc_ptr + node), i1 = __ldg(A.ninc_ptr + node + 1);
+          for (int k = i0; k < i1; ++k) {
+            const int slot = __ldg(A.node_slot + __ldg(A.ninc_other + k));
+            if (slot < 0) {
+              const double qe = __ldg(q + (__ldg(A.ninc_edge + k) >> 1));
+              const double* xp = xsb + 3 * (int64_t)(-slot - 1);
+              acc.x += qe * __ldg(xp); acc.y += qe * __ldg(xp + 1); acc.z += qe * __ldg(xp + 2);
+            }
+          }
+        }
+        const double* lp = A.loads + b * A.loads_stride + 3 * (int64_t)node;
+        r0 = sigma * (__ldg(lp) + acc.x); r1 = sigma * (__ldg(lp + 1) + acc.y); r2 = sigma * (__ldg(lp + 2) + acc.z);
+      }
+      fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
     }
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-    if (R0 + lane < n) {
-      const int gi = __ldg(A.iperm + R0 + lane);
-      r0 = sigma * rhs[3 * gi]; r1 = sigma * rhs[3 * gi + 1]; r2 = sigma * rhs[3 * gi + 2];
-    }
-    fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
   };
 
   double W[4][4][2], y[3];
@@ -648,6 +705,64 @@ size_t chol_warp_workspace_bytes(const fdm_plan* p, int64_t batch) {
   return (size_t)batch * (size_t)ws_stride_of(p) * sizeof(double);
 }
 
+bool chol_warp_from_q_supported(const fdm_plan* p) { return chol_warp_supported(p) && p->hbw <= 30; }
+
+static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, void* ws, int64_t batch) {
+  A.n = (int)p->Nf;
+  A.bw = p->hbw;
+  A.nblk = (int)((p->Nf + 31) / 32);
+  A.rowkidx = p->d.band_rowkidx;
+  A.iperm = p->d.band_iperm;
+  A.Kdata = nullptr;
+  A.rhs = nullptr;
+  A.x = x;
+  A.info = info;
+  A.ws = (double*)ws;
+  A.ws_stride = ws_stride_of(p);
+  A.nnz = p->nnz;
+  A.batch = batch;
+  A.forward = 0;
+  A.q = A.xs = A.loads = nullptr;
+  A.q_stride = A.xs_stride = A.loads_stride = 0;
+  A.rowedge = p->d.band_rowedge; A.diags_ptr = p->d.diags_ptr; A.diags_idx = p->d.diags_idx;
+  A.free_node = p->d.free_node; A.node_slot = p->d.node_slot; A.ninc_ptr = p->d.ninc_ptr;
+  A.ninc_edge = p->d.ninc_edge; A.ninc_other = p->d.ninc_other; A.sup_mask = p->d.sup_mask;
+}
+
+static int launch_invdiag_and_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
+  const int64_t items = batch * A.nblk * 4 * 8;
+  chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
+  void (*skern)(WArgs) = p->hbw <= 7 ? chol_subst_kernel<1> : p->hbw <= 15 ? chol_subst_kernel<2>
+                       : p->hbw <= 23 ? chol_subst_kernel<3> : chol_subst_kernel<4>;
+  const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
+  FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  skern<<<(unsigned)((batch + kSubWarps - 1) / kSubWarps), kSubThreads, smem, st>>>(A);
+  return FDM_OK;
+}
+
+int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
+                           double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss,
+                           int64_t ls, cudaStream_t st) {
+  if (!chol_warp_from_q_supported(p)) {
+    fdm_set_error("chol_warp_solve_from_q: half bandwidth " + std::to_string(p->hbw) + " > 30");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  if (ws_bytes < chol_warp_workspace_bytes(p, batch)) {
+    fdm_set_error("chol_warp_solve_from_q: workspace too small");
+    return FDM_ERR_WORKSPACE;
+  }
+  WArgs A;
+  fill_common(A, p, x, info, ws, batch);
+  A.q = q; A.xs = xs; A.loads = loads;
+  A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
+  const size_t smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
+  FDM_CUDA(cudaFuncSetAttribute(chol_factor_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chol_factor_mma_kernel<true><<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+  int rc = launch_invdiag_and_backward(p, A, batch, st);
+  if (rc != FDM_OK) return rc;
+  return fdm_check_launch("chol_warp_solve_from_q");
+}
+
 int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
                     void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st) {
   if (!chol_warp_supported(p)) {
@@ -673,6 +788,10 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.nnz = p->nnz;
   A.batch = batch;
   A.forward = o.reuse_factor ? 1 : 0;
+  A.q = A.xs = A.loads = nullptr;
+  A.q_stride = A.xs_stride = A.loads_stride = 0;
+  A.rowedge = nullptr; A.diags_ptr = A.diags_idx = A.free_node = A.node_slot = nullptr;
+  A.ninc_ptr = A.ninc_edge = A.ninc_other = nullptr; A.sup_mask = nullptr;
   void (*fkern)(WArgs) = nullptr;
   void (*skern)(WArgs) = nullptr;
   if (p->hbw <= 7) { fkern = chol_factor_kernel<7>; skern = chol_subst_kernel<1>; }
@@ -683,7 +802,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     static const bool force_simt = std::getenv("FDM_CHOL_SIMT") != nullptr;   // A/B switch for profiling
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
     if (p->hbw <= 30 && !force_simt) {
-      fkern = chol_factor_mma_kernel;
+      fkern = chol_factor_mma_kernel<false>;
       smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

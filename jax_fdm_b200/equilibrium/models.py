@@ -119,9 +119,18 @@ class _FusedFreePositions(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, xyz_fixed, loads, structure, opts):
-        K, rhs = ops.assemble(structure, q, xyz_fixed, loads)
         ws = ops.Workspace()
-        x = ops.solve(structure, K, rhs, workspace=ws, **opts)
+        x = K = None
+        if opts.get("fused_assembly", False) and opts.get("solver", "auto") in ("auto", "cholesky"):
+            x = ops.solve_from_q(structure, q, xyz_fixed, loads, workspace=ws)   # batched designs: K never materialised
+        if x is None:
+            opts = {k: v for k, v in opts.items() if k != "fused_assembly"}
+            K, rhs = ops.assemble(structure, q, xyz_fixed, loads)
+            x = ops.solve(structure, K, rhs, workspace=ws, **opts)
+        else:
+            K = torch.empty(0, dtype=q.dtype, device=q.device)
+            opts = {k: v for k, v in opts.items() if k != "fused_assembly"}
+            opts["solver"] = "cholesky"
         ctx.structure, ctx.opts, ctx.ws = structure, opts, ws
         ctx.save_for_backward(q, xyz_fixed, x, K)
         return x
@@ -131,7 +140,8 @@ class _FusedFreePositions(torch.autograd.Function):
         q, xyz_fixed, x, K = ctx.saved_tensors
         s = ctx.structure
         # same K, same workspace: the Cholesky factor / coarse inverse of the forward solve is reused
-        lam = ops.solve(s, K, g.contiguous(), workspace=ctx.ws, reuse_factor=True, **ctx.opts)
+        # after a fused forward the stored factor is all the adjoint solve needs (K was never formed)
+        lam = ops.solve(s, K if K.numel() else None, g.contiguous(), workspace=ctx.ws, reuse_factor=True, **ctx.opts)
         xyz = ops.positions(s, x, xyz_fixed)
         qbar, pbar, xsbar = ops.adjoint_grads(s, q, xyz, lam)
         return qbar, xsbar, pbar, None, None

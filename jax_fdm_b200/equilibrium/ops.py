@@ -99,14 +99,21 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     """K2: x = K^{-1} rhs (sparse.py:207-230 / 296).  Kdata (B?,nnz), rhs (B?,Nf,3)."""
     s = structure
     Nf, nnz = s.num_free, s.nnz
-    Kdata = _chk(Kdata, "Kdata", (nnz,))
     rhs = _chk(rhs, "rhs", (Nf, 3))
-    B, batched = _resolve_batch((Kdata, 1), (rhs, 2))
-    if batched:
-        if Kdata.dim() == 1:
-            Kdata = Kdata.expand(B, nnz).contiguous()
-        if rhs.dim() == 2:
-            rhs = rhs.expand(B, Nf, 3).contiguous()
+    if Kdata is None:
+        # only the stored factor is read (band Cholesky with reuse_factor, after solve_from_q)
+        if not reuse_factor:
+            raise ValueError("Kdata may be omitted only with reuse_factor=True")
+        B, batched = _resolve_batch((rhs, 2))
+        Kdata = rhs                                   # placeholder pointer, never dereferenced
+    else:
+        Kdata = _chk(Kdata, "Kdata", (nnz,))
+        B, batched = _resolve_batch((Kdata, 1), (rhs, 2))
+        if batched:
+            if Kdata.dim() == 1:
+                Kdata = Kdata.expand(B, nnz).contiguous()
+            if rhs.dim() == 2:
+                rhs = rhs.expand(B, Nf, 3).contiguous()
     x = torch.empty_like(rhs)
     info = torch.zeros((B, L.INFO_STRIDE), dtype=F64, device=rhs.device)
     sid = L.SOLVERS[solver] if isinstance(solver, str) else int(solver)
@@ -115,6 +122,36 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)))
     L.check(L.lib().fdm_solve(s.plan, _ptr(Kdata), _ptr(rhs), _ptr(x), _ptr(info), _ptr(buf),
                               buf.numel(), B, C.byref(opts), _stream()))
+    return (x, info) if return_info else x
+
+
+def solve_from_q(structure, q, xyz_fixed, loads, workspace=None, return_info=False):
+    """
+    K1 + K2 fused: x_free = K(q)^{-1} (loads_f - C_f^T Q C_s xyz_fixed) without materialising K.data
+    (models.py:222-256).  Returns None when this structure / batch is not served by the in-place
+    assembling Cholesky (the caller then runs `assemble` + `solve`, another CUDA path).
+    """
+    s = structure
+    E, Ns, N, Nf = s.num_edges, s.num_supports, s.num_nodes, s.num_free
+    q = _chk(q, "q", (E,))
+    xyz_fixed = _chk(xyz_fixed, "xyz_fixed", (Ns, 3))
+    loads = _chk(loads, "loads", (N, 3))
+    B, batched = _resolve_batch((q, 1), (xyz_fixed, 2), (loads, 2))
+    if batched and q.dim() == 1:
+        q = q.expand(B, E).contiguous()
+    sid = L.SOLVER_CHOLESKY_BATCHED
+    if B < 2 or int(L.lib().fdm_workspace_bytes(s.plan, B, sid)) == 0 or s.half_bandwidth > 30:
+        return None
+    ws = workspace if workspace is not None else Workspace()
+    buf, _ = ws.get(s, B, sid, q.device)
+    x = torch.empty(((B,) if batched else ()) + (Nf, 3), dtype=F64, device=q.device)
+    info = torch.zeros((B, L.INFO_STRIDE), dtype=F64, device=q.device)
+    opts = L.SolveOpts(sid, 0, 0.0, 0, 0)
+    rc = L.lib().fdm_solve_from_q(s.plan, _ptr(q), _ptr(xyz_fixed), _ptr(loads), _ptr(x), _ptr(info), _ptr(buf),
+                                  buf.numel(), B, E, _stride(xyz_fixed, 2), _stride(loads, 2), C.byref(opts), _stream())
+    if rc == -5:          # FDM_ERR_UNSUPPORTED
+        return None
+    L.check(rc)
     return (x, info) if return_info else x
 
 

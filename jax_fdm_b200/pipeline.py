@@ -27,7 +27,7 @@ def _p(t):
 
 class ForwardAdjoint:
     def __init__(self, structure, batch=1, solver="auto", tol=1e-12, max_iters=0, with_state=True,
-                 use_graph=True, device=None):
+                 use_graph=True, device=None, fused_assembly=False):
         s = self.s = structure
         self.B = B = int(batch)
         self.dev = dev = torch.device("cuda", s.device if device is None else device)
@@ -53,6 +53,11 @@ class ForwardAdjoint:
         # the adjoint system has the same K: reuse the Cholesky factor / coarse inverse left in ws
         self.opts_a = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, 1)
         self.capturable = not (solver == "pcg" or (solver == "auto" and self._auto_is_multikernel()))
+        # fused_assembly: fdm_solve_from_q (K.data never formed: 33 KB less memory per 30x30 design).  Off by
+        # default: measured 3 % slower per step than assemble + solve (profiles/r01i_bench_fused_assembly.json),
+        # the per-row diagonal / load-term loops sit on the factor kernel's staging path.
+        is_chol = solver == "cholesky" or (solver == "auto" and self._auto_is_cholesky())
+        self.fused_assembly = bool(fused_assembly and is_chol and B > 1 and s.half_bandwidth <= 30)
         self.graph = None
         self.use_graph = use_graph and self.capturable
         self.stream = torch.cuda.Stream(device=dev)
@@ -87,10 +92,15 @@ class ForwardAdjoint:
         E, N, Nf, Ns = s.num_edges, s.num_nodes, s.num_free, s.num_supports
         ck = L.check
         n = 0
-        ck(lib.fdm_assemble(s.plan, _p(self.q), _p(self.xyz_fixed), _p(self.loads), _p(self.K),
-                            _p(self.rhs), B, E, 0, 0, st)); n += 1
-        ck(lib.fdm_solve(s.plan, _p(self.K), _p(self.rhs), _p(self.x), _p(self.info_f), _p(self.ws),
-                         self.ws.numel(), B, C.byref(self.opts_f), st)); n += 1
+        if self.fused_assembly:
+            # K1 + K2 in one call: the batched factorisation assembles its rows from q in place
+            ck(lib.fdm_solve_from_q(s.plan, _p(self.q), _p(self.xyz_fixed), _p(self.loads), _p(self.x), _p(self.info_f),
+                                    _p(self.ws), self.ws.numel(), B, E, 0, 0, C.byref(self.opts_f), st)); n += 1
+        else:
+            ck(lib.fdm_assemble(s.plan, _p(self.q), _p(self.xyz_fixed), _p(self.loads), _p(self.K),
+                                _p(self.rhs), B, E, 0, 0, st)); n += 1
+            ck(lib.fdm_solve(s.plan, _p(self.K), _p(self.rhs), _p(self.x), _p(self.info_f), _p(self.ws),
+                             self.ws.numel(), B, C.byref(self.opts_f), st)); n += 1
         ck(lib.fdm_positions(s.plan, _p(self.x), _p(self.xyz_fixed), _p(self.xyz), B, 0, 0, st)); n += 1
         if self.with_state:
             ck(lib.fdm_state(s.plan, _p(self.q), _p(self.xyz), _p(self.loads), _p(self.vectors),

@@ -96,3 +96,30 @@ def test_band_too_wide_is_refused_and_auto_uses_pcg():
     x, info = eq.ops.solve(s, K, rhs, solver="auto", tol=1e-13, return_info=True)
     xo = oracle.sparse_solve(oracle.stiffness_matrix_sparse(q, so), oracle.load_matrix(q, xs, loads, so))
     assert info[0, 0] == 0 and np.abs(x.cpu().numpy() - xo).max() <= 1e-10 * np.abs(xo).max()
+
+
+def test_fused_assembly_is_bit_identical_to_assemble_then_solve():
+    """fdm_solve_from_q (K1 + K2 in one kernel, K.data never formed) against fdm_assemble + fdm_solve:
+    same additions in the same order, so the positions must agree bit for bit; the adjoint solve then
+    runs on the stored factor without K."""
+    import jax_fdm_b200.equilibrium as eq
+
+    for nx, sign in ((30, -1.0), (12, 1.0)):
+        prob = datasets.pillow_problem(nx)
+        s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+        rng = np.random.default_rng(nx)
+        B = 37
+        qb = sign * np.abs(datasets.pillow_batch_q(prob.edges.shape[0], 0, B)) * rng.uniform(0.7, 1.4, size=(B, 1))
+        xs = prob.xyz_fixed + 0.05 * rng.standard_normal(prob.xyz_fixed.shape)
+        q, xs_t, p = T(qb), T(xs), T(prob.loads)
+        K, rhs = eq.ops.assemble(s, q, xs_t, p)
+        x_ref = eq.ops.solve(s, K, rhs, solver="cholesky")
+        ws = eq.ops.Workspace()
+        x, info = eq.ops.solve_from_q(s, q, xs_t, p, workspace=ws, return_info=True)
+        assert (info[:, 0] == 0).all() and (info[:, 3] == sign).all()
+        assert torch.equal(x, x_ref)
+        g = T(rng.standard_normal((B, s.num_free, 3)))
+        lam = eq.ops.solve(s, None, g, solver="cholesky", workspace=ws, reuse_factor=True)
+        lam_ref = eq.ops.solve(s, K, g, solver="cholesky")     # forward substitution fused in the factor kernel:
+        err = (lam - lam_ref).abs().max() / lam_ref.abs().max()  # another summation order, not bit-identical
+        assert err <= 1e-12

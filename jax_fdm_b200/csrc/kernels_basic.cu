@@ -35,7 +35,7 @@ __device__ __forceinline__ void st3(double* p, int64_t row, double3 v) {
 constexpr int kAsmRows = 256;
 constexpr int kAsmCap = 2560;   // staged entries per tile (20 KB); tiles with more fall back to direct stores
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 8)   // 8 CTAs per SM: the kernel lives on loads in flight
 assemble_kernel(int nnz, int Nf, int N, int Ns,
                 const int32_t* __restrict__ rowptr, const int32_t* __restrict__ entry_edge,
                 const int32_t* __restrict__ diag_pos, const int32_t* __restrict__ free_node,

@@ -43,9 +43,9 @@ CONFIG5_BATCH = 4096          # BASELINE config 5's fixed global batch (reported
 GLOBAL_BATCH = PER_GPU_BATCH  # the CPU arm times a bounded sample of one GPU's share
 CABLENET_NX = 200
 E2E_CHUNKS = 8
-# dram__bytes_read.sum + dram__bytes_write.sum of the forward Cholesky launch (B = 4096), from
-# profiles/r01b_chol_warp_v1_ncu.txt; null until a capture of the current kernel exists
-NCU_TRAFFIC_CHOL_FWD = 2.333e9
+# dram__bytes_read.sum + dram__bytes_write.sum of one chol_factor_mma_kernel launch (B = 4096), from
+# profiles/r01k_chol_final_ncu.txt (0.325 GB read + 0.960 GB written)
+NCU_TRAFFIC_CHOL_FWD = 1.284e9
 
 
 def peaks():
@@ -229,12 +229,22 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
     E, N, Nf, Ns, nnz = s.num_edges, s.num_nodes, s.num_free, s.num_supports, s.nnz
     fac = 8 * 1024 * ((Nf + 31) // 32)                       # factor columns, 32 doubles each, rows padded to 32
     Y = pipe.rhs.clone()
+    stage_opts = {m: L.SolveOpts(pipe.solver_id, 0, 0.0, 0, 0, m) for m in (1, 2, 4)}
     calls = [
         ("assemble (K1)", 8 * E + 8 * nnz + 24 * Nf,
          lambda: lib.fdm_assemble(s.plan, P(pipe.q), P(pipe.xyz_fixed), P(pipe.loads), P(pipe.K), P(pipe.rhs), B, E, 0, 0, st)),
-        ("band Cholesky factor+solve (K2b, forward)", 8 * nnz + 48 * Nf + fac,
+        ("band Cholesky forward solve (K2b: the three launches below)", 8 * nnz + 48 * Nf + fac,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(pipe.opts_f), st)),
+        ("  chol_factor_mma_kernel (factorisation + fused forward substitution)", 8 * nnz + 24 * Nf + fac + fac // 8,
+         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
+                               C.byref(stage_opts[1]), st)),
+        ("  chol_invdiag_kernel (8x8 diagonal blocks inverted in place)", 2 * 8 * 36 * 4 * ((Nf + 31) // 32),
+         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
+                               C.byref(stage_opts[2]), st)),
+        ("  chol_subst_kernel (backward substitution, factor streamed by TMA)", fac + fac // 8 + 24 * Nf,
+         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
+                               C.byref(stage_opts[4]), st)),
         ("positions", 24 * Nf + 24 * N,
          lambda: lib.fdm_positions(s.plan, P(pipe.x), P(pipe.xyz_fixed), P(pipe.xyz), B, 0, 0, st)),
         ("state (K4)", 8 * E + 24 * N + 40 * E + 24 * N,
@@ -242,7 +252,7 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
                                P(pipe.forces), P(pipe.residuals), B, E, 0, st)),
         ("loss + cotangent", 48 * Nf + 8,
          lambda: lib.fdm_loss_sqdist(P(pipe.x), P(pipe.x0), P(pipe.g), P(pipe.loss), Nf * 3, B, 0, st)),
-        ("band Cholesky solve with stored factor (K3 adjoint solve)", fac + 48 * Nf,
+        ("chol_subst_kernel, adjoint solve: forward + backward sweep over the stored factor", 2 * (fac + fac // 8) + 48 * Nf,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.g), P(pipe.lam), P(pipe.info_a), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(pipe.opts_a), st)),
         ("adjoint gradients (K3)", 8 * E + 24 * N + 24 * Nf + 8 * E + 24 * N + 24 * Ns,
@@ -427,7 +437,7 @@ def run_ours(args):
     if rank != 0:
         return None
 
-    dom = kernels[1]
+    dom = kernels[2]                                     # chol_factor_mma_kernel, the largest share of the step
     ms_per_step = sum_dev / steps
     value = B * world / (ms_per_step * 1e-3)
     e2e_value = B * world / (sum_e2e / steps * 1e-3)
@@ -449,7 +459,7 @@ def run_ours(args):
                 "how": f"pinned host q -> device, step, loss + q_bar -> pinned host, {E2E_CHUNKS} chunks on "
                        "separate streams so copies overlap kernels; host wall clock, synchronised both sides"},
         "gpu_launches": pipe.launches_per_step * steps,
-        "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm,
+        "roofline": {"kernel": dom["kernel"].strip(), "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm,
                      "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm, "traffic": NCU_TRAFFIC_CHOL_FWD,
                      "peak_source": hbm_src, "kernel_ms": dom["ms"],
                      "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],

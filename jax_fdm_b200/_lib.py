@@ -36,7 +36,7 @@ EXPORTS = [
 
 class SolveOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("max_iters", C.c_int32), ("tol", C.c_double),
-                ("check_every", C.c_int32), ("reuse_factor", C.c_int32)]
+                ("check_every", C.c_int32), ("reuse_factor", C.c_int32), ("stages", C.c_int32)]
 
 
 class FdmError(RuntimeError):

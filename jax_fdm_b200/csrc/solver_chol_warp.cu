@@ -798,7 +798,8 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   else if (p->hbw <= 15) { fkern = chol_factor_kernel<15>; skern = chol_subst_kernel<2>; }
   else if (p->hbw <= 23) { fkern = chol_factor_kernel<23>; skern = chol_subst_kernel<3>; }
   else { fkern = chol_factor_kernel<31>; skern = chol_subst_kernel<4>; }
-  if (!o.reuse_factor) {
+  const int stages = o.stages ? o.stages : 7;
+  if (!o.reuse_factor && (stages & 1)) {
     static const bool force_simt = std::getenv("FDM_CHOL_SIMT") != nullptr;   // A/B switch for profiling
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
     if (p->hbw <= 30 && !force_simt) {
@@ -807,11 +808,15 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+  }
+  if (!o.reuse_factor && (stages & 2)) {
     const int64_t items = batch * A.nblk * 4 * 8;
     chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
   }
-  const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
-  FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  skern<<<(unsigned)((batch + kSubWarps - 1) / kSubWarps), kSubThreads, smem, st>>>(A);
+  if (stages & 4) {
+    const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
+    FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    skern<<<(unsigned)((batch + kSubWarps - 1) / kSubWarps), kSubThreads, smem, st>>>(A);
+  }
   return fdm_check_launch("chol_warp_solve");
 }

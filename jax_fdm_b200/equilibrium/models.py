@@ -274,6 +274,29 @@ class EquilibriumModel:
         P = self.load_matrix(q, xyz_fixed, loads, structure)
         return self.linearsolve_fn(K, P)
 
+    def nodes_free_positions_jvp(self, q, xyz_fixed, loads, structure, q_dot=None, xyz_fixed_dot=None, loads_dot=None):
+        """
+        Forward-mode rule of the linear FDM step: returns (x_free, x_free_dot) with
+            K x_dot = b_dot - K_dot x,   K_dot = K(q_dot)  (K is linear in q),
+            b_dot = loads_dot_f - C_f^T (q_dot * C_s x_s) - C_f^T (q * C_s x_s_dot),
+        one extra 3-rhs solve with the factor / coarse inverse of the primal solve.  The reference has
+        no such rule: its sparse solve is reverse-only (sparse.py:1), which is why constraints
+        (constrained.py:88, jacfwd) and Hessians force the dense model (fdm.py:266-271).
+        """
+        s = structure
+        zero_like = torch.zeros_like
+        q_dot = zero_like(q) if q_dot is None else q_dot
+        xyz_fixed_dot = zero_like(xyz_fixed) if xyz_fixed_dot is None else xyz_fixed_dot
+        loads_dot = zero_like(loads) if loads_dot is None else loads_dot
+        opts = {k: v for k, v in self.solve_opts.items() if k != "fused_assembly"}
+        K, rhs = ops.assemble(s, q, xyz_fixed, loads)
+        ws = ops.Workspace()
+        x = ops.solve(s, K, rhs, workspace=ws, **opts)
+        K_dot, b1 = ops.assemble(s, q_dot, xyz_fixed, loads_dot)           # loads_dot_f - C_f^T (q_dot * C_s x_s)
+        _, b2 = ops.assemble(s, q, xyz_fixed_dot, zero_like(loads), want_K=False)   # - C_f^T (q * C_s x_s_dot)
+        x_dot = ops.solve(s, K, (b1 + b2 - ops.spmm(s, K_dot, x)).contiguous(), workspace=ws, reuse_factor=True, **opts)
+        return x, x_dot
+
     def nodes_equilibrium(self, q, xyz_fixed, loads_nodes, structure):
         return self.nodes_free_positions(q, xyz_fixed, loads_nodes, structure)
 

@@ -109,3 +109,25 @@ def test_tmax1_ignores_edge_loads_in_the_solve_but_reports_them():
     assert np.abs(st.xyz.cpu().numpy() - xyz).max() <= 1e-10 * np.abs(xyz).max()
     loads_ref = oracle.nodes_load_edges(xyz, prob.loads, eload, so)
     assert np.abs(st.loads.cpu().numpy() - loads_ref).max() <= 1e-12 * np.abs(loads_ref).max()
+
+
+@pytest.mark.parametrize("solver", ["cholesky", "pcg"])
+def test_forward_mode_rule_matches_finite_differences(solver):
+    """nodes_free_positions_jvp (tangent solve with the primal factor) against central differences of the
+    CPU oracle's forward solve, along a random direction in (q, xyz_fixed, loads)."""
+    import jax_fdm_b200.equilibrium as eq
+
+    prob, _ = problem(nx=7, seed=11)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    rng = np.random.default_rng(2)
+    dq, dxs, dp = (rng.standard_normal(a.shape) for a in (prob.q, prob.xyz_fixed, prob.loads))
+    model = eq.EquilibriumModelSparse(tmax=1, solver=solver, tol=1e-14)
+    x, x_dot = model.nodes_free_positions_jvp(T(prob.q), T(prob.xyz_fixed), T(prob.loads), s, T(dq), T(dxs), T(dp))
+    eps = 1e-6
+    xp = oracle.forward(prob.q + eps * dq, prob.xyz_fixed + eps * dxs, prob.loads + eps * dp, so)[1]
+    xm = oracle.forward(prob.q - eps * dq, prob.xyz_fixed - eps * dxs, prob.loads - eps * dp, so)[1]
+    fd = (xp - xm) / (2 * eps)
+    x0 = oracle.forward(prob.q, prob.xyz_fixed, prob.loads, so)[1]
+    assert np.abs(x.cpu().numpy() - x0).max() <= 1e-10 * np.abs(x0).max()
+    assert np.abs(x_dot.cpu().numpy() - fd).max() <= 1e-6 * np.abs(fd).max()

@@ -223,6 +223,29 @@ int fdm_edge_loads_vjp(const fdm_plan* plan, const double* d_xyz, const double* 
                        const double* d_cot, double* d_xyz_bar, double* d_edges_load_bar,
                        int64_t batch, int64_t edges_load_stride, void* stream);
 
+/* Tributary FACE (area) loads in the global frame (models.py:333-344, loads.py:35-71, 187-288): every
+ * edge takes, from each of its (first two) incident faces, the face load times the area of the triangle
+ * (edge, face centroid); the edge total goes half to each end node.  The mesh arrays are device int32
+ * operands built by the host mirror of EquilibriumMeshStructure (structures/meshes.py:108-204):
+ *   d_faces (F,D) vertex indices padded -1;  d_edges_faces (E,2) padded -1;
+ *   d_faces_edges (F,D): edge on side i of the face, -1 when the face is not among that edge's two;
+ *   d_node_faces_ptr (N+1), d_node_faces (sum deg): faces around each node.
+ * d_centroids (B,F,3) is caller-provided scratch.  loads_out_n = loads_in_n + tributary face loads. */
+int fdm_face_loads(const fdm_plan* plan, const int32_t* d_faces, int64_t num_faces, int64_t max_deg,
+                   const int32_t* d_edges_faces, const double* d_xyz, const double* d_loads_in,
+                   const double* d_faces_load, double* d_centroids, double* d_loads_out, int64_t batch,
+                   int64_t loads_stride, int64_t faces_load_stride, void* stream);
+
+/* VJP of fdm_face_loads at the cotangent d_cot (B,N,3).  Outputs OVERWRITTEN, any may be NULL:
+ * xyz_bar (B,N,3) [through areas and centroids], faces_load_bar (B,F,3).  d_centroids as filled by the
+ * forward call; d_cen_bar (B,F,3) is scratch. */
+int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num_faces, int64_t max_deg,
+                       const int32_t* d_edges_faces, const int32_t* d_faces_edges,
+                       const int32_t* d_node_faces_ptr, const int32_t* d_node_faces, const double* d_xyz,
+                       const double* d_faces_load, const double* d_centroids, const double* d_cot,
+                       double* d_cen_bar, double* d_xyz_bar, double* d_faces_load_bar, int64_t batch,
+                       int64_t faces_load_stride, void* stream);
+
 /* ---- helper used by the benchmark's loss (above the path; kept here so the timed region
  * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */
 int fdm_loss_sqdist(const double* d_x, const double* d_x0, double* d_g, double* d_loss,

@@ -29,7 +29,7 @@ EXPORTS = [
     "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",
     "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_solve_from_q", "fdm_spmm",
     "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_adjoint_grads", "fdm_edge_loads",
-    "fdm_edge_loads_vjp", "fdm_loss_sqdist",
+    "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_loss_sqdist",
     "fdm_last_error", "fdm_version",
 ]
 
@@ -93,6 +93,10 @@ def lib():
     L.fdm_edge_loads.restype = C.c_int
     L.fdm_edge_loads_vjp.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.fdm_edge_loads_vjp.restype = C.c_int
+    L.fdm_face_loads.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.fdm_face_loads.restype = C.c_int
+    L.fdm_face_loads_vjp.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.fdm_face_loads_vjp.restype = C.c_int
     L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.fdm_loss_sqdist.restype = C.c_int
     L.fdm_last_error.argtypes = []

@@ -329,6 +329,32 @@ int fdm_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges
   return launch_edge_loads_vjp(p, xyz, edges_load, cot, xyz_bar, edges_load_bar, batch, es, (cudaStream_t)stream);
 }
 
+int fdm_face_loads(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
+                   const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* out,
+                   int64_t batch, int64_t ls, int64_t fs, void* stream) {
+  if (!ready(p, "fdm_face_loads")) return FDM_ERR_INVALID;
+  if (!faces || !edges_faces || !xyz || !loads_in || !faces_load || !cen || !out || F <= 0 || D < 3 || batch <= 0) {
+    fdm_set_error("fdm_face_loads: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_face_loads(p, faces, F, D, edges_faces, xyz, loads_in, faces_load, cen, out, batch, ls, fs,
+                           (cudaStream_t)stream);
+}
+
+int fdm_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
+                       const int32_t* faces_edges, const int32_t* nf_ptr, const int32_t* nf, const double* xyz,
+                       const double* faces_load, const double* cen, const double* cot, double* cen_bar,
+                       double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs, void* stream) {
+  if (!ready(p, "fdm_face_loads_vjp")) return FDM_ERR_INVALID;
+  if (!faces || !edges_faces || !faces_edges || !nf_ptr || !nf || !xyz || !faces_load || !cen || !cot || !cen_bar ||
+      F <= 0 || D < 3 || batch <= 0) {
+    fdm_set_error("fdm_face_loads_vjp: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_face_loads_vjp(p, faces, F, D, edges_faces, faces_edges, nf_ptr, nf, xyz, faces_load, cen, cot, cen_bar,
+                               xyz_bar, fl_bar, batch, fs, (cudaStream_t)stream);
+}
+
 int fdm_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                     int64_t batch, int64_t x0_stride, void* stream) {
   if (!x || !x0 || n <= 0 || batch <= 0) {

@@ -402,6 +402,157 @@ edge_loads_vjp_kernel(int N, int E, const int32_t* __restrict__ edge_nodes, cons
 }
 
 // ---------------------------------------------------------------------------------------
+// tributary face loads in the global frame (loads.py:35-71, 187-288)
+//   centroid_f = mean of the face's vertices                                    (thread per face)
+//   load_e     = sum_{f in first two faces of e} A(x_t, x_h, centroid_f) w_f,  A = |(x_h-x_t) x (c-x_t)| / 2
+//   out_n      = loads_n + 1/2 sum_{e incident to n} load_e                     (thread per node)
+// reverse:  per face: w_bar_f, centroid_bar_f over the face's edges; per node: direct area terms of its
+// incident edges + centroid_bar_f / deg_f of the faces around it.  No atomics, fixed summation orders.
+// ---------------------------------------------------------------------------------------
+struct TriGrad { double area; double3 gh, gc; };   // dA/dx_h, dA/dc  (dA/dx_t = -(gh + gc))
+
+__device__ __forceinline__ TriGrad tri_area(double3 a, double3 b, double3 c, bool want_grad) {
+  const double3 u = make_double3(b.x - a.x, b.y - a.y, b.z - a.z), v = make_double3(c.x - a.x, c.y - a.y, c.z - a.z);
+  const double3 n = make_double3(u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x);
+  const double len = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+  TriGrad g;
+  g.area = 0.5 * len;
+  g.gh = g.gc = make_double3(0.0, 0.0, 0.0);
+  if (want_grad) {
+    const double s = 0.5 / len;   // zero-area triangle -> NaN, like the norm's gradient in the reference
+    const double3 h = make_double3(n.x * s, n.y * s, n.z * s);
+    g.gh = make_double3(v.y * h.z - v.z * h.y, v.z * h.x - v.x * h.z, v.x * h.y - v.y * h.x);   // v x n^ / 2
+    g.gc = make_double3(h.y * u.z - h.z * u.y, h.z * u.x - h.x * u.z, h.x * u.y - h.y * u.x);   // n^ x u / 2
+  }
+  return g;
+}
+
+__global__ void __launch_bounds__(kThreads)
+face_centroids_kernel(int F, int D, int N, const int32_t* __restrict__ faces, const double* __restrict__ xyz,
+                      double* __restrict__ cen) {
+  const int64_t b = blockIdx.y;
+  const int f = blockIdx.x * kThreads + threadIdx.x;
+  if (f >= F) return;
+  xyz += b * (int64_t)N * 3;
+  double3 acc = make_double3(0.0, 0.0, 0.0);
+  int cnt = 0;
+  for (int i = 0; i < D; ++i) {
+    const int v = __ldg(faces + (int64_t)f * D + i);
+    if (v >= 0) { const double3 x = ld3(xyz, v); acc.x += x.x; acc.y += x.y; acc.z += x.z; ++cnt; }
+  }
+  const double w = 1.0 / cnt;
+  st3(cen + b * (int64_t)F * 3, f, make_double3(acc.x * w, acc.y * w, acc.z * w));
+}
+
+__global__ void __launch_bounds__(kThreads)
+face_loads_kernel(int N, int F, const int32_t* __restrict__ edges_faces, const int32_t* __restrict__ ninc_ptr,
+                  const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
+                  const double* __restrict__ xyz, const double* __restrict__ loads_in,
+                  const double* __restrict__ faces_load, const double* __restrict__ cen, double* __restrict__ out,
+                  int64_t ls, int64_t fs) {
+  const int64_t b = blockIdx.y;
+  const int n = blockIdx.x * kThreads + threadIdx.x;
+  if (n >= N) return;
+  xyz += b * (int64_t)N * 3;
+  cen += b * (int64_t)F * 3;
+  faces_load += b * fs;
+  double3 acc = make_double3(0.0, 0.0, 0.0);
+  const double3 xn = ld3(xyz, n);
+  const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
+  for (int k = k0; k < k1; ++k) {
+    const int code = __ldg(ninc_edge + k), e = code >> 1;
+    const double3 xo = ld3(xyz, __ldg(ninc_other + k));
+    const double3 xt = (code & 1) ? xo : xn, xh = (code & 1) ? xn : xo;   // code & 1: n is the head
+    for (int slot = 0; slot < 2; ++slot) {
+      const int f = __ldg(edges_faces + 2 * (int64_t)e + slot);
+      if (f >= 0) {
+        const double a = tri_area(xt, xh, ld3(cen, f), false).area;
+        const double3 w = ld3(faces_load, f);
+        acc.x += a * w.x; acc.y += a * w.y; acc.z += a * w.z;
+      }
+    }
+  }
+  const double3 p = ld3(loads_in + b * ls, n);
+  st3(out + b * (int64_t)N * 3, n, make_double3(p.x + 0.5 * acc.x, p.y + 0.5 * acc.y, p.z + 0.5 * acc.z));
+}
+
+__global__ void __launch_bounds__(kThreads)
+face_loads_vjp_faces_kernel(int F, int D, int N, const int32_t* __restrict__ faces_edges,
+                            const int32_t* __restrict__ edge_nodes, const double* __restrict__ xyz,
+                            const double* __restrict__ faces_load, const double* __restrict__ cen,
+                            const double* __restrict__ cot, double* __restrict__ cen_bar,
+                            double* __restrict__ fl_bar, int64_t fs, int E) {
+  const int64_t b = blockIdx.y;
+  const int f = blockIdx.x * kThreads + threadIdx.x;
+  if (f >= F) return;
+  xyz += b * (int64_t)N * 3;
+  cot += b * (int64_t)N * 3;
+  const double3 c = ld3(cen + b * (int64_t)F * 3, f);
+  const double3 w = ld3(faces_load + b * fs, f);
+  double3 cb = make_double3(0.0, 0.0, 0.0), wb = make_double3(0.0, 0.0, 0.0);
+  for (int i = 0; i < D; ++i) {
+    const int e = __ldg(faces_edges + (int64_t)f * D + i);
+    if (e < 0) continue;
+    const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + e);
+    const double3 ct = ld3(cot, th.x), ch = ld3(cot, th.y);
+    const double3 hc = make_double3(0.5 * (ct.x + ch.x), 0.5 * (ct.y + ch.y), 0.5 * (ct.z + ch.z));
+    const TriGrad g = tri_area(ld3(xyz, th.x), ld3(xyz, th.y), c, true);
+    wb.x += g.area * hc.x; wb.y += g.area * hc.y; wb.z += g.area * hc.z;
+    const double abar = w.x * hc.x + w.y * hc.y + w.z * hc.z;       // cotangent of the triangle area
+    cb.x += abar * g.gc.x; cb.y += abar * g.gc.y; cb.z += abar * g.gc.z;
+  }
+  if (cen_bar) st3(cen_bar + b * (int64_t)F * 3, f, cb);
+  if (fl_bar) st3(fl_bar + b * (int64_t)F * 3, f, wb);
+}
+
+__global__ void __launch_bounds__(kThreads)
+face_loads_vjp_nodes_kernel(int N, int F, int D, const int32_t* __restrict__ faces,
+                            const int32_t* __restrict__ edges_faces, const int32_t* __restrict__ node_faces_ptr,
+                            const int32_t* __restrict__ node_faces, const int32_t* __restrict__ ninc_ptr,
+                            const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
+                            const double* __restrict__ xyz, const double* __restrict__ faces_load,
+                            const double* __restrict__ cen, const double* __restrict__ cot,
+                            const double* __restrict__ cen_bar, double* __restrict__ xyz_bar, int64_t fs) {
+  const int64_t b = blockIdx.y;
+  const int n = blockIdx.x * kThreads + threadIdx.x;
+  if (n >= N) return;
+  xyz += b * (int64_t)N * 3;
+  cot += b * (int64_t)N * 3;
+  cen += b * (int64_t)F * 3;
+  cen_bar += b * (int64_t)F * 3;
+  faces_load += b * fs;
+  double3 acc = make_double3(0.0, 0.0, 0.0);
+  const double3 xn = ld3(xyz, n), cn = ld3(cot, n);
+  const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
+  for (int k = k0; k < k1; ++k) {
+    const int code = __ldg(ninc_edge + k), e = code >> 1, o = __ldg(ninc_other + k);
+    const bool is_head = code & 1;
+    const double3 xo = ld3(xyz, o), co = ld3(cot, o);
+    const double3 hc = make_double3(0.5 * (cn.x + co.x), 0.5 * (cn.y + co.y), 0.5 * (cn.z + co.z));
+    for (int slot = 0; slot < 2; ++slot) {
+      const int f = __ldg(edges_faces + 2 * (int64_t)e + slot);
+      if (f < 0) continue;
+      const TriGrad g = tri_area(is_head ? xo : xn, is_head ? xn : xo, ld3(cen, f), true);
+      const double3 w = ld3(faces_load, f);
+      const double abar = w.x * hc.x + w.y * hc.y + w.z * hc.z;
+      // dA/dx_head = gh ; dA/dx_tail = -(gh + gc)
+      const double3 gn = is_head ? g.gh : make_double3(-(g.gh.x + g.gc.x), -(g.gh.y + g.gc.y), -(g.gh.z + g.gc.z));
+      acc.x += abar * gn.x; acc.y += abar * gn.y; acc.z += abar * gn.z;
+    }
+  }
+  const int f0 = __ldg(node_faces_ptr + n), f1 = __ldg(node_faces_ptr + n + 1);
+  for (int k = f0; k < f1; ++k) {
+    const int f = __ldg(node_faces + k);
+    int cnt = 0;
+    for (int i = 0; i < D; ++i) cnt += __ldg(faces + (int64_t)f * D + i) >= 0;
+    const double3 cbv = ld3(cen_bar, f);
+    const double w = 1.0 / cnt;
+    acc.x += w * cbv.x; acc.y += w * cbv.y; acc.z += w * cbv.z;
+  }
+  st3(xyz_bar + b * (int64_t)N * 3, n, acc);
+}
+
+// ---------------------------------------------------------------------------------------
 // loss helper: g = x - x0, loss_b = 0.5 sum g^2   (one CTA per design, fixed-order reduction)
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
@@ -533,6 +684,38 @@ int launch_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* ed
         edges_load_bar ? edges_load_bar + b0 * p->E * 3 : nullptr, es);
   }
   return fdm_check_launch("edge_loads_vjp");
+}
+
+int launch_face_loads(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
+                      const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* out,
+                      int64_t batch, int64_t ls, int64_t fs, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    face_centroids_kernel<<<grid_for(F, nb), kThreads, 0, st>>>((int)F, (int)D, (int)p->N, faces, xyz + b0 * p->N * 3,
+                                                               cen + b0 * F * 3);
+    face_loads_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
+        (int)p->N, (int)F, edges_faces, d.ninc_ptr, d.ninc_edge, d.ninc_other, xyz + b0 * p->N * 3, loads_in + b0 * ls,
+        faces_load + b0 * fs, cen + b0 * F * 3, out + b0 * p->N * 3, ls, fs);
+  }
+  return fdm_check_launch("face_loads");
+}
+
+int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
+                          const int32_t* faces_edges, const int32_t* nf_ptr, const int32_t* nf, const double* xyz,
+                          const double* faces_load, const double* cen, const double* cot, double* cen_bar,
+                          double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    face_loads_vjp_faces_kernel<<<grid_for(F, nb), kThreads, 0, st>>>(
+        (int)F, (int)D, (int)p->N, faces_edges, d.edge_nodes, xyz + b0 * p->N * 3, faces_load + b0 * fs, cen + b0 * F * 3,
+        cot + b0 * p->N * 3, cen_bar + b0 * F * 3, fl_bar ? fl_bar + b0 * F * 3 : nullptr, fs, (int)p->E);
+    if (xyz_bar)
+      face_loads_vjp_nodes_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
+          (int)p->N, (int)F, (int)D, faces, edges_faces, nf_ptr, nf, d.ninc_ptr, d.ninc_edge, d.ninc_other,
+          xyz + b0 * p->N * 3, faces_load + b0 * fs, cen + b0 * F * 3, cot + b0 * p->N * 3, cen_bar + b0 * F * 3,
+          xyz_bar + b0 * p->N * 3, fs);
+  }
+  return fdm_check_launch("face_loads_vjp");
 }
 
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,

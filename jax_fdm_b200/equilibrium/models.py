@@ -164,6 +164,24 @@ class _NodesLoad(torch.autograd.Function):
         return xb, g, eb, None
 
 
+class _FacesLoad(torch.autograd.Function):
+    """nodes_load with tributary face loads in the global frame (models.py:333-344, loads.py:35-71, 187-288)."""
+
+    @staticmethod
+    def forward(ctx, xyz, loads_nodes, faces_load, structure):
+        out, cen = ops.face_loads(structure, xyz, loads_nodes, faces_load)
+        ctx.structure = structure
+        ctx.save_for_backward(xyz, faces_load, cen)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xyz, faces_load, cen = ctx.saved_tensors
+        xb, fb = ops.face_loads_vjp(ctx.structure, xyz, faces_load, cen, g.contiguous(),
+                                    want_xyz=ctx.needs_input_grad[0], want_faces=ctx.needs_input_grad[2])
+        return xb, g, fb, None
+
+
 class _FixedPoint(torch.autograd.Function):
     """
     x* = K(q)^{-1} P(x*),  P(x) = nodes_load(xyz(x))[free] - R_fixed(q, x_s): the fixed-point
@@ -174,7 +192,7 @@ class _FixedPoint(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, q, xyz_fixed, loads_nodes, edges_load, x_init, structure, opts, config):
+    def forward(ctx, q, xyz_fixed, loads_nodes, edges_load, faces_load, x_init, structure, opts, config):
         s = structure
         K, rhs0 = ops.assemble(s, q, xyz_fixed, torch.zeros_like(loads_nodes))     # rhs0 = -R_fixed
         ws = ops.Workspace()
@@ -187,21 +205,28 @@ class _FixedPoint(torch.autograd.Function):
 
         free = torch.as_tensor(s.indices_free, device=q.device)
 
+        has_faces = faces_load.numel() > 0
+
         def f(_, x):
             xyz = ops.positions(s, x, xyz_fixed)
             loads = ops.edge_loads(s, xyz, loads_nodes, edges_load)
+            if has_faces:
+                loads, _ = ops.face_loads(s, xyz, loads, faces_load)
             return solve_fn(loads.index_select(-2, free) + rhs0)
 
         x = solver_fixedpoint_implicit(config.get("solver"), config, f, None, x_init)
-        ctx.structure, ctx.solve_fn, ctx.free = s, solve_fn, free
-        ctx.save_for_backward(q, xyz_fixed, edges_load, x)
+        ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces = s, solve_fn, free, has_faces
+        ctx.save_for_backward(q, xyz_fixed, edges_load, faces_load, x)
         return x
 
     @staticmethod
     def backward(ctx, g):
-        q, xyz_fixed, edges_load, x = ctx.saved_tensors
-        s, solve_fn, free = ctx.structure, ctx.solve_fn, ctx.free
+        q, xyz_fixed, edges_load, faces_load, x = ctx.saved_tensors
+        s, solve_fn, free, has_faces = ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces
         xyz = ops.positions(s, x, xyz_fixed)
+        cen = None
+        if has_faces:   # centroids of the converged geometry, needed by the face-load transpose
+            _, cen = ops.face_loads(s, xyz, torch.zeros_like(xyz), faces_load)
 
         def scatter_free(lam):
             c = torch.zeros(lam.shape[:-2] + (s.num_nodes, 3), dtype=lam.dtype, device=lam.device)
@@ -209,23 +234,31 @@ class _FixedPoint(torch.autograd.Function):
             return c
 
         def loads_vjp_x(lam):                       # J_P^T lam, free rows
-            xb, _ = ops.edge_loads_vjp(s, xyz, edges_load, scatter_free(lam), want_edges=False)
+            c = scatter_free(lam)
+            xb, _ = ops.edge_loads_vjp(s, xyz, edges_load, c, want_edges=False)
+            if has_faces:
+                xb = xb + ops.face_loads_vjp(s, xyz, faces_load, cen, c, want_faces=False)[0]
             return xb.index_select(-2, free)
 
         w, lam = fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, g.contiguous())
         # cotangents of f(theta, x*) at w: K and R_fixed terms (K3), then the load terms
         qbar, pbar, xsbar = ops.adjoint_grads(s, q, xyz, lam)
         xb, ebar = ops.edge_loads_vjp(s, xyz, edges_load, pbar)
+        fbar = None
+        if has_faces:
+            xb2, fbar = ops.face_loads_vjp(s, xyz, faces_load, cen, pbar)
+            xb = xb + xb2
         fixed = torch.as_tensor(s.indices_fixed, device=q.device)
-        xsbar = xsbar + xb.index_select(-2, fixed)  # edge lengths at the supports depend on x_s
-        return qbar, xsbar, pbar, ebar, None, None, None, None
+        xsbar = xsbar + xb.index_select(-2, fixed)  # edge lengths / face areas at the supports depend on x_s
+        return qbar, xsbar, pbar, ebar, fbar, None, None, None, None
 
 
 class EquilibriumModel:
     """
     FDM model (models.py:47-91).  `tmax=1`: one linear FDM step with nodal loads.  `tmax>1`: the
-    fixed-point iteration for shape-dependent loads (edge line loads in the global frame) with the
-    implicit adjoint; face loads and local (follower) frames raise NotImplementedError.
+    fixed-point iteration for shape-dependent loads (edge line loads and, on mesh structures, face area
+    loads, both in the global frame) with the implicit adjoint; local (follower) frames raise
+    NotImplementedError.
     The dense variant assembles the same K and solves with the same kernels: the "dense" vs
     "sparse" split of the reference is a storage choice, not different arithmetic.
     """
@@ -306,12 +339,14 @@ class EquilibriumModel:
     def nodes_load(self, xyz, load_state, structure):
         """models.py:290-344: nodal loads plus tributary edge loads when an (E,3) edge load is present."""
         nodes_load, edges_load, faces_load = load_state
-        if isinstance(faces_load, torch.Tensor) and faces_load.numel() > 1:
-            raise NotImplementedError("face tributary loads are outside this build (SURVEY.md §8f)")
-        if isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1:
-            if self.is_load_local:
-                raise NotImplementedError("local (follower) edge loads are outside this build (SURVEY.md §8f)")
-            return _NodesLoad.apply(xyz, nodes_load, edges_load, structure)
+        has_edges = isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1
+        has_faces = isinstance(faces_load, torch.Tensor) and faces_load.numel() > 1 and hasattr(structure, "faces_indexed")
+        if (has_edges or has_faces) and self.is_load_local:
+            raise NotImplementedError("local (follower) load frames are outside this build (SURVEY.md §8f)")
+        if has_edges:
+            nodes_load = _NodesLoad.apply(xyz, nodes_load, edges_load, structure)
+        if has_faces:   # a non-scalar face load only takes effect on a mesh structure (models.py:333-344)
+            nodes_load = _FacesLoad.apply(xyz, nodes_load, faces_load, structure)
         return nodes_load
 
     def equilibrium_iterative_xyz(self, q, xyz_fixed, load_state, structure, xyz_free_init=None, tmax=100,
@@ -324,12 +359,16 @@ class EquilibriumModel:
         edges_load = load_state.edges
         if not (isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1):
             edges_load = torch.zeros((structure.num_edges, 3), dtype=q.dtype, device=q.device)
-        if isinstance(load_state.faces, torch.Tensor) and load_state.faces.numel() > 1:
-            raise NotImplementedError("face tributary loads are outside this build (SURVEY.md §8f)")
+        faces_load = load_state.faces
+        if not (isinstance(faces_load, torch.Tensor) and faces_load.numel() > 1 and hasattr(structure, "faces_indexed")):
+            faces_load = torch.zeros((0, 3), dtype=q.dtype, device=q.device)
+        if self.is_load_local:
+            raise NotImplementedError("local (follower) load frames are outside this build (SURVEY.md §8f)")
         config = {"tmax": tmax, "eta": eta, "verbose": verbose, "solver": solver or self.itersolve_fn}
         self.last_solver_config = config
-        return _FixedPoint.apply(q, xyz_fixed, load_state.nodes, edges_load, xyz_free_init.detach(), structure,
-                                 self.solve_opts, config)
+        opts = {k: v for k, v in self.solve_opts.items() if k != "fused_assembly"}
+        return _FixedPoint.apply(q, xyz_fixed, load_state.nodes, edges_load, faces_load, xyz_free_init.detach(),
+                                 structure, opts, config)
 
     def equilibrium_state(self, q, xyz, loads_nodes, structure):
         vectors, lengths, forces, residuals = _State.apply(q, xyz, loads_nodes, structure)

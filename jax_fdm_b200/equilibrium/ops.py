@@ -315,6 +315,53 @@ def edge_loads_vjp(structure, xyz, edges_load, cot, want_xyz=True, want_edges=Tr
     return xyz_bar, e_bar
 
 
+def face_loads(structure, xyz, loads_in, faces_load):
+    """nodes_load with tributary face (area) loads, global frame (loads.py:35-71, 187-288) -> (loads, centroids)."""
+    s = structure
+    N, Fn = s.num_nodes, s.num_faces
+    xyz = _chk(xyz, "xyz", (N, 3))
+    loads_in = _chk(loads_in, "loads", (N, 3))
+    faces_load = _chk(faces_load, "faces_load", (Fn, 3))
+    B, batched = _resolve_batch((xyz, 2), (loads_in, 2), (faces_load, 2))
+    if batched and xyz.dim() == 2:
+        xyz = xyz.expand(B, N, 3).contiguous()
+    lead = (B,) if batched else ()
+    d = s.device_arrays(xyz.device)
+    cen = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device)
+    out = torch.empty(lead + (N, 3), dtype=F64, device=xyz.device)
+    L.check(L.lib().fdm_face_loads(s.plan, _ptr(d["faces"]), Fn, s.faces_indexed.shape[1], _ptr(d["edges_faces"]),
+                                   _ptr(xyz), _ptr(loads_in), _ptr(faces_load), _ptr(cen), _ptr(out), B,
+                                   _stride(loads_in, 2), _stride(faces_load, 2), _stream()))
+    return out, cen
+
+
+def face_loads_vjp(structure, xyz, faces_load, centroids, cot, want_xyz=True, want_faces=True):
+    """VJP of `face_loads` -> (xyz_bar, faces_load_bar); the cotangent of loads_in is `cot` itself."""
+    s = structure
+    N, Fn = s.num_nodes, s.num_faces
+    xyz = _chk(xyz, "xyz", (N, 3))
+    faces_load = _chk(faces_load, "faces_load", (Fn, 3))
+    cot = _chk(cot, "cot", (N, 3))
+    centroids = _chk(centroids, "centroids", (Fn, 3))
+    B, batched = _resolve_batch((xyz, 2), (cot, 2))
+    if batched and xyz.dim() == 2:
+        xyz = xyz.expand(B, N, 3).contiguous()
+    if batched and cot.dim() == 2:
+        cot = cot.expand(B, N, 3).contiguous()
+    lead = (B,) if batched else ()
+    d = s.device_arrays(xyz.device)
+    cen_bar = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device)
+    xyz_bar = torch.empty(lead + (N, 3), dtype=F64, device=xyz.device) if want_xyz else None
+    fl_bar = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device) if want_faces else None
+    L.check(L.lib().fdm_face_loads_vjp(s.plan, _ptr(d["faces"]), Fn, s.faces_indexed.shape[1], _ptr(d["edges_faces"]),
+                                       _ptr(d["faces_edges"]), _ptr(d["node_faces_ptr"]), _ptr(d["node_faces"]),
+                                       _ptr(xyz), _ptr(faces_load), _ptr(centroids), _ptr(cot), _ptr(cen_bar),
+                                       _ptr(xyz_bar), _ptr(fl_bar), B, _stride(faces_load, 2), _stream()))
+    if fl_bar is not None and batched and faces_load.dim() == 2:
+        fl_bar = fl_bar.sum(0)
+    return xyz_bar, fl_bar
+
+
 def loss_sqdist(x, x0):
     """loss_b = 0.5 * sum (x - x0)^2 per design, g = x - x0 (benchmark loss)."""
     x = x.contiguous()

@@ -21,6 +21,8 @@ __all__ = [
     "GraphSparse",
     "EquilibriumStructure",
     "EquilibriumStructureSparse",
+    "EquilibriumMeshStructure",
+    "EquilibriumMeshStructureSparse",
     "IndexArray",
 ]
 
@@ -215,3 +217,93 @@ class EquilibriumStructureSparse(EquilibriumStructure, GraphSparse):
     @property
     def part_of_row(self):
         return self._get(L.ARR_PART_OF_ROW, np.int32, self.num_free)
+
+
+class EquilibriumMeshStructureSparse(EquilibriumStructureSparse):
+    """
+    Mesh flavour (structures/structures.py:358-505, structures/meshes.py:29-293): the graph structure plus
+    faces, for tributary area loads.  `faces` is (F, maxdeg) of vertex KEYS padded with -1.
+
+    Attributes named as in the reference: `vertices`, `faces`, `faces_indexed`, `edges_faces_indexed`
+    (first two incident faces of every edge over both windings, padded -1, meshes.py:146-204),
+    `connectivity_faces_vertices` (row-normalised face-vertex matrix, meshes.py:361-399), `face_keys`,
+    `num_faces`.  `faces_edges` and `node_faces` are the transposed adjacencies the reverse kernels need.
+    """
+
+    def __init__(self, vertices, faces, edges, supports, face_keys=None, device=0, **kwargs):
+        super().__init__(nodes=vertices, edges=edges, supports=supports, device=device, **kwargs)
+        self.vertices = self.nodes
+        self.faces = np.asarray(faces, dtype=np.int64)
+        assert self.faces.ndim == 2 and self.faces.shape[1] > 2, "The mesh faces must have at least 3 vertices each"
+        self.face_keys = np.arange(self.faces.shape[0]) if face_keys is None else np.asarray(face_keys, dtype=np.int64)
+        vi = self.node_index
+        self.faces_indexed = np.array([[vi[int(v)] if v >= 0 else int(v) for v in face] for face in self.faces],
+                                      dtype=np.int64)
+        self.edges_faces_indexed = self._edges_faces_indexed()
+        self.faces_edges, self.node_faces_ptr, self.node_faces = self._transposed_adjacency()
+        self._dev = None
+
+    @property
+    def num_faces(self):
+        return int(self.faces.shape[0])
+
+    @property
+    def vertex_index(self):
+        return self.node_index
+
+    @property
+    def connectivity_faces_vertices(self):
+        import scipy.sparse as sp
+
+        mask = self.faces_indexed >= 0
+        counts = mask.sum(axis=1)
+        rows = np.repeat(np.arange(self.num_faces), counts)
+        return sp.coo_matrix((np.repeat(1.0 / counts, counts), (rows, self.faces_indexed[mask])),
+                             shape=(self.num_faces, self.num_nodes)).tocsc()
+
+    def _edges_faces_indexed(self):
+        half = {}
+        for f, face in enumerate(self.faces_indexed):
+            clean = [int(v) for v in face if v >= 0]
+            for u, v in zip(clean, clean[1:] + clean[:1]):
+                half.setdefault((u, v), []).append(f)
+        out = np.full((self.num_edges, 2), -1, dtype=np.int64)
+        for e, (u, v) in enumerate(self.edges_indexed):
+            fs = half.get((int(u), int(v)), []) + half.get((int(v), int(u)), [])
+            out[e, :len(fs[:2])] = fs[:2]
+        return out
+
+    def _transposed_adjacency(self):
+        eidx = {}
+        for e, (u, v) in enumerate(self.edges_indexed):
+            eidx[(int(u), int(v))] = e
+            eidx[(int(v), int(u))] = e
+        F, D = self.faces_indexed.shape
+        fe = np.full((F, D), -1, dtype=np.int32)
+        nf = [[] for _ in range(self.num_nodes)]
+        for f, face in enumerate(self.faces_indexed):
+            clean = [int(v) for v in face if v >= 0]
+            for i, (u, v) in enumerate(zip(clean, clean[1:] + clean[:1])):
+                e = eidx.get((u, v), -1)
+                if e >= 0 and f in self.edges_faces_indexed[e]:
+                    fe[f, i] = e
+            for v in clean:
+                nf[v].append(f)
+        ptr = np.zeros(self.num_nodes + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(x) for x in nf])
+        flat = np.array([f for x in nf for f in x], dtype=np.int32)
+        return fe, ptr, flat
+
+    def device_arrays(self, device):
+        """int32 device copies of the mesh adjacency (built once)."""
+        import torch
+
+        if self._dev is None or self._dev["faces"].device != device:
+            t = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32), device=device)
+            self._dev = {"faces": t(self.faces_indexed), "edges_faces": t(self.edges_faces_indexed),
+                         "faces_edges": t(self.faces_edges), "node_faces_ptr": t(self.node_faces_ptr),
+                         "node_faces": t(self.node_faces if self.node_faces.size else np.zeros(1))}
+        return self._dev
+
+
+EquilibriumMeshStructure = EquilibriumMeshStructureSparse

@@ -39,5 +39,6 @@ from .model import (  # noqa: F401
     forward,
     forward_adjoint,
     nodes_load_edges,
+    nodes_load_faces,
     fixed_point_forward,
 )

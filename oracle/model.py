@@ -216,7 +216,32 @@ def nodes_load_edges(xyz, loads_nodes, edges_load, s):
     return out
 
 
-def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=1e-6):
+def nodes_load_faces(xyz, loads_nodes, faces_load, s, faces_indexed, edges_faces_indexed):
+    """
+    models.py:333-344 with loads.py:35-71, 187-288 (global frame): every edge takes, from each of its
+    (first two) incident faces, the face load times the area of the triangle (edge, face centroid)
+    (loads.py:226-288); half of the edge total goes to each end node (loads.py:435-465).
+    `faces_indexed` (F, maxdeg) padded -1 and `edges_faces_indexed` (E, 2) padded -1 as the reference
+    defines them (structures/meshes.py:108-204).
+    """
+    mask = faces_indexed >= 0
+    cen = np.stack([xyz[face[m]].mean(axis=0) for face, m in zip(faces_indexed, mask)])
+    ei = s.edges_indexed
+    a, b = xyz[ei[:, 0]], xyz[ei[:, 1]]
+    edge_load = np.zeros((ei.shape[0], 3))
+    for slot in range(2):
+        f = edges_faces_indexed[:, slot]
+        ok = f >= 0
+        c = cen[np.where(ok, f, 0)]
+        area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1)
+        edge_load += np.where(ok, area, 0.0)[:, None] * np.asarray(faces_load)[np.where(ok, f, 0)]
+    out = np.array(loads_nodes, dtype=np.float64, copy=True)
+    np.add.at(out, ei[:, 0], 0.5 * edge_load)
+    np.add.at(out, ei[:, 1], 0.5 * edge_load)
+    return out
+
+
+def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=1e-6, faces=None):
     """
     models.py:410-478, 512-618 + fixed_point.py:139-198: one linear step with the nodal loads, then
     x <- K^{-1} (nodes_load(xyz(x))[free] - R_fixed) until the mean nodal move <= eta or tmax steps.
@@ -227,8 +252,10 @@ def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=
 
     def f(x):
         xyz = nodes_positions(x, xyz_fixed, s)
-        p = nodes_load_edges(xyz, loads_nodes, edges_load, s)[s.indices_free, :] - r_fixed
-        return sparse_solve(K, p)
+        loads = nodes_load_edges(xyz, loads_nodes, edges_load, s)
+        if faces is not None:      # (faces_load, faces_indexed, edges_faces_indexed)
+            loads = nodes_load_faces(xyz, loads, faces[0], s, faces[1], faces[2])
+        return sparse_solve(K, loads[s.indices_free, :] - r_fixed)
 
     x_prev = sparse_solve(K, np.asarray(loads_nodes)[s.indices_free, :] - r_fixed)
     x = f(x_prev)

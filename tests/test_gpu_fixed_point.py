@@ -131,3 +131,78 @@ def test_forward_mode_rule_matches_finite_differences(solver):
     x0 = oracle.forward(prob.q, prob.xyz_fixed, prob.loads, so)[1]
     assert np.abs(x.cpu().numpy() - x0).max() <= 1e-10 * np.abs(x0).max()
     assert np.abs(x_dot.cpu().numpy() - fd).max() <= 1e-6 * np.abs(fd).max()
+
+
+def _oracle_edges_faces(faces_indexed, edges_indexed):
+    """structures/meshes.py:146-204 restated: first two incident faces of every edge over both windings."""
+    half = {}
+    for f, face in enumerate(faces_indexed):
+        clean = [int(v) for v in face if v >= 0]
+        for u, v in zip(clean, clean[1:] + clean[:1]):
+            half.setdefault((u, v), []).append(f)
+    out = np.full((len(edges_indexed), 2), -1, dtype=np.int64)
+    for e, (u, v) in enumerate(edges_indexed):
+        fs = half.get((int(u), int(v)), []) + half.get((int(v), int(u)), [])
+        out[e, :len(fs[:2])] = fs[:2]
+    return out
+
+
+def test_face_loads_fixed_point_and_gradients():
+    """Area (face) loads on a mesh structure: kernel vs oracle for nodes_load, the tmax > 1 fixed point, and
+    the implicit gradients w.r.t. q, xyz_fixed and the face loads against finite differences of the oracle."""
+    import jax_fdm_b200.equilibrium as eq
+
+    nx = 5
+    m = datasets.meshgrid(nx)
+    prob = datasets.cablenet_problem(nx, seed=9)
+    # quads plus two degenerate paddings to exercise the -1 handling: turn two quads into triangles + pad
+    faces = np.concatenate([m.faces, -np.ones((m.faces.shape[0], 1), dtype=np.int64)], axis=1)
+    s = eq.EquilibriumMeshStructureSparse(prob.nodes, faces, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    ef = _oracle_edges_faces(s.faces_indexed, so.edges_indexed)
+    assert np.array_equal(ef, s.edges_faces_indexed)
+    rng = np.random.default_rng(3)
+    fload = np.zeros((faces.shape[0], 3))
+    fload[:, 2] = -0.08 * rng.uniform(0.5, 1.5, size=faces.shape[0])
+    fload[:, 1] = 0.01 * rng.standard_normal(faces.shape[0])
+    x0 = prob.xyz0
+
+    # nodes_load alone, at a non-flat geometry
+    xyz = prob.xyz0.copy()
+    xyz[:, 2] += 0.3 * np.sin(xyz[:, 0]) * np.cos(0.7 * xyz[:, 1])
+    got, _ = eq.ops.face_loads(s, T(xyz), T(prob.loads), T(fload))
+    ref = oracle.nodes_load_faces(xyz, prob.loads, fload, so, s.faces_indexed, ef)
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+
+    def oracle_loss(q, xs, fl):
+        x, steps = oracle.fixed_point_forward(q, xs, prob.loads, np.zeros((so.num_edges, 3)), so, tmax=200, eta=1e-13,
+                                              faces=(fl, s.faces_indexed, ef))
+        xyz_ = oracle.nodes_positions(x, xs, so)
+        return 0.5 * np.sum((xyz_ - x0) ** 2), x, steps
+
+    q, xs, fl = T(prob.q, True), T(prob.xyz_fixed, True), T(fload, True)
+    model = eq.EquilibriumModelSparse(tmax=200, eta=1e-13, tol=1e-14)
+    state = model(eq.EquilibriumParametersState(q, xs, eq.LoadState(T(prob.loads), 0.0, fl)), s)
+    loss = 0.5 * ((state.xyz - T(x0)) ** 2).sum()
+    loss.backward()
+    ref_loss, x_ref, steps = oracle_loss(prob.q, prob.xyz_fixed, fload)
+    assert 1 < steps < 200
+    xf = state.xyz.detach().cpu().numpy()[so.indices_free]
+    assert np.abs(xf - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
+
+    def fd(arr, mk, n_probe=5, eps=1e-6):
+        out = []
+        for k in rng.choice(arr.size, size=min(n_probe, arr.size), replace=False):
+            d = np.zeros(arr.size)
+            d[k] = eps * max(1.0, abs(arr.flat[k]))
+            d = d.reshape(arr.shape)
+            out.append((k, (oracle_loss(*mk(arr + d))[0] - oracle_loss(*mk(arr - d))[0]) / (2 * d.flat[k])))
+        return out
+
+    for grad, arr, mk in [(q.grad, prob.q, lambda a: (a, prob.xyz_fixed, fload)),
+                          (xs.grad, prob.xyz_fixed, lambda a: (prob.q, a, fload)),
+                          (fl.grad, fload, lambda a: (prob.q, prob.xyz_fixed, a))]:
+        gnp = grad.cpu().numpy()
+        scale = np.abs(gnp).max()
+        for k, refv in fd(arr, mk):
+            assert abs(gnp.flat[k] - refv) <= 1e-6 * scale + 1e-9, (k, gnp.flat[k], refv)

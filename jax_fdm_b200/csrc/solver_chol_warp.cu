@@ -91,20 +91,27 @@ __global__ void __launch_bounds__(256) chol_invdiag_kernel(WArgs A) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int groups = A.nblk * 4;
   const int64_t item = t >> 3;            // (design, group)
-  const int c = (int)(t & 7);
+  const int c = (int)(t & 7), lane = threadIdx.x & 31, base = lane & ~7;
   const bool live = item < A.batch * groups;
   double* fb = nullptr;
-  double Lr[8][8];
+  // lane c reads the block entries of ITS column once (a contiguous run of 8 - c doubles inside the
+  // rotated record: one or two 32-byte sectors); the others get them by shuffle
+  double col[8];
+#pragma unroll
+  for (int d = 0; d < 8; ++d) col[d] = 0.0;
   if (live) {
     const int64_t b = item / groups;
     const int grp = (int)(item - b * groups);
     fb = A.ws + b * A.ws_stride + (int64_t)grp * 8 * 32;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int k = 0; k <= r; ++k) Lr[r][k] = fb[k * 32 + FROT(k, r - k)];   // L(r,k) below, 1/L(r,r) on the diagonal
+    for (int d = 0; d < 8; ++d)
+      if (d < 8 - c) col[d] = fb[c * 32 + FROT(c, d)];      // L(c + d, c); 1/L(c,c) at d = 0
   }
-  __syncwarp();                            // every lane of the block has read it before anyone overwrites
+  double Lr[8][8];                         // Lr[r][k] = L(r, k), k <= r
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int r = k; r < 8; ++r) Lr[r][k] = __shfl_sync(0xffffffffu, col[r - k], base + k);
   if (!live) return;
   double X[8];
 #pragma unroll

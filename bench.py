@@ -42,7 +42,7 @@ PER_GPU_BATCH = 4096          # designs per GPU (weak scaling); N=1 is BASELINE 
 CONFIG5_BATCH = 4096          # BASELINE config 5's fixed global batch (reported beside the headline at N > 1)
 GLOBAL_BATCH = PER_GPU_BATCH  # the CPU arm times a bounded sample of one GPU's share
 CABLENET_NX = 200
-E2E_CHUNKS = 8
+E2E_CHUNKS = int(os.environ.get("FDM_BENCH_E2E_CHUNKS", "8"))
 # dram__bytes_read.sum + dram__bytes_write.sum of one chol_factor_mma_kernel launch (B = 4096), from
 # profiles/r01k_chol_final_ncu.txt (0.325 GB read + 0.960 GB written)
 NCU_TRAFFIC_CHOL_FWD = 1.284e9

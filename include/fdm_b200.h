@@ -207,44 +207,50 @@ int fdm_adjoint_grads(const fdm_plan* plan, const double* d_q, const double* d_x
                       void* stream);
 
 /* ---- shape-dependent loads (tmax > 1) -------------------------------------------------------
- * Replaces nodes_load with non-scalar edge loads in the global frame (models.py:290-344,
- * loads.py:296-331, 407-465): line loads scaled by the edge length, half to each end node:
- *     loads_out_n = loads_nodes_n + 1/2 sum_{e incident to n} edges_load_e |x_head - x_tail|
+ * Replaces nodes_load with non-scalar edge loads (models.py:290-344, loads.py:296-331, 340-465): line
+ * loads scaled by the edge length, half to each end node; is_local != 0: the load is given in the edge's
+ * local frame (geometry.py:581-618 line_lcs) and follows the deformed geometry:
+ *     loads_out_n = loads_nodes_n + 1/2 sum_{e incident to n} frame_e(edges_load_e) |x_head - x_tail|
  *   d_xyz (B,N,3)  d_loads_nodes (B|1,N,3)  d_edges_load (B|1,E,3)  ->  d_loads_out (B,N,3)
  */
 int fdm_edge_loads(const fdm_plan* plan, const double* d_xyz, const double* d_loads_nodes,
                    const double* d_edges_load, double* d_loads_out, int64_t batch,
-                   int64_t loads_stride, int64_t edges_load_stride, void* stream);
+                   int64_t loads_stride, int64_t edges_load_stride, int is_local, void* stream);
 
 /* VJP of fdm_edge_loads at the cotangent d_cot (B,N,3) of loads_out.  Outputs are OVERWRITTEN and
  * any of them may be NULL:  xyz_bar (B,N,3) [through the edge lengths; a zero-length edge gives
  * NaN like jnp.linalg.norm], edges_load_bar (B,E,3);  loads_nodes_bar is d_cot itself. */
 int fdm_edge_loads_vjp(const fdm_plan* plan, const double* d_xyz, const double* d_edges_load,
                        const double* d_cot, double* d_xyz_bar, double* d_edges_load_bar,
-                       int64_t batch, int64_t edges_load_stride, void* stream);
+                       int64_t batch, int64_t edges_load_stride, int is_local, void* stream);
 
-/* Tributary FACE (area) loads in the global frame (models.py:333-344, loads.py:35-71, 187-288): every
- * edge takes, from each of its (first two) incident faces, the face load times the area of the triangle
- * (edge, face centroid); the edge total goes half to each end node.  The mesh arrays are device int32
- * operands built by the host mirror of EquilibriumMeshStructure (structures/meshes.py:108-204):
- *   d_faces (F,D) vertex indices padded -1;  d_edges_faces (E,2) padded -1;
+/* Tributary FACE (area) loads (models.py:333-344, loads.py:35-71, 80-185, 187-288): every edge takes,
+ * from each of its (first two) incident faces, the face load times the area of the triangle (edge, face
+ * centroid); the edge total goes half to each end node.  is_local != 0: the face load is given in the
+ * face's local frame (geometry.py:621-657 polygon_lcs; identity for a degenerate normal) and follows the
+ * deformed geometry.  The mesh arrays are device int32 operands built by the host mirror of
+ * EquilibriumMeshStructure (structures/meshes.py:108-204):
+ *   d_faces (F,D) vertex indices padded -1 (D <= 8);  d_edges_faces (E,2) padded -1;
  *   d_faces_edges (F,D): edge on side i of the face, -1 when the face is not among that edge's two;
  *   d_node_faces_ptr (N+1), d_node_faces (sum deg): faces around each node.
- * d_centroids (B,F,3) is caller-provided scratch.  loads_out_n = loads_in_n + tributary face loads. */
+ * Caller-provided scratch: d_centroids (B,F,3), d_gl (B,F,3) (face loads in global coordinates).
+ * loads_out_n = loads_in_n + tributary face loads. */
 int fdm_face_loads(const fdm_plan* plan, const int32_t* d_faces, int64_t num_faces, int64_t max_deg,
                    const int32_t* d_edges_faces, const double* d_xyz, const double* d_loads_in,
-                   const double* d_faces_load, double* d_centroids, double* d_loads_out, int64_t batch,
-                   int64_t loads_stride, int64_t faces_load_stride, void* stream);
+                   const double* d_faces_load, double* d_centroids, double* d_gl, double* d_loads_out,
+                   int64_t batch, int64_t loads_stride, int64_t faces_load_stride, int is_local, void* stream);
 
 /* VJP of fdm_face_loads at the cotangent d_cot (B,N,3).  Outputs OVERWRITTEN, any may be NULL:
- * xyz_bar (B,N,3) [through areas and centroids], faces_load_bar (B,F,3).  d_centroids as filled by the
- * forward call; d_cen_bar (B,F,3) is scratch. */
+ * xyz_bar (B,N,3) [through areas, centroids and, for local loads, the face frames], faces_load_bar (B,F,3).
+ * d_centroids / d_gl as filled by the forward call; scratch: d_cen_bar (B,F,3), d_vert_bar (B,F,D,3)
+ * (local loads only). */
 int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num_faces, int64_t max_deg,
                        const int32_t* d_edges_faces, const int32_t* d_faces_edges,
                        const int32_t* d_node_faces_ptr, const int32_t* d_node_faces, const double* d_xyz,
-                       const double* d_faces_load, const double* d_centroids, const double* d_cot,
-                       double* d_cen_bar, double* d_xyz_bar, double* d_faces_load_bar, int64_t batch,
-                       int64_t faces_load_stride, void* stream);
+                       const double* d_faces_load, const double* d_centroids, const double* d_gl,
+                       const double* d_cot, double* d_cen_bar, double* d_vert_bar, double* d_xyz_bar,
+                       double* d_faces_load_bar, int64_t batch, int64_t faces_load_stride, int is_local,
+                       void* stream);
 
 /* ---- helper used by the benchmark's loss (above the path; kept here so the timed region
  * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */

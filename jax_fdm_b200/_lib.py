@@ -89,13 +89,13 @@ def lib():
     L.fdm_state_vjp.restype = C.c_int
     L.fdm_adjoint_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
     L.fdm_adjoint_grads.restype = C.c_int
-    L.fdm_edge_loads.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.fdm_edge_loads.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, C.c_int, vp]
     L.fdm_edge_loads.restype = C.c_int
-    L.fdm_edge_loads_vjp.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.fdm_edge_loads_vjp.argtypes = [vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
     L.fdm_edge_loads_vjp.restype = C.c_int
-    L.fdm_face_loads.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp]
+    L.fdm_face_loads.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, C.c_int, vp]
     L.fdm_face_loads.restype = C.c_int
-    L.fdm_face_loads_vjp.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.fdm_face_loads_vjp.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
     L.fdm_face_loads_vjp.restype = C.c_int
     L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.fdm_loss_sqdist.restype = C.c_int

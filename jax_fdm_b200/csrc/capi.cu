@@ -310,49 +310,54 @@ int fdm_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, con
 }
 
 int fdm_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
-                   double* loads_out, int64_t batch, int64_t ls, int64_t es, void* stream) {
+                   double* loads_out, int64_t batch, int64_t ls, int64_t es, int is_local, void* stream) {
   if (!ready(p, "fdm_edge_loads")) return FDM_ERR_INVALID;
   if (!xyz || !loads_nodes || !edges_load || !loads_out || batch <= 0) {
     fdm_set_error("fdm_edge_loads: bad arguments");
     return FDM_ERR_INVALID;
   }
-  return launch_edge_loads(p, xyz, loads_nodes, edges_load, loads_out, batch, ls, es, (cudaStream_t)stream);
+  return launch_edge_loads(p, xyz, loads_nodes, edges_load, loads_out, batch, ls, es, is_local, (cudaStream_t)stream);
 }
 
 int fdm_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges_load, const double* cot,
-                       double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, void* stream) {
+                       double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, int is_local, void* stream) {
   if (!ready(p, "fdm_edge_loads_vjp")) return FDM_ERR_INVALID;
   if (!xyz || !edges_load || !cot || batch <= 0) {
     fdm_set_error("fdm_edge_loads_vjp: bad arguments");
     return FDM_ERR_INVALID;
   }
-  return launch_edge_loads_vjp(p, xyz, edges_load, cot, xyz_bar, edges_load_bar, batch, es, (cudaStream_t)stream);
+  return launch_edge_loads_vjp(p, xyz, edges_load, cot, xyz_bar, edges_load_bar, batch, es, is_local, (cudaStream_t)stream);
 }
 
 int fdm_face_loads(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
-                   const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* out,
-                   int64_t batch, int64_t ls, int64_t fs, void* stream) {
+                   const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* gl,
+                   double* out, int64_t batch, int64_t ls, int64_t fs, int is_local, void* stream) {
   if (!ready(p, "fdm_face_loads")) return FDM_ERR_INVALID;
-  if (!faces || !edges_faces || !xyz || !loads_in || !faces_load || !cen || !out || F <= 0 || D < 3 || batch <= 0) {
+  if (!faces || !edges_faces || !xyz || !loads_in || !faces_load || !cen || !gl || !out || F <= 0 || D < 3 || batch <= 0) {
     fdm_set_error("fdm_face_loads: bad arguments");
     return FDM_ERR_INVALID;
   }
-  return launch_face_loads(p, faces, F, D, edges_faces, xyz, loads_in, faces_load, cen, out, batch, ls, fs,
+  if (D > 8) {
+    fdm_set_error("fdm_face_loads: faces with more than 8 vertices are not supported");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  return launch_face_loads(p, faces, F, D, edges_faces, xyz, loads_in, faces_load, cen, gl, out, batch, ls, fs, is_local,
                            (cudaStream_t)stream);
 }
 
 int fdm_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
                        const int32_t* faces_edges, const int32_t* nf_ptr, const int32_t* nf, const double* xyz,
-                       const double* faces_load, const double* cen, const double* cot, double* cen_bar,
-                       double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs, void* stream) {
+                       const double* faces_load, const double* cen, const double* gl, const double* cot,
+                       double* cen_bar, double* vert_bar, double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs,
+                       int is_local, void* stream) {
   if (!ready(p, "fdm_face_loads_vjp")) return FDM_ERR_INVALID;
-  if (!faces || !edges_faces || !faces_edges || !nf_ptr || !nf || !xyz || !faces_load || !cen || !cot || !cen_bar ||
-      F <= 0 || D < 3 || batch <= 0) {
+  if (!faces || !edges_faces || !faces_edges || !nf_ptr || !nf || !xyz || !faces_load || !cen || !gl || !cot ||
+      !cen_bar || (is_local && !vert_bar) || F <= 0 || D < 3 || D > 8 || batch <= 0) {
     fdm_set_error("fdm_face_loads_vjp: bad arguments");
     return FDM_ERR_INVALID;
   }
-  return launch_face_loads_vjp(p, faces, F, D, edges_faces, faces_edges, nf_ptr, nf, xyz, faces_load, cen, cot, cen_bar,
-                               xyz_bar, fl_bar, batch, fs, (cudaStream_t)stream);
+  return launch_face_loads_vjp(p, faces, F, D, edges_faces, faces_edges, nf_ptr, nf, xyz, faces_load, cen, gl, cot,
+                               cen_bar, vert_bar, xyz_bar, fl_bar, batch, fs, is_local, (cudaStream_t)stream);
 }
 
 int fdm_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,

@@ -334,16 +334,76 @@ adjoint_grads_kernel(int E, int N, int Nf, int Ns, const int32_t* __restrict__ e
 }
 
 // ---------------------------------------------------------------------------------------
-// shape-dependent loads: tributary edge line loads in the global frame (loads.py:296-331, 407-465)
-//   forward, thread per node:  out_n = loads_n + 1/2 sum_inc w_e |x_h - x_t|      (ascending edge id)
-//   reverse, thread per edge:  w_bar_e = 1/2 |v_e| (c_t + c_h)
-//            thread per node:  xyz_bar_n = sum_inc (+-) 1/2 (w_e . (c_t + c_h)) v_e / |v_e|
+// small vector helpers for the load kernels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double3 v_sub(double3 a, double3 b) { return make_double3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ double3 v_add(double3 a, double3 b) { return make_double3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ double3 v_scale(double s, double3 a) { return make_double3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ double v_dot(double3 a, double3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double3 v_cross(double3 a, double3 b) {
+  return make_double3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+// cotangent of a through y = a / |a| :  (ybar - y (y . ybar)) / |a|
+__device__ __forceinline__ double3 unit_bar(double3 y, double norm, double3 ybar) {
+  return v_scale(1.0 / norm, v_sub(ybar, v_scale(v_dot(y, ybar), y)));
+}
+// jnp.allclose(|e . w|, 1.0) with the default tolerances (geometry.py:609, 648)
+__device__ __forceinline__ bool near_one(double c) { return fabs(fabs(c) - 1.0) <= 1e-8 + 1e-5; }
+
+// Local coordinate system of a line (geometry.py:581-618): U = unit(x_h - x_t), V = unit(vperp x U) with
+// vperp = Z (Y when U is parallel to Z), W = unit(+-(U x V)) signed so that W . vperp >= 0.
+struct LineFrame {
+  double3 u, v, w, vperp;
+  double len, nv, nw, s;
+};
+__device__ __forceinline__ LineFrame line_frame(double3 xt, double3 xh) {
+  LineFrame f;
+  const double3 d = v_sub(xh, xt);
+  f.len = sqrt(v_dot(d, d));
+  f.u = v_scale(1.0 / f.len, d);
+  f.vperp = near_one(f.u.z) ? make_double3(0.0, 1.0, 0.0) : make_double3(0.0, 0.0, 1.0);
+  const double3 v0 = v_cross(f.vperp, f.u);
+  f.nv = sqrt(v_dot(v0, v0));
+  f.v = v_scale(1.0 / f.nv, v0);
+  const double3 w0 = v_cross(f.u, f.v);
+  f.s = v_dot(w0, f.vperp) < 0.0 ? -1.0 : 1.0;
+  f.nw = sqrt(v_dot(w0, w0));
+  f.w = v_scale(f.s / f.nw, w0);
+  return f;
+}
+// total load of an edge: |d| * (w_u U + w_v V + w_w W) in the local frame, |d| * w in the global one
+__device__ __forceinline__ double3 edge_total(const LineFrame& f, double3 wl, bool local) {
+  const double3 g = local ? v_add(v_add(v_scale(wl.x, f.u), v_scale(wl.y, f.v)), v_scale(wl.z, f.w)) : wl;
+  return v_scale(f.len, g);
+}
+// cotangent of d = x_h - x_t given the cotangent `ob` of the edge total
+__device__ __forceinline__ double3 edge_total_dbar(const LineFrame& f, double3 wl, double3 ob, bool local) {
+  if (!local) return v_scale(v_dot(wl, ob), f.u);                      // only the length depends on d
+  const double3 g = v_add(v_add(v_scale(wl.x, f.u), v_scale(wl.y, f.v)), v_scale(wl.z, f.w));
+  const double lbar = v_dot(g, ob);
+  const double3 gb = v_scale(f.len, ob);
+  double3 ub = v_scale(wl.x, gb), vb = v_scale(wl.y, gb);
+  const double3 wb = v_scale(wl.z, gb);
+  const double3 w0b = v_scale(f.s, unit_bar(f.w, f.nw, wb));           // w = unit(s w0), w0 = u x v
+  ub = v_add(ub, v_cross(f.v, w0b));
+  vb = v_add(vb, v_cross(w0b, f.u));
+  const double3 v0b = unit_bar(f.v, f.nv, vb);                          // v = unit(v0), v0 = vperp x u
+  ub = v_add(ub, v_cross(v0b, f.vperp));
+  return v_add(unit_bar(f.u, f.len, ub), v_scale(lbar, f.u));           // u = unit(d), len = |d|
+}
+
+// ---------------------------------------------------------------------------------------
+// shape-dependent loads: tributary edge line loads (loads.py:296-331, 340-465), global frame or the
+// edge's local frame (follower loads)
+//   forward, thread per node:  out_n = loads_n + 1/2 sum_inc total_e                (ascending edge id)
+//   reverse, thread per edge:  w_bar_e = |d| * (frame^T) 1/2 (c_t + c_h)
+//            thread per node:  xyz_bar_n = sum_inc (+-) dbar_e
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 edge_loads_kernel(int N, int E, const int32_t* __restrict__ ninc_ptr, const int32_t* __restrict__ ninc_edge,
                   const int32_t* __restrict__ ninc_other, const double* __restrict__ xyz,
                   const double* __restrict__ loads_nodes, const double* __restrict__ edges_load,
-                  double* __restrict__ out, int64_t ls, int64_t es) {
+                  double* __restrict__ out, int64_t ls, int64_t es, int local) {
   const int64_t b = blockIdx.y;
   const int n = blockIdx.x * kThreads + threadIdx.x;
   if (n >= N) return;
@@ -353,12 +413,10 @@ edge_loads_kernel(int N, int E, const int32_t* __restrict__ ninc_ptr, const int3
   const double3 xn = ld3(xyz, n);
   const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
   for (int k = k0; k < k1; ++k) {
-    const int e = __ldg(ninc_edge + k) >> 1;
+    const int code = __ldg(ninc_edge + k), e = code >> 1;
     const double3 xo = ld3(xyz, __ldg(ninc_other + k));
-    const double dx = xo.x - xn.x, dy = xo.y - xn.y, dz = xo.z - xn.z;
-    const double len = sqrt(dx * dx + dy * dy + dz * dz);
-    const double3 w = ld3(edges_load, e);
-    acc.x += w.x * len; acc.y += w.y * len; acc.z += w.z * len;
+    const LineFrame f = line_frame((code & 1) ? xo : xn, (code & 1) ? xn : xo);   // code & 1: n is the head
+    acc = v_add(acc, edge_total(f, ld3(edges_load, e), local != 0));
   }
   const double3 p = ld3(loads_nodes + b * ls, n);
   st3(out + b * (int64_t)N * 3, n, make_double3(p.x + 0.5 * acc.x, p.y + 0.5 * acc.y, p.z + 0.5 * acc.z));
@@ -369,7 +427,7 @@ edge_loads_vjp_kernel(int N, int E, const int32_t* __restrict__ edge_nodes, cons
                       const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
                       const double* __restrict__ xyz, const double* __restrict__ edges_load,
                       const double* __restrict__ cot, double* __restrict__ xyz_bar,
-                      double* __restrict__ edges_load_bar, int64_t es) {
+                      double* __restrict__ edges_load_bar, int64_t es, int local) {
   const int64_t b = blockIdx.y;
   const int t = blockIdx.x * kThreads + threadIdx.x;
   xyz += b * (int64_t)N * 3;
@@ -377,25 +435,23 @@ edge_loads_vjp_kernel(int N, int E, const int32_t* __restrict__ edge_nodes, cons
   edges_load += b * es;
   if (t < E && edges_load_bar) {
     const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + t);
-    const double3 a = ld3(xyz, th.x), c = ld3(xyz, th.y);
-    const double dx = c.x - a.x, dy = c.y - a.y, dz = c.z - a.z;
-    const double h = 0.5 * sqrt(dx * dx + dy * dy + dz * dz);
-    const double3 ct = ld3(cot, th.x), ch = ld3(cot, th.y);
-    st3(edges_load_bar + b * (int64_t)E * 3, t, make_double3(h * (ct.x + ch.x), h * (ct.y + ch.y), h * (ct.z + ch.z)));
+    const LineFrame f = line_frame(ld3(xyz, th.x), ld3(xyz, th.y));
+    const double3 gb = v_scale(0.5 * f.len, v_add(ld3(cot, th.x), ld3(cot, th.y)));
+    st3(edges_load_bar + b * (int64_t)E * 3, t,
+        local ? make_double3(v_dot(f.u, gb), v_dot(f.v, gb), v_dot(f.w, gb)) : gb);
   }
   if (t < N && xyz_bar) {
     double3 acc = make_double3(0.0, 0.0, 0.0);
     const double3 xn = ld3(xyz, t), cn = ld3(cot, t);
     const int k0 = __ldg(ninc_ptr + t), k1 = __ldg(ninc_ptr + t + 1);
     for (int k = k0; k < k1; ++k) {
-      const int e = __ldg(ninc_edge + k) >> 1, o = __ldg(ninc_other + k);
-      const double3 xo = ld3(xyz, o), co = ld3(cot, o);
-      const double3 w = ld3(edges_load, e);
-      // d len / d x_n = (x_n - x_o) / len, whichever end n is
-      const double dx = xn.x - xo.x, dy = xn.y - xo.y, dz = xn.z - xo.z;
-      const double len = sqrt(dx * dx + dy * dy + dz * dz);
-      const double s = 0.5 * (w.x * (cn.x + co.x) + w.y * (cn.y + co.y) + w.z * (cn.z + co.z)) / len;
-      acc.x += s * dx; acc.y += s * dy; acc.z += s * dz;
+      const int code = __ldg(ninc_edge + k), e = code >> 1, o = __ldg(ninc_other + k);
+      const bool is_head = code & 1;
+      const double3 xo = ld3(xyz, o);
+      const LineFrame f = line_frame(is_head ? xo : xn, is_head ? xn : xo);
+      const double3 ob = v_scale(0.5, v_add(cn, ld3(cot, o)));
+      const double3 db = edge_total_dbar(f, ld3(edges_load, e), ob, local != 0);
+      acc = is_head ? v_add(acc, db) : v_sub(acc, db);     // d = x_head - x_tail
     }
     st3(xyz_bar + b * (int64_t)N * 3, t, acc);
   }
@@ -427,35 +483,76 @@ __device__ __forceinline__ TriGrad tri_area(double3 a, double3 b, double3 c, boo
   return g;
 }
 
+// Local coordinate system of a polygon (geometry.py:621-657, normal_polygon :380-425): W = unit normal
+// of the centred polygon, V = unit(W x vperp) with vperp = X (Y when W is parallel to X), U = unit(+-(W x V))
+// signed so that U . vperp >= 0; a (near) zero normal falls back to the identity frame (loads.py:161-185).
+constexpr int kMaxFaceDeg = 8;
+struct PolyFrame {
+  double3 u, v, w, vperp, c;
+  double nn, nv, nu, s;
+  bool identity;
+};
+__device__ __forceinline__ PolyFrame poly_frame(const double3* p, int deg, double3* r) {
+  PolyFrame f;
+  f.c = make_double3(0.0, 0.0, 0.0);
+  for (int i = 0; i < deg; ++i) f.c = v_add(f.c, p[i]);
+  f.c = v_scale(1.0 / deg, f.c);
+  for (int i = 0; i < deg; ++i) r[i] = v_sub(p[i], f.c);
+  double3 n0 = make_double3(0.0, 0.0, 0.0);
+  for (int i = 0; i < deg; ++i) n0 = v_add(n0, v_scale(0.5, v_cross(r[i == 0 ? deg - 1 : i - 1], r[i])));
+  f.identity = fabs(n0.x) <= 1e-8 && fabs(n0.y) <= 1e-8 && fabs(n0.z) <= 1e-8;
+  if (f.identity) {
+    f.u = make_double3(1.0, 0.0, 0.0); f.v = make_double3(0.0, 1.0, 0.0); f.w = make_double3(0.0, 0.0, 1.0);
+    f.vperp = f.u; f.nn = f.nv = f.nu = f.s = 1.0;
+    return f;
+  }
+  f.nn = sqrt(v_dot(n0, n0));
+  f.w = v_scale(1.0 / f.nn, n0);
+  f.vperp = near_one(f.w.x) ? make_double3(0.0, 1.0, 0.0) : make_double3(1.0, 0.0, 0.0);
+  const double3 v0 = v_cross(f.w, f.vperp);
+  f.nv = sqrt(v_dot(v0, v0));
+  f.v = v_scale(1.0 / f.nv, v0);
+  const double3 u0 = v_cross(f.w, f.v);
+  f.s = v_dot(u0, f.vperp) < 0.0 ? -1.0 : 1.0;
+  f.nu = sqrt(v_dot(u0, u0));
+  f.u = v_scale(f.s / f.nu, u0);
+  return f;
+}
+
+// per face: centroid and the face load in global coordinates (gl = fl, or fl rotated by the face frame)
 __global__ void __launch_bounds__(kThreads)
 face_centroids_kernel(int F, int D, int N, const int32_t* __restrict__ faces, const double* __restrict__ xyz,
-                      double* __restrict__ cen) {
+                      const double* __restrict__ faces_load, double* __restrict__ cen, double* __restrict__ gl,
+                      int64_t fs, int local) {
   const int64_t b = blockIdx.y;
   const int f = blockIdx.x * kThreads + threadIdx.x;
   if (f >= F) return;
   xyz += b * (int64_t)N * 3;
-  double3 acc = make_double3(0.0, 0.0, 0.0);
-  int cnt = 0;
+  double3 p[kMaxFaceDeg], r[kMaxFaceDeg];
+  int deg = 0;
   for (int i = 0; i < D; ++i) {
     const int v = __ldg(faces + (int64_t)f * D + i);
-    if (v >= 0) { const double3 x = ld3(xyz, v); acc.x += x.x; acc.y += x.y; acc.z += x.z; ++cnt; }
+    if (v >= 0 && deg < kMaxFaceDeg) p[deg++] = ld3(xyz, v);
   }
-  const double w = 1.0 / cnt;
-  st3(cen + b * (int64_t)F * 3, f, make_double3(acc.x * w, acc.y * w, acc.z * w));
+  const PolyFrame fr = poly_frame(p, deg, r);
+  st3(cen + b * (int64_t)F * 3, f, fr.c);
+  const double3 fl = ld3(faces_load + b * fs, f);
+  const double3 g = local ? v_add(v_add(v_scale(fl.x, fr.u), v_scale(fl.y, fr.v)), v_scale(fl.z, fr.w)) : fl;
+  st3(gl + b * (int64_t)F * 3, f, g);
 }
 
 __global__ void __launch_bounds__(kThreads)
 face_loads_kernel(int N, int F, const int32_t* __restrict__ edges_faces, const int32_t* __restrict__ ninc_ptr,
                   const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
                   const double* __restrict__ xyz, const double* __restrict__ loads_in,
-                  const double* __restrict__ faces_load, const double* __restrict__ cen, double* __restrict__ out,
-                  int64_t ls, int64_t fs) {
+                  const double* __restrict__ gl, const double* __restrict__ cen, double* __restrict__ out,
+                  int64_t ls) {
   const int64_t b = blockIdx.y;
   const int n = blockIdx.x * kThreads + threadIdx.x;
   if (n >= N) return;
   xyz += b * (int64_t)N * 3;
   cen += b * (int64_t)F * 3;
-  faces_load += b * fs;
+  gl += b * (int64_t)F * 3;
   double3 acc = make_double3(0.0, 0.0, 0.0);
   const double3 xn = ld3(xyz, n);
   const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
@@ -467,7 +564,7 @@ face_loads_kernel(int N, int F, const int32_t* __restrict__ edges_faces, const i
       const int f = __ldg(edges_faces + 2 * (int64_t)e + slot);
       if (f >= 0) {
         const double a = tri_area(xt, xh, ld3(cen, f), false).area;
-        const double3 w = ld3(faces_load, f);
+        const double3 w = ld3(gl, f);
         acc.x += a * w.x; acc.y += a * w.y; acc.z += a * w.z;
       }
     }
@@ -476,33 +573,72 @@ face_loads_kernel(int N, int F, const int32_t* __restrict__ edges_faces, const i
   st3(out + b * (int64_t)N * 3, n, make_double3(p.x + 0.5 * acc.x, p.y + 0.5 * acc.y, p.z + 0.5 * acc.z));
 }
 
+// per face: centroid_bar, faces_load_bar and (local frames) the cotangents of the face's own vertices
 __global__ void __launch_bounds__(kThreads)
-face_loads_vjp_faces_kernel(int F, int D, int N, const int32_t* __restrict__ faces_edges,
-                            const int32_t* __restrict__ edge_nodes, const double* __restrict__ xyz,
-                            const double* __restrict__ faces_load, const double* __restrict__ cen,
+face_loads_vjp_faces_kernel(int F, int D, int N, const int32_t* __restrict__ faces,
+                            const int32_t* __restrict__ faces_edges, const int32_t* __restrict__ edge_nodes,
+                            const double* __restrict__ xyz, const double* __restrict__ faces_load,
+                            const double* __restrict__ gl, const double* __restrict__ cen,
                             const double* __restrict__ cot, double* __restrict__ cen_bar,
-                            double* __restrict__ fl_bar, int64_t fs, int E) {
+                            double* __restrict__ fl_bar, double* __restrict__ vert_bar, int64_t fs, int local) {
   const int64_t b = blockIdx.y;
   const int f = blockIdx.x * kThreads + threadIdx.x;
   if (f >= F) return;
   xyz += b * (int64_t)N * 3;
   cot += b * (int64_t)N * 3;
   const double3 c = ld3(cen + b * (int64_t)F * 3, f);
-  const double3 w = ld3(faces_load + b * fs, f);
-  double3 cb = make_double3(0.0, 0.0, 0.0), wb = make_double3(0.0, 0.0, 0.0);
+  const double3 w = ld3(gl + b * (int64_t)F * 3, f);
+  double3 cb = make_double3(0.0, 0.0, 0.0), glb = make_double3(0.0, 0.0, 0.0);
   for (int i = 0; i < D; ++i) {
     const int e = __ldg(faces_edges + (int64_t)f * D + i);
     if (e < 0) continue;
     const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + e);
-    const double3 ct = ld3(cot, th.x), ch = ld3(cot, th.y);
-    const double3 hc = make_double3(0.5 * (ct.x + ch.x), 0.5 * (ct.y + ch.y), 0.5 * (ct.z + ch.z));
+    const double3 hc = v_scale(0.5, v_add(ld3(cot, th.x), ld3(cot, th.y)));
     const TriGrad g = tri_area(ld3(xyz, th.x), ld3(xyz, th.y), c, true);
-    wb.x += g.area * hc.x; wb.y += g.area * hc.y; wb.z += g.area * hc.z;
-    const double abar = w.x * hc.x + w.y * hc.y + w.z * hc.z;       // cotangent of the triangle area
-    cb.x += abar * g.gc.x; cb.y += abar * g.gc.y; cb.z += abar * g.gc.z;
+    glb = v_add(glb, v_scale(g.area, hc));
+    cb = v_add(cb, v_scale(v_dot(w, hc), g.gc));                        // cotangent of the triangle area times dA/dc
   }
   if (cen_bar) st3(cen_bar + b * (int64_t)F * 3, f, cb);
-  if (fl_bar) st3(fl_bar + b * (int64_t)F * 3, f, wb);
+  if (!local) {
+    if (fl_bar) st3(fl_bar + b * (int64_t)F * 3, f, glb);
+    return;
+  }
+  // local frame: gl = fl.x U + fl.y V + fl.z W  ->  fl_bar = frame . gl_bar, and gl_bar flows into the vertices
+  double3 p[kMaxFaceDeg], r[kMaxFaceDeg], rb[kMaxFaceDeg];
+  int deg = 0;
+  for (int i = 0; i < D; ++i) {
+    const int v = __ldg(faces + (int64_t)f * D + i);
+    if (v >= 0 && deg < kMaxFaceDeg) p[deg++] = ld3(xyz, v);
+  }
+  const PolyFrame fr = poly_frame(p, deg, r);
+  const double3 fl = ld3(faces_load + b * fs, f);
+  if (fl_bar) st3(fl_bar + b * (int64_t)F * 3, f, make_double3(v_dot(fr.u, glb), v_dot(fr.v, glb), v_dot(fr.w, glb)));
+  double* vb_out = vert_bar + (b * (int64_t)F + f) * D * 3;
+  for (int i = 0; i < deg; ++i) rb[i] = make_double3(0.0, 0.0, 0.0);
+  if (!fr.identity) {
+    double3 ub = v_scale(fl.x, glb), vb = v_scale(fl.y, glb), wb = v_scale(fl.z, glb);
+    const double3 u0b = v_scale(fr.s, unit_bar(fr.u, fr.nu, ub));       // u = unit(s u0), u0 = w x v
+    wb = v_add(wb, v_cross(fr.v, u0b));
+    vb = v_add(vb, v_cross(u0b, fr.w));
+    const double3 v0b = unit_bar(fr.v, fr.nv, vb);                      // v = unit(v0), v0 = w x vperp
+    wb = v_add(wb, v_cross(fr.vperp, v0b));
+    const double3 n0b = unit_bar(fr.w, fr.nn, wb);                      // w = unit(n0), n0 = 1/2 sum r_{i-1} x r_i
+    for (int i = 0; i < deg; ++i) {
+      const int im = i == 0 ? deg - 1 : i - 1;
+      rb[im] = v_add(rb[im], v_scale(0.5, v_cross(r[i], n0b)));
+      rb[i] = v_add(rb[i], v_scale(0.5, v_cross(n0b, r[im])));
+    }
+  }
+  double3 mean = make_double3(0.0, 0.0, 0.0);
+  for (int i = 0; i < deg; ++i) mean = v_add(mean, rb[i]);
+  mean = v_scale(1.0 / deg, mean);
+  int k = 0;
+  for (int i = 0; i < D; ++i) {                                         // r_i = p_i - mean(p)
+    const bool valid = __ldg(faces + (int64_t)f * D + i) >= 0 && k < deg;
+    const double3 o = valid ? v_sub(rb[k], mean) : make_double3(0.0, 0.0, 0.0);
+    vb_out[3 * i] = o.x; vb_out[3 * i + 1] = o.y; vb_out[3 * i + 2] = o.z;
+    k += valid;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -510,9 +646,10 @@ face_loads_vjp_nodes_kernel(int N, int F, int D, const int32_t* __restrict__ fac
                             const int32_t* __restrict__ edges_faces, const int32_t* __restrict__ node_faces_ptr,
                             const int32_t* __restrict__ node_faces, const int32_t* __restrict__ ninc_ptr,
                             const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
-                            const double* __restrict__ xyz, const double* __restrict__ faces_load,
+                            const double* __restrict__ xyz, const double* __restrict__ gl,
                             const double* __restrict__ cen, const double* __restrict__ cot,
-                            const double* __restrict__ cen_bar, double* __restrict__ xyz_bar, int64_t fs) {
+                            const double* __restrict__ cen_bar, const double* __restrict__ vert_bar,
+                            double* __restrict__ xyz_bar, int local) {
   const int64_t b = blockIdx.y;
   const int n = blockIdx.x * kThreads + threadIdx.x;
   if (n >= N) return;
@@ -520,34 +657,36 @@ face_loads_vjp_nodes_kernel(int N, int F, int D, const int32_t* __restrict__ fac
   cot += b * (int64_t)N * 3;
   cen += b * (int64_t)F * 3;
   cen_bar += b * (int64_t)F * 3;
-  faces_load += b * fs;
+  gl += b * (int64_t)F * 3;
   double3 acc = make_double3(0.0, 0.0, 0.0);
   const double3 xn = ld3(xyz, n), cn = ld3(cot, n);
   const int k0 = __ldg(ninc_ptr + n), k1 = __ldg(ninc_ptr + n + 1);
   for (int k = k0; k < k1; ++k) {
     const int code = __ldg(ninc_edge + k), e = code >> 1, o = __ldg(ninc_other + k);
     const bool is_head = code & 1;
-    const double3 xo = ld3(xyz, o), co = ld3(cot, o);
-    const double3 hc = make_double3(0.5 * (cn.x + co.x), 0.5 * (cn.y + co.y), 0.5 * (cn.z + co.z));
+    const double3 xo = ld3(xyz, o);
+    const double3 hc = v_scale(0.5, v_add(cn, ld3(cot, o)));
     for (int slot = 0; slot < 2; ++slot) {
       const int f = __ldg(edges_faces + 2 * (int64_t)e + slot);
       if (f < 0) continue;
       const TriGrad g = tri_area(is_head ? xo : xn, is_head ? xn : xo, ld3(cen, f), true);
-      const double3 w = ld3(faces_load, f);
-      const double abar = w.x * hc.x + w.y * hc.y + w.z * hc.z;
+      const double abar = v_dot(ld3(gl, f), hc);
       // dA/dx_head = gh ; dA/dx_tail = -(gh + gc)
-      const double3 gn = is_head ? g.gh : make_double3(-(g.gh.x + g.gc.x), -(g.gh.y + g.gc.y), -(g.gh.z + g.gc.z));
-      acc.x += abar * gn.x; acc.y += abar * gn.y; acc.z += abar * gn.z;
+      const double3 gn = is_head ? g.gh : v_scale(-1.0, v_add(g.gh, g.gc));
+      acc = v_add(acc, v_scale(abar, gn));
     }
   }
   const int f0 = __ldg(node_faces_ptr + n), f1 = __ldg(node_faces_ptr + n + 1);
   for (int k = f0; k < f1; ++k) {
     const int f = __ldg(node_faces + k);
-    int cnt = 0;
-    for (int i = 0; i < D; ++i) cnt += __ldg(faces + (int64_t)f * D + i) >= 0;
-    const double3 cbv = ld3(cen_bar, f);
-    const double w = 1.0 / cnt;
-    acc.x += w * cbv.x; acc.y += w * cbv.y; acc.z += w * cbv.z;
+    int cnt = 0, pos = -1;
+    for (int i = 0; i < D; ++i) {
+      const int v = __ldg(faces + (int64_t)f * D + i);
+      cnt += v >= 0;
+      if (v == n && pos < 0) pos = i;
+    }
+    acc = v_add(acc, v_scale(1.0 / cnt, ld3(cen_bar, f)));
+    if (local && pos >= 0) acc = v_add(acc, ld3(vert_bar + (b * (int64_t)F + f) * D * 3, pos));
   }
   st3(xyz_bar + b * (int64_t)N * 3, n, acc);
 }
@@ -663,57 +802,61 @@ int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, 
 }
 
 int launch_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
-                      double* loads_out, int64_t batch, int64_t ls, int64_t es, cudaStream_t st) {
+                      double* loads_out, int64_t batch, int64_t ls, int64_t es, int local, cudaStream_t st) {
   const DeviceArrays& d = p->d;
   FDM_BATCH_LOOP(batch, b0, nb) {
     edge_loads_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
         (int)p->N, (int)p->E, d.ninc_ptr, d.ninc_edge, d.ninc_other, xyz + b0 * p->N * 3, loads_nodes + b0 * ls,
-        edges_load + b0 * es, loads_out + b0 * p->N * 3, ls, es);
+        edges_load + b0 * es, loads_out + b0 * p->N * 3, ls, es, local);
   }
   return fdm_check_launch("edge_loads");
 }
 
 int launch_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges_load, const double* cot,
-                          double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, cudaStream_t st) {
+                          double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, int local,
+                          cudaStream_t st) {
   const DeviceArrays& d = p->d;
   const int64_t work = std::max(p->E, p->N);
   FDM_BATCH_LOOP(batch, b0, nb) {
     edge_loads_vjp_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
         (int)p->N, (int)p->E, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, xyz + b0 * p->N * 3,
         edges_load + b0 * es, cot + b0 * p->N * 3, xyz_bar ? xyz_bar + b0 * p->N * 3 : nullptr,
-        edges_load_bar ? edges_load_bar + b0 * p->E * 3 : nullptr, es);
+        edges_load_bar ? edges_load_bar + b0 * p->E * 3 : nullptr, es, local);
   }
   return fdm_check_launch("edge_loads_vjp");
 }
 
 int launch_face_loads(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
-                      const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* out,
-                      int64_t batch, int64_t ls, int64_t fs, cudaStream_t st) {
+                      const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* gl,
+                      double* out, int64_t batch, int64_t ls, int64_t fs, int local, cudaStream_t st) {
   const DeviceArrays& d = p->d;
   FDM_BATCH_LOOP(batch, b0, nb) {
     face_centroids_kernel<<<grid_for(F, nb), kThreads, 0, st>>>((int)F, (int)D, (int)p->N, faces, xyz + b0 * p->N * 3,
-                                                               cen + b0 * F * 3);
+                                                               faces_load + b0 * fs, cen + b0 * F * 3, gl + b0 * F * 3,
+                                                               fs, local);
     face_loads_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
         (int)p->N, (int)F, edges_faces, d.ninc_ptr, d.ninc_edge, d.ninc_other, xyz + b0 * p->N * 3, loads_in + b0 * ls,
-        faces_load + b0 * fs, cen + b0 * F * 3, out + b0 * p->N * 3, ls, fs);
+        gl + b0 * F * 3, cen + b0 * F * 3, out + b0 * p->N * 3, ls);
   }
   return fdm_check_launch("face_loads");
 }
 
 int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
                           const int32_t* faces_edges, const int32_t* nf_ptr, const int32_t* nf, const double* xyz,
-                          const double* faces_load, const double* cen, const double* cot, double* cen_bar,
-                          double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs, cudaStream_t st) {
+                          const double* faces_load, const double* cen, const double* gl, const double* cot,
+                          double* cen_bar, double* vert_bar, double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs,
+                          int local, cudaStream_t st) {
   const DeviceArrays& d = p->d;
   FDM_BATCH_LOOP(batch, b0, nb) {
     face_loads_vjp_faces_kernel<<<grid_for(F, nb), kThreads, 0, st>>>(
-        (int)F, (int)D, (int)p->N, faces_edges, d.edge_nodes, xyz + b0 * p->N * 3, faces_load + b0 * fs, cen + b0 * F * 3,
-        cot + b0 * p->N * 3, cen_bar + b0 * F * 3, fl_bar ? fl_bar + b0 * F * 3 : nullptr, fs, (int)p->E);
+        (int)F, (int)D, (int)p->N, faces, faces_edges, d.edge_nodes, xyz + b0 * p->N * 3, faces_load + b0 * fs,
+        gl + b0 * F * 3, cen + b0 * F * 3, cot + b0 * p->N * 3, cen_bar + b0 * F * 3,
+        fl_bar ? fl_bar + b0 * F * 3 : nullptr, vert_bar ? vert_bar + b0 * F * D * 3 : nullptr, fs, local);
     if (xyz_bar)
       face_loads_vjp_nodes_kernel<<<grid_for(p->N, nb), kThreads, 0, st>>>(
           (int)p->N, (int)F, (int)D, faces, edges_faces, nf_ptr, nf, d.ninc_ptr, d.ninc_edge, d.ninc_other,
-          xyz + b0 * p->N * 3, faces_load + b0 * fs, cen + b0 * F * 3, cot + b0 * p->N * 3, cen_bar + b0 * F * 3,
-          xyz_bar + b0 * p->N * 3, fs);
+          xyz + b0 * p->N * 3, gl + b0 * F * 3, cen + b0 * F * 3, cot + b0 * p->N * 3, cen_bar + b0 * F * 3,
+          vert_bar ? vert_bar + b0 * F * D * 3 : nullptr, xyz_bar + b0 * p->N * 3, local);
   }
   return fdm_check_launch("face_loads_vjp");
 }

@@ -48,16 +48,17 @@ int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, 
                          double* q_bar, double* loads_bar, double* xs_bar, int64_t batch, int64_t qs,
                          int accumulate, cudaStream_t st);
 int launch_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
-                      double* loads_out, int64_t batch, int64_t ls, int64_t es, cudaStream_t st);
+                      double* loads_out, int64_t batch, int64_t ls, int64_t es, int local, cudaStream_t st);
 int launch_edge_loads_vjp(const fdm_plan* p, const double* xyz, const double* edges_load, const double* cot,
-                          double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, cudaStream_t st);
+                          double* xyz_bar, double* edges_load_bar, int64_t batch, int64_t es, int local, cudaStream_t st);
 int launch_face_loads(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
-                      const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* out,
-                      int64_t batch, int64_t ls, int64_t fs, cudaStream_t st);
+                      const double* xyz, const double* loads_in, const double* faces_load, double* cen, double* gl,
+                      double* out, int64_t batch, int64_t ls, int64_t fs, int local, cudaStream_t st);
 int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64_t D, const int32_t* edges_faces,
                           const int32_t* faces_edges, const int32_t* nf_ptr, const int32_t* nf, const double* xyz,
-                          const double* faces_load, const double* cen, const double* cot, double* cen_bar,
-                          double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs, cudaStream_t st);
+                          const double* faces_load, const double* cen, const double* gl, const double* cot,
+                          double* cen_bar, double* vert_bar, double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs,
+                          int local, cudaStream_t st);
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                        int64_t batch, int64_t x0_stride, cudaStream_t st);
 

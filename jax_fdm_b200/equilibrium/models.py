@@ -148,38 +148,39 @@ class _FusedFreePositions(torch.autograd.Function):
 
 
 class _NodesLoad(torch.autograd.Function):
-    """nodes_load with tributary edge loads in the global frame (models.py:290-344, loads.py:296-331)."""
+    """nodes_load with tributary edge loads, global or edge-local frame (models.py:290-344, loads.py:296-465)."""
 
     @staticmethod
-    def forward(ctx, xyz, loads_nodes, edges_load, structure):
-        ctx.structure = structure
+    def forward(ctx, xyz, loads_nodes, edges_load, structure, is_local):
+        ctx.structure, ctx.is_local = structure, is_local
         ctx.save_for_backward(xyz, edges_load)
-        return ops.edge_loads(structure, xyz, loads_nodes, edges_load)
+        return ops.edge_loads(structure, xyz, loads_nodes, edges_load, is_local=is_local)
 
     @staticmethod
     def backward(ctx, g):
         xyz, edges_load = ctx.saved_tensors
-        xb, eb = ops.edge_loads_vjp(ctx.structure, xyz, edges_load, g.contiguous(),
-                                    want_xyz=ctx.needs_input_grad[0], want_edges=ctx.needs_input_grad[2])
-        return xb, g, eb, None
+        xb, eb = ops.edge_loads_vjp(ctx.structure, xyz, edges_load, g.contiguous(), want_xyz=ctx.needs_input_grad[0],
+                                    want_edges=ctx.needs_input_grad[2], is_local=ctx.is_local)
+        return xb, g, eb, None, None
 
 
 class _FacesLoad(torch.autograd.Function):
-    """nodes_load with tributary face loads in the global frame (models.py:333-344, loads.py:35-71, 187-288)."""
+    """nodes_load with tributary face loads, global or face-local frame (models.py:333-344, loads.py:35-288)."""
 
     @staticmethod
-    def forward(ctx, xyz, loads_nodes, faces_load, structure):
-        out, cen = ops.face_loads(structure, xyz, loads_nodes, faces_load)
-        ctx.structure = structure
-        ctx.save_for_backward(xyz, faces_load, cen)
+    def forward(ctx, xyz, loads_nodes, faces_load, structure, is_local):
+        out, aux = ops.face_loads(structure, xyz, loads_nodes, faces_load, is_local=is_local)
+        ctx.structure, ctx.is_local = structure, is_local
+        ctx.save_for_backward(xyz, faces_load, *aux)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xyz, faces_load, cen = ctx.saved_tensors
-        xb, fb = ops.face_loads_vjp(ctx.structure, xyz, faces_load, cen, g.contiguous(),
-                                    want_xyz=ctx.needs_input_grad[0], want_faces=ctx.needs_input_grad[2])
-        return xb, g, fb, None
+        xyz, faces_load, cen, gl = ctx.saved_tensors
+        xb, fb = ops.face_loads_vjp(ctx.structure, xyz, faces_load, (cen, gl), g.contiguous(),
+                                    want_xyz=ctx.needs_input_grad[0], want_faces=ctx.needs_input_grad[2],
+                                    is_local=ctx.is_local)
+        return xb, g, fb, None, None
 
 
 class _FixedPoint(torch.autograd.Function):
@@ -197,6 +198,7 @@ class _FixedPoint(torch.autograd.Function):
         K, rhs0 = ops.assemble(s, q, xyz_fixed, torch.zeros_like(loads_nodes))     # rhs0 = -R_fixed
         ws = ops.Workspace()
         first = [True]
+        local = bool(config.get("is_load_local", False))
 
         def solve_fn(b):
             x = ops.solve(s, K, b.contiguous(), workspace=ws, reuse_factor=not first[0], **opts)
@@ -209,24 +211,24 @@ class _FixedPoint(torch.autograd.Function):
 
         def f(_, x):
             xyz = ops.positions(s, x, xyz_fixed)
-            loads = ops.edge_loads(s, xyz, loads_nodes, edges_load)
+            loads = ops.edge_loads(s, xyz, loads_nodes, edges_load, is_local=local)
             if has_faces:
-                loads, _ = ops.face_loads(s, xyz, loads, faces_load)
+                loads, _ = ops.face_loads(s, xyz, loads, faces_load, is_local=local)
             return solve_fn(loads.index_select(-2, free) + rhs0)
 
         x = solver_fixedpoint_implicit(config.get("solver"), config, f, None, x_init)
-        ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces = s, solve_fn, free, has_faces
+        ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces, ctx.local = s, solve_fn, free, has_faces, local
         ctx.save_for_backward(q, xyz_fixed, edges_load, faces_load, x)
         return x
 
     @staticmethod
     def backward(ctx, g):
         q, xyz_fixed, edges_load, faces_load, x = ctx.saved_tensors
-        s, solve_fn, free, has_faces = ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces
+        s, solve_fn, free, has_faces, local = ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces, ctx.local
         xyz = ops.positions(s, x, xyz_fixed)
-        cen = None
-        if has_faces:   # centroids of the converged geometry, needed by the face-load transpose
-            _, cen = ops.face_loads(s, xyz, torch.zeros_like(xyz), faces_load)
+        aux = None
+        if has_faces:   # centroids / global face loads of the converged geometry, needed by the face-load transpose
+            _, aux = ops.face_loads(s, xyz, torch.zeros_like(xyz), faces_load, is_local=local)
 
         def scatter_free(lam):
             c = torch.zeros(lam.shape[:-2] + (s.num_nodes, 3), dtype=lam.dtype, device=lam.device)
@@ -235,18 +237,18 @@ class _FixedPoint(torch.autograd.Function):
 
         def loads_vjp_x(lam):                       # J_P^T lam, free rows
             c = scatter_free(lam)
-            xb, _ = ops.edge_loads_vjp(s, xyz, edges_load, c, want_edges=False)
+            xb, _ = ops.edge_loads_vjp(s, xyz, edges_load, c, want_edges=False, is_local=local)
             if has_faces:
-                xb = xb + ops.face_loads_vjp(s, xyz, faces_load, cen, c, want_faces=False)[0]
+                xb = xb + ops.face_loads_vjp(s, xyz, faces_load, aux, c, want_faces=False, is_local=local)[0]
             return xb.index_select(-2, free)
 
         w, lam = fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, g.contiguous())
         # cotangents of f(theta, x*) at w: K and R_fixed terms (K3), then the load terms
         qbar, pbar, xsbar = ops.adjoint_grads(s, q, xyz, lam)
-        xb, ebar = ops.edge_loads_vjp(s, xyz, edges_load, pbar)
+        xb, ebar = ops.edge_loads_vjp(s, xyz, edges_load, pbar, is_local=local)
         fbar = None
         if has_faces:
-            xb2, fbar = ops.face_loads_vjp(s, xyz, faces_load, cen, pbar)
+            xb2, fbar = ops.face_loads_vjp(s, xyz, faces_load, aux, pbar, is_local=local)
             xb = xb + xb2
         fixed = torch.as_tensor(s.indices_fixed, device=q.device)
         xsbar = xsbar + xb.index_select(-2, fixed)  # edge lengths / face areas at the supports depend on x_s
@@ -257,8 +259,8 @@ class EquilibriumModel:
     """
     FDM model (models.py:47-91).  `tmax=1`: one linear FDM step with nodal loads.  `tmax>1`: the
     fixed-point iteration for shape-dependent loads (edge line loads and, on mesh structures, face area
-    loads, both in the global frame) with the implicit adjoint; local (follower) frames raise
-    NotImplementedError.
+    loads, in the global frame or -- is_load_local -- in the edge / face frames that follow the deformed
+    geometry, geometry.py:581-657) with the implicit adjoint.
     The dense variant assembles the same K and solves with the same kernels: the "dense" vs
     "sparse" split of the reference is a storage choice, not different arithmetic.
     """
@@ -341,12 +343,10 @@ class EquilibriumModel:
         nodes_load, edges_load, faces_load = load_state
         has_edges = isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1
         has_faces = isinstance(faces_load, torch.Tensor) and faces_load.numel() > 1 and hasattr(structure, "faces_indexed")
-        if (has_edges or has_faces) and self.is_load_local:
-            raise NotImplementedError("local (follower) load frames are outside this build (SURVEY.md §8f)")
         if has_edges:
-            nodes_load = _NodesLoad.apply(xyz, nodes_load, edges_load, structure)
+            nodes_load = _NodesLoad.apply(xyz, nodes_load, edges_load, structure, self.is_load_local)
         if has_faces:   # a non-scalar face load only takes effect on a mesh structure (models.py:333-344)
-            nodes_load = _FacesLoad.apply(xyz, nodes_load, faces_load, structure)
+            nodes_load = _FacesLoad.apply(xyz, nodes_load, faces_load, structure, self.is_load_local)
         return nodes_load
 
     def equilibrium_iterative_xyz(self, q, xyz_fixed, load_state, structure, xyz_free_init=None, tmax=100,
@@ -362,9 +362,8 @@ class EquilibriumModel:
         faces_load = load_state.faces
         if not (isinstance(faces_load, torch.Tensor) and faces_load.numel() > 1 and hasattr(structure, "faces_indexed")):
             faces_load = torch.zeros((0, 3), dtype=q.dtype, device=q.device)
-        if self.is_load_local:
-            raise NotImplementedError("local (follower) load frames are outside this build (SURVEY.md §8f)")
-        config = {"tmax": tmax, "eta": eta, "verbose": verbose, "solver": solver or self.itersolve_fn}
+        config = {"tmax": tmax, "eta": eta, "verbose": verbose, "solver": solver or self.itersolve_fn,
+                  "is_load_local": self.is_load_local}
         self.last_solver_config = config
         opts = {k: v for k, v in self.solve_opts.items() if k != "fused_assembly"}
         return _FixedPoint.apply(q, xyz_fixed, load_state.nodes, edges_load, faces_load, xyz_free_init.detach(),

@@ -277,8 +277,8 @@ def adjoint_grads(structure, q, xyz, lam, q_bar=None, loads_bar=None, xyz_fixed_
     return q_bar, loads_bar, xyz_fixed_bar
 
 
-def edge_loads(structure, xyz, loads_nodes, edges_load):
-    """nodes_load with tributary edge line loads, global frame (models.py:290-344, loads.py:296-331, 407-465)."""
+def edge_loads(structure, xyz, loads_nodes, edges_load, is_local=False):
+    """nodes_load with tributary edge line loads; is_local: loads follow the edge frame (models.py:290-344, loads.py:296-465)."""
     s = structure
     E, N = s.num_edges, s.num_nodes
     xyz = _chk(xyz, "xyz", (N, 3))
@@ -289,11 +289,11 @@ def edge_loads(structure, xyz, loads_nodes, edges_load):
         xyz = xyz.expand(B, N, 3).contiguous()
     out = torch.empty(((B,) if batched else ()) + (N, 3), dtype=F64, device=xyz.device)
     L.check(L.lib().fdm_edge_loads(s.plan, _ptr(xyz), _ptr(loads_nodes), _ptr(edges_load), _ptr(out), B,
-                                   _stride(loads_nodes, 2), _stride(edges_load, 2), _stream()))
+                                   _stride(loads_nodes, 2), _stride(edges_load, 2), int(bool(is_local)), _stream()))
     return out
 
 
-def edge_loads_vjp(structure, xyz, edges_load, cot, want_xyz=True, want_edges=True):
+def edge_loads_vjp(structure, xyz, edges_load, cot, want_xyz=True, want_edges=True, is_local=False):
     """VJP of `edge_loads` -> (xyz_bar, edges_load_bar); the cotangent of loads_nodes is `cot` itself."""
     s = structure
     E, N = s.num_edges, s.num_nodes
@@ -309,14 +309,17 @@ def edge_loads_vjp(structure, xyz, edges_load, cot, want_xyz=True, want_edges=Tr
     xyz_bar = torch.empty(lead + (N, 3), dtype=F64, device=xyz.device) if want_xyz else None
     e_bar = torch.empty(lead + (E, 3), dtype=F64, device=xyz.device) if want_edges else None
     L.check(L.lib().fdm_edge_loads_vjp(s.plan, _ptr(xyz), _ptr(edges_load), _ptr(cot), _ptr(xyz_bar), _ptr(e_bar), B,
-                                       _stride(edges_load, 2), _stream()))
+                                       _stride(edges_load, 2), int(bool(is_local)), _stream()))
     if e_bar is not None and batched and edges_load.dim() == 2:
         e_bar = e_bar.sum(0)            # one edge load shared by the batch: its cotangent sums over designs
     return xyz_bar, e_bar
 
 
-def face_loads(structure, xyz, loads_in, faces_load):
-    """nodes_load with tributary face (area) loads, global frame (loads.py:35-71, 187-288) -> (loads, centroids)."""
+def face_loads(structure, xyz, loads_in, faces_load, is_local=False):
+    """
+    nodes_load with tributary face (area) loads (loads.py:35-71, 80-185, 187-288) -> (loads, aux); `aux` =
+    (centroids, face loads in global coordinates) is what `face_loads_vjp` needs from the forward pass.
+    """
     s = structure
     N, Fn = s.num_nodes, s.num_faces
     xyz = _chk(xyz, "xyz", (N, 3))
@@ -328,35 +331,43 @@ def face_loads(structure, xyz, loads_in, faces_load):
     lead = (B,) if batched else ()
     d = s.device_arrays(xyz.device)
     cen = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device)
+    gl = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device)
     out = torch.empty(lead + (N, 3), dtype=F64, device=xyz.device)
     L.check(L.lib().fdm_face_loads(s.plan, _ptr(d["faces"]), Fn, s.faces_indexed.shape[1], _ptr(d["edges_faces"]),
-                                   _ptr(xyz), _ptr(loads_in), _ptr(faces_load), _ptr(cen), _ptr(out), B,
-                                   _stride(loads_in, 2), _stride(faces_load, 2), _stream()))
-    return out, cen
+                                   _ptr(xyz), _ptr(loads_in), _ptr(faces_load), _ptr(cen), _ptr(gl), _ptr(out), B,
+                                   _stride(loads_in, 2), _stride(faces_load, 2), int(bool(is_local)), _stream()))
+    return out, (cen, gl)
 
 
-def face_loads_vjp(structure, xyz, faces_load, centroids, cot, want_xyz=True, want_faces=True):
+def face_loads_vjp(structure, xyz, faces_load, aux, cot, want_xyz=True, want_faces=True, is_local=False):
     """VJP of `face_loads` -> (xyz_bar, faces_load_bar); the cotangent of loads_in is `cot` itself."""
     s = structure
     N, Fn = s.num_nodes, s.num_faces
+    D = s.faces_indexed.shape[1]
     xyz = _chk(xyz, "xyz", (N, 3))
     faces_load = _chk(faces_load, "faces_load", (Fn, 3))
     cot = _chk(cot, "cot", (N, 3))
-    centroids = _chk(centroids, "centroids", (Fn, 3))
+    centroids = _chk(aux[0], "centroids", (Fn, 3))
+    gl = _chk(aux[1], "faces_load_global", (Fn, 3))
     B, batched = _resolve_batch((xyz, 2), (cot, 2))
     if batched and xyz.dim() == 2:
         xyz = xyz.expand(B, N, 3).contiguous()
     if batched and cot.dim() == 2:
         cot = cot.expand(B, N, 3).contiguous()
+    if batched and centroids.dim() == 2:
+        centroids = centroids.expand(B, Fn, 3).contiguous()
+        gl = gl.expand(B, Fn, 3).contiguous()
     lead = (B,) if batched else ()
     d = s.device_arrays(xyz.device)
     cen_bar = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device)
+    vert_bar = torch.empty(lead + (Fn, D, 3), dtype=F64, device=xyz.device) if is_local else None
     xyz_bar = torch.empty(lead + (N, 3), dtype=F64, device=xyz.device) if want_xyz else None
     fl_bar = torch.empty(lead + (Fn, 3), dtype=F64, device=xyz.device) if want_faces else None
-    L.check(L.lib().fdm_face_loads_vjp(s.plan, _ptr(d["faces"]), Fn, s.faces_indexed.shape[1], _ptr(d["edges_faces"]),
+    L.check(L.lib().fdm_face_loads_vjp(s.plan, _ptr(d["faces"]), Fn, D, _ptr(d["edges_faces"]),
                                        _ptr(d["faces_edges"]), _ptr(d["node_faces_ptr"]), _ptr(d["node_faces"]),
-                                       _ptr(xyz), _ptr(faces_load), _ptr(centroids), _ptr(cot), _ptr(cen_bar),
-                                       _ptr(xyz_bar), _ptr(fl_bar), B, _stride(faces_load, 2), _stream()))
+                                       _ptr(xyz), _ptr(faces_load), _ptr(centroids), _ptr(gl), _ptr(cot),
+                                       _ptr(cen_bar), _ptr(vert_bar), _ptr(xyz_bar), _ptr(fl_bar), B,
+                                       _stride(faces_load, 2), int(bool(is_local)), _stream()))
     if fl_bar is not None and batched and faces_load.dim() == 2:
         fl_bar = fl_bar.sum(0)
     return xyz_bar, fl_bar

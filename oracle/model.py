@@ -202,28 +202,107 @@ def forward_adjoint(q, xyz_fixed, loads, s, cot_fn):
 # shape-dependent loads and the fixed-point equilibrium (tmax > 1)
 # ----------------------------------------------------------------------------
 
-def nodes_load_edges(xyz, loads_nodes, edges_load, s):
+WORLD_X, WORLD_Y, WORLD_Z = np.eye(3)
+
+
+def _allclose(a, b):
+    """jnp.allclose defaults (rtol 1e-5, atol 1e-8), as the frame code uses them."""
+    return bool(np.all(np.abs(np.asarray(a) - b) <= 1e-8 + 1e-5 * np.abs(b)))
+
+
+def normal_polygon(polygon):
+    """geometry.py:383-425 (unitized; a near-zero normal comes back as the zero vector, :138-168)."""
+    r = np.asarray(polygon, dtype=np.float64)
+    r = r - r.mean(axis=0)
+    n = (0.5 * np.cross(np.roll(r, 1, axis=0), r)).sum(axis=0)
+    if _allclose(n, 0.0):
+        return np.zeros(3)
+    return n / np.linalg.norm(n)
+
+
+def line_lcs(line):
+    """geometry.py:583-618: rows U, V, W of the edge frame."""
+    line = np.asarray(line, dtype=np.float64)
+    u = line[1] - line[0]
+    u = u / np.linalg.norm(u)
+    vperp = WORLD_Y if _allclose(abs(WORLD_Z @ u), 1.0) else WORLD_Z
+    v = np.cross(vperp, u)
+    v = v / np.linalg.norm(v)
+    w = np.cross(u, v)
+    if w @ vperp < 0.0:
+        w = -w
+    w = w / np.linalg.norm(w)
+    return np.vstack((u, v, w))
+
+
+def polygon_lcs(polygon):
+    """geometry.py:621-657: rows U, V, W of the face frame."""
+    w = normal_polygon(polygon)
+    vperp = WORLD_Y if _allclose(abs(WORLD_X @ w), 1.0) else WORLD_X
+    v = np.cross(w, vperp)
+    v = v / np.linalg.norm(v)
+    u = np.cross(w, v)
+    if u @ vperp < 0.0:
+        u = -u
+    u = u / np.linalg.norm(u)
+    return np.vstack((u, v, w))
+
+
+def edges_load_global(xyz, edges_load, s, is_local):
+    """loads.py:340-405: edge loads given in the edge frames rotated to global coordinates."""
+    edges_load = np.asarray(edges_load, dtype=np.float64)
+    if not is_local:
+        return edges_load
+    return np.stack([load @ line_lcs(xyz[edge]) for edge, load in zip(s.edges_indexed, edges_load)])
+
+
+def faces_load_global(xyz, faces_load, faces_indexed, is_local, pad="wrap"):
     """
-    models.py:290-344 with loads.py:296-331, 407-465 (global frame): line loads times edge length,
-    half to each end node, added to the nodal loads.
+    loads.py:80-185: face loads given in the face frames rotated to global coordinates; a face with a
+    (near) zero normal keeps its load unrotated.  `pad`: how the -1 padding of faces with fewer
+    vertices than the widest face is read.  "wrap" is what loads.py:170 does (xyz[face] with -1 ->
+    the LAST node of the structure, an artefact); "first" is the face_xyz helper of loads.py:108-145
+    the reference leaves commented out at :169 (pads repeat the first vertex: same normal as the
+    unpadded polygon).  The CUDA path drops the pads, which equals "first".
+    """
+    faces_load = np.asarray(faces_load, dtype=np.float64)
+    if not is_local:
+        return faces_load
+    out = np.empty_like(faces_load)
+    for i, (face, load) in enumerate(zip(faces_indexed, faces_load)):
+        face = np.asarray(face)
+        if pad == "first":
+            face = np.where(face >= 0, face, face[0])
+        fxyz = xyz[face]
+        lcs = np.eye(3) if _allclose(normal_polygon(fxyz), 0.0) else polygon_lcs(fxyz)
+        out[i] = load @ lcs
+    return out
+
+
+def nodes_load_edges(xyz, loads_nodes, edges_load, s, is_local=False):
+    """
+    models.py:290-344 with loads.py:296-331, 340-465: line loads (rotated from the edge frames when
+    `is_local`) times edge length, half to each end node, added to the nodal loads.
     """
     ei = s.edges_indexed
     lengths = np.linalg.norm(xyz[ei[:, 1]] - xyz[ei[:, 0]], axis=1, keepdims=True)
-    total = np.asarray(edges_load, dtype=np.float64) * lengths
+    total = edges_load_global(xyz, edges_load, s, is_local) * lengths
     out = np.array(loads_nodes, dtype=np.float64, copy=True)
     np.add.at(out, ei[:, 0], 0.5 * total)
     np.add.at(out, ei[:, 1], 0.5 * total)
     return out
 
 
-def nodes_load_faces(xyz, loads_nodes, faces_load, s, faces_indexed, edges_faces_indexed):
+def nodes_load_faces(xyz, loads_nodes, faces_load, s, faces_indexed, edges_faces_indexed, is_local=False,
+                     pad="wrap"):
     """
-    models.py:333-344 with loads.py:35-71, 187-288 (global frame): every edge takes, from each of its
-    (first two) incident faces, the face load times the area of the triangle (edge, face centroid)
-    (loads.py:226-288); half of the edge total goes to each end node (loads.py:435-465).
-    `faces_indexed` (F, maxdeg) padded -1 and `edges_faces_indexed` (E, 2) padded -1 as the reference
-    defines them (structures/meshes.py:108-204).
+    models.py:333-344 with loads.py:35-71, 80-288: every edge takes, from each of its (first two)
+    incident faces, the face load (rotated from the face frame when `is_local`) times the area of the
+    triangle (edge, face centroid) (loads.py:226-288); half of the edge total goes to each end node
+    (loads.py:435-465).  `faces_indexed` (F, maxdeg) padded -1 and `edges_faces_indexed` (E, 2) padded -1
+    as the reference defines them (structures/meshes.py:108-204).
     """
+    faces_load = faces_load_global(xyz, faces_load, faces_indexed, is_local, pad)
     mask = faces_indexed >= 0
     cen = np.stack([xyz[face[m]].mean(axis=0) for face, m in zip(faces_indexed, mask)])
     ei = s.edges_indexed
@@ -234,14 +313,14 @@ def nodes_load_faces(xyz, loads_nodes, faces_load, s, faces_indexed, edges_faces
         ok = f >= 0
         c = cen[np.where(ok, f, 0)]
         area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1)
-        edge_load += np.where(ok, area, 0.0)[:, None] * np.asarray(faces_load)[np.where(ok, f, 0)]
+        edge_load += np.where(ok, area, 0.0)[:, None] * faces_load[np.where(ok, f, 0)]
     out = np.array(loads_nodes, dtype=np.float64, copy=True)
     np.add.at(out, ei[:, 0], 0.5 * edge_load)
     np.add.at(out, ei[:, 1], 0.5 * edge_load)
     return out
 
 
-def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=1e-6, faces=None):
+def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=1e-6, faces=None, is_local=False):
     """
     models.py:410-478, 512-618 + fixed_point.py:139-198: one linear step with the nodal loads, then
     x <- K^{-1} (nodes_load(xyz(x))[free] - R_fixed) until the mean nodal move <= eta or tmax steps.
@@ -252,9 +331,9 @@ def fixed_point_forward(q, xyz_fixed, loads_nodes, edges_load, s, tmax=100, eta=
 
     def f(x):
         xyz = nodes_positions(x, xyz_fixed, s)
-        loads = nodes_load_edges(xyz, loads_nodes, edges_load, s)
+        loads = nodes_load_edges(xyz, loads_nodes, edges_load, s, is_local)
         if faces is not None:      # (faces_load, faces_indexed, edges_faces_indexed)
-            loads = nodes_load_faces(xyz, loads, faces[0], s, faces[1], faces[2])
+            loads = nodes_load_faces(xyz, loads, faces[0], s, faces[1], faces[2], is_local)
         return sparse_solve(K, loads[s.indices_free, :] - r_fixed)
 
     x_prev = sparse_solve(K, np.asarray(loads_nodes)[s.indices_free, :] - r_fixed)

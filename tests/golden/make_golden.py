@@ -207,8 +207,11 @@ class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         if root not in FAKE_ROOTS:
             return None
         if fullname in REAL:
-            rel = fullname.replace(".", os.sep) + ".py"
-            return importlib.util.spec_from_file_location(fullname, os.path.join(SRC, rel))
+            base = os.path.join(SRC, fullname.replace(".", os.sep))
+            if os.path.isdir(base):     # a real package: its own __init__.py
+                return importlib.util.spec_from_file_location(fullname, os.path.join(base, "__init__.py"),
+                                                              submodule_search_locations=[base])
+            return importlib.util.spec_from_file_location(fullname, base + ".py")
         return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
 
     def create_module(self, spec):

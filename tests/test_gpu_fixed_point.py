@@ -206,3 +206,124 @@ def test_face_loads_fixed_point_and_gradients():
         scale = np.abs(gnp).max()
         for k, refv in fd(arr, mk):
             assert abs(gnp.flat[k] - refv) <= 1e-6 * scale + 1e-9, (k, gnp.flat[k], refv)
+
+
+# ---------------------------------------------------------------------------------------------------
+# local (follower) load frames: is_load_local=True (geometry.py:583-657, loads.py:80-185, 340-405)
+# ---------------------------------------------------------------------------------------------------
+
+def _golden_loads():
+    import os
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loads_frames.npz")))
+
+
+@pytest.mark.parametrize("tag", ["quad", "mixed"])
+def test_local_frame_loads_vs_reference_arrays_and_fd(tag):
+    """nodes_load with edge / face loads given in the element frames: kernels against arrays the reference's
+    loads.py produced (quad mesh) and the oracle, then both VJPs against central differences of the oracle."""
+    import jax_fdm_b200.equilibrium as eq
+    from oracle import model as om
+
+    g = _golden_loads()
+    s = eq.EquilibriumMeshStructureSparse(g[f"{tag}_nodes"], g[f"{tag}_faces"], g[f"{tag}_edges"], g[f"{tag}_supports"], device=0)
+    so = oracle.build_structure(g[f"{tag}_nodes"], g[f"{tag}_edges"], g[f"{tag}_supports"])
+    assert np.array_equal(s.faces_indexed, g[f"{tag}_faces_indexed"])
+    fi, ef = s.faces_indexed, s.edges_faces_indexed
+    xyz, el, fl = g[f"{tag}_xyz"], g[f"{tag}_edges_load"], g[f"{tag}_faces_load"]
+    zero = np.zeros_like(xyz)
+
+    got_e = eq.ops.edge_loads(s, T(xyz), T(zero), T(el), is_local=True).cpu().numpy()
+    ref_e = g[f"{tag}_ref_nodes_load_edges_local"]
+    assert np.abs(got_e - ref_e).max() <= 1e-13 * np.abs(ref_e).max()
+    got_f = eq.ops.face_loads(s, T(xyz), T(zero), T(fl), is_local=True)[0].cpu().numpy()
+    # padded faces: the kernels read the polygon without its pads (oracle pad="first"); loads.py:170 reads xyz[-1]
+    ref_f = oracle.nodes_load_faces(xyz, zero, fl, so, fi, ef, is_local=True, pad="first")
+    assert np.abs(got_f - ref_f).max() <= 1e-13 * np.abs(ref_f).max()
+    if tag == "quad":
+        ref = g["quad_ref_nodes_load_faces_local"]
+        assert np.abs(got_f - ref).max() <= 1e-13 * np.abs(ref).max()
+    # global mode is untouched by the frame code
+    got = eq.ops.face_loads(s, T(xyz), T(zero), T(fl))[0].cpu().numpy()
+    ref = g[f"{tag}_ref_nodes_load_faces_global"]
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+    rng = np.random.default_rng(4)
+    cot = rng.standard_normal(xyz.shape)
+
+    def phi_e(x, w):
+        return np.sum(cot * oracle.nodes_load_edges(x, zero, w, so, is_local=True))
+
+    def phi_f(x, w):
+        return np.sum(cot * oracle.nodes_load_faces(x, zero, w, so, fi, ef, is_local=True, pad="first"))
+
+    xb_e, wb_e = eq.ops.edge_loads_vjp(s, T(xyz), T(el), T(cot), is_local=True)
+    _, aux = eq.ops.face_loads(s, T(xyz), T(zero), T(fl), is_local=True)
+    xb_f, wb_f = eq.ops.face_loads_vjp(s, T(xyz), T(fl), aux, T(cot), is_local=True)
+    for phi, xb, wb, w in ((phi_e, xb_e, wb_e, el), (phi_f, xb_f, wb_f, fl)):
+        xb, wb = xb.cpu().numpy(), wb.cpu().numpy()
+        for arr, grad, mk in ((xyz, xb, lambda a: (a, w)), (w, wb, lambda a: (xyz, a))):
+            scale = np.abs(grad).max()
+            for k in rng.choice(arr.size, size=12, replace=False):
+                d = np.zeros(arr.size)
+                d[k] = 1e-6
+                d = d.reshape(arr.shape)
+                fdv = (phi(*mk(arr + d)) - phi(*mk(arr - d))) / 2e-6
+                assert abs(grad.flat[k] - fdv) <= 2e-8 * scale + 1e-10, (k, grad.flat[k], fdv)
+
+
+def test_follower_face_loads_fixed_point_and_gradients():
+    """After the reference's tests/test_adjoint_routing.py:40-75 (meshgrid, q = -2, face loads [0, 0, -0.1] in the
+    FACE frames, is_load_local=True, tmax > 1), here on the corner-supported 5x5 cable net with follower edge
+    loads on top: forward vs the oracle, implicit gradients vs central differences of the oracle."""
+    import jax_fdm_b200.equilibrium as eq
+
+    nx = 5
+    m = datasets.meshgrid(nx)
+    prob = datasets.cablenet_problem(nx, seed=2)
+    s = eq.EquilibriumMeshStructureSparse(prob.nodes, m.faces, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    fi, ef = s.faces_indexed, s.edges_faces_indexed
+    rng = np.random.default_rng(8)
+    q0 = -2.0 * np.ones(so.num_edges)
+    fload = np.tile([0.0, 0.0, -0.1], (s.num_faces, 1)) + 0.01 * rng.standard_normal((s.num_faces, 3))
+    eload = 0.02 * rng.standard_normal((so.num_edges, 3))
+    xs0 = prob.xyz_fixed.copy()
+    xs0[:, 2] += 0.5 * np.sin(xs0[:, 0])              # non-flat boundary so that the frames rotate
+    loads0 = np.zeros_like(prob.loads)
+    loads0[:, 2] = -0.05
+
+    def oracle_loss(q, xs, fl, el):
+        x, steps = oracle.fixed_point_forward(q, xs, loads0, el, so, tmax=300, eta=1e-13, faces=(fl, fi, ef), is_local=True)
+        xyz_ = oracle.nodes_positions(x, xs, so)
+        ei = so.edges_indexed
+        lengths = np.linalg.norm(xyz_[ei[:, 1]] - xyz_[ei[:, 0]], axis=1)
+        return 0.5 * np.sum((lengths - 1.0) ** 2), x, steps
+
+    q, xs, fl, el = T(q0, True), T(xs0, True), T(fload, True), T(eload, True)
+    model = eq.EquilibriumModelSparse(tmax=300, eta=1e-13, tol=1e-14, is_load_local=True)
+    state = model(eq.EquilibriumParametersState(q, xs, eq.LoadState(T(loads0), el, fl)), s)
+    loss = 0.5 * ((state.lengths - 1.0) ** 2).sum()
+    loss.backward()
+    ref_loss, x_ref, steps = oracle_loss(q0, xs0, fload, eload)
+    assert 1 < steps < 300
+    xf = state.xyz.detach().cpu().numpy()[so.indices_free]
+    assert np.abs(xf - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
+    assert abs(loss.item() - ref_loss) <= 1e-10 * abs(ref_loss)
+    # the loads reported in the state are the follower loads at the converged geometry
+    xyz_ref = oracle.nodes_positions(x_ref, xs0, so)
+    loads_ref = oracle.nodes_load_faces(xyz_ref, oracle.nodes_load_edges(xyz_ref, loads0, eload, so, is_local=True),
+                                        fload, so, fi, ef, is_local=True)
+    assert np.abs(state.loads.detach().cpu().numpy() - loads_ref).max() <= 1e-10 * np.abs(loads_ref).max()
+
+    for grad, arr, mk in [(q.grad, q0, lambda a: (a, xs0, fload, eload)),
+                          (xs.grad, xs0, lambda a: (q0, a, fload, eload)),
+                          (fl.grad, fload, lambda a: (q0, xs0, a, eload)),
+                          (el.grad, eload, lambda a: (q0, xs0, fload, a))]:
+        gnp = grad.cpu().numpy()
+        scale = np.abs(gnp).max()
+        for k in rng.choice(arr.size, size=5, replace=False):
+            d = np.zeros(arr.size)
+            d[k] = 1e-6 * max(1.0, abs(arr.flat[k]))
+            d = d.reshape(arr.shape)
+            refv = (oracle_loss(*mk(arr + d))[0] - oracle_loss(*mk(arr - d))[0]) / (2 * d.flat[k])
+            assert abs(gnp.flat[k] - refv) <= 1e-6 * scale + 1e-9, (k, gnp.flat[k], refv)

@@ -305,6 +305,9 @@ void fdm_build_band_order(fdm_plan& p) {
   // -1 = structural zero (or column < 0), -2 = one (diagonal of a padding row).
   p.band_rowkidx.clear();
   p.band_rowedge.clear();
+  p.band_stage_ptr.clear();
+  p.band_stage_kent.clear();
+  p.band_stage_eent.clear();
   if (p.hbw <= 31) {
     const int64_t rows = ((int64_t)(n + 31) / 32 + 1) * 32;
     p.band_rowkidx.assign((size_t)rows * 32, -1);
@@ -323,6 +326,32 @@ void fdm_build_band_order(fdm_plan& p) {
       const int32_t k = p.band_rowkidx[i];
       p.band_rowedge[i] = k >= 0 ? (p.entry_edge[k] >= 0 ? p.entry_edge[k] : -3) : k;
     }
+    // The tables are mostly zeros (a row of K has degree + 1 entries, the band 32 slots): per block of 32
+    // rows keep only the non-zero entries as (r*32 + slot, index) pairs, slot = (r - t) & 31 = column & 31,
+    // in groups of 32 so that a warp reads a group with one coalesced load.
+    const int64_t blocks = rows / 32;
+    p.band_stage_ptr.assign((size_t)blocks + 1, 0);
+    p.band_stage_kent.clear();
+    p.band_stage_eent.clear();
+    for (int64_t b = 0; b < blocks; ++b) {
+      p.band_stage_ptr[(size_t)b] = (int32_t)(p.band_stage_kent.size() / 64);
+      for (int32_t r = 0; r < 32; ++r)
+        for (int32_t t = 0; t < 32; ++t) {
+          const size_t i = (size_t)(b * 32 + r) * 32 + t;
+          if (p.band_rowkidx[i] == -1) continue;
+          const int32_t pos = r * 32 + ((r - t) & 31);
+          const int32_t e = p.band_rowedge[i];
+          p.band_stage_kent.push_back(pos);
+          p.band_stage_kent.push_back(p.band_rowkidx[i]);
+          p.band_stage_eent.push_back(pos);
+          p.band_stage_eent.push_back(e == -3 ? -1 : e);
+        }
+      while (p.band_stage_kent.size() % 64) {
+        p.band_stage_kent.push_back(0); p.band_stage_kent.push_back(-4);
+        p.band_stage_eent.push_back(0); p.band_stage_eent.push_back(-4);
+      }
+    }
+    p.band_stage_ptr[(size_t)blocks] = (int32_t)(p.band_stage_kent.size() / 64);
   }
 }
 

@@ -68,6 +68,7 @@ struct WArgs {
   int64_t q_stride, xs_stride, loads_stride;
   const int32_t *rowedge, *diags_ptr, *diags_idx, *free_node, *node_slot, *ninc_ptr, *ninc_edge, *ninc_other;
   const uint32_t* sup_mask;
+  const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
 };
 
 // 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~22 bits) + two Newton steps in
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
 // Out-of-band entries of the window stay exactly zero (an update needs both factors non-zero).
 // ===========================================================================================
 constexpr int kMS = 36;                                  // staged row: 32 column slots + 3 right-hand sides + pad
-constexpr int kMmaWarpSmem = 32 * kMS + 64;              // staged rows + panel exchange
+constexpr int kMmaWarpSmem = 32 * kMS + 128;             // staged rows + panel exchange (32 rows x up to 4 columns)
 
 __device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -266,7 +267,7 @@ __device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double 
                : "d"(a), "d"(b));
 }
 
-template <bool FROM_Q>
+template <bool FROM_Q, int PW>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,62 +298,70 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
   else sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
 
   // fs[r][s] = sigma * A(R0 + r, C), C = the column with slot s among the 32 ending at row R0 + r;
-  // fs[r][32..34] = sigma * rhs(R0 + r)
-  auto stage_rows = [&](int R0) {
+  // fs[r][32..34] = sigma * rhs(R0 + r).  K is sparse inside the band: the plan lists the non-zero (r, s) of
+  // every block (band_stage_*), a few per lane; fs is all zero between blocks (the previous block's entries
+  // are taken back first), so a block costs one round of index loads and one of value loads.
+  const int2* ent = reinterpret_cast<const int2*>(A.stage_ent);
+  auto stage_rows = [&](int blk) {
+    const int R0 = blk * 32;
+    if (blk > 0) {
+      const int h0 = __ldg(A.stage_ptr + blk - 1), h1 = __ldg(A.stage_ptr + blk);
+      for (int gq = h0; gq < h1; ++gq) {
+        const int2 e = __ldg(ent + gq * 32 + lane);
+        if (e.y != -4) fs[e.x + (e.x >> 5) * (kMS - 32)] = 0.0;
+      }
+      __syncwarp();
+    }
+    const int g0 = __ldg(A.stage_ptr + blk), g1 = __ldg(A.stage_ptr + blk + 1);
+    // right-hand sides of row R0 + lane (FROM_Q: lane r also finishes row R0 + r, below)
+    int gi = -1;
+    if (R0 + lane < n) gi = __ldg(A.iperm + R0 + lane);
+    for (int gq = g0; gq < g1; gq += 4) {
+      int2 e[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) e[u] = gq + u < g1 ? __ldg(ent + (gq + u) * 32 + lane) : make_int2(0, -4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = e[u].y == -2 ? 1.0 : 0.0;
+        if (e[u].y >= 0) v[u] = FROM_Q ? -sigma * __ldg(q + e[u].y) : sigma * __ldg(Kd + e[u].y);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e[u].y != -4) fs[e[u].x + (e[u].x >> 5) * (kMS - 32)] = v[u];
+    }
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    if (FROM_Q) __syncwarp();                                // the list wrote a zero on the diagonals, see below
     if (!FROM_Q) {
-      const int32_t* idxp = A.rowkidx + (int64_t)R0 * 32;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int idx = __ldg(idxp + r * 32 + ((r - lane) & 31));
-        double v = 0.0;
-        if (idx >= 0) v = sigma * __ldg(Kd + idx);
-        else if (idx == -2) v = 1.0;
-        fs[r * kMS + lane] = v;
-      }
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-      if (R0 + lane < n) {
-        const int gi = __ldg(A.iperm + R0 + lane);
-        r0 = sigma * rhs[3 * gi]; r1 = sigma * rhs[3 * gi + 1]; r2 = sigma * rhs[3 * gi + 2];
-      }
-      fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
-    } else {
-      // assembly in place (models.py:1064-1079, 828-856, 949-976): off-diagonals -q[e], then lane r finishes
-      // row R0 + r: its diagonal and its load term loads_f + sum_{e to support s} q_e x_s
-      const int32_t* idxp = A.rowedge + (int64_t)R0 * 32;
-      const double nsig = -sigma;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int e = __ldg(idxp + r * 32 + ((r - lane) & 31));
-        double v = 0.0;
-        if (e >= 0) v = nsig * __ldg(q + e);
-        else if (e == -2) v = 1.0;
-        fs[r * kMS + lane] = v;
-      }
-      double r0 = 0.0, r1 = 0.0, r2 = 0.0;
-      if (R0 + lane < n) {
-        const int f = __ldg(A.iperm + R0 + lane);
-        fs[lane * kMS + lane] = sigma * diag_of(f);          // slot of column R0 + lane is lane
-        const int node = __ldg(A.free_node + f);
-        double3 acc = make_double3(0.0, 0.0, 0.0);
-        if ((__ldg(A.sup_mask + (f >> 5)) >> (f & 31)) & 1u) {
-          const double* xsb = A.xs + b * A.xs_stride;
-          const int i0 = __ldg(A.ninc_ptr + node), i1 = __ldg(A.ninc_ptr + node + 1);
-          for (int k = i0; k < i1; ++k) {
-            const int slot = __ldg(A.node_slot + __ldg(A.ninc_other + k));
-            if (slot < 0) {
-              const double qe = __ldg(q + (__ldg(A.ninc_edge + k) >> 1));
-              const double* xp = xsb + 3 * (int64_t)(-slot - 1);
-              acc.x += qe * __ldg(xp); acc.y += qe * __ldg(xp + 1); acc.z += qe * __ldg(xp + 2);
-            }
+      if (gi >= 0) { r0 = sigma * rhs[3 * gi]; r1 = sigma * rhs[3 * gi + 1]; r2 = sigma * rhs[3 * gi + 2]; }
+    } else if (gi >= 0) {
+      // assembly in place (models.py:1064-1079, 828-856, 949-976): the off-diagonals are -q[e] (above); lane r
+      // finishes row R0 + r: its diagonal and its load term loads_f + sum_{e to support s} q_e x_s
+      const int f = gi;
+      fs[lane * kMS + lane] = sigma * diag_of(f);            // slot of column R0 + lane is lane
+      const int node = __ldg(A.free_node + f);
+      double3 acc = make_double3(0.0, 0.0, 0.0);
+      if ((__ldg(A.sup_mask + (f >> 5)) >> (f & 31)) & 1u) {
+        const double* xsb = A.xs + b * A.xs_stride;
+        const int i0 = __ldg(A.ninc_ptr + node), i1 = __ldg(A.ninc_ptr + node + 1);
+        for (int k = i0; k < i1; ++k) {
+          const int slot = __ldg(A.node_slot + __ldg(A.ninc_other + k));
+          if (slot < 0) {
+            const double qe = __ldg(q + (__ldg(A.ninc_edge + k) >> 1));
+            const double* xp = xsb + 3 * (int64_t)(-slot - 1);
+            acc.x += qe * __ldg(xp); acc.y += qe * __ldg(xp + 1); acc.z += qe * __ldg(xp + 2);
           }
         }
-        const double* lp = A.loads + b * A.loads_stride + 3 * (int64_t)node;
-        r0 = sigma * (__ldg(lp) + acc.x); r1 = sigma * (__ldg(lp + 1) + acc.y); r2 = sigma * (__ldg(lp + 2) + acc.z);
       }
-      fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
+      const double* lp = A.loads + b * A.loads_stride + 3 * (int64_t)node;
+      r0 = sigma * (__ldg(lp) + acc.x); r1 = sigma * (__ldg(lp + 1) + acc.y); r2 = sigma * (__ldg(lp + 2) + acc.z);
     }
+    fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
   };
 
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) fs[r * kMS + lane] = 0.0;
+  __syncwarp();
   double W[4][4][2], y[3];
   stage_rows(0);
   __syncwarp();
@@ -372,8 +381,125 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
     double* const fb = fac + (int64_t)j0 * 32;
     double* const yb = ysol + (int64_t)j0 * 4;
     __syncwarp();
-    stage_rows(j0 + 32);
+    stage_rows(jb + 1);
     __syncwarp();
+    if constexpr (PW == 4) {
+      // Four columns per panel (hbw <= 29): all four k-slices of the DMMA carry data.  Column j+3 can reach
+      // row j+32, one row past the window: that entry has no fill before it (rows j+32 and j..j+2 are more
+      // than hbw apart), so it is x3 = A(j+32, j+3) / L(j+3, j+3) straight from the staged block.  The window
+      // is REFILLED FIRST and the update runs afterwards with the panel rows of the four incoming rows set to
+      // (0, 0, 0, x3), (0..), (0..), (0..): row j+32 receives its update from column j+3 with everyone else.
+#pragma unroll
+      for (int p4 = 0; p4 < 8; ++p4) {
+        const int s0 = 4 * p4;            // slots (= columns of this block) of the panel: s0 .. s0 + 3
+        const int tc0 = p4 >> 1, mh = p4 & 1;
+        const bool collane = (m >> 1) == mh;               // holds panel columns s0 + 2 (m & 1), + 1 of every tile row
+        const bool rowlane = (g >> 2) == mh;               // holds panel row 8 tc0 + g of tile row tc0
+        // ---- 1. panel columns -> lanes = rows
+        __syncwarp();                                      // the previous panel's fragment reads of Pn are done
+        if (collane) {
+#pragma unroll
+          for (int tr = 0; tr < 4; ++tr)
+            *reinterpret_cast<double2*>(Pn + (8 * tr + g) * 4 + 2 * (m & 1)) = make_double2(W[tr][tc0][0], W[tr][tc0][1]);
+        }
+        __syncwarp();
+        const double2 va = *reinterpret_cast<const double2*>(Pn + 4 * lane);
+        const double2 vb = *reinterpret_cast<const double2*>(Pn + 4 * lane + 2);
+        const int d0 = (lane - s0) & 31;                 // row of this lane = j0 + s0 + d0
+        const double piv0 = __shfl_sync(kFull, va.x, s0);
+        const double inv0 = rsqrt_nr(piv0);
+        const double l0 = va.x * inv0;
+        double v1 = fma(-l0, __shfl_sync(kFull, l0, s0 + 1), va.y);
+        double v2 = fma(-l0, __shfl_sync(kFull, l0, s0 + 2), vb.x);
+        double v3 = fma(-l0, __shfl_sync(kFull, l0, s0 + 3), vb.y);
+        const double piv1 = __shfl_sync(kFull, v1, s0 + 1);
+        const double inv1 = rsqrt_nr(piv1);
+        const double l1 = v1 * inv1;
+        v2 = fma(-l1, __shfl_sync(kFull, l1, s0 + 2), v2);
+        v3 = fma(-l1, __shfl_sync(kFull, l1, s0 + 3), v3);
+        const double piv2 = __shfl_sync(kFull, v2, s0 + 2);
+        const double inv2 = rsqrt_nr(piv2);
+        const double l2 = v2 * inv2;
+        v3 = fma(-l2, __shfl_sync(kFull, l2, s0 + 3), v3);
+        const double piv3 = __shfl_sync(kFull, v3, s0 + 3);
+        const double inv3 = rsqrt_nr(piv3);
+        const double l3 = v3 * inv3;
+        bad |= !(piv0 > 0.0) | !(piv1 > 0.0) | !(piv2 > 0.0) | !(piv3 > 0.0);
+        const double x3 = fs[s0 * kMS + s0 + 3] * inv3;  // L(j+32, j+3), see above
+        // ---- 2. right-hand sides; lane s0 + k keeps the solved entries of column j + k
+        double yd0, yd1, yd2;
+        {
+          const double linv[4] = {inv0, inv1, inv2, inv3}, lcol[4] = {l0, l1, l2, l3};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double t0 = y[0] * linv[k], t1 = y[1] * linv[k], t2 = y[2] * linv[k];
+            if (lane == s0 + k) { yb[(s0 + k) * 4] = t0; yb[(s0 + k) * 4 + 1] = t1; yb[(s0 + k) * 4 + 2] = t2; }
+            yd0 = __shfl_sync(kFull, t0, s0 + k);
+            yd1 = __shfl_sync(kFull, t1, s0 + k);
+            yd2 = __shfl_sync(kFull, t2, s0 + k);
+            y[0] = fma(-lcol[k], yd0, y[0]); y[1] = fma(-lcol[k], yd1, y[1]); y[2] = fma(-lcol[k], yd2, y[2]);
+          }
+        }
+        // ---- 3. factor records (the diagonal slot holds 1/L(j,j), see chol_invdiag_kernel); rows above the
+        //         diagonal of the 4x4 pivot block are zero, row j+32 of column j+3 is x3
+        {
+          double r1 = l1, r2 = l2, r3 = l3;
+          if (lane == s0) { r1 = 0.0; r2 = 0.0; r3 = x3; }
+          if (lane == s0 + 1) { r1 = inv1; r2 = 0.0; r3 = 0.0; }
+          if (lane == s0 + 2) { r2 = inv2; r3 = 0.0; }
+          if (lane == s0 + 3) r3 = inv3;
+          fb[s0 * 32 + FROT(s0, d0)] = lane == s0 ? inv0 : l0;
+          fb[(s0 + 1) * 32 + FROT(s0 + 1, (d0 - 1) & 31)] = r1;
+          fb[(s0 + 2) * 32 + FROT(s0 + 2, (d0 - 2) & 31)] = r2;
+          fb[(s0 + 3) * 32 + FROT(s0 + 3, (d0 - 3) & 31)] = r3;
+        }
+        // ---- 4. rows / columns j+32 .. j+35 enter at slots s0 .. s0+3 (fs holds lower triangles: entry
+        //         (R, C) of two incoming rows is staged with the later one as the row)
+        if (rowlane) {
+          const int R = 8 * tc0 + g;
+          const double* fr = fs + R * kMS;
+#pragma unroll
+          for (int tc = 0; tc < 4; ++tc) {
+            const double2 w = *reinterpret_cast<const double2*>(fr + 8 * tc + 2 * m);
+            W[tc0][tc][0] = w.x;
+            W[tc0][tc][1] = w.y;
+          }
+          if (collane) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int C = 8 * tc0 + 2 * m + e;
+              if (C > R) W[tc0][tc0][e] = fs[C * kMS + R];
+            }
+          }
+        }
+        if (collane) {
+#pragma unroll
+          for (int tr = 0; tr < 4; ++tr) {
+            if (!(tr == tc0 && rowlane)) {
+              W[tr][tc0][0] = fs[(8 * tc0 + 2 * m) * kMS + 8 * tr + g];
+              W[tr][tc0][1] = fs[(8 * tc0 + 2 * m + 1) * kMS + 8 * tr + g];
+            }
+          }
+        }
+        if (d0 < 4) { y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34]; }
+        if (d0 == 0) { y[0] = fma(-x3, yd0, y[0]); y[1] = fma(-x3, yd1, y[1]); y[2] = fma(-x3, yd2, y[2]); }
+        // ---- 5. W -= P P^T on the tensor pipe, P = panel with the incoming rows' entries
+        const bool inc = d0 < 4;
+        *reinterpret_cast<double2*>(Pn + 4 * lane) = inc ? make_double2(0.0, 0.0) : make_double2(l0, l1);
+        *reinterpret_cast<double2*>(Pn + 4 * lane + 2) = inc ? make_double2(0.0, d0 == 0 ? x3 : 0.0) : make_double2(l2, l3);
+        __syncwarp();
+        double af[4], nf[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          af[t] = Pn[(8 * t + g) * 4 + m];
+          nf[t] = -af[t];
+        }
+#pragma unroll
+        for (int tr = 0; tr < 4; ++tr)
+#pragma unroll
+          for (int tc = 0; tc < 4; ++tc) dmma_f(W[tr][tc][0], W[tr][tc][1], nf[tr], af[tc]);
+      }
+    } else {
 #pragma unroll
     for (int p2 = 0; p2 < 16; ++p2) {
       const int s0 = 2 * p2;            // slots (= columns of this block) of the panel: s0, s0 + 1
@@ -447,6 +573,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         }
       }
       if ((lane >> 1) == p2) { y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34]; }
+    }
     }
   }
   if (lane == 0) {
@@ -699,6 +826,12 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   }
 }
 
+// four-column panels need column j+3 to stay within one row of the 32-row window; FDM_CHOL_PANEL2 is the A/B switch
+inline bool mma_panel4(const fdm_plan* p) {
+  static const bool force2 = std::getenv("FDM_CHOL_PANEL2") != nullptr;
+  return p->hbw <= 29 && !force2;
+}
+
 inline int64_t ws_stride_of(const fdm_plan* p) {
   const int64_t nblk = (p->Nf + 31) / 32;
   return nblk * 1024 + nblk * 128 + 8;
@@ -734,6 +867,7 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   A.rowedge = p->d.band_rowedge; A.diags_ptr = p->d.diags_ptr; A.diags_idx = p->d.diags_idx;
   A.free_node = p->d.free_node; A.node_slot = p->d.node_slot; A.ninc_ptr = p->d.ninc_ptr;
   A.ninc_edge = p->d.ninc_edge; A.ninc_other = p->d.ninc_other; A.sup_mask = p->d.sup_mask;
+  A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_eent;
 }
 
 static int launch_invdiag_and_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
@@ -763,8 +897,9 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   A.q = q; A.xs = xs; A.loads = loads;
   A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
   const size_t smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
-  FDM_CUDA(cudaFuncSetAttribute(chol_factor_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  chol_factor_mma_kernel<true><<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+  void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4> : chol_factor_mma_kernel<true, 2>;
+  FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
   int rc = launch_invdiag_and_backward(p, A, batch, st);
   if (rc != FDM_OK) return rc;
   return fdm_check_launch("chol_warp_solve_from_q");
@@ -799,6 +934,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.q_stride = A.xs_stride = A.loads_stride = 0;
   A.rowedge = nullptr; A.diags_ptr = A.diags_idx = A.free_node = A.node_slot = nullptr;
   A.ninc_ptr = A.ninc_edge = A.ninc_other = nullptr; A.sup_mask = nullptr;
+  A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_kent;
   void (*fkern)(WArgs) = nullptr;
   void (*skern)(WArgs) = nullptr;
   if (p->hbw <= 7) { fkern = chol_factor_kernel<7>; skern = chol_subst_kernel<1>; }
@@ -810,7 +946,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     static const bool force_simt = std::getenv("FDM_CHOL_SIMT") != nullptr;   // A/B switch for profiling
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
     if (p->hbw <= 30 && !force_simt) {
-      fkern = chol_factor_mma_kernel<false>;
+      fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4> : chol_factor_mma_kernel<false, 2>;
       smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

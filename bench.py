@@ -45,7 +45,7 @@ CABLENET_NX = 200
 E2E_CHUNKS = int(os.environ.get("FDM_BENCH_E2E_CHUNKS", "8"))
 # dram__bytes_read.sum + dram__bytes_write.sum of one chol_factor_mma_kernel launch (B = 4096), from
 # profiles/r01k_chol_final_ncu.txt (0.325 GB read + 0.960 GB written)
-NCU_TRAFFIC_CHOL_FWD = 1.284e9
+NCU_TRAFFIC_CHOL_FWD = 1.295e9   # dram read+write of chol_factor_mma_kernel<0,4>, ncu --set full (profiles/r01n_chol_panel4_ncu.txt)
 
 
 def peaks():
@@ -229,19 +229,17 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
     E, N, Nf, Ns, nnz = s.num_edges, s.num_nodes, s.num_free, s.num_supports, s.nnz
     fac = 8 * 1024 * ((Nf + 31) // 32)                       # factor columns, 32 doubles each, rows padded to 32
     Y = pipe.rhs.clone()
-    stage_opts = {m: L.SolveOpts(pipe.solver_id, 0, 0.0, 0, 0, m) for m in (1, 2, 4)}
+    stage_opts = {m: L.SolveOpts(pipe.solver_id, 0, 0.0, 0, 0, m) for m in (1, 4)}
     calls = [
         ("assemble (K1)", 8 * E + 8 * nnz + 24 * Nf,
          lambda: lib.fdm_assemble(s.plan, P(pipe.q), P(pipe.xyz_fixed), P(pipe.loads), P(pipe.K), P(pipe.rhs), B, E, 0, 0, st)),
-        ("band Cholesky forward solve (K2b: the three launches below)", 8 * nnz + 48 * Nf + fac,
+        ("band Cholesky forward solve (K2b: the two launches below)", 8 * nnz + 48 * Nf + fac,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(pipe.opts_f), st)),
-        ("  chol_factor_mma_kernel (factorisation + fused forward substitution)", 8 * nnz + 24 * Nf + fac + fac // 8,
+        ("  chol_factor_mma_kernel (factorisation, fused forward substitution, diagonal blocks inverted)",
+         8 * nnz + 24 * Nf + fac + fac // 8,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(stage_opts[1]), st)),
-        ("  chol_invdiag_kernel (8x8 diagonal blocks inverted in place)", 2 * 8 * 36 * 4 * ((Nf + 31) // 32),
-         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
-                               C.byref(stage_opts[2]), st)),
         ("  chol_subst_kernel (backward substitution, factor streamed by TMA)", fac + fac // 8 + 24 * Nf,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(stage_opts[4]), st)),

@@ -267,6 +267,31 @@ __device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double 
                : "d"(a), "d"(b));
 }
 
+// The 8x8 diagonal blocks of one 32-column block inverted in place by the warp that has just written the
+// block's records (same arithmetic as chol_invdiag_kernel: lane c of every 8-lane group solves
+// L X(:,c) = e_c; the entries of L come from the lane that owns their column, by shuffle).
+__device__ __forceinline__ void invdiag_load(const double* fb, int lane, double (&col)[8]) {
+  const int c = lane & 7;
+  const double* gb = fb + (lane >> 3) * 256;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) col[d] = d < 8 - c ? gb[c * 32 + FROT(c, d)] : 0.0;   // L(c + d, c); 1/L(c,c) at d = 0
+}
+__device__ __forceinline__ void invdiag_solve_store(double* fb, int lane, const double (&col)[8]) {
+  const int c = lane & 7, base = lane & ~7;
+  double* gb = fb + (lane >> 3) * 256;
+  double X[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    double sacc = 0.0;
+#pragma unroll
+    for (int k = 0; k < r; ++k) sacc = fma(__shfl_sync(kFull, col[r - k], base + k), X[k], sacc);   // X[k] = 0 for k < c
+    X[r] = __shfl_sync(kFull, col[0], base + r) * ((r == c ? 1.0 : 0.0) - sacc);
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+    if (r >= c) gb[c * 32 + FROT(c, r - c)] = X[r];
+}
+
 template <bool FROM_Q, int PW>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
@@ -575,6 +600,12 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
       if ((lane >> 1) == p2) { y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34]; }
     }
     }
+    {                                                    // the block's diagonal 8x8 blocks, inverted in place
+      __syncwarp();                                      // (its records are written)
+      double dcol[8];
+      invdiag_load(fb, lane, dcol);
+      invdiag_solve_store(fb, lane, dcol);
+    }
   }
   if (lane == 0) {
     meta[0] = sigma;
@@ -870,9 +901,7 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_eent;
 }
 
-static int launch_invdiag_and_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
-  const int64_t items = batch * A.nblk * 4 * 8;
-  chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
+static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
   void (*skern)(WArgs) = p->hbw <= 7 ? chol_subst_kernel<1> : p->hbw <= 15 ? chol_subst_kernel<2>
                        : p->hbw <= 23 ? chol_subst_kernel<3> : chol_subst_kernel<4>;
   const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
@@ -900,7 +929,7 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4> : chol_factor_mma_kernel<true, 2>;
   FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
-  int rc = launch_invdiag_and_backward(p, A, batch, st);
+  int rc = launch_backward(p, A, batch, st);
   if (rc != FDM_OK) return rc;
   return fdm_check_launch("chol_warp_solve_from_q");
 }
@@ -942,17 +971,18 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   else if (p->hbw <= 23) { fkern = chol_factor_kernel<23>; skern = chol_subst_kernel<3>; }
   else { fkern = chol_factor_kernel<31>; skern = chol_subst_kernel<4>; }
   const int stages = o.stages ? o.stages : 7;
+  static const bool force_simt = std::getenv("FDM_CHOL_SIMT") != nullptr;   // A/B switch for profiling
+  const bool mma = p->hbw <= 30 && !force_simt;                             // these invert the diagonal blocks themselves
   if (!o.reuse_factor && (stages & 1)) {
-    static const bool force_simt = std::getenv("FDM_CHOL_SIMT") != nullptr;   // A/B switch for profiling
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
-    if (p->hbw <= 30 && !force_simt) {
+    if (mma) {
       fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4> : chol_factor_mma_kernel<false, 2>;
       smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
   }
-  if (!o.reuse_factor && (stages & 2)) {
+  if (!o.reuse_factor && (stages & 2) && !mma) {
     const int64_t items = batch * A.nblk * 4 * 8;
     chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
   }

@@ -296,7 +296,7 @@ template <bool FROM_Q, int PW>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * kFacWarps + warp;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // designs per CTA = warps per CTA (host's choice)
   if (b >= A.batch) return;
   double* fs = smem + warp * kMmaWarpSmem;
   double* Pn = fs + 32 * kMS;
@@ -863,6 +863,16 @@ inline bool mma_panel4(const fdm_plan* p) {
   return p->hbw <= 29 && !force2;
 }
 
+// designs (= warps) per CTA of the tensor-core factor kernels; FDM_CHOL_FACWARPS overrides for experiments
+inline int mma_warps_per_cta() {
+  static const int w = [] {
+    const char* e = std::getenv("FDM_CHOL_FACWARPS");
+    const int v = e ? std::atoi(e) : kFacWarps;
+    return v >= 1 && v <= kFacWarps ? v : kFacWarps;
+  }();
+  return w;
+}
+
 inline int64_t ws_stride_of(const fdm_plan* p) {
   const int64_t nblk = (p->Nf + 31) / 32;
   return nblk * 1024 + nblk * 128 + 8;
@@ -925,10 +935,11 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   fill_common(A, p, x, info, ws, batch);
   A.q = q; A.xs = xs; A.loads = loads;
   A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
-  const size_t smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
+  const int fw = mma_warps_per_cta();
+  const size_t smem = (size_t)fw * kMmaWarpSmem * sizeof(double);
   void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4> : chol_factor_mma_kernel<true, 2>;
   FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+  fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
   int rc = launch_backward(p, A, batch, st);
   if (rc != FDM_OK) return rc;
   return fdm_check_launch("chol_warp_solve_from_q");
@@ -975,12 +986,14 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   const bool mma = p->hbw <= 30 && !force_simt;                             // these invert the diagonal blocks themselves
   if (!o.reuse_factor && (stages & 1)) {
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
+    int fw = kFacWarps;
     if (mma) {
       fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4> : chol_factor_mma_kernel<false, 2>;
-      smem = (size_t)kFacWarps * kMmaWarpSmem * sizeof(double);
+      fw = mma_warps_per_cta();
+      smem = (size_t)fw * kMmaWarpSmem * sizeof(double);
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fkern<<<(unsigned)((batch + kFacWarps - 1) / kFacWarps), kFacThreads, smem, st>>>(A);
+    fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
   }
   if (!o.reuse_factor && (stages & 2) && !mma) {
     const int64_t items = batch * A.nblk * 4 * 8;

@@ -95,8 +95,9 @@ class Workspace:
 
 
 def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_factor=False,
-          workspace=None, return_info=False, check_every=0):
-    """K2: x = K^{-1} rhs (sparse.py:207-230 / 296).  Kdata (B?,nnz), rhs (B?,Nf,3)."""
+          workspace=None, return_info=False, check_every=0, stages=0):
+    """K2: x = K^{-1} rhs (sparse.py:207-230 / 296).  Kdata (B?,nnz), rhs (B?,Nf,3).
+    `stages` (profiling): bit mask of the band Cholesky launches to run, 0 = all (fdm_b200.h)."""
     s = structure
     Nf, nnz = s.num_free, s.nnz
     rhs = _chk(rhs, "rhs", (Nf, 3))
@@ -119,7 +120,7 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     sid = L.SOLVERS[solver] if isinstance(solver, str) else int(solver)
     ws = workspace if workspace is not None else Workspace()
     buf, need = ws.get(s, B, sid, rhs.device)
-    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)))
+    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)), int(stages))
     L.check(L.lib().fdm_solve(s.plan, _ptr(Kdata), _ptr(rhs), _ptr(x), _ptr(info), _ptr(buf),
                               buf.numel(), B, C.byref(opts), _stream()))
     return (x, info) if return_info else x

@@ -57,6 +57,7 @@ class ForwardAdjoint:
         # default: measured 3 % slower per step than assemble + solve (profiles/r01i_bench_fused_assembly.json),
         # the per-row diagonal / load-term loops sit on the factor kernel's staging path.
         is_chol = solver == "cholesky" or (solver == "auto" and self._auto_is_cholesky())
+        self.is_cholesky = is_chol
         self.fused_assembly = bool(fused_assembly and is_chol and B > 1 and s.half_bandwidth <= 30)
         self.graph = None
         self.use_graph = use_graph and self.capturable
@@ -87,7 +88,8 @@ class ForwardAdjoint:
         torch.cuda.synchronize(self.dev)
 
     def _launch(self, st):
-        """The kernel sequence of one forward+adjoint step on stream `st` (a raw cudaStream_t)."""
+        """The kernel sequence of one forward+adjoint step on stream `st` (a raw cudaStream_t); returns the
+        number of kernels launched (the forward band Cholesky solve is two: factor, substitution)."""
         s, lib, B = self.s, self.lib, self.B
         E, N, Nf, Ns = s.num_edges, s.num_nodes, s.num_free, s.num_supports
         ck = L.check
@@ -95,12 +97,12 @@ class ForwardAdjoint:
         if self.fused_assembly:
             # K1 + K2 in one call: the batched factorisation assembles its rows from q in place
             ck(lib.fdm_solve_from_q(s.plan, _p(self.q), _p(self.xyz_fixed), _p(self.loads), _p(self.x), _p(self.info_f),
-                                    _p(self.ws), self.ws.numel(), B, E, 0, 0, C.byref(self.opts_f), st)); n += 1
+                                    _p(self.ws), self.ws.numel(), B, E, 0, 0, C.byref(self.opts_f), st)); n += 2
         else:
             ck(lib.fdm_assemble(s.plan, _p(self.q), _p(self.xyz_fixed), _p(self.loads), _p(self.K),
                                 _p(self.rhs), B, E, 0, 0, st)); n += 1
             ck(lib.fdm_solve(s.plan, _p(self.K), _p(self.rhs), _p(self.x), _p(self.info_f), _p(self.ws),
-                             self.ws.numel(), B, C.byref(self.opts_f), st)); n += 1
+                             self.ws.numel(), B, C.byref(self.opts_f), st)); n += 2 if self.is_cholesky else 1
         ck(lib.fdm_positions(s.plan, _p(self.x), _p(self.xyz_fixed), _p(self.xyz), B, 0, 0, st)); n += 1
         if self.with_state:
             ck(lib.fdm_state(s.plan, _p(self.q), _p(self.xyz), _p(self.loads), _p(self.vectors),
@@ -173,11 +175,14 @@ class ChunkedForwardAdjoint:
         for off, part in zip(self.offsets, self.parts):
             part.set_inputs(q[off:off + part.B], xyz_fixed, loads, x0)
 
-    def __call__(self, q_host=None):
+    def enqueue(self, q_host=None):
+        """Asynchronous end-to-end pass of every slice on its own stream (no synchronisation)."""
         for off, part in zip(self.offsets, self.parts):
             part.enqueue_e2e(None if q_host is None else q_host[off:off + part.B])
-        for part in self.parts:
-            part.stream.synchronize()
+
+    def __call__(self, q_host=None):
+        self.enqueue(q_host)
+        self.synchronize()
         return [p.h_loss for p in self.parts], [p.h_q_bar for p in self.parts]
 
     def synchronize(self):

@@ -252,6 +252,44 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
                        double* d_faces_load_bar, int64_t batch, int64_t faces_load_stride, int is_local,
                        void* stream);
 
+/* ---- goals and losses fused after the state --------------------------------
+ * Replaces Loss.__call__ (losses/loss.py:60-90) / Error.__call__ (losses/errors.py:100-135) for goals
+ * whose prediction reads one element of the equilibrium state, and the reverse pass JAX derives:
+ *   kind 0 NodePointGoal (goals/node/point.py)            xyz[i]            vs target[3]
+ *        1 NodeResidualForceGoal (goals/node/residual.py) |residuals[i]|
+ *        2 NodeResidualVectorGoal                         residuals[i]      vs target[3]
+ *        3 EdgeLengthGoal (goals/edge/length.py)          lengths[e]
+ *        4 EdgeForceGoal (goals/edge/force.py)            forces[e]
+ *        5 EdgeLoadPathGoal (goals/edge/loadpath.py)      |forces[e]| lengths[e]
+ *        6 NetworkLoadPathGoal (goals/network/loadpath.py) sum_e |forces[e] lengths[e]|   (index unused)
+ *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
+ *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
+ * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):
+ *   loss = sum_g group_outer[g] * f_g(group_inner[g] * S_g),  S_g = sum of the group's term errors,
+ *   f = identity (group_final 0) or sqrt (1): alpha, the 1/number_of_goals of the Mean* errors and the root
+ *   of RootMeanSquaredError (errors.py:262-300).
+ * All arrays of the program are DEVICE pointers shared by the batch. */
+typedef struct fdm_goal_program {
+  int32_t num_terms, num_groups, has_network_loadpath;
+  const int32_t* kind;        /* (T) */
+  const int32_t* index;       /* (T) node or edge index (structure order) */
+  const int32_t* error;       /* (T) */
+  const double* weight;       /* (T) */
+  const double* target;       /* (T,3) scalar targets in column 0 */
+  const int32_t* group_ptr;   /* (G+1) */
+  const int32_t* group_final; /* (G) */
+  const double* group_inner;  /* (G) */
+  const double* group_outer;  /* (G) */
+} fdm_goal_program;
+
+/* loss (B); group_sums (B,G) or NULL.  With the four cotangent arrays (all or none) the kernel also
+ * writes d loss_b / d state: xyz_bar (B,N,3), lengths_bar (B,E), forces_bar (B,E), residuals_bar (B,N,3)
+ * -- the cotangents fdm_state_vjp takes. */
+int fdm_goals_loss(const fdm_plan* plan, const fdm_goal_program* program, const double* d_xyz,
+                   const double* d_lengths, const double* d_forces, const double* d_residuals, double* d_loss,
+                   double* d_group_sums, double* d_xyz_bar, double* d_lengths_bar, double* d_forces_bar,
+                   double* d_residuals_bar, int64_t batch, void* stream);
+
 /* ---- helper used by the benchmark's loss (above the path; kept here so the timed region
  * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */
 int fdm_loss_sqdist(const double* d_x, const double* d_x0, double* d_g, double* d_loss,

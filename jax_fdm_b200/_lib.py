@@ -29,7 +29,7 @@ EXPORTS = [
     "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",
     "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_solve_from_q", "fdm_spmm",
     "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_adjoint_grads", "fdm_edge_loads",
-    "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_loss_sqdist",
+    "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_goals_loss", "fdm_loss_sqdist",
     "fdm_last_error", "fdm_version",
 ]
 
@@ -37,6 +37,14 @@ EXPORTS = [
 class SolveOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("max_iters", C.c_int32), ("tol", C.c_double),
                 ("check_every", C.c_int32), ("reuse_factor", C.c_int32), ("stages", C.c_int32)]
+
+
+class GoalProgram(C.Structure):
+    """fdm_goal_program (include/fdm_b200.h): device pointers of a compiled Loss."""
+    _fields_ = [("num_terms", C.c_int32), ("num_groups", C.c_int32), ("has_network_loadpath", C.c_int32),
+                ("kind", C.c_void_p), ("index", C.c_void_p), ("error", C.c_void_p), ("weight", C.c_void_p),
+                ("target", C.c_void_p), ("group_ptr", C.c_void_p), ("group_final", C.c_void_p),
+                ("group_inner", C.c_void_p), ("group_outer", C.c_void_p)]
 
 
 class FdmError(RuntimeError):
@@ -97,6 +105,8 @@ def lib():
     L.fdm_face_loads.restype = C.c_int
     L.fdm_face_loads_vjp.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
     L.fdm_face_loads_vjp.restype = C.c_int
+    L.fdm_goals_loss.argtypes = [vp, C.POINTER(GoalProgram), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.fdm_goals_loss.restype = C.c_int
     L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.fdm_loss_sqdist.restype = C.c_int
     L.fdm_last_error.argtypes = []

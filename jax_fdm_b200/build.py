@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libfdm_b200.so")
-SOURCES = ["plan.cpp", "kernels_basic.cu", "spmm.cu", "solver_pcg.cu", "solver_chol.cu", "solver_chol_warp.cu",
+SOURCES = ["plan.cpp", "kernels_basic.cu", "goals.cu", "spmm.cu", "solver_pcg.cu", "solver_chol.cu", "solver_chol_warp.cu",
            "solver_pcg2.cu", "capi.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]

@@ -364,6 +364,31 @@ int fdm_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64
                                cen_bar, vert_bar, xyz_bar, fl_bar, batch, fs, is_local, (cudaStream_t)stream);
 }
 
+int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* xyz, const double* lengths,
+                   const double* forces, const double* residuals, double* loss, double* group_sums, double* xyz_bar,
+                   double* lengths_bar, double* forces_bar, double* residuals_bar, int64_t batch, void* stream) {
+  if (!ready(p, "fdm_goals_loss")) return FDM_ERR_INVALID;
+  if (!g || !xyz || !lengths || !forces || !residuals || !loss || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
+      (g->num_terms > 0 && (!g->kind || !g->index || !g->error || !g->weight || !g->target)) ||
+      (g->num_groups > 0 && (!g->group_ptr || !g->group_final || !g->group_inner || !g->group_outer))) {
+    fdm_set_error("fdm_goals_loss: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  if (g->num_groups > 64) {
+    fdm_set_error("fdm_goals_loss: more than 64 error terms in one loss");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  const bool any_bar = xyz_bar || lengths_bar || forces_bar || residuals_bar;
+  if (any_bar && !(xyz_bar && lengths_bar && forces_bar && residuals_bar)) {
+    fdm_set_error("fdm_goals_loss: pass all four cotangent arrays or none");
+    return FDM_ERR_INVALID;
+  }
+  return launch_goals_loss(p, g->num_terms, g->kind, g->index, g->error, g->weight, g->target, g->num_groups,
+                           g->group_ptr, g->group_final, g->group_inner, g->group_outer, g->has_network_loadpath, xyz,
+                           lengths, forces, residuals, loss, group_sums, xyz_bar, lengths_bar, forces_bar, residuals_bar,
+                           batch, (cudaStream_t)stream);
+}
+
 int fdm_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                     int64_t batch, int64_t x0_stride, void* stream) {
   if (!x || !x0 || n <= 0 || batch <= 0) {

@@ -1,0 +1,207 @@
+// Loss = sum over error terms of goals evaluated on the equilibrium state, fused with the cotangents of
+// the state.  Replaces, for the goals that read one element of the state,
+//   Error.__call__            losses/errors.py:100-135   (vmap of the per-element error, summed per collection)
+//   SquaredError / AbsoluteError / PredictionError / LogMaxError .error      errors.py:232-431
+//   Mean* / RootMeanSquaredError .errors                                      errors.py:262-300, 340-400
+//   Loss.__call__             losses/loss.py:60-90
+//   NodePointGoal, NodeResidualForceGoal, NodeResidualVectorGoal, EdgeLengthGoal, EdgeForceGoal,
+//   EdgeLoadPathGoal, NetworkLoadPathGoal .prediction   (goals/node/point.py, node/residual.py,
+//   edge/length.py, edge/force.py, edge/loadpath.py, network/loadpath.py)
+// and the reverse pass JAX derives from them.
+//
+// One CTA per design.  The goal "program" (shared by the batch) is a table of terms sorted by group
+// (= one Error instance): kind, element index, error kind, weight, target.  Pass 1 reduces every
+// group's sum S_g with a fixed tree (deterministic); loss = sum_g outer_g * f_g(inner_g * S_g), f = id or
+// sqrt.  Pass 2 scatters d loss / d state into xyz_bar, lengths_bar, forces_bar, residuals_bar (zeroed
+// here first; atomicAdd because several terms may read the same element -- two addends commute exactly,
+// three or more on one element are summed in an unspecified order).
+#include <cuda_runtime.h>
+
+#include "launch.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+enum GoalKind : int {
+  G_NODE_POINT = 0,        // xyz[i]                 (3) vs target (3)
+  G_NODE_RESIDUAL_FORCE,   // |residuals[i]|         (1)
+  G_NODE_RESIDUAL_VECTOR,  // residuals[i]           (3)
+  G_EDGE_LENGTH,           // lengths[e]             (1)
+  G_EDGE_FORCE,            // forces[e]              (1)
+  G_EDGE_LOADPATH,         // |forces[e]| lengths[e] (1)
+  G_NETWORK_LOADPATH,      // sum_e |forces[e] lengths[e]| (1)
+};
+enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
+
+struct GoalArgs {
+  int T, G, N, E;
+  const int32_t *kind, *index, *err, *group_ptr;   // (T), (T), (T), (G+1)
+  const double *weight, *target;                   // (T), (T,3)
+  const int32_t* gfinal;                           // (G) 0 identity, 1 sqrt
+  const double *ginner, *gouter;                   // (G)
+  const double *xyz, *lengths, *forces, *residuals;
+  double *loss, *gsum;                             // (B), (B,G)
+  double *xyz_bar, *lengths_bar, *forces_bar, *residuals_bar;
+  int need_loadpath;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  // fixed tree: warp shuffles then one warp over the partials
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double s = (threadIdx.x < kThreads / 32) ? red[threadIdx.x] : 0.0;
+  if (w == 0) {
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (l == 0) red[8] = s;
+  }
+  __syncthreads();
+  return red[8];
+}
+
+__device__ __forceinline__ double err_value(int ek, double w, double p, double t) {
+  const double d = p - t;
+  switch (ek) {
+    case E_SQUARED: return w * d * d;
+    case E_ABSOLUTE: return w * fabs(d);
+    case E_PREDICTION: return w * p;
+    default: return w * log1p(fmax(d, 0.0));
+  }
+}
+__device__ __forceinline__ double err_deriv(int ek, double w, double p, double t) {
+  const double d = p - t;
+  switch (ek) {
+    case E_SQUARED: return 2.0 * w * d;
+    case E_ABSOLUTE: return d > 0.0 ? w : (d < 0.0 ? -w : 0.0);
+    case E_PREDICTION: return w;
+    default: return d > 0.0 ? w / (1.0 + d) : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
+  __shared__ double red[16];
+  __shared__ double s_mult[64];
+  const int64_t b = blockIdx.x;
+  const double* xyz = A.xyz + b * (int64_t)A.N * 3;
+  const double* res = A.residuals + b * (int64_t)A.N * 3;
+  const double* len = A.lengths + b * (int64_t)A.E;
+  const double* frc = A.forces + b * (int64_t)A.E;
+  const bool bwd = A.xyz_bar != nullptr;
+  double* xb = bwd ? A.xyz_bar + b * (int64_t)A.N * 3 : nullptr;
+  double* rb = bwd ? A.residuals_bar + b * (int64_t)A.N * 3 : nullptr;
+  double* lb = bwd ? A.lengths_bar + b * (int64_t)A.E : nullptr;
+  double* fb = bwd ? A.forces_bar + b * (int64_t)A.E : nullptr;
+  if (bwd) {
+    for (int i = threadIdx.x; i < 3 * A.N; i += kThreads) { xb[i] = 0.0; rb[i] = 0.0; }
+    for (int i = threadIdx.x; i < A.E; i += kThreads) { lb[i] = 0.0; fb[i] = 0.0; }
+  }
+  double loadpath = 0.0;
+  if (A.need_loadpath) {
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < A.E; e += kThreads) acc += fabs(len[e] * frc[e]);
+    loadpath = block_sum(acc, red);
+  }
+  auto predict = [&](int k, int i, const double* t, double (&p)[3]) -> int {   // returns the number of components
+    switch (k) {
+      case G_NODE_POINT: p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2]; return 3;
+      case G_NODE_RESIDUAL_VECTOR: p[0] = res[3 * i]; p[1] = res[3 * i + 1]; p[2] = res[3 * i + 2]; return 3;
+      case G_NODE_RESIDUAL_FORCE:
+        p[0] = sqrt(res[3 * i] * res[3 * i] + res[3 * i + 1] * res[3 * i + 1] + res[3 * i + 2] * res[3 * i + 2]);
+        return 1;
+      case G_EDGE_LENGTH: p[0] = len[i]; return 1;
+      case G_EDGE_FORCE: p[0] = frc[i]; return 1;
+      case G_EDGE_LOADPATH: p[0] = fabs(frc[i]) * len[i]; return 1;
+      default: p[0] = loadpath; return 1;
+    }
+  };
+  // ---- pass 1: group sums, loss
+  double loss = 0.0;
+  for (int g = 0; g < A.G; ++g) {
+    double acc = 0.0;
+    for (int t = A.group_ptr[g] + threadIdx.x; t < A.group_ptr[g + 1]; t += kThreads) {
+      double p[3];
+      const int nc = predict(A.kind[t], A.index[t], A.target + 3 * t, p);
+      for (int c = 0; c < nc; ++c) acc += err_value(A.err[t], A.weight[t], p[c], A.target[3 * t + c]);
+    }
+    const double S = block_sum(acc, red);
+    const double u = A.ginner[g] * S;
+    const bool root = A.gfinal[g] == 1;
+    loss += A.gouter[g] * (root ? sqrt(u) : u);
+    if (threadIdx.x == 0) {
+      if (A.gsum) A.gsum[b * A.G + g] = S;
+      if (g < 64) s_mult[g] = A.gouter[g] * A.ginner[g] * (root ? 0.5 / sqrt(u) : 1.0);   // d loss / d S_g
+    }
+  }
+  if (threadIdx.x == 0) A.loss[b] = loss;
+  if (!bwd) return;
+  __syncthreads();
+  // ---- pass 2: cotangents of the state
+  for (int g = 0; g < A.G; ++g) {
+    const double mult = s_mult[g];
+    for (int t = A.group_ptr[g] + threadIdx.x; t < A.group_ptr[g + 1]; t += kThreads) {
+      const int k = A.kind[t], i = A.index[t], ek = A.err[t];
+      const double w = A.weight[t];
+      double p[3];
+      const int nc = predict(k, i, A.target + 3 * t, p);
+      double d[3];
+      for (int c = 0; c < nc; ++c) d[c] = mult * err_deriv(ek, w, p[c], A.target[3 * t + c]);
+      switch (k) {
+        case G_NODE_POINT:
+          for (int c = 0; c < 3; ++c) atomicAdd(xb + 3 * i + c, d[c]);
+          break;
+        case G_NODE_RESIDUAL_VECTOR:
+          for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, d[c]);
+          break;
+        case G_NODE_RESIDUAL_FORCE:
+          if (p[0] > 0.0)
+            for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, d[0] * res[3 * i + c] / p[0]);
+          break;
+        case G_EDGE_LENGTH: atomicAdd(lb + i, d[0]); break;
+        case G_EDGE_FORCE: atomicAdd(fb + i, d[0]); break;
+        case G_EDGE_LOADPATH: {
+          const double f = frc[i];
+          atomicAdd(fb + i, d[0] * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) * len[i]);
+          atomicAdd(lb + i, d[0] * fabs(f));
+          break;
+        }
+        default: break;   // network load path: every edge, by the whole CTA below
+      }
+    }
+    __syncthreads();
+    // network load path terms of this group: all threads scatter over the edges
+    for (int t = A.group_ptr[g]; t < A.group_ptr[g + 1]; ++t) {
+      if (A.kind[t] != G_NETWORK_LOADPATH) continue;
+      const double d0 = mult * err_deriv(A.err[t], A.weight[t], loadpath, A.target[3 * t]);
+      for (int e = threadIdx.x; e < A.E; e += kThreads) {
+        const double pl = len[e] * frc[e];
+        const double sg = pl > 0.0 ? 1.0 : (pl < 0.0 ? -1.0 : 0.0);
+        atomicAdd(fb + e, d0 * sg * len[e]);
+        atomicAdd(lb + e, d0 * sg * frc[e]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const int32_t* index, const int32_t* err,
+                      const double* weight, const double* target, int n_groups, const int32_t* group_ptr,
+                      const int32_t* gfinal, const double* ginner, const double* gouter, int need_loadpath,
+                      const double* xyz, const double* lengths, const double* forces, const double* residuals,
+                      double* loss, double* gsum, double* xyz_bar, double* lengths_bar, double* forces_bar,
+                      double* residuals_bar, int64_t batch, cudaStream_t st) {
+  GoalArgs A;
+  A.T = n_terms; A.G = n_groups; A.N = (int)p->N; A.E = (int)p->E;
+  A.kind = kind; A.index = index; A.err = err; A.group_ptr = group_ptr;
+  A.weight = weight; A.target = target; A.gfinal = gfinal; A.ginner = ginner; A.gouter = gouter;
+  A.xyz = xyz; A.lengths = lengths; A.forces = forces; A.residuals = residuals;
+  A.loss = loss; A.gsum = gsum;
+  A.xyz_bar = xyz_bar; A.lengths_bar = lengths_bar; A.forces_bar = forces_bar; A.residuals_bar = residuals_bar;
+  A.need_loadpath = need_loadpath;
+  goals_loss_kernel<<<(unsigned)batch, kThreads, 0, st>>>(A);
+  return fdm_check_launch("goals_loss");
+}

@@ -59,6 +59,12 @@ int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, in
                           const double* faces_load, const double* cen, const double* gl, const double* cot,
                           double* cen_bar, double* vert_bar, double* xyz_bar, double* fl_bar, int64_t batch, int64_t fs,
                           int local, cudaStream_t st);
+int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const int32_t* index, const int32_t* err,
+                      const double* weight, const double* target, int n_groups, const int32_t* group_ptr,
+                      const int32_t* gfinal, const double* ginner, const double* gouter, int need_loadpath,
+                      const double* xyz, const double* lengths, const double* forces, const double* residuals,
+                      double* loss, double* gsum, double* xyz_bar, double* lengths_bar, double* forces_bar,
+                      double* residuals_bar, int64_t batch, cudaStream_t st);
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                        int64_t batch, int64_t x0_stride, cudaStream_t st);
 

@@ -71,16 +71,15 @@ struct WArgs {
   const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
 };
 
-// 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~22 bits) + two Newton steps in
-// FP64 (relative error ~1e-16).  No special-case path: a non-positive pivot is reported through `bad`.
+// 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~20 bits) + ONE third-order step
+// y (1 + e/2 + 3e^2/8), e = 1 - x y^2 (error e^3: below double rounding) -- four dependent FP64 operations
+// on the pivot chain instead of the six of two Newton steps.  No special-case path: a non-positive pivot is
+// reported through `bad`.
 __device__ __forceinline__ double rsqrt_nr(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double h = 0.5 * x;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  return fma(y, e, y);
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -1,0 +1,125 @@
+"""
+Goals (mirror of `jax_fdm.goals` for the goals that read one element of the equilibrium state).
+
+A goal names an element by KEY (node key, edge key pair), a target and a weight, as in the reference
+(goals/goal.py:152-260); `index(structure)` resolves the key against the structure's ordering
+(equilibrium/indexing.py:88-150).  `prediction(eq_state, structure)` is the reference's per-goal
+prediction on torch tensors (used by tests and by `Error.evaluate_state`); the hot path does not call
+it: a `Loss` compiles its goals into a table and evaluates them with one fused kernel
+(csrc/goals.cu, `fdm_goals_loss`).
+"""
+import numpy as np
+
+__all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "NodeResidualForceGoal",
+           "NodeResidualVectorGoal", "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "NetworkLoadPathGoal",
+           "GoalState"]
+
+from collections import namedtuple
+
+GoalState = namedtuple("GoalState", "goal weight prediction")     # goals/state.py:8-25
+
+
+class Goal:
+    """goals/goal.py:152-379: key, target, weight; `kind` is the row of the kernel's prediction table."""
+    kind = -1
+    components = 1
+
+    def __init__(self, key, target, weight=1.0):
+        self.key = key
+        self.target = np.asarray(target, dtype=np.float64)
+        self.weight = float(weight)
+        if self.target.size != self.components:
+            raise ValueError(f"{type(self).__name__}: target must have {self.components} component(s)")
+
+    def index(self, structure):
+        raise NotImplementedError
+
+    def prediction(self, eq_state, structure):
+        raise NotImplementedError
+
+    def __call__(self, eq_state, structure):
+        import torch
+        p = self.prediction(eq_state, structure)
+        t = torch.as_tensor(self.target, dtype=p.dtype, device=p.device).reshape(p.shape[-1:] if self.components == 3 else ())
+        return GoalState(goal=t, weight=self.weight, prediction=p)
+
+
+class NodeGoal(Goal):
+    """goals/node/node.py: the key is a node key."""
+
+    def index(self, structure):
+        return structure.node_index[int(self.key)]
+
+
+class EdgeGoal(Goal):
+    """goals/edge/edge.py: the key is the (u, v) pair of the edge as the structure lists it."""
+
+    def index(self, structure):
+        return structure.edge_index[(int(self.key[0]), int(self.key[1]))]
+
+
+class NetworkGoal(Goal):
+    """goals/network/network.py: one goal for the whole structure (key -1)."""
+
+    def __init__(self, target=0.0, weight=1.0, key=-1):
+        super().__init__(key, target, weight)
+
+    def index(self, structure):
+        return 0
+
+
+class NodePointGoal(NodeGoal):
+    """goals/node/point.py: xyz of the node."""
+    kind, components = 0, 3
+
+    def prediction(self, eq_state, structure):
+        return eq_state.xyz[..., self.index(structure), :]
+
+
+class NodeResidualForceGoal(NodeGoal):
+    """goals/node/residual.py: magnitude of the residual force at the node."""
+    kind = 1
+
+    def prediction(self, eq_state, structure):
+        return eq_state.residuals[..., self.index(structure), :].norm(dim=-1)
+
+
+class NodeResidualVectorGoal(NodeGoal):
+    """goals/node/residual.py: residual force vector at the node."""
+    kind, components = 2, 3
+
+    def prediction(self, eq_state, structure):
+        return eq_state.residuals[..., self.index(structure), :]
+
+
+class EdgeLengthGoal(EdgeGoal):
+    """goals/edge/length.py:16-25."""
+    kind = 3
+
+    def prediction(self, eq_state, structure):
+        return eq_state.lengths[..., self.index(structure), 0]
+
+
+class EdgeForceGoal(EdgeGoal):
+    """goals/edge/force.py:16-25."""
+    kind = 4
+
+    def prediction(self, eq_state, structure):
+        return eq_state.forces[..., self.index(structure), 0]
+
+
+class EdgeLoadPathGoal(EdgeGoal):
+    """goals/edge/loadpath.py: |force| * length of the edge."""
+    kind = 5
+
+    def prediction(self, eq_state, structure):
+        i = self.index(structure)
+        return eq_state.forces[..., i, 0].abs() * eq_state.lengths[..., i, 0]
+
+
+class NetworkLoadPathGoal(NetworkGoal):
+    """goals/network/loadpath.py: sum over the edges of |force * length|."""
+    kind = 6
+
+    def prediction(self, eq_state, structure):
+        return (eq_state.lengths * eq_state.forces).abs().sum(dim=(-2, -1))

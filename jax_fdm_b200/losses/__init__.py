@@ -1,0 +1,227 @@
+"""
+Losses (mirror of `jax_fdm.losses`): error terms over goals, regularizers, and `Loss`.
+
+`Loss.__call__(params, model, structure)` follows losses/loss.py:60-90: the model's equilibrium state,
+plus every error term, plus every regularizer.  All error terms of a loss are compiled once per
+structure into ONE goal program and evaluated by ONE kernel launch (`fdm_goals_loss`) that also writes
+the cotangents of the state, so the reverse pass continues straight into `fdm_state_vjp`.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..goals import Goal
+
+__all__ = ["Error", "SquaredError", "MeanSquaredError", "RootMeanSquaredError", "AbsoluteError", "MeanAbsoluteError",
+           "PredictionError", "MeanPredictionError", "LogMaxError", "Regularizer", "L2Regularizer", "Loss"]
+
+F64 = torch.float64
+
+
+def _over_features(e, gs):
+    """Sum over the feature axis of a vector goal (xyz, residual vector); scalar goals have none."""
+    return e.sum(dim=-1) if gs.goal.dim() else e
+
+
+class Error:
+    """losses/errors.py:34-230: alpha * errors(sum over the goals of error(goal state))."""
+    err_kind = -1
+    mean = False
+    root = False
+
+    def __init__(self, goals, alpha=1.0, name=None):
+        self.goals = list(goals)
+        for g in self.goals:
+            if not isinstance(g, Goal) or g.kind < 0:
+                raise TypeError(f"{type(g).__name__} is not a goal the fused loss kernel evaluates")
+        self.alpha = float(alpha)
+        self.name = name or type(self).__name__
+
+    def number_of_goals(self):
+        return len(self.goals)
+
+    @staticmethod
+    def error(gstate):
+        raise NotImplementedError
+
+    def errors(self, total):
+        if self.mean:
+            total = total / self.number_of_goals()
+        return total.sqrt() if self.root else total
+
+    def evaluate_state(self, eq_state, structure):
+        """errors.py:165-200: the same value goal by goal in torch (tests, small problems; not the hot path)."""
+        total = sum(self.error(g(eq_state, structure)) for g in self.goals)
+        return self.errors(total) * self.alpha
+
+
+class SquaredError(Error):
+    """errors.py:232-258."""
+    err_kind = 0
+
+    @staticmethod
+    def error(gs):
+        return _over_features(gs.weight * (gs.prediction - gs.goal) ** 2, gs)
+
+
+class MeanSquaredError(SquaredError):
+    """errors.py:261-281."""
+    mean = True
+
+
+class RootMeanSquaredError(MeanSquaredError):
+    """errors.py:284-301."""
+    root = True
+
+
+class PredictionError(Error):
+    """errors.py:304-330."""
+    err_kind = 2
+
+    @staticmethod
+    def error(gs):
+        return _over_features(gs.weight * gs.prediction, gs)
+
+
+class MeanPredictionError(PredictionError):
+    """errors.py:333-352."""
+    mean = True
+
+
+class AbsoluteError(Error):
+    """errors.py:355-380."""
+    err_kind = 1
+
+    @staticmethod
+    def error(gs):
+        return _over_features(gs.weight * (gs.prediction - gs.goal).abs(), gs)
+
+
+class MeanAbsoluteError(AbsoluteError):
+    """errors.py:383-400."""
+    mean = True
+
+
+class LogMaxError(Error):
+    """errors.py:403-431."""
+    err_kind = 3
+
+    @staticmethod
+    def error(gs):
+        return _over_features(gs.weight * torch.log1p(torch.clamp(gs.prediction - gs.goal, min=0.0)), gs)
+
+
+class Regularizer:
+    """losses/regularizers.py:14-40."""
+
+    def __init__(self, alpha, name=None):
+        self.alpha = float(alpha)
+        self.name = name or type(self).__name__
+
+    def __call__(self, params):
+        raise NotImplementedError("Regularizer subclasses must implement __call__")
+
+
+class L2Regularizer(Regularizer):
+    """regularizers.py:43-70: alpha * sum(q^2)."""
+
+    def __call__(self, params):
+        return self.alpha * (params.q ** 2).sum(dim=-1)
+
+
+class _Program:
+    """A Loss's error terms compiled against one structure: device tables + the fdm_goal_program struct."""
+
+    def __init__(self, errors, structure, device):
+        kind, index, err, weight, target, gptr, gfinal, ginner, gouter = [], [], [], [], [], [0], [], [], []
+        for term in errors:
+            for g in term.goals:
+                kind.append(g.kind)
+                index.append(g.index(structure))
+                err.append(term.err_kind)
+                weight.append(g.weight)
+                t = np.zeros(3)
+                t[:g.components] = g.target.ravel()
+                target.append(t)
+            gptr.append(len(kind))
+            gfinal.append(1 if term.root else 0)
+            ginner.append(1.0 / term.number_of_goals() if term.mean else 1.0)
+            gouter.append(term.alpha)
+        self.num_terms, self.num_groups = len(kind), len(gfinal)
+
+        def dev(a, dt):
+            return torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
+
+        self.arrays = [dev(kind, np.int32), dev(index, np.int32), dev(err, np.int32), dev(weight, np.float64),
+                       dev(np.asarray(target).reshape(-1, 3), np.float64), dev(gptr, np.int32), dev(gfinal, np.int32),
+                       dev(ginner, np.float64), dev(gouter, np.float64)]
+        ptr = [C.c_void_p(a.data_ptr()) for a in self.arrays]
+        self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), *ptr)
+
+
+class _GoalsLoss(torch.autograd.Function):
+    """One launch: loss per design and d loss / d (xyz, lengths, forces, residuals)."""
+
+    @staticmethod
+    def forward(ctx, xyz, lengths, forces, residuals, structure, program):
+        s = structure
+        N, E = s.num_nodes, s.num_edges
+        batched = xyz.dim() == 3
+        B = xyz.shape[0] if batched else 1
+        xyz, lengths, forces, residuals = (t.contiguous() for t in (xyz, lengths, forces, residuals))
+        dev = xyz.device
+        loss = torch.empty((B,), dtype=F64, device=dev)
+        bars = [torch.empty_like(xyz), torch.empty_like(lengths), torch.empty_like(forces), torch.empty_like(residuals)]
+        P = lambda t: C.c_void_p(t.data_ptr())
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L.check(L.lib().fdm_goals_loss(s.plan, C.byref(program.struct), P(xyz), P(lengths), P(forces), P(residuals),
+                                       P(loss), None, *[P(t) for t in bars], B, st))
+        ctx.save_for_backward(*bars)
+        ctx.batched = batched
+        return loss if batched else loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        bars = ctx.saved_tensors
+        g = g.reshape(-1, 1, 1) if ctx.batched else g
+        return (*[b * g for b in bars], None, None)
+
+
+class Loss:
+    """losses/loss.py:22-171."""
+
+    def __init__(self, *args, name=None):
+        self.terms_error = [t for t in args if isinstance(t, Error)]
+        self.terms_regularization = [t for t in args if isinstance(t, Regularizer)]
+        self.name = name or type(self).__name__
+        self._programs = {}
+
+    @property
+    def terms(self):
+        return self.terms_error + self.terms_regularization
+
+    def number_of_goals(self):
+        return sum(t.number_of_goals() for t in self.terms_error)
+
+    def number_of_regularizers(self):
+        return len(self.terms_regularization)
+
+    def program(self, structure, device):
+        key = (id(structure), str(device))
+        if key not in self._programs:
+            self._programs[key] = _Program(self.terms_error, structure, device)
+        return self._programs[key]
+
+    def errors_from_state(self, eq_state, structure):
+        """Sum of the error terms on an equilibrium state: one fused kernel (fdm_goals_loss)."""
+        prog = self.program(structure, eq_state.xyz.device)
+        return _GoalsLoss.apply(eq_state.xyz, eq_state.lengths, eq_state.forces, eq_state.residuals, structure, prog)
+
+    def __call__(self, params, model, structure):
+        eq_state = model(params, structure)
+        loss = self.errors_from_state(eq_state, structure)
+        for reg in self.terms_regularization:
+            loss = loss + reg(params)
+        return loss

@@ -42,3 +42,4 @@ from .model import (  # noqa: F401
     nodes_load_faces,
     fixed_point_forward,
 )
+from . import goals  # noqa: F401

@@ -1,0 +1,57 @@
+"""
+oracle/goals.py -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Goal predictions, error terms and the loss, restated in numpy from the reference one-liners:
+  goals/node/point.py           NodePointGoal.prediction          xyz[i, :]
+  goals/node/residual.py        NodeResidualForceGoal             |residuals[i]|
+                                NodeResidualVectorGoal            residuals[i, :]
+  goals/edge/length.py:16-25    EdgeLengthGoal                    lengths[e, 0]
+  goals/edge/force.py:16-25     EdgeForceGoal                     forces[e, 0]
+  goals/edge/loadpath.py        EdgeLoadPathGoal                  |forces[e, 0]| * lengths[e, 0]
+  goals/network/loadpath.py     NetworkLoadPathGoal               sum |lengths * forces|
+  losses/errors.py:232-431      SquaredError, AbsoluteError, PredictionError, LogMaxError (.error),
+                                Mean*, RootMeanSquaredError (.errors), Error.__call__ (alpha)
+  losses/loss.py:60-90          Loss.__call__  (sum of error terms + regularizers)
+  losses/regularizers.py:43-70  L2Regularizer  alpha * sum(q^2)
+Parity unpinned against executed reference code (equinox / jax are absent); every function is the cited
+one-liner.  `state` is the dict of oracle.equilibrium_state.
+"""
+import numpy as np
+
+PREDICTIONS = {
+    "NodePointGoal": lambda st, i: st["xyz"][i, :],
+    "NodeResidualForceGoal": lambda st, i: np.linalg.norm(st["residuals"][i, :]),
+    "NodeResidualVectorGoal": lambda st, i: st["residuals"][i, :],
+    "EdgeLengthGoal": lambda st, i: st["lengths"][i, 0],
+    "EdgeForceGoal": lambda st, i: st["forces"][i, 0],
+    "EdgeLoadPathGoal": lambda st, i: np.abs(st["forces"][i, 0]) * st["lengths"][i, 0],
+    "NetworkLoadPathGoal": lambda st, i: np.sum(np.abs(st["lengths"] * st["forces"])),
+}
+
+ERRORS = {
+    "SquaredError": lambda w, p, t: np.sum(w * np.square(p - t)),
+    "AbsoluteError": lambda w, p, t: np.sum(w * np.abs(p - t)),
+    "PredictionError": lambda w, p, t: np.sum(p * w),
+    "LogMaxError": lambda w, p, t: np.sum(w * np.log1p(np.maximum(p - t, 0.0))),
+}
+BASE = {"MeanSquaredError": "SquaredError", "RootMeanSquaredError": "SquaredError",
+        "MeanAbsoluteError": "AbsoluteError", "MeanPredictionError": "PredictionError"}
+
+
+def error_term(name, goals, alpha, state):
+    """goals: list of (goal class name, element index, target, weight)."""
+    fn = ERRORS[BASE.get(name, name)]
+    total = sum(fn(w, PREDICTIONS[g](state, i), np.asarray(t, dtype=np.float64)) for g, i, t, w in goals)
+    if name.startswith("Mean") or name.startswith("RootMean"):
+        total = total / len(goals)
+    if name.startswith("Root"):
+        total = np.sqrt(total)
+    return alpha * total
+
+
+def loss(terms, state, q=None, l2_alpha=0.0):
+    """terms: list of (error class name, goals, alpha)."""
+    value = sum(error_term(n, g, a, state) for n, g, a in terms)
+    if l2_alpha:
+        value = value + l2_alpha * np.sum(np.square(q))
+    return value

@@ -1,0 +1,140 @@
+"""
+Goals and losses on the GPU: the fused kernel (fdm_goals_loss) against the oracle's numpy restatement
+of the reference's goal predictions / error terms (goals/*, losses/errors.py:232-431, losses/loss.py:
+60-90), against the goal-by-goal torch evaluation, and the gradient of Loss(params, model, structure)
+through the whole forward path against central differences of the oracle.  Tolerances: 1e-12 relative on
+the loss, 1e-6 relative on finite-difference gradients.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from oracle import goals as og  # noqa: E402
+from jax_fdm_b200 import datasets  # noqa: E402
+
+
+def T(a, grad=False):
+    t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=torch.device("cuda", 0))
+    return t.requires_grad_(True) if grad else t
+
+
+def build_loss(prob, s, rng):
+    """A loss with every goal kind and every error kind; returns (Loss, the same terms for the oracle)."""
+    from jax_fdm_b200 import goals as G, losses as LS
+
+    nodes, edges = prob.nodes, prob.edges
+    free = np.flatnonzero(prob.supports == 0)
+    fixed = np.flatnonzero(prob.supports != 0)
+    pick_n = rng.choice(free, size=min(12, free.size), replace=False)
+    pick_e = rng.choice(len(edges), size=min(15, len(edges)), replace=False)
+    ni, ei = s.node_index, s.edge_index
+
+    def ekey(e):
+        return (int(edges[e][0]), int(edges[e][1]))
+
+    spec = [
+        ("SquaredError", 1.0, [("NodePointGoal", int(nodes[n]), prob.xyz0[n] + 0.1 * rng.standard_normal(3), rng.uniform(0.5, 2)) for n in pick_n]),
+        ("MeanSquaredError", 0.7, [("EdgeLengthGoal", ekey(e), rng.uniform(0.5, 1.5), rng.uniform(0.5, 2)) for e in pick_e]),
+        ("RootMeanSquaredError", 1.3, [("EdgeForceGoal", ekey(e), rng.uniform(0.5, 3.0), 1.0) for e in pick_e[:7]]),
+        ("AbsoluteError", 0.5, [("NodeResidualForceGoal", int(nodes[n]), 0.3, 1.5) for n in fixed[:3]]),
+        ("MeanAbsoluteError", 0.9, [("NodeResidualVectorGoal", int(nodes[n]), 0.2 * rng.standard_normal(3), 1.0) for n in fixed[:4]]),
+        ("PredictionError", 0.01, [("NetworkLoadPathGoal", -1, 0.0, 1.0)]),
+        ("MeanPredictionError", 0.05, [("EdgeLoadPathGoal", ekey(e), 0.0, 2.0) for e in pick_e[:5]]),
+        ("LogMaxError", 2.0, [("EdgeLengthGoal", ekey(e), 0.8, 1.0) for e in pick_e[5:12]]),
+        ("SquaredError", 1e-4, [("NetworkLoadPathGoal", -1, 50.0, 1.0), ("EdgeLengthGoal", ekey(pick_e[0]), 1.0, 3.0)]),
+    ]
+    terms, oterms = [], []
+    for ename, alpha, goals in spec:
+        gl, ol = [], []
+        for gname, key, target, weight in goals:
+            cls = getattr(G, gname)
+            g = cls(target=target, weight=weight) if gname == "NetworkLoadPathGoal" else cls(key, target, weight)
+            gl.append(g)
+            idx = 0 if gname == "NetworkLoadPathGoal" else (ni[key] if isinstance(key, int) else ei[key])
+            ol.append((gname, idx, target, weight))
+        terms.append(getattr(LS, ename)(gl, alpha=alpha))
+        oterms.append((ename, ol, alpha))
+    l2 = 1e-3
+    return LS.Loss(*terms, LS.L2Regularizer(l2)), oterms, l2
+
+
+def oracle_loss(q, xs, loads, so, oterms, l2):
+    st, _ = oracle.forward(q, xs, loads, so)
+    return og.loss(oterms, st, q=q, l2_alpha=l2)
+
+
+def test_fused_loss_matches_oracle_and_goalwise_torch():
+    import jax_fdm_b200.equilibrium as eq
+
+    prob = datasets.cablenet_problem(8, seed=4)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    rng = np.random.default_rng(0)
+    loss, oterms, l2 = build_loss(prob, s, rng)
+    model = eq.EquilibriumModelSparse(tmax=1)
+    B = 5
+    qb = prob.q[None, :] * rng.uniform(0.8, 1.25, size=(B, prob.q.size))
+    params = eq.EquilibriumParametersState(T(qb), T(prob.xyz_fixed), eq.LoadState(T(prob.loads), 0.0, 0.0))
+    got = loss(params, model, s).cpu().numpy()
+    assert got.shape == (B,)
+    for b in range(B):
+        ref = oracle_loss(qb[b], prob.xyz_fixed, prob.loads, so, oterms, l2)
+        assert abs(got[b] - ref) <= 1e-12 * abs(ref), (b, got[b], ref)
+    # unbatched, and the goal-by-goal evaluation of errors.py:165-200
+    p1 = eq.EquilibriumParametersState(T(prob.q), T(prob.xyz_fixed), eq.LoadState(T(prob.loads), 0.0, 0.0))
+    one = loss(p1, model, s)
+    ref = oracle_loss(prob.q, prob.xyz_fixed, prob.loads, so, oterms, l2)
+    assert one.dim() == 0 and abs(one.item() - ref) <= 1e-12 * abs(ref)
+    st = model(p1, s)
+    slow = sum(t.evaluate_state(st, s) for t in loss.terms_error) + loss.terms_regularization[0](p1)
+    assert abs(slow.item() - ref) <= 1e-12 * abs(ref)
+
+
+def test_loss_gradients_through_the_model_vs_finite_differences():
+    import jax_fdm_b200.equilibrium as eq
+
+    prob = datasets.cablenet_problem(7, seed=11)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    rng = np.random.default_rng(1)
+    loss, oterms, l2 = build_loss(prob, s, rng)
+    model = eq.EquilibriumModelSparse(tmax=1)
+    q, xs, p = T(prob.q, True), T(prob.xyz_fixed, True), T(prob.loads, True)
+    val = loss(eq.EquilibriumParametersState(q, xs, eq.LoadState(p, 0.0, 0.0)), model, s)
+    val.backward()
+    for grad, arr, mk in [(q.grad, prob.q, lambda a: (a, prob.xyz_fixed, prob.loads)),
+                          (xs.grad, prob.xyz_fixed, lambda a: (prob.q, a, prob.loads)),
+                          (p.grad, prob.loads, lambda a: (prob.q, prob.xyz_fixed, a))]:
+        gnp = grad.cpu().numpy()
+        scale = np.abs(gnp).max()
+        for k in rng.choice(arr.size, size=8, replace=False):
+            d = np.zeros(arr.size)
+            d[k] = 1e-6 * max(1.0, abs(arr.flat[k]))
+            d = d.reshape(arr.shape)
+            fd = (oracle_loss(*mk(arr + d), so, oterms, l2) - oracle_loss(*mk(arr - d), so, oterms, l2)) / (2 * d.flat[k])
+            assert abs(gnp.flat[k] - fd) <= 1e-6 * scale + 1e-9, (k, gnp.flat[k], fd)
+
+
+def test_batched_gradients_are_per_design():
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import goals as G, losses as LS
+
+    prob = datasets.pillow_problem(10)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    loss = LS.Loss(LS.SquaredError([G.EdgeLengthGoal((int(u), int(v)), 0.9) for u, v in prob.edges]),
+                   LS.PredictionError([G.NetworkLoadPathGoal()], alpha=0.01))
+    model = eq.EquilibriumModelSparse(tmax=1)
+    B = 6
+    qb = datasets.pillow_batch_q(prob.edges.shape[0], 0, B)
+    q = T(qb, True)
+    vals = loss(eq.EquilibriumParametersState(q, T(prob.xyz_fixed), eq.LoadState(T(prob.loads), 0.0, 0.0)), model, s)
+    vals.sum().backward()
+    for b in (0, B - 1):
+        q1 = T(qb[b], True)
+        v1 = loss(eq.EquilibriumParametersState(q1, T(prob.xyz_fixed), eq.LoadState(T(prob.loads), 0.0, 0.0)), model, s)
+        v1.backward()
+        assert abs(v1.item() - vals[b].item()) <= 1e-13 * abs(v1.item())
+        assert (q1.grad - q.grad[b]).abs().max().item() <= 1e-12 * q1.grad.abs().max().item()

@@ -47,8 +47,9 @@ enum {
 enum {
   FDM_STATUS_OK = 0,
   FDM_STATUS_NOT_CONVERGED = 1,
-  FDM_STATUS_INDEFINITE = 2,   /* mixed-sign diagonal / pivot: K neither SPD nor -SPD   */
-  FDM_STATUS_BREAKDOWN = 3     /* non-finite scalar met in the iteration                */
+  FDM_STATUS_INDEFINITE = 2,   /* mixed-sign diagonal / pivot: K neither SPD nor -SPD (the batched band
+                                  Cholesky solves such designs itself when hbw <= 29: FDM_INFO_SIGN 0) */
+  FDM_STATUS_BREAKDOWN = 3     /* non-finite scalar met in the iteration / vanishing pivot */
 };
 
 /* layout of the per-solve info record (doubles), one record per design of the batch */
@@ -56,7 +57,7 @@ enum {
   FDM_INFO_STATUS = 0,
   FDM_INFO_ITERS = 1,
   FDM_INFO_RELRES = 2,         /* max over rhs of ||r|| / ||b|| (recurrence residual)   */
-  FDM_INFO_SIGN = 3,           /* +1: K SPD, -1: -K SPD                                 */
+  FDM_INFO_SIGN = 3,           /* +1: K SPD, -1: -K SPD, 0: indefinite K factored as L D L^T (signed pivots) */
   FDM_INFO_STRIDE = 8
 };
 

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
   if (lane == 0) {
     meta[0] = sigma;
     meta[1] = (double)bad;
+    meta[2] = 0.0;
   }
 }
 
@@ -291,8 +292,15 @@ __device__ __forceinline__ void invdiag_solve_store(double* fb, int lane, const 
     if (r >= c) gb[c * 32 + FROT(c, r - c)] = X[r];
 }
 
-template <bool FROM_Q, int PW>
+// SIGNED: second pass over the designs the plain factorisation flagged (a pivot of sigma*K was not positive:
+// mixed-sign q).  Same kernel with signed pivots, sigma*K = L D L^T, D = diag(+-1), no pivoting: column k is
+// L(:,k) = A(:,k) / (d_k sqrt|piv_k|), the update W -= d_k l_k l_k^T, and the forward-substituted right-hand
+// sides are stored multiplied by D so that the backward substitution runs unchanged.  The signs go to the
+// fourth slot of the intermediate right-hand sides (the adjoint's forward sweep needs them), meta[2] = 1.
+// A pivot below 1e-13 of the largest diagonal entry seen is reported as a breakdown (meta[1] = 2).
+template <bool FROM_Q, int PW, bool SIGNED>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
+  static_assert(!SIGNED || PW == 4, "signed pivots are implemented for four-column panels");
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // designs per CTA = warps per CTA (host's choice)
@@ -308,6 +316,8 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
   double* ysol = fac + (int64_t)nblk * 1024;
   double* meta = ysol + (int64_t)nblk * 128;
   int bad = 0;
+  if (SIGNED && meta[1] == 0.0) return;                    // the plain factorisation succeeded for this design
+  double dmax = 0.0;                                       // SIGNED: largest |diagonal entry| staged so far
 
   // K(i,i) = sum of q over the incident edges of free row f, in ascending edge id (the order of the
   // reference's `diags @ q`, structures.py:316-350 -- same additions as assemble_kernel)
@@ -386,9 +396,16 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
 #pragma unroll 8
   for (int r = 0; r < 32; ++r) fs[r * kMS + lane] = 0.0;
   __syncwarp();
+  auto track_dmax = [&]() {                                // after a __syncwarp that follows stage_rows
+    double dm = fabs(fs[lane * kMS + lane]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dm = fmax(dm, __shfl_xor_sync(kFull, dm, o));
+    dmax = fmax(dmax, dm);
+  };
   double W[4][4][2], y[3];
   stage_rows(0);
   __syncwarp();
+  if (SIGNED) track_dmax();
 #pragma unroll
   for (int tr = 0; tr < 4; ++tr)
 #pragma unroll
@@ -407,6 +424,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
     __syncwarp();
     stage_rows(jb + 1);
     __syncwarp();
+    if (SIGNED) track_dmax();
     if constexpr (PW == 4) {
       // Four columns per panel (hbw <= 29): all four k-slices of the DMMA carry data.  Column j+3 can reach
       // row j+32, one row past the window: that entry has no fill before it (rows j+32 and j..j+2 are more
@@ -430,34 +448,52 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         const double2 va = *reinterpret_cast<const double2*>(Pn + 4 * lane);
         const double2 vb = *reinterpret_cast<const double2*>(Pn + 4 * lane + 2);
         const int d0 = (lane - s0) & 31;                 // row of this lane = j0 + s0 + d0
+        // signed pivots (SIGNED): d_k = sign(piv_k), l_k = v_k / (d_k sqrt|piv_k|), update with d_k l_k l_k^T
+        const double thr = SIGNED ? 1e-13 * dmax : 0.0;
         const double piv0 = __shfl_sync(kFull, va.x, s0);
-        const double inv0 = rsqrt_nr(piv0);
-        const double l0 = va.x * inv0;
-        double v1 = fma(-l0, __shfl_sync(kFull, l0, s0 + 1), va.y);
-        double v2 = fma(-l0, __shfl_sync(kFull, l0, s0 + 2), vb.x);
-        double v3 = fma(-l0, __shfl_sync(kFull, l0, s0 + 3), vb.y);
+        const double sg0 = SIGNED && piv0 < 0.0 ? -1.0 : 1.0;
+        const double inv0 = rsqrt_nr(SIGNED ? fabs(piv0) : piv0);
+        const double l0 = va.x * (SIGNED ? sg0 * inv0 : inv0);
+        const double m0s = SIGNED ? -sg0 * l0 : -l0;
+        double v1 = fma(m0s, __shfl_sync(kFull, l0, s0 + 1), va.y);
+        double v2 = fma(m0s, __shfl_sync(kFull, l0, s0 + 2), vb.x);
+        double v3 = fma(m0s, __shfl_sync(kFull, l0, s0 + 3), vb.y);
         const double piv1 = __shfl_sync(kFull, v1, s0 + 1);
-        const double inv1 = rsqrt_nr(piv1);
-        const double l1 = v1 * inv1;
-        v2 = fma(-l1, __shfl_sync(kFull, l1, s0 + 2), v2);
-        v3 = fma(-l1, __shfl_sync(kFull, l1, s0 + 3), v3);
+        const double sg1 = SIGNED && piv1 < 0.0 ? -1.0 : 1.0;
+        const double inv1 = rsqrt_nr(SIGNED ? fabs(piv1) : piv1);
+        const double l1 = v1 * (SIGNED ? sg1 * inv1 : inv1);
+        const double m1s = SIGNED ? -sg1 * l1 : -l1;
+        v2 = fma(m1s, __shfl_sync(kFull, l1, s0 + 2), v2);
+        v3 = fma(m1s, __shfl_sync(kFull, l1, s0 + 3), v3);
         const double piv2 = __shfl_sync(kFull, v2, s0 + 2);
-        const double inv2 = rsqrt_nr(piv2);
-        const double l2 = v2 * inv2;
-        v3 = fma(-l2, __shfl_sync(kFull, l2, s0 + 3), v3);
+        const double sg2 = SIGNED && piv2 < 0.0 ? -1.0 : 1.0;
+        const double inv2 = rsqrt_nr(SIGNED ? fabs(piv2) : piv2);
+        const double l2 = v2 * (SIGNED ? sg2 * inv2 : inv2);
+        const double m2s = SIGNED ? -sg2 * l2 : -l2;
+        v3 = fma(m2s, __shfl_sync(kFull, l2, s0 + 3), v3);
         const double piv3 = __shfl_sync(kFull, v3, s0 + 3);
-        const double inv3 = rsqrt_nr(piv3);
-        const double l3 = v3 * inv3;
-        bad |= !(piv0 > 0.0) | !(piv1 > 0.0) | !(piv2 > 0.0) | !(piv3 > 0.0);
-        const double x3 = fs[s0 * kMS + s0 + 3] * inv3;  // L(j+32, j+3), see above
+        const double sg3 = SIGNED && piv3 < 0.0 ? -1.0 : 1.0;
+        const double inv3 = rsqrt_nr(SIGNED ? fabs(piv3) : piv3);
+        const double l3 = v3 * (SIGNED ? sg3 * inv3 : inv3);
+        if (SIGNED) {
+          if (!(fabs(piv0) > thr) | !(fabs(piv1) > thr) | !(fabs(piv2) > thr) | !(fabs(piv3) > thr)) bad = 2;
+        } else {
+          bad |= !(piv0 > 0.0) | !(piv1 > 0.0) | !(piv2 > 0.0) | !(piv3 > 0.0);
+        }
+        const double x3 = fs[s0 * kMS + s0 + 3] * (SIGNED ? sg3 * inv3 : inv3);  // L(j+32, j+3), see above
         // ---- 2. right-hand sides; lane s0 + k keeps the solved entries of column j + k
         double yd0, yd1, yd2;
         {
           const double linv[4] = {inv0, inv1, inv2, inv3}, lcol[4] = {l0, l1, l2, l3};
+          const double lsgn[4] = {sg0, sg1, sg2, sg3};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const double t0 = y[0] * linv[k], t1 = y[1] * linv[k], t2 = y[2] * linv[k];
-            if (lane == s0 + k) { yb[(s0 + k) * 4] = t0; yb[(s0 + k) * 4 + 1] = t1; yb[(s0 + k) * 4 + 2] = t2; }
+            if (lane == s0 + k) {
+              const double dk = SIGNED ? lsgn[k] : 1.0;    // stored as D w: the backward substitution starts from it
+              yb[(s0 + k) * 4] = dk * t0; yb[(s0 + k) * 4 + 1] = dk * t1; yb[(s0 + k) * 4 + 2] = dk * t2;
+              if (SIGNED) yb[(s0 + k) * 4 + 3] = dk;
+            }
             yd0 = __shfl_sync(kFull, t0, s0 + k);
             yd1 = __shfl_sync(kFull, t1, s0 + k);
             yd2 = __shfl_sync(kFull, t2, s0 + k);
@@ -514,9 +550,11 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         __syncwarp();
         double af[4], nf[4];
 #pragma unroll
+        const double dm = SIGNED ? (m == 0 ? sg0 : m == 1 ? sg1 : m == 2 ? sg2 : sg3) : 1.0;   // this lane's k slice
+#pragma unroll
         for (int t = 0; t < 4; ++t) {
           af[t] = Pn[(8 * t + g) * 4 + m];
-          nf[t] = -af[t];
+          nf[t] = SIGNED ? -dm * af[t] : -af[t];
         }
 #pragma unroll
         for (int tr = 0; tr < 4; ++tr)
@@ -609,6 +647,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
   if (lane == 0) {
     meta[0] = sigma;
     meta[1] = (double)bad;
+    meta[2] = SIGNED ? 1.0 : 0.0;
   }
 }
 
@@ -671,7 +710,8 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   double* ysol = fac + (int64_t)nblk * 1024;
   const double* meta = ysol + (int64_t)nblk * 128;
   const double sigma = meta[0];
-  const bool bad = meta[1] != 0.0;
+  const int bad = (int)meta[1];
+  const bool sgn = meta[2] != 0.0;                        // sigma*K = L D L^T: D in slot 3 of the intermediate rhs
 
   if (lane == 0) {
     mbar_init(bars, 1);
@@ -788,7 +828,12 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
           dmma(z0, z1, a0, b0);
           dmma(z0, z1, a1, b1);
         }
-        if (m < 2) *reinterpret_cast<double2*>(ysol + (int64_t)(j0 + cb + g) * 4 + 2 * m) = make_double2(z0, z1);
+        {                                                  // stored as D z (slot 3 keeps D): the backward sweep starts from it
+          double* zo = ysol + (int64_t)(j0 + cb + g) * 4;
+          const double dk = sgn ? zo[3] : 1.0;
+          if (m == 0) *reinterpret_cast<double2*>(zo) = make_double2(dk * z0, dk * z1);
+          if (m == 1) zo[2] = dk * z0;
+        }
         // T[i] -= L_{k+i,k} z_k
         *reinterpret_cast<double2*>(zt2 + g * 8 + 2 * m) = make_double2(z0, z1);
         __syncwarp();
@@ -849,10 +894,10 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   }
   if (A.info && lane == 0) {
     double* inf = A.info + b * FDM_INFO_STRIDE;
-    inf[FDM_INFO_STATUS] = bad ? (double)FDM_STATUS_INDEFINITE : (double)FDM_STATUS_OK;
+    inf[FDM_INFO_STATUS] = bad == 0 ? (double)FDM_STATUS_OK : bad == 2 ? (double)FDM_STATUS_BREAKDOWN : (double)FDM_STATUS_INDEFINITE;
     inf[FDM_INFO_ITERS] = 0.0;
     inf[FDM_INFO_RELRES] = 0.0;
-    inf[FDM_INFO_SIGN] = sigma;
+    inf[FDM_INFO_SIGN] = sgn ? 0.0 : sigma;               // 0: indefinite K, solved with signed pivots
   }
 }
 
@@ -936,9 +981,13 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
   const int fw = mma_warps_per_cta();
   const size_t smem = (size_t)fw * kMmaWarpSmem * sizeof(double);
-  void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4> : chol_factor_mma_kernel<true, 2>;
+  void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, false> : chol_factor_mma_kernel<true, 2, false>;
   FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+  if (mma_panel4(p)) {   // designs with a non-positive pivot (mixed-sign q) are factored again with signed pivots
+    FDM_CUDA(cudaFuncSetAttribute(chol_factor_mma_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    chol_factor_mma_kernel<true, 4, true><<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+  }
   int rc = launch_backward(p, A, batch, st);
   if (rc != FDM_OK) return rc;
   return fdm_check_launch("chol_warp_solve_from_q");
@@ -987,12 +1036,16 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
     int fw = kFacWarps;
     if (mma) {
-      fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4> : chol_factor_mma_kernel<false, 2>;
+      fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, false> : chol_factor_mma_kernel<false, 2, false>;
       fw = mma_warps_per_cta();
       smem = (size_t)fw * kMmaWarpSmem * sizeof(double);
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    if (mma && mma_panel4(p)) {   // designs with a non-positive pivot (mixed-sign q): again, with signed pivots
+      FDM_CUDA(cudaFuncSetAttribute(chol_factor_mma_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      chol_factor_mma_kernel<false, 4, true><<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    }
   }
   if (!o.reuse_factor && (stages & 2) && !mma) {
     const int64_t items = batch * A.nblk * 4 * 8;

@@ -68,10 +68,49 @@ def test_band_cholesky_forward_and_stored_factor(nx, ny, batch, sign):
         assert np.abs(lam[b].cpu().numpy() - lo).max() <= 1e-10 * np.abs(lo).max()
 
 
-def test_indefinite_design_is_flagged_not_solved():
+@pytest.mark.parametrize("nx,ny,batch", [(9, 6, 3), (30, 30, 40), (12, 25, 5)])
+def test_mixed_sign_designs_are_solved_with_signed_pivots(nx, ny, batch):
+    """Mixed-sign q makes K indefinite; the reference's LU (sparse.py:147-149) still solves it.  The plain
+    Cholesky flags those designs and a second pass factors them as L D L^T (hbw <= 29): status 0, sign 0,
+    positions and the adjoint solve with the stored factor against the oracle's SuperLU; the definite designs
+    of the same batch are untouched (sign +-1)."""
     import jax_fdm_b200.equilibrium as eq
 
-    m, supports, q, xs, loads = strip_problem(9, 6, 1.0, seed=3)
+    m, supports, q, xs, loads = strip_problem(nx, ny, 1.0, seed=3 + nx)
+    s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
+    so = oracle.build_structure(m.nodes, m.edges, supports)
+    assert s.half_bandwidth <= 29
+    rng = np.random.default_rng(nx)
+    qb = q[None, :] * rng.uniform(0.8, 1.25, size=(batch, q.size))
+    mixed = np.arange(batch) % 2 == 1
+    flip = np.where(rng.random(q.size) < 0.3, -1.0, 1.0)            # 30 % of the edges in compression
+    qb[mixed] *= flip
+    qb[0] *= -1.0                                                   # and one all-negative design (K = -SPD)
+    K, rhs = eq.ops.assemble(s, T(qb), T(xs), T(loads))
+    ws = eq.ops.Workspace()
+    x, info = eq.ops.solve(s, K, rhs, solver="cholesky", return_info=True, workspace=ws)
+    info = info.cpu().numpy()
+    assert (info[:, 0] == 0).all()
+    assert (info[mixed, 3] == 0).all() and info[0, 3] == -1 and (info[~mixed, 3] != 0).all()
+    g = rng.standard_normal((batch, s.num_free, 3))
+    lam = eq.ops.solve(s, K, T(g), solver="cholesky", workspace=ws, reuse_factor=True)
+    for b in list(range(min(batch, 6))) + [batch - 1]:
+        Kb = oracle.stiffness_matrix_sparse(qb[b], so)
+        xo = oracle.sparse_solve(Kb, oracle.load_matrix(qb[b], xs, loads, so))
+        lo = oracle.sparse_solve(Kb, g[b])
+        cond_slack = 1e-9 if mixed[b] else 1e-10                    # no pivoting: a little element growth is allowed
+        assert np.abs(x[b].cpu().numpy() - xo).max() <= cond_slack * np.abs(xo).max(), b
+        assert np.abs(lam[b].cpu().numpy() - lo).max() <= cond_slack * np.abs(lo).max(), b
+    # the fused route (K never formed) takes the same second pass: same bits
+    x2, info2 = eq.ops.solve_from_q(s, T(qb), T(xs), T(loads), return_info=True)
+    assert torch.equal(x2, x) and torch.equal(info2[:, :4].cpu(), torch.as_tensor(info[:, :4]))
+
+
+def test_indefinite_design_is_flagged_at_half_bandwidth_30_and_31():
+    """The signed second pass exists for the four-column kernel (hbw <= 29); wider bands keep the flag."""
+    import jax_fdm_b200.equilibrium as eq
+
+    m, supports, q, xs, loads = strip_problem(31, 40, 1.0, seed=3)
     s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
     qb = np.stack([q, q * np.where(np.arange(q.size) % 2, -1.0, 1.0), q])
     K, rhs = eq.ops.assemble(s, T(qb), T(xs), T(loads))

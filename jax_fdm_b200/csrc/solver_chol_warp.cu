@@ -338,23 +338,34 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
   const int2* ent = reinterpret_cast<const int2*>(A.stage_ent);
   auto stage_rows = [&](int blk) {
     const int R0 = blk * 32;
-    if (blk > 0) {
-      const int h0 = __ldg(A.stage_ptr + blk - 1), h1 = __ldg(A.stage_ptr + blk);
-      for (int gq = h0; gq < h1; ++gq) {
-        const int2 e = __ldg(ent + gq * 32 + lane);
-        if (e.y != -4) fs[e.x + (e.x >> 5) * (kMS - 32)] = 0.0;
+    // loads are issued in the order that keeps two chains in flight side by side: entry lists -> K.data,
+    // band-to-free index -> right-hand side
+    const int g0 = __ldg(A.stage_ptr + blk), g1 = __ldg(A.stage_ptr + blk + 1);
+    int gi = -1;
+    if (R0 + lane < n) gi = __ldg(A.iperm + R0 + lane);
+    int2 e[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) e[u] = g0 + u < g1 ? __ldg(ent + (g0 + u) * 32 + lane) : make_int2(0, -4);
+    if (blk > 0) {                                           // take back the previous block's entries
+      const int h0 = __ldg(A.stage_ptr + blk - 1);
+      for (int gq = h0; gq < g0; gq += 4) {
+        int2 o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = gq + u < g0 ? __ldg(ent + (gq + u) * 32 + lane) : make_int2(0, -4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (o[u].y != -4) fs[o[u].x + (o[u].x >> 5) * (kMS - 32)] = 0.0;
       }
       __syncwarp();
     }
-    const int g0 = __ldg(A.stage_ptr + blk), g1 = __ldg(A.stage_ptr + blk + 1);
-    // right-hand sides of row R0 + lane (FROM_Q: lane r also finishes row R0 + r, below)
-    int gi = -1;
-    if (R0 + lane < n) gi = __ldg(A.iperm + R0 + lane);
+    double rr0 = 0.0, rr1 = 0.0, rr2 = 0.0;
+    if (!FROM_Q && gi >= 0) { rr0 = rhs[3 * gi]; rr1 = rhs[3 * gi + 1]; rr2 = rhs[3 * gi + 2]; }
     for (int gq = g0; gq < g1; gq += 4) {
-      int2 e[4];
       double v[4];
+      if (gq > g0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) e[u] = gq + u < g1 ? __ldg(ent + (gq + u) * 32 + lane) : make_int2(0, -4);
+        for (int u = 0; u < 4; ++u) e[u] = gq + u < g1 ? __ldg(ent + (gq + u) * 32 + lane) : make_int2(0, -4);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         v[u] = e[u].y == -2 ? 1.0 : 0.0;
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     if (FROM_Q) __syncwarp();                                // the list wrote a zero on the diagonals, see below
     if (!FROM_Q) {
-      if (gi >= 0) { r0 = sigma * rhs[3 * gi]; r1 = sigma * rhs[3 * gi + 1]; r2 = sigma * rhs[3 * gi + 2]; }
+      r0 = sigma * rr0; r1 = sigma * rr1; r2 = sigma * rr2;
     } else if (gi >= 0) {
       // assembly in place (models.py:1064-1079, 828-856, 949-976): the off-diagonals are -q[e] (above); lane r
       // finishes row R0 + r: its diagonal and its load term loads_f + sum_{e to support s} q_e x_s

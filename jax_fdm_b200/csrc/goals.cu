@@ -5,8 +5,8 @@
 //   Mean* / RootMeanSquaredError .errors                                      errors.py:262-300, 340-400
 //   Loss.__call__             losses/loss.py:60-90
 //   NodePointGoal, NodeResidualForceGoal, NodeResidualVectorGoal, EdgeLengthGoal, EdgeForceGoal,
-//   EdgeLoadPathGoal, NetworkLoadPathGoal .prediction   (goals/node/point.py, node/residual.py,
-//   edge/length.py, edge/force.py, edge/loadpath.py, network/loadpath.py)
+//   EdgeLoadPathGoal, NetworkLoadPathGoal, Node{X,Y,Z}CoordinateGoal .prediction   (goals/node/point.py,
+//   node/residual.py, node/coordinates.py, edge/length.py, edge/force.py, edge/loadpath.py, network/loadpath.py)
 // and the reverse pass JAX derives from them.
 //
 // One CTA per design.  The goal "program" (shared by the batch) is a table of terms sorted by group
@@ -31,6 +31,9 @@ enum GoalKind : int {
   G_EDGE_FORCE,            // forces[e]              (1)
   G_EDGE_LOADPATH,         // |forces[e]| lengths[e] (1)
   G_NETWORK_LOADPATH,      // sum_e |forces[e] lengths[e]| (1)
+  G_NODE_X,                // xyz[i, 0], G_NODE_X + 1: xyz[i, 1], + 2: xyz[i, 2]   (1)
+  G_NODE_Y,
+  G_NODE_Z,
 };
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
 
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       case G_EDGE_LENGTH: p[0] = len[i]; return 1;
       case G_EDGE_FORCE: p[0] = frc[i]; return 1;
       case G_EDGE_LOADPATH: p[0] = fabs(frc[i]) * len[i]; return 1;
+      case G_NODE_X: case G_NODE_Y: case G_NODE_Z: p[0] = xyz[3 * i + (k - G_NODE_X)]; return 1;
       default: p[0] = loadpath; return 1;
     }
   };
@@ -159,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
           if (p[0] > 0.0)
             for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, d[0] * res[3 * i + c] / p[0]);
           break;
+        case G_NODE_X: case G_NODE_Y: case G_NODE_Z: atomicAdd(xb + 3 * i + (k - G_NODE_X), d[0]); break;
         case G_EDGE_LENGTH: atomicAdd(lb + i, d[0]); break;
         case G_EDGE_FORCE: atomicAdd(fb + i, d[0]); break;
         case G_EDGE_LOADPATH: {

@@ -11,8 +11,10 @@ it: a `Loss` compiles its goals into a table and evaluates them with one fused k
 import numpy as np
 
 __all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "NodeResidualForceGoal",
-           "NodeResidualVectorGoal", "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "NetworkLoadPathGoal",
-           "GoalState"]
+           "NodeResidualVectorGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
+           "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "NetworkLoadPathGoal",
+           "VertexGoal", "VertexPointGoal", "VertexResidualForceGoal", "VertexResidualVectorGoal",
+           "VertexXCoordinateGoal", "VertexYCoordinateGoal", "VertexZCoordinateGoal", "MeshLoadPathGoal", "GoalState"]
 
 from collections import namedtuple
 
@@ -123,3 +125,58 @@ class NetworkLoadPathGoal(NetworkGoal):
 
     def prediction(self, eq_state, structure):
         return (eq_state.lengths * eq_state.forces).abs().sum(dim=(-2, -1))
+
+
+class _NodeCoordinateGoal(NodeGoal):
+    axis = 0
+
+    def prediction(self, eq_state, structure):
+        return eq_state.xyz[..., self.index(structure), self.axis]
+
+
+class NodeXCoordinateGoal(_NodeCoordinateGoal):
+    """goals/node/coordinates.py:16-44."""
+    kind, axis = 7, 0
+
+
+class NodeYCoordinateGoal(_NodeCoordinateGoal):
+    """goals/node/coordinates.py:47-75."""
+    kind, axis = 8, 1
+
+
+class NodeZCoordinateGoal(_NodeCoordinateGoal):
+    """goals/node/coordinates.py:78-106."""
+    kind, axis = 9, 2
+
+
+# Mesh flavour (goals/vertex/*.py, goals/mesh/loadpath.py): the same predictions, keys are vertex keys.
+class VertexGoal(NodeGoal):
+    """goals/vertex/vertex.py."""
+
+
+class VertexPointGoal(VertexGoal, NodePointGoal):
+    """goals/vertex/point.py:7."""
+
+
+class VertexResidualForceGoal(VertexGoal, NodeResidualForceGoal):
+    """goals/vertex/residual.py:17."""
+
+
+class VertexResidualVectorGoal(VertexGoal, NodeResidualVectorGoal):
+    """goals/vertex/residual.py:23."""
+
+
+class VertexXCoordinateGoal(VertexGoal, NodeXCoordinateGoal):
+    """goals/vertex/coordinates.py:13."""
+
+
+class VertexYCoordinateGoal(VertexGoal, NodeYCoordinateGoal):
+    """goals/vertex/coordinates.py:19."""
+
+
+class VertexZCoordinateGoal(VertexGoal, NodeZCoordinateGoal):
+    """goals/vertex/coordinates.py:25."""
+
+
+class MeshLoadPathGoal(NetworkLoadPathGoal):
+    """goals/mesh/loadpath.py:7."""

@@ -26,6 +26,9 @@ PREDICTIONS = {
     "EdgeForceGoal": lambda st, i: st["forces"][i, 0],
     "EdgeLoadPathGoal": lambda st, i: np.abs(st["forces"][i, 0]) * st["lengths"][i, 0],
     "NetworkLoadPathGoal": lambda st, i: np.sum(np.abs(st["lengths"] * st["forces"])),
+    "NodeXCoordinateGoal": lambda st, i: st["xyz"][i, 0],      # goals/node/coordinates.py:44, 75, 106
+    "NodeYCoordinateGoal": lambda st, i: st["xyz"][i, 1],
+    "NodeZCoordinateGoal": lambda st, i: st["xyz"][i, 2],
 }
 
 ERRORS = {

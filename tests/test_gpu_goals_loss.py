@@ -45,6 +45,8 @@ def build_loss(prob, s, rng):
         ("MeanPredictionError", 0.05, [("EdgeLoadPathGoal", ekey(e), 0.0, 2.0) for e in pick_e[:5]]),
         ("LogMaxError", 2.0, [("EdgeLengthGoal", ekey(e), 0.8, 1.0) for e in pick_e[5:12]]),
         ("SquaredError", 1e-4, [("NetworkLoadPathGoal", -1, 50.0, 1.0), ("EdgeLengthGoal", ekey(pick_e[0]), 1.0, 3.0)]),
+        ("SquaredError", 0.3, [(f"Node{ax}CoordinateGoal", int(nodes[n]), prob.xyz0[n, c] - 0.2, 1.0 + c)
+                               for c, ax in enumerate("XYZ") for n in pick_n[:4]]),
     ]
     terms, oterms = [], []
     for ename, alpha, goals in spec:

@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
 //   2. forward substitution of the three right-hand sides with those two columns
 //   3. the factor records (rotated, see FROT) and the 8x8 diagonal block of the column group
 //   4. the panel goes back through shared memory as mma A/B fragments (k = 2 of 4 used) and the
-//      whole window gets W -= L_panel L_panel^T as 16 independent DMMAs             [FP64 tensor pipe]
+//      whole window gets W -= L_panel L_panel^T as independent DMMAs (16; 10 with four-column panels,
+//      which keep only the tiles on and below the diagonal)                          [FP64 tensor pipe]
 //   5. the two retired rows and columns are refilled with rows j+32, j+33 from the staged block
 // Out-of-band entries of the window stay exactly zero (an update needs both factors non-zero).
 // ===========================================================================================
@@ -450,10 +451,19 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         const bool rowlane = (g >> 2) == mh;               // holds panel row 8 tc0 + g of tile row tc0
         // ---- 1. panel columns -> lanes = rows
         __syncwarp();                                      // the previous panel's fragment reads of Pn are done
+        // (only the tiles on and below the diagonal of the symmetric window are kept: rows of tile rows above
+        //  tc0 come from the transposed tiles W[tc0][tr], held by the lanes that own the panel columns as ROWS)
         if (collane) {
 #pragma unroll
-          for (int tr = 0; tr < 4; ++tr)
+          for (int tr = tc0; tr < 4; ++tr)
             *reinterpret_cast<double2*>(Pn + (8 * tr + g) * 4 + 2 * (m & 1)) = make_double2(W[tr][tc0][0], W[tr][tc0][1]);
+        }
+        if (rowlane) {
+#pragma unroll
+          for (int tr = 0; tr < tc0; ++tr) {
+            Pn[(8 * tr + 2 * m) * 4 + (g & 3)] = W[tc0][tr][0];
+            Pn[(8 * tr + 2 * m + 1) * 4 + (g & 3)] = W[tc0][tr][1];
+          }
         }
         __syncwarp();
         const double2 va = *reinterpret_cast<const double2*>(Pn + 4 * lane);
@@ -530,7 +540,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
           const int R = 8 * tc0 + g;
           const double* fr = fs + R * kMS;
 #pragma unroll
-          for (int tc = 0; tc < 4; ++tc) {
+          for (int tc = 0; tc <= tc0; ++tc) {
             const double2 w = *reinterpret_cast<const double2*>(fr + 8 * tc + 2 * m);
             W[tc0][tc][0] = w.x;
             W[tc0][tc][1] = w.y;
@@ -545,7 +555,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         }
         if (collane) {
 #pragma unroll
-          for (int tr = 0; tr < 4; ++tr) {
+          for (int tr = tc0; tr < 4; ++tr) {
             if (!(tr == tc0 && rowlane)) {
               W[tr][tc0][0] = fs[(8 * tc0 + 2 * m) * kMS + 8 * tr + g];
               W[tr][tc0][1] = fs[(8 * tc0 + 2 * m + 1) * kMS + 8 * tr + g];
@@ -570,7 +580,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
 #pragma unroll
         for (int tr = 0; tr < 4; ++tr)
 #pragma unroll
-          for (int tc = 0; tc < 4; ++tc) dmma_f(W[tr][tc][0], W[tr][tc][1], nf[tr], af[tc]);
+          for (int tc = 0; tc <= tr; ++tc) dmma_f(W[tr][tc][0], W[tr][tc][1], nf[tr], af[tc]);
       }
     } else {
 #pragma unroll

@@ -260,7 +260,11 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
 // Out-of-band entries of the window stay exactly zero (an update needs both factors non-zero).
 // ===========================================================================================
 constexpr int kMS = 36;                                  // staged row: 32 column slots + 3 right-hand sides + pad
-constexpr int kMmaWarpSmem = 32 * kMS + 128;             // staged rows + panel exchange (32 rows x up to 4 columns)
+// panel exchange of the four-column kernel: entry (row, column c) at h * kPH + 2 * (row ^ h) + (c & 1), h = c >> 1:
+// a lane's 16-byte accesses are contiguous across the warp, and the 16-byte column writes, the 8-byte transposed
+// writes and the fragment reads are all free of bank conflicts
+constexpr int kPH = 72;
+constexpr int kMmaWarpSmem = 32 * kMS + 144;             // staged rows + panel exchange (32 rows x up to 4 columns)
 
 __device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -456,18 +460,19 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         if (collane) {
 #pragma unroll
           for (int tr = tc0; tr < 4; ++tr)
-            *reinterpret_cast<double2*>(Pn + (8 * tr + g) * 4 + 2 * (m & 1)) = make_double2(W[tr][tc0][0], W[tr][tc0][1]);
+            *reinterpret_cast<double2*>(Pn + (m & 1) * kPH + 2 * ((8 * tr + g) ^ (m & 1))) = make_double2(W[tr][tc0][0], W[tr][tc0][1]);
         }
         if (rowlane) {
 #pragma unroll
           for (int tr = 0; tr < tc0; ++tr) {
-            Pn[(8 * tr + 2 * m) * 4 + (g & 3)] = W[tc0][tr][0];
-            Pn[(8 * tr + 2 * m + 1) * 4 + (g & 3)] = W[tc0][tr][1];
+            const int h = (g >> 1) & 1;
+            Pn[h * kPH + 2 * ((8 * tr + 2 * m) ^ h) + (g & 1)] = W[tc0][tr][0];
+            Pn[h * kPH + 2 * ((8 * tr + 2 * m + 1) ^ h) + (g & 1)] = W[tc0][tr][1];
           }
         }
         __syncwarp();
-        const double2 va = *reinterpret_cast<const double2*>(Pn + 4 * lane);
-        const double2 vb = *reinterpret_cast<const double2*>(Pn + 4 * lane + 2);
+        const double2 va = *reinterpret_cast<const double2*>(Pn + 2 * lane);
+        const double2 vb = *reinterpret_cast<const double2*>(Pn + kPH + 2 * (lane ^ 1));
         const int d0 = (lane - s0) & 31;                 // row of this lane = j0 + s0 + d0
         // signed pivots (SIGNED): d_k = sign(piv_k), l_k = v_k / (d_k sqrt|piv_k|), update with d_k l_k l_k^T
         const double thr = SIGNED ? 1e-13 * dmax : 0.0;
@@ -566,15 +571,15 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         if (d0 == 0) { y[0] = fma(-x3, yd0, y[0]); y[1] = fma(-x3, yd1, y[1]); y[2] = fma(-x3, yd2, y[2]); }
         // ---- 5. W -= P P^T on the tensor pipe, P = panel with the incoming rows' entries
         const bool inc = d0 < 4;
-        *reinterpret_cast<double2*>(Pn + 4 * lane) = inc ? make_double2(0.0, 0.0) : make_double2(l0, l1);
-        *reinterpret_cast<double2*>(Pn + 4 * lane + 2) = inc ? make_double2(0.0, d0 == 0 ? x3 : 0.0) : make_double2(l2, l3);
+        *reinterpret_cast<double2*>(Pn + 2 * lane) = inc ? make_double2(0.0, 0.0) : make_double2(l0, l1);
+        *reinterpret_cast<double2*>(Pn + kPH + 2 * (lane ^ 1)) = inc ? make_double2(0.0, d0 == 0 ? x3 : 0.0) : make_double2(l2, l3);
         __syncwarp();
         double af[4], nf[4];
 #pragma unroll
         const double dm = SIGNED ? (m == 0 ? sg0 : m == 1 ? sg1 : m == 2 ? sg2 : sg3) : 1.0;   // this lane's k slice
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          af[t] = Pn[(8 * t + g) * 4 + m];
+          af[t] = Pn[(m >> 1) * kPH + 2 * ((8 * t + g) ^ (m >> 1)) + (m & 1)];
           nf[t] = SIGNED ? -dm * af[t] : -af[t];
         }
 #pragma unroll

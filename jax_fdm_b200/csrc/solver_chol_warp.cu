@@ -854,9 +854,11 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
           dmma(z0, z1, a0, b0);
           dmma(z0, z1, a1, b1);
         }
-        {                                                  // stored as D z (slot 3 keeps D): the backward sweep starts from it
+        if (!sgn) {
+          if (m < 2) *reinterpret_cast<double2*>(ysol + (int64_t)(j0 + cb + g) * 4 + 2 * m) = make_double2(z0, z1);
+        } else {                                           // stored as D z (slot 3 keeps D): the backward sweep starts from it
           double* zo = ysol + (int64_t)(j0 + cb + g) * 4;
-          const double dk = sgn ? zo[3] : 1.0;
+          const double dk = zo[3];
           if (m == 0) *reinterpret_cast<double2*>(zo) = make_double2(dk * z0, dk * z1);
           if (m == 1) zo[2] = dk * z0;
         }

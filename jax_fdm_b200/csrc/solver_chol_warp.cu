@@ -264,7 +264,7 @@ constexpr int kMS = 36;                                  // staged row: 32 colum
 // a lane's 16-byte accesses are contiguous across the warp, and the 16-byte column writes, the 8-byte transposed
 // writes and the fragment reads are all free of bank conflicts
 constexpr int kPH = 72;
-constexpr int kMmaWarpSmem = 32 * kMS + 144;             // staged rows + panel exchange (32 rows x up to 4 columns)
+constexpr int kMmaWarpSmem = 32 * kMS + 160;             // staged rows + panel exchange (40 rows x up to 4 columns)
 
 __device__ __forceinline__ void dmma_f(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -431,7 +431,12 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         const int R = 8 * tr + g, C = 8 * tc + 2 * m + e;
         W[tr][tc][e] = C <= R ? fs[R * kMS + C] : fs[C * kMS + R];
       }
-  y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34];
+  y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34];   // two-column panels
+  double Y[4][2];                                                                         // four-column panels
+#pragma unroll
+  for (int tc = 0; tc < 4; ++tc)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) Y[tc][e] = g < 3 ? fs[(8 * tc + 2 * m + e) * kMS + 32 + g] : 0.0;
 
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * 32;
@@ -462,6 +467,8 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
           for (int tr = tc0; tr < 4; ++tr)
             *reinterpret_cast<double2*>(Pn + (m & 1) * kPH + 2 * ((8 * tr + g) ^ (m & 1))) = make_double2(W[tr][tc0][0], W[tr][tc0][1]);
         }
+        if (collane && g < 3)                              // rows 32..34 of the exchange: the three right-hand sides
+          *reinterpret_cast<double2*>(Pn + (m & 1) * kPH + 2 * ((32 + g) ^ (m & 1))) = make_double2(Y[tc0][0], Y[tc0][1]);
         if (rowlane) {
 #pragma unroll
           for (int tr = 0; tr < tc0; ++tr) {
@@ -481,22 +488,25 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         const double inv0 = rsqrt_nr(SIGNED ? fabs(piv0) : piv0);
         const double l0 = va.x * (SIGNED ? sg0 * inv0 : inv0);
         const double m0s = SIGNED ? -sg0 * l0 : -l0;
-        double v1 = fma(m0s, __shfl_sync(kFull, l0, s0 + 1), va.y);
-        double v2 = fma(m0s, __shfl_sync(kFull, l0, s0 + 2), vb.x);
-        double v3 = fma(m0s, __shfl_sync(kFull, l0, s0 + 3), vb.y);
+        const double L10 = __shfl_sync(kFull, l0, s0 + 1), L20 = __shfl_sync(kFull, l0, s0 + 2), L30 = __shfl_sync(kFull, l0, s0 + 3);
+        double v1 = fma(m0s, L10, va.y);
+        double v2 = fma(m0s, L20, vb.x);
+        double v3 = fma(m0s, L30, vb.y);
         const double piv1 = __shfl_sync(kFull, v1, s0 + 1);
         const double sg1 = SIGNED && piv1 < 0.0 ? -1.0 : 1.0;
         const double inv1 = rsqrt_nr(SIGNED ? fabs(piv1) : piv1);
         const double l1 = v1 * (SIGNED ? sg1 * inv1 : inv1);
         const double m1s = SIGNED ? -sg1 * l1 : -l1;
-        v2 = fma(m1s, __shfl_sync(kFull, l1, s0 + 2), v2);
-        v3 = fma(m1s, __shfl_sync(kFull, l1, s0 + 3), v3);
+        const double L21 = __shfl_sync(kFull, l1, s0 + 2), L31 = __shfl_sync(kFull, l1, s0 + 3);
+        v2 = fma(m1s, L21, v2);
+        v3 = fma(m1s, L31, v3);
         const double piv2 = __shfl_sync(kFull, v2, s0 + 2);
         const double sg2 = SIGNED && piv2 < 0.0 ? -1.0 : 1.0;
         const double inv2 = rsqrt_nr(SIGNED ? fabs(piv2) : piv2);
         const double l2 = v2 * (SIGNED ? sg2 * inv2 : inv2);
         const double m2s = SIGNED ? -sg2 * l2 : -l2;
-        v3 = fma(m2s, __shfl_sync(kFull, l2, s0 + 3), v3);
+        const double L32 = __shfl_sync(kFull, l2, s0 + 3);
+        v3 = fma(m2s, L32, v3);
         const double piv3 = __shfl_sync(kFull, v3, s0 + 3);
         const double sg3 = SIGNED && piv3 < 0.0 ? -1.0 : 1.0;
         const double inv3 = rsqrt_nr(SIGNED ? fabs(piv3) : piv3);
@@ -507,24 +517,23 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
           bad |= !(piv0 > 0.0) | !(piv1 > 0.0) | !(piv2 > 0.0) | !(piv3 > 0.0);
         }
         const double x3 = fs[s0 * kMS + s0 + 3] * (SIGNED ? sg3 * inv3 : inv3);  // L(j+32, j+3), see above
-        // ---- 2. right-hand sides; lane s0 + k keeps the solved entries of column j + k
-        double yd0, yd1, yd2;
+        // ---- 2. right-hand sides.  They are three more ROWS of the window (tile row 4: lane (g, m) holds rhs g,
+        //         columns 8 tc + 2m, + 1 of Y[tc]; g < 3): forward substitution is the same elimination.  Lane
+        //         (g, m) runs the four pivot columns on rhs g (the entries of the pivot block are the shuffled
+        //         l's above), keeps w_m as its mma A fragment and stores it as the solved entry of column j + m.
+        double ay;
         {
-          const double linv[4] = {inv0, inv1, inv2, inv3}, lcol[4] = {l0, l1, l2, l3};
-          const double lsgn[4] = {sg0, sg1, sg2, sg3};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const double t0 = y[0] * linv[k], t1 = y[1] * linv[k], t2 = y[2] * linv[k];
-            if (lane == s0 + k) {
-              const double dk = SIGNED ? lsgn[k] : 1.0;    // stored as D w: the backward substitution starts from it
-              yb[(s0 + k) * 4] = dk * t0; yb[(s0 + k) * 4 + 1] = dk * t1; yb[(s0 + k) * 4 + 2] = dk * t2;
-              if (SIGNED) yb[(s0 + k) * 4 + 3] = dk;
-            }
-            yd0 = __shfl_sync(kFull, t0, s0 + k);
-            yd1 = __shfl_sync(kFull, t1, s0 + k);
-            yd2 = __shfl_sync(kFull, t2, s0 + k);
-            y[0] = fma(-lcol[k], yd0, y[0]); y[1] = fma(-lcol[k], yd1, y[1]); y[2] = fma(-lcol[k], yd2, y[2]);
-          }
+          const double2 ya = *reinterpret_cast<const double2*>(Pn + 2 * (32 + g));
+          const double2 yc = *reinterpret_cast<const double2*>(Pn + kPH + 2 * ((32 + g) ^ 1));
+          const double w0 = ya.x * inv0;
+          const double w1 = fma(-L10, w0, ya.y) * inv1;
+          const double w2 = fma(-L21, w1, fma(-L20, w0, yc.x)) * inv2;
+          const double w3 = fma(-L32, w2, fma(-L31, w1, fma(-L30, w0, yc.y))) * inv3;
+          ay = m == 0 ? w0 : m == 1 ? w1 : m == 2 ? w2 : w3;
+          const double dk = SIGNED ? (m == 0 ? sg0 : m == 1 ? sg1 : m == 2 ? sg2 : sg3) : 1.0;
+          if (g < 3) yb[(s0 + m) * 4 + g] = dk * ay;      // stored as D w: the backward substitution starts from it
+          if (SIGNED && g == 3) yb[(s0 + m) * 4 + 3] = dk;
+          if (g >= 3) ay = 0.0;
         }
         // ---- 3. factor records (the diagonal slot holds 1/L(j,j), see chol_invdiag_kernel); rows above the
         //         diagonal of the 4x4 pivot block are zero, row j+32 of column j+3 is x3
@@ -567,15 +576,16 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
             }
           }
         }
-        if (d0 < 4) { y[0] = fs[lane * kMS + 32]; y[1] = fs[lane * kMS + 33]; y[2] = fs[lane * kMS + 34]; }
-        if (d0 == 0) { y[0] = fma(-x3, yd0, y[0]); y[1] = fma(-x3, yd1, y[1]); y[2] = fma(-x3, yd2, y[2]); }
+        if (collane && g < 3) {                            // right-hand sides of the incoming rows (the update below
+          Y[tc0][0] = fs[(8 * tc0 + 2 * m) * kMS + 32 + g];      // carries x3 * w_3 into row j+32's)
+          Y[tc0][1] = fs[(8 * tc0 + 2 * m + 1) * kMS + 32 + g];
+        }
         // ---- 5. W -= P P^T on the tensor pipe, P = panel with the incoming rows' entries
         const bool inc = d0 < 4;
         *reinterpret_cast<double2*>(Pn + 2 * lane) = inc ? make_double2(0.0, 0.0) : make_double2(l0, l1);
         *reinterpret_cast<double2*>(Pn + kPH + 2 * (lane ^ 1)) = inc ? make_double2(0.0, d0 == 0 ? x3 : 0.0) : make_double2(l2, l3);
         __syncwarp();
         double af[4], nf[4];
-#pragma unroll
         const double dm = SIGNED ? (m == 0 ? sg0 : m == 1 ? sg1 : m == 2 ? sg2 : sg3) : 1.0;   // this lane's k slice
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
@@ -586,6 +596,9 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         for (int tr = 0; tr < 4; ++tr)
 #pragma unroll
           for (int tc = 0; tc <= tr; ++tc) dmma_f(W[tr][tc][0], W[tr][tc][1], nf[tr], af[tc]);
+        const double nay = -ay;
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc) dmma_f(Y[tc][0], Y[tc][1], nay, af[tc]);
       }
     } else {
 #pragma unroll

@@ -43,6 +43,7 @@ CONFIG5_BATCH = 4096          # BASELINE config 5's fixed global batch (reported
 GLOBAL_BATCH = PER_GPU_BATCH  # the CPU arm times a bounded sample of one GPU's share
 CABLENET_NX = 200
 E2E_CHUNKS = int(os.environ.get("FDM_BENCH_E2E_CHUNKS", "16"))
+DEV_CHUNKS = int(os.environ.get("FDM_BENCH_DEV_CHUNKS", "2"))   # slices of the device-resident step (own streams)
 # dram__bytes_read.sum + dram__bytes_write.sum of one chol_factor_mma_kernel launch (B = 4096), from
 # profiles/r01k_chol_final_ncu.txt (0.325 GB read + 0.960 GB written)
 NCU_TRAFFIC_CHOL_FWD = 1.295e9   # dram read+write of chol_factor_mma_kernel<0,4>, ncu --set full (profiles/r01n_chol_panel4_ncu.txt)
@@ -301,6 +302,10 @@ def run_ours(args):
     pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
     e2e_pipe = ChunkedForwardAdjoint(s, B, chunks=E2E_CHUNKS, solver="cholesky", device=local)
     e2e_pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+    # the timed device-resident step: the batch in DEV_CHUNKS slices on their own streams (fork/join on
+    # dev_pipe.stream), so one slice's bandwidth-bound substitutions overlap another's factorisation
+    dev_pipe = ChunkedForwardAdjoint(s, B, chunks=DEV_CHUNKS, solver="cholesky", device=local)
+    dev_pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def flush():
@@ -314,9 +319,13 @@ def run_ours(args):
             with torch.cuda.stream(p.stream):
                 total_loss(p.loss, out=total)             # local sum + one 8-byte NCCL all-reduce
 
+    def flush_dev():
+        with torch.cuda.stream(dev_pipe.stream):
+            flush_buf.fill_(1)
+
     def step_dev():
-        pipe.step()
-        reduce_loss(pipe)
+        dev_pipe.step()
+        reduce_loss(dev_pipe)
 
     def step_e2e():
         e2e_pipe()
@@ -339,7 +348,7 @@ def run_ours(args):
         sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    t_dev = timed_steps(step_dev, pipe.stream, steps, flush)
+    t_dev = timed_steps(step_dev, dev_pipe.stream, steps, flush_dev)
     barrier()
     wall = time.perf_counter() - wall0
     # end to end: pinned host q in, loss + q_bar out, every step
@@ -374,14 +383,15 @@ def run_ours(args):
     sum_dev = reduce_max(sum(t_dev))
     sum_e2e = reduce_max(sum(t_e2e))
     t_pipelined = reduce_max(t_pipelined)
-    status_ok = bool((pipe.info_f[:, 0] == 0).all().item() and (pipe.info_a[:, 0] == 0).all().item())
+    status_ok = all(bool((p_.info_f[:, 0] == 0).all().item() and (p_.info_a[:, 0] == 0).all().item())
+                    for p_ in dev_pipe.parts)
 
     # diagnostic at N > 1: the same steps without the loss all-reduce (what the collective + the lock-step
     # it imposes on the ranks cost), and the spread of the per-rank times
     scaling_diag = None
     if world > 1:
         barrier()
-        t_local = timed_steps(pipe.step, pipe.stream, steps, flush)
+        t_local = timed_steps(dev_pipe.step, dev_pipe.stream, steps, flush_dev)
         barrier()
         mine = torch.tensor([sum(t_dev) / steps, sum(t_local) / steps], dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
@@ -458,6 +468,8 @@ def run_ours(args):
                                "BASELINE config 5 at N=1",
                    "per_gpu_batch": B, "global_batch": B * world, "solver": "batched band Cholesky, one warp per design",
                    "l2": "flushed between timed steps (256 MiB write, outside the events)",
+                   "device_step": f"{DEV_CHUNKS} slices of the batch on their own streams, forked from and joined to the "
+                                  "timed stream (CUDA events on it bracket the whole step)",
                    "parallelism": f"designs sharded x{world}, no data-path collective"
                                   + (", 8-byte loss all-reduce (NCCL) per step" if world > 1 else "")},
         "clocks": clocks,
@@ -470,7 +482,7 @@ def run_ours(args):
                               "how": "the same K steps enqueued back to back and synchronised once: step k+1's copy-in "
                                      "overlaps step k's kernels and copy-out (independent batches; an optimiser loop "
                                      "that needs step k's gradient before step k+1 gets the synchronous number)"}},
-        "gpu_launches": pipe.launches_per_step * steps,
+        "gpu_launches": dev_pipe.launches_per_step * steps,
         "roofline": {"kernel": dom["kernel"].strip(), "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm,
                      "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm, "traffic": NCU_TRAFFIC_CHOL_FWD,
                      "peak_source": hbm_src, "kernel_ms": dom["ms"],

@@ -169,6 +169,21 @@ class ChunkedForwardAdjoint:
         self.offsets = [sum(sizes[:i]) for i in range(chunks)]
         self.parts = [ForwardAdjoint(structure, batch=b, **kw) for b in sizes]
         self.B = int(batch)
+        # one loss vector for the whole batch; every slice writes its part (set before the graphs are captured)
+        self.loss = torch.empty((self.B,), dtype=F64, device=self.parts[0].dev)
+        for off, part in zip(self.offsets, self.parts):
+            part.loss = self.loss[off:off + part.B]
+        self.stream = torch.cuda.Stream(device=self.parts[0].dev)
+
+    def step(self):
+        """One forward+adjoint of the whole batch on device-resident inputs, ordered on `self.stream`: the slices
+        run on their own streams between a fork and a join, so the bandwidth-bound substitution kernels of one
+        slice overlap the factorisation of another.  Asynchronous; events recorded on self.stream bracket it."""
+        for part in self.parts:
+            part.stream.wait_stream(self.stream)
+            part.step()
+        for part in self.parts:
+            self.stream.wait_stream(part.stream)
 
     def set_inputs(self, q, xyz_fixed, loads, x0):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(self.B, -1)
@@ -188,10 +203,6 @@ class ChunkedForwardAdjoint:
     def synchronize(self):
         for part in self.parts:
             part.stream.synchronize()
-
-    @property
-    def loss(self):
-        return torch.cat([p.loss for p in self.parts])
 
     @property
     def h2d_bytes(self):

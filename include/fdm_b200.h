@@ -140,7 +140,8 @@ typedef struct fdm_solve_opts {
   int32_t reuse_factor; /* Cholesky: nonzero -> d_ws already holds the factor of this K (adjoint
                            solve after the forward solve, tmax>1 iterations): skip refactoring */
   int32_t stages;       /* batched Cholesky, measurement only: 0 = the whole solve; otherwise a mask of the
-                           launches to issue (1 factorisation, 2 diagonal-block inversion, 4 substitution),
+                           launches to issue (1 factorisation [+ its signed second pass], 2 diagonal-block inversion
+                           [separate launch at half bandwidth 31 only], 4 substitution),
                            so that a benchmark can time each kernel of one solve on its own */
 } fdm_solve_opts;
 

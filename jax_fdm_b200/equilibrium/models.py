@@ -126,7 +126,7 @@ class _FusedFreePositions(torch.autograd.Function):
         if x is None:
             opts = {k: v for k, v in opts.items() if k != "fused_assembly"}
             K, rhs = ops.assemble(structure, q, xyz_fixed, loads)
-            x = ops.solve(structure, K, rhs, workspace=ws, **opts)
+            x = ops.solve(structure, K, rhs, workspace=ws, nan_on_failure=True, **opts)
         else:
             K = torch.empty(0, dtype=q.dtype, device=q.device)
             opts = {k: v for k, v in opts.items() if k != "fused_assembly"}

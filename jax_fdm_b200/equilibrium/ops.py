@@ -95,9 +95,11 @@ class Workspace:
 
 
 def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_factor=False,
-          workspace=None, return_info=False, check_every=0, stages=0):
+          workspace=None, return_info=False, check_every=0, stages=0, nan_on_failure=False):
     """K2: x = K^{-1} rhs (sparse.py:207-230 / 296).  Kdata (B?,nnz), rhs (B?,Nf,3).
-    `stages` (profiling): bit mask of the band Cholesky launches to run, 0 = all (fdm_b200.h)."""
+    `stages` (profiling): bit mask of the band Cholesky launches to run, 0 = all (fdm_b200.h).
+    `nan_on_failure`: designs whose solve status is not OK come back as NaN (what the reference's
+    solvers hand to the optimiser's NaN check, optimizer.py:372-380) -- a device-side select, no sync."""
     s = structure
     Nf, nnz = s.num_free, s.nnz
     rhs = _chk(rhs, "rhs", (Nf, 3))
@@ -123,6 +125,9 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)), int(stages))
     L.check(L.lib().fdm_solve(s.plan, _ptr(Kdata), _ptr(rhs), _ptr(x), _ptr(info), _ptr(buf),
                               buf.numel(), B, C.byref(opts), _stream()))
+    if nan_on_failure:
+        failed = (info[:, 0] != 0).view((B, 1, 1) if x.dim() == 3 else (1, 1))
+        x = torch.where(failed, torch.full_like(x, float("nan")), x)
     return (x, info) if return_info else x
 
 

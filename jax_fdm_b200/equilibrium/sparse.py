@@ -111,7 +111,7 @@ def _outer_on_pattern(s, a, b):
 class _SparseSolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data, b, structure, opts):
-        x = ops.solve(structure, data, b, **opts)
+        x = ops.solve(structure, data, b, nan_on_failure=True, **opts)
         ctx.structure, ctx.opts = structure, opts
         ctx.save_for_backward(x, data, b)               # residuals (xk, A, b), sparse.py:264
         return x

@@ -117,6 +117,11 @@ def test_indefinite_design_is_flagged_at_half_bandwidth_30_and_31():
     _, info = eq.ops.solve(s, K, rhs, solver="cholesky", return_info=True)
     st = info[:, 0].cpu().numpy()
     assert st[0] == 0 and st[2] == 0 and st[1] == 2        # FDM_STATUS_INDEFINITE for the mixed-sign design only
+    # the model level hands NaN to the caller for that design (the reference's optimisers check for it)
+    model = eq.EquilibriumModelSparse(tmax=1, solver="cholesky")
+    state = model(eq.EquilibriumParametersState(T(qb), T(xs), eq.LoadState(T(loads), 0.0, 0.0)), s)
+    finite = torch.isfinite(state.xyz).flatten(1).all(dim=1).cpu().numpy()
+    assert finite[0] and finite[2] and not finite[1]
 
 
 def test_band_too_wide_is_refused_and_auto_uses_pcg():

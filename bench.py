@@ -210,10 +210,9 @@ def timed_steps(fn, stream, steps, flush, dist=None):
     import torch
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for s0, s1 in ev:
-        flush()
-        stream.synchronize()
-        s0.record(stream)
-        fn()
+        flush()                 # on `stream`: the start event below is ordered after it, no host sync needed
+        s0.record(stream)       # (a host sync per step would add the ranks' host-side start skew to every
+        fn()                    #  step that ends in a collective)
         s1.record(stream)
     stream.synchronize()
     return [a.elapsed_time(b) for a, b in ev]

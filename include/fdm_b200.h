@@ -48,7 +48,7 @@ enum {
   FDM_STATUS_OK = 0,
   FDM_STATUS_NOT_CONVERGED = 1,
   FDM_STATUS_INDEFINITE = 2,   /* mixed-sign diagonal / pivot: K neither SPD nor -SPD (the batched band
-                                  Cholesky solves such designs itself when hbw <= 29: FDM_INFO_SIGN 0) */
+                                  Cholesky solves such designs itself when hbw <= 30: FDM_INFO_SIGN 0) */
   FDM_STATUS_BREAKDOWN = 3     /* non-finite scalar met in the iteration / vanishing pivot */
 };
 

@@ -198,6 +198,9 @@ int fdm_assemble(const fdm_plan* p, const double* q, const double* xs, const dou
 
 static int pick_solver(const fdm_plan* p, int64_t batch, int32_t want) {
   if (want != FDM_SOLVER_AUTO) return want;
+  // narrow bands (one warp per design): direct, deterministic, and the only solver here that also handles
+  // mixed-sign q -- for one design as well as for a batch
+  if (chol_warp_supported(p)) return FDM_SOLVER_CHOLESKY_BATCHED;
   if (chol_supported(p) && (batch > 1 || !pcg2_supported(p))) return FDM_SOLVER_CHOLESKY_BATCHED;
   if (pcg2_supported(p)) return FDM_SOLVER_PCG_PERSISTENT;
   return FDM_SOLVER_PCG;

@@ -305,7 +305,6 @@ __device__ __forceinline__ void invdiag_solve_store(double* fb, int lane, const 
 // A pivot below 1e-13 of the largest diagonal entry seen is reported as a breakdown (meta[1] = 2).
 template <bool FROM_Q, int PW, bool SIGNED>
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
-  static_assert(!SIGNED || PW == 4, "signed pivots are implemented for four-column panels");
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // designs per CTA = warps per CTA (host's choice)
@@ -615,16 +614,23 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
       __syncwarp();
       const double2 v = *reinterpret_cast<const double2*>(Pn + 2 * lane);
       const int d0 = (lane - s0) & 31;                 // row of this lane = j0 + s0 + d0
+      const double thr = SIGNED ? 1e-13 * dmax : 0.0;
       const double piv0 = __shfl_sync(kFull, v.x, s0);
-      const double inv0 = rsqrt_nr(piv0);
-      const double l0 = v.x * inv0;
+      const double sg0 = SIGNED && piv0 < 0.0 ? -1.0 : 1.0;
+      const double inv0 = rsqrt_nr(SIGNED ? fabs(piv0) : piv0);
+      const double l0 = v.x * (SIGNED ? sg0 * inv0 : inv0);
       const double c10 = __shfl_sync(kFull, l0, s0 + 1);
-      const double t1 = fma(-l0, c10, v.y);
+      const double t1 = fma(SIGNED ? -sg0 * l0 : -l0, c10, v.y);
       const double piv1 = __shfl_sync(kFull, t1, s0 + 1);
-      const double inv1 = rsqrt_nr(piv1);
-      const double l1 = t1 * inv1;
-      bad |= !(piv0 > 0.0) | !(piv1 > 0.0);
-      // ---- 2. right-hand sides
+      const double sg1 = SIGNED && piv1 < 0.0 ? -1.0 : 1.0;
+      const double inv1 = rsqrt_nr(SIGNED ? fabs(piv1) : piv1);
+      const double l1 = t1 * (SIGNED ? sg1 * inv1 : inv1);
+      if (SIGNED) {
+        if (!(fabs(piv0) > thr) | !(fabs(piv1) > thr)) bad = 2;
+      } else {
+        bad |= !(piv0 > 0.0) | !(piv1 > 0.0);
+      }
+      // ---- 2. right-hand sides (SIGNED: stored as D w, the sign in the spare fourth slot)
       const double ya0 = __shfl_sync(kFull, y[0] * inv0, s0);
       const double ya1 = __shfl_sync(kFull, y[1] * inv0, s0);
       const double ya2 = __shfl_sync(kFull, y[2] * inv0, s0);
@@ -633,8 +639,14 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
       const double yc1 = __shfl_sync(kFull, y[1] * inv1, s0 + 1);
       const double yc2 = __shfl_sync(kFull, y[2] * inv1, s0 + 1);
       y[0] = fma(-l1, yc0, y[0]); y[1] = fma(-l1, yc1, y[1]); y[2] = fma(-l1, yc2, y[2]);
-      if (lane == s0) { yb[s0 * 4] = ya0; yb[s0 * 4 + 1] = ya1; yb[s0 * 4 + 2] = ya2; }
-      if (lane == s0 + 1) { yb[s0 * 4 + 4] = yc0; yb[s0 * 4 + 5] = yc1; yb[s0 * 4 + 6] = yc2; }
+      if (lane == s0) {
+        yb[s0 * 4] = sg0 * ya0; yb[s0 * 4 + 1] = sg0 * ya1; yb[s0 * 4 + 2] = sg0 * ya2;
+        if (SIGNED) yb[s0 * 4 + 3] = sg0;
+      }
+      if (lane == s0 + 1) {
+        yb[s0 * 4 + 4] = sg1 * yc0; yb[s0 * 4 + 5] = sg1 * yc1; yb[s0 * 4 + 6] = sg1 * yc2;
+        if (SIGNED) yb[s0 * 4 + 7] = sg1;
+      }
       // ---- 3. factor records and the diagonal block of the column group
       // (the diagonal slot holds 1/L(j,j); chol_invdiag_kernel turns the 8x8 diagonal blocks into
       //  their inverses afterwards)
@@ -647,7 +659,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         af[t] = m < 2 ? Pn[(8 * t + g) * 2 + m] : 0.0;
-        nf[t] = -af[t];
+        nf[t] = SIGNED ? -(m == 0 ? sg0 : sg1) * af[t] : -af[t];
       }
 #pragma unroll
       for (int tr = 0; tr < 4; ++tr)
@@ -1025,9 +1037,10 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, false> : chol_factor_mma_kernel<true, 2, false>;
   FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
-  if (mma_panel4(p)) {   // designs with a non-positive pivot (mixed-sign q) are factored again with signed pivots
-    FDM_CUDA(cudaFuncSetAttribute(chol_factor_mma_kernel<true, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    chol_factor_mma_kernel<true, 4, true><<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+  {   // designs with a non-positive pivot (mixed-sign q) are factored again with signed pivots
+    void (*skern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, true> : chol_factor_mma_kernel<true, 2, true>;
+    FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    skern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
   }
   int rc = launch_backward(p, A, batch, st);
   if (rc != FDM_OK) return rc;
@@ -1083,9 +1096,10 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
-    if (mma && mma_panel4(p)) {   // designs with a non-positive pivot (mixed-sign q): again, with signed pivots
-      FDM_CUDA(cudaFuncSetAttribute(chol_factor_mma_kernel<false, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      chol_factor_mma_kernel<false, 4, true><<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    if (mma) {   // designs with a non-positive pivot (mixed-sign q): again, with signed pivots
+      void (*skern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, true> : chol_factor_mma_kernel<false, 2, true>;
+      FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      skern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
     }
   }
   if (!o.reuse_factor && (stages & 2) && !mma) {

@@ -72,7 +72,7 @@ class ForwardAdjoint:
         # mirrors pick_solver() in csrc/capi.cu: batches go to the band Cholesky when the plan supports it
         has_chol = int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_CHOLESKY_BATCHED)) > 0
         has_pcg2 = int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_PCG_PERSISTENT)) > 0
-        return has_chol and (self.B > 1 or not has_pcg2)
+        return has_chol and (self.B > 1 or not has_pcg2 or self.s.half_bandwidth <= 31)
 
     def _auto_is_multikernel(self):
         return not self._auto_is_cholesky() and int(self.lib.fdm_workspace_bytes(self.s.plan, self.B, L.SOLVER_PCG_PERSISTENT)) == 0

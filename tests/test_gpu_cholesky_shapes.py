@@ -68,10 +68,10 @@ def test_band_cholesky_forward_and_stored_factor(nx, ny, batch, sign):
         assert np.abs(lam[b].cpu().numpy() - lo).max() <= 1e-10 * np.abs(lo).max()
 
 
-@pytest.mark.parametrize("nx,ny,batch", [(9, 6, 3), (30, 30, 40), (12, 25, 5)])
+@pytest.mark.parametrize("nx,ny,batch", [(9, 6, 3), (30, 30, 40), (12, 25, 5), (31, 40, 6)])
 def test_mixed_sign_designs_are_solved_with_signed_pivots(nx, ny, batch):
     """Mixed-sign q makes K indefinite; the reference's LU (sparse.py:147-149) still solves it.  The plain
-    Cholesky flags those designs and a second pass factors them as L D L^T (hbw <= 29): status 0, sign 0,
+    Cholesky flags those designs and a second pass factors them as L D L^T (hbw <= 30): status 0, sign 0,
     positions and the adjoint solve with the stored factor against the oracle's SuperLU; the definite designs
     of the same batch are untouched (sign +-1)."""
     import jax_fdm_b200.equilibrium as eq
@@ -79,7 +79,7 @@ def test_mixed_sign_designs_are_solved_with_signed_pivots(nx, ny, batch):
     m, supports, q, xs, loads = strip_problem(nx, ny, 1.0, seed=3 + nx)
     s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
     so = oracle.build_structure(m.nodes, m.edges, supports)
-    assert s.half_bandwidth <= 29
+    assert s.half_bandwidth <= 30
     rng = np.random.default_rng(nx)
     qb = q[None, :] * rng.uniform(0.8, 1.25, size=(batch, q.size))
     mixed = np.arange(batch) % 2 == 1
@@ -106,11 +106,11 @@ def test_mixed_sign_designs_are_solved_with_signed_pivots(nx, ny, batch):
     assert torch.equal(x2, x) and torch.equal(info2[:, :4].cpu(), torch.as_tensor(info[:, :4]))
 
 
-def test_indefinite_design_is_flagged_at_half_bandwidth_30_and_31():
-    """The signed second pass exists for the four-column kernel (hbw <= 29); wider bands keep the flag."""
+def test_indefinite_design_is_flagged_at_half_bandwidth_31():
+    """The signed second pass exists for the tensor-core kernels (hbw <= 30); the rank-1 kernel keeps the flag."""
     import jax_fdm_b200.equilibrium as eq
 
-    m, supports, q, xs, loads = strip_problem(31, 40, 1.0, seed=3)
+    m, supports, q, xs, loads = strip_problem(32, 34, 1.0, seed=3)
     s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
     qb = np.stack([q, q * np.where(np.arange(q.size) % 2, -1.0, 1.0), q])
     K, rhs = eq.ops.assemble(s, T(qb), T(xs), T(loads))

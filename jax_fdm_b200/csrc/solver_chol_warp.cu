@@ -481,32 +481,45 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
         const double2 vb = *reinterpret_cast<const double2*>(Pn + kPH + 2 * (lane ^ 1));
         const int d0 = (lane - s0) & 31;                 // row of this lane = j0 + s0 + d0
         // signed pivots (SIGNED): d_k = sign(piv_k), l_k = v_k / (d_k sqrt|piv_k|), update with d_k l_k l_k^T
+        // The 4x4 pivot block is read by every lane (broadcast reads of rows s0..s0+3 of the exchange) and
+        // factored redundantly: no shuffle on the pivot chain; each operation is the one the lane that owns the
+        // row performs below, so the pivots and the block's entries of L are the same bits in every lane.
         const double thr = SIGNED ? 1e-13 * dmax : 0.0;
-        const double piv0 = __shfl_sync(kFull, va.x, s0);
+        const double* B0 = Pn + 2 * s0;                          // columns 0, 1 of rows s0 + k at B0[2k], B0[2k+1]
+        const double* B1 = Pn + kPH;                             // columns 2, 3 of row r at B1[2 (r ^ 1)], + 1
+        const double piv0 = B0[0];
         const double sg0 = SIGNED && piv0 < 0.0 ? -1.0 : 1.0;
         const double inv0 = rsqrt_nr(SIGNED ? fabs(piv0) : piv0);
-        const double l0 = va.x * (SIGNED ? sg0 * inv0 : inv0);
+        const double i0s = SIGNED ? sg0 * inv0 : inv0;
+        const double L10 = B0[2] * i0s, L20 = B0[4] * i0s, L30 = B0[6] * i0s;
+        const double l0 = va.x * i0s;
         const double m0s = SIGNED ? -sg0 * l0 : -l0;
-        const double L10 = __shfl_sync(kFull, l0, s0 + 1), L20 = __shfl_sync(kFull, l0, s0 + 2), L30 = __shfl_sync(kFull, l0, s0 + 3);
+        const double n10 = SIGNED ? -sg0 * L10 : -L10, n20 = SIGNED ? -sg0 * L20 : -L20, n30 = SIGNED ? -sg0 * L30 : -L30;
         double v1 = fma(m0s, L10, va.y);
         double v2 = fma(m0s, L20, vb.x);
         double v3 = fma(m0s, L30, vb.y);
-        const double piv1 = __shfl_sync(kFull, v1, s0 + 1);
+        const double piv1 = fma(n10, L10, B0[3]);
         const double sg1 = SIGNED && piv1 < 0.0 ? -1.0 : 1.0;
         const double inv1 = rsqrt_nr(SIGNED ? fabs(piv1) : piv1);
-        const double l1 = v1 * (SIGNED ? sg1 * inv1 : inv1);
+        const double i1s = SIGNED ? sg1 * inv1 : inv1;
+        const double L21 = fma(n20, L10, B0[5]) * i1s, L31 = fma(n30, L10, B0[7]) * i1s;
+        const double l1 = v1 * i1s;
         const double m1s = SIGNED ? -sg1 * l1 : -l1;
-        const double L21 = __shfl_sync(kFull, l1, s0 + 2), L31 = __shfl_sync(kFull, l1, s0 + 3);
+        const double n21 = SIGNED ? -sg1 * L21 : -L21, n31 = SIGNED ? -sg1 * L31 : -L31;
         v2 = fma(m1s, L21, v2);
         v3 = fma(m1s, L31, v3);
-        const double piv2 = __shfl_sync(kFull, v2, s0 + 2);
+        const double2 c2 = *reinterpret_cast<const double2*>(B1 + 2 * ((s0 + 2) ^ 1));   // A(s0+2, s0+2), A(s0+2, s0+3)
+        const double2 c3 = *reinterpret_cast<const double2*>(B1 + 2 * ((s0 + 3) ^ 1));   // A(s0+3, s0+2), A(s0+3, s0+3)
+        const double piv2 = fma(n21, L21, fma(n20, L20, c2.x));
         const double sg2 = SIGNED && piv2 < 0.0 ? -1.0 : 1.0;
         const double inv2 = rsqrt_nr(SIGNED ? fabs(piv2) : piv2);
-        const double l2 = v2 * (SIGNED ? sg2 * inv2 : inv2);
+        const double i2s = SIGNED ? sg2 * inv2 : inv2;
+        const double L32 = fma(n31, L21, fma(n30, L20, c3.x)) * i2s;
+        const double l2 = v2 * i2s;
         const double m2s = SIGNED ? -sg2 * l2 : -l2;
-        const double L32 = __shfl_sync(kFull, l2, s0 + 3);
+        const double n32 = SIGNED ? -sg2 * L32 : -L32;
         v3 = fma(m2s, L32, v3);
-        const double piv3 = __shfl_sync(kFull, v3, s0 + 3);
+        const double piv3 = fma(n32, L32, fma(n31, L31, fma(n30, L30, c3.y)));
         const double sg3 = SIGNED && piv3 < 0.0 ? -1.0 : 1.0;
         const double inv3 = rsqrt_nr(SIGNED ? fabs(piv3) : piv3);
         const double l3 = v3 * (SIGNED ? sg3 * inv3 : inv3);

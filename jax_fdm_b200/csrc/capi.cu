@@ -23,7 +23,7 @@ void free_device(fdm_plan* p) {
   DeviceArrays& d = p->d;
   void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
-                  d.band_iperm, d.band_kidx, d.band_rowkidx, d.band_rowedge, d.diags_ptr, d.diags_idx, d.sup_mask,
+                  d.band_iperm, d.band_kidx, d.band_rowkidx, d.diags_ptr, d.diags_idx, d.sup_mask,
                   d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent};
   for (void* q : ptrs)
     if (q) cudaFree(q);
@@ -117,7 +117,6 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->band_iperm, &q->d.band_iperm); },
         [](fdm_plan* q) { return upload(q->band_kidx, &q->d.band_kidx); },
         [](fdm_plan* q) { return upload(q->band_rowkidx, &q->d.band_rowkidx); },
-        [](fdm_plan* q) { return upload(q->band_rowedge, &q->d.band_rowedge); },
         [](fdm_plan* q) { return upload(q->band_stage_ptr, &q->d.band_stage_ptr); },
         [](fdm_plan* q) { return upload(q->band_stage_kent, &q->d.band_stage_kent); },
         [](fdm_plan* q) { return upload(q->band_stage_eent, &q->d.band_stage_eent); },

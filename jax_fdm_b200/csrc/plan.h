@@ -28,7 +28,6 @@ struct DeviceArrays {
   int32_t* band_iperm = nullptr;   // (Nf) band position -> free index
   int32_t* band_kidx = nullptr;    // (Nf, hbw+1) column-oriented: [j*(hbw+1)+d] = position in K.data of A(j+d, j), -1 = zero
   int32_t* band_rowkidx = nullptr; // ((ceil(Nf/32)+1)*32, 32) row-oriented: [R*32+t] = position of A(R, R-t), -1 zero, -2 one
-  int32_t* band_rowedge = nullptr; // same shape: edge id of the entry, -3 diagonal, -1 zero, -2 one
   // the same two tables without their zeros: per 32-row block, groups of 32 (position, index) pairs
   int32_t* band_stage_ptr = nullptr;   // (ceil(Nf/32)+2) first group of every block
   int32_t* band_stage_kent = nullptr;  // (groups*32, 2): r*32 + slot, position in K.data | -2 one | -4 padding
@@ -53,7 +52,8 @@ struct fdm_plan {
   std::vector<uint32_t> sup_mask;
 
   // band ordering
-  std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx, band_rowedge;
+  std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx;
+  std::vector<int32_t> band_rowedge;   // host only: band_rowkidx in terms of edge ids (-3 diagonal), source of band_stage_eent
   std::vector<int32_t> band_stage_ptr, band_stage_kent, band_stage_eent;
   int32_t hbw = 0;
 

@@ -66,7 +66,7 @@ struct WArgs {
   const double* xs;        // (B|1, Ns, 3)
   const double* loads;     // (B|1, N, 3)
   int64_t q_stride, xs_stride, loads_stride;
-  const int32_t *rowedge, *diags_ptr, *diags_idx, *free_node, *node_slot, *ninc_ptr, *ninc_edge, *ninc_other;
+  const int32_t *diags_ptr, *diags_idx, *free_node, *node_slot, *ninc_ptr, *ninc_edge, *ninc_other;
   const uint32_t* sup_mask;
   const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
 };
@@ -1015,7 +1015,7 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   A.forward = 0;
   A.q = A.xs = A.loads = nullptr;
   A.q_stride = A.xs_stride = A.loads_stride = 0;
-  A.rowedge = p->d.band_rowedge; A.diags_ptr = p->d.diags_ptr; A.diags_idx = p->d.diags_idx;
+  A.diags_ptr = p->d.diags_ptr; A.diags_idx = p->d.diags_idx;
   A.free_node = p->d.free_node; A.node_slot = p->d.node_slot; A.ninc_ptr = p->d.ninc_ptr;
   A.ninc_edge = p->d.ninc_edge; A.ninc_other = p->d.ninc_other; A.sup_mask = p->d.sup_mask;
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_eent;
@@ -1087,7 +1087,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.forward = o.reuse_factor ? 1 : 0;
   A.q = A.xs = A.loads = nullptr;
   A.q_stride = A.xs_stride = A.loads_stride = 0;
-  A.rowedge = nullptr; A.diags_ptr = A.diags_idx = A.free_node = A.node_slot = nullptr;
+  A.diags_ptr = A.diags_idx = A.free_node = A.node_slot = nullptr;
   A.ninc_ptr = A.ninc_edge = A.ninc_other = nullptr; A.sup_mask = nullptr;
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_kent;
   void (*fkern)(WArgs) = nullptr;

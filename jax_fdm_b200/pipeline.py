@@ -163,9 +163,13 @@ class ChunkedForwardAdjoint:
     them concatenated (views of one pinned allocation each).
     """
 
-    def __init__(self, structure, batch, chunks=4, **kw):
-        chunks = max(1, min(int(chunks), int(batch)))
-        sizes = [batch // chunks + (1 if i < batch % chunks else 0) for i in range(chunks)]
+    def __init__(self, structure, batch, chunks=4, sizes=None, **kw):
+        if sizes is None:
+            chunks = max(1, min(int(chunks), int(batch)))
+            sizes = [batch // chunks + (1 if i < batch % chunks else 0) for i in range(chunks)]
+        sizes = [int(b) for b in sizes]
+        assert sum(sizes) == int(batch) and min(sizes) > 0, "slice sizes must add up to the batch"
+        chunks = len(sizes)
         self.offsets = [sum(sizes[:i]) for i in range(chunks)]
         self.parts = [ForwardAdjoint(structure, batch=b, **kw) for b in sizes]
         self.B = int(batch)

@@ -701,8 +701,17 @@ loss_sqdist_kernel(const double* __restrict__ x, const double* __restrict__ x0,
   x += b * n;
   x0 += b * x0_stride;
   if (g) g += b * n;
+  // fixed order: thread t accumulates elements t, t + T, t + 2T, ... in that order (four loads in flight per trip)
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+  const int T = blockDim.x;
+  int64_t i = threadIdx.x;
+  for (; i + 3 * T < n; i += 4 * T) {
+    const double d0 = x[i] - __ldg(x0 + i), d1 = x[i + T] - __ldg(x0 + i + T);
+    const double d2 = x[i + 2 * T] - __ldg(x0 + i + 2 * T), d3 = x[i + 3 * T] - __ldg(x0 + i + 3 * T);
+    if (g) { g[i] = d0; g[i + T] = d1; g[i + 2 * T] = d2; g[i + 3 * T] = d3; }
+    acc += d0 * d0; acc += d1 * d1; acc += d2 * d2; acc += d3 * d3;
+  }
+  for (; i < n; i += T) {
     const double d = x[i] - __ldg(x0 + i);
     if (g) g[i] = d;
     acc += d * d;
@@ -863,7 +872,7 @@ int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, in
 
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                        int64_t batch, int64_t x0_stride, cudaStream_t st) {
-  const int threads = n >= 1024 ? 1024 : (int)std::max<int64_t>(32, ((n + 31) / 32) * 32);
+  const int threads = n >= 256 ? 256 : (int)std::max<int64_t>(32, ((n + 31) / 32) * 32);
   loss_sqdist_kernel<<<(unsigned)batch, threads, 0, st>>>(x, x0, g, loss, n, x0_stride);
   return fdm_check_launch("loss_sqdist");
 }

@@ -265,6 +265,9 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *        5 EdgeLoadPathGoal (goals/edge/loadpath.py)      |forces[e]| lengths[e]
  *        6 NetworkLoadPathGoal (goals/network/loadpath.py) sum_e |forces[e] lengths[e]|   (index unused)
  *        7, 8, 9 Node{X,Y,Z}CoordinateGoal (goals/node/coordinates.py)  xyz[i, 0 | 1 | 2]
+ *        10 NodeLineGoal, 11 NodePlaneGoal, 12 NodeSegmentGoal (goals/node/line.py, plane.py, segment.py):
+ *           xyz[i] vs its projection on the line / plane / segment given by target[0:6] (two points; origin and
+ *           normal); the projection is differentiated through, as JAX does
  *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
  *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
  * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):
@@ -278,7 +281,7 @@ typedef struct fdm_goal_program {
   const int32_t* index;       /* (T) node or edge index (structure order) */
   const int32_t* error;       /* (T) */
   const double* weight;       /* (T) */
-  const double* target;       /* (T,3) scalar targets in column 0 */
+  const double* target;       /* (T,6) scalar targets in column 0, points in columns 0..2 */
   const int32_t* group_ptr;   /* (G+1) */
   const int32_t* group_final; /* (G) */
   const double* group_inner;  /* (G) */

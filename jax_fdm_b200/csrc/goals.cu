@@ -34,13 +34,16 @@ enum GoalKind : int {
   G_NODE_X,                // xyz[i, 0], G_NODE_X + 1: xyz[i, 1], + 2: xyz[i, 2]   (1)
   G_NODE_Y,
   G_NODE_Z,
+  G_NODE_LINE,             // xyz[i] vs its projection on the line through target[0:3], target[3:6]   (3)
+  G_NODE_PLANE,            // xyz[i] vs its projection on the plane (origin target[0:3], normal target[3:6])  (3)
+  G_NODE_SEGMENT,          // xyz[i] vs the closest point of the segment target[0:3] - target[3:6]     (3)
 };
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
 
 struct GoalArgs {
   int T, G, N, E;
   const int32_t *kind, *index, *err, *group_ptr;   // (T), (T), (T), (G+1)
-  const double *weight, *target;                   // (T), (T,3)
+  const double *weight, *target;                   // (T), (T,6)
   const int32_t* gfinal;                           // (G) 0 identity, 1 sqrt
   const double *ginner, *gouter;                   // (G)
   const double *xyz, *lengths, *forces, *residuals;
@@ -84,6 +87,46 @@ __device__ __forceinline__ double err_deriv(int ek, double w, double p, double t
   }
 }
 
+
+// Goals whose reference value is a projection of the prediction (goals/node/line.py, plane.py, segment.py with
+// geometry.py:260-358).  gp = goal point; the Jacobian of p -> gp is the symmetric projector P = s * d d^T (line,
+// segment interior; d unit), I - n n^T (plane), 0 (segment end points); JAX differentiates through it, so the
+// cotangent of p is (I - P) e for the error derivative e.
+struct ProjGoal {
+  double gp[3];
+  double d[3];    // unit direction (line / segment interior) or unit normal (plane)
+  int mode;       // 0: P = d d^T, 1: P = I - d d^T, 2: P = 0
+};
+__device__ __forceinline__ ProjGoal proj_goal(int kind, const double* p, const double* t) {
+  ProjGoal r;
+  if (kind == G_NODE_PLANE) {
+    const double nn = sqrt(t[3] * t[3] + t[4] * t[4] + t[5] * t[5]);
+    const bool zero = fabs(t[3]) <= 1e-8 && fabs(t[4]) <= 1e-8 && fabs(t[5]) <= 1e-8;   // normalize_vector, geometry.py:138-168
+    const double inv = zero ? 1.0 : 1.0 / nn;
+    for (int c = 0; c < 3; ++c) r.d[c] = zero ? 0.0 : t[3 + c] * inv;
+    const double e = r.d[0] * (p[0] - t[0]) + r.d[1] * (p[1] - t[1]) + r.d[2] * (p[2] - t[2]);
+    const double k = e / (r.d[0] * r.d[0] + r.d[1] * r.d[1] + r.d[2] * r.d[2]);
+    for (int c = 0; c < 3; ++c) r.gp[c] = p[c] - r.d[c] * k;
+    r.mode = 1;
+    return r;
+  }
+  const double ab[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]};
+  const double l2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+  const double s = ((p[0] - t[0]) * ab[0] + (p[1] - t[1]) * ab[1] + (p[2] - t[2]) * ab[2]) / l2;
+  const double il = 1.0 / sqrt(l2);
+  for (int c = 0; c < 3; ++c) { r.gp[c] = t[c] + s * ab[c]; r.d[c] = ab[c] * il; }
+  r.mode = 0;
+  if (kind == G_NODE_SEGMENT) {
+    double d1 = 0.0, d2 = 0.0;
+    for (int c = 0; c < 3; ++c) { d1 += (t[c] - r.gp[c]) * (t[c] - r.gp[c]); d2 += (t[3 + c] - r.gp[c]) * (t[3 + c] - r.gp[c]); }
+    if (d1 > l2 || d2 > l2) {                       // outside: the nearer end point
+      for (int c = 0; c < 3; ++c) r.gp[c] = d1 < d2 ? t[c] : t[3 + c];
+      r.mode = 2;
+    }
+  }
+  return r;
+}
+
 __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
   __shared__ double red[16];
   __shared__ double s_mult[64];
@@ -109,7 +152,8 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
   }
   auto predict = [&](int k, int i, const double* t, double (&p)[3]) -> int {   // returns the number of components
     switch (k) {
-      case G_NODE_POINT: p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2]; return 3;
+      case G_NODE_POINT: case G_NODE_LINE: case G_NODE_PLANE: case G_NODE_SEGMENT:
+        p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2]; return 3;
       case G_NODE_RESIDUAL_VECTOR: p[0] = res[3 * i]; p[1] = res[3 * i + 1]; p[2] = res[3 * i + 2]; return 3;
       case G_NODE_RESIDUAL_FORCE:
         p[0] = sqrt(res[3 * i] * res[3 * i] + res[3 * i + 1] * res[3 * i + 1] + res[3 * i + 2] * res[3 * i + 2]);
@@ -127,8 +171,14 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     double acc = 0.0;
     for (int t = A.group_ptr[g] + threadIdx.x; t < A.group_ptr[g + 1]; t += kThreads) {
       double p[3];
-      const int nc = predict(A.kind[t], A.index[t], A.target + 3 * t, p);
-      for (int c = 0; c < nc; ++c) acc += err_value(A.err[t], A.weight[t], p[c], A.target[3 * t + c]);
+      const int k = A.kind[t];
+      const int nc = predict(k, A.index[t], A.target + 6 * t, p);
+      if (k >= G_NODE_LINE) {
+        const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
+        for (int c = 0; c < 3; ++c) acc += err_value(A.err[t], A.weight[t], p[c], pg.gp[c]);
+      } else {
+        for (int c = 0; c < nc; ++c) acc += err_value(A.err[t], A.weight[t], p[c], A.target[6 * t + c]);
+      }
     }
     const double S = block_sum(acc, red);
     const double u = A.ginner[g] * S;
@@ -149,9 +199,19 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       const int k = A.kind[t], i = A.index[t], ek = A.err[t];
       const double w = A.weight[t];
       double p[3];
-      const int nc = predict(k, i, A.target + 3 * t, p);
+      const int nc = predict(k, i, A.target + 6 * t, p);
       double d[3];
-      for (int c = 0; c < nc; ++c) d[c] = mult * err_deriv(ek, w, p[c], A.target[3 * t + c]);
+      if (k >= G_NODE_LINE) {
+        const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
+        for (int c = 0; c < 3; ++c) d[c] = mult * err_deriv(ek, w, p[c], pg.gp[c]);
+        const double de = pg.d[0] * d[0] + pg.d[1] * d[1] + pg.d[2] * d[2];
+        for (int c = 0; c < 3; ++c) {                     // (I - P) d
+          const double Pd = pg.mode == 0 ? pg.d[c] * de : pg.mode == 1 ? d[c] - pg.d[c] * de : 0.0;
+          atomicAdd(xb + 3 * i + c, d[c] - Pd);
+        }
+        continue;
+      }
+      for (int c = 0; c < nc; ++c) d[c] = mult * err_deriv(ek, w, p[c], A.target[6 * t + c]);
       switch (k) {
         case G_NODE_POINT:
           for (int c = 0; c < 3; ++c) atomicAdd(xb + 3 * i + c, d[c]);
@@ -179,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     // network load path terms of this group: all threads scatter over the edges
     for (int t = A.group_ptr[g]; t < A.group_ptr[g + 1]; ++t) {
       if (A.kind[t] != G_NETWORK_LOADPATH) continue;
-      const double d0 = mult * err_deriv(A.err[t], A.weight[t], loadpath, A.target[3 * t]);
+      const double d0 = mult * err_deriv(A.err[t], A.weight[t], loadpath, A.target[6 * t]);
       for (int e = threadIdx.x; e < A.E; e += kThreads) {
         const double pl = len[e] * frc[e];
         const double sg = pl > 0.0 ? 1.0 : (pl < 0.0 ? -1.0 : 0.0);

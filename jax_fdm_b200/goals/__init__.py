@@ -11,7 +11,8 @@ it: a `Loss` compiles its goals into a table and evaluates them with one fused k
 import numpy as np
 
 __all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "NodeResidualForceGoal",
-           "NodeResidualVectorGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
+           "NodeResidualVectorGoal", "NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal", "VertexLineGoal",
+           "VertexPlaneGoal", "VertexSegmentGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
            "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "NetworkLoadPathGoal",
            "VertexGoal", "VertexPointGoal", "VertexResidualForceGoal", "VertexResidualVectorGoal",
            "VertexXCoordinateGoal", "VertexYCoordinateGoal", "VertexZCoordinateGoal", "MeshLoadPathGoal", "GoalState"]
@@ -24,14 +25,20 @@ GoalState = namedtuple("GoalState", "goal weight prediction")     # goals/state.
 class Goal:
     """goals/goal.py:152-379: key, target, weight; `kind` is the row of the kernel's prediction table."""
     kind = -1
-    components = 1
+    components = 1          # of the prediction
+    target_size = None      # of the target when it is not a value of the prediction's shape (line, plane: 2 x 3)
 
     def __init__(self, key, target, weight=1.0):
         self.key = key
         self.target = np.asarray(target, dtype=np.float64)
         self.weight = float(weight)
-        if self.target.size != self.components:
-            raise ValueError(f"{type(self).__name__}: target must have {self.components} component(s)")
+        want = self.target_size or self.components
+        if self.target.size != want:
+            raise ValueError(f"{type(self).__name__}: target must have {want} component(s)")
+
+    def goal(self, target, prediction):
+        """goals/goal.py: the reference value the prediction is compared with (the target itself by default)."""
+        return target
 
     def index(self, structure):
         raise NotImplementedError
@@ -42,8 +49,9 @@ class Goal:
     def __call__(self, eq_state, structure):
         import torch
         p = self.prediction(eq_state, structure)
-        t = torch.as_tensor(self.target, dtype=p.dtype, device=p.device).reshape(p.shape[-1:] if self.components == 3 else ())
-        return GoalState(goal=t, weight=self.weight, prediction=p)
+        t = torch.as_tensor(self.target, dtype=p.dtype, device=p.device)
+        t = t.reshape(2, 3) if self.target_size == 6 else t.reshape(p.shape[-1:] if self.components == 3 else ())
+        return GoalState(goal=self.goal(t, p), weight=self.weight, prediction=p)
 
 
 class NodeGoal(Goal):
@@ -180,3 +188,52 @@ class VertexZCoordinateGoal(VertexGoal, NodeZCoordinateGoal):
 
 class MeshLoadPathGoal(NetworkLoadPathGoal):
     """goals/mesh/loadpath.py:7."""
+
+
+class NodeLineGoal(NodePointGoal):
+    """goals/node/line.py: the node against its closest point on the line through target[0], target[1]."""
+    kind, target_size = 10, 6
+
+    def goal(self, target, prediction):                 # geometry.py:288-313
+        a, b = target[0], target[1]
+        ab = b - a
+        s = ((prediction - a) * ab).sum(dim=-1, keepdim=True) / (ab * ab).sum()
+        return a + s * ab
+
+
+class NodePlaneGoal(NodePointGoal):
+    """goals/node/plane.py: the node against its closest point on the plane (origin target[0], normal target[1])."""
+    kind, target_size = 11, 6
+
+    def goal(self, target, prediction):                 # geometry.py:260-286
+        origin, normal = target[0], target[1]
+        normal = normal / normal.norm() if bool((normal.abs() > 1e-8).any()) else normal * 0.0
+        e = (prediction * normal).sum(dim=-1, keepdim=True) - (normal * origin).sum()
+        return prediction - normal * (e / (normal * normal).sum())
+
+
+class NodeSegmentGoal(NodeLineGoal):
+    """goals/node/segment.py: the node against the closest point of the segment target[0] - target[1]."""
+    kind = 12
+
+    def goal(self, target, prediction):                 # geometry.py:315-357
+        import torch
+        a, b = target[0], target[1]
+        p = NodeLineGoal.goal(self, target, prediction)
+        d = ((a - b) ** 2).sum()
+        d1 = ((a - p) ** 2).sum(dim=-1, keepdim=True)
+        d2 = ((b - p) ** 2).sum(dim=-1, keepdim=True)
+        end = torch.where(d1 < d2, a.expand_as(p), b.expand_as(p))
+        return torch.where((d1 > d) | (d2 > d), end, p)
+
+
+class VertexLineGoal(VertexGoal, NodeLineGoal):
+    """goals/vertex/line.py."""
+
+
+class VertexPlaneGoal(VertexGoal, NodePlaneGoal):
+    """goals/vertex/plane.py."""
+
+
+class VertexSegmentGoal(VertexGoal, NodeSegmentGoal):
+    """goals/vertex/segment.py."""

@@ -142,8 +142,8 @@ class _Program:
                 index.append(g.index(structure))
                 err.append(term.err_kind)
                 weight.append(g.weight)
-                t = np.zeros(3)
-                t[:g.components] = g.target.ravel()
+                t = np.zeros(6)
+                t[:g.target.size] = g.target.ravel()
                 target.append(t)
             gptr.append(len(kind))
             gfinal.append(1 if term.root else 0)
@@ -155,7 +155,7 @@ class _Program:
             return torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
 
         self.arrays = [dev(kind, np.int32), dev(index, np.int32), dev(err, np.int32), dev(weight, np.float64),
-                       dev(np.asarray(target).reshape(-1, 3), np.float64), dev(gptr, np.int32), dev(gfinal, np.int32),
+                       dev(np.asarray(target).reshape(-1, 6), np.float64), dev(gptr, np.int32), dev(gfinal, np.int32),
                        dev(ginner, np.float64), dev(gouter, np.float64)]
         ptr = [C.c_void_p(a.data_ptr()) for a in self.arrays]
         self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), *ptr)

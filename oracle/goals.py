@@ -31,6 +31,39 @@ PREDICTIONS = {
     "NodeZCoordinateGoal": lambda st, i: st["xyz"][i, 2],
 }
 
+
+
+def _closest_point_on_line(p, line):
+    """geometry.py:288-313."""
+    a, b = np.asarray(line, dtype=np.float64).reshape(2, 3)
+    ab = b - a
+    return a + ab * ((p - a) @ ab) / (ab @ ab)
+
+
+def _closest_point_on_plane(p, plane):
+    """geometry.py:260-286 (normal through normalize_vector, :138-168)."""
+    origin, normal = np.asarray(plane, dtype=np.float64).reshape(2, 3)
+    normal = np.zeros(3) if np.all(np.abs(normal) <= 1e-8) else normal / np.linalg.norm(normal)
+    e = normal @ p - normal @ origin
+    return p - normal * (e / np.sum(np.square(normal)))
+
+
+def _closest_point_on_segment(p, seg):
+    """geometry.py:315-357."""
+    a, b = np.asarray(seg, dtype=np.float64).reshape(2, 3)
+    c = _closest_point_on_line(p, seg)
+    d, d1, d2 = np.sum((a - b) ** 2), np.sum((a - c) ** 2), np.sum((b - c) ** 2)
+    if d1 > d or d2 > d:
+        return a if d1 < d2 else b
+    return c
+
+
+# goals whose reference value depends on the prediction (goals/node/line.py, plane.py, segment.py)
+GOALS = {"NodeLineGoal": _closest_point_on_line, "NodePlaneGoal": _closest_point_on_plane,
+         "NodeSegmentGoal": _closest_point_on_segment}
+for _n in GOALS:
+    PREDICTIONS[_n] = PREDICTIONS["NodePointGoal"]
+
 ERRORS = {
     "SquaredError": lambda w, p, t: np.sum(w * np.square(p - t)),
     "AbsoluteError": lambda w, p, t: np.sum(w * np.abs(p - t)),
@@ -44,7 +77,11 @@ BASE = {"MeanSquaredError": "SquaredError", "RootMeanSquaredError": "SquaredErro
 def error_term(name, goals, alpha, state):
     """goals: list of (goal class name, element index, target, weight)."""
     fn = ERRORS[BASE.get(name, name)]
-    total = sum(fn(w, PREDICTIONS[g](state, i), np.asarray(t, dtype=np.float64)) for g, i, t, w in goals)
+    total = 0.0
+    for g, i, t, w in goals:
+        p = PREDICTIONS[g](state, i)
+        t = GOALS[g](p, t) if g in GOALS else np.asarray(t, dtype=np.float64)
+        total = total + fn(w, p, t)
     if name.startswith("Mean") or name.startswith("RootMean"):
         total = total / len(goals)
     if name.startswith("Root"):

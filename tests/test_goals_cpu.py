@@ -39,6 +39,10 @@ def test_goalwise_errors_match_the_oracle():
         (LS.MeanAbsoluteError, "MeanAbsoluteError", [(G.NodeResidualVectorGoal, "NodeResidualVectorGoal", n1, [0.1, -0.2, 0.0], 1.0)]),
         (LS.PredictionError, "PredictionError", [(G.EdgeLoadPathGoal, "EdgeLoadPathGoal", e1, 0.0, 2.0)]),
         (LS.LogMaxError, "LogMaxError", [(G.EdgeLengthGoal, "EdgeLengthGoal", e0, 0.5, 1.0)]),
+        (LS.SquaredError, "SquaredError", [(G.NodeLineGoal, "NodeLineGoal", n0, [[0, 0, 1], [3, 4, 2]], 1.5),
+                                           (G.NodePlaneGoal, "NodePlaneGoal", n0, [[0, 0, 0.5], [0.1, 0.2, 2.0]], 1.0),
+                                           (G.NodeSegmentGoal, "NodeSegmentGoal", n0, [[0, 0, 1], [0.5, 0.5, 1.2]], 2.0),
+                                           (G.NodeSegmentGoal, "NodeSegmentGoal", n0, [[-50, 0, 1], [60, 40, 2]], 1.0)]),
     ]
     for ecls, ename, goals in cases:
         term = ecls([g(key, target, weight) for g, _, key, target, weight in goals], alpha=0.7)
@@ -64,7 +68,7 @@ def test_goal_program_layout():
     kind, index, err, weight, target, gptr, gfinal, ginner, gouter = [a.numpy() for a in prog.arrays]
     assert kind.tolist() == [3, 3, 0, 6] and err.tolist() == [0, 0, 0, 2]
     assert index.tolist() == [0, 2, 4, 0] and weight.tolist() == [1.0, 3.0, 1.0, 1.0]
-    assert target.tolist() == [[1, 0, 0], [2, 0, 0], [1, 2, 3], [0, 0, 0]]
+    assert target.tolist() == [[1, 0, 0, 0, 0, 0], [2, 0, 0, 0, 0, 0], [1, 2, 3, 0, 0, 0], [0, 0, 0, 0, 0, 0]]
     assert gptr.tolist() == [0, 2, 3, 4] and gfinal.tolist() == [0, 1, 0]
     assert ginner.tolist() == [0.5, 1.0, 1.0] and gouter.tolist() == [0.5, 1.0, 0.1]
     assert prog.struct.num_terms == 4 and prog.struct.num_groups == 3 and prog.struct.has_network_loadpath == 1

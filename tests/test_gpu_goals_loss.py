@@ -47,6 +47,13 @@ def build_loss(prob, s, rng):
         ("SquaredError", 1e-4, [("NetworkLoadPathGoal", -1, 50.0, 1.0), ("EdgeLengthGoal", ekey(pick_e[0]), 1.0, 3.0)]),
         ("SquaredError", 0.3, [(f"Node{ax}CoordinateGoal", int(nodes[n]), prob.xyz0[n, c] - 0.2, 1.0 + c)
                                for c, ax in enumerate("XYZ") for n in pick_n[:4]]),
+        # reference values that are projections of the prediction (differentiated through, as JAX does)
+        ("SquaredError", 0.8, [("NodeLineGoal", int(nodes[pick_n[0]]), [prob.xyz0[pick_n[0]] + [0.3, -0.2, 0.5], prob.xyz0[pick_n[0]] + [1.0, 2.0, 3.0]], 1.2),
+                               ("NodePlaneGoal", int(nodes[pick_n[1]]), [prob.xyz0[pick_n[1]] + [0.0, 0.0, 0.4], [0.2, -0.1, 1.0]], 0.7),
+                               ("NodeSegmentGoal", int(nodes[pick_n[2]]), [prob.xyz0[pick_n[2]] + [-1.0, 0.1, 0.3], prob.xyz0[pick_n[2]] + [1.0, 0.4, 0.6]], 1.0),
+                               ("NodeSegmentGoal", int(nodes[pick_n[3]]), [prob.xyz0[pick_n[3]] + [5.0, 5.0, 1.0], prob.xyz0[pick_n[3]] + [9.0, 6.0, 2.0]], 1.0)]),
+        ("AbsoluteError", 0.4, [("NodeLineGoal", int(nodes[pick_n[4]]), [prob.xyz0[pick_n[4]] + [0.3, 0.2, -0.4], prob.xyz0[pick_n[4]] + [-1.0, 1.5, 2.0]], 1.0),
+                                ("NodePlaneGoal", int(nodes[pick_n[5]]), [prob.xyz0[pick_n[5]] + [0.1, 0.0, 0.3], [1.0, 0.5, 0.25]], 2.0)]),
     ]
     terms, oterms = [], []
     for ename, alpha, goals in spec:
@@ -56,7 +63,7 @@ def build_loss(prob, s, rng):
             g = cls(target=target, weight=weight) if gname == "NetworkLoadPathGoal" else cls(key, target, weight)
             gl.append(g)
             idx = 0 if gname == "NetworkLoadPathGoal" else (ni[key] if isinstance(key, int) else ei[key])
-            ol.append((gname, idx, target, weight))
+            ol.append((gname, idx, np.asarray(target, dtype=np.float64), weight))
         terms.append(getattr(LS, ename)(gl, alpha=alpha))
         oterms.append((ename, ol, alpha))
     l2 = 1e-3

@@ -268,6 +268,8 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *        10 NodeLineGoal, 11 NodePlaneGoal, 12 NodeSegmentGoal (goals/node/line.py, plane.py, segment.py):
  *           xyz[i] vs its projection on the line / plane / segment given by target[0:6] (two points; origin and
  *           normal); the projection is differentiated through, as JAX does
+ *        13 NodeResidualDirectionGoal, 14 NodeResidualPlaneGoal (goals/node/residual.py:86-219): the unit
+ *           residual against the unit target / against its projection on the plane with normal target[0:3]
  *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
  *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
  * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):

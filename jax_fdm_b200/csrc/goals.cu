@@ -37,6 +37,8 @@ enum GoalKind : int {
   G_NODE_LINE,             // xyz[i] vs its projection on the line through target[0:3], target[3:6]   (3)
   G_NODE_PLANE,            // xyz[i] vs its projection on the plane (origin target[0:3], normal target[3:6])  (3)
   G_NODE_SEGMENT,          // xyz[i] vs the closest point of the segment target[0:3] - target[3:6]     (3)
+  G_NODE_RESIDUAL_DIRECTION,  // residuals[i] / |residuals[i]| vs target / |target|                    (3)
+  G_NODE_RESIDUAL_PLANE,      // the same unit vector vs its projection on the plane through 0 with normal target (3)
 };
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
 
@@ -97,8 +99,30 @@ struct ProjGoal {
   double d[3];    // unit direction (line / segment interior) or unit normal (plane)
   int mode;       // 0: P = d d^T, 1: P = I - d d^T, 2: P = 0
 };
+// normalize_vector (geometry.py:138-168): the zero vector stays zero
+__device__ __forceinline__ double unit3(const double* v, double* u) {
+  const bool zero = fabs(v[0]) <= 1e-8 && fabs(v[1]) <= 1e-8 && fabs(v[2]) <= 1e-8;
+  const double nn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const double inv = zero ? 1.0 : 1.0 / nn;
+  for (int c = 0; c < 3; ++c) u[c] = zero ? 0.0 : v[c] * inv;
+  return zero ? 0.0 : nn;
+}
+
 __device__ __forceinline__ ProjGoal proj_goal(int kind, const double* p, const double* t) {
   ProjGoal r;
+  if (kind == G_NODE_RESIDUAL_DIRECTION) {          // goals/node/residual.py:86-145: the target's direction, constant
+    unit3(t, r.gp);
+    r.d[0] = r.d[1] = r.d[2] = 0.0;
+    r.mode = 2;
+    return r;
+  }
+  if (kind == G_NODE_RESIDUAL_PLANE) {              // residual.py:148-219: p - (p . n) n
+    unit3(t, r.d);
+    const double pn = p[0] * r.d[0] + p[1] * r.d[1] + p[2] * r.d[2];
+    for (int c = 0; c < 3; ++c) r.gp[c] = p[c] - pn * r.d[c];
+    r.mode = 1;
+    return r;
+  }
   if (kind == G_NODE_PLANE) {
     const double nn = sqrt(t[3] * t[3] + t[4] * t[4] + t[5] * t[5]);
     const bool zero = fabs(t[3]) <= 1e-8 && fabs(t[4]) <= 1e-8 && fabs(t[5]) <= 1e-8;   // normalize_vector, geometry.py:138-168
@@ -155,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       case G_NODE_POINT: case G_NODE_LINE: case G_NODE_PLANE: case G_NODE_SEGMENT:
         p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2]; return 3;
       case G_NODE_RESIDUAL_VECTOR: p[0] = res[3 * i]; p[1] = res[3 * i + 1]; p[2] = res[3 * i + 2]; return 3;
+      case G_NODE_RESIDUAL_DIRECTION: case G_NODE_RESIDUAL_PLANE: unit3(res + 3 * i, p); return 3;
       case G_NODE_RESIDUAL_FORCE:
         p[0] = sqrt(res[3 * i] * res[3 * i] + res[3 * i + 1] * res[3 * i + 1] + res[3 * i + 2] * res[3 * i + 2]);
         return 1;
@@ -205,9 +230,20 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
         const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
         for (int c = 0; c < 3; ++c) d[c] = mult * err_deriv(ek, w, p[c], pg.gp[c]);
         const double de = pg.d[0] * d[0] + pg.d[1] * d[1] + pg.d[2] * d[2];
+        double cp[3];
         for (int c = 0; c < 3; ++c) {                     // (I - P) d
           const double Pd = pg.mode == 0 ? pg.d[c] * de : pg.mode == 1 ? d[c] - pg.d[c] * de : 0.0;
-          atomicAdd(xb + 3 * i + c, d[c] - Pd);
+          cp[c] = d[c] - Pd;
+        }
+        if (k >= G_NODE_RESIDUAL_DIRECTION) {             // through r -> r / |r|: (I - p p^T) / |r|
+          double u[3];
+          const double nn = unit3(res + 3 * i, u);
+          if (nn > 0.0) {
+            const double pc = p[0] * cp[0] + p[1] * cp[1] + p[2] * cp[2];
+            for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, (cp[c] - p[c] * pc) / nn);
+          }
+        } else {
+          for (int c = 0; c < 3; ++c) atomicAdd(xb + 3 * i + c, cp[c]);
         }
         continue;
       }

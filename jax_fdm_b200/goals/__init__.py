@@ -11,7 +11,8 @@ it: a `Loss` compiles its goals into a table and evaluates them with one fused k
 import numpy as np
 
 __all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "NodeResidualForceGoal",
-           "NodeResidualVectorGoal", "NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal", "VertexLineGoal",
+           "NodeResidualVectorGoal", "NodeResidualDirectionGoal", "NodeResidualPlaneGoal",
+           "VertexResidualDirectionGoal", "VertexResidualPlaneGoal", "NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal", "VertexLineGoal",
            "VertexPlaneGoal", "VertexSegmentGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
            "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "NetworkLoadPathGoal",
            "VertexGoal", "VertexPointGoal", "VertexResidualForceGoal", "VertexResidualVectorGoal",
@@ -237,3 +238,41 @@ class VertexPlaneGoal(VertexGoal, NodePlaneGoal):
 
 class VertexSegmentGoal(VertexGoal, NodeSegmentGoal):
     """goals/vertex/segment.py."""
+
+
+def _unit(v):
+    """normalize_vector (geometry.py:138-168): the zero vector stays zero."""
+    n = v.norm(dim=-1, keepdim=True)
+    zero = (v.abs() <= 1e-8).all(dim=-1, keepdim=True)
+    return v / n.masked_fill(zero, 1.0) * (~zero)
+
+
+class NodeResidualDirectionGoal(NodeGoal):
+    """goals/node/residual.py:86-145: unit residual against the unit target."""
+    kind, components = 13, 3
+
+    def prediction(self, eq_state, structure):
+        return _unit(eq_state.residuals[..., self.index(structure), :])
+
+    def goal(self, target, prediction):
+        return _unit(target)
+
+
+class NodeResidualPlaneGoal(NodeGoal):
+    """goals/node/residual.py:148-219: unit residual against its projection on the plane with normal `target`."""
+    kind, components = 14, 3
+
+    def prediction(self, eq_state, structure):
+        return _unit(eq_state.residuals[..., self.index(structure), :])
+
+    def goal(self, target, prediction):
+        n = _unit(target)
+        return prediction - (prediction * n).sum(dim=-1, keepdim=True) * n
+
+
+class VertexResidualDirectionGoal(VertexGoal, NodeResidualDirectionGoal):
+    """goals/vertex/residual.py:29."""
+
+
+class VertexResidualPlaneGoal(VertexGoal, NodeResidualPlaneGoal):
+    """goals/vertex/residual.py:40."""

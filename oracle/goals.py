@@ -58,11 +58,22 @@ def _closest_point_on_segment(p, seg):
     return c
 
 
-# goals whose reference value depends on the prediction (goals/node/line.py, plane.py, segment.py)
+def _normalize_vector(v):
+    """geometry.py:138-168."""
+    v = np.asarray(v, dtype=np.float64)
+    return np.zeros(3) if np.all(np.abs(v) <= 1e-8) else v / np.linalg.norm(v)
+
+
+# goals whose reference value is computed from the target and the prediction (goals/node/line.py, plane.py,
+# segment.py, residual.py:125-145, 197-219)
 GOALS = {"NodeLineGoal": _closest_point_on_line, "NodePlaneGoal": _closest_point_on_plane,
-         "NodeSegmentGoal": _closest_point_on_segment}
-for _n in GOALS:
+         "NodeSegmentGoal": _closest_point_on_segment,
+         "NodeResidualDirectionGoal": lambda p, t: _normalize_vector(t),
+         "NodeResidualPlaneGoal": lambda p, t: p - (p @ _normalize_vector(t)) * _normalize_vector(t)}
+for _n in ("NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal"):
     PREDICTIONS[_n] = PREDICTIONS["NodePointGoal"]
+PREDICTIONS["NodeResidualDirectionGoal"] = lambda st, i: _normalize_vector(st["residuals"][i, :])   # residual.py:98-123
+PREDICTIONS["NodeResidualPlaneGoal"] = PREDICTIONS["NodeResidualDirectionGoal"]                      # residual.py:170-195
 
 ERRORS = {
     "SquaredError": lambda w, p, t: np.sum(w * np.square(p - t)),

@@ -52,6 +52,8 @@ def build_loss(prob, s, rng):
                                ("NodePlaneGoal", int(nodes[pick_n[1]]), [prob.xyz0[pick_n[1]] + [0.0, 0.0, 0.4], [0.2, -0.1, 1.0]], 0.7),
                                ("NodeSegmentGoal", int(nodes[pick_n[2]]), [prob.xyz0[pick_n[2]] + [-1.0, 0.1, 0.3], prob.xyz0[pick_n[2]] + [1.0, 0.4, 0.6]], 1.0),
                                ("NodeSegmentGoal", int(nodes[pick_n[3]]), [prob.xyz0[pick_n[3]] + [5.0, 5.0, 1.0], prob.xyz0[pick_n[3]] + [9.0, 6.0, 2.0]], 1.0)]),
+        ("SquaredError", 1.1, [("NodeResidualDirectionGoal", int(nodes[n]), [0.1, -0.3, 1.0], 1.0 + 0.5 * j) for j, n in enumerate(fixed[:3])]
+                              + [("NodeResidualPlaneGoal", int(nodes[fixed[3 % len(fixed)]]), [0.2, 1.0, 0.3], 2.0)]),
         ("AbsoluteError", 0.4, [("NodeLineGoal", int(nodes[pick_n[4]]), [prob.xyz0[pick_n[4]] + [0.3, 0.2, -0.4], prob.xyz0[pick_n[4]] + [-1.0, 1.5, 2.0]], 1.0),
                                 ("NodePlaneGoal", int(nodes[pick_n[5]]), [prob.xyz0[pick_n[5]] + [0.1, 0.0, 0.3], [1.0, 0.5, 0.25]], 2.0)]),
     ]

@@ -270,6 +270,8 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *           normal); the projection is differentiated through, as JAX does
  *        13 NodeResidualDirectionGoal, 14 NodeResidualPlaneGoal (goals/node/residual.py:86-219): the unit
  *           residual against the unit target / against its projection on the plane with normal target[0:3]
+ *        15 EdgeDirectionGoal (goals/edge/direction.py): unit edge vector xyz[head]-xyz[tail] vs unit target
+ *        16 EdgeAngleGoal (goals/edge/angle.py): angle between the edge vector and target[1:4] vs target[0]
  *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
  *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
  * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):

@@ -39,12 +39,15 @@ enum GoalKind : int {
   G_NODE_SEGMENT,          // xyz[i] vs the closest point of the segment target[0:3] - target[3:6]     (3)
   G_NODE_RESIDUAL_DIRECTION,  // residuals[i] / |residuals[i]| vs target / |target|                    (3)
   G_NODE_RESIDUAL_PLANE,      // the same unit vector vs its projection on the plane through 0 with normal target (3)
+  G_EDGE_DIRECTION,           // unit edge vector (xyz[head] - xyz[tail]) vs target / |target|          (3)
+  G_EDGE_ANGLE,               // angle between the edge vector and target[1:4] vs target[0]             (1)
 };
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
 
 struct GoalArgs {
   int T, G, N, E;
   const int32_t *kind, *index, *err, *group_ptr;   // (T), (T), (T), (G+1)
+  const int32_t* edge_nodes;                       // plan: (E,2) tail, head
   const double *weight, *target;                   // (T), (T,6)
   const int32_t* gfinal;                           // (G) 0 identity, 1 sqrt
   const double *ginner, *gouter;                   // (G)
@@ -110,7 +113,7 @@ __device__ __forceinline__ double unit3(const double* v, double* u) {
 
 __device__ __forceinline__ ProjGoal proj_goal(int kind, const double* p, const double* t) {
   ProjGoal r;
-  if (kind == G_NODE_RESIDUAL_DIRECTION) {          // goals/node/residual.py:86-145: the target's direction, constant
+  if (kind == G_NODE_RESIDUAL_DIRECTION || kind == G_EDGE_DIRECTION) {   // residual.py:86-145, edge/direction.py:49-69
     unit3(t, r.gp);
     r.d[0] = r.d[1] = r.d[2] = 0.0;
     r.mode = 2;
@@ -180,6 +183,16 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
         p[0] = xyz[3 * i]; p[1] = xyz[3 * i + 1]; p[2] = xyz[3 * i + 2]; return 3;
       case G_NODE_RESIDUAL_VECTOR: p[0] = res[3 * i]; p[1] = res[3 * i + 1]; p[2] = res[3 * i + 2]; return 3;
       case G_NODE_RESIDUAL_DIRECTION: case G_NODE_RESIDUAL_PLANE: unit3(res + 3 * i, p); return 3;
+      case G_EDGE_DIRECTION: case G_EDGE_ANGLE: {      // goals/edge/direction.py:23-47, angle.py:74-101, geometry.py:46-99
+        const int a = A.edge_nodes[2 * i], h = A.edge_nodes[2 * i + 1];
+        const double v[3] = {xyz[3 * h] - xyz[3 * a], xyz[3 * h + 1] - xyz[3 * a + 1], xyz[3 * h + 2] - xyz[3 * a + 2]};
+        if (k == G_EDGE_DIRECTION) { unit3(v, p); return 3; }
+        double u[3], w[3];
+        unit3(v, u); unit3(t + 1, w);
+        p[1] = fmin(1.0, fmax(-1.0, u[0] * w[0] + u[1] * w[1] + u[2] * w[2]));   // the clipped cosine, kept for pass 2
+        p[0] = acos(p[1]);
+        return 1;
+      }
       case G_NODE_RESIDUAL_FORCE:
         p[0] = sqrt(res[3 * i] * res[3 * i] + res[3 * i + 1] * res[3 * i + 1] + res[3 * i + 2] * res[3 * i + 2]);
         return 1;
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       double p[3];
       const int k = A.kind[t];
       const int nc = predict(k, A.index[t], A.target + 6 * t, p);
-      if (k >= G_NODE_LINE) {
+      if (k >= G_NODE_LINE && k != G_EDGE_ANGLE) {
         const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
         for (int c = 0; c < 3; ++c) acc += err_value(A.err[t], A.weight[t], p[c], pg.gp[c]);
       } else {
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       double p[3];
       const int nc = predict(k, i, A.target + 6 * t, p);
       double d[3];
-      if (k >= G_NODE_LINE) {
+      if (k >= G_NODE_LINE && k != G_EDGE_ANGLE) {
         const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
         for (int c = 0; c < 3; ++c) d[c] = mult * err_deriv(ek, w, p[c], pg.gp[c]);
         const double de = pg.d[0] * d[0] + pg.d[1] * d[1] + pg.d[2] * d[2];
@@ -235,7 +248,20 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
           const double Pd = pg.mode == 0 ? pg.d[c] * de : pg.mode == 1 ? d[c] - pg.d[c] * de : 0.0;
           cp[c] = d[c] - Pd;
         }
-        if (k >= G_NODE_RESIDUAL_DIRECTION) {             // through r -> r / |r|: (I - p p^T) / |r|
+        if (k == G_EDGE_DIRECTION) {                      // through v -> v / |v|, v = xyz[head] - xyz[tail]
+          const int a = A.edge_nodes[2 * i], h = A.edge_nodes[2 * i + 1];
+          const double v[3] = {xyz[3 * h] - xyz[3 * a], xyz[3 * h + 1] - xyz[3 * a + 1], xyz[3 * h + 2] - xyz[3 * a + 2]};
+          double u[3];
+          const double nn = unit3(v, u);
+          if (nn > 0.0) {
+            const double pc = p[0] * cp[0] + p[1] * cp[1] + p[2] * cp[2];
+            for (int c = 0; c < 3; ++c) {
+              const double gv = (cp[c] - p[c] * pc) / nn;
+              atomicAdd(xb + 3 * h + c, gv);
+              atomicAdd(xb + 3 * a + c, -gv);
+            }
+          }
+        } else if (k >= G_NODE_RESIDUAL_DIRECTION) {      // through r -> r / |r|: (I - p p^T) / |r|
           double u[3];
           const double nn = unit3(res + 3 * i, u);
           if (nn > 0.0) {
@@ -260,6 +286,23 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
             for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, d[0] * res[3 * i + c] / p[0]);
           break;
         case G_NODE_X: case G_NODE_Y: case G_NODE_Z: atomicAdd(xb + 3 * i + (k - G_NODE_X), d[0]); break;
+        case G_EDGE_ANGLE: {
+          const int a = A.edge_nodes[2 * i], h = A.edge_nodes[2 * i + 1];
+          const double v[3] = {xyz[3 * h] - xyz[3 * a], xyz[3 * h + 1] - xyz[3 * a + 1], xyz[3 * h + 2] - xyz[3 * a + 2]};
+          double u[3], wv[3];
+          const double nn = unit3(v, u);
+          unit3(A.target + 6 * t + 1, wv);
+          const double c = p[1], s2 = 1.0 - c * c;
+          if (nn > 0.0 && s2 > 0.0) {
+            const double f = -d[0] / (sqrt(s2) * nn);     // d acos / d cos, through u = v / |v|
+            for (int cc = 0; cc < 3; ++cc) {
+              const double gv = f * (wv[cc] - u[cc] * c);
+              atomicAdd(xb + 3 * h + cc, gv);
+              atomicAdd(xb + 3 * a + cc, -gv);
+            }
+          }
+          break;
+        }
         case G_EDGE_LENGTH: atomicAdd(lb + i, d[0]); break;
         case G_EDGE_FORCE: atomicAdd(fb + i, d[0]); break;
         case G_EDGE_LOADPATH: {
@@ -297,7 +340,7 @@ int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const
                       double* residuals_bar, int64_t batch, cudaStream_t st) {
   GoalArgs A;
   A.T = n_terms; A.G = n_groups; A.N = (int)p->N; A.E = (int)p->E;
-  A.kind = kind; A.index = index; A.err = err; A.group_ptr = group_ptr;
+  A.kind = kind; A.index = index; A.err = err; A.group_ptr = group_ptr; A.edge_nodes = p->d.edge_nodes;
   A.weight = weight; A.target = target; A.gfinal = gfinal; A.ginner = ginner; A.gouter = gouter;
   A.xyz = xyz; A.lengths = lengths; A.forces = forces; A.residuals = residuals;
   A.loss = loss; A.gsum = gsum;

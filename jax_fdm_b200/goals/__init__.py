@@ -14,7 +14,8 @@ __all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "Node
            "NodeResidualVectorGoal", "NodeResidualDirectionGoal", "NodeResidualPlaneGoal",
            "VertexResidualDirectionGoal", "VertexResidualPlaneGoal", "NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal", "VertexLineGoal",
            "VertexPlaneGoal", "VertexSegmentGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
-           "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "NetworkLoadPathGoal",
+           "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "EdgeDirectionGoal", "EdgeAngleGoal",
+           "NetworkLoadPathGoal",
            "VertexGoal", "VertexPointGoal", "VertexResidualForceGoal", "VertexResidualVectorGoal",
            "VertexXCoordinateGoal", "VertexYCoordinateGoal", "VertexZCoordinateGoal", "MeshLoadPathGoal", "GoalState"]
 
@@ -276,3 +277,36 @@ class VertexResidualDirectionGoal(VertexGoal, NodeResidualDirectionGoal):
 
 class VertexResidualPlaneGoal(VertexGoal, NodeResidualPlaneGoal):
     """goals/vertex/residual.py:40."""
+
+
+class EdgeDirectionGoal(EdgeGoal):
+    """goals/edge/direction.py: unit edge vector against the unit target."""
+    kind, components = 15, 3
+
+    def prediction(self, eq_state, structure):
+        return _unit(eq_state.vectors[..., self.index(structure), :])
+
+    def goal(self, target, prediction):
+        return _unit(target)
+
+
+class EdgeAngleGoal(EdgeGoal):
+    """goals/edge/angle.py: angle (radians) between the edge vector and `vector` against the target angle."""
+    kind = 16
+
+    def __init__(self, key, target, weight=1.0, *, vector):
+        self.vector = np.asarray(vector, dtype=np.float64).reshape(3)
+        super().__init__(key, target, weight)
+        self.target = np.concatenate([np.asarray(target, dtype=np.float64).reshape(1), self.vector])   # kernel row
+        self.target_size = 4
+
+    def prediction(self, eq_state, structure):
+        import torch
+        u = _unit(eq_state.vectors[..., self.index(structure), :])
+        w = _unit(torch.as_tensor(self.vector, dtype=u.dtype, device=u.device))
+        return torch.arccos(torch.clamp((u * w).sum(dim=-1), -1.0, 1.0))
+
+    def __call__(self, eq_state, structure):
+        import torch
+        p = self.prediction(eq_state, structure)
+        return GoalState(goal=torch.as_tensor(self.target[0], dtype=p.dtype, device=p.device), weight=self.weight, prediction=p)

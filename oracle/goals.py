@@ -74,6 +74,14 @@ for _n in ("NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal"):
     PREDICTIONS[_n] = PREDICTIONS["NodePointGoal"]
 PREDICTIONS["NodeResidualDirectionGoal"] = lambda st, i: _normalize_vector(st["residuals"][i, :])   # residual.py:98-123
 PREDICTIONS["NodeResidualPlaneGoal"] = PREDICTIONS["NodeResidualDirectionGoal"]                      # residual.py:170-195
+PREDICTIONS["EdgeDirectionGoal"] = lambda st, i: _normalize_vector(st["vectors"][i, :])             # edge/direction.py:23-47
+GOALS["EdgeDirectionGoal"] = lambda p, t: _normalize_vector(t)                                       # edge/direction.py:49-69
+
+
+def edge_angle(st, i, vector):
+    """goals/edge/angle.py:74-101 with geometry.py:46-99 (radians)."""
+    c = _normalize_vector(st["vectors"][i, :]) @ _normalize_vector(vector)
+    return np.arccos(np.clip(c, -1.0, 1.0))
 
 ERRORS = {
     "SquaredError": lambda w, p, t: np.sum(w * np.square(p - t)),
@@ -90,6 +98,9 @@ def error_term(name, goals, alpha, state):
     fn = ERRORS[BASE.get(name, name)]
     total = 0.0
     for g, i, t, w in goals:
+        if g == "EdgeAngleGoal":                      # t = (target angle, reference vector)
+            total = total + fn(w, edge_angle(state, i, t[1]), np.float64(t[0]))
+            continue
         p = PREDICTIONS[g](state, i)
         t = GOALS[g](p, t) if g in GOALS else np.asarray(t, dtype=np.float64)
         total = total + fn(w, p, t)

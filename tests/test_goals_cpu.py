@@ -44,7 +44,8 @@ def test_goalwise_errors_match_the_oracle():
                                            (G.NodeSegmentGoal, "NodeSegmentGoal", n0, [[0, 0, 1], [0.5, 0.5, 1.2]], 2.0),
                                            (G.NodeSegmentGoal, "NodeSegmentGoal", n0, [[-50, 0, 1], [60, 40, 2]], 1.0)]),
         (LS.SquaredError, "SquaredError", [(G.NodeResidualDirectionGoal, "NodeResidualDirectionGoal", n1, [0.1, -0.3, 1.0], 1.5),
-                                           (G.NodeResidualPlaneGoal, "NodeResidualPlaneGoal", n1, [0.2, 1.0, 0.3], 2.0)]),
+                                           (G.NodeResidualPlaneGoal, "NodeResidualPlaneGoal", n1, [0.2, 1.0, 0.3], 2.0),
+                                           (G.EdgeDirectionGoal, "EdgeDirectionGoal", e0, [0.3, 1.0, -0.2], 1.0)]),
     ]
     for ecls, ename, goals in cases:
         term = ecls([g(key, target, weight) for g, _, key, target, weight in goals], alpha=0.7)

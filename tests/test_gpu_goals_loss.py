@@ -54,6 +54,8 @@ def build_loss(prob, s, rng):
                                ("NodeSegmentGoal", int(nodes[pick_n[3]]), [prob.xyz0[pick_n[3]] + [5.0, 5.0, 1.0], prob.xyz0[pick_n[3]] + [9.0, 6.0, 2.0]], 1.0)]),
         ("SquaredError", 1.1, [("NodeResidualDirectionGoal", int(nodes[n]), [0.1, -0.3, 1.0], 1.0 + 0.5 * j) for j, n in enumerate(fixed[:3])]
                               + [("NodeResidualPlaneGoal", int(nodes[fixed[3 % len(fixed)]]), [0.2, 1.0, 0.3], 2.0)]),
+        ("SquaredError", 0.9, [("EdgeDirectionGoal", ekey(e), [0.3, 1.0, -0.2], 1.0) for e in pick_e[:4]]
+                              + [("EdgeAngleGoal", ekey(e), (0.4 + 0.1 * j, [0.0, 0.2, 1.0]), 1.5) for j, e in enumerate(pick_e[4:8])]),
         ("AbsoluteError", 0.4, [("NodeLineGoal", int(nodes[pick_n[4]]), [prob.xyz0[pick_n[4]] + [0.3, 0.2, -0.4], prob.xyz0[pick_n[4]] + [-1.0, 1.5, 2.0]], 1.0),
                                 ("NodePlaneGoal", int(nodes[pick_n[5]]), [prob.xyz0[pick_n[5]] + [0.1, 0.0, 0.3], [1.0, 0.5, 0.25]], 2.0)]),
     ]
@@ -62,10 +64,13 @@ def build_loss(prob, s, rng):
         gl, ol = [], []
         for gname, key, target, weight in goals:
             cls = getattr(G, gname)
-            g = cls(target=target, weight=weight) if gname == "NetworkLoadPathGoal" else cls(key, target, weight)
+            if gname == "EdgeAngleGoal":
+                g = cls(key, target[0], weight, vector=target[1])
+            else:
+                g = cls(target=target, weight=weight) if gname == "NetworkLoadPathGoal" else cls(key, target, weight)
             gl.append(g)
             idx = 0 if gname == "NetworkLoadPathGoal" else (ni[key] if isinstance(key, int) else ei[key])
-            ol.append((gname, idx, np.asarray(target, dtype=np.float64), weight))
+            ol.append((gname, idx, target if gname == "EdgeAngleGoal" else np.asarray(target, dtype=np.float64), weight))
         terms.append(getattr(LS, ename)(gl, alpha=alpha))
         oterms.append((ename, ol, alpha))
     l2 = 1e-3

@@ -14,7 +14,7 @@ from .models import EquilibriumModel, EquilibriumModelSparse
 from .states import EquilibriumParametersState, LoadState
 from .structures import EquilibriumStructure, EquilibriumStructureSparse
 
-__all__ = ["fdm", "model_from_sparsity", "structure_from_arrays", "arrays_validate"]
+__all__ = ["fdm", "constrained_fdm", "model_from_sparsity", "structure_from_arrays", "arrays_validate"]
 
 
 def arrays_validate(edges, supports, q):
@@ -49,3 +49,26 @@ def fdm(nodes, edges, supports, q, xyz_fixed, loads, sparse=True, tmax=1, eta=1e
         torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
     params = EquilibriumParametersState(as_t(q), as_t(xyz_fixed), LoadState(as_t(loads), 0.0, 0.0))
     return model(params, structure), structure
+
+
+def constrained_fdm(nodes, edges, supports, q, xyz_fixed, loads, optimizer, loss, bounds=(None, None), maxiter=100,
+                    tol=1e-6, sparse=True, tmax=1, eta=1e-6, is_load_local=False, device=0, structure=None,
+                    callback=None, **solve_opts):
+    """
+    `constrained_fdm` on arrays (fdm.py:177-308) with the force densities as the parameters: minimise `loss`
+    over q within `bounds` with `optimizer` (jax_fdm_b200.optimization: LBFGSB, SLSQP, ...), then one forward
+    solve at the optimum.  Returns (EquilibriumState, structure, q_opt).  Every optimiser iteration is one
+    forward + adjoint pass on the device; constraints (which the reference routes through the dense model and
+    forward mode, fdm.py:266-271) are outside this build.
+    """
+    q0 = q.detach().cpu().numpy() if isinstance(q, torch.Tensor) else np.asarray(q, dtype=np.float64)
+    arrays_validate(edges, supports, q0)
+    model = model_from_sparsity(sparse, tmax=tmax, eta=eta, is_load_local=is_load_local, **solve_opts)
+    if structure is None:
+        structure = structure_from_arrays(nodes, edges, supports, sparse, device)
+    problem = optimizer.problem(model, structure, loss, q0, xyz_fixed, loads, bounds=bounds, maxiter=maxiter, tol=tol,
+                                callback=callback)
+    q_opt = optimizer.solve(problem)
+    state, _ = fdm(nodes, edges, supports, q_opt, xyz_fixed, loads, sparse=sparse, tmax=tmax, eta=eta,
+                   is_load_local=is_load_local, device=device, structure=structure, **solve_opts)
+    return state, structure, q_opt

@@ -36,25 +36,63 @@ class Optimizer:
         self.disp = disp
 
     def problem(self, model, structure, loss, q0, xyz_fixed, loads, bounds=(None, None), maxiter=100, tol=1e-6,
-                callback=None):
+                callback=None, opt_xyz_fixed=None, bounds_xyz_fixed=(None, None), opt_loads=None,
+                bounds_loads=(None, None)):
+        """
+        The flat parameter vector is [q, xyz_fixed[opt_xyz_fixed], loads[opt_loads]]: every force density, plus
+        the support coordinates and nodal load components selected by the boolean masks (Ns,3) / (N,3) -- the
+        parameter kinds of the reference (parameters/parameters.py: EdgeForceDensityParameter,
+        NodeSupport{X,Y,Z}Parameter, NodeLoad{X,Y,Z}Parameter), as in its gridshell inverse-design examples.
+        """
         dev = torch.device("cuda", structure.device) if isinstance(structure.device, int) else torch.device(structure.device)
-        xs = torch.as_tensor(np.ascontiguousarray(xyz_fixed, dtype=np.float64), device=dev)
-        p = torch.as_tensor(np.ascontiguousarray(loads, dtype=np.float64), device=dev)
-        load_state = p if isinstance(loads, LoadState) else LoadState(p, 0.0, 0.0)
+        xs0 = np.ascontiguousarray(xyz_fixed, dtype=np.float64)
+        p0 = np.ascontiguousarray(loads, dtype=np.float64)
+        x0 = np.ascontiguousarray(q0, dtype=np.float64)
+        nq = x0.size
+        mxs = None if opt_xyz_fixed is None else np.asarray(opt_xyz_fixed, dtype=bool).reshape(xs0.shape)
+        mp = None if opt_loads is None else np.asarray(opt_loads, dtype=bool).reshape(p0.shape)
+        nxs = 0 if mxs is None else int(mxs.sum())
+        xs_t = torch.as_tensor(xs0, device=dev)
+        p_t = torch.as_tensor(p0, device=dev)
+        mxs_t = None if mxs is None else torch.as_tensor(mxs, device=dev)
+        mp_t = None if mp is None else torch.as_tensor(mp, device=dev)
+
+        def unpack(x):
+            """x (numpy) -> q, xyz_fixed, loads as leaf tensors on the device."""
+            xt = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
+            q = xt[:nq].clone().requires_grad_(True)
+            xs, p = xs_t, p_t
+            if mxs_t is not None:
+                xs = xs_t.clone()
+                xs[mxs_t] = xt[nq:nq + nxs]
+            if mp_t is not None:
+                p = p_t.clone()
+                p[mp_t] = xt[nq + nxs:]
+            return q, xs.requires_grad_(mxs_t is not None), p.requires_grad_(mp_t is not None)
 
         def loss_and_grad(x):                            # optimizer.py:365-370: jit(value_and_grad(loss))
-            q = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev).requires_grad_(True)
-            val = loss(EquilibriumParametersState(q, xs, load_state), model, structure)
+            q, xs, p = unpack(x)
+            val = loss(EquilibriumParametersState(q, xs, LoadState(p, 0.0, 0.0)), model, structure)
             val.backward()
-            return float(val.item()), q.grad.detach().cpu().numpy()
+            grads = [q.grad]
+            if mxs_t is not None:
+                grads.append(xs.grad[mxs_t])
+            if mp_t is not None:
+                grads.append(p.grad[mp_t])
+            return float(val.item()), torch.cat([g.reshape(-1) for g in grads]).cpu().numpy()
 
-        x0 = np.ascontiguousarray(q0, dtype=np.float64)
+        parts = [x0] + ([xs0[mxs]] if mxs is not None else []) + ([p0[mp]] if mp is not None else [])
+        x0 = np.concatenate([a.reshape(-1) for a in parts])
         val, grad = loss_and_grad(x0)                    # optimizer.py:372-380: warm start, no NaN allowed
         assert np.isfinite(val) and np.all(np.isfinite(grad)), "the loss or its gradient is not finite at x0"
-        lo, hi = bounds
-        lo = np.broadcast_to(-np.inf if lo is None else lo, x0.shape)
-        hi = np.broadcast_to(np.inf if hi is None else hi, x0.shape)
-        return OptProblem(loss_and_grad, x0, list(zip(lo, hi)), self.name, tol, maxiter, callback)
+        bnds = []
+        for (lo, hi), n in ((bounds, nq), (bounds_xyz_fixed, nxs), (bounds_loads, x0.size - nq - nxs)):
+            lo = np.broadcast_to(-np.inf if lo is None else lo, (n,))
+            hi = np.broadcast_to(np.inf if hi is None else hi, (n,))
+            bnds += list(zip(lo, hi))
+        prob = OptProblem(loss_and_grad, x0, bnds, self.name, tol, maxiter, callback)
+        prob.unpack = lambda x: tuple(t.detach().cpu().numpy() for t in unpack(x))
+        return prob
 
     def solve(self, opt_problem):
         from scipy.optimize import minimize

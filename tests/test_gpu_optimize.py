@@ -92,3 +92,47 @@ def test_constrained_fdm_on_arrays():
     e0 = float(((s0.lengths - 0.55) ** 2).sum())
     e1 = float(((state.lengths - 0.55) ** 2).sum())
     assert e1 <= 1e-2 * e0 and q_opt.shape == prob.q.shape and np.all(q_opt < 0)
+
+
+def test_inverse_design_over_q_supports_and_loads():
+    """BASELINE config 3 in miniature (gridshell inverse design over q, loads and supports with vertex goals):
+    the flat parameter vector [q, z of the supports, z of the free nodes' loads], point goals on the free
+    nodes.  The gradient of the packed loss against central differences of the oracle, then L-BFGS-B."""
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import goals as G, losses as LS
+    from jax_fdm_b200.optimization import LBFGSB
+
+    prob = datasets.pillow_problem(6)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+    free = np.flatnonzero(prob.supports == 0)
+    rng = np.random.default_rng(3)
+    target = prob.xyz0[free] + np.c_[np.zeros((free.size, 2)), 0.6 + 0.3 * np.sin(prob.xyz0[free, 0])]
+    loss = LS.Loss(LS.MeanSquaredError([G.VertexPointGoal(int(prob.nodes[n]), t) for n, t in zip(free, target)]),
+                   LS.L2Regularizer(1e-5))
+    model = eq.EquilibriumModelSparse(tmax=1)
+    mxs = np.zeros(prob.xyz_fixed.shape, dtype=bool); mxs[:, 2] = True
+    mp = np.zeros(prob.loads.shape, dtype=bool); mp[free, 2] = True
+    opt = LBFGSB()
+    problem = opt.problem(model, s, loss, prob.q, prob.xyz_fixed, prob.loads, bounds=(-20.0, -0.05), maxiter=200, tol=1e-10,
+                          opt_xyz_fixed=mxs, bounds_xyz_fixed=(-1.0, 2.0), opt_loads=mp, bounds_loads=(-1.0, 1.0))
+    x0 = problem.x0
+    assert x0.size == prob.q.size + mxs.sum() + mp.sum()
+    oterms = [("MeanSquaredError", [("NodePointGoal", int(n), t, 1.0) for n, t in zip(free, target)], 1.0)]
+
+    def f(x):
+        q, xs, p = problem.unpack(x)
+        st, _ = oracle.forward(q, xs, p, so)
+        return og.loss(oterms, st, q=q, l2_alpha=1e-5)
+
+    val, grad = problem.fun(x0)
+    assert abs(val - f(x0)) <= 1e-12 * abs(val)
+    scale = np.abs(grad).max()
+    for k in rng.choice(x0.size, size=15, replace=False):
+        d = np.zeros_like(x0); d[k] = 1e-6
+        fd = (f(x0 + d) - f(x0 - d)) / 2e-6
+        assert abs(grad[k] - fd) <= 1e-6 * scale + 1e-10, (k, grad[k], fd)
+    x = opt.solve(problem)
+    assert opt.result.fun <= 0.05 * val
+    lo = np.array([b[0] for b in problem.bounds]); hi = np.array([b[1] for b in problem.bounds])
+    assert np.all(x >= lo - 1e-12) and np.all(x <= hi + 1e-12)

@@ -136,3 +136,49 @@ def test_inverse_design_over_q_supports_and_loads():
     assert opt.result.fun <= 0.05 * val
     lo = np.array([b[0] for b in problem.bounds]); hi = np.array([b[1] for b in problem.bounds])
     assert np.all(x >= lo - 1e-12) and np.all(x <= hi + 1e-12)
+
+
+def test_liew_dome_inverse_design_steps():
+    """BASELINE config 3 on the reference's own dome (tests/data/liew_dome.json through tests/golden/liew_dome.npz):
+    vertex point goals 10 % above the form-found heights, parameters q + support z + nodal load z; a few
+    L-BFGS-B iterations must cut the loss, and the packed gradient must match the oracle's finite differences."""
+    import os
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import goals as G, losses as LS
+    from jax_fdm_b200.optimization import LBFGSB
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "liew_dome.npz")))
+    nodes, edges, supports = g["nodes"], g["edges"], g["supports"]
+    s = eq.EquilibriumStructureSparse(nodes, edges, supports, device=0)
+    so = oracle.build_structure(nodes, edges, supports)
+    free = np.flatnonzero(supports == 0)
+    xyz_ref = g["ref_state_xyz"]
+    target = xyz_ref[free] * np.array([1.0, 1.0, 1.1])
+    loss = LS.Loss(LS.MeanSquaredError([G.VertexPointGoal(int(nodes[n]), t) for n, t in zip(free, target)]))
+    model = eq.EquilibriumModelSparse(tmax=1)
+    mxs = np.zeros(g["xyz_fixed"].shape, dtype=bool); mxs[:, 2] = True
+    mp = np.zeros(g["loads"].shape, dtype=bool); mp[free, 2] = True
+    qsign = np.sign(g["q"][0])
+    qb = (-1e3, -1e-3) if qsign < 0 else (1e-3, 1e3)
+    opt = LBFGSB()
+    problem = opt.problem(model, s, loss, g["q"], g["xyz_fixed"], g["loads"], bounds=qb, maxiter=15, tol=1e-12,
+                          opt_xyz_fixed=mxs, opt_loads=mp)
+    x0 = problem.x0
+    oterms = [("MeanSquaredError", [("NodePointGoal", int(n), t, 1.0) for n, t in zip(free, target)], 1.0)]
+
+    def f(x):
+        q, xs, p = problem.unpack(x)
+        st, _ = oracle.forward(q, xs, p, so)
+        return og.loss(oterms, st)
+
+    val, grad = problem.fun(x0)
+    assert abs(val - f(x0)) <= 1e-10 * abs(val)
+    rng = np.random.default_rng(0)
+    scale = np.abs(grad).max()
+    for k in rng.choice(x0.size, size=8, replace=False):
+        h = 1e-6 * max(1.0, abs(x0[k]))
+        d = np.zeros_like(x0); d[k] = h
+        fd = (f(x0 + d) - f(x0 - d)) / (2 * h)
+        assert abs(grad[k] - fd) <= 1e-5 * scale + 1e-10, (k, grad[k], fd)
+    opt.solve(problem)
+    assert opt.result.fun <= 0.5 * val

@@ -297,7 +297,8 @@ def run_ours(args):
     lo, hi = shard_range(B * world, rank, world)
     qb = datasets.pillow_batch_q(prob.edges.shape[0], lo, hi - lo)
     x0 = prob.xyz0[s.indices_free]
-    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local)
+    # launch-by-launch table: the unfused sequence (assembly kernel, then the solve on K.data)
+    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local, fused_assembly=False)
     pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
     e2e_pipe = ChunkedForwardAdjoint(s, B, chunks=E2E_CHUNKS, solver="cholesky", device=local)
     e2e_pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
@@ -468,7 +469,9 @@ def run_ours(args):
                    "per_gpu_batch": B, "global_batch": B * world, "solver": "batched band Cholesky, one warp per design",
                    "l2": "flushed between timed steps (256 MiB write, outside the events)",
                    "device_step": f"{DEV_CHUNKS} slices of the batch on their own streams, forked from and joined to the "
-                                  "timed stream (CUDA events on it bracket the whole step)",
+                                  "timed stream (CUDA events on it bracket the whole step); the factorisation "
+                                  "assembles its rows from q in place (fdm_solve_from_q), the `kernels` table times "
+                                  "the unfused launches",
                    "parallelism": f"designs sharded x{world}, no data-path collective"
                                   + (", 8-byte loss all-reduce (NCCL) per step" if world > 1 else "")},
         "clocks": clocks,

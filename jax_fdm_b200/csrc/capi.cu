@@ -24,7 +24,7 @@ void free_device(fdm_plan* p) {
   void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
                   d.band_iperm, d.band_kidx, d.band_rowkidx, d.diags_ptr, d.diags_idx, d.sup_mask,
-                  d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent};
+                  d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent, d.band_row_diag, d.band_row_sup, d.band_row_node};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   d = DeviceArrays();
@@ -120,6 +120,9 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->band_stage_ptr, &q->d.band_stage_ptr); },
         [](fdm_plan* q) { return upload(q->band_stage_kent, &q->d.band_stage_kent); },
         [](fdm_plan* q) { return upload(q->band_stage_eent, &q->d.band_stage_eent); },
+        [](fdm_plan* q) { return upload(q->band_row_diag, &q->d.band_row_diag); },
+        [](fdm_plan* q) { return upload(q->band_row_sup, &q->d.band_row_sup); },
+        [](fdm_plan* q) { return upload(q->band_row_node, &q->d.band_row_node); },
         [](fdm_plan* q) { return upload(q->diags_indptr, &q->d.diags_ptr); },
         [](fdm_plan* q) { return upload(q->diags_indices, &q->d.diags_idx); },
         [](fdm_plan* q) { return upload(q->sup_mask, &q->d.sup_mask); },

@@ -308,6 +308,9 @@ void fdm_build_band_order(fdm_plan& p) {
   p.band_stage_ptr.clear();
   p.band_stage_kent.clear();
   p.band_stage_eent.clear();
+  p.band_row_diag.clear();
+  p.band_row_sup.clear();
+  p.band_row_node.clear();
   if (p.hbw <= 31) {
     const int64_t rows = ((int64_t)(n + 31) / 32 + 1) * 32;
     p.band_rowkidx.assign((size_t)rows * 32, -1);
@@ -352,6 +355,33 @@ void fdm_build_band_order(fdm_plan& p) {
       }
     }
     p.band_stage_ptr[(size_t)blocks] = (int32_t)(p.band_stage_kent.size() / 64);
+    // per band row, padded and vector-loadable: what the row needs from q, x_s and loads when the factorisation
+    // assembles it in place -- the same terms, in the same order, as the assembly kernel adds them
+    p.band_row_diag.assign((size_t)rows * 8, -1);
+    p.band_row_sup.assign((size_t)rows * 8, -1);
+    p.band_row_node.assign((size_t)rows, -1);
+    for (int32_t R = 0; R < n; ++R) {
+      const int32_t f = p.band_iperm[R];
+      const int32_t node = p.free_node[f];
+      p.band_row_node[(size_t)R] = node;
+      const int32_t d0 = p.diags_indptr[f], d1 = p.diags_indptr[f + 1];
+      if (d1 - d0 > 8) p.band_row_diag[(size_t)R * 8] = -2;
+      else for (int32_t k = d0; k < d1; ++k) p.band_row_diag[(size_t)R * 8 + (k - d0)] = p.diags_indices[k];
+      int32_t cnt = 0;
+      bool overflow = false;
+      for (int32_t k = p.ninc_ptr[node]; k < p.ninc_ptr[node + 1]; ++k) {
+        const int32_t slot = p.node_slot[p.ninc_other[k]];
+        if (slot >= 0) continue;
+        if (cnt == 4) { overflow = true; break; }
+        p.band_row_sup[(size_t)R * 8 + 2 * cnt] = p.ninc_edge[k] >> 1;
+        p.band_row_sup[(size_t)R * 8 + 2 * cnt + 1] = -slot - 1;
+        ++cnt;
+      }
+      if (overflow) {
+        for (int j = 0; j < 8; ++j) p.band_row_sup[(size_t)R * 8 + j] = -1;
+        p.band_row_sup[(size_t)R * 8] = -2;
+      }
+    }
   }
 }
 

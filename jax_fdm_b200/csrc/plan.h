@@ -31,6 +31,10 @@ struct DeviceArrays {
   // the same two tables without their zeros: per 32-row block, groups of 32 (position, index) pairs
   int32_t* band_stage_ptr = nullptr;   // (ceil(Nf/32)+2) first group of every block
   int32_t* band_stage_kent = nullptr;  // (groups*32, 2): r*32 + slot, position in K.data | -2 one | -4 padding
+  // per band row (padded rows), for the factorisation that assembles its rows from q (fdm_solve_from_q):
+  int32_t* band_row_diag = nullptr;    // (rows, 8)  incident edge ids in ascending order, -1 padded; [0] = -2: list too long, walk `diags`
+  int32_t* band_row_sup = nullptr;     // (rows, 8)  up to 4 (edge id, fixed index) pairs in incidence order, -1 padded; [0] = -2: walk the incidence list
+  int32_t* band_row_node = nullptr;    // (rows)     node id of the row, -1 for padding rows
   int32_t* band_stage_eent = nullptr;  // (groups*32, 2): r*32 + slot, edge id | -1 zero (diagonal) | -2 one | -4 padding
   // two-level persistent PCG (solver_pcg_persistent.cu); built lazily by the host
   void* pcg2 = nullptr;
@@ -55,6 +59,7 @@ struct fdm_plan {
   std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx;
   std::vector<int32_t> band_rowedge;   // host only: band_rowkidx in terms of edge ids (-3 diagonal), source of band_stage_eent
   std::vector<int32_t> band_stage_ptr, band_stage_kent, band_stage_eent;
+  std::vector<int32_t> band_row_diag, band_row_sup, band_row_node;
   int32_t hbw = 0;
 
   // aggregates for the two-level preconditioner

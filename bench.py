@@ -489,7 +489,9 @@ def run_ours(args):
                      "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm, "traffic": NCU_TRAFFIC_CHOL_FWD,
                      "peak_source": hbm_src, "kernel_ms": dom["ms"],
                      "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
-                     "share_of_step": dom["ms"] / ms_per_step},
+                     "share_of_step": dom["ms"] / ms_per_step,
+                     "note": "timed alone on K.data (template instance <FROM_Q=0>); inside the step the <FROM_Q=1> "
+                             "instance runs, which reads q (15 KB per design) instead of K.data (33 KB)"},
         "kernels": kernels,
         "wall_s_timed_region": wall,
         "solve_status_ok": status_ok and (single is None or single["status"] == [0, 0]),

@@ -167,3 +167,22 @@ def test_fused_assembly_is_bit_identical_to_assemble_then_solve():
         lam_ref = eq.ops.solve(s, K, g, solver="cholesky")     # forward substitution fused in the factor kernel:
         err = (lam - lam_ref).abs().max() / lam_ref.abs().max()  # another summation order, not bit-identical
         assert err <= 1e-12
+
+
+def test_fused_assembly_with_per_design_supports_and_loads():
+    """fdm_solve_from_q with (B,Ns,3) support positions and (B,N,3) loads (non-zero strides), and a structure whose
+    boundary rows have several support neighbours: bit-identical to fdm_assemble + fdm_solve."""
+    import jax_fdm_b200.equilibrium as eq
+
+    for prob in (datasets.pillow_problem(9), datasets.cablenet_problem(7, seed=3)):
+        s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+        rng = np.random.default_rng(5)
+        B = 19
+        qb = prob.q[None, :] * rng.uniform(0.7, 1.4, size=(B, prob.q.size))
+        xs = prob.xyz_fixed[None] + 0.05 * rng.standard_normal((B,) + prob.xyz_fixed.shape)
+        ld = prob.loads[None] + 0.02 * rng.standard_normal((B,) + prob.loads.shape)
+        q, xs_t, p = T(qb), T(xs), T(ld)
+        K, rhs = eq.ops.assemble(s, q, xs_t, p)
+        x_ref = eq.ops.solve(s, K, rhs, solver="cholesky")
+        x = eq.ops.solve_from_q(s, q, xs_t, p)
+        assert x is not None and torch.equal(x, x_ref)

@@ -3,9 +3,16 @@
 // batches of small designs that share one topology, and the adjoint solve of
 // sparse_solve_bwd (sparse.py:296) with the factor reused instead of recomputed.
 //
-// Two kernels:
+// Kernels:
 //
-// chol_factor_kernel  factorisation + fused forward substitution.  Band order = plan.band_perm.
+// chol_factor_mma_kernel<FROM_Q, PW, SIGNED>  (half bandwidth <= 30) factorisation + fused forward substitution
+//   on the FP64 tensor pipe, see the comment above the kernel: the trailing window in registers as 8x8 tiles,
+//   PW = 4 or 2 columns per panel, the right-hand sides as extra window rows (PW = 4), the diagonal 8x8 blocks
+//   of every 32-column block inverted in place; FROM_Q assembles its rows from q (fdm_solve_from_q); SIGNED is
+//   the second pass over designs with a non-positive pivot (sigma K = L D L^T).
+//
+// chol_factor_kernel<KMAX>  (half bandwidth 31, and the A/B reference) the same factorisation with rank-1 updates.
+//   Band order = plan.band_perm.
 //   Lane (R & 31) owns row R of the lower triangle while R is inside the 32-row window [j, j+32)
 //   of the right-looking factorisation; the row lives in 32 REGISTERS, slot (C & 31) holding
 //   A(R, C).  Step j:
@@ -246,18 +253,26 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
 // ===========================================================================================
 // factorisation + fused forward substitution, FP64 tensor-core trailing updates (hbw <= 30)
 //
-// The 32x32 trailing window (rows / columns j..j+31, slot = index & 31, full symmetric storage) lives
-// in REGISTERS as 4x4 tiles of 8x8 in the accumulator layout of mma.sync.m8n8k4.f64: lane
-// (g = lane>>2, m = lane&3) holds rows 8tr+g, columns 8tc+2m and 8tc+2m+1 of every tile.  Columns
-// are eliminated two at a time:
-//   1. the two panel columns go through shared memory to a lanes = rows layout; two pivots
-//      (shuffle, rsqrt), the 1x1 update between them, the two columns of L            [FP64 FMA pipe]
-//   2. forward substitution of the three right-hand sides with those two columns
-//   3. the factor records (rotated, see FROT) and the 8x8 diagonal block of the column group
-//   4. the panel goes back through shared memory as mma A/B fragments (k = 2 of 4 used) and the
-//      whole window gets W -= L_panel L_panel^T as independent DMMAs (16; 10 with four-column panels,
-//      which keep only the tiles on and below the diagonal)                          [FP64 tensor pipe]
-//   5. the two retired rows and columns are refilled with rows j+32, j+33 from the staged block
+// The 32x32 trailing window (rows / columns j..j+31, slot = index & 31, symmetric) lives in REGISTERS as
+// tiles of 8x8 in the accumulator layout of mma.sync.m8n8k4.f64: lane (g = lane>>2, m = lane&3) holds rows
+// 8tr+g, columns 8tc+2m and 8tc+2m+1 of tile (tr, tc).
+//
+// PW = 4 (half bandwidth <= 29), four columns per panel; only the tiles on and below the diagonal are kept and
+// the three right-hand sides are a fifth tile row Y (rows 32..34):
+//   1. the four panel columns (and the right-hand sides' entries in them) go through the shared-memory exchange
+//      to a lanes = rows layout; rows of tile rows above the panel's come from the transposed tiles
+//   2. every lane reads the 4x4 pivot block from the exchange and factors it redundantly (four rsqrt, no
+//      shuffle on the chain), then computes its own row of the four columns of L            [FP64 FMA pipe]
+//   3. lanes (g < 3, m) run the four pivot columns on right-hand side g: w_m is lane (g, m)'s mma A fragment
+//      and the solved entry of column j+m (stored once per panel)
+//   4. the factor records (rotated, see FROT)
+//   5. rows / columns j+32..j+35 REFILL the four retired slots from the staged block
+//   6. the panel P (incoming rows: zeros, except L(j+32, j+3) for row j+32) goes back through the exchange as
+//      A/B fragments: W -= P P^T as 10 DMMAs, Y -= w P^T as 4 more (all four k slices used) [FP64 tensor pipe]
+// After the 8 panels of a 32-column block the block's four 8x8 diagonal blocks are inverted in place.
+//
+// PW = 2 (half bandwidth 30), two columns per panel, full window, right-hand sides in per-lane registers:
+//   pivots by shuffle, forward substitution by shuffle, update (k = 2 of 4 used, 16 DMMAs), then refill.
 // Out-of-band entries of the window stay exactly zero (an update needs both factors non-zero).
 // ===========================================================================================
 constexpr int kMS = 36;                                  // staged row: 32 column slots + 3 right-hand sides + pad

@@ -121,8 +121,9 @@ class _FusedFreePositions(torch.autograd.Function):
     def forward(ctx, q, xyz_fixed, loads, structure, opts):
         ws = ops.Workspace()
         x = K = None
-        if opts.get("fused_assembly", False) and opts.get("solver", "auto") in ("auto", "cholesky"):
-            x = ops.solve_from_q(structure, q, xyz_fixed, loads, workspace=ws)   # batched designs: K never materialised
+        if opts.get("fused_assembly", True) and opts.get("solver", "auto") in ("auto", "cholesky"):
+            # batched designs on a narrow band: K is never materialised (None when this structure / batch is not served)
+            x = ops.solve_from_q(structure, q, xyz_fixed, loads, workspace=ws, nan_on_failure=True)
         if x is None:
             opts = {k: v for k, v in opts.items() if k != "fused_assembly"}
             K, rhs = ops.assemble(structure, q, xyz_fixed, loads)

@@ -131,7 +131,7 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     return (x, info) if return_info else x
 
 
-def solve_from_q(structure, q, xyz_fixed, loads, workspace=None, return_info=False):
+def solve_from_q(structure, q, xyz_fixed, loads, workspace=None, return_info=False, nan_on_failure=False):
     """
     K1 + K2 fused: x_free = K(q)^{-1} (loads_f - C_f^T Q C_s xyz_fixed) without materialising K.data
     (models.py:222-256).  Returns None when this structure / batch is not served by the in-place
@@ -158,6 +158,9 @@ def solve_from_q(structure, q, xyz_fixed, loads, workspace=None, return_info=Fal
     if rc == -5:          # FDM_ERR_UNSUPPORTED
         return None
     L.check(rc)
+    if nan_on_failure:    # as in `solve`
+        failed = (info[:, 0] != 0).view((B, 1, 1) if x.dim() == 3 else (1, 1))
+        x = torch.where(failed, torch.full_like(x, float("nan")), x)
     return (x, info) if return_info else x
 
 

@@ -138,8 +138,12 @@ class _Program:
         kind, index, err, weight, target, gptr, gfinal, ginner, gouter = [], [], [], [], [], [0], [], [], []
         for term in errors:
             for g in term.goals:
+                i = int(g.index(structure))
+                limit = structure.num_edges if g.kind in (3, 4, 5, 15, 16) else structure.num_nodes
+                if not 0 <= i < limit:                      # the kernel trusts the table
+                    raise IndexError(f"{type(g).__name__}: element index {i} outside [0, {limit})")
                 kind.append(g.kind)
-                index.append(g.index(structure))
+                index.append(i)
                 err.append(term.err_kind)
                 weight.append(g.weight)
                 t = np.zeros(6)

@@ -272,6 +272,9 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *           residual against the unit target / against its projection on the plane with normal target[0:3]
  *        15 EdgeDirectionGoal (goals/edge/direction.py): unit edge vector xyz[head]-xyz[tail] vs unit target
  *        16 EdgeAngleGoal (goals/edge/angle.py): angle between the edge vector and target[1:4] vs target[0]
+ *        17 EdgesLengthEqualGoal (goals/edge/length.py:49-75): var(lengths[S]) / mean(lengths[S]) over the edge
+ *           set S = agg_index[agg_ptr[t] .. agg_ptr[t+1]); 18 EdgesForceEqualGoal (goals/edge/force.py:49-75):
+ *           var(forces[S]) / mean(|forces[S]|); index[t] = running number of the aggregate goal (< 16)
  *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
  *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
  * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):
@@ -280,7 +283,7 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *   of RootMeanSquaredError (errors.py:262-300).
  * All arrays of the program are DEVICE pointers shared by the batch. */
 typedef struct fdm_goal_program {
-  int32_t num_terms, num_groups, has_network_loadpath;
+  int32_t num_terms, num_groups, has_network_loadpath, num_aggregates;
   const int32_t* kind;        /* (T) */
   const int32_t* index;       /* (T) node or edge index (structure order) */
   const int32_t* error;       /* (T) */
@@ -290,6 +293,8 @@ typedef struct fdm_goal_program {
   const int32_t* group_final; /* (G) */
   const double* group_inner;  /* (G) */
   const double* group_outer;  /* (G) */
+  const int32_t* agg_ptr;     /* (T+1) element sets of the aggregate goals (empty ranges for the others), or NULL */
+  const int32_t* agg_index;   /* (sum of set sizes) */
 } fdm_goal_program;
 
 /* loss (B); group_sums (B,G) or NULL.  With the four cotangent arrays (all or none) the kernel also

@@ -42,9 +42,10 @@ class SolveOpts(C.Structure):
 class GoalProgram(C.Structure):
     """fdm_goal_program (include/fdm_b200.h): device pointers of a compiled Loss."""
     _fields_ = [("num_terms", C.c_int32), ("num_groups", C.c_int32), ("has_network_loadpath", C.c_int32),
-                ("kind", C.c_void_p), ("index", C.c_void_p), ("error", C.c_void_p), ("weight", C.c_void_p),
+                ("num_aggregates", C.c_int32), ("kind", C.c_void_p), ("index", C.c_void_p), ("error", C.c_void_p), ("weight", C.c_void_p),
                 ("target", C.c_void_p), ("group_ptr", C.c_void_p), ("group_final", C.c_void_p),
-                ("group_inner", C.c_void_p), ("group_outer", C.c_void_p)]
+                ("group_inner", C.c_void_p), ("group_outer", C.c_void_p), ("agg_ptr", C.c_void_p),
+                ("agg_index", C.c_void_p)]
 
 
 class FdmError(RuntimeError):

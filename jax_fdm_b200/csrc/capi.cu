@@ -379,6 +379,10 @@ int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* x
     fdm_set_error("fdm_goals_loss: bad arguments");
     return FDM_ERR_INVALID;
   }
+  if (g->num_aggregates > 16 || (g->num_aggregates > 0 && (!g->agg_ptr || !g->agg_index))) {
+    fdm_set_error("fdm_goals_loss: at most 16 aggregate goals per loss, with their element sets");
+    return FDM_ERR_UNSUPPORTED;
+  }
   if (g->num_groups > 64) {
     fdm_set_error("fdm_goals_loss: more than 64 error terms in one loss");
     return FDM_ERR_UNSUPPORTED;
@@ -389,7 +393,8 @@ int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* x
     return FDM_ERR_INVALID;
   }
   return launch_goals_loss(p, g->num_terms, g->kind, g->index, g->error, g->weight, g->target, g->num_groups,
-                           g->group_ptr, g->group_final, g->group_inner, g->group_outer, g->has_network_loadpath, xyz,
+                           g->group_ptr, g->group_final, g->group_inner, g->group_outer, g->has_network_loadpath,
+                           g->agg_ptr, g->agg_index, xyz,
                            lengths, forces, residuals, loss, group_sums, xyz_bar, lengths_bar, forces_bar, residuals_bar,
                            batch, (cudaStream_t)stream);
 }

@@ -41,13 +41,17 @@ enum GoalKind : int {
   G_NODE_RESIDUAL_PLANE,      // the same unit vector vs its projection on the plane through 0 with normal target (3)
   G_EDGE_DIRECTION,           // unit edge vector (xyz[head] - xyz[tail]) vs target / |target|          (3)
   G_EDGE_ANGLE,               // angle between the edge vector and target[1:4] vs target[0]             (1)
+  G_EDGES_LENGTH_EQUAL,       // var(lengths[S]) / mean(lengths[S]) over the edge set S of the term (index = aggregate slot)
+  G_EDGES_FORCE_EQUAL,        // var(forces[S]) / mean(|forces[S]|)
 };
+constexpr int kMaxAgg = 16;    // aggregate goals per loss
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
 
 struct GoalArgs {
   int T, G, N, E;
   const int32_t *kind, *index, *err, *group_ptr;   // (T), (T), (T), (G+1)
   const int32_t* edge_nodes;                       // plan: (E,2) tail, head
+  const int32_t *agg_ptr, *agg_index;              // (T+1), (sum of set sizes): element sets of the aggregate goals
   const double *weight, *target;                   // (T), (T,6)
   const int32_t* gfinal;                           // (G) 0 identity, 1 sqrt
   const double *ginner, *gouter;                   // (G)
@@ -177,6 +181,31 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     for (int e = threadIdx.x; e < A.E; e += kThreads) acc += fabs(len[e] * frc[e]);
     loadpath = block_sum(acc, red);
   }
+  // aggregate goals (goals/edge/length.py:49-75, force.py:49-75): p = var(v) / M over the term's edge set, v = lengths
+  // (M = mean v) or forces (M = mean |v|); evaluated by the whole CTA, kept per aggregate slot for both passes
+  __shared__ double s_aggp[kMaxAgg], s_aggmu[kMaxAgg], s_aggV[kMaxAgg], s_aggM[kMaxAgg];
+  if (A.agg_ptr) {
+    for (int t = 0; t < A.T; ++t) {
+      const int k = A.kind[t];
+      if (k < G_EDGES_LENGTH_EQUAL) continue;
+      const double* v = k == G_EDGES_LENGTH_EQUAL ? len : frc;
+      const int a0 = A.agg_ptr[t], a1 = A.agg_ptr[t + 1], n = a1 - a0;
+      double s1 = 0.0, sa = 0.0;
+      for (int j = a0 + threadIdx.x; j < a1; j += kThreads) { const double x = v[A.agg_index[j]]; s1 += x; sa += fabs(x); }
+      s1 = block_sum(s1, red);
+      sa = block_sum(sa, red);
+      const double mu = s1 / n;
+      double s2 = 0.0;
+      for (int j = a0 + threadIdx.x; j < a1; j += kThreads) { const double x = v[A.agg_index[j]] - mu; s2 += x * x; }
+      s2 = block_sum(s2, red);
+      if (threadIdx.x == 0) {
+        const int slot = A.index[t];
+        const double V = s2 / n, M = k == G_EDGES_LENGTH_EQUAL ? mu : sa / n;
+        s_aggp[slot] = V / M; s_aggmu[slot] = mu; s_aggV[slot] = V; s_aggM[slot] = M;
+      }
+    }
+    __syncthreads();
+  }
   auto predict = [&](int k, int i, const double* t, double (&p)[3]) -> int {   // returns the number of components
     switch (k) {
       case G_NODE_POINT: case G_NODE_LINE: case G_NODE_PLANE: case G_NODE_SEGMENT:
@@ -200,6 +229,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       case G_EDGE_FORCE: p[0] = frc[i]; return 1;
       case G_EDGE_LOADPATH: p[0] = fabs(frc[i]) * len[i]; return 1;
       case G_NODE_X: case G_NODE_Y: case G_NODE_Z: p[0] = xyz[3 * i + (k - G_NODE_X)]; return 1;
+      case G_EDGES_LENGTH_EQUAL: case G_EDGES_FORCE_EQUAL: p[0] = s_aggp[i]; return 1;
       default: p[0] = loadpath; return 1;
     }
   };
@@ -211,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       double p[3];
       const int k = A.kind[t];
       const int nc = predict(k, A.index[t], A.target + 6 * t, p);
-      if (k >= G_NODE_LINE && k != G_EDGE_ANGLE) {
+      if (k >= G_NODE_LINE && k <= G_EDGE_DIRECTION) {
         const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
         for (int c = 0; c < 3; ++c) acc += err_value(A.err[t], A.weight[t], p[c], pg.gp[c]);
       } else {
@@ -239,7 +269,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       double p[3];
       const int nc = predict(k, i, A.target + 6 * t, p);
       double d[3];
-      if (k >= G_NODE_LINE && k != G_EDGE_ANGLE) {
+      if (k >= G_NODE_LINE && k <= G_EDGE_DIRECTION) {
         const ProjGoal pg = proj_goal(k, p, A.target + 6 * t);
         for (int c = 0; c < 3; ++c) d[c] = mult * err_deriv(ek, w, p[c], pg.gp[c]);
         const double de = pg.d[0] * d[0] + pg.d[1] * d[1] + pg.d[2] * d[2];
@@ -317,6 +347,21 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     __syncthreads();
     // network load path terms of this group: all threads scatter over the edges
     for (int t = A.group_ptr[g]; t < A.group_ptr[g + 1]; ++t) {
+      const int kk = A.kind[t];
+      if (kk == G_EDGES_LENGTH_EQUAL || kk == G_EDGES_FORCE_EQUAL) {
+        const int slot = A.index[t], a0 = A.agg_ptr[t], a1 = A.agg_ptr[t + 1], n = a1 - a0;
+        const double d0 = mult * err_deriv(A.err[t], A.weight[t], s_aggp[slot], A.target[6 * t]);
+        const double mu = s_aggmu[slot], V = s_aggV[slot], M = s_aggM[slot];
+        const double* v = kk == G_EDGES_LENGTH_EQUAL ? len : frc;
+        double* vb = kk == G_EDGES_LENGTH_EQUAL ? lb : fb;
+        for (int j = a0 + threadIdx.x; j < a1; j += kThreads) {
+          const int e = A.agg_index[j];
+          const double x = v[e];
+          const double dM = kk == G_EDGES_LENGTH_EQUAL ? 1.0 : (x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0));
+          atomicAdd(vb + e, d0 * (2.0 * (x - mu) / (n * M) - V * dM / (M * M * n)));
+        }
+        continue;
+      }
       if (A.kind[t] != G_NETWORK_LOADPATH) continue;
       const double d0 = mult * err_deriv(A.err[t], A.weight[t], loadpath, A.target[6 * t]);
       for (int e = threadIdx.x; e < A.E; e += kThreads) {
@@ -335,12 +380,14 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
 int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const int32_t* index, const int32_t* err,
                       const double* weight, const double* target, int n_groups, const int32_t* group_ptr,
                       const int32_t* gfinal, const double* ginner, const double* gouter, int need_loadpath,
+                      const int32_t* agg_ptr, const int32_t* agg_index,
                       const double* xyz, const double* lengths, const double* forces, const double* residuals,
                       double* loss, double* gsum, double* xyz_bar, double* lengths_bar, double* forces_bar,
                       double* residuals_bar, int64_t batch, cudaStream_t st) {
   GoalArgs A;
   A.T = n_terms; A.G = n_groups; A.N = (int)p->N; A.E = (int)p->E;
   A.kind = kind; A.index = index; A.err = err; A.group_ptr = group_ptr; A.edge_nodes = p->d.edge_nodes;
+  A.agg_ptr = agg_ptr; A.agg_index = agg_index;
   A.weight = weight; A.target = target; A.gfinal = gfinal; A.ginner = ginner; A.gouter = gouter;
   A.xyz = xyz; A.lengths = lengths; A.forces = forces; A.residuals = residuals;
   A.loss = loss; A.gsum = gsum;

@@ -15,6 +15,7 @@ __all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "Node
            "VertexResidualDirectionGoal", "VertexResidualPlaneGoal", "NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal", "VertexLineGoal",
            "VertexPlaneGoal", "VertexSegmentGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
            "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "EdgeDirectionGoal", "EdgeAngleGoal",
+           "EdgesLengthEqualGoal", "EdgesForceEqualGoal",
            "NetworkLoadPathGoal",
            "VertexGoal", "VertexPointGoal", "VertexResidualForceGoal", "VertexResidualVectorGoal",
            "VertexXCoordinateGoal", "VertexYCoordinateGoal", "VertexZCoordinateGoal", "MeshLoadPathGoal", "GoalState"]
@@ -310,3 +311,40 @@ class EdgeAngleGoal(EdgeGoal):
         import torch
         p = self.prediction(eq_state, structure)
         return GoalState(goal=torch.as_tensor(self.target[0], dtype=p.dtype, device=p.device), weight=self.weight, prediction=p)
+
+
+class _EdgesAggregateGoal(EdgeGoal):
+    """goals/goal.py:165-190: an aggregate goal takes the keys of the elements it reduces over; target 0."""
+    is_aggregate = True
+
+    def __init__(self, key, weight=1.0):
+        super().__init__(key=key, target=0.0, weight=weight)
+
+    def indices(self, structure):
+        ei = structure.edge_index
+        return [ei[(int(u), int(v))] for u, v in self.key]
+
+    def index(self, structure):
+        return 0
+
+
+class EdgesLengthEqualGoal(_EdgesAggregateGoal):
+    """goals/edge/length.py:49-75: var(lengths) / mean(lengths) over the edge set."""
+    kind = 17
+
+    def prediction(self, eq_state, structure):
+        import torch
+        idx = torch.as_tensor(self.indices(structure), device=eq_state.lengths.device)
+        v = eq_state.lengths[..., 0].index_select(-1, idx)
+        return v.var(dim=-1, unbiased=False) / v.mean(dim=-1)
+
+
+class EdgesForceEqualGoal(_EdgesAggregateGoal):
+    """goals/edge/force.py:49-75: var(forces) / mean(|forces|) over the edge set."""
+    kind = 18
+
+    def prediction(self, eq_state, structure):
+        import torch
+        idx = torch.as_tensor(self.indices(structure), device=eq_state.forces.device)
+        v = eq_state.forces[..., 0].index_select(-1, idx)
+        return v.var(dim=-1, unbiased=False) / v.abs().mean(dim=-1)

@@ -136,12 +136,22 @@ class _Program:
 
     def __init__(self, errors, structure, device):
         kind, index, err, weight, target, gptr, gfinal, ginner, gouter = [], [], [], [], [], [0], [], [], []
+        agg_ptr, agg_index, n_agg = [0], [], 0
         for term in errors:
             for g in term.goals:
-                i = int(g.index(structure))
-                limit = structure.num_edges if g.kind in (3, 4, 5, 15, 16) else structure.num_nodes
-                if not 0 <= i < limit:                      # the kernel trusts the table
-                    raise IndexError(f"{type(g).__name__}: element index {i} outside [0, {limit})")
+                if getattr(g, "is_aggregate", False):         # index = running number of the aggregate, set = its elements
+                    members = [int(i) for i in g.indices(structure)]
+                    if not members or min(members) < 0 or max(members) >= structure.num_edges:
+                        raise IndexError(f"{type(g).__name__}: element set outside [0, {structure.num_edges})")
+                    i = n_agg
+                    n_agg += 1
+                    agg_index += members
+                else:
+                    i = int(g.index(structure))
+                    limit = structure.num_edges if g.kind in (3, 4, 5, 15, 16) else structure.num_nodes
+                    if not 0 <= i < limit:                      # the kernel trusts the table
+                        raise IndexError(f"{type(g).__name__}: element index {i} outside [0, {limit})")
+                agg_ptr.append(len(agg_index))
                 kind.append(g.kind)
                 index.append(i)
                 err.append(term.err_kind)
@@ -160,9 +170,10 @@ class _Program:
 
         self.arrays = [dev(kind, np.int32), dev(index, np.int32), dev(err, np.int32), dev(weight, np.float64),
                        dev(np.asarray(target).reshape(-1, 6), np.float64), dev(gptr, np.int32), dev(gfinal, np.int32),
-                       dev(ginner, np.float64), dev(gouter, np.float64)]
+                       dev(ginner, np.float64), dev(gouter, np.float64), dev(agg_ptr, np.int32),
+                       dev(agg_index if agg_index else [0], np.int32)]
         ptr = [C.c_void_p(a.data_ptr()) for a in self.arrays]
-        self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), *ptr)
+        self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), n_agg, *ptr)
 
 
 class _GoalsLoss(torch.autograd.Function):

@@ -78,6 +78,12 @@ PREDICTIONS["EdgeDirectionGoal"] = lambda st, i: _normalize_vector(st["vectors"]
 GOALS["EdgeDirectionGoal"] = lambda p, t: _normalize_vector(t)                                       # edge/direction.py:49-69
 
 
+def edges_equal(st, field, idx):
+    """goals/edge/length.py:49-75, force.py:49-75: var(v) / mean(v) for lengths, var(v) / mean(|v|) for forces."""
+    v = st[field][np.asarray(idx), 0]
+    return np.var(v) / (np.mean(v) if field == "lengths" else np.mean(np.abs(v)))
+
+
 def edge_angle(st, i, vector):
     """goals/edge/angle.py:74-101 with geometry.py:46-99 (radians)."""
     c = _normalize_vector(st["vectors"][i, :]) @ _normalize_vector(vector)
@@ -98,6 +104,9 @@ def error_term(name, goals, alpha, state):
     fn = ERRORS[BASE.get(name, name)]
     total = 0.0
     for g, i, t, w in goals:
+        if g in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal"):      # i = the list of edge indices
+            total = total + fn(w, edges_equal(state, "lengths" if g == "EdgesLengthEqualGoal" else "forces", i), np.float64(0.0))
+            continue
         if g == "EdgeAngleGoal":                      # t = (target angle, reference vector)
             total = total + fn(w, edge_angle(state, i, t[1]), np.float64(t[0]))
             continue

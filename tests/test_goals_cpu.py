@@ -54,6 +54,11 @@ def test_goalwise_errors_match_the_oracle():
         ref = og.error_term(ename, idx, 0.7, st)
         got = term.evaluate_state(eqs, s).item()
         assert abs(got - ref) <= 1e-13 * max(1.0, abs(ref)), (ename, got, ref)
+    keys = [(int(u), int(v)) for u, v in prob.edges[:7]]
+    agg = LS.SquaredError([G.EdgesLengthEqualGoal(keys, 2.0), G.EdgesForceEqualGoal(keys)], alpha=1.3)
+    ref = og.error_term("SquaredError", [("EdgesLengthEqualGoal", list(range(7)), 0.0, 2.0),
+                                         ("EdgesForceEqualGoal", list(range(7)), 0.0, 1.0)], 1.3, st)
+    assert abs(agg.evaluate_state(eqs, s).item() - ref) <= 1e-13 * abs(ref)
     net = LS.MeanPredictionError([G.NetworkLoadPathGoal()], alpha=0.01)
     ref = og.error_term("MeanPredictionError", [("NetworkLoadPathGoal", 0, 0.0, 1.0)], 0.01, st)
     assert abs(net.evaluate_state(eqs, s).item() - ref) <= 1e-13 * abs(ref)
@@ -68,7 +73,8 @@ def test_goal_program_layout():
                    LS.PredictionError([G.NetworkLoadPathGoal()], alpha=0.1), LS.L2Regularizer(1e-3))
     assert loss.number_of_goals() == 4 and loss.number_of_regularizers() == 1
     prog = loss.program(s, torch.device("cpu"))
-    kind, index, err, weight, target, gptr, gfinal, ginner, gouter = [a.numpy() for a in prog.arrays]
+    kind, index, err, weight, target, gptr, gfinal, ginner, gouter, agg_ptr, agg_index = [a.numpy() for a in prog.arrays]
+    assert agg_ptr.tolist() == [0, 0, 0, 0, 0] and prog.struct.num_aggregates == 0
     assert kind.tolist() == [3, 3, 0, 6] and err.tolist() == [0, 0, 0, 2]
     assert index.tolist() == [0, 2, 4, 0] and weight.tolist() == [1.0, 3.0, 1.0, 1.0]
     assert target.tolist() == [[1, 0, 0, 0, 0, 0], [2, 0, 0, 0, 0, 0], [1, 2, 3, 0, 0, 0], [0, 0, 0, 0, 0, 0]]

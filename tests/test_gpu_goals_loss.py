@@ -56,6 +56,8 @@ def build_loss(prob, s, rng):
                               + [("NodeResidualPlaneGoal", int(nodes[fixed[3 % len(fixed)]]), [0.2, 1.0, 0.3], 2.0)]),
         ("SquaredError", 0.9, [("EdgeDirectionGoal", ekey(e), [0.3, 1.0, -0.2], 1.0) for e in pick_e[:4]]
                               + [("EdgeAngleGoal", ekey(e), (0.4 + 0.1 * j, [0.0, 0.2, 1.0]), 1.5) for j, e in enumerate(pick_e[4:8])]),
+        ("SquaredError", 3.0, [("EdgesLengthEqualGoal", [ekey(e) for e in pick_e[:9]], 0.0, 2.0),
+                               ("EdgesForceEqualGoal", [ekey(e) for e in range(len(edges))], 0.0, 1.0)]),
         ("AbsoluteError", 0.4, [("NodeLineGoal", int(nodes[pick_n[4]]), [prob.xyz0[pick_n[4]] + [0.3, 0.2, -0.4], prob.xyz0[pick_n[4]] + [-1.0, 1.5, 2.0]], 1.0),
                                 ("NodePlaneGoal", int(nodes[pick_n[5]]), [prob.xyz0[pick_n[5]] + [0.1, 0.0, 0.3], [1.0, 0.5, 0.25]], 2.0)]),
     ]
@@ -64,6 +66,10 @@ def build_loss(prob, s, rng):
         gl, ol = [], []
         for gname, key, target, weight in goals:
             cls = getattr(G, gname)
+            if gname in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal"):
+                gl.append(cls(key, weight))
+                ol.append((gname, [ei[k] for k in key], 0.0, weight))
+                continue
             if gname == "EdgeAngleGoal":
                 g = cls(key, target[0], weight, vector=target[1])
             else:

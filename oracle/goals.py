@@ -13,8 +13,9 @@ Goal predictions, error terms and the loss, restated in numpy from the reference
                                 Mean*, RootMeanSquaredError (.errors), Error.__call__ (alpha)
   losses/loss.py:60-90          Loss.__call__  (sum of error terms + regularizers)
   losses/regularizers.py:43-70  L2Regularizer  alpha * sum(q^2)
-Parity unpinned against executed reference code (equinox / jax are absent); every function is the cited
-one-liner.  `state` is the dict of oracle.equilibrium_state.
+Pinned: tests/test_oracle_goals_golden.py checks every prediction, reference value, error kernel and aggregator
+here against values produced by the reference's own goal / error / geometry code (tests/golden/make_golden_goals.py).
+`state` is the dict of oracle.equilibrium_state.
 """
 import numpy as np
 

@@ -183,7 +183,7 @@ def _make_jnp():
 
 
 class _CustomVJP:
-    def __init__(self, fn):
+    def __init__(self, fn, nondiff_argnums=()):
         self.fn = fn
         self.__doc__ = fn.__doc__
 

@@ -327,3 +327,27 @@ def test_follower_face_loads_fixed_point_and_gradients():
             d = d.reshape(arr.shape)
             refv = (oracle_loss(*mk(arr + d))[0] - oracle_loss(*mk(arr - d))[0]) / (2 * d.flat[k])
             assert abs(gnp.flat[k] - refv) <= 1e-6 * scale + 1e-9, (k, gnp.flat[k], refv)
+
+
+@pytest.mark.parametrize("tag", ["net6", "net9"])
+@pytest.mark.parametrize("local", [False, True])
+def test_fixed_point_state_vs_reference_arrays(tag, local):
+    """The CUDA fixed point against states the reference's own models.py / fixed_point.py / loads.py produced
+    (tests/golden/make_golden_fixed_point.py), same tmax and eta: positions to 1e-9 (both stop on the same rule,
+    mean nodal move <= 1e-10), every field of the reported state to 1e-8."""
+    import os
+    import jax_fdm_b200.equilibrium as eq
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixed_point.npz")))
+    s = eq.EquilibriumStructureSparse(g[f"{tag}_nodes"], g[f"{tag}_edges"], g[f"{tag}_supports"], device=0)
+    model = eq.EquilibriumModelSparse(tmax=100, eta=1e-10, is_load_local=local, tol=1e-14)
+    params = eq.EquilibriumParametersState(T(g[f"{tag}_q"]), T(g[f"{tag}_xyz_fixed"]),
+                                           eq.LoadState(T(g[f"{tag}_loads"]), T(g[f"{tag}_edges_load"]), 0.0))
+    st = model(params, s)
+    key = f"{tag}_{'local' if local else 'global'}"
+    ref = g[f"{key}_state_xyz"]
+    assert np.abs(st.xyz.cpu().numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
+    for f in ("residuals", "lengths", "forces", "loads", "vectors"):
+        r = g[f"{key}_state_{f}"]
+        got = getattr(st, f).cpu().numpy().reshape(r.shape)
+        assert np.abs(got - r).max() <= 1e-8 * max(1.0, np.abs(r).max()), f

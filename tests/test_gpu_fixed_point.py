@@ -222,7 +222,6 @@ def test_local_frame_loads_vs_reference_arrays_and_fd(tag):
     """nodes_load with edge / face loads given in the element frames: kernels against arrays the reference's
     loads.py produced (quad mesh) and the oracle, then both VJPs against central differences of the oracle."""
     import jax_fdm_b200.equilibrium as eq
-    from oracle import model as om
 
     g = _golden_loads()
     s = eq.EquilibriumMeshStructureSparse(g[f"{tag}_nodes"], g[f"{tag}_faces"], g[f"{tag}_edges"], g[f"{tag}_supports"], device=0)

@@ -23,8 +23,8 @@ checks this restatement against them bit-for-bit (integers) / to 1e-12 (floats),
 and against the reference's own KATs (arch baseline JSON, olympia / stuttgart21
 CSVs, Liew dome statistics, README cable-net table).  The same is done for the local
 frames and tributary loads (make_golden_loads.py), the goals / error terms
-(make_golden_goals.py) and the tmax > 1 fixed point with edge loads
-(make_golden_fixed_point.py), each with its own tests/test_oracle_*_golden.py.
+(make_golden_goals.py), the tmax > 1 fixed point with edge loads
+(make_golden_fixed_point.py) and the mesh structures + face loads (make_golden_mesh.py), each with its own tests/test_oracle_*_golden.py.
 """
 
 from .structure import OracleStructure, build_structure  # noqa: F401

@@ -350,3 +350,26 @@ def test_fixed_point_state_vs_reference_arrays(tag, local):
         r = g[f"{key}_state_{f}"]
         got = getattr(st, f).cpu().numpy().reshape(r.shape)
         assert np.abs(got - r).max() <= 1e-8 * max(1.0, np.abs(r).max()), f
+
+
+@pytest.mark.parametrize("tag,local", [("quad", False), ("quad", True), ("mixed", False)])
+def test_face_load_fixed_point_vs_reference_arrays(tag, local):
+    """The CUDA fixed point under face (area) loads against states the reference's own mesh structure, models.py,
+    fixed_point.py and loads.py produced (tests/golden/make_golden_mesh.py).  (Local loads on the mixed mesh are the
+    one documented divergence: the reference reads xyz[-1] for padded faces.)"""
+    import os
+    import jax_fdm_b200.equilibrium as eq
+
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mesh_faces.npz")))
+    s = eq.EquilibriumMeshStructureSparse(g[f"{tag}_nodes"], g[f"{tag}_faces"], g[f"{tag}_edges"], g[f"{tag}_supports"], device=0)
+    model = eq.EquilibriumModelSparse(tmax=100, eta=1e-10, is_load_local=local, tol=1e-14)
+    params = eq.EquilibriumParametersState(T(g[f"{tag}_q"]), T(g[f"{tag}_xyz_fixed"]),
+                                           eq.LoadState(T(g[f"{tag}_loads"]), 0.0, T(g[f"{tag}_faces_load"])))
+    st = model(params, s)
+    key = f"{tag}_{'local' if local else 'global'}"
+    ref = g[f"{key}_state_xyz"]
+    assert np.abs(st.xyz.cpu().numpy() - ref).max() <= 1e-9 * np.abs(ref).max()
+    for f in ("residuals", "lengths", "forces", "loads", "vectors"):
+        r = g[f"{key}_state_{f}"]
+        got = getattr(st, f).cpu().numpy().reshape(r.shape)
+        assert np.abs(got - r).max() <= 1e-8 * max(1.0, np.abs(r).max()), f

@@ -8,9 +8,9 @@ EXECUTING THE REFERENCE'S OWN CODE:
 
 loaded unmodified from /root/reference under the numpy stand-in for `jax` of make_golden.py, plus
 a loop-based `vmap`.  The mesh index arrays (`faces_indexed`, `edges_faces_indexed`,
-`connectivity_faces_vertices`) come from this repo's host mirror of EquilibriumMeshStructure
-(structures/meshes.py needs COMPAS and cannot load here); what the fixture pins is the load
-arithmetic given those arrays.
+`connectivity_faces_vertices`) fed to loads.py here come from this repo's host mirror of EquilibriumMeshStructure;
+make_golden_mesh.py runs the reference's real mesh structure class and pins those tables (and the face-load
+fixed point) separately.
 
 Run here (needs /root/reference):   python tests/golden/make_golden_loads.py
 Output: tests/golden/loads_frames.npz

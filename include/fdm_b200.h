@@ -274,7 +274,8 @@ int fdm_face_loads_vjp(const fdm_plan* plan, const int32_t* d_faces, int64_t num
  *        16 EdgeAngleGoal (goals/edge/angle.py): angle between the edge vector and target[1:4] vs target[0]
  *        17 EdgesLengthEqualGoal (goals/edge/length.py:49-75): var(lengths[S]) / mean(lengths[S]) over the edge
  *           set S = agg_index[agg_ptr[t] .. agg_ptr[t+1]); 18 EdgesForceEqualGoal (goals/edge/force.py:49-75):
- *           var(forces[S]) / mean(|forces[S]|); index[t] = running number of the aggregate goal (< 16)
+ *           var(forces[S]) / mean(|forces[S]|); 19 NodesColinearGoal (goals/node/colinear.py:19-60): colinearity
+ *           energy of the ordered node sequence S; index[t] = running number of the aggregate goal (< 16)
  *   error 0 SquaredError w (p-t)^2, 1 AbsoluteError w |p-t|, 2 PredictionError w p,
  *         3 LogMaxError w log1p(max(p-t, 0))                                   (errors.py:232-431)
  * Terms are grouped by Error instance (terms of group g = [group_ptr[g], group_ptr[g+1])):

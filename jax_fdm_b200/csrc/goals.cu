@@ -43,6 +43,7 @@ enum GoalKind : int {
   G_EDGE_ANGLE,               // angle between the edge vector and target[1:4] vs target[0]             (1)
   G_EDGES_LENGTH_EQUAL,       // var(lengths[S]) / mean(lengths[S]) over the edge set S of the term (index = aggregate slot)
   G_EDGES_FORCE_EQUAL,        // var(forces[S]) / mean(|forces[S]|)
+  G_NODES_COLINEAR,           // colinearity energy of the ordered node sequence S (geometry.py:660-694)
 };
 constexpr int kMaxAgg = 16;    // aggregate goals per loss
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
@@ -188,8 +189,26 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     for (int t = 0; t < A.T; ++t) {
       const int k = A.kind[t];
       if (k < G_EDGES_LENGTH_EQUAL) continue;
-      const double* v = k == G_EDGES_LENGTH_EQUAL ? len : frc;
       const int a0 = A.agg_ptr[t], a1 = A.agg_ptr[t + 1], n = a1 - a0;
+      if (k == G_NODES_COLINEAR) {
+        // colinearity_points: sum_i |d_{i+1} - d_i|^2 / (0.5 (|d_i|^2 + |d_{i+1}|^2)) / max(n - 2, 1), d_i = P_{i+1} - P_i
+        double acc = 0.0;
+        for (int j = a0 + threadIdx.x; j + 2 < a1; j += kThreads) {
+          const double* P0 = xyz + 3 * A.agg_index[j];
+          const double* P1 = xyz + 3 * A.agg_index[j + 1];
+          const double* P2 = xyz + 3 * A.agg_index[j + 2];
+          double dd = 0.0, l0 = 0.0, l1 = 0.0;
+          for (int c = 0; c < 3; ++c) {
+            const double d0 = P1[c] - P0[c], d1 = P2[c] - P1[c];
+            dd += (d1 - d0) * (d1 - d0); l0 += d0 * d0; l1 += d1 * d1;
+          }
+          acc += dd / (0.5 * (l0 + l1));
+        }
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) s_aggp[A.index[t]] = acc / (n - 2 > 1 ? n - 2 : 1);
+        continue;
+      }
+      const double* v = k == G_EDGES_LENGTH_EQUAL ? len : frc;
       double s1 = 0.0, sa = 0.0;
       for (int j = a0 + threadIdx.x; j < a1; j += kThreads) { const double x = v[A.agg_index[j]]; s1 += x; sa += fabs(x); }
       s1 = block_sum(s1, red);
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       case G_EDGE_FORCE: p[0] = frc[i]; return 1;
       case G_EDGE_LOADPATH: p[0] = fabs(frc[i]) * len[i]; return 1;
       case G_NODE_X: case G_NODE_Y: case G_NODE_Z: p[0] = xyz[3 * i + (k - G_NODE_X)]; return 1;
-      case G_EDGES_LENGTH_EQUAL: case G_EDGES_FORCE_EQUAL: p[0] = s_aggp[i]; return 1;
+      case G_EDGES_LENGTH_EQUAL: case G_EDGES_FORCE_EQUAL: case G_NODES_COLINEAR: p[0] = s_aggp[i]; return 1;
       default: p[0] = loadpath; return 1;
     }
   };
@@ -348,6 +367,28 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     // network load path terms of this group: all threads scatter over the edges
     for (int t = A.group_ptr[g]; t < A.group_ptr[g + 1]; ++t) {
       const int kk = A.kind[t];
+      if (kk == G_NODES_COLINEAR) {
+        const int slot = A.index[t], a0 = A.agg_ptr[t], a1 = A.agg_ptr[t + 1], n = a1 - a0;
+        const double d0s = mult * err_deriv(A.err[t], A.weight[t], s_aggp[slot], A.target[6 * t]) / (n - 2 > 1 ? n - 2 : 1);
+        for (int j = a0 + threadIdx.x; j + 2 < a1; j += kThreads) {
+          const int i0 = A.agg_index[j], i1 = A.agg_index[j + 1], i2 = A.agg_index[j + 2];
+          double d0[3], d1[3], dd = 0.0, l0 = 0.0, l1 = 0.0;
+          for (int c = 0; c < 3; ++c) {
+            d0[c] = xyz[3 * i1 + c] - xyz[3 * i0 + c]; d1[c] = xyz[3 * i2 + c] - xyz[3 * i1 + c];
+            dd += (d1[c] - d0[c]) * (d1[c] - d0[c]); l0 += d0[c] * d0[c]; l1 += d1[c] * d1[c];
+          }
+          const double lbar = 0.5 * (l0 + l1);
+          for (int c = 0; c < 3; ++c) {
+            const double gD = 2.0 * (d1[c] - d0[c]) / lbar;       // d T / d (d1 - d0)
+            const double g0 = -gD - dd / (lbar * lbar) * d0[c];   // d T / d d0  (lbar = (|d0|^2 + |d1|^2) / 2)
+            const double g1 = gD - dd / (lbar * lbar) * d1[c];    // d T / d d1
+            atomicAdd(xb + 3 * i0 + c, -d0s * g0);
+            atomicAdd(xb + 3 * i1 + c, d0s * (g0 - g1));
+            atomicAdd(xb + 3 * i2 + c, d0s * g1);
+          }
+        }
+        continue;
+      }
       if (kk == G_EDGES_LENGTH_EQUAL || kk == G_EDGES_FORCE_EQUAL) {
         const int slot = A.index[t], a0 = A.agg_ptr[t], a1 = A.agg_ptr[t + 1], n = a1 - a0;
         const double d0 = mult * err_deriv(A.err[t], A.weight[t], s_aggp[slot], A.target[6 * t]);

@@ -15,7 +15,7 @@ __all__ = ["Goal", "NodeGoal", "EdgeGoal", "NetworkGoal", "NodePointGoal", "Node
            "VertexResidualDirectionGoal", "VertexResidualPlaneGoal", "NodeLineGoal", "NodePlaneGoal", "NodeSegmentGoal", "VertexLineGoal",
            "VertexPlaneGoal", "VertexSegmentGoal", "NodeXCoordinateGoal", "NodeYCoordinateGoal", "NodeZCoordinateGoal",
            "EdgeLengthGoal", "EdgeForceGoal", "EdgeLoadPathGoal", "EdgeDirectionGoal", "EdgeAngleGoal",
-           "EdgesLengthEqualGoal", "EdgesForceEqualGoal",
+           "EdgesLengthEqualGoal", "EdgesForceEqualGoal", "NodesColinearGoal", "VerticesColinearGoal",
            "NetworkLoadPathGoal",
            "VertexGoal", "VertexPointGoal", "VertexResidualForceGoal", "VertexResidualVectorGoal",
            "VertexXCoordinateGoal", "VertexYCoordinateGoal", "VertexZCoordinateGoal", "MeshLoadPathGoal", "GoalState"]
@@ -348,3 +348,33 @@ class EdgesForceEqualGoal(_EdgesAggregateGoal):
         idx = torch.as_tensor(self.indices(structure), device=eq_state.forces.device)
         v = eq_state.forces[..., 0].index_select(-1, idx)
         return v.var(dim=-1, unbiased=False) / v.abs().mean(dim=-1)
+
+
+class NodesColinearGoal(NodeGoal):
+    """goals/node/colinear.py:19-60: length-normalised colinearity energy of an ordered node sequence (geometry.py:660-694)."""
+    kind = 19
+    is_aggregate = True
+
+    def __init__(self, key, weight=1.0):
+        super().__init__(key=key, target=0.0, weight=weight)
+
+    def indices(self, structure):
+        ni = structure.node_index
+        return [ni[int(k)] for k in self.key]
+
+    def index(self, structure):
+        return 0
+
+    def prediction(self, eq_state, structure):
+        import torch
+        idx = torch.as_tensor(self.indices(structure), device=eq_state.xyz.device)
+        P = eq_state.xyz.index_select(-2, idx)
+        d = P[..., 1:, :] - P[..., :-1, :]
+        l2 = (d * d).sum(dim=-1)
+        dt = d[..., 1:, :] - d[..., :-1, :]
+        lbar = 0.5 * (l2[..., 1:] + l2[..., :-1])
+        return ((dt * dt).sum(dim=-1) / lbar).sum(dim=-1) / max(dt.shape[-2], 1)
+
+
+class VerticesColinearGoal(VertexGoal, NodesColinearGoal):
+    """goals/vertex/colinear.py."""

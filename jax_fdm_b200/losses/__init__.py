@@ -141,8 +141,9 @@ class _Program:
             for g in term.goals:
                 if getattr(g, "is_aggregate", False):         # index = running number of the aggregate, set = its elements
                     members = [int(i) for i in g.indices(structure)]
-                    if not members or min(members) < 0 or max(members) >= structure.num_edges:
-                        raise IndexError(f"{type(g).__name__}: element set outside [0, {structure.num_edges})")
+                    limit = structure.num_nodes if g.kind == 19 else structure.num_edges
+                    if not members or min(members) < 0 or max(members) >= limit:
+                        raise IndexError(f"{type(g).__name__}: element set outside [0, {limit})")
                     i = n_agg
                     n_agg += 1
                     agg_index += members

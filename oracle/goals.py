@@ -85,6 +85,16 @@ def edges_equal(st, field, idx):
     return np.var(v) / (np.mean(v) if field == "lengths" else np.mean(np.abs(v)))
 
 
+def nodes_colinear(st, idx):
+    """goals/node/colinear.py:19-60 with geometry.py:660-694 (colinearity_points)."""
+    P = st["xyz"][np.asarray(idx), :]
+    d = P[1:] - P[:-1]
+    l2 = np.sum(d * d, axis=-1)
+    dt = d[1:] - d[:-1]
+    lbar = 0.5 * (l2[1:] + l2[:-1])
+    return np.sum(np.sum(dt ** 2, axis=-1) / lbar) / max(dt.shape[0], 1)
+
+
 def edge_angle(st, i, vector):
     """goals/edge/angle.py:74-101 with geometry.py:46-99 (radians)."""
     c = _normalize_vector(st["vectors"][i, :]) @ _normalize_vector(vector)
@@ -107,6 +117,9 @@ def error_term(name, goals, alpha, state):
     for g, i, t, w in goals:
         if g in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal"):      # i = the list of edge indices
             total = total + fn(w, edges_equal(state, "lengths" if g == "EdgesLengthEqualGoal" else "forces", i), np.float64(0.0))
+            continue
+        if g == "NodesColinearGoal":                  # i = the ordered list of node indices
+            total = total + fn(w, nodes_colinear(state, i), np.float64(0.0))
             continue
         if g == "EdgeAngleGoal":                      # t = (target angle, reference vector)
             total = total + fn(w, edge_angle(state, i, t[1]), np.float64(t[0]))

@@ -38,6 +38,7 @@ GOAL_MODULES = {
     "EdgeForceGoal": "jax_fdm.goals.edge.force", "EdgesForceEqualGoal": "jax_fdm.goals.edge.force",
     "EdgeLoadPathGoal": "jax_fdm.goals.edge.loadpath", "EdgeDirectionGoal": "jax_fdm.goals.edge.direction",
     "EdgeAngleGoal": "jax_fdm.goals.edge.angle", "NetworkLoadPathGoal": "jax_fdm.goals.network.loadpath",
+    "NodesColinearGoal": "jax_fdm.goals.node.colinear",
 }
 G.REAL |= set(GOAL_MODULES.values()) | {
     "jax_fdm.goals.goal", "jax_fdm.goals.state", "jax_fdm.goals.node.node", "jax_fdm.goals.edge.edge",
@@ -90,7 +91,8 @@ def main():
                   ("EdgeDirectionGoal", e, rng.standard_normal(3), None),
                   ("EdgeAngleGoal", e, 0.5, rng.standard_normal(3))]
     cases += [("EdgesLengthEqualGoal", list(range(4, 15)), 0.0, None), ("EdgesForceEqualGoal", list(range(0, 30)), 0.0, None),
-              ("NetworkLoadPathGoal", 0, 0.0, None)]
+              ("NetworkLoadPathGoal", 0, 0.0, None), ("NodesColinearGoal", [8, 9, 10, 11, 12], 0.0, None),
+              ("NodesColinearGoal", [1, 9, 17, 24], 0.0, None)]
 
     errors = importlib.import_module("jax_fdm.losses.errors")
     kinds = ["SquaredError", "AbsoluteError", "PredictionError", "LogMaxError"]

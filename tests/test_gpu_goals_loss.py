@@ -57,7 +57,8 @@ def build_loss(prob, s, rng):
         ("SquaredError", 0.9, [("EdgeDirectionGoal", ekey(e), [0.3, 1.0, -0.2], 1.0) for e in pick_e[:4]]
                               + [("EdgeAngleGoal", ekey(e), (0.4 + 0.1 * j, [0.0, 0.2, 1.0]), 1.5) for j, e in enumerate(pick_e[4:8])]),
         ("SquaredError", 3.0, [("EdgesLengthEqualGoal", [ekey(e) for e in pick_e[:9]], 0.0, 2.0),
-                               ("EdgesForceEqualGoal", [ekey(e) for e in range(len(edges))], 0.0, 1.0)]),
+                               ("EdgesForceEqualGoal", [ekey(e) for e in range(len(edges))], 0.0, 1.0),
+                               ("NodesColinearGoal", [int(nodes[n]) for n in free[:6]], 0.0, 1.5)]),
         ("AbsoluteError", 0.4, [("NodeLineGoal", int(nodes[pick_n[4]]), [prob.xyz0[pick_n[4]] + [0.3, 0.2, -0.4], prob.xyz0[pick_n[4]] + [-1.0, 1.5, 2.0]], 1.0),
                                 ("NodePlaneGoal", int(nodes[pick_n[5]]), [prob.xyz0[pick_n[5]] + [0.1, 0.0, 0.3], [1.0, 0.5, 0.25]], 2.0)]),
     ]
@@ -66,9 +67,9 @@ def build_loss(prob, s, rng):
         gl, ol = [], []
         for gname, key, target, weight in goals:
             cls = getattr(G, gname)
-            if gname in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal"):
+            if gname in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal", "NodesColinearGoal"):
                 gl.append(cls(key, weight))
-                ol.append((gname, [ei[k] for k in key], 0.0, weight))
+                ol.append((gname, [ni[k] for k in key] if gname == "NodesColinearGoal" else [ei[k] for k in key], 0.0, weight))
                 continue
             if gname == "EdgeAngleGoal":
                 g = cls(key, target[0], weight, vector=target[1])

@@ -33,6 +33,8 @@ def _oracle_case(g, st, i, name):
     if name in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal"):
         p = og.edges_equal(st, "lengths" if name == "EdgesLengthEqualGoal" else "forces", g[f"case{i}_set"])
         return np.atleast_1d(p), np.atleast_1d(0.0)
+    if name == "NodesColinearGoal":
+        return np.atleast_1d(og.nodes_colinear(st, g[f"case{i}_set"])), np.atleast_1d(0.0)
     if name == "EdgeAngleGoal":
         return np.atleast_1d(og.edge_angle(st, idx, g[f"case{i}_vector"])), np.atleast_1d(target)
     p = og.PREDICTIONS[name](st, idx)
@@ -81,6 +83,8 @@ def test_torch_goal_classes_vs_reference(setup):
         idx, target = int(g["case_index"][i]), g[f"case{i}_target"]
         if name in ("EdgesLengthEqualGoal", "EdgesForceEqualGoal"):
             goal = cls([(int(edges[e][0]), int(edges[e][1])) for e in g[f"case{i}_set"]])
+        elif name == "NodesColinearGoal":
+            goal = cls([int(nodes[n]) for n in g[f"case{i}_set"]])
         elif name == "NetworkLoadPathGoal":
             goal = cls()
         elif name == "EdgeAngleGoal":

@@ -14,29 +14,54 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-shared"]
 
 
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "fdm_b200.h"))
+    return hs
+
+
 def _stale():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "fdm_b200.h"))
+    deps = [os.path.join(CSRC, f) for f in SOURCES] + _headers()
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
-        return OUT
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every source to an object (in parallel, only the stale ones) and link the shared library.
+    `defines` / `out`: an alternative build of the same library (e.g. -DFDM_DEBUG bounds asserts)."""
+    out = out or OUT
+    if not force and not defines and not _stale():
+        return out
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(os.path.dirname(out), "obj" + ("_" + "_".join(defines) if defines else ""))
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    flags = [f for f in FLAGS if f != "-shared"] + ["-D" + d for d in defines]
+
+    def compile_one(src):
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_t):
+            return obj, ""
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"nvcc failed compiling {src}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nvcc, "-shared", "-o", out] + [o for o, _ in res], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libfdm_b200.so")
+        raise RuntimeError("nvcc failed linking libfdm_b200.so")
     if verbose:
-        print(r.stderr)
-    return OUT
+        print("".join(log for _, log in res))
+    return out
 
 
 if __name__ == "__main__":

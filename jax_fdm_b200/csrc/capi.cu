@@ -139,6 +139,9 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
     return rc;
   }
   p->on_device = true;
+  // the persistent PCG's per-aggregate tables are built and uploaded HERE (plan_create is the only call that
+  // allocates or synchronises); pcg2_supported() below is then a pure query, safe from any thread
+  pcg2_prepare(p);
   *out = p;
   return FDM_OK;
 }

@@ -16,6 +16,8 @@
 #include <cstdint>
 #include <string>
 
+#include <cuda_runtime_api.h>
+
 #include "fdm_b200.h"
 #include "xla/ffi/api/ffi.h"
 
@@ -70,6 +72,66 @@ ffi::Error SolveImpl(cudaStream_t stream, int64_t plan, int64_t solver, int64_t 
                           workspace->typed_data(), workspace->size_bytes(), batch_of(rhs, 2), &o, stream));
 }
 
+// Adjoint / repeated solve with the factor (or coarse inverse) a previous fdm_b200_solve left in `workspace_in`.
+// XLA aliases operand 2 onto result 2 (input_output_aliases={2: 2} in jax_ffi.py), so both name one buffer;
+// without the alias they differ and the factor is copied over first (device-to-device, on the stream).
+ffi::Error SolveReuseImpl(cudaStream_t stream, int64_t plan, int64_t solver, int64_t max_iters, double tol, F64 Kdata,
+                          F64 rhs, ffi::Buffer<ffi::U8> workspace_in, F64R x, F64R info, U8R workspace) {
+  fdm_plan* p = plan_of(plan);
+  if (workspace_in.size_bytes() != workspace->size_bytes())
+    return ffi::Error(ffi::ErrorCode::kInvalidArgument, "fdm_b200_solve_reuse: workspace operand and result differ in size");
+  if (workspace_in.typed_data() != workspace->typed_data() &&
+      cudaMemcpyAsync(workspace->typed_data(), workspace_in.typed_data(), workspace->size_bytes(),
+                      cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    return ffi::Error(ffi::ErrorCode::kInternal, "fdm_b200_solve_reuse: workspace copy failed");
+  fdm_solve_opts o{};
+  o.solver = (int32_t)solver;
+  o.max_iters = (int32_t)max_iters;
+  o.tol = tol;
+  o.reuse_factor = 1;
+  return status(fdm_solve(p, Kdata.typed_data(), rhs.typed_data(), x->typed_data(), info->typed_data(),
+                          workspace->typed_data(), workspace->size_bytes(), batch_of(rhs, 2), &o, stream));
+}
+
+// ---- K1 + K2 fused: (q, xyz_fixed, loads) -> (x_free, info, workspace)     models.py:222-256
+ffi::Error SolveFromQImpl(cudaStream_t stream, int64_t plan, int64_t solver, F64 q, F64 xyz_fixed, F64 loads, F64R x,
+                          F64R info, U8R workspace) {
+  fdm_plan* p = plan_of(plan);
+  const int64_t E = fdm_plan_size(p, FDM_SIZE_EDGES), N = fdm_plan_size(p, FDM_SIZE_NODES),
+                Ns = fdm_plan_size(p, FDM_SIZE_FIXED);
+  fdm_solve_opts o{};
+  o.solver = (int32_t)solver;
+  return status(fdm_solve_from_q(p, q.typed_data(), xyz_fixed.typed_data(), loads.typed_data(), x->typed_data(),
+                                 info->typed_data(), workspace->typed_data(), workspace->size_bytes(), batch_of(q, 1), E,
+                                 stride_of(xyz_fixed, 2, Ns * 3), stride_of(loads, 2, N * 3), &o, stream));
+}
+
+// ---- tributary edge loads and their VJP (tmax > 1)      models.py:290-344, loads.py:296-331
+ffi::Error EdgeLoadsImpl(cudaStream_t stream, int64_t plan, int64_t is_local, F64 xyz, F64 loads_nodes, F64 edges_load,
+                         F64R loads_out) {
+  fdm_plan* p = plan_of(plan);
+  const int64_t E = fdm_plan_size(p, FDM_SIZE_EDGES), N = fdm_plan_size(p, FDM_SIZE_NODES);
+  return status(fdm_edge_loads(p, xyz.typed_data(), loads_nodes.typed_data(), edges_load.typed_data(),
+                               loads_out->typed_data(), batch_of(xyz, 2), stride_of(loads_nodes, 2, N * 3),
+                               stride_of(edges_load, 2, E * 3), (int)is_local, stream));
+}
+ffi::Error EdgeLoadsVjpImpl(cudaStream_t stream, int64_t plan, int64_t is_local, F64 xyz, F64 edges_load, F64 cot,
+                            F64R xyz_bar, F64R edges_load_bar) {
+  fdm_plan* p = plan_of(plan);
+  return status(fdm_edge_loads_vjp(p, xyz.typed_data(), edges_load.typed_data(), cot.typed_data(), xyz_bar->typed_data(),
+                                   edges_load_bar->typed_data(), batch_of(xyz, 2),
+                                   stride_of(edges_load, 2, fdm_plan_size(p, FDM_SIZE_EDGES) * 3), (int)is_local, stream));
+}
+
+// ---- benchmark loss: (x, x0) -> (g, loss)
+ffi::Error LossSqdistImpl(cudaStream_t stream, int64_t plan, F64 x, F64 x0, F64R g, F64R loss) {
+  (void)plan;
+  const int64_t B = batch_of(x, 2);
+  const int64_t per = (int64_t)x.element_count() / (B > 0 ? B : 1);
+  return status(fdm_loss_sqdist(x.typed_data(), x0.typed_data(), g->typed_data(), loss->typed_data(), per, B,
+                                stride_of(x0, 2, per), stream));
+}
+
 // ---- SpMM: (Kdata, X) -> Y                               models.py:1012, sparse.py:301
 ffi::Error SpmmImpl(cudaStream_t stream, int64_t plan, F64 Kdata, F64 X, F64R Y) {
   return status(fdm_spmm(plan_of(plan), Kdata.typed_data(), X.typed_data(), Y->typed_data(), batch_of(X, 2), stream));
@@ -122,6 +184,22 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_solve, SolveImpl,
                               ffi::Ffi::Bind() FDM_STREAM.Attr<int64_t>("solver").Attr<int64_t>("max_iters")
                                   .Attr<double>("tol").Attr<int64_t>("reuse_factor")
                                   .Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_solve_reuse, SolveReuseImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Attr<int64_t>("solver").Attr<int64_t>("max_iters")
+                                  .Attr<double>("tol")
+                                  .Arg<F64>().Arg<F64>().Arg<ffi::Buffer<ffi::U8>>()
+                                  .Ret<F64>().Ret<F64>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_solve_from_q, SolveFromQImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Attr<int64_t>("solver")
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<ffi::Buffer<ffi::U8>>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_edge_loads, EdgeLoadsImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Attr<int64_t>("is_local")
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_edge_loads_vjp, EdgeLoadsVjpImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Attr<int64_t>("is_local")
+                                  .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_loss_sqdist, LossSqdistImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_spmm, SpmmImpl, ffi::Ffi::Bind() FDM_STREAM.Arg<F64>().Arg<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_positions, PositionsImpl,
                               ffi::Ffi::Bind() FDM_STREAM.Arg<F64>().Arg<F64>().Ret<F64>());

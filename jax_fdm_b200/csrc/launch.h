@@ -101,3 +101,4 @@ bool pcg2_supported(const fdm_plan* p);
 int pcg2_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
                void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
 void pcg2_destroy(fdm_plan* p);
+void pcg2_prepare(fdm_plan* p);

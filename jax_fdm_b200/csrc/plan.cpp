@@ -433,6 +433,34 @@ void fdm_build_partition(fdm_plan& p, int num_parts) {
       break;
     }
   }
+  // More connected components than parts: the components no seed reached are handed, whole, to the
+  // part that is smallest at that moment (an aggregate may then span several components; the coarse
+  // space stays piecewise constant and every row has an owner).
+  {
+    std::vector<int64_t> size(p.num_parts, 0);
+    for (int32_t v = 0; v < n; ++v)
+      if (owner[v] >= 0) ++size[owner[v]];
+    for (int32_t v = 0; v < n; ++v) {
+      if (owner[v] >= 0) continue;
+      const int32_t id = (int32_t)(std::min_element(size.begin(), size.end()) - size.begin());
+      owner[v] = id;
+      frontier.assign(1, v);
+      int64_t cnt = 1;
+      while (!frontier.empty()) {
+        next.clear();
+        for (int32_t u : frontier)
+          g.for_each(u, [&](int32_t w) {
+            if (owner[w] < 0) {
+              owner[w] = id;
+              ++cnt;
+              next.push_back(w);
+            }
+          });
+        frontier.swap(next);
+      }
+      size[id] += cnt;
+    }
+  }
   // compact ids (every seed owns at least itself, so all ids 0..num_parts-1 are present)
   p.part_of_row = owner;
 }

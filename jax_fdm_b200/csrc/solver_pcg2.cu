@@ -670,15 +670,20 @@ size_t ws_layout(const Pcg2Host* H, size_t* ainv_off, size_t* x_off) {
 
 }  // namespace
 
-bool pcg2_supported(const fdm_plan* cp) {
-  fdm_plan* p = const_cast<fdm_plan*>(cp);
-  if (!p->on_device || !shape_ok(p)) return false;
-  if (!p->d.pcg2) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != p->device) cudaSetDevice(p->device);
-    if (pcg2_build(p) != FDM_OK) return false;
+// Called once by fdm_plan_create (current device = the plan's): builds and uploads the tables when the mesh
+// has the shape the persistent kernel handles.  Failure only means "not supported".
+void pcg2_prepare(fdm_plan* p) {
+  if (!p->on_device || p->d.pcg2 || !shape_ok(p)) return;
+  for (int32_t c : p->part_of_row)
+    if (c < 0 || c >= p->num_parts) return;               // every row must have an owner
+  if (pcg2_build(p) != FDM_OK) {
+    pcg2_destroy(p);
+    cudaGetLastError();
   }
+}
+
+bool pcg2_supported(const fdm_plan* p) {
+  if (!p->on_device || !p->d.pcg2) return false;
   const Pcg2Host* H = (const Pcg2Host*)p->d.pcg2;
   return H->dev.rows_per_thread <= kMaxRowsPerThread && H->dev.smem_bytes <= 227 * 1024 - 1024;
 }
@@ -742,7 +747,8 @@ int pcg2_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double
     a.rhs = rhs + b * p->Nf * 3;
     a.x = x + b * p->Nf * 3;
     a.info = info ? info + b * FDM_INFO_STRIDE : nullptr;
-    if (!o.reuse_factor || b > 0) {
+    // the coarse inverse in the workspace belongs to ONE K: it is reused only for a single design
+    if (!o.reuse_factor || batch > 1) {
       // coarse inverse + clear exchange tags (CTA 0: coarse; CTAs 1..: clear)
       pcg2_setup_kernel<<<1 + 16, 1024, H->coarse_smem, st>>>(a, H->xwords);
     } else {

@@ -6,13 +6,15 @@ JAX is NOT installed in this image (nor on the GPU box), so this module is sourc
 importing it raises ImportError with that explanation, and nothing else in the package depends
 on it.  Where JAX and `lib/libfdm_b200_xla.so` (csrc/ffi/xla_ffi.cc) exist it provides
 
-    sparse_solve(A, b)         the reference's jax.custom_vjp function (sparse.py:207-308) with the
-                               forward and the adjoint solve as custom calls, the forward's
-                               workspace (Cholesky factor / coarse inverse) carried as a residual
-    register(structure_plan)   ->  callables for assemble / positions / state / adjoint_grads
-
-and registers the solver through the reference's own seam:
-    jax_fdm.equilibrium.sparse.register_sparse_solver({"gpu": spsolve_b200})   (sparse.py:167-199)
+    Ops(structure)             custom-call wrappers bound to one structure: assemble, solve (+ the
+                               factor-reusing solve), solve_from_q, spmm, positions, state,
+                               adjoint_grads, edge_loads(+vjp), loss_sqdist, and
+                               `nodes_free_positions`: the reference's jax.custom_vjp shape
+                               (sparse.py:207-308) with the forward and the adjoint solve as custom
+                               calls, the forward's workspace (Cholesky factor / coarse inverse)
+                               carried as a residual
+    spsolve_b200(structure)    -> a `(A: CSC, b) -> x` callable for the reference's own seam:
+        jax_fdm.equilibrium.sparse.register_sparse_solver({"gpu": spsolve_b200(structure)})  (sparse.py:167-199)
 """
 
 import ctypes
@@ -28,7 +30,8 @@ except ImportError as exc:  # pragma: no cover - the image has no jax
 from . import _lib as L
 
 _XLA_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfdm_b200_xla.so")
-_TARGETS = ["assemble", "solve", "spmm", "positions", "state", "state_vjp", "adjoint_grads"]
+_TARGETS = ["assemble", "solve", "solve_reuse", "solve_from_q", "spmm", "positions", "state", "state_vjp",
+            "adjoint_grads", "edge_loads", "edge_loads_vjp", "loss_sqdist"]
 _registered = False
 
 
@@ -71,11 +74,35 @@ class Ops:
             batch *= d
         nbytes = int(L.lib().fdm_workspace_bytes(self.s.plan, batch, solver))
         outs = (_f64(*lead, self.Nf, 3), _f64(batch, L.INFO_STRIDE), jax.ShapeDtypeStruct((max(nbytes, 16),), jnp.uint8))
-        # reuse_factor: the backward pass aliases the forward workspace onto the result buffer
         if workspace is None:
             return self._call("solve", outs, Kdata, rhs, solver=solver, max_iters=max_iters, tol=tol, reuse_factor=0)
-        return jax.ffi.ffi_call("fdm_b200_solve", outs, vmap_method="broadcast_all", input_output_aliases={2: 2})(
-            Kdata, rhs, workspace, plan=self.plan, solver=solver, max_iters=max_iters, tol=tol, reuse_factor=1)
+        # the backward pass: a second target with the workspace as a third OPERAND, aliased onto the workspace result
+        return jax.ffi.ffi_call("fdm_b200_solve_reuse", outs, vmap_method="broadcast_all", input_output_aliases={2: 2})(
+            Kdata, rhs, workspace, plan=self.plan, solver=solver, max_iters=max_iters, tol=tol)
+
+    def solve_from_q(self, q, xyz_fixed, loads, solver=L.SOLVER_CHOLESKY_BATCHED):
+        """K1 + K2 fused (fdm_solve_from_q): -> (x_free, info, workspace)."""
+        lead = q.shape[:-1]
+        batch = 1
+        for d in lead:
+            batch *= d
+        nbytes = int(L.lib().fdm_workspace_bytes(self.s.plan, batch, solver))
+        outs = (_f64(*lead, self.Nf, 3), _f64(batch, L.INFO_STRIDE), jax.ShapeDtypeStruct((max(nbytes, 16),), jnp.uint8))
+        return self._call("solve_from_q", outs, q, xyz_fixed, loads, solver=solver)
+
+    def spmm(self, Kdata, X):
+        return self._call("spmm", _f64(*X.shape), Kdata, X)
+
+    def edge_loads(self, xyz, loads_nodes, edges_load, is_local=False):
+        return self._call("edge_loads", _f64(*xyz.shape), xyz, loads_nodes, edges_load, is_local=int(is_local))
+
+    def edge_loads_vjp(self, xyz, edges_load, cot, is_local=False):
+        lead = xyz.shape[:-2]
+        return self._call("edge_loads_vjp", (_f64(*xyz.shape), _f64(*lead, self.E, 3)), xyz, edges_load, cot,
+                          is_local=int(is_local))
+
+    def loss_sqdist(self, x, x0):
+        return self._call("loss_sqdist", (_f64(*x.shape), _f64(*x.shape[:-2])), x, x0)
 
     def positions(self, x_free, xyz_fixed):
         return self._call("positions", _f64(*x_free.shape[:-2], self.N, 3), x_free, xyz_fixed)
@@ -113,3 +140,14 @@ class Ops:
 
         f.defvjp(fwd, bwd)
         return f(q, xyz_fixed, loads)
+
+
+def spsolve_b200(structure, **solve_kw):
+    """A solver for the reference's backend seam (sparse.py:167-199): `(A, b) -> x` with A the reference's CSC
+    StiffnessMatrix on this structure's pattern (only A.data is read) and b of shape (Nf, 3)."""
+    ops = Ops(structure)
+
+    def solve(A, b):
+        return ops.solve(A.data, b, **solve_kw)[0]
+
+    return solve

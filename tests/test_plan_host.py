@@ -88,3 +88,17 @@ def test_compute_on_host_plan_is_refused():
     s = EquilibriumStructureSparse(*datasets.arch_problem(10)[:3], device=None)
     rc = L.lib().fdm_spmm(s.plan, C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), 1, C.c_void_p(0))
     assert rc == -1 and b"host-only" in L.lib().fdm_last_error()
+
+
+def test_partition_with_more_components_than_parts():
+    """300 disjoint support-free-free-support cables: 300 components of the free-node graph against 148 aggregates.
+    Every row must have an owner in [0, parts) (rows left at -1 used to index out of bounds in pcg2_build)."""
+    k = 300
+    nodes = np.arange(4 * k)
+    edges = np.concatenate([np.array([[4 * c, 4 * c + 1], [4 * c + 1, 4 * c + 2], [4 * c + 2, 4 * c + 3]]) for c in range(k)])
+    sup = np.tile(np.array([1, 0, 0, 1]), k)
+    s = EquilibriumStructureSparse(nodes, edges, sup, device=None)
+    part = s.part_of_row
+    assert s.num_free == 2 * k and part.min() == 0 and part.max() == 147
+    assert np.bincount(part, minlength=148).min() >= 1
+    assert np.array_equal(part[0::2], part[1::2])        # a component is never split by the fallback

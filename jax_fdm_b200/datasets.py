@@ -28,6 +28,7 @@ __all__ = [
     "pillow_problem",
     "pillow_batch_q",
     "arch_problem",
+    "arch_benchmark_problem",
 ]
 
 
@@ -183,4 +184,23 @@ def arch_problem(num_segments: int = 10, span: float = 5.0, q0: float = -1.0,
     q = np.full(n - 1, q0)
     loads = np.zeros((n, 3))
     loads[supports == 0, 2] = pz
+    return Problem(nodes, edges, supports, q, xyz[np.flatnonzero(supports)], loads, xyz)
+
+
+def arch_benchmark_problem(num_vertices: int, span: float = 10.0, rho: float = 1.0, q0: float = -10.0) -> Problem:
+    """
+    BASELINE config 2, the analytical arch benchmark (tests/test_arch_benchmark.py:73-97): `num_vertices`
+    vertices evenly spaced on [-span/2, span/2] along x, the two ends anchored, every edge at q0, the uniform
+    load rho lumped into equal point loads (0, -rho span / n_v, 0) on EVERY vertex (supports included).
+    """
+    n = int(num_vertices)
+    nodes = np.arange(n, dtype=np.int64)
+    xyz = np.zeros((n, 3))
+    xyz[:, 0] = -span / 2.0 + span * np.arange(n) / (n - 1)
+    edges = np.stack((nodes[:-1], nodes[1:]), axis=1)
+    supports = np.zeros(n, dtype=np.int64)
+    supports[[0, n - 1]] = 1
+    q = np.full(n - 1, q0)
+    loads = np.zeros((n, 3))
+    loads[:, 1] = (-rho * span) / n
     return Problem(nodes, edges, supports, q, xyz[np.flatnonzero(supports)], loads, xyz)

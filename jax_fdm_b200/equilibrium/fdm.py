@@ -53,7 +53,7 @@ def fdm(nodes, edges, supports, q, xyz_fixed, loads, sparse=True, tmax=1, eta=1e
 
 def constrained_fdm(nodes, edges, supports, q, xyz_fixed, loads, optimizer, loss, bounds=(None, None), maxiter=100,
                     tol=1e-6, sparse=True, tmax=1, eta=1e-6, is_load_local=False, device=0, structure=None,
-                    callback=None, **solve_opts):
+                    callback=None, q_groups=None, **solve_opts):
     """
     `constrained_fdm` on arrays (fdm.py:177-308) with the force densities as the parameters: minimise `loss`
     over q within `bounds` with `optimizer` (jax_fdm_b200.optimization: LBFGSB, SLSQP, ...), then one forward
@@ -67,8 +67,8 @@ def constrained_fdm(nodes, edges, supports, q, xyz_fixed, loads, optimizer, loss
     if structure is None:
         structure = structure_from_arrays(nodes, edges, supports, sparse, device)
     problem = optimizer.problem(model, structure, loss, q0, xyz_fixed, loads, bounds=bounds, maxiter=maxiter, tol=tol,
-                                callback=callback)
-    q_opt = optimizer.solve(problem)
+                                callback=callback, q_groups=q_groups)
+    q_opt = problem.unpack(optimizer.solve(problem))[0]      # (E,): grouped parameters expanded to their edges
     state, _ = fdm(nodes, edges, supports, q_opt, xyz_fixed, loads, sparse=sparse, tmax=tmax, eta=eta,
                    is_load_local=is_load_local, device=device, structure=structure, **solve_opts)
     return state, structure, q_opt

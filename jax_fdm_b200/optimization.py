@@ -37,17 +37,33 @@ class Optimizer:
 
     def problem(self, model, structure, loss, q0, xyz_fixed, loads, bounds=(None, None), maxiter=100, tol=1e-6,
                 callback=None, opt_xyz_fixed=None, bounds_xyz_fixed=(None, None), opt_loads=None,
-                bounds_loads=(None, None)):
+                bounds_loads=(None, None), q_groups=None):
         """
         The flat parameter vector is [q, xyz_fixed[opt_xyz_fixed], loads[opt_loads]]: every force density, plus
         the support coordinates and nodal load components selected by the boolean masks (Ns,3) / (N,3) -- the
         parameter kinds of the reference (parameters/parameters.py: EdgeForceDensityParameter,
         NodeSupport{X,Y,Z}Parameter, NodeLoad{X,Y,Z}Parameter), as in its gridshell inverse-design examples.
+        `q_groups`: a list of edge-index arrays, each ONE parameter shared by its edges (the reference's
+        EdgeGroupForceDensityParameter, parameters/parameters.py; tests/test_arch_benchmark.py:107): the q part of the
+        flat vector is then [one value per group, the ungrouped edges in edge order]; a group starts from the mean of
+        its edges' q0 and its gradient is the sum of its edges' q_bar.
         """
         dev = torch.device("cuda", structure.device) if isinstance(structure.device, int) else torch.device(structure.device)
         xs0 = np.ascontiguousarray(xyz_fixed, dtype=np.float64)
         p0 = np.ascontiguousarray(loads, dtype=np.float64)
-        x0 = np.ascontiguousarray(q0, dtype=np.float64)
+        q_full0 = np.ascontiguousarray(q0, dtype=np.float64).reshape(-1)
+        x0 = q_full0
+        expand = None                                      # (E,) position in the packed q part of every edge
+        if q_groups:
+            slot = np.full(q_full0.size, -1, dtype=np.int64)
+            for gi, idx in enumerate(q_groups):
+                idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+                assert idx.size and np.all(slot[idx] < 0), "q_groups must be non-empty and disjoint"
+                slot[idx] = gi
+            rest = np.flatnonzero(slot < 0)
+            slot[rest] = len(q_groups) + np.arange(rest.size)
+            x0 = np.concatenate([[q_full0[np.asarray(idx, dtype=np.int64)].mean() for idx in q_groups], q_full0[rest]])
+            expand = torch.as_tensor(slot, device=dev)
         nq = x0.size
         mxs = None if opt_xyz_fixed is None else np.asarray(opt_xyz_fixed, dtype=bool).reshape(xs0.shape)
         mp = None if opt_loads is None else np.asarray(opt_loads, dtype=bool).reshape(p0.shape)
@@ -61,6 +77,8 @@ class Optimizer:
             """x (numpy) -> q, xyz_fixed, loads as leaf tensors on the device."""
             xt = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=dev)
             q = xt[:nq].clone().requires_grad_(True)
+            if expand is not None:                          # leaf = the packed vector; autograd sums a group's q_bar
+                q = (q, q.index_select(0, expand))
             xs, p = xs_t, p_t
             if mxs_t is not None:
                 xs = xs_t.clone()
@@ -72,9 +90,10 @@ class Optimizer:
 
         def loss_and_grad(x):                            # optimizer.py:365-370: jit(value_and_grad(loss))
             q, xs, p = unpack(x)
+            q_leaf, q = q if isinstance(q, tuple) else (q, q)
             val = loss(EquilibriumParametersState(q, xs, LoadState(p, 0.0, 0.0)), model, structure)
             val.backward()
-            grads = [q.grad]
+            grads = [q_leaf.grad]
             if mxs_t is not None:
                 grads.append(xs.grad[mxs_t])
             if mp_t is not None:
@@ -91,7 +110,7 @@ class Optimizer:
             hi = np.broadcast_to(np.inf if hi is None else hi, (n,))
             bnds += list(zip(lo, hi))
         prob = OptProblem(loss_and_grad, x0, bnds, self.name, tol, maxiter, callback)
-        prob.unpack = lambda x: tuple(t.detach().cpu().numpy() for t in unpack(x))
+        prob.unpack = lambda x: tuple((t[1] if isinstance(t, tuple) else t).detach().cpu().numpy() for t in unpack(x))
         return prob
 
     def solve(self, opt_problem):

@@ -44,9 +44,10 @@ GLOBAL_BATCH = PER_GPU_BATCH  # the CPU arm times a bounded sample of one GPU's 
 CABLENET_NX = 200
 E2E_CHUNKS = int(os.environ.get("FDM_BENCH_E2E_CHUNKS", "16"))
 DEV_CHUNKS = int(os.environ.get("FDM_BENCH_DEV_CHUNKS", "2"))   # slices of the device-resident step (own streams)
-# dram__bytes_read.sum + dram__bytes_write.sum of one chol_factor_mma_kernel launch (B = 4096), from
-# profiles/r01k_chol_final_ncu.txt (0.325 GB read + 0.960 GB written)
-NCU_TRAFFIC_CHOL_FWD = 1.295e9   # dram read+write of chol_factor_mma_kernel<0,4>, ncu --set full (profiles/r01n_chol_panel4_ncu.txt)
+SWEEP_NX = 2000                # one mesh far beyond L2 for the HBM-bound kernels' fractions (SURVEY.md §8d size sweep)
+WORKLOAD = (f"{PER_GPU_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} designs per GPU (841 free nodes, 1860 edges, "
+            "q_b = -2 + 0.1(U-0.5) seed b): forward solve + state + loss + adjoint solve + gradients; "
+            "BASELINE config 5 at N=1")
 
 
 def peaks():
@@ -169,12 +170,14 @@ def cpu_time_cablenet(reps):
 
 
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference path on ALL 4096 designs of the workload per step
+    (one process per host core), the step's own wall time as ms_per_step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     cores = len(os.sched_getaffinity(0))
-    sample = min(GLOBAL_BATCH, max(cores * 64, 512))
+    sample = GLOBAL_BATCH
     times = []
     for i in range(args.warmup + args.steps):
         dt = cpu_time_designs(range(sample), cores)
@@ -185,16 +188,15 @@ def run_reference(args):
     ms_cable = cpu_time_cablenet(2) * 1e3
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3 * GLOBAL_BATCH / sample,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{GLOBAL_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} designs (841 free nodes, 1860 edges, "
-                               "q_b = -2 + 0.1(U-0.5) seed b): forward solve + adjoint solve + gradients on the host "
-                               "cores (rank 0 only; the reference has no multi-device path)",
-                   "per_gpu_batch": GLOBAL_BATCH, "timed_sample_designs": sample},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": GLOBAL_BATCH, "global_batch": GLOBAL_BATCH,
+                   "where": "host cores, rank 0 only (the reference has no multi-device path): scipy SuperLU forward "
+                            "+ adjoint solve + closed-form gradients per design, one process per core"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {GLOBAL_BATCH} designs per step, one process per core; "
-                                   "numpy/scipy restatement of the reference CPU path (SuperLU fwd + adjoint)"},
+                         "sample": f"all {sample} designs of the workload per step, one process per core; "
+                                   "numpy/scipy restatement of the reference CPU path (sparse.py:147-149, 296)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "single_mesh": {"workload": f"cable-net {CABLENET_NX}x{CABLENET_NX}", "ms_per_solve": ms_cable,
                         "solves_per_s": 1e3 / ms_cable, "cores": 1},
@@ -218,6 +220,26 @@ def timed_steps(fn, stream, steps, flush, dist=None):
     return [a.elapsed_time(b) for a, b in ev]
 
 
+def ncu_counters():
+    """Counters of the dominant kernel from the committed ncu capture (profiles/ncu_counters.json, written by
+    profiles/summarize.py from `ncu --set full` of the same instance the step launches)."""
+    path = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def strict_bytes(s):
+    """SURVEY.md §8d's compulsory traffic per design of the whole forward + adjoint step (inputs read once,
+    outputs written once; the factor, intermediate right-hand sides and the state re-reads are NOT compulsory):
+    read q, write x_free, xyz and the state, write q_bar, loads_bar, xyz_fixed_bar, loss."""
+    E, N, Nf, Ns = s.num_edges, s.num_nodes, s.num_free, s.num_supports
+    fwd = 8 * E + 24 * Nf + 24 * N + (24 * E + 8 * E + 8 * E + 24 * N)
+    rev = 8 * E + 24 * N + 24 * Ns + 8
+    return fwd + rev
+
+
 def kernel_table(pipe, s, B, steps, flush, hbm):
     """Each C-ABI call of the step timed alone (CUDA events on pipe.stream, L2 flushed before every
     launch): algorithmic bytes per launch, time, achieved GB/s and fraction of the measured HBM peak."""
@@ -229,18 +251,18 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
     E, N, Nf, Ns, nnz = s.num_edges, s.num_nodes, s.num_free, s.num_supports, s.nnz
     fac = 8 * 1024 * ((Nf + 31) // 32)                       # factor columns, 32 doubles each, rows padded to 32
     Y = pipe.rhs.clone()
-    stage_opts = {m: L.SolveOpts(pipe.solver_id, 0, 0.0, 0, 0, m) for m in (1, 4)}
+    stage_opts = {m: L.SolveOpts(pipe.solver_id, 0, 0.0, 0, 0, m, 0) for m in (1, 4)}
     calls = [
         ("assemble (K1)", 8 * E + 8 * nnz + 24 * Nf,
          lambda: lib.fdm_assemble(s.plan, P(pipe.q), P(pipe.xyz_fixed), P(pipe.loads), P(pipe.K), P(pipe.rhs), B, E, 0, 0, st)),
-        ("band Cholesky forward solve (K2b: the two launches below)", 8 * nnz + 48 * Nf + fac,
-         lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
-                               C.byref(pipe.opts_f), st)),
-        ("  chol_factor_mma_kernel (factorisation, fused forward substitution, diagonal blocks inverted)",
-         8 * nnz + 24 * Nf + fac + fac // 8,
+        ("chol_factor_mma_kernel<FROM_Q=1,PW=4> (the instance the step launches: rows assembled from q, factorisation, "
+         "fused forward substitution, diagonal blocks inverted)", 8 * E + fac + fac // 8,
+         lambda: lib.fdm_solve_from_q(s.plan, P(pipe.q), P(pipe.xyz_fixed), P(pipe.loads), P(pipe.x), P(pipe.info_f), P(pipe.ws),
+                                      pipe.ws.numel(), B, E, 0, 0, C.byref(stage_opts[1]), st)),
+        ("chol_factor_mma_kernel<FROM_Q=0,PW=4> (the same on K.data)", 8 * nnz + 24 * Nf + fac + fac // 8,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(stage_opts[1]), st)),
-        ("  chol_subst_kernel (backward substitution, factor streamed by TMA)", fac + fac // 8 + 24 * Nf,
+        ("chol_subst_kernel (backward substitution, factor streamed by TMA)", fac + fac // 8 + 24 * Nf,
          lambda: lib.fdm_solve(s.plan, P(pipe.K), P(pipe.rhs), P(pipe.x), P(pipe.info_f), P(pipe.ws), pipe.ws.numel(), B,
                                C.byref(stage_opts[4]), st)),
         ("positions", 24 * Nf + 24 * N,
@@ -269,6 +291,77 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
     return out
 
 
+def sweep_large_mesh(nx, steps, flush_buf, hbm):
+    """The HBM-bound kernels (assembly, SpMM, state, gradients) on ONE nx x nx cable-net whose working set is far
+    beyond L2 -- SURVEY.md §8d's size sweep, the point where the >= 60 % of HBM target is judged."""
+    import ctypes as C
+    import torch
+    from jax_fdm_b200 import _lib as L
+    from jax_fdm_b200 import datasets
+    import jax_fdm_b200.equilibrium as eq
+    lib = L.lib()
+    dev = flush_buf.device
+    prob = datasets.cablenet_problem(nx)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=dev.index)
+    E, N, Nf, Ns, nnz = s.num_edges, s.num_nodes, s.num_free, s.num_supports, s.nnz
+    stream = torch.cuda.Stream(device=dev)
+    st = C.c_void_p(stream.cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    z = lambda *shape: torch.zeros(shape, dtype=torch.float64, device=dev)
+    q, xs, loads = (torch.as_tensor(a, device=dev) for a in (prob.q, prob.xyz_fixed, prob.loads))
+    xyz = torch.as_tensor(prob.xyz0, device=dev).contiguous()
+    K, rhs, y = z(nnz), z(Nf, 3), z(Nf, 3)
+    x = xyz[torch.as_tensor(s.indices_free, device=dev)].contiguous()
+    lam = torch.as_tensor(np.random.default_rng(1).standard_normal((Nf, 3)), device=dev)
+    vec, lng, frc, res, qb, lb, xb = z(E, 3), z(E), z(E), z(N, 3), z(E), z(N, 3), z(Ns, 3)
+
+    def flush():
+        with torch.cuda.stream(stream):
+            flush_buf.fill_(1)
+    calls = [
+        ("assemble (K1)", 16 * E + 12 * nnz + 52 * Nf + 24 * Ns,
+         lambda: lib.fdm_assemble(s.plan, P(q), P(xs), P(loads), P(K), P(rhs), 1, E, 0, 0, st)),
+        ("SpMM K X (3 rhs)", 12 * nnz + 52 * Nf, lambda: lib.fdm_spmm(s.plan, P(K), P(x), P(y), 1, st)),
+        ("state (K4)", 56 * E + 72 * N,
+         lambda: lib.fdm_state(s.plan, P(q), P(xyz), P(loads), P(vec), P(lng), P(frc), P(res), 1, E, 0, st)),
+        ("adjoint gradients (K3)", 24 * E + 24 * Nf + 48 * N + 24 * Ns,
+         lambda: lib.fdm_adjoint_grads(s.plan, P(q), P(xyz), P(lam), P(qb), P(lb), P(xb), 1, E, 0, st)),
+    ]
+    out = []
+    for name, per, fn in calls:
+        for _ in range(3):
+            L.check(fn())
+        ms = float(np.median(timed_steps(lambda: L.check(fn()), stream, steps, flush)))
+        gbs = per / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "ms": ms, "algorithmic_bytes_per_launch": per, "achieved_gbs": gbs,
+                    "frac_of_measured_hbm": gbs / hbm})
+    return {"workload": f"one cable-net {nx}x{nx} ({N} nodes, {E} edges): working set beyond L2", "kernels": out}
+
+
+def parity_sample(fa, prob, so, qb, x0, designs):
+    """Sampled designs of the timed batch against the CPU oracle (the checker, never the thing measured)."""
+    import oracle
+    x = fa.array("x").cpu().numpy()
+    q_bar = fa.array("q_bar").cpu().numpy()
+    loss = fa.array("loss").cpu().numpy()
+
+    def cot(st, xf):
+        c = np.zeros_like(st["xyz"])
+        c[so.indices_free] = xf - x0
+        return {"xyz": c}
+
+    rel = lambda a, b: float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    ex = eq_ = el = 0.0
+    for b in designs:
+        ref = oracle.forward_adjoint(qb[b], prob.xyz_fixed, prob.loads, so, cot)
+        lref = 0.5 * np.sum((ref["x_free"] - x0) ** 2)
+        ex, eq_ = max(ex, rel(x[b], ref["x_free"])), max(eq_, rel(q_bar[b], ref["q_bar"]))
+        el = max(el, abs(loss[b] - lref) / lref)
+    return {"designs_checked": len(designs), "designs": [int(b) for b in designs], "max_rel_err_x_free": ex,
+            "max_rel_err_loss": el, "max_rel_err_q_bar": eq_, "tolerance": {"x_free": 1e-10, "q_bar": 1e-8},
+            "ok": bool(ex <= 1e-10 and el <= 1e-10 and eq_ <= 1e-8), "against": "oracle/ (numpy/scipy SuperLU)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -276,7 +369,7 @@ def run_ours(args):
     from jax_fdm_b200 import datasets
     import jax_fdm_b200.equilibrium as eq
     from jax_fdm_b200.distributed import shard_range, total_loss
-    from jax_fdm_b200.pipeline import ChunkedForwardAdjoint, ForwardAdjoint
+    from jax_fdm_b200.pipeline import ForwardAdjoint, NativeForwardAdjoint
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -297,42 +390,41 @@ def run_ours(args):
     lo, hi = shard_range(B * world, rank, world)
     qb = datasets.pillow_batch_q(prob.edges.shape[0], lo, hi - lo)
     x0 = prob.xyz0[s.indices_free]
-    # launch-by-launch table: the unfused sequence (assembly kernel, then the solve on K.data)
-    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local, fused_assembly=False)
-    pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
-    e2e_pipe = ChunkedForwardAdjoint(s, B, chunks=E2E_CHUNKS, solver="cholesky", device=local)
-    e2e_pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
-    # the timed device-resident step: the batch in DEV_CHUNKS slices on their own streams (fork/join on
-    # dev_pipe.stream), so one slice's bandwidth-bound substitutions overlap another's factorisation
-    dev_pipe = ChunkedForwardAdjoint(s, B, chunks=DEV_CHUNKS, solver="cholesky", device=local)
-    dev_pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+    # the timed device-resident step: the library-owned pipeline (fdm_fa_*), the batch in DEV_CHUNKS slices on their
+    # own streams inside ONE CUDA graph (fork / join), so one slice's bandwidth-bound substitutions overlap
+    # another's factorisation; one ctypes call per step
+    dev_fa = NativeForwardAdjoint(s, B, chunks=DEV_CHUNKS, solver="cholesky", device=local)
+    dev_fa.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+    # end to end: host q in, host loss + q_bar out through the same object with more, smaller slices
+    e2e_fa = NativeForwardAdjoint(s, B, chunks=E2E_CHUNKS, solver="cholesky", device=local)
+    e2e_fa.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    main_stream = dev_fa.stream
 
-    def flush():
-        with torch.cuda.stream(pipe.stream):
-            flush_buf.fill_(1)
+    def flush_on(stream):
+        def f():
+            with torch.cuda.stream(stream):
+                flush_buf.fill_(1)
+        return f
 
+    flush_dev = flush_on(main_stream)
     total = torch.zeros(1, dtype=torch.float64, device=dev)
 
-    def reduce_loss(p):
+    def reduce_loss(loss_vec, stream):
         if world > 1:
-            with torch.cuda.stream(p.stream):
-                total_loss(p.loss, out=total)             # local sum + one 8-byte NCCL all-reduce
-
-    def flush_dev():
-        with torch.cuda.stream(dev_pipe.stream):
-            flush_buf.fill_(1)
+            with torch.cuda.stream(stream):
+                total_loss(loss_vec, out=total)           # fdm_batch_sum + one 8-byte NCCL all-reduce
+    dev_loss, e2e_loss = dev_fa.array("loss"), e2e_fa.array("loss")
 
     def step_dev():
-        dev_pipe.step()
-        reduce_loss(dev_pipe)
+        dev_fa.step(main_stream)
+        reduce_loss(dev_loss, main_stream)
 
     def step_e2e():
-        e2e_pipe()
+        e2e_fa()
         if world > 1:
-            with torch.cuda.stream(pipe.stream):
-                total_loss(e2e_pipe.loss, out=total)
-            pipe.stream.synchronize()
+            reduce_loss(e2e_loss, main_stream)
+            main_stream.synchronize()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -348,7 +440,7 @@ def run_ours(args):
         sampler.start()
     barrier()
     wall0 = time.perf_counter()
-    t_dev = timed_steps(step_dev, dev_pipe.stream, steps, flush_dev)
+    t_dev = timed_steps(step_dev, main_stream, steps, flush_dev)
     barrier()
     wall = time.perf_counter() - wall0
     # end to end: pinned host q in, loss + q_bar out, every step
@@ -357,20 +449,28 @@ def run_ours(args):
     barrier()
     t_e2e = []
     for _ in range(steps):
-        flush()
+        flush_dev()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         step_e2e()
-        torch.cuda.synchronize(dev)
         t_e2e.append((time.perf_counter() - t0) * 1e3)
     barrier()
     # the same steps enqueued back to back (throughput mode for independent batches): every step still copies
     # its q in and its loss + q_bar out, but step k+1's copy-in overlaps step k's kernels and copy-out
     t0 = time.perf_counter()
     for _ in range(steps):
-        e2e_pipe.enqueue()
-    e2e_pipe.synchronize()
+        e2e_fa.enqueue()
+    e2e_fa.synchronize()
     t_pipelined = (time.perf_counter() - t0) * 1e3 / steps
+    barrier()
+    # what the link alone can do for this call: the same copies, same slices and streams, no kernels
+    t_copy = []
+    for _ in range(steps):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_fa.enqueue_copies_only()
+        e2e_fa.synchronize()
+        t_copy.append((time.perf_counter() - t0) * 1e3)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -382,71 +482,118 @@ def run_ours(args):
 
     sum_dev = reduce_max(sum(t_dev))
     sum_e2e = reduce_max(sum(t_e2e))
+    sum_copy = reduce_max(sum(t_copy))
     t_pipelined = reduce_max(t_pipelined)
-    status_ok = all(bool((p_.info_f[:, 0] == 0).all().item() and (p_.info_a[:, 0] == 0).all().item())
-                    for p_ in dev_pipe.parts)
+    dev_fa.step(main_stream)                              # leave the device arrays of a plain step for the checks below
+    main_stream.synchronize()
+    status_ok = bool((dev_fa.array("info_f")[:, 0] == 0).all().item() and (dev_fa.array("info_a")[:, 0] == 0).all().item())
 
     # diagnostic at N > 1: the same steps without the loss all-reduce (what the collective + the lock-step
     # it imposes on the ranks cost), and the spread of the per-rank times
     scaling_diag = None
     if world > 1:
         barrier()
-        t_local = timed_steps(dev_pipe.step, dev_pipe.stream, steps, flush_dev)
+        t_local = timed_steps(lambda: dev_fa.step(main_stream), main_stream, steps, flush_dev)
         barrier()
-        mine = torch.tensor([sum(t_dev) / steps, sum(t_local) / steps], dtype=torch.float64, device=dev)
+        mine = torch.tensor([sum(t_dev) / steps, sum(t_local) / steps, sum(t_e2e) / steps, sum(t_copy) / steps],
+                            dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = torch.stack(allr).cpu().numpy()
         scaling_diag = {"ms_per_step_with_allreduce_per_rank": [float(v) for v in per_rank[:, 0]],
-                        "ms_per_step_without_allreduce_per_rank": [float(v) for v in per_rank[:, 1]]}
+                        "ms_per_step_without_allreduce_per_rank": [float(v) for v in per_rank[:, 1]],
+                        "e2e_ms_per_step_per_rank": [float(v) for v in per_rank[:, 2]],
+                        "copies_only_ms_per_step_per_rank": [float(v) for v in per_rank[:, 3]]}
 
-    # every kernel of the step alone, for the roofline table (rank 0's numbers are reported)
-    kernels = kernel_table(pipe, s, B, max(3, min(steps, 10)), flush, hbm)
-
-    # BASELINE config 5 exactly (fixed global batch 4096 cut over the ranks), strong scaling, N > 1 only
-    fixed = None
+    # BASELINE config 5 exactly (fixed global batch 4096 cut over the ranks), strong scaling -- at every N
+    lo5, hi5 = shard_range(CONFIG5_BATCH, rank, world)
     if world > 1:
-        lo5, hi5 = shard_range(CONFIG5_BATCH, rank, world)
-        p5 = ForwardAdjoint(s, batch=hi5 - lo5, solver="cholesky", device=local)
+        p5 = NativeForwardAdjoint(s, hi5 - lo5, chunks=1, solver="cholesky", device=local)
         p5.set_inputs(datasets.pillow_batch_q(prob.edges.shape[0], lo5, hi5 - lo5), prob.xyz_fixed, prob.loads, x0)
+        p5_loss = p5.array("loss")
 
         def step5():
-            p5.step()
-            reduce_loss(p5)
+            p5.step(main_stream)
+            reduce_loss(p5_loss, main_stream)
         for _ in range(warmup):
             step5()
         barrier()
+        t5 = reduce_max(sum(timed_steps(step5, main_stream, steps, flush_dev)))
+        p5.close()
+    else:
+        t5 = sum_dev
+    fixed = {"workload": f"{CONFIG5_BATCH} designs in total, {hi5 - lo5} per GPU", "scaling": "strong",
+             "ms_per_step": t5 / steps, "value": CONFIG5_BATCH / (t5 / steps * 1e-3), "unit": UNIT}
 
-        def flush5():
-            with torch.cuda.stream(p5.stream):
-                flush_buf.fill_(1)
-        t5 = reduce_max(sum(timed_steps(step5, p5.stream, steps, flush5)))
-        fixed = {"workload": f"{CONFIG5_BATCH} designs in total, {hi5 - lo5} per GPU", "scaling": "strong",
-                 "ms_per_step": t5 / steps, "value": CONFIG5_BATCH / (t5 / steps * 1e-3), "unit": UNIT}
+    line_extra = {}
+    if rank == 0:
+        # ---- parity at the timed size: sampled designs of rank 0's shard against the oracle
+        import oracle
+        so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
+        rng = np.random.default_rng(0)
+        sample = sorted({0, 1, B // 2 - 1, B // 2, 2367, 2368, B - 2, B - 1} | set(int(b) for b in rng.choice(B, 8, replace=False)))
+        line_extra["parity"] = parity_sample(dev_fa, prob, so, qb, x0, sample)
+
+        # ---- the public model API on the same batch: EquilibriumModelSparse.__call__ + Loss + backward (autograd
+        #      bookkeeping, per-call allocations, no CUDA graph): what API-level overhead costs
+        from jax_fdm_b200 import goals as G, losses as LS
+        free = s.indices_free
+        api_loss = LS.Loss(LS.SquaredError([G.NodePointGoal(int(prob.nodes[n]), t) for n, t in zip(free, x0)], alpha=0.5))
+        model = eq.EquilibriumModelSparse(tmax=1)
+        q_t = torch.as_tensor(qb, device=dev)
+        xs_t, p_t = torch.as_tensor(prob.xyz_fixed, device=dev), torch.as_tensor(prob.loads, device=dev)
+        api_out = {}
+
+        def api_step():
+            q_leaf = q_t.detach().requires_grad_(True)
+            val = api_loss(eq.EquilibriumParametersState(q_leaf, xs_t, eq.LoadState(p_t, 0.0, 0.0)), model, s)
+            val.backward(torch.ones_like(val))
+            api_out["loss"], api_out["q_bar"] = val.detach(), q_leaf.grad
+        cur = torch.cuda.current_stream(dev)
+        for _ in range(3):
+            api_step()
+        t_api = timed_steps(api_step, cur, max(3, min(steps, 10)), flush_on(cur))
+        ref_loss, ref_qbar = dev_fa.array("loss"), dev_fa.array("q_bar")
+        line_extra["api_path"] = {
+            "ms_per_step": float(np.mean(t_api)), "value": B / (float(np.mean(t_api)) * 1e-3), "unit": UNIT,
+            "how": "EquilibriumModelSparse(tmax=1)(params, structure) + losses.Loss(SquaredError(NodePointGoal x "
+                   f"{len(free)}, alpha=0.5)) + .backward() on the same {B} designs, device-resident, torch autograd "
+                   "nodes over the same kernels, per-call allocations, no CUDA graph",
+            "max_rel_diff_loss_vs_pipeline": float(((api_out["loss"] - ref_loss).abs() / ref_loss.abs()).max().item()),
+            "max_rel_diff_q_bar_vs_pipeline": float(((api_out["q_bar"] - ref_qbar).abs().max() / ref_qbar.abs().max()).item())}
+        del q_t, api_out
+        torch.cuda.empty_cache()
+
+    # every kernel of the step alone, for the roofline table (rank 0's numbers are reported)
+    pipe = ForwardAdjoint(s, batch=B, solver="cholesky", device=local, fused_assembly=False)
+    pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+    pipe.step()
+    pipe.stream.synchronize()
+    kernels = kernel_table(pipe, s, B, max(3, min(steps, 10)), flush_on(pipe.stream), hbm)
+    del pipe
+    torch.cuda.empty_cache()
 
     # ---------------- second workload: one 200x200 cable-net (rank 0 only) ----------------
-    single = None
+    single = sweep = None
     if rank == 0:
         cprob = datasets.cablenet_problem(CABLENET_NX)
         cs = eq.EquilibriumStructureSparse(cprob.nodes, cprob.edges, cprob.supports, device=local)
-        cpipe = ForwardAdjoint(cs, batch=1, solver="auto", tol=1e-12, device=local)
-        cpipe.set_inputs(cprob.q[None], cprob.xyz_fixed, cprob.loads, cprob.xyz0[cs.indices_free])
+        cfa = NativeForwardAdjoint(cs, 1, solver="auto", tol=1e-12, device=local)
+        cfa.set_inputs(cprob.q[None], cprob.xyz_fixed, cprob.loads, cprob.xyz0[cs.indices_free])
         for _ in range(3):
-            cpipe.step()
-        cpipe.stream.synchronize()
+            cfa.step(main_stream)
+        main_stream.synchronize()
         k = max(3, min(steps, 10))
-
-        def cflush():
-            with torch.cuda.stream(cpipe.stream):
-                flush_buf.fill_(1)
-        tc = timed_steps(cpipe.step, cpipe.stream, k, cflush)
-        inf_f, inf_a = cpipe.info_f.cpu().numpy()[0], cpipe.info_a.cpu().numpy()[0]
+        tc = timed_steps(lambda: cfa.step(main_stream), main_stream, k, flush_dev)
+        inf_f, inf_a = cfa.array("info_f").cpu().numpy()[0], cfa.array("info_a").cpu().numpy()[0]
         single = {"workload": f"cable-net {CABLENET_NX}x{CABLENET_NX}, 4 corners fixed, q~U[0.5,2], fwd+adjoint",
                   "ms_per_solve": float(np.mean(tc)), "solves_per_s": 1e3 / float(np.mean(tc)),
-                  "solver": "two-level PCG (persistent)" if cpipe.capturable else "Jacobi-PCG (multi-kernel)",
+                  "solver": "two-level PCG (persistent)",
                   "iters_fwd": int(inf_f[1]), "iters_adj": int(inf_a[1]),
                   "relres_fwd": float(inf_f[2]), "relres_adj": float(inf_a[2]),
                   "status": [int(inf_f[0]), int(inf_a[0])]}
+        cfa.close()
+        sweep = sweep_large_mesh(SWEEP_NX, 5, flush_buf, hbm)
 
     if world > 1:
         barrier()
@@ -454,51 +601,76 @@ def run_ours(args):
     if rank != 0:
         return None
 
-    dom = kernels[2]                                     # chol_factor_mma_kernel, the largest share of the step
+    dom = kernels[1]                                     # the factor kernel instance the step launches (FROM_Q = 1)
     ms_per_step = sum_dev / steps
     value = B * world / (ms_per_step * 1e-3)
-    e2e_value = B * world / (sum_e2e / steps * 1e-3)
+    e2e_ms = sum_e2e / steps
+    e2e_value = B * world / (e2e_ms * 1e-3)
+    copy_ms = sum_copy / steps
+    ctr = ncu_counters().get("chol_factor_mma_kernel<1,4,0>", {})
+    strict = strict_bytes(s)
+    E, Nf = s.num_edges, s.num_free
+    fac_strict = 8 * E + 24 * Nf                         # the factor kernel's compulsory share: q in (x out comes later)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{B} x pillow {PILLOW_NX}x{PILLOW_NX} designs per GPU (841 free nodes, 1860 edges, "
-                               "q_b = -2 + 0.1(U-0.5) seed b): forward solve + state + loss + adjoint solve + gradients; "
-                               "BASELINE config 5 at N=1",
+        "config": {"workload": WORKLOAD,
                    "per_gpu_batch": B, "global_batch": B * world, "solver": "batched band Cholesky, one warp per design",
                    "l2": "flushed between timed steps (256 MiB write, outside the events)",
-                   "device_step": f"{DEV_CHUNKS} slices of the batch on their own streams, forked from and joined to the "
-                                  "timed stream (CUDA events on it bracket the whole step); the factorisation "
-                                  "assembles its rows from q in place (fdm_solve_from_q), the `kernels` table times "
-                                  "the unfused launches",
+                   "device_step": f"library-owned pipeline (fdm_fa_step_device): {DEV_CHUNKS} slices of the batch on their "
+                                  "own streams inside one CUDA graph, forked from and joined to the timed stream (CUDA "
+                                  "events on it bracket the whole step); the factorisation assembles its rows from q in "
+                                  "place (fdm_solve_from_q)",
                    "parallelism": f"designs sharded x{world}, no data-path collective"
                                   + (", 8-byte loss all-reduce (NCCL) per step" if world > 1 else "")},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_pipe.h2d_bytes * world,
-                "d2h_bytes_per_step": e2e_pipe.d2h_bytes * world, "ms_per_step": sum_e2e / steps,
-                "how": f"pinned host q -> device, step, loss + q_bar -> pinned host, {E2E_CHUNKS} chunks on "
-                       "separate streams so copies overlap kernels; host wall clock, synchronised both sides of "
-                       "EVERY step",
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_fa.h2d_bytes * world,
+                "d2h_bytes_per_step": e2e_fa.d2h_bytes * world, "ms_per_step": e2e_ms,
+                "how": f"fdm_fa_run_host: pinned host q -> device, forward + adjoint, loss + q_bar -> pinned host, in "
+                       f"{E2E_CHUNKS} slices on their own streams so copies overlap kernels; one C call per step; host "
+                       "wall clock, synchronised both sides of EVERY step",
+                "copy_roofline": {"ms_per_step": copy_ms,
+                                  "gbs_per_gpu_each_way": e2e_fa.h2d_bytes / (copy_ms * 1e-3) / 1e9,
+                                  "e2e_over_copy": e2e_ms / copy_ms,
+                                  "how": "the same cudaMemcpyAsync calls (same slices, streams, pinned buffers) with no "
+                                         "kernels between them, all ranks at once: what the host <-> device links deliver"},
                 "pipelined": {"value": B * world / (t_pipelined * 1e-3), "unit": UNIT, "ms_per_step": t_pipelined,
                               "how": "the same K steps enqueued back to back and synchronised once: step k+1's copy-in "
                                      "overlaps step k's kernels and copy-out (independent batches; an optimiser loop "
                                      "that needs step k's gradient before step k+1 gets the synchronous number)"}},
-        "gpu_launches": dev_pipe.launches_per_step * steps,
-        "roofline": {"kernel": dom["kernel"].strip(), "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm,
-                     "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm, "traffic": NCU_TRAFFIC_CHOL_FWD,
+        "gpu_launches": dev_fa.launches_per_step * steps,
+        "roofline": {"kernel": "chol_factor_mma_kernel<FROM_Q=1,PW=4> (factorisation from q, fused forward substitution)",
+                     "bound": "hbm", "achieved": dom["achieved_gbs"], "peak": hbm,
+                     "unit": "GB/s", "frac": dom["achieved_gbs"] / hbm, "traffic": ctr.get("dram_bytes"),
+                     "traffic_source": ctr.get("source"),
                      "peak_source": hbm_src, "kernel_ms": dom["ms"],
                      "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"],
+                     "algorithmic_bytes_note": "q read + the factor (32 doubles per column) and forward-substituted "
+                                               "right-hand sides written: what THIS design must move; SURVEY §8d's "
+                                               "compulsory input is the q read alone (`strict`)",
+                     "strict": {"bytes_per_launch": fac_strict * B,
+                                "achieved": fac_strict * B / (dom["ms"] * 1e-3) / 1e9,
+                                "frac": fac_strict * B / (dom["ms"] * 1e-3) / 1e9 / hbm},
                      "share_of_step": dom["ms"] / ms_per_step,
-                     "note": "timed alone on K.data (template instance <FROM_Q=0>); inside the step the <FROM_Q=1> "
-                             "instance runs, which reads q (15 KB per design) instead of K.data (33 KB)"},
+                     "limiter": "latency / issue: the 841-pivot dependency chain of one warp per design at "
+                                "register-capped occupancy; neither HBM nor a math pipe is near its limit (ncu `counters`)",
+                     "counters": {k: ctr.get(k) for k in ("warps_active_pct", "l1_data_pipe_pct", "dmma_pipe_pct",
+                                                          "fp64_pipe_pct", "dram_pct", "duration_us", "source")}},
+        "step_roofline": {"strict_bytes_per_step": strict * B,
+                          "achieved": strict * B / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
+                          "frac": strict * B / (ms_per_step * 1e-3) / 1e9 / hbm,
+                          "note": "SURVEY.md §8d compulsory bytes of the whole forward + adjoint step (q in; x_free, xyz, "
+                                  "state, loss, q_bar, loads_bar, xyz_fixed_bar out) over the timed step"},
         "kernels": kernels,
+        "sweep_large_mesh": sweep,
+        "config5_fixed_global_batch": fixed,
         "wall_s_timed_region": wall,
         "solve_status_ok": status_ok and (single is None or single["status"] == [0, 0]),
         "single_mesh": single,
     }
-    if fixed:
-        line["config5_fixed_global_batch"] = fixed
+    line.update(line_extra)
     if scaling_diag:
         line["scaling_diagnostic"] = scaling_diag
     if world == 1:

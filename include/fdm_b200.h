@@ -143,6 +143,8 @@ typedef struct fdm_solve_opts {
                            launches to issue (1 factorisation [+ its signed second pass], 2 diagonal-block inversion
                            [separate launch at half bandwidth 31 only], 4 substitution),
                            so that a benchmark can time each kernel of one solve on its own */
+  int32_t nan_on_failure; /* nonzero: a design whose status is not FDM_STATUS_OK gets x = NaN (what the reference's
+                           solvers hand to the optimiser's NaN check, optimizer.py:372-380); needs d_info */
 } fdm_solve_opts;
 
 size_t fdm_workspace_bytes(const fdm_plan* plan, int64_t batch, int32_t solver);
@@ -310,6 +312,68 @@ int fdm_goals_loss(const fdm_plan* plan, const fdm_goal_program* program, const 
  * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */
 int fdm_loss_sqdist(const double* d_x, const double* d_x0, double* d_g, double* d_loss,
                     int64_t n_per_design, int64_t batch, int64_t x0_stride, void* stream);
+
+/* ---- the method-by-method route's transposes ------------------------------------------------------
+ * Kbar.data[k] = sign * sum_xyz a[row_k] . b[col_k] on the plan's pattern: the cotangent of K that
+ * sparse_solve_bwd hands back (sparse.py:299-306, a = lam, b = x, sign = -1) and the VJP of `K @ x`
+ * (a = cotangent, b = x, sign = +1).   a, b (B,Nf,3) -> Kbar (B,nnz) */
+int fdm_kbar_pattern(const fdm_plan* plan, const double* d_a, const double* d_b, double* d_Kbar_data, double sign,
+                     int64_t batch, void* stream);
+/* transpose of stiffness_matrix (models.py:1069-1077): q_bar (B,E) from Kbar.data (B,nnz); overwritten */
+int fdm_stiffness_vjp(const fdm_plan* plan, const double* d_Kbar_data, double* d_q_bar, int64_t batch, void* stream);
+
+/* out[i] = sum_b in[b, i], fixed summation order: the local half of the two exchanges a sharded batch has (the
+ * scalar loss, n = 1, and the gradient of a parameter shared by all designs), before the NCCL all-reduce. */
+int fdm_batch_sum(const double* d_in /*(B,n)*/, double* d_out /*(n)*/, int64_t batch, int64_t n, void* stream);
+
+/* ---- value and gradient of a loss over a batch, host in / host out ------------------------------
+ * Replaces `jit(value_and_grad(loss_fn))(params)` (optimization/optimizers/optimizer.py:365-370) and the
+ * vmap over designs of visualization/plotters/loss_plotter.py:98-103 for parameters = force densities:
+ * one object that owns the device buffers, streams, events and CUDA graphs of the whole forward + adjoint
+ * pass, so a step costs the host a handful of driver calls.  The batch is cut into `chunks` contiguous
+ * slices; slice c copies its q in, runs (fdm_solve_from_q | fdm_assemble + fdm_solve) -> fdm_positions ->
+ * fdm_state -> loss and cotangents -> fdm_solve with the stored factor -> fdm_adjoint_grads, and copies its
+ * loss and q_bar out, all on its own stream, so copies and kernels of different slices overlap.
+ * Loss: L_b = 1/2 |x_free - x0|^2 (default, fdm_loss_sqdist) or a goal program (fdm_fa_set_goal_program:
+ * fdm_goals_loss + fdm_state_vjp + the transposes).  A design whose solve fails yields NaN loss / gradient. */
+typedef struct fdm_fa fdm_fa;
+typedef struct fdm_fa_opts {
+  int32_t chunks;      /* slices of the batch (<= 0 -> 1)                                              */
+  int32_t with_state;  /* also write vectors / lengths / forces / residuals (always on with a goal program) */
+  int32_t solver;      /* FDM_SOLVER_*                                                                   */
+  int32_t use_graph;   /* replay each slice (and the device-resident step) as a CUDA graph when capturable */
+  int32_t max_iters;   /* PCG                                                                            */
+  double tol;          /* PCG; <= 0 -> 1e-12                                                             */
+} fdm_fa_opts;
+int fdm_fa_create(const fdm_plan* plan, int64_t batch, const fdm_fa_opts* opts, fdm_fa** out);  /* allocates; synchronous */
+void fdm_fa_destroy(fdm_fa* fa);
+/* shared by the batch: xyz_fixed (Ns,3), loads (N,3), x0 (Nf,3) [may be NULL with a goal program]; synchronous */
+int fdm_fa_set_constants(fdm_fa* fa, const double* h_xyz_fixed, const double* h_loads, const double* h_x0);
+/* `h_program`: a fdm_goal_program whose arrays are HOST pointers; copied to the device; synchronous */
+int fdm_fa_set_goal_program(fdm_fa* fa, const fdm_goal_program* h_program);
+int fdm_fa_set_q(fdm_fa* fa, const double* h_q /*(B,E)*/);                       /* synchronous upload */
+/* one forward + adjoint pass on the q resident on the device; asynchronous, ordered on `stream` (fork / join) */
+int fdm_fa_step_device(fdm_fa* fa, void* stream);
+/* end to end: h_q (B,E) in, h_loss (B) and h_q_bar (B,E) [may be NULL] out.  Pinned host memory
+ * (fdm_host_alloc) makes the copies asynchronous.  enqueue + wait = run. */
+int fdm_fa_enqueue_host(fdm_fa* fa, const double* h_q, double* h_loss, double* h_q_bar);
+int fdm_fa_wait(fdm_fa* fa);
+/* measurement only: the copies of fdm_fa_enqueue_host without the kernels (the link's ceiling for this call) */
+int fdm_fa_enqueue_copies_only(fdm_fa* fa, const double* h_q, double* h_loss, double* h_q_bar);
+int fdm_fa_run_host(fdm_fa* fa, const double* h_q, double* h_loss, double* h_q_bar);
+enum {
+  FDM_FA_Q = 0, FDM_FA_X_FREE = 1, FDM_FA_XYZ = 2, FDM_FA_LOSS = 3, FDM_FA_Q_BAR = 4, FDM_FA_LOADS_BAR = 5,
+  FDM_FA_XYZ_FIXED_BAR = 6, FDM_FA_INFO_FORWARD = 7, FDM_FA_INFO_ADJOINT = 8, FDM_FA_LENGTHS = 9, FDM_FA_FORCES = 10,
+  FDM_FA_RESIDUALS = 11, FDM_FA_VECTORS = 12, FDM_FA_XYZ_FIXED = 13, FDM_FA_LOADS = 14
+};
+/* device pointer of one of the object's arrays (valid until fdm_fa_destroy) and its doubles per design */
+int fdm_fa_device_array(fdm_fa* fa, int which, void** d_out, int64_t* per_design);
+enum { FDM_FA_INFO_CHUNKS = 0, FDM_FA_INFO_LAUNCHES = 1, FDM_FA_INFO_FUSED_ASSEMBLY = 2, FDM_FA_INFO_GRAPH = 3,
+       FDM_FA_INFO_BATCH = 4 };
+int64_t fdm_fa_info(const fdm_fa* fa, int which);   /* LAUNCHES: kernels per step (0 before the first step) */
+/* page-locked host memory for the end-to-end calls */
+void* fdm_host_alloc(size_t bytes);
+void fdm_host_free(void* p);
 
 const char* fdm_last_error(void);
 const char* fdm_version(void);

@@ -30,13 +30,28 @@ EXPORTS = [
     "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_solve_from_q", "fdm_spmm",
     "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_adjoint_grads", "fdm_edge_loads",
     "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_goals_loss", "fdm_loss_sqdist",
+    "fdm_fa_create", "fdm_fa_destroy", "fdm_fa_set_constants", "fdm_fa_set_goal_program", "fdm_fa_set_q",
+    "fdm_fa_step_device", "fdm_fa_enqueue_host", "fdm_fa_enqueue_copies_only", "fdm_fa_wait", "fdm_fa_run_host", "fdm_fa_device_array", "fdm_fa_info",
+    "fdm_host_alloc", "fdm_host_free", "fdm_batch_sum", "fdm_kbar_pattern", "fdm_stiffness_vjp",
     "fdm_last_error", "fdm_version",
 ]
 
 
 class SolveOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("max_iters", C.c_int32), ("tol", C.c_double),
-                ("check_every", C.c_int32), ("reuse_factor", C.c_int32), ("stages", C.c_int32)]
+                ("check_every", C.c_int32), ("reuse_factor", C.c_int32), ("stages", C.c_int32),
+                ("nan_on_failure", C.c_int32)]
+
+
+class FaOpts(C.Structure):
+    """fdm_fa_opts (include/fdm_b200.h)."""
+    _fields_ = [("chunks", C.c_int32), ("with_state", C.c_int32), ("solver", C.c_int32), ("use_graph", C.c_int32),
+                ("max_iters", C.c_int32), ("tol", C.c_double)]
+
+
+(FA_Q, FA_X_FREE, FA_XYZ, FA_LOSS, FA_Q_BAR, FA_LOADS_BAR, FA_XYZ_FIXED_BAR, FA_INFO_FORWARD, FA_INFO_ADJOINT,
+ FA_LENGTHS, FA_FORCES, FA_RESIDUALS, FA_VECTORS, FA_XYZ_FIXED, FA_LOADS) = range(15)
+FA_INFO_CHUNKS, FA_INFO_LAUNCHES, FA_INFO_FUSED_ASSEMBLY, FA_INFO_GRAPH, FA_INFO_BATCH = range(5)
 
 
 class GoalProgram(C.Structure):
@@ -110,6 +125,40 @@ def lib():
     L.fdm_goals_loss.restype = C.c_int
     L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.fdm_loss_sqdist.restype = C.c_int
+    L.fdm_fa_create.argtypes = [vp, i64, C.POINTER(FaOpts), C.POINTER(vp)]
+    L.fdm_fa_create.restype = C.c_int
+    L.fdm_fa_destroy.argtypes = [vp]
+    L.fdm_fa_destroy.restype = None
+    L.fdm_fa_set_constants.argtypes = [vp, vp, vp, vp]
+    L.fdm_fa_set_constants.restype = C.c_int
+    L.fdm_fa_set_goal_program.argtypes = [vp, C.POINTER(GoalProgram)]
+    L.fdm_fa_set_goal_program.restype = C.c_int
+    L.fdm_fa_set_q.argtypes = [vp, vp]
+    L.fdm_fa_set_q.restype = C.c_int
+    L.fdm_fa_step_device.argtypes = [vp, vp]
+    L.fdm_fa_step_device.restype = C.c_int
+    L.fdm_fa_enqueue_host.argtypes = [vp, vp, vp, vp]
+    L.fdm_fa_enqueue_host.restype = C.c_int
+    L.fdm_fa_enqueue_copies_only.argtypes = [vp, vp, vp, vp]
+    L.fdm_fa_enqueue_copies_only.restype = C.c_int
+    L.fdm_fa_wait.argtypes = [vp]
+    L.fdm_fa_wait.restype = C.c_int
+    L.fdm_fa_run_host.argtypes = [vp, vp, vp, vp]
+    L.fdm_fa_run_host.restype = C.c_int
+    L.fdm_fa_device_array.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    L.fdm_fa_device_array.restype = C.c_int
+    L.fdm_fa_info.argtypes = [vp, C.c_int]
+    L.fdm_fa_info.restype = i64
+    L.fdm_kbar_pattern.argtypes = [vp, vp, vp, vp, C.c_double, i64, vp]
+    L.fdm_kbar_pattern.restype = C.c_int
+    L.fdm_stiffness_vjp.argtypes = [vp, vp, vp, i64, vp]
+    L.fdm_stiffness_vjp.restype = C.c_int
+    L.fdm_batch_sum.argtypes = [vp, vp, i64, i64, vp]
+    L.fdm_batch_sum.restype = C.c_int
+    L.fdm_host_alloc.argtypes = [sz]
+    L.fdm_host_alloc.restype = vp
+    L.fdm_host_free.argtypes = [vp]
+    L.fdm_host_free.restype = None
     L.fdm_last_error.argtypes = []
     L.fdm_last_error.restype = C.c_char_p
     L.fdm_version.argtypes = []

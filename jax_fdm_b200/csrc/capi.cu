@@ -232,13 +232,24 @@ int fdm_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double*
   std::memset(&o, 0, sizeof(o));
   if (opts) o = *opts;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (pick_solver(p, batch, o.solver)) {
-    case FDM_SOLVER_PCG: return pcg_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
-    case FDM_SOLVER_PCG_PERSISTENT: return pcg2_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
-    case FDM_SOLVER_CHOLESKY_BATCHED: return chol_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
+  if (o.nan_on_failure && !info) {
+    fdm_set_error("fdm_solve: nan_on_failure needs d_info");
+    return FDM_ERR_INVALID;
   }
-  fdm_set_error("fdm_solve: unknown solver id");
-  return FDM_ERR_INVALID;
+  int rc;
+  switch (pick_solver(p, batch, o.solver)) {
+    case FDM_SOLVER_PCG: rc = pcg_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st); break;
+    case FDM_SOLVER_PCG_PERSISTENT: rc = pcg2_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st); break;
+    case FDM_SOLVER_CHOLESKY_BATCHED:
+      rc = chol_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
+      if (chol_warp_supported(p)) return rc;             // its substitution kernel writes the NaNs itself
+      break;
+    default:
+      fdm_set_error("fdm_solve: unknown solver id");
+      return FDM_ERR_INVALID;
+  }
+  if (rc == FDM_OK && o.nan_on_failure) rc = launch_nan_failed(info, x, p->Nf * 3, batch, st);
+  return rc;
 }
 
 int fdm_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
@@ -261,7 +272,11 @@ int fdm_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const
                   "call fdm_assemble + fdm_solve");
     return FDM_ERR_UNSUPPORTED;
   }
-  return chol_warp_solve_from_q(p, q, xs, loads, x, info, ws, ws_bytes, batch, qs, xss, ls, (cudaStream_t)stream);
+  if (o.nan_on_failure && !info) {
+    fdm_set_error("fdm_solve_from_q: nan_on_failure needs d_info");
+    return FDM_ERR_INVALID;
+  }
+  return chol_warp_solve_from_q(p, q, xs, loads, x, info, ws, ws_bytes, batch, qs, xss, ls, o, (cudaStream_t)stream);
 }
 
 int fdm_spmm(const fdm_plan* p, const double* Kdata, const double* X, double* Y, int64_t batch,
@@ -409,6 +424,33 @@ int fdm_loss_sqdist(const double* x, const double* x0, double* g, double* loss, 
     return FDM_ERR_INVALID;
   }
   return launch_loss_sqdist(x, x0, g, loss, n, batch, x0_stride, (cudaStream_t)stream);
+}
+
+int fdm_kbar_pattern(const fdm_plan* p, const double* a, const double* b, double* Kbar, double sign, int64_t batch,
+                     void* stream) {
+  if (!ready(p, "fdm_kbar_pattern")) return FDM_ERR_INVALID;
+  if (!a || !b || !Kbar || batch <= 0) {
+    fdm_set_error("fdm_kbar_pattern: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_kbar_pattern(p, a, b, Kbar, sign, batch, (cudaStream_t)stream);
+}
+
+int fdm_stiffness_vjp(const fdm_plan* p, const double* Kbar, double* q_bar, int64_t batch, void* stream) {
+  if (!ready(p, "fdm_stiffness_vjp")) return FDM_ERR_INVALID;
+  if (!Kbar || !q_bar || batch <= 0) {
+    fdm_set_error("fdm_stiffness_vjp: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_stiffness_vjp(p, Kbar, q_bar, batch, (cudaStream_t)stream);
+}
+
+int fdm_batch_sum(const double* d_in, double* d_out, int64_t batch, int64_t n, void* stream) {
+  if (!d_in || !d_out || batch <= 0 || n <= 0) {
+    fdm_set_error("fdm_batch_sum: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_batch_sum(d_in, d_out, batch, n, (cudaStream_t)stream);
 }
 
 }  // extern "C"

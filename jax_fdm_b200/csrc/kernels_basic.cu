@@ -334,6 +334,53 @@ adjoint_grads_kernel(int E, int N, int Nf, int Ns, const int32_t* __restrict__ e
 }
 
 // ---------------------------------------------------------------------------------------
+// The cotangent structure of the reference's custom_vjp, materialised (sparse.py:299-306): for every stored
+// entry k of the pattern, Kbar.data[k] = sign * sum_xyz a[row_k] * b[col_k].  Thread per COLUMN c (the pattern is
+// CSC = CSR, symmetric): b[c] in registers, its entries are contiguous.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+kbar_pattern_kernel(int Nf, int64_t nnz, const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
+                    const double* __restrict__ a, const double* __restrict__ bvec, double* __restrict__ out, double sign) {
+  const int64_t b = blockIdx.y;
+  const int c = blockIdx.x * kThreads + threadIdx.x;
+  if (c >= Nf) return;
+  a += b * (int64_t)Nf * 3;
+  bvec += b * (int64_t)Nf * 3;
+  out += b * nnz;
+  const double3 bc = ld3(bvec, c);
+  const int k0 = __ldg(colptr + c), k1 = __ldg(colptr + c + 1);
+  for (int k = k0; k < k1; ++k) {
+    const double3 ar = ld3(a, __ldg(rowidx + k));
+    out[k] = sign * (ar.x * bc.x + ar.y * bc.y + ar.z * bc.z);
+  }
+}
+
+// Transpose of the assembly of K.data (models.py:1069-1077): q_bar_e = [tail free] Kbar[diag_tail] +
+// [head free] Kbar[diag_head] - [both free] (Kbar[(tail, head)] + Kbar[(head, tail)]).  Thread per edge; the two
+// off-diagonal entries are found by scanning the (short) columns of its end nodes.
+__global__ void __launch_bounds__(kThreads)
+stiffness_vjp_kernel(int E, int64_t nnz, const int32_t* __restrict__ edge_nodes, const int32_t* __restrict__ node_slot,
+                     const int32_t* __restrict__ colptr, const int32_t* __restrict__ rowidx,
+                     const int32_t* __restrict__ diag_pos, const double* __restrict__ Kbar, double* __restrict__ q_bar) {
+  const int64_t b = blockIdx.y;
+  const int e = blockIdx.x * kThreads + threadIdx.x;
+  if (e >= E) return;
+  Kbar += b * nnz;
+  const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + e);
+  const int i = __ldg(node_slot + th.x), j = __ldg(node_slot + th.y);
+  double g = 0.0;
+  if (i >= 0) g += Kbar[__ldg(diag_pos + i)];
+  if (j >= 0) g += Kbar[__ldg(diag_pos + j)];
+  if (i >= 0 && j >= 0) {
+    for (int k = __ldg(colptr + i); k < __ldg(colptr + i + 1); ++k)
+      if (__ldg(rowidx + k) == j) { g -= Kbar[k]; break; }
+    for (int k = __ldg(colptr + j); k < __ldg(colptr + j + 1); ++k)
+      if (__ldg(rowidx + k) == i) { g -= Kbar[k]; break; }
+  }
+  q_bar[b * (int64_t)E + e] = g;
+}
+
+// ---------------------------------------------------------------------------------------
 // small vector helpers for the load kernels
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double3 v_sub(double3 a, double3 b) { return make_double3(a.x - b.x, a.y - b.y, a.z - b.z); }
@@ -694,6 +741,43 @@ face_loads_vjp_nodes_kernel(int N, int F, int D, const int32_t* __restrict__ fac
 // ---------------------------------------------------------------------------------------
 // loss helper: g = x - x0, loss_b = 0.5 sum g^2   (one CTA per design, fixed-order reduction)
 // ---------------------------------------------------------------------------------------
+// out[i] = sum_b in[b, i] in a fixed order (deterministic, launch-geometry independent): the local part of the
+// loss / shared-gradient all-reduce (distributed.py).  n == 1: one CTA, thread t adds b = t, t + T, ... then a
+// fixed tree; otherwise one thread per column, b ascending (coalesced across the warp).
+__global__ void __launch_bounds__(1024) batch_sum_scalar_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t B) {
+  double acc = 0.0;
+  for (int64_t b = threadIdx.x; b < B; b += 1024) acc += in[b];
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = red[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) out[0] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) batch_sum_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t B, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int64_t b = 0;
+  for (; b + 3 < B; b += 4) {
+    a0 += in[b * n + i]; a1 += in[(b + 1) * n + i]; a2 += in[(b + 2) * n + i]; a3 += in[(b + 3) * n + i];
+  }
+  for (; b < B; ++b) a0 += in[b * n + i];
+  out[i] = (a0 + a1) + (a2 + a3);
+}
+
+// fdm_solve_opts.nan_on_failure for the solvers whose own kernels do not do it: design b (blockIdx.y) with a
+// status other than OK gets x = NaN
+__global__ void __launch_bounds__(256) nan_failed_kernel(const double* __restrict__ info, double* __restrict__ x, int64_t n) {
+  const int64_t b = blockIdx.y;
+  if (__ldg(info + b * FDM_INFO_STRIDE + FDM_INFO_STATUS) == 0.0) return;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) x[b * n + i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
 __global__ void __launch_bounds__(1024)
 loss_sqdist_kernel(const double* __restrict__ x, const double* __restrict__ x0,
                    double* __restrict__ g, double* __restrict__ loss, int64_t n, int64_t x0_stride) {
@@ -810,6 +894,25 @@ int launch_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, 
   return fdm_check_launch("adjoint_grads");
 }
 
+int launch_kbar_pattern(const fdm_plan* p, const double* a, const double* bvec, double* out, double sign, int64_t batch,
+                        cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    kbar_pattern_kernel<<<grid_for(p->Nf, nb), kThreads, 0, st>>>((int)p->Nf, p->nnz, d.rowptr, d.colidx, a + b0 * p->Nf * 3,
+                                                                 bvec + b0 * p->Nf * 3, out + b0 * p->nnz, sign);
+  }
+  return fdm_check_launch("kbar_pattern");
+}
+
+int launch_stiffness_vjp(const fdm_plan* p, const double* Kbar, double* q_bar, int64_t batch, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    stiffness_vjp_kernel<<<grid_for(p->E, nb), kThreads, 0, st>>>((int)p->E, p->nnz, d.edge_nodes, d.node_slot, d.rowptr,
+                                                                 d.colidx, d.diag_pos, Kbar + b0 * p->nnz, q_bar + b0 * p->E);
+  }
+  return fdm_check_launch("stiffness_vjp");
+}
+
 int launch_edge_loads(const fdm_plan* p, const double* xyz, const double* loads_nodes, const double* edges_load,
                       double* loads_out, int64_t batch, int64_t ls, int64_t es, int local, cudaStream_t st) {
   const DeviceArrays& d = p->d;
@@ -868,6 +971,20 @@ int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, in
           vert_bar ? vert_bar + b0 * F * D * 3 : nullptr, xyz_bar + b0 * p->N * 3, local);
   }
   return fdm_check_launch("face_loads_vjp");
+}
+
+int launch_batch_sum(const double* in, double* out, int64_t batch, int64_t n, cudaStream_t st) {
+  if (n == 1) batch_sum_scalar_kernel<<<1, 1024, 0, st>>>(in, out, batch);
+  else batch_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, batch, n);
+  return fdm_check_launch("batch_sum");
+}
+
+int launch_nan_failed(const double* info, double* x, int64_t n, int64_t batch, cudaStream_t st) {
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    nan_failed_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)nb), 256, 0, st>>>(info + b0 * FDM_INFO_STRIDE,
+                                                                                       x + b0 * n, n);
+  }
+  return fdm_check_launch("nan_failed");
 }
 
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,

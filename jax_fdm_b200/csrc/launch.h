@@ -66,6 +66,12 @@ int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const
                       const double* xyz, const double* lengths, const double* forces, const double* residuals,
                       double* loss, double* gsum, double* xyz_bar, double* lengths_bar, double* forces_bar,
                       double* residuals_bar, int64_t batch, cudaStream_t st);
+int launch_kbar_pattern(const fdm_plan* p, const double* a, const double* bvec, double* out, double sign, int64_t batch,
+                        cudaStream_t st);
+int launch_stiffness_vjp(const fdm_plan* p, const double* Kbar, double* q_bar, int64_t batch, cudaStream_t st);
+int launch_batch_sum(const double* in, double* out, int64_t batch, int64_t n, cudaStream_t st);
+// x[b] = NaN for every design whose info status is not OK (fdm_solve_opts.nan_on_failure)
+int launch_nan_failed(const double* info, double* x, int64_t n_per_design, int64_t batch, cudaStream_t st);
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                        int64_t batch, int64_t x0_stride, cudaStream_t st);
 
@@ -93,7 +99,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
 bool chol_warp_from_q_supported(const fdm_plan* p);
 int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
                            double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss,
-                           int64_t ls, cudaStream_t st);
+                           int64_t ls, const fdm_solve_opts& o, cudaStream_t st);
 
 // solver_pcg2.cu  (persistent two-level PCG)
 size_t pcg2_workspace_bytes(const fdm_plan* p);

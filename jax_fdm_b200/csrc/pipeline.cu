@@ -1,0 +1,485 @@
+// fdm_fa: value-and-gradient of a loss over a batch of designs as ONE native object -- what
+// `jit(value_and_grad(loss_fn))(params)` is to the reference (optimization/optimizers/optimizer.py:365-370)
+// and `vmap(...)(q)` over designs to visualization/plotters/loss_plotter.py:98-103.
+//
+// The object owns every device buffer, the chunk streams, the events and one CUDA graph per chunk, so that a
+// step costs the host a handful of driver calls: the batch is cut into contiguous chunks; chunk c copies its
+// q in (one cudaMemcpyAsync), replays its graph (solve from q -> positions -> state -> loss and cotangents ->
+// adjoint solve with the stored factor -> gradients) and copies loss and q_bar out (one cudaMemcpyAsync
+// each), all on its own stream: the H2D copy of one chunk, the kernels of another and the D2H copy of a third
+// overlap on the copy engines and the SMs.  Two losses: the benchmark's quadratic distance to x0
+// (fdm_loss_sqdist) and a compiled goal program (fdm_goals_loss + fdm_state_vjp).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "launch.h"
+
+extern "C" size_t fdm_workspace_bytes(const fdm_plan* p, int64_t batch, int32_t solver);
+
+namespace {
+
+struct Chunk {
+  int64_t off = 0, B = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t done = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+struct Buf {
+  double* p = nullptr;
+  int64_t per = 0;   // doubles per design (0: shared by the batch)
+  double* at(int64_t b) const { return p ? p + b * per : nullptr; }
+};
+
+}  // namespace
+
+struct fdm_fa {
+  const fdm_plan* plan = nullptr;
+  int64_t B = 0;
+  fdm_fa_opts o{};
+  bool fused = false, capturable = true, has_prog = false;
+  int solver = 0;
+  fdm_goal_program prog{};
+  std::vector<void*> prog_mem;
+  // inputs
+  Buf q, xs, loads, x0;
+  // forward
+  Buf K, rhs, x, xyz, vectors, lengths, forces, residuals, info_f;
+  // reverse
+  Buf g, lam, loss, q_bar, loads_bar, xs_bar, info_a, xyz_cot, len_cot, for_cot, res_cot, xyz_bar;
+  std::vector<void*> allocs;
+  std::vector<Chunk> chunks;
+  cudaEvent_t fork = nullptr;
+  cudaStream_t own = nullptr;      // run_host's ordering stream
+  cudaGraphExec_t step_exec = nullptr;   // the whole device-resident step (fork / chunks / join) as one graph
+  int64_t launches_per_step = 0;
+};
+
+namespace {
+
+int alloc(fdm_fa* f, Buf& b, int64_t per, int64_t count, bool zero = true) {
+  b.per = per;
+  const size_t bytes = (size_t)std::max<int64_t>(per * count, 2) * sizeof(double);
+  FDM_CUDA(cudaMalloc((void**)&b.p, bytes));
+  f->allocs.push_back(b.p);
+  if (zero) FDM_CUDA(cudaMemset(b.p, 0, bytes));
+  return FDM_OK;
+}
+
+// the kernel sequence of one forward + adjoint pass over designs [c.off, c.off + c.B) on stream st
+int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
+  const fdm_plan* p = f->plan;
+  const int64_t o = c.off, B = c.B, E = p->E, N = p->N, Nf = p->Nf, Ns = p->Ns;
+  int rc;
+  int64_t n = 0;
+  fdm_solve_opts so;
+  std::memset(&so, 0, sizeof(so));
+  so.solver = f->solver;
+  so.max_iters = f->o.max_iters;
+  so.tol = f->o.tol;
+  so.nan_on_failure = 1;
+  if (f->fused) {
+    rc = fdm_solve_from_q(p, f->q.at(o), f->xs.p, f->loads.p, f->x.at(o), f->info_f.at(o), c.ws, c.ws_bytes, B, E, 0, 0,
+                          &so, st);
+    n += 2;
+  } else {
+    rc = fdm_assemble(p, f->q.at(o), f->xs.p, f->loads.p, f->K.at(o), f->rhs.at(o), B, E, 0, 0, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_solve(p, f->K.at(o), f->rhs.at(o), f->x.at(o), f->info_f.at(o), c.ws, c.ws_bytes, B, &so, st);
+    n += 2;
+  }
+  if (rc != FDM_OK) return rc;
+  rc = fdm_positions(p, f->x.at(o), f->xs.p, f->xyz.at(o), B, 0, 0, st);
+  if (rc != FDM_OK) return rc;
+  ++n;
+  if (f->o.with_state || f->has_prog) {
+    rc = fdm_state(p, f->q.at(o), f->xyz.at(o), f->loads.p, f->vectors.at(o), f->lengths.at(o), f->forces.at(o),
+                   f->residuals.at(o), B, E, 0, st);
+    if (rc != FDM_OK) return rc;
+    ++n;
+  }
+  so.reuse_factor = 1;
+  if (!f->has_prog) {
+    // L_b = 1/2 |x_free - x0|^2, g = x_free - x0
+    rc = fdm_loss_sqdist(f->x.at(o), f->x0.p, f->g.at(o), f->loss.at(o), Nf * 3, B, 0, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_solve(p, f->fused ? f->x.at(o) /* unused */ : f->K.at(o), f->g.at(o), f->lam.at(o), f->info_a.at(o), c.ws,
+                   c.ws_bytes, B, &so, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_adjoint_grads(p, f->q.at(o), f->xyz.at(o), f->lam.at(o), f->q_bar.at(o), f->loads_bar.at(o), f->xs_bar.at(o),
+                           B, E, 0, st);
+    if (rc != FDM_OK) return rc;
+    n += 3;
+  } else {
+    // goal program: loss and the cotangents of the state, their transposes through the state (direct terms of
+    // q_bar, loads_bar and the cotangent of xyz), the split of xyz_bar into free / fixed rows, the adjoint solve
+    // and the implicit terms accumulated on top
+    rc = fdm_goals_loss(p, &f->prog, f->xyz.at(o), f->lengths.at(o), f->forces.at(o), f->residuals.at(o), f->loss.at(o),
+                        nullptr, f->xyz_cot.at(o), f->len_cot.at(o), f->for_cot.at(o), f->res_cot.at(o), B, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_state_vjp(p, f->q.at(o), f->xyz.at(o), f->xyz_cot.at(o), f->res_cot.at(o), f->len_cot.at(o), f->for_cot.at(o),
+                       nullptr, nullptr, f->q_bar.at(o), f->xyz_bar.at(o), f->loads_bar.at(o), B, E, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_positions(p, f->g.at(o), f->xs_bar.at(o), f->xyz_bar.at(o), B, Ns * 3, 1, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_solve(p, f->fused ? f->x.at(o) : f->K.at(o), f->g.at(o), f->lam.at(o), f->info_a.at(o), c.ws, c.ws_bytes, B,
+                   &so, st);
+    if (rc != FDM_OK) return rc;
+    rc = fdm_adjoint_grads(p, f->q.at(o), f->xyz.at(o), f->lam.at(o), f->q_bar.at(o), f->loads_bar.at(o), f->xs_bar.at(o),
+                           B, E, 1, st);
+    if (rc != FDM_OK) return rc;
+    n += 5;
+  }
+  (void)N;
+  if (count) *count += n;
+  return FDM_OK;
+}
+
+int run_chunk(fdm_fa* f, Chunk& c, cudaStream_t st) {
+  if (c.exec) {
+    FDM_CUDA(cudaGraphLaunch(c.exec, st));
+    return FDM_OK;
+  }
+  return launch_chunk(f, c, st, nullptr);
+}
+
+int capture_chunks(fdm_fa* f) {
+  f->launches_per_step = 0;
+  for (Chunk& c : f->chunks) {
+    int64_t n = 0;
+    int rc = launch_chunk(f, c, c.st, &n);                // warm-up outside capture (also sets function attributes)
+    if (rc != FDM_OK) return rc;
+    f->launches_per_step += n;
+    FDM_CUDA(cudaStreamSynchronize(c.st));
+    if (!f->capturable || !f->o.use_graph) continue;
+    if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    FDM_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeThreadLocal));
+    rc = launch_chunk(f, c, c.st, nullptr);
+    cudaError_t e = cudaStreamEndCapture(c.st, &graph);
+    if (rc != FDM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph capture: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+    e = cudaGraphInstantiate(&c.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+  }
+  // the device-resident step as ONE graph: fork from the capturing stream to the chunk streams and join back
+  if (f->capturable && f->o.use_graph && f->chunks.size() > 1) {
+    if (f->step_exec) { cudaGraphExecDestroy(f->step_exec); f->step_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    FDM_CUDA(cudaStreamBeginCapture(f->own, cudaStreamCaptureModeThreadLocal));
+    int rc = FDM_OK;
+    cudaError_t e = cudaEventRecord(f->fork, f->own);
+    for (Chunk& c : f->chunks) {
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(c.st, f->fork, 0);
+      if (e == cudaSuccess && rc == FDM_OK) rc = launch_chunk(f, c, c.st, nullptr);
+      if (e == cudaSuccess) e = cudaEventRecord(c.done, c.st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(f->own, c.done, 0);
+    }
+    cudaError_t e2 = cudaStreamEndCapture(f->own, &graph);
+    if (rc != FDM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+      fdm_set_error(std::string("fdm_fa: step graph capture: ") + cudaGetErrorString(e != cudaSuccess ? e : e2));
+      if (graph) cudaGraphDestroy(graph);
+      return FDM_ERR_CUDA;
+    }
+    e = cudaGraphInstantiate(&f->step_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: step graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+  }
+  return FDM_OK;
+}
+
+void destroy(fdm_fa* f) {
+  if (!f) return;
+  if (f->plan && f->plan->on_device) cudaSetDevice(f->plan->device);
+  for (Chunk& c : f->chunks) {
+    if (c.st) cudaStreamSynchronize(c.st);
+    if (c.exec) cudaGraphExecDestroy(c.exec);
+    if (c.done) cudaEventDestroy(c.done);
+    if (c.st) cudaStreamDestroy(c.st);
+    if (c.ws) cudaFree(c.ws);
+  }
+  if (f->step_exec) cudaGraphExecDestroy(f->step_exec);
+  if (f->fork) cudaEventDestroy(f->fork);
+  if (f->own) cudaStreamDestroy(f->own);
+  for (void* q : f->allocs) cudaFree(q);
+  for (void* q : f->prog_mem) cudaFree(q);
+  delete f;
+}
+
+template <class T>
+int upload_arr(fdm_fa* f, const T* h, size_t count, const T** d) {
+  void* m = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  FDM_CUDA(cudaMalloc(&m, bytes));
+  f->prog_mem.push_back(m);
+  if (count) FDM_CUDA(cudaMemcpy(m, h, count * sizeof(T), cudaMemcpyHostToDevice));
+  *d = (const T*)m;
+  return FDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdm_fa_create(const fdm_plan* p, int64_t batch, const fdm_fa_opts* opts, fdm_fa** out) {
+  if (!out) return FDM_ERR_INVALID;
+  *out = nullptr;
+  if (!p || !p->on_device || batch <= 0) {
+    fdm_set_error("fdm_fa_create: plan is null or host-only, or batch <= 0");
+    return FDM_ERR_INVALID;
+  }
+  FDM_CUDA(cudaSetDevice(p->device));
+  fdm_fa* f = new (std::nothrow) fdm_fa();
+  if (!f) return FDM_ERR_INVALID;
+  f->plan = p;
+  f->B = batch;
+  if (opts) f->o = *opts;
+  else { f->o.with_state = 1; f->o.use_graph = 1; }
+  if (f->o.chunks <= 0) f->o.chunks = 1;
+  if (f->o.tol <= 0) f->o.tol = 1e-12;
+  const int64_t nch = std::min<int64_t>(f->o.chunks, batch);
+  const int64_t E = p->E, N = p->N, Nf = p->Nf, Ns = p->Ns, nnz = p->nnz;
+  // which solver serves this plan and chunk size (chunks differ by at most one design: same choice for all)
+  const int64_t cb = batch / nch;
+  fdm_solve_opts probe;
+  std::memset(&probe, 0, sizeof(probe));
+  probe.solver = f->o.solver;
+  f->fused = chol_warp_from_q_supported(p) && cb > 1 &&
+             (f->o.solver == FDM_SOLVER_AUTO || f->o.solver == FDM_SOLVER_CHOLESKY_BATCHED);
+  f->solver = f->fused ? FDM_SOLVER_CHOLESKY_BATCHED : f->o.solver;
+  // the multi-kernel PCG polls convergence from the host: not capturable
+  {
+    const bool chol = chol_warp_supported(p) || (chol_supported(p) && (cb > 1 || !pcg2_supported(p)));
+    const int eff = f->solver != FDM_SOLVER_AUTO ? f->solver
+                    : chol ? FDM_SOLVER_CHOLESKY_BATCHED : pcg2_supported(p) ? FDM_SOLVER_PCG_PERSISTENT : FDM_SOLVER_PCG;
+    f->capturable = eff != FDM_SOLVER_PCG;
+  }
+  int rc = FDM_OK;
+  auto A = [&](Buf& b, int64_t per, int64_t count) { if (rc == FDM_OK) rc = alloc(f, b, per, count); };
+  A(f->q, E, batch); A(f->xs, Ns * 3, 1); A(f->loads, N * 3, 1); A(f->x0, Nf * 3, 1);
+  if (!f->fused) { A(f->K, nnz, batch); A(f->rhs, Nf * 3, batch); }
+  A(f->x, Nf * 3, batch); A(f->xyz, N * 3, batch);
+  A(f->info_f, FDM_INFO_STRIDE, batch); A(f->info_a, FDM_INFO_STRIDE, batch);
+  A(f->g, Nf * 3, batch); A(f->lam, Nf * 3, batch); A(f->loss, 1, batch);
+  A(f->q_bar, E, batch); A(f->loads_bar, N * 3, batch); A(f->xs_bar, Ns * 3, batch);
+  if (f->o.with_state) {
+    A(f->vectors, E * 3, batch); A(f->lengths, E, batch); A(f->forces, E, batch); A(f->residuals, N * 3, batch);
+  }
+  if (rc == FDM_OK && cudaStreamCreateWithFlags(&f->own, cudaStreamNonBlocking) != cudaSuccess) rc = FDM_ERR_CUDA;
+  if (rc == FDM_OK && cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) rc = FDM_ERR_CUDA;
+  f->chunks.resize((size_t)nch);
+  int64_t off = 0;
+  for (int64_t i = 0; i < nch && rc == FDM_OK; ++i) {
+    Chunk& c = f->chunks[(size_t)i];
+    c.off = off;
+    c.B = batch / nch + (i < batch % nch ? 1 : 0);
+    off += c.B;
+    if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess) { rc = FDM_ERR_CUDA; break; }
+    c.ws_bytes = std::max<size_t>(fdm_workspace_bytes(p, c.B, f->solver), 16);
+    if (cudaMalloc(&c.ws, c.ws_bytes) != cudaSuccess) { rc = FDM_ERR_CUDA; break; }
+  }
+  if (rc != FDM_OK) {
+    if (rc == FDM_ERR_CUDA) fdm_set_error(std::string("fdm_fa_create: ") + cudaGetErrorString(cudaGetLastError()));
+    destroy(f);
+    return rc;
+  }
+  *out = f;
+  return FDM_OK;
+}
+
+void fdm_fa_destroy(fdm_fa* f) { destroy(f); }
+
+int fdm_fa_set_constants(fdm_fa* f, const double* h_xyz_fixed, const double* h_loads, const double* h_x0) {
+  if (!f || !h_xyz_fixed || !h_loads) {
+    fdm_set_error("fdm_fa_set_constants: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  const fdm_plan* p = f->plan;
+  FDM_CUDA(cudaSetDevice(p->device));
+  FDM_CUDA(cudaMemcpy(f->xs.p, h_xyz_fixed, (size_t)p->Ns * 3 * 8, cudaMemcpyHostToDevice));
+  FDM_CUDA(cudaMemcpy(f->loads.p, h_loads, (size_t)p->N * 3 * 8, cudaMemcpyHostToDevice));
+  if (h_x0) FDM_CUDA(cudaMemcpy(f->x0.p, h_x0, (size_t)p->Nf * 3 * 8, cudaMemcpyHostToDevice));
+  return FDM_OK;
+}
+
+int fdm_fa_set_goal_program(fdm_fa* f, const fdm_goal_program* h) {
+  if (!f || !h) {
+    fdm_set_error("fdm_fa_set_goal_program: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  const fdm_plan* p = f->plan;
+  FDM_CUDA(cudaSetDevice(p->device));
+  for (void* q : f->prog_mem) cudaFree(q);
+  f->prog_mem.clear();
+  fdm_goal_program d = *h;
+  const size_t T = (size_t)h->num_terms, G = (size_t)h->num_groups;
+  int rc = FDM_OK;
+  if (rc == FDM_OK) rc = upload_arr(f, h->kind, T, &d.kind);
+  if (rc == FDM_OK) rc = upload_arr(f, h->index, T, &d.index);
+  if (rc == FDM_OK) rc = upload_arr(f, h->error, T, &d.error);
+  if (rc == FDM_OK) rc = upload_arr(f, h->weight, T, &d.weight);
+  if (rc == FDM_OK) rc = upload_arr(f, h->target, T * 6, &d.target);
+  if (rc == FDM_OK) rc = upload_arr(f, h->group_ptr, G + 1, &d.group_ptr);
+  if (rc == FDM_OK) rc = upload_arr(f, h->group_final, G, &d.group_final);
+  if (rc == FDM_OK) rc = upload_arr(f, h->group_inner, G, &d.group_inner);
+  if (rc == FDM_OK) rc = upload_arr(f, h->group_outer, G, &d.group_outer);
+  if (rc == FDM_OK && h->agg_ptr) {
+    rc = upload_arr(f, h->agg_ptr, T + 1, &d.agg_ptr);
+    if (rc == FDM_OK) rc = upload_arr(f, h->agg_index, (size_t)h->agg_ptr[T], &d.agg_index);
+  }
+  if (rc != FDM_OK) return rc;
+  f->prog = d;
+  const int64_t B = f->B, E = p->E, N = p->N;
+  auto A = [&](Buf& b, int64_t per) { if (rc == FDM_OK && !b.p) rc = alloc(f, b, per, B); };
+  A(f->vectors, E * 3); A(f->lengths, E); A(f->forces, E); A(f->residuals, N * 3);
+  A(f->xyz_cot, N * 3); A(f->len_cot, E); A(f->for_cot, E); A(f->res_cot, N * 3); A(f->xyz_bar, N * 3);
+  if (rc != FDM_OK) return rc;
+  f->has_prog = true;
+  for (Chunk& c : f->chunks)
+    if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }   // recaptured by the next run
+  if (f->step_exec) { cudaGraphExecDestroy(f->step_exec); f->step_exec = nullptr; }
+  f->launches_per_step = 0;
+  return FDM_OK;
+}
+
+int fdm_fa_set_q(fdm_fa* f, const double* h_q) {
+  if (!f || !h_q) return FDM_ERR_INVALID;
+  FDM_CUDA(cudaSetDevice(f->plan->device));
+  FDM_CUDA(cudaMemcpy(f->q.p, h_q, (size_t)f->B * f->plan->E * 8, cudaMemcpyHostToDevice));
+  return FDM_OK;
+}
+
+static int ensure_captured(fdm_fa* f) {
+  if (f->launches_per_step) return FDM_OK;
+  return capture_chunks(f);
+}
+
+int fdm_fa_step_device(fdm_fa* f, void* stream) {
+  if (!f) return FDM_ERR_INVALID;
+  int rc = ensure_captured(f);
+  if (rc != FDM_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (f->step_exec) {
+    FDM_CUDA(cudaGraphLaunch(f->step_exec, s));
+    return FDM_OK;
+  }
+  if (f->chunks.size() == 1) return run_chunk(f, f->chunks[0], s);
+  FDM_CUDA(cudaEventRecord(f->fork, s));
+  for (Chunk& c : f->chunks) {
+    FDM_CUDA(cudaStreamWaitEvent(c.st, f->fork, 0));
+    rc = run_chunk(f, c, c.st);
+    if (rc != FDM_OK) return rc;
+    FDM_CUDA(cudaEventRecord(c.done, c.st));
+    FDM_CUDA(cudaStreamWaitEvent(s, c.done, 0));
+  }
+  return FDM_OK;
+}
+
+int fdm_fa_enqueue_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar) {
+  if (!f || !h_q || !h_loss) {
+    fdm_set_error("fdm_fa_enqueue_host: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  int rc = ensure_captured(f);
+  if (rc != FDM_OK) return rc;
+  const int64_t E = f->plan->E;
+  for (Chunk& c : f->chunks) {
+    FDM_CUDA(cudaMemcpyAsync(f->q.at(c.off), h_q + c.off * E, (size_t)c.B * E * 8, cudaMemcpyHostToDevice, c.st));
+    rc = run_chunk(f, c, c.st);
+    if (rc != FDM_OK) return rc;
+    FDM_CUDA(cudaMemcpyAsync(h_loss + c.off, f->loss.at(c.off), (size_t)c.B * 8, cudaMemcpyDeviceToHost, c.st));
+    if (h_q_bar)
+      FDM_CUDA(cudaMemcpyAsync(h_q_bar + c.off * E, f->q_bar.at(c.off), (size_t)c.B * E * 8, cudaMemcpyDeviceToHost, c.st));
+  }
+  return FDM_OK;
+}
+
+// measurement only: exactly the copies of fdm_fa_enqueue_host (same chunking, same streams), no kernels --
+// what the host <-> device link can do for this call
+int fdm_fa_enqueue_copies_only(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar) {
+  if (!f || !h_q || !h_loss) return FDM_ERR_INVALID;
+  const int64_t E = f->plan->E;
+  for (Chunk& c : f->chunks) {
+    FDM_CUDA(cudaMemcpyAsync(f->q.at(c.off), h_q + c.off * E, (size_t)c.B * E * 8, cudaMemcpyHostToDevice, c.st));
+    FDM_CUDA(cudaMemcpyAsync(h_loss + c.off, f->loss.at(c.off), (size_t)c.B * 8, cudaMemcpyDeviceToHost, c.st));
+    if (h_q_bar)
+      FDM_CUDA(cudaMemcpyAsync(h_q_bar + c.off * E, f->q_bar.at(c.off), (size_t)c.B * E * 8, cudaMemcpyDeviceToHost, c.st));
+  }
+  return FDM_OK;
+}
+
+int fdm_fa_wait(fdm_fa* f) {
+  if (!f) return FDM_ERR_INVALID;
+  for (Chunk& c : f->chunks) FDM_CUDA(cudaStreamSynchronize(c.st));
+  return FDM_OK;
+}
+
+int fdm_fa_run_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar) {
+  int rc = fdm_fa_enqueue_host(f, h_q, h_loss, h_q_bar);
+  if (rc != FDM_OK) return rc;
+  return fdm_fa_wait(f);
+}
+
+int fdm_fa_device_array(fdm_fa* f, int which, void** d_out, int64_t* per_design) {
+  if (!f || !d_out) return FDM_ERR_INVALID;
+  const Buf* b = nullptr;
+  switch (which) {
+    case FDM_FA_Q: b = &f->q; break;
+    case FDM_FA_X_FREE: b = &f->x; break;
+    case FDM_FA_XYZ: b = &f->xyz; break;
+    case FDM_FA_LOSS: b = &f->loss; break;
+    case FDM_FA_Q_BAR: b = &f->q_bar; break;
+    case FDM_FA_LOADS_BAR: b = &f->loads_bar; break;
+    case FDM_FA_XYZ_FIXED_BAR: b = &f->xs_bar; break;
+    case FDM_FA_INFO_FORWARD: b = &f->info_f; break;
+    case FDM_FA_INFO_ADJOINT: b = &f->info_a; break;
+    case FDM_FA_LENGTHS: b = &f->lengths; break;
+    case FDM_FA_FORCES: b = &f->forces; break;
+    case FDM_FA_RESIDUALS: b = &f->residuals; break;
+    case FDM_FA_VECTORS: b = &f->vectors; break;
+    case FDM_FA_XYZ_FIXED: b = &f->xs; break;
+    case FDM_FA_LOADS: b = &f->loads; break;
+  }
+  if (!b || !b->p) {
+    fdm_set_error("fdm_fa_device_array: unknown or unallocated array");
+    return FDM_ERR_INVALID;
+  }
+  *d_out = b->p;
+  if (per_design) *per_design = b->per;
+  return FDM_OK;
+}
+
+int64_t fdm_fa_info(const fdm_fa* f, int which) {
+  if (!f) return FDM_ERR_INVALID;
+  switch (which) {
+    case FDM_FA_INFO_CHUNKS: return (int64_t)f->chunks.size();
+    case FDM_FA_INFO_LAUNCHES: return f->launches_per_step;
+    case FDM_FA_INFO_FUSED_ASSEMBLY: return f->fused ? 1 : 0;
+    case FDM_FA_INFO_GRAPH: return (f->capturable && f->o.use_graph) ? 1 : 0;
+    case FDM_FA_INFO_BATCH: return f->B;
+  }
+  return FDM_ERR_INVALID;
+}
+
+void* fdm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    fdm_set_error(std::string("fdm_host_alloc: ") + cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+
+void fdm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -68,6 +68,7 @@ struct WArgs {
   int64_t ws_stride;       // nblk*1024 (factor) + nblk*128 (intermediate rhs) + 8 (sigma, bad)
   int64_t nnz, batch;
   int forward;             // subst kernel: run the forward substitution on `rhs` first
+  int nan_fail;            // subst kernel: a design whose factorisation failed gets x = NaN
   // in-place assembly (chol_factor_mma_kernel<true>): K and the load term straight from q
   const double* q;         // (B, E)
   const double* xs;        // (B|1, Ns, 3)
@@ -810,7 +811,7 @@ template <int NBL>  // column group k reaches row groups k+1 .. k+NBL
 __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * kSubWarps + warp;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // designs per CTA = warps per CTA (host's choice)
   if (b >= A.batch) return;
   double* fsb = smem + warp * kSubWarpSmem;   // two staged blocks
   double* zt1 = fsb + 2 * 32 * kSS;
@@ -1008,6 +1009,12 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
       }
     }
   }
+  if (A.nan_fail && bad != 0) {                            // fdm_solve_opts.nan_on_failure
+    __syncwarp();
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double* xo = A.x + b * (int64_t)n * 3;
+    for (int i = lane; i < 3 * n; i += 32) xo[i] = qnan;
+  }
   if (A.info && lane == 0) {
     double* inf = A.info + b * FDM_INFO_STRIDE;
     inf[FDM_INFO_STATUS] = bad == 0 ? (double)FDM_STATUS_OK : bad == 2 ? (double)FDM_STATUS_BREAKDOWN : (double)FDM_STATUS_INDEFINITE;
@@ -1031,6 +1038,25 @@ inline int mma_warps_per_cta() {
     return v >= 1 && v <= kFacWarps ? v : kFacWarps;
   }();
   return w;
+}
+
+// designs (= warps) per CTA of the substitution kernel (FDM_CHOL_SUBWARPS) and extra dynamic shared memory
+// requested by the factor kernels to cap their CTAs per SM (FDM_CHOL_FAC_SMEM_PAD, bytes): experiments on
+// co-residency of the latency-bound factorisation of one slice with the bandwidth-bound kernels of another
+inline int sub_warps_per_cta() {
+  static const int w = [] {
+    const char* e = std::getenv("FDM_CHOL_SUBWARPS");
+    const int v = e ? std::atoi(e) : kSubWarps;
+    return v >= 1 && v <= kSubWarps ? v : kSubWarps;
+  }();
+  return w;
+}
+inline size_t fac_smem_pad() {
+  static const size_t v = [] {
+    const char* e = std::getenv("FDM_CHOL_FAC_SMEM_PAD");
+    return e ? (size_t)std::atol(e) : (size_t)0;
+  }();
+  return v;
 }
 
 inline int64_t ws_stride_of(const fdm_plan* p) {
@@ -1063,6 +1089,7 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   A.nnz = p->nnz;
   A.batch = batch;
   A.forward = 0;
+  A.nan_fail = 0;
   A.q = A.xs = A.loads = nullptr;
   A.q_stride = A.xs_stride = A.loads_stride = 0;
   A.diags_ptr = p->d.diags_ptr; A.diags_idx = p->d.diags_idx;
@@ -1075,15 +1102,16 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
 static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
   void (*skern)(WArgs) = p->hbw <= 7 ? chol_subst_kernel<1> : p->hbw <= 15 ? chol_subst_kernel<2>
                        : p->hbw <= 23 ? chol_subst_kernel<3> : chol_subst_kernel<4>;
-  const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
+  const int sw = sub_warps_per_cta();
+  const size_t smem = (size_t)sw * kSubWarpSmem * sizeof(double);
   FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  skern<<<(unsigned)((batch + kSubWarps - 1) / kSubWarps), kSubThreads, smem, st>>>(A);
+  skern<<<(unsigned)((batch + sw - 1) / sw), sw * 32, smem, st>>>(A);
   return FDM_OK;
 }
 
 int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
                            double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss,
-                           int64_t ls, cudaStream_t st) {
+                           int64_t ls, const fdm_solve_opts& o, cudaStream_t st) {
   if (!chol_warp_from_q_supported(p)) {
     fdm_set_error("chol_warp_solve_from_q: half bandwidth " + std::to_string(p->hbw) + " > 30");
     return FDM_ERR_UNSUPPORTED;
@@ -1096,18 +1124,23 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   fill_common(A, p, x, info, ws, batch);
   A.q = q; A.xs = xs; A.loads = loads;
   A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
+  A.nan_fail = o.nan_on_failure;
+  const int stages = o.stages ? o.stages : 7;
   const int fw = mma_warps_per_cta();
-  const size_t smem = (size_t)fw * kMmaWarpSmem * sizeof(double);
+  const size_t smem = (size_t)fw * kMmaWarpSmem * sizeof(double) + fac_smem_pad();
   void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, false> : chol_factor_mma_kernel<true, 2, false>;
-  FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
-  {   // designs with a non-positive pivot (mixed-sign q) are factored again with signed pivots
+  if (stages & 1) {
+    FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    // designs with a non-positive pivot (mixed-sign q) are factored again with signed pivots
     void (*skern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, true> : chol_factor_mma_kernel<true, 2, true>;
     FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     skern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
   }
-  int rc = launch_backward(p, A, batch, st);
-  if (rc != FDM_OK) return rc;
+  if (stages & 4) {
+    int rc = launch_backward(p, A, batch, st);
+    if (rc != FDM_OK) return rc;
+  }
   return fdm_check_launch("chol_warp_solve_from_q");
 }
 
@@ -1136,6 +1169,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.nnz = p->nnz;
   A.batch = batch;
   A.forward = o.reuse_factor ? 1 : 0;
+  A.nan_fail = o.nan_on_failure;
   A.q = A.xs = A.loads = nullptr;
   A.q_stride = A.xs_stride = A.loads_stride = 0;
   A.diags_ptr = A.diags_idx = A.free_node = A.node_slot = nullptr;
@@ -1157,7 +1191,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     if (mma) {
       fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, false> : chol_factor_mma_kernel<false, 2, false>;
       fw = mma_warps_per_cta();
-      smem = (size_t)fw * kMmaWarpSmem * sizeof(double);
+      smem = (size_t)fw * kMmaWarpSmem * sizeof(double) + fac_smem_pad();
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
@@ -1172,9 +1206,10 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
   }
   if (stages & 4) {
-    const size_t smem = (size_t)kSubWarps * kSubWarpSmem * sizeof(double);
+    const int sw = sub_warps_per_cta();
+    const size_t smem = (size_t)sw * kSubWarpSmem * sizeof(double);
     FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    skern<<<(unsigned)((batch + kSubWarps - 1) / kSubWarps), kSubThreads, smem, st>>>(A);
+    skern<<<(unsigned)((batch + sw - 1) / sw), sw * 32, smem, st>>>(A);
   }
   return fdm_check_launch("chol_warp_solve");
 }

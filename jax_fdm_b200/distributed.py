@@ -13,6 +13,8 @@ form is `jax.vmap(model, in_axes=(0, None))` on one device (visualization/plotte
 loss_plotter.py:98-103).  This module is what replaces "vmap on one device" at 2-8 GPUs.
 """
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -42,11 +44,24 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def _batch_sum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[i] = sum_b x[b, i]: this library's fixed-order reduction kernel (fdm_batch_sum) for device tensors; the
+    world-size-2 `gloo` tests drive the host logic with CPU tensors, which take torch.sum."""
+    if not x.is_cuda:
+        return out.copy_(torch.sum(x, dim=0).reshape(out.shape))
+    from . import _lib as L
+    x = x.contiguous()
+    n = x[0].numel() if x.dim() > 1 else 1
+    st = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    L.check(L.lib().fdm_batch_sum(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), x.shape[0], n, st))
+    return out
+
+
 def total_loss(loss_per_design: torch.Tensor, out: torch.Tensor = None, group=None) -> torch.Tensor:
     """sum_b L_b over the local shard, then over ranks: the scalar a shared optimiser sees."""
     if out is None:
         out = torch.zeros(1, dtype=loss_per_design.dtype, device=loss_per_design.device)
-    torch.sum(loss_per_design, dim=0, keepdim=True, out=out)
+    _batch_sum(loss_per_design, out)
     return allreduce_sum_(out, group)
 
 
@@ -57,5 +72,5 @@ def shared_parameter_grad(grad_per_design: torch.Tensor, out: torch.Tensor = Non
     """
     if out is None:
         out = torch.zeros(grad_per_design.shape[1:], dtype=grad_per_design.dtype, device=grad_per_design.device)
-    torch.sum(grad_per_design, dim=0, out=out)
+    _batch_sum(grad_per_design, out)
     return allreduce_sum_(out, group)

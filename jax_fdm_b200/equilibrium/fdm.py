@@ -11,10 +11,14 @@ import numpy as np
 import torch
 
 from .models import EquilibriumModel, EquilibriumModelSparse
-from .states import EquilibriumParametersState, LoadState
-from .structures import EquilibriumStructure, EquilibriumStructureSparse
+from .states import DatastructureState, EquilibriumParametersState, EquilibriumState, LoadState, _is_mesh
+from .structures import (EquilibriumMeshStructure, EquilibriumMeshStructureSparse, EquilibriumStructure,
+                         EquilibriumStructureSparse)
 
-__all__ = ["fdm", "constrained_fdm", "model_from_sparsity", "structure_from_arrays", "arrays_validate"]
+__all__ = ["fdm", "constrained_fdm", "model_from_sparsity", "structure_from_arrays", "arrays_validate",
+           "structure_from_datastructure", "structure_from_network", "structure_from_mesh", "datastructure_state",
+           "datastructure_validate", "datastructure_updated", "datastructure_update", "datastructure_edges_update",
+           "datastructure_nodes_update"]
 
 
 def arrays_validate(edges, supports, q):
@@ -72,3 +76,79 @@ def constrained_fdm(nodes, edges, supports, q, xyz_fixed, loads, optimizer, loss
     state, _ = fdm(nodes, edges, supports, q_opt, xyz_fixed, loads, sparse=sparse, tmax=tmax, eta=eta,
                    is_load_local=is_load_local, device=device, structure=structure, **solve_opts)
     return state, structure, q_opt
+
+
+# ---- the COMPAS-facing helpers of fdm.py:365-700 ------------------------------------------------------------------
+# COMPAS (FDNetwork / FDMesh) is a modelling layer above the path and is not installed here; these take ANY object
+# with the accessors the reference calls (nodes() / edges() / is_node_support(), edges_forcedensities(),
+# node_attribute(), ...), so a COMPAS datastructure works unchanged and the tests use a small array-backed stand-in.
+def structure_from_network(network, sparse=True, device=0):
+    """fdm.py:396-417."""
+    return (EquilibriumStructureSparse if sparse else EquilibriumStructure).from_network(network, device=device)
+
+
+def structure_from_mesh(mesh, sparse=True, device=0):
+    """fdm.py:420-441."""
+    return (EquilibriumMeshStructureSparse if sparse else EquilibriumMeshStructure).from_mesh(mesh, device=device)
+
+
+def structure_from_datastructure(datastructure, sparse=True, device=0):
+    """fdm.py:365-393."""
+    return (structure_from_mesh if _is_mesh(datastructure) else structure_from_network)(datastructure, sparse, device)
+
+
+def datastructure_state(datastructure, sparse=True, device=0):
+    """fdm.py:444-488: structure, parameters and the STORED equilibrium state of a datastructure, without solving."""
+    structure = structure_from_datastructure(datastructure, sparse, device)
+    dev = None if device is None else torch.device("cuda", device)
+    parameters = EquilibriumParametersState.from_datastructure(datastructure, device=dev)
+    eq_state = EquilibriumState.from_datastructure(datastructure, structure, device=dev)
+    return DatastructureState(eq_state, structure, parameters)
+
+
+def datastructure_validate(datastructure):
+    """fdm.py:491-522."""
+    assert datastructure.number_of_supports() > 0, "The FD datastructure has no supports"
+    assert datastructure.number_of_edges() > 0, "The FD datastructure has no edges"
+    has_fd = np.abs(np.array(datastructure.edges_forcedensities())) > 0.0
+    assert np.all(has_fd), f"The FD datastructure has {int(np.sum(~has_fd))} edges with zero force density"
+    if _is_mesh(datastructure):
+        assert datastructure.number_of_vertices() > 0, "The FD datastructure has no vertices"
+    else:
+        assert datastructure.number_of_nodes() > 0, "The FD datastructure has no nodes"
+
+
+def datastructure_updated(datastructure, eq_state, params, use_loadsfromparams=False):
+    """fdm.py:525-563: a copy of the datastructure carrying the equilibrium state."""
+    datastructure = datastructure.copy()
+    datastructure_update(datastructure, eq_state, params, use_loadsfromparams)
+    return datastructure
+
+
+def datastructure_update(datastructure, eq_state, params, use_loadsfromparams=False):
+    """fdm.py:566-613: write the state onto the datastructure in place (one device-to-host copy per array)."""
+    host = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    loads = host(params.loads.nodes) if use_loadsfromparams else host(eq_state.loads)
+    datastructure_edges_update(datastructure, (host(eq_state.lengths), host(eq_state.forces), host(params.q)))
+    datastructure_nodes_update(datastructure, (host(eq_state.xyz), host(eq_state.residuals), loads))
+
+
+def datastructure_edges_update(datastructure, eqstate_edges):
+    """fdm.py:616-637: per-edge length, force and force density."""
+    lengths, forces, forcedensities = (np.asarray(a, dtype=np.float64).reshape(-1) for a in eqstate_edges)
+    for idx, edge in datastructure.index_edge().items():
+        datastructure.edge_attribute(edge, name="length", value=float(lengths[idx]))
+        datastructure.edge_attribute(edge, name="force", value=float(forces[idx]))
+        datastructure.edge_attribute(edge, name="q", value=float(forcedensities[idx]))
+
+
+def datastructure_nodes_update(datastructure, eqstate_nodes):
+    """fdm.py:640-672: per-node (vertex) coordinates, residuals and loads."""
+    xyz, residuals, loads = (np.asarray(a, dtype=np.float64).reshape(-1, 3) for a in eqstate_nodes)
+    mesh = _is_mesh(datastructure)
+    update = datastructure.vertex_attribute if mesh else datastructure.node_attribute
+    index_key = datastructure.index_vertex if mesh else datastructure.index_node
+    for idx, key in index_key().items():
+        for names, row in ((("x", "y", "z"), xyz[idx]), (("rx", "ry", "rz"), residuals[idx]), (("px", "py", "pz"), loads[idx])):
+            for name, value in zip(names, row):
+                update(key, name=name, value=float(value))

@@ -13,7 +13,8 @@ Both give the same numbers; tests compare them.
 import torch
 
 from . import ops
-from .solvers import fixed_point_bwd_adjoint, solver_fixedpoint_implicit, solver_forward
+from .solvers import (fixed_point_bwd_adjoint, is_solver_fixedpoint, is_solver_leastsquares, is_solver_root_finding,
+                      solver_fixedpoint_implicit, solver_forward)
 from .sparse import CSC, sparse_solve
 from .states import EquilibriumParametersState, EquilibriumState, LoadState
 
@@ -33,25 +34,7 @@ class _Stiffness(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gK):
-        s = ctx.structure
-        dev = gK.device
-        cache = getattr(s, "_torch_kmap", None)
-        if cache is None or cache[0].device != dev:
-            import numpy as np
-            ia = s.index_array
-            off = np.flatnonzero(ia.data > 0)
-            cache = (torch.as_tensor(off, device=dev),
-                     torch.as_tensor(ia.data[off] - 1, device=dev),
-                     torch.as_tensor(s.diag_indices, device=dev),
-                     torch.as_tensor(np.repeat(np.arange(s.num_free), np.diff(s.diags_indptr)), device=dev),
-                     torch.as_tensor(s.diags_indices.astype("int64"), device=dev))
-            s._torch_kmap = cache
-        off, off_edge, dpos, drow, dedge = cache
-        lead = gK.shape[:-1]
-        qbar = torch.zeros(lead + (s.num_edges,), dtype=gK.dtype, device=dev)
-        qbar.index_add_(-1, off_edge, -gK.index_select(-1, off))
-        qbar.index_add_(-1, dedge, gK.index_select(-1, dpos).index_select(-1, drow))
-        return qbar, None
+        return ops.stiffness_vjp(ctx.structure, gK.contiguous()), None
 
 
 class _LoadMatrix(torch.autograd.Function):
@@ -95,6 +78,51 @@ class _State(torch.autograd.Function):
         qb, xb, pb = ops.state_vjp(ctx.structure, q, xyz, residuals_cot=gr, lengths_cot=gl,
                                    forces_cot=gf, vectors_cot=gv)
         return qb, xb, pb, None
+
+
+class _NodesResiduals(torch.autograd.Function):
+    """loads - C^T (q * vectors) for GIVEN edge vectors (models.py:164-193) and its transposes.  C^T w is the
+    xyz-cotangent of the state map for a cotangent w of `vectors` alone (vectors = C xyz), so the segmented sum over
+    each node's incident edges runs in fdm_state_vjp; C g, needed by the transposes, is fdm_state on g."""
+
+    @staticmethod
+    def forward(ctx, q, loads, vectors, structure):
+        ctx.structure = structure
+        ctx.save_for_backward(q, vectors)
+        qv = (q.unsqueeze(-1) * vectors).contiguous()
+        zero_xyz = torch.zeros_like(loads)
+        # xyz_bar of the state VJP with only a `vectors` cotangent is C^T vectors_cot
+        _, ct, _ = ops.state_vjp(structure, q.contiguous(), zero_xyz, vectors_cot=qv)
+        return loads - ct
+
+    @staticmethod
+    def backward(ctx, g):
+        q, vectors = ctx.saved_tensors
+        s = ctx.structure
+        # C g per edge = edge vectors of the "geometry" g
+        Cg = ops.state(s, torch.zeros_like(q), g.contiguous(), torch.zeros_like(g))[0]
+        gq = -(Cg * vectors).sum(-1) if ctx.needs_input_grad[0] else None
+        gv = -(q.unsqueeze(-1) * Cg) if ctx.needs_input_grad[2] else None
+        return gq, g, gv, None
+
+
+def _Positions_free(loads_nodes, structure):
+    """loads[indices_free]: the free rows of a nodal array (the transpose half of nodes_positions)."""
+    return _PositionsT.apply(loads_nodes, structure)
+
+
+class _PositionsT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz_like, structure):
+        ctx.structure = structure
+        ctx.ns = structure.num_supports
+        return ops.positions_vjp(structure, xyz_like.contiguous())[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        s = ctx.structure
+        zeros = torch.zeros(g.shape[:-2] + (ctx.ns, 3), dtype=g.dtype, device=g.device)
+        return ops.positions(s, g.contiguous(), zeros), None
 
 
 class _Positions(torch.autograd.Function):
@@ -266,22 +294,69 @@ class EquilibriumModel:
     "sparse" split of the reference is a storage choice, not different arithmetic.
     """
 
-    def __init__(self, tmax=1, eta=1e-6, is_load_local=False, itersolve_fn=None, iterload_fn=None,
+    def __init__(self, tmax=100, eta=1e-6, is_load_local=False, itersolve_fn=None, iterload_fn=None,
                  implicit_diff=True, verbose=False, solver="auto", tol=0.0, max_iters=0):
-        self.tmax = tmax
+        self.tmax = tmax                                  # default 100, as models.py:77
         self.eta = eta
         self.is_load_local = is_load_local
-        self.itersolve_fn = itersolve_fn
+        self.itersolve_fn = itersolve_fn or solver_forward
         self.iterload_fn = iterload_fn
+        self.eq_iterative_fn = self.select_equilibrium_iterative_fn(self.itersolve_fn)
         self.implicit_diff = implicit_diff
         self.verbose = verbose
         self.solve_opts = {"solver": solver, "tol": tol, "max_iters": max_iters}
         self.linearsolve_fn = lambda K, P: sparse_solve(K, P, **self.solve_opts)
 
     # ---- edges / nodes (models.py:99-193) -------------------------------------------
+    # The method-by-method route: the reference's one-liners with the same names and argument meaning.  `connectivity`
+    # is `structure.connectivity` (scipy CSC / dense array carrying a reference to its structure) or the structure
+    # itself; the products run in this library's kernels (fdm_state), not as matrix products.
+    @staticmethod
+    def _structure_of(connectivity):
+        s = getattr(connectivity, "_fdm_structure", None)
+        s = s() if callable(s) else s
+        if s is None and hasattr(connectivity, "plan"):
+            s = connectivity
+        if s is None:
+            raise TypeError("pass `structure.connectivity` (or the structure): the edge lists live in its plan")
+        return s
+
+    @classmethod
+    def edges_vectors(cls, xyz, connectivity):
+        """models.py:99-119: C @ xyz."""
+        s = cls._structure_of(connectivity)
+        q0 = torch.zeros(xyz.shape[:-2] + (s.num_edges,), dtype=xyz.dtype, device=xyz.device)
+        return _State.apply(q0, xyz, torch.zeros_like(xyz), s)[0]
+
+    @staticmethod
+    def edges_lengths(vectors):
+        """models.py:121-136: row norms, shape (E, 1)."""
+        return torch.linalg.norm(vectors, dim=-1, keepdim=True)
+
+    @staticmethod
+    def edges_forces(q, lengths):
+        """models.py:138-162: q * lengths, shape (E, 1)."""
+        return q.unsqueeze(-1) * lengths
+
+    @classmethod
+    def nodes_residuals(cls, q, loads, vectors, connectivity):
+        """models.py:164-193: loads - C^T (q * vectors)."""
+        s = cls._structure_of(connectivity)
+        return _NodesResiduals.apply(q, loads, vectors, s)
+
     @staticmethod
     def nodes_positions(xyz_free, xyz_fixed, structure):
         return _Positions.apply(xyz_free, xyz_fixed, structure)
+
+    @staticmethod
+    def faces_load(xyz, faces_load, structure, is_local=False):
+        """models.py:348-375: tributary face loads on the nodes (nodes_load_from_faces)."""
+        return _FacesLoad.apply(xyz, torch.zeros_like(xyz), faces_load, structure, is_local)
+
+    @staticmethod
+    def edges_load(xyz, edges_load, structure, is_local=False):
+        """models.py:377-404: tributary edge loads on the nodes (nodes_load_from_edges)."""
+        return _NodesLoad.apply(xyz, torch.zeros_like(xyz), edges_load, structure, is_local)
 
     # ---- matrices -------------------------------------------------------------------------
     @staticmethod
@@ -296,11 +371,46 @@ class EquilibriumModel:
         zero = torch.zeros((structure.num_nodes, 3), dtype=q.dtype, device=q.device)
         return -_LoadMatrix.apply(q, xyz_fixed, zero, structure)
 
-    def residual_free_matrix(self, params, xyz_free, structure):
+    def load_xyz_matrix(self, params, xyz_free, structure):
+        """models.py:858-896: the load matrix with the shape-dependent loads evaluated at xyz_free."""
         q, xyz_fixed, load_state = params
+        xyz = self.nodes_positions(xyz_free, xyz_fixed, structure)
+        loads_nodes = self.nodes_load(xyz, load_state, structure)
+        return self.load_matrix(q, xyz_fixed, loads_nodes, structure)
+
+    def load_xyz_matrix_from_r_fixed(self, params, xyz_free, structure):
+        """models.py:898-947: the same with the support term R_fixed precomputed: params = (K, R_fixed, xyz_fixed,
+        load_state)."""
+        _, R_fixed, xyz_fixed, load_state = params
+        xyz = self.nodes_positions(xyz_free, xyz_fixed, structure)
+        loads_nodes = self.nodes_load(xyz, load_state, structure)
+        return _Positions_free(loads_nodes, structure) - R_fixed
+
+    def residual_free_matrix(self, params, xyz_free, structure):
+        """models.py:978-1014: K x_free - P(x_free)."""
+        q = params[0]
         K = self.stiffness_matrix(q, structure)
-        P = self.load_matrix(q, xyz_fixed, load_state.nodes, structure)
+        P = self.load_xyz_matrix(params, xyz_free, structure)
         return K @ xyz_free - P
+
+    def select_equilibrium_iterative_fn(self, solver):
+        """models.py:721-751.  Fixed-point solvers drive equilibrium_iterative_xyz; the least-squares and
+        root-finding families (jaxopt / optimistix wrappers, solvers/least_squares.py, root_finding.py) drive the
+        residual form, which is outside this build."""
+        if is_solver_fixedpoint(solver):
+            return self.equilibrium_iterative_xyz
+        if is_solver_leastsquares(solver) or is_solver_root_finding(solver):
+            return self.equilibrium_iterative_residual
+        raise ValueError(f"Solver {solver} is not supported!")
+
+    def equilibrium_iterative_residual(self, q, xyz_fixed, load_state, structure, xyz_free_init=None, tmax=100,
+                                       eta=1e-6, solver=None, implicit_diff=True, verbose=False):
+        """models.py:620-719: root of K x - P(x) by a least-squares / Newton solver.  Those solvers are wrappers
+        of jaxopt / optimistix, which this build does not restate; the fixed-point form
+        (`equilibrium_iterative_xyz`, the reference's default) reaches the same equilibrium."""
+        raise NotImplementedError("the residual form needs a least-squares or root-finding solver (jaxopt / "
+                                  "optimistix wrappers): outside this build; use a fixed-point solver "
+                                  "(itersolve_fn=solver_forward, the default)")
 
     # ---- equilibrium ------------------------------------------------------------------------
     def nodes_free_positions(self, q, xyz_fixed, loads, structure, fused=True):
@@ -353,10 +463,19 @@ class EquilibriumModel:
     def equilibrium_iterative_xyz(self, q, xyz_fixed, load_state, structure, xyz_free_init=None, tmax=100,
                                   eta=1e-6, solver=None, implicit_diff=True, verbose=False):
         """models.py:512-618."""
-        if not implicit_diff:
-            raise NotImplementedError("unrolled differentiation of the fixed point is not built; use implicit_diff=True")
         if xyz_free_init is None:
             xyz_free_init = self.equilibrium(q, xyz_fixed, load_state.nodes, structure)
+        if not implicit_diff:
+            # Unrolled differentiation (models.py:615, fixed_point.py:139-198 differentiated through the loop):
+            # every iteration x <- K(q)^{-1} P(theta, x) is an autograd node of the same kernels, so the reverse
+            # pass walks the iterations backwards.  Like the reference's loop it re-factorises K per iteration.
+            def f(_, x):
+                xyz = self.nodes_positions(x, xyz_fixed, structure)
+                return _FusedFreePositions.apply(q, xyz_fixed, self.nodes_load(xyz, load_state, structure), structure,
+                                                 self.solve_opts)
+            config = {"tmax": tmax, "eta": eta, "verbose": verbose}
+            self.last_solver_config = config
+            return (solver or self.itersolve_fn)(f, None, xyz_free_init, config)
         edges_load = load_state.edges
         if not (isinstance(edges_load, torch.Tensor) and edges_load.numel() > 1):
             edges_load = torch.zeros((structure.num_edges, 3), dtype=q.dtype, device=q.device)

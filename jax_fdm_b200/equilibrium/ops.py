@@ -5,6 +5,7 @@ batch axis (B designs sharing the structure) and runs on torch's current stream.
 """
 
 import ctypes as C
+import threading
 
 import torch
 
@@ -13,8 +14,14 @@ from .. import _lib as L
 F64 = torch.float64
 
 
+_tls = threading.local()
+
+
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """torch's current stream ON THE DEVICE OF THE TENSORS of this call (the last one `_chk` saw), not on the
+    process's current device."""
+    dev = getattr(_tls, "device", None)
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def _ptr(t):
@@ -26,6 +33,7 @@ def _chk(t, name, shape_tail):
         raise TypeError(f"{name}: expected a float64 CUDA tensor, got {t.dtype} on {t.device}")
     if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
         raise ValueError(f"{name}: trailing shape {tuple(t.shape)} != {tuple(shape_tail)}")
+    _tls.device = t.device
     return t.contiguous()
 
 
@@ -122,12 +130,10 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     sid = L.SOLVERS[solver] if isinstance(solver, str) else int(solver)
     ws = workspace if workspace is not None else Workspace()
     buf, need = ws.get(s, B, sid, rhs.device)
-    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)), int(stages))
+    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)), int(stages),
+                       int(bool(nan_on_failure)))                 # the NaN select happens in the solve's own kernels
     L.check(L.lib().fdm_solve(s.plan, _ptr(Kdata), _ptr(rhs), _ptr(x), _ptr(info), _ptr(buf),
                               buf.numel(), B, C.byref(opts), _stream()))
-    if nan_on_failure:
-        failed = (info[:, 0] != 0).view((B, 1, 1) if x.dim() == 3 else (1, 1))
-        x = torch.where(failed, torch.full_like(x, float("nan")), x)
     return (x, info) if return_info else x
 
 
@@ -152,15 +158,12 @@ def solve_from_q(structure, q, xyz_fixed, loads, workspace=None, return_info=Fal
     buf, _ = ws.get(s, B, sid, q.device)
     x = torch.empty(((B,) if batched else ()) + (Nf, 3), dtype=F64, device=q.device)
     info = torch.zeros((B, L.INFO_STRIDE), dtype=F64, device=q.device)
-    opts = L.SolveOpts(sid, 0, 0.0, 0, 0)
+    opts = L.SolveOpts(sid, 0, 0.0, 0, 0, 0, int(bool(nan_on_failure)))
     rc = L.lib().fdm_solve_from_q(s.plan, _ptr(q), _ptr(xyz_fixed), _ptr(loads), _ptr(x), _ptr(info), _ptr(buf),
                                   buf.numel(), B, E, _stride(xyz_fixed, 2), _stride(loads, 2), C.byref(opts), _stream())
     if rc == -5:          # FDM_ERR_UNSUPPORTED
         return None
     L.check(rc)
-    if nan_on_failure:    # as in `solve`
-        failed = (info[:, 0] != 0).view((B, 1, 1) if x.dim() == 3 else (1, 1))
-        x = torch.where(failed, torch.full_like(x, float("nan")), x)
     return (x, info) if return_info else x
 
 
@@ -178,6 +181,31 @@ def spmm(structure, Kdata, X):
     Y = torch.empty_like(X)
     L.check(L.lib().fdm_spmm(s.plan, _ptr(Kdata), _ptr(X), _ptr(Y), B, _stream()))
     return Y
+
+
+def kbar_pattern(structure, a, b, sign=1.0):
+    """Kbar.data[k] = sign * sum_xyz a[row_k] * b[col_k] on the structure's pattern (fdm_kbar_pattern): the
+    cotangent of K of sparse_solve_bwd (sparse.py:299-306) and the VJP of `K @ x` w.r.t. K.data."""
+    s = structure
+    a = _chk(a, "a", (s.num_free, 3))
+    b = _chk(b, "b", (s.num_free, 3))
+    B, batched = _resolve_batch((a, 2), (b, 2))
+    if batched:
+        a = a if a.dim() == 3 else a.expand(B, -1, -1).contiguous()
+        b = b if b.dim() == 3 else b.expand(B, -1, -1).contiguous()
+    out = torch.empty(((B,) if batched else ()) + (s.nnz,), dtype=F64, device=a.device)
+    L.check(L.lib().fdm_kbar_pattern(s.plan, _ptr(a), _ptr(b), _ptr(out), float(sign), B, _stream()))
+    return out
+
+
+def stiffness_vjp(structure, Kbar):
+    """q_bar from Kbar.data: the transpose of stiffness_matrix (models.py:1069-1077; fdm_stiffness_vjp)."""
+    s = structure
+    Kbar = _chk(Kbar, "Kbar", (s.nnz,))
+    B, batched = _resolve_batch((Kbar, 1))
+    out = torch.empty(((B,) if batched else ()) + (s.num_edges,), dtype=F64, device=Kbar.device)
+    L.check(L.lib().fdm_stiffness_vjp(s.plan, _ptr(Kbar), _ptr(out), B, _stream()))
+    return out
 
 
 def positions(structure, x_free, xyz_fixed):

@@ -18,11 +18,38 @@ import torch
 
 from . import ops
 
-__all__ = ["solver_forward", "solver_fixedpoint_implicit", "fixed_point_bwd_adjoint", "is_solver_fixedpoint"]
+from typing import NamedTuple
+
+__all__ = ["solver_forward", "solver_fixedpoint_implicit", "fixed_point_bwd_adjoint", "is_solver_fixedpoint",
+           # the rest of the reference's solvers namespace (solvers/*.py __all__): importable, see the bottom
+           "SolverIterParams", "fixed_point_bwd_adjoint_general", "fixed_point_bwd_fixedpoint",
+           "fixed_point_bwd_materialize", "fixed_point_fwd", "solver_anderson", "solver_fixedpoint",
+           "is_solver_leastsquares", "is_solver_root_finding", "solver_dogleg", "solver_gauss_newton",
+           "solver_levenberg_marquardt", "solver_newton", "solver_jaxopt", "solver_optimistix",
+           "nonlinear_bwd", "nonlinear_fwd", "solver_nonlinear_implicit"]
+
+
+class SolverIterParams(NamedTuple):
+    """solvers/types.py: the knobs every iterative solver takes."""
+    tmax: int = 100
+    eta: float = 1e-6
+    implicit_diff: bool = True
+    verbose: bool = False
 
 
 def is_solver_fixedpoint(solver) -> bool:
-    return solver in (None, solver_forward)
+    """fixed_point.py:48-63."""
+    return solver in (None, solver_forward, solver_fixedpoint, solver_anderson)
+
+
+def is_solver_leastsquares(solver) -> bool:
+    """least_squares.py: the Gauss-Newton family."""
+    return solver in (solver_gauss_newton, solver_levenberg_marquardt, solver_dogleg)
+
+
+def is_solver_root_finding(solver) -> bool:
+    """root_finding.py."""
+    return solver in (solver_newton,)
 
 
 def solver_forward(f, a, x_init, solver_config):
@@ -60,3 +87,43 @@ def fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, vec, tol=1e-12, max_iters=200
 def solver_fixedpoint_implicit(solver, solver_config, f, a, x_init):
     """fixed_point.py:206-240: run `solver`; the implicit backward rule lives in models._FixedPoint."""
     return (solver or solver_forward)(f, a, x_init, solver_config)
+
+
+# ---- the remaining names of the reference's solvers namespace ------------------------------------------------------
+# The equilibrium path of BASELINE.json runs on `solver_forward` (the reference's default, models.py:89) and its
+# implicit adjoint.  The other entries are thin wrappers of third-party iteration libraries (jaxopt, optimistix:
+# Anderson acceleration, Gauss-Newton / Levenberg-Marquardt / dogleg, Newton) or alternative backward rules of the
+# same fixed point; they are kept importable so code that names them loads, and say what to use when called.
+def _outside(name, use):
+    def fn(*args, **kwargs):
+        raise NotImplementedError(f"{name}: a wrapper of a third-party iteration library in the reference, outside this "
+                                  f"build (SURVEY.md §8, out of scope); use {use}")
+    fn.__name__ = name
+    fn.__doc__ = f"Reference name kept importable; raises NotImplementedError (use {use})."
+    return fn
+
+
+def solver_fixedpoint(f, a, x_init, solver_config):
+    """fixed_point.py:66-136 (jaxopt FixedPointIteration): the same iteration as `solver_forward`."""
+    return solver_forward(f, a, x_init, solver_config)
+
+
+def fixed_point_fwd(solver, solver_config, f, a, x_init):
+    """fixed_point.py:243-290: forward pass of the implicit rule -> (x*, residuals)."""
+    x_star = solver_fixedpoint_implicit(solver, solver_config, f, a, x_init)
+    return x_star, (a, x_star)
+
+
+solver_anderson = _outside("solver_anderson", "solver_forward")
+solver_gauss_newton = _outside("solver_gauss_newton", "solver_forward")
+solver_levenberg_marquardt = _outside("solver_levenberg_marquardt", "solver_forward")
+solver_dogleg = _outside("solver_dogleg", "solver_forward")
+solver_newton = _outside("solver_newton", "solver_forward")
+solver_jaxopt = _outside("solver_jaxopt", "solver_forward")
+solver_optimistix = _outside("solver_optimistix", "solver_forward")
+solver_nonlinear_implicit = _outside("solver_nonlinear_implicit", "solver_fixedpoint_implicit")
+nonlinear_fwd = _outside("nonlinear_fwd", "solver_fixedpoint_implicit")
+nonlinear_bwd = _outside("nonlinear_bwd", "fixed_point_bwd_adjoint")
+fixed_point_bwd_adjoint_general = _outside("fixed_point_bwd_adjoint_general", "fixed_point_bwd_adjoint")
+fixed_point_bwd_fixedpoint = _outside("fixed_point_bwd_fixedpoint", "fixed_point_bwd_adjoint")
+fixed_point_bwd_materialize = _outside("fixed_point_bwd_materialize", "fixed_point_bwd_adjoint")

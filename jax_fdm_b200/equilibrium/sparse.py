@@ -18,12 +18,23 @@ from . import ops
 
 __all__ = [
     "CSC",
+    "SparseSolveResidual",
+    "SystemMatrixLHS",
+    "SystemMatrixRHS",
+    "SystemSolution",
+    "blockdiag_matrix_sparse",
     "register_sparse_solver",
     "sparse_solve",
     "sparse_solve_fwd",
     "sparse_solve_bwd",
+    "splu_clear",
+    "splu_cpu",
+    "splu_solve_cpu",
     "spsolve",
+    "spsolve_cpu",
     "spsolve_gpu",
+    "spsolve_gpu_ravel",
+    "spsolve_gpu_stack",
 ]
 
 
@@ -90,22 +101,9 @@ class _SpMM(torch.autograd.Function):
         return gd, gx, None
 
 
-def _pattern_rows_cols(s, device):
-    cache = getattr(s, "_torch_pattern", None)
-    if cache is None or cache[0].device != device:
-        import numpy as np
-        ia = s.index_array
-        cols = np.repeat(np.arange(s.num_free), np.diff(ia.indptr))
-        cache = (torch.as_tensor(ia.indices.astype("int64"), device=device),
-                 torch.as_tensor(cols.astype("int64"), device=device))
-        s._torch_pattern = cache
-    return cache
-
-
-def _outer_on_pattern(s, a, b):
-    """sum_xyz a[row_k] * b[col_k] for every stored entry k (API-parity path, not the hot path)."""
-    rows, cols = _pattern_rows_cols(s, a.device)
-    return (a.index_select(-2, rows) * b.index_select(-2, cols)).sum(-1)
+def _outer_on_pattern(s, a, b, sign=1.0):
+    """sign * sum_xyz a[row_k] * b[col_k] for every stored entry k: this library's kernel (fdm_kbar_pattern)."""
+    return ops.kbar_pattern(s, a.contiguous(), b.contiguous(), sign)
 
 
 class _SparseSolve(torch.autograd.Function):
@@ -121,7 +119,7 @@ class _SparseSolve(torch.autograd.Function):
         x, data, b = ctx.saved_tensors
         s = ctx.structure
         lam = ops.solve(s, data, g.contiguous(), **ctx.opts)      # sparse.py:296 (A symmetric)
-        gd = -_outer_on_pattern(s, lam, x) if ctx.needs_input_grad[0] else None   # sparse.py:299-306
+        gd = _outer_on_pattern(s, lam, x, -1.0) if ctx.needs_input_grad[0] else None   # sparse.py:299-306
         gb = lam if ctx.needs_input_grad[1] else None
         return gd, gb, None, None
 
@@ -143,4 +141,75 @@ def sparse_solve_bwd(res, g, **opts):
     xk, A, b = res
     o = {**_DEFAULT_OPTS, **opts}
     lam = ops.solve(A.structure, A.data.detach(), g.contiguous(), **o)
-    return CSC(-_outer_on_pattern(A.structure, lam, xk.detach()), A.structure), lam
+    return CSC(_outer_on_pattern(A.structure, lam, xk.detach(), -1.0), A.structure), lam
+
+
+# ---- the remaining names of sparse.py:33-51 --------------------------------------------------------------------
+SystemMatrixLHS = CSC                      # sparse.py:25-30: type aliases of the solve's operands
+SystemMatrixRHS = torch.Tensor
+SystemSolution = torch.Tensor
+SparseSolveResidual = tuple                # (xk, A, b), sparse.py:239
+
+# one 3-rhs kernel solve serves both GPU formulations of the reference (ravelled 3n x 3n block system,
+# sparse.py:54-84; three stacked single-rhs solves, :86-96): same solution, no block-diagonal copy
+spsolve_gpu_ravel = spsolve_gpu
+spsolve_gpu_stack = spsolve_gpu
+
+
+def spsolve_cpu(A, b):
+    """sparse.py:130-159 (scipy SuperLU through a host callback).  This build has no CPU path by contract."""
+    raise RuntimeError("spsolve_cpu: there is no CPU path in jax_fdm_b200 (the solve runs in the sm_100a kernels); "
+                       "use spsolve / spsolve_gpu")
+
+
+def blockdiag_matrix_sparse(A: CSC, num: int = 2, format=None):
+    """sparse.py:161-205: `num` copies of A on the diagonal, as (data, indices, indptr, shape) in CSC order.  The
+    reference needs it to solve three right-hand sides with a single-rhs solver; the kernels here take the three
+    right-hand sides directly, so nothing on the path calls it."""
+    import numpy as np
+
+    assert num > 1, "Block diagonal matrix must have at least 2 blocks."
+    n, m = A.shape
+    assert n == m, "Supported sparse matrices must be square."
+    nnz = int(A.indptr[-1])
+    indptr = np.concatenate([(A.indptr + i * nnz)[(1 if i else 0):] for i in range(num)])
+    indices = np.concatenate([A.indices + i * n for i in range(num)])
+    data = torch.cat([A.data] * num, dim=-1)
+    out = (data, indices, indptr)
+    return format(out, shape=(n * num, n * num)) if format is not None else out + ((n * num, n * num),)
+
+
+# sparse.py:386-503: a single-entry cache of one factorisation, keyed by a session id.  The reference keeps a scipy
+# SuperLU object in a process-global dict on the host; here the entry is the matrix and the DEVICE workspace that
+# holds its factor / coarse inverse (the names keep the reference's `_cpu` suffix so call sites import unchanged).
+_SPLU_CACHE = {"factorization": None, "session_id": 0}
+
+
+def splu_clear():
+    _SPLU_CACHE["session_id"] = 0
+    _SPLU_CACHE["factorization"] = None
+
+
+def splu_cpu(A: CSC, session_id=None, **opts):
+    """sparse.py:394-445: register A for repeated solves; the factorisation happens in the first
+    `splu_solve_cpu` and stays in a device workspace."""
+    sid = 0 if session_id is None else int(session_id)
+    _SPLU_CACHE["factorization"] = {"A": A, "ws": ops.Workspace(), "factored": False, "opts": {**_DEFAULT_OPTS, **opts}}
+    _SPLU_CACHE["session_id"] = sid
+    return sid
+
+
+def splu_solve_cpu(session_id, b):
+    """sparse.py:448-503: solve with the cached factorisation; a session mismatch or an empty cache raises."""
+    sid = int(session_id)
+    if _SPLU_CACHE["session_id"] != sid:
+        raise ValueError(f"Session mismatch: expected {sid}, but cache has {_SPLU_CACHE['session_id']}. "
+                         "Make sure to call splu_cpu before splu_solve_cpu in the same session.")
+    f = _SPLU_CACHE["factorization"]
+    if f is None:
+        raise ValueError("No factorization found in cache. Call splu_cpu first.")
+    A = f["A"]
+    x = ops.solve(A.structure, A.data.detach(), b.contiguous(), workspace=f["ws"], reuse_factor=f["factored"],
+                  nan_on_failure=True, **f["opts"])
+    f["factored"] = True
+    return x

@@ -19,12 +19,95 @@ from .. import _lib as L
 __all__ = [
     "Graph",
     "GraphSparse",
+    "Mesh",
+    "MeshSparse",
     "EquilibriumStructure",
     "EquilibriumStructureSparse",
     "EquilibriumMeshStructure",
     "EquilibriumMeshStructureSparse",
     "IndexArray",
+    "adjacency_matrix",
+    "connectivity_matrix",
+    "face_matrix",
+    "mesh_edges_faces",
+    "mesh_connectivity_edges_faces",
 ]
+
+
+# ==========================================================================
+# Helper functions (structures/graphs.py:176-250, structures/meshes.py:301-399)
+# ==========================================================================
+def connectivity_matrix(edges, num_nodes=None):
+    """Signed edge-node incidence matrix as scipy CSC (graphs.py:176-211): -1 at the tail, +1 at the head."""
+    import scipy.sparse as sp
+
+    ei = np.asarray(edges)
+    m = len(ei)
+    data = np.concatenate((-np.ones(m), np.ones(m)))
+    rows = np.concatenate((np.arange(m), np.arange(m)))
+    cols = np.concatenate((ei[:, 0], ei[:, 1]))
+    n = num_nodes if num_nodes is not None else int(np.max(ei)) + 1
+    return sp.coo_matrix((data, (rows, cols)), shape=(m, n)).tocsc()
+
+
+def adjacency_matrix(edges, num_nodes=None):
+    """Symmetric node-node adjacency as scipy CSC (graphs.py:214-250): a one wherever two nodes share an edge."""
+    import scipy.sparse as sp
+
+    ei = np.asarray(edges)
+    n = num_nodes if num_nodes is not None else int(np.max(np.ravel(ei))) + 1
+    rows = np.concatenate((ei[:, 0], ei[:, 1]))
+    cols = np.concatenate((ei[:, 1], ei[:, 0]))
+    return sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(n, n)).tocsc()
+
+
+def face_matrix(face_vertices, normalize=True):
+    """Face-vertex incidence as scipy CSC, -1 padding ignored (meshes.py:361-399); rows sum to one when normalised."""
+    import scipy.sparse as sp
+
+    faces = np.asarray(face_vertices)
+    mask = faces >= 0
+    counts = mask.sum(axis=1)
+    rows = np.repeat(np.arange(faces.shape[0]), counts)
+    data = np.repeat(1.0 / counts, counts) if normalize else np.ones(rows.size)
+    return sp.coo_matrix((data, (rows, faces[mask]))).tocsc()
+
+
+def mesh_edges_faces(mesh):
+    """Face indices incident to each edge of a COMPAS-style mesh (meshes.py:301-331): anything with `faces()`,
+    `edges()` and `edge_faces((u, v))`."""
+    face_index = {fkey: idx for idx, fkey in enumerate(mesh.faces())}
+    out = []
+    for u, v in mesh.edges():
+        found = tuple(face_index[f] for f in mesh.edge_faces((u, v)) if f is not None)
+        assert len(found) <= 2
+        out.append(found)
+    return out
+
+
+def mesh_connectivity_edges_faces(mesh):
+    """Dense edge-face incidence of a COMPAS-style mesh (meshes.py:334-358)."""
+    ef = mesh_edges_faces(mesh)
+    C_ = np.zeros((len(ef), mesh.number_of_faces()))
+    for e, fs in enumerate(ef):
+        C_[e, list(fs)] = 1.0
+    return C_
+
+
+class _TaggedArray(np.ndarray):
+    """A dense connectivity matrix that remembers its structure (see `_tag`)."""
+    _fdm_structure = None
+
+
+def _tag(matrix, structure):
+    """`structure.connectivity` is what the reference's model methods take (models.py:99-193: `connectivity @ xyz`);
+    the kernels need the structure's plan instead, so the matrix carries a weak reference to its owner."""
+    import weakref
+
+    if isinstance(matrix, np.ndarray):
+        matrix = matrix.view(_TaggedArray)
+    matrix._fdm_structure = weakref.ref(structure)
+    return matrix
 
 
 class IndexArray(NamedTuple):
@@ -67,6 +150,27 @@ class Graph:
     def edge_index(self):
         return {(int(u), int(v)): i for i, (u, v) in enumerate(self.edges)}
 
+    # The reference stores these two as arrays built in __init__ (graphs.py:54-55, 99-116); here they are built on
+    # first access and cached: the kernels never read them (connectivity is implicit in the plan's edge lists), and
+    # the DENSE flavour is E x N doubles -- 26 GB at 200x200 -- so nothing pays for it unless it asks.
+    @property
+    def connectivity(self):
+        if getattr(self, "_connectivity", None) is None:
+            self._connectivity = _tag(self._connectivity_matrix(), self)
+        return self._connectivity
+
+    @property
+    def adjacency(self):
+        if getattr(self, "_adjacency", None) is None:
+            self._adjacency = self._adjacency_matrix()
+        return self._adjacency
+
+    def _connectivity_matrix(self):
+        return connectivity_matrix(self.edges_indexed, self.num_nodes).toarray()
+
+    def _adjacency_matrix(self):
+        return adjacency_matrix(self.edges_indexed, self.num_nodes).toarray()
+
     def _edges_indexed(self):
         # vectorised equivalent of the per-edge dictionary lookup in graphs.py:86-97
         if np.unique(self.nodes).size != self.nodes.size:
@@ -85,15 +189,16 @@ class GraphSparse(Graph):
 
     @property
     def connectivity_scipy(self):
-        """Signed incidence matrix as scipy CSC (graphs.py:176-211); built on demand, host only."""
-        import scipy.sparse as sp
+        """Signed incidence matrix as scipy CSC (graphs.py:140-158, 176-211); rebuilt on every access like the
+        reference's, host only."""
+        return connectivity_matrix(self.edges_indexed, self.num_nodes)
 
-        m = self.num_edges
-        ei = self.edges_indexed
-        data = np.concatenate((-np.ones(m), np.ones(m)))
-        rows = np.concatenate((np.arange(m), np.arange(m)))
-        cols = np.concatenate((ei[:, 0], ei[:, 1]))
-        return sp.coo_matrix((data, (rows, cols)), shape=(m, self.num_nodes)).tocsc()
+    def _connectivity_matrix(self):
+        """Sparse flavour (graphs.py:134-138): scipy CSC where the reference holds a BCOO of the same matrix."""
+        return self.connectivity_scipy
+
+    def _adjacency_matrix(self):
+        return adjacency_matrix(self.edges_indexed, self.num_nodes)
 
 
 class EquilibriumStructure(Graph):
@@ -163,6 +268,28 @@ class EquilibriumStructure(Graph):
         return self._size(L.SIZE_FREE)
 
     @property
+    def connectivity_free(self):
+        """C[:, indices_free] (structures.py:46, 190-194 dense; :236-240 sparse), built on first access."""
+        if getattr(self, "_connectivity_free", None) is None:
+            self._connectivity_free = self.connectivity[:, self.indices_free]
+        return self._connectivity_free
+
+    @property
+    def connectivity_fixed(self):
+        """C[:, indices_fixed] (structures.py:47, 242-246)."""
+        if getattr(self, "_connectivity_fixed", None) is None:
+            self._connectivity_fixed = self.connectivity[:, self.indices_fixed]
+        return self._connectivity_fixed
+
+    @classmethod
+    def from_network(cls, network, **kw):
+        """structures.py:71-112 for any COMPAS-style network: `nodes()`, `edges()`, `is_node_support(node)`."""
+        nodes = np.array(list(network.nodes()), dtype=np.int64)
+        edges = np.array([tuple(e) for e in network.edges()], dtype=np.int64)
+        supports = np.array([1 if network.is_node_support(n) else 0 for n in nodes], dtype=np.int64)
+        return cls(nodes, edges, supports, **kw)
+
+    @property
     def support_index(self):
         return {int(k): i for i, k in enumerate(self.nodes_fixed)}
 
@@ -219,29 +346,33 @@ class EquilibriumStructureSparse(EquilibriumStructure, GraphSparse):
         return self._get(L.ARR_PART_OF_ROW, np.int32, self.num_free)
 
 
-class EquilibriumMeshStructureSparse(EquilibriumStructureSparse):
+class Mesh(Graph):
     """
-    Mesh flavour (structures/structures.py:358-505, structures/meshes.py:29-293): the graph structure plus
-    faces, for tributary area loads.  `faces` is (F, maxdeg) of vertex KEYS padded with -1.
-
-    Attributes named as in the reference: `vertices`, `faces`, `faces_indexed`, `edges_faces_indexed`
-    (first two incident faces of every edge over both windings, padded -1, meshes.py:146-204),
-    `connectivity_faces_vertices` (row-normalised face-vertex matrix, meshes.py:361-399), `face_keys`,
-    `num_faces`.  `faces_edges` and `node_faces` are the transposed adjacencies the reverse kernels need.
+    A graph with faces (structures/meshes.py:29-259).  `faces` is (F, maxdeg) of vertex KEYS padded with -1;
+    edges are derived from the faces when not given.  Attributes as in the reference: `vertices`, `faces`,
+    `faces_indexed`, `edges_faces_indexed` (first two incident faces of every edge over both windings, padded
+    -1, meshes.py:146-204), `connectivity_faces_vertices` (row-normalised face-vertex matrix, the centroid
+    operator, meshes.py:247-259), `connectivity_edges_faces` (meshes.py:135-144), `face_keys`.
     """
 
-    def __init__(self, vertices, faces, edges, supports, face_keys=None, device=0, **kwargs):
-        super().__init__(nodes=vertices, edges=edges, supports=supports, device=device, **kwargs)
-        self.vertices = self.nodes
-        self.faces = np.asarray(faces, dtype=np.int64)
-        assert self.faces.ndim == 2 and self.faces.shape[1] > 2, "The mesh faces must have at least 3 vertices each"
-        self.face_keys = np.arange(self.faces.shape[0]) if face_keys is None else np.asarray(face_keys, dtype=np.int64)
+    def __init__(self, vertices, faces, edges=None, face_keys=None, **kwargs):
+        faces = np.asarray(faces, dtype=np.int64)
+        assert faces.ndim == 2 and faces.shape[1] > 2, "Mesh faces must connect at least 3 vertices"
+        if edges is None:
+            edges = self._edges_from_faces(faces)
+        kwargs.pop("nodes", None)
+        self.vertices = np.asarray(vertices, dtype=np.int64)
+        self.faces = faces
+        self.face_keys = np.arange(len(faces)) if face_keys is None else np.asarray(face_keys, dtype=np.int64)
+        super().__init__(nodes=self.vertices, edges=edges, **kwargs)
         vi = self.node_index
         self.faces_indexed = np.array([[vi[int(v)] if v >= 0 else int(v) for v in face] for face in self.faces],
                                       dtype=np.int64)
         self.edges_faces_indexed = self._edges_faces_indexed()
-        self.faces_edges, self.node_faces_ptr, self.node_faces = self._transposed_adjacency()
-        self._dev = None
+
+    @property
+    def num_vertices(self):
+        return int(self.vertices.size)
 
     @property
     def num_faces(self):
@@ -252,26 +383,103 @@ class EquilibriumMeshStructureSparse(EquilibriumStructureSparse):
         return self.node_index
 
     @property
+    def face_index(self):
+        return {int(f): i for i, f in enumerate(self.face_keys)}
+
+    @property
     def connectivity_faces_vertices(self):
+        return face_matrix(self.faces_indexed, normalize=True).toarray()
+
+    @property
+    def connectivity_edges_faces(self):
+        return self._connectivity_edges_faces_scipy().toarray()
+
+    def _connectivity_edges_faces_scipy(self):
         import scipy.sparse as sp
 
-        mask = self.faces_indexed >= 0
-        counts = mask.sum(axis=1)
-        rows = np.repeat(np.arange(self.num_faces), counts)
-        return sp.coo_matrix((np.repeat(1.0 / counts, counts), (rows, self.faces_indexed[mask])),
-                             shape=(self.num_faces, self.num_nodes)).tocsc()
+        ef = self.edges_faces_indexed
+        mask = ef >= 0
+        rows = np.repeat(np.arange(self.num_edges), mask.sum(axis=1))
+        return sp.coo_matrix((np.ones(rows.size), (rows, ef[mask])), shape=(self.num_edges, self.num_faces)).tocsc()
 
-    def _edges_faces_indexed(self):
+    def _edges_faces(self):
+        """Face indices incident to each edge over both windings (meshes.py:162-204)."""
         half = {}
         for f, face in enumerate(self.faces_indexed):
             clean = [int(v) for v in face if v >= 0]
             for u, v in zip(clean, clean[1:] + clean[:1]):
                 half.setdefault((u, v), []).append(f)
-        out = np.full((self.num_edges, 2), -1, dtype=np.int64)
-        for e, (u, v) in enumerate(self.edges_indexed):
+        out = []
+        for u, v in self.edges_indexed:
             fs = half.get((int(u), int(v)), []) + half.get((int(v), int(u)), [])
+            if len(fs) > 2:
+                print(f"Warning: Edge {(int(u), int(v))} is non-manifold, it's shared by ({len(fs)}) faces. "
+                      "This might lead to unexpected behavior in e.g. in area load calculations.")
+            out.append(tuple(fs))
+        return tuple(out)
+
+    def _edges_faces_indexed(self):
+        out = np.full((self.num_edges, 2), -1, dtype=np.int64)
+        for e, fs in enumerate(self._edges_faces()):
             out[e, :len(fs[:2])] = fs[:2]
         return out
+
+    @staticmethod
+    def _edges_from_faces(faces):
+        """Unique undirected edges in order of first appearance around the faces (meshes.py:207-245)."""
+        edges, seen = [], set()
+        for face in np.asarray(faces):
+            loop = [int(v) for v in face] + [int(face[0])]
+            for u, v in zip(loop, loop[1:]):
+                if (u, v) in seen or (v, u) in seen:
+                    continue
+                seen.add((u, v))
+                edges.append((u, v))
+        return np.asarray(edges, dtype=np.int64)
+
+
+class MeshSparse(Mesh, GraphSparse):
+    """Sparse flavour (meshes.py:261-293): the two incidence matrices as scipy CSC (the reference holds BCOO)."""
+
+    @property
+    def connectivity_faces_vertices(self):
+        return face_matrix(self.faces_indexed, normalize=True)
+
+    @property
+    def connectivity_edges_faces(self):
+        return self._connectivity_edges_faces_scipy()
+
+
+class _MeshStructureMixin:
+    """What both mesh structures add to their graph structure (structures.py:358-505): the classmethod
+    `from_mesh`, the vertex aliases, and the transposed adjacencies the reverse kernels of the face loads read."""
+
+    def _init_mesh_tables(self):
+        self.faces_edges, self.node_faces_ptr, self.node_faces = self._transposed_adjacency()
+        self._dev = None
+
+    @classmethod
+    def from_mesh(cls, mesh, **kw):
+        """structures.py:394-452 for any COMPAS-style mesh: `vertices()`, `edges()`, `faces()`,
+        `face_vertices(fkey)`, `is_vertex_support(vertex)`; faces padded with -1 to a common length."""
+        vertices = list(mesh.vertices())
+        edges = [tuple(e) for e in mesh.edges()]
+        supports = [1 if mesh.is_vertex_support(v) else 0 for v in vertices]
+        face_keys = np.asarray(list(mesh.faces()), dtype=np.int64)
+        faces = [list(mesh.face_vertices(f)) for f in face_keys]
+        deg = max(len(f) for f in faces)
+        assert deg > 2, "The mesh faces must have at least 3 vertices each"
+        faces = np.asarray([f + [-1] * (deg - len(f)) for f in faces], dtype=np.int64)
+        return cls(np.asarray(vertices, dtype=np.int64), faces, edges=np.asarray(edges, dtype=np.int64),
+                   supports=np.asarray(supports, dtype=np.int64), face_keys=face_keys, **kw)
+
+    @property
+    def vertices_free(self):
+        return self.vertices[self.indices_free]
+
+    @property
+    def vertices_fixed(self):
+        return self.vertices[self.indices_fixed]
 
     def _transposed_adjacency(self):
         eidx = {}
@@ -306,4 +514,20 @@ class EquilibriumMeshStructureSparse(EquilibriumStructureSparse):
         return self._dev
 
 
-EquilibriumMeshStructure = EquilibriumMeshStructureSparse
+class EquilibriumMeshStructure(_MeshStructureMixin, EquilibriumStructure, Mesh):
+    """Mesh flavour of the structure (structures.py:358-476): vertices play the role of nodes, faces carry the
+    tributary area loads."""
+
+    def __init__(self, vertices, faces, edges, supports, face_keys=None, device=0, **kwargs):
+        super().__init__(nodes=vertices, edges=edges, supports=supports, device=device, vertices=vertices, faces=faces,
+                         face_keys=face_keys, **kwargs)
+        self._init_mesh_tables()
+
+
+class EquilibriumMeshStructureSparse(_MeshStructureMixin, EquilibriumStructureSparse, MeshSparse):
+    """Sparse mesh structure (structures.py:479-505): EquilibriumStructureSparse + MeshSparse."""
+
+    def __init__(self, vertices, faces, edges, supports, face_keys=None, device=0, **kwargs):
+        super().__init__(nodes=vertices, edges=edges, supports=supports, device=device, vertices=vertices, faces=faces,
+                         face_keys=face_keys, **kwargs)
+        self._init_mesh_tables()

@@ -166,15 +166,19 @@ class _Program:
             gouter.append(term.alpha)
         self.num_terms, self.num_groups = len(kind), len(gfinal)
 
-        def dev(a, dt):
-            return torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device=device)
-
-        self.arrays = [dev(kind, np.int32), dev(index, np.int32), dev(err, np.int32), dev(weight, np.float64),
-                       dev(np.asarray(target).reshape(-1, 6), np.float64), dev(gptr, np.int32), dev(gfinal, np.int32),
-                       dev(ginner, np.float64), dev(gouter, np.float64), dev(agg_ptr, np.int32),
-                       dev(agg_index if agg_index else [0], np.int32)]
-        ptr = [C.c_void_p(a.data_ptr()) for a in self.arrays]
-        self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), n_agg, *ptr)
+        host = [(kind, np.int32), (index, np.int32), (err, np.int32), (weight, np.float64),
+                (np.asarray(target).reshape(-1, 6), np.float64), (gptr, np.int32), (gfinal, np.int32),
+                (ginner, np.float64), (gouter, np.float64), (agg_ptr, np.int32),
+                (agg_index if agg_index else [0], np.int32)]
+        # the same tables on the host (fdm_fa_set_goal_program copies them to the device itself)
+        self.host_arrays = [np.ascontiguousarray(a, dtype=dt) for a, dt in host]
+        self.host_struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), n_agg,
+                                         *[C.c_void_p(a.ctypes.data) for a in self.host_arrays])
+        self.arrays, self.struct = None, None
+        if device is not None:
+            self.arrays = [torch.as_tensor(a, device=device) for a in self.host_arrays]
+            ptr = [C.c_void_p(a.data_ptr()) for a in self.arrays]
+            self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), n_agg, *ptr)
 
 
 class _GoalsLoss(torch.autograd.Function):

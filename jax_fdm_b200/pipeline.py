@@ -221,3 +221,128 @@ class ChunkedForwardAdjoint:
     @property
     def launches_per_step(self):
         return sum(p.launches_per_step for p in self.parts)
+
+
+class _DevView:
+    """A raw device pointer as a `__cuda_array_interface__` object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class NativeForwardAdjoint:
+    """
+    The same forward + adjoint pass as `ChunkedForwardAdjoint`, owned by the library (`fdm_fa_*`,
+    include/fdm_b200.h, csrc/pipeline.cu): device buffers, chunk streams, events and CUDA graphs live in C++,
+    so a step costs Python ONE ctypes call -- `step()` on device-resident q, `__call__` end to end (host q in,
+    host loss and q_bar out; the pinned staging comes from fdm_host_alloc).  Loss: the quadratic benchmark loss
+    by default, or any `jax_fdm_b200.losses.Loss` of goals (`set_loss`), compiled to a goal program.
+    """
+    ARRAYS = {"q": (L.FA_Q, "E"), "x": (L.FA_X_FREE, "Nf3"), "xyz": (L.FA_XYZ, "N3"), "loss": (L.FA_LOSS, ""),
+              "q_bar": (L.FA_Q_BAR, "E"), "loads_bar": (L.FA_LOADS_BAR, "N3"), "xs_bar": (L.FA_XYZ_FIXED_BAR, "Ns3"),
+              "info_f": (L.FA_INFO_FORWARD, "I"), "info_a": (L.FA_INFO_ADJOINT, "I"), "lengths": (L.FA_LENGTHS, "E"),
+              "forces": (L.FA_FORCES, "E"), "residuals": (L.FA_RESIDUALS, "N3"), "vectors": (L.FA_VECTORS, "E3")}
+
+    def __init__(self, structure, batch, chunks=1, solver="auto", with_state=True, use_graph=True, tol=1e-12,
+                 max_iters=0, device=None):
+        s = self.s = structure
+        self.B = int(batch)
+        self.lib = L.lib()
+        self.dev = torch.device("cuda", s.device if device is None else device)
+        opts = L.FaOpts(int(chunks), int(bool(with_state)), L.SOLVERS[solver], int(bool(use_graph)), int(max_iters), float(tol))
+        self.handle = C.c_void_p()
+        L.check(self.lib.fdm_fa_create(s.plan, self.B, C.byref(opts), C.byref(self.handle)))
+        E = s.num_edges
+        self._pinned = []
+        self.h_q = self._host((self.B, E))
+        self.h_loss = self._host((self.B,))
+        self.h_q_bar = self._host((self.B, E))
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self._loss_program = None
+
+    def _host(self, shape):
+        n = int(np.prod(shape))
+        ptr = self.lib.fdm_host_alloc(n * 8)
+        if not ptr:
+            raise L.FdmError(-2, self.lib.fdm_last_error().decode())
+        self._pinned.append(ptr)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,)).reshape(shape)
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.fdm_fa_destroy(self.handle)
+            self.handle = C.c_void_p()
+        for ptr in getattr(self, "_pinned", []):
+            self.lib.fdm_host_free(ptr)
+        self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_inputs(self, q, xyz_fixed, loads, x0=None):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        q = f(q).reshape(self.B, -1)
+        xs, p = f(xyz_fixed), f(loads)
+        x0 = None if x0 is None else f(x0)
+        L.check(self.lib.fdm_fa_set_constants(self.handle, xs.ctypes.data, p.ctypes.data,
+                                              None if x0 is None else x0.ctypes.data))
+        self.h_q[...] = q
+        L.check(self.lib.fdm_fa_set_q(self.handle, self.h_q.ctypes.data))
+
+    def set_loss(self, loss):
+        """A `losses.Loss` (error terms only; regularisers act on the parameters above the path)."""
+        prog = loss.program(self.s, None)
+        self._loss_program = prog                           # keeps the host tables alive during the call
+        L.check(self.lib.fdm_fa_set_goal_program(self.handle, C.byref(prog.host_struct)))
+
+    def step(self, stream=None):
+        st = self.stream if stream is None else stream
+        L.check(self.lib.fdm_fa_step_device(self.handle, C.c_void_p(st.cuda_stream)))
+
+    def enqueue(self, q_host=None, want_q_bar=True):
+        src = self.h_q if q_host is None else q_host
+        L.check(self.lib.fdm_fa_enqueue_host(self.handle, src.ctypes.data, self.h_loss.ctypes.data,
+                                             self.h_q_bar.ctypes.data if want_q_bar else None))
+
+    def synchronize(self):
+        L.check(self.lib.fdm_fa_wait(self.handle))
+
+    def enqueue_copies_only(self):
+        """Measurement: the host <-> device copies of `enqueue` without the kernels."""
+        L.check(self.lib.fdm_fa_enqueue_copies_only(self.handle, self.h_q.ctypes.data, self.h_loss.ctypes.data,
+                                                    self.h_q_bar.ctypes.data))
+
+    def __call__(self, q_host=None):
+        src = self.h_q if q_host is None else q_host
+        L.check(self.lib.fdm_fa_run_host(self.handle, src.ctypes.data, self.h_loss.ctypes.data, self.h_q_bar.ctypes.data))
+        return self.h_loss, self.h_q_bar
+
+    def array(self, name):
+        """A device array of the object as a torch tensor (a view; valid while the object lives)."""
+        which, kind = self.ARRAYS[name]
+        ptr, per = C.c_void_p(), C.c_int64()
+        L.check(self.lib.fdm_fa_device_array(self.handle, which, C.byref(ptr), C.byref(per)))
+        s = self.s
+        tail = {"E": (s.num_edges,), "Nf3": (s.num_free, 3), "N3": (s.num_nodes, 3), "Ns3": (s.num_supports, 3),
+                "I": (L.INFO_STRIDE,), "E3": (s.num_edges, 3), "": ()}[kind]
+        return torch.as_tensor(_DevView(ptr.value, (self.B,) + tail), device=self.dev)
+
+    @property
+    def launches_per_step(self):
+        return int(self.lib.fdm_fa_info(self.handle, L.FA_INFO_LAUNCHES))
+
+    @property
+    def chunks(self):
+        return int(self.lib.fdm_fa_info(self.handle, L.FA_INFO_CHUNKS))
+
+    @property
+    def h2d_bytes(self):
+        return self.h_q.size * 8
+
+    @property
+    def d2h_bytes(self):
+        return (self.h_loss.size + self.h_q_bar.size) * 8

@@ -3,6 +3,7 @@
 
   python profiles/summarize.py launches gpurun_out/launches.csv        > profiles/rNN_launches.txt
   python profiles/summarize.py raw      gpurun_out/prof.ncu-rep        > profiles/rNN_kernel.txt
+  python profiles/summarize.py counters gpurun_out/prof.ncu-rep profiles/rNN_kernel.txt > profiles/ncu_counters.json
 """
 import collections
 import csv
@@ -53,9 +54,49 @@ def raw(path):
                     print(f"  {h:95s} {d[i]:>18s} {units[i]}")
 
 
+def counters(path, source):
+    """JSON for profiles/ncu_counters.json: per kernel instance (template arguments kept) the figures bench.py
+    prints beside its own timings -- DRAM bytes per launch and the pipe / occupancy percentages."""
+    import json
+    import re
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0,
+             "nsecond": 1e-3, "msecond": 1e3}
+
+    def val(d, name):
+        i = col.get(name)
+        if i is None or d[i] == "":
+            return None
+        return float(d[i].replace(",", "")) * scale.get(units[i], 1.0)
+
+    res = {}
+    for d in data:
+        name = d[col["Kernel Name"]]
+        m = re.search(r"(\w+)<([^>]*)>", name)
+        key = f"{m.group(1)}<{m.group(2).replace(' ', '')}>" if m else re.sub(r"\(.*", "", name).split("::")[-1]
+        rd, wr = val(d, "dram__bytes_read.sum"), val(d, "dram__bytes_write.sum")
+        res[key] = {
+            "dram_bytes": None if rd is None else rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+            "duration_us": val(d, "gpu__time_duration.sum"),
+            "warps_active_pct": val(d, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "l1_data_pipe_pct": val(d, "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            "dmma_pipe_pct": val(d, "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"),
+            "fp64_pipe_pct": val(d, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+            "dram_pct": val(d, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "registers_per_thread": val(d, "launch__registers_per_thread"),
+            "grid": val(d, "launch__grid_size"), "source": source}
+    print(json.dumps(res, indent=1))
+
+
 def k_ok(h):
     return not any(x in h for x in (".max", ".min", "peak_sustained ", ".per_second Ghz", "_not_issued"))
 
 
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "counters":
+        counters(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else sys.argv[2])
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])

@@ -398,7 +398,7 @@ def run_reference(case, structures, states, models, dense_too):
     out["ref_diags_indices"] = dg.indices
     out["ref_diags_indptr"] = dg.indptr
     for nm, mat in (("cfree", s.connectivity_free.m), ("cfixed", s.connectivity_fixed.m),
-                    ("conn", s.connectivity.m)):
+                    ("conn", s.connectivity.m), ("adj", s.adjacency.m)):
         mat = sp.csc_matrix(mat)
         out[f"ref_{nm}_data"] = mat.data
         out[f"ref_{nm}_indices"] = mat.indices

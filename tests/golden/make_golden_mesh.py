@@ -73,6 +73,9 @@ def main():
         cfv = sp.csr_matrix(s.connectivity_faces_vertices.m)
         cfv.sort_indices()
         out[f"{tag}_ref_cfv_data"], out[f"{tag}_ref_cfv_indices"], out[f"{tag}_ref_cfv_indptr"] = cfv.data, cfv.indices, cfv.indptr
+        cef = sp.csr_matrix(s.connectivity_edges_faces.m)
+        cef.sort_indices()
+        out[f"{tag}_ref_cef_data"], out[f"{tag}_ref_cef_indices"], out[f"{tag}_ref_cef_indptr"] = cef.data, cef.indices, cef.indptr
         qj, xs, loads = G.jarr(q), G.jarr(prob.xyz_fixed), G.jarr(prob.loads)
         for local in (False, True):
             model = models.EquilibriumModelSparse(tmax=100, eta=1e-10, is_load_local=local, itersolve_fn=fp.solver_forward,

@@ -121,7 +121,7 @@ def lib():
     L.fdm_face_loads.restype = C.c_int
     L.fdm_face_loads_vjp.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
     L.fdm_face_loads_vjp.restype = C.c_int
-    L.fdm_goals_loss.argtypes = [vp, C.POINTER(GoalProgram), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.fdm_goals_loss.argtypes = [vp, C.POINTER(GoalProgram), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.fdm_goals_loss.restype = C.c_int
     L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.fdm_loss_sqdist.restype = C.c_int

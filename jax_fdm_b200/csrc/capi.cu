@@ -388,10 +388,11 @@ int fdm_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, int64
 }
 
 int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* xyz, const double* lengths,
-                   const double* forces, const double* residuals, double* loss, double* group_sums, double* xyz_bar,
-                   double* lengths_bar, double* forces_bar, double* residuals_bar, int64_t batch, void* stream) {
+                   const double* forces, const double* residuals, double* loss, double* group_sums,
+                   const double* loss_cot, double* xyz_bar, double* lengths_bar, double* forces_bar, double* residuals_bar,
+                   int64_t batch, void* stream) {
   if (!ready(p, "fdm_goals_loss")) return FDM_ERR_INVALID;
-  if (!g || !xyz || !lengths || !forces || !residuals || !loss || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
+  if (!g || !xyz || !lengths || !forces || !residuals || (!loss && !xyz_bar) || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
       (g->num_terms > 0 && (!g->kind || !g->index || !g->error || !g->weight || !g->target)) ||
       (g->num_groups > 0 && (!g->group_ptr || !g->group_final || !g->group_inner || !g->group_outer))) {
     fdm_set_error("fdm_goals_loss: bad arguments");
@@ -412,8 +413,8 @@ int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* x
   }
   return launch_goals_loss(p, g->num_terms, g->kind, g->index, g->error, g->weight, g->target, g->num_groups,
                            g->group_ptr, g->group_final, g->group_inner, g->group_outer, g->has_network_loadpath,
-                           g->agg_ptr, g->agg_index, xyz,
-                           lengths, forces, residuals, loss, group_sums, xyz_bar, lengths_bar, forces_bar, residuals_bar,
+                           g->agg_ptr, g->agg_index, g->num_aggregates, xyz,
+                           lengths, forces, residuals, loss, group_sums, loss_cot, xyz_bar, lengths_bar, forces_bar, residuals_bar,
                            batch, (cudaStream_t)stream);
 }
 

@@ -58,6 +58,8 @@ struct GoalArgs {
   const double *ginner, *gouter;                   // (G)
   const double *xyz, *lengths, *forces, *residuals;
   double *loss, *gsum;                             // (B), (B,G)
+  const double* loss_cot;                          // (B) upstream cotangent of the loss, or null (= 1)
+  int num_agg;                                     // aggregate goals in the program (0: their serial term scans are skipped)
   double *xyz_bar, *lengths_bar, *forces_bar, *residuals_bar;
   int need_loadpath;
 };
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
   // aggregate goals (goals/edge/length.py:49-75, force.py:49-75): p = var(v) / M over the term's edge set, v = lengths
   // (M = mean v) or forces (M = mean |v|); evaluated by the whole CTA, kept per aggregate slot for both passes
   __shared__ double s_aggp[kMaxAgg], s_aggmu[kMaxAgg], s_aggV[kMaxAgg], s_aggM[kMaxAgg];
-  if (A.agg_ptr) {
+  if (A.agg_ptr && A.num_agg > 0) {
     for (int t = 0; t < A.T; ++t) {
       const int k = A.kind[t];
       if (k < G_EDGES_LENGTH_EQUAL) continue;
@@ -273,10 +275,10 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
     loss += A.gouter[g] * (root ? sqrt(u) : u);
     if (threadIdx.x == 0) {
       if (A.gsum) A.gsum[b * A.G + g] = S;
-      if (g < 64) s_mult[g] = A.gouter[g] * A.ginner[g] * (root ? 0.5 / sqrt(u) : 1.0);   // d loss / d S_g
+      if (g < 64) s_mult[g] = (A.loss_cot ? A.loss_cot[b] : 1.0) * A.gouter[g] * A.ginner[g] * (root ? 0.5 / sqrt(u) : 1.0);   // loss_bar * d loss / d S_g
     }
   }
-  if (threadIdx.x == 0) A.loss[b] = loss;
+  if (threadIdx.x == 0 && A.loss) A.loss[b] = loss;
   if (!bwd) return;
   __syncthreads();
   // ---- pass 2: cotangents of the state
@@ -364,7 +366,9 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       }
     }
     __syncthreads();
-    // network load path terms of this group: all threads scatter over the edges
+    // aggregate and network load path terms of this group: all threads scatter over their element sets (the
+    // serial scan of the group's terms is skipped when the program has none of them)
+    if (A.num_agg == 0 && !A.need_loadpath) continue;
     for (int t = A.group_ptr[g]; t < A.group_ptr[g + 1]; ++t) {
       const int kk = A.kind[t];
       if (kk == G_NODES_COLINEAR) {
@@ -421,17 +425,17 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
 int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const int32_t* index, const int32_t* err,
                       const double* weight, const double* target, int n_groups, const int32_t* group_ptr,
                       const int32_t* gfinal, const double* ginner, const double* gouter, int need_loadpath,
-                      const int32_t* agg_ptr, const int32_t* agg_index,
+                      const int32_t* agg_ptr, const int32_t* agg_index, int num_agg,
                       const double* xyz, const double* lengths, const double* forces, const double* residuals,
-                      double* loss, double* gsum, double* xyz_bar, double* lengths_bar, double* forces_bar,
-                      double* residuals_bar, int64_t batch, cudaStream_t st) {
+                      double* loss, double* gsum, const double* loss_cot, double* xyz_bar, double* lengths_bar,
+                      double* forces_bar, double* residuals_bar, int64_t batch, cudaStream_t st) {
   GoalArgs A;
   A.T = n_terms; A.G = n_groups; A.N = (int)p->N; A.E = (int)p->E;
   A.kind = kind; A.index = index; A.err = err; A.group_ptr = group_ptr; A.edge_nodes = p->d.edge_nodes;
-  A.agg_ptr = agg_ptr; A.agg_index = agg_index;
+  A.agg_ptr = agg_ptr; A.agg_index = agg_index; A.num_agg = num_agg;
   A.weight = weight; A.target = target; A.gfinal = gfinal; A.ginner = ginner; A.gouter = gouter;
   A.xyz = xyz; A.lengths = lengths; A.forces = forces; A.residuals = residuals;
-  A.loss = loss; A.gsum = gsum;
+  A.loss = loss; A.gsum = gsum; A.loss_cot = loss_cot;
   A.xyz_bar = xyz_bar; A.lengths_bar = lengths_bar; A.forces_bar = forces_bar; A.residuals_bar = residuals_bar;
   A.need_loadpath = need_loadpath;
   goals_loss_kernel<<<(unsigned)batch, kThreads, 0, st>>>(A);

@@ -62,10 +62,10 @@ int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, in
 int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const int32_t* index, const int32_t* err,
                       const double* weight, const double* target, int n_groups, const int32_t* group_ptr,
                       const int32_t* gfinal, const double* ginner, const double* gouter, int need_loadpath,
-                      const int32_t* agg_ptr, const int32_t* agg_index,
+                      const int32_t* agg_ptr, const int32_t* agg_index, int num_agg,
                       const double* xyz, const double* lengths, const double* forces, const double* residuals,
-                      double* loss, double* gsum, double* xyz_bar, double* lengths_bar, double* forces_bar,
-                      double* residuals_bar, int64_t batch, cudaStream_t st);
+                      double* loss, double* gsum, const double* loss_cot, double* xyz_bar, double* lengths_bar,
+                      double* forces_bar, double* residuals_bar, int64_t batch, cudaStream_t st);
 int launch_kbar_pattern(const fdm_plan* p, const double* a, const double* bvec, double* out, double sign, int64_t batch,
                         cudaStream_t st);
 int launch_stiffness_vjp(const fdm_plan* p, const double* Kbar, double* q_bar, int64_t batch, cudaStream_t st);

@@ -120,7 +120,7 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
     // q_bar, loads_bar and the cotangent of xyz), the split of xyz_bar into free / fixed rows, the adjoint solve
     // and the implicit terms accumulated on top
     rc = fdm_goals_loss(p, &f->prog, f->xyz.at(o), f->lengths.at(o), f->forces.at(o), f->residuals.at(o), f->loss.at(o),
-                        nullptr, f->xyz_cot.at(o), f->len_cot.at(o), f->for_cot.at(o), f->res_cot.at(o), B, st);
+                        nullptr, nullptr, f->xyz_cot.at(o), f->len_cot.at(o), f->for_cot.at(o), f->res_cot.at(o), B, st);
     if (rc != FDM_OK) return rc;
     rc = fdm_state_vjp(p, f->q.at(o), f->xyz.at(o), f->xyz_cot.at(o), f->res_cot.at(o), f->len_cot.at(o), f->for_cot.at(o),
                        nullptr, nullptr, f->q_bar.at(o), f->xyz_bar.at(o), f->loads_bar.at(o), B, E, st);

@@ -181,32 +181,91 @@ class _Program:
             self.struct = L.GoalProgram(self.num_terms, self.num_groups, int(6 in kind), n_agg, *ptr)
 
 
+def _goals_call(structure, program, xyz, lengths, forces, residuals, loss, loss_cot, bars):
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    st = C.c_void_p(torch.cuda.current_stream(xyz.device).cuda_stream)
+    B = xyz.shape[0] if xyz.dim() == 3 else 1
+    L.check(L.lib().fdm_goals_loss(structure.plan, C.byref(program.struct), P(xyz), P(lengths), P(forces), P(residuals),
+                                   P(loss), None, P(loss_cot), *[P(t) for t in bars], B, st))
+
+
 class _GoalsLoss(torch.autograd.Function):
-    """One launch: loss per design and d loss / d (xyz, lengths, forces, residuals)."""
+    """Forward: one launch, the loss per design.  Backward: one launch of the same kernel in its reverse mode --
+    d loss / d (xyz, lengths, forces, residuals) already scaled by the upstream cotangent (no elementwise passes)."""
 
     @staticmethod
     def forward(ctx, xyz, lengths, forces, residuals, structure, program):
-        s = structure
-        N, E = s.num_nodes, s.num_edges
         batched = xyz.dim() == 3
         B = xyz.shape[0] if batched else 1
         xyz, lengths, forces, residuals = (t.contiguous() for t in (xyz, lengths, forces, residuals))
-        dev = xyz.device
-        loss = torch.empty((B,), dtype=F64, device=dev)
-        bars = [torch.empty_like(xyz), torch.empty_like(lengths), torch.empty_like(forces), torch.empty_like(residuals)]
-        P = lambda t: C.c_void_p(t.data_ptr())
-        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        L.check(L.lib().fdm_goals_loss(s.plan, C.byref(program.struct), P(xyz), P(lengths), P(forces), P(residuals),
-                                       P(loss), None, *[P(t) for t in bars], B, st))
-        ctx.save_for_backward(*bars)
-        ctx.batched = batched
+        loss = torch.empty((B,), dtype=F64, device=xyz.device)
+        _goals_call(structure, program, xyz, lengths, forces, residuals, loss, None, [None] * 4)
+        ctx.save_for_backward(xyz, lengths, forces, residuals)
+        ctx.structure, ctx.program, ctx.batched = structure, program, batched
         return loss if batched else loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        bars = ctx.saved_tensors
-        g = g.reshape(-1, 1, 1) if ctx.batched else g
-        return (*[b * g for b in bars], None, None)
+        xyz, lengths, forces, residuals = ctx.saved_tensors
+        bars = [torch.empty_like(t) for t in (xyz, lengths, forces, residuals)]
+        _goals_call(ctx.structure, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
+        return (*bars, None, None)
+
+
+class _FusedValueAndGrad(torch.autograd.Function):
+    """
+    `Loss(params, model, structure)` for the linear model (tmax = 1, nodal loads) as ONE autograd node: forward =
+    solve from q -> positions -> state -> goal kernel; backward = goal kernel (reverse mode, scaled by the upstream
+    cotangent) -> state VJP -> split of xyz_bar -> adjoint solve with the stored factor -> gradient kernel
+    accumulating on the direct terms.  The same launches as the library's own pipeline (fdm_fa_*), with no autograd
+    bookkeeping or elementwise passes between them.
+    """
+
+    @staticmethod
+    def forward(ctx, q, xyz_fixed, loads, structure, program, solve_opts):
+        from ..equilibrium import ops
+        s = structure
+        ws = ops.Workspace()
+        x = K = None
+        opts = {k: v for k, v in solve_opts.items() if k != "fused_assembly"}
+        if solve_opts.get("fused_assembly", True) and opts.get("solver", "auto") in ("auto", "cholesky"):
+            x = ops.solve_from_q(s, q, xyz_fixed, loads, workspace=ws, nan_on_failure=True)
+            if x is not None:
+                opts["solver"] = "cholesky"
+        if x is None:
+            K, rhs = ops.assemble(s, q, xyz_fixed, loads)
+            x = ops.solve(s, K, rhs, workspace=ws, nan_on_failure=True, **opts)
+        xyz = ops.positions(s, x, xyz_fixed)
+        _, lengths, forces, residuals = ops.state(s, q, xyz, loads)
+        batched = xyz.dim() == 3
+        loss = torch.empty((xyz.shape[0] if batched else 1,), dtype=F64, device=xyz.device)
+        _goals_call(s, program, xyz, lengths, forces, residuals, loss, None, [None] * 4)
+        ctx.save_for_backward(q, xyz_fixed, loads, xyz, lengths, forces, residuals, K if K is not None else x.new_empty(0))
+        ctx.structure, ctx.program, ctx.opts, ctx.ws, ctx.batched = s, program, opts, ws, batched
+        return loss if batched else loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        from ..equilibrium import ops
+        from ..distributed import _batch_sum
+        q, xyz_fixed, loads, xyz, lengths, forces, residuals, K = ctx.saved_tensors
+        s = ctx.structure
+        bars = [torch.empty_like(t) for t in (xyz, lengths, forces, residuals)]
+        _goals_call(s, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
+        q_bar, xyz_bar, loads_bar = ops.state_vjp(s, q, xyz, xyz_cot=bars[0], residuals_cot=bars[3], lengths_cot=bars[1],
+                                                  forces_cot=bars[2])
+        gx, xs_bar = ops.positions_vjp(s, xyz_bar)
+        lam = ops.solve(s, K if K.numel() else None, gx, workspace=ctx.ws, reuse_factor=True, **ctx.opts)
+        ops.adjoint_grads(s, q, xyz, lam, q_bar=q_bar, loads_bar=loads_bar, xyz_fixed_bar=xs_bar)
+
+        def to_shape(grad, like):                          # a parameter shared by the batch takes the sum over designs
+            if grad.dim() == like.dim():
+                return grad
+            out = torch.empty(like.shape, dtype=F64, device=grad.device)
+            return _batch_sum(grad.reshape(grad.shape[0], -1), out.view(-1)).view(like.shape)
+        return (to_shape(q_bar, q) if ctx.needs_input_grad[0] else None,
+                to_shape(xs_bar, xyz_fixed) if ctx.needs_input_grad[1] else None,
+                to_shape(loads_bar, loads) if ctx.needs_input_grad[2] else None, None, None, None)
 
 
 class Loss:
@@ -240,8 +299,17 @@ class Loss:
         return _GoalsLoss.apply(eq_state.xyz, eq_state.lengths, eq_state.forces, eq_state.residuals, structure, prog)
 
     def __call__(self, params, model, structure):
-        eq_state = model(params, structure)
-        loss = self.errors_from_state(eq_state, structure)
+        load_state = params[2]
+        nodes_load = load_state.nodes if hasattr(load_state, "nodes") else load_state
+        shape_dependent = any(isinstance(t, torch.Tensor) and t.numel() > 1
+                              for t in (getattr(load_state, "edges", 0.0), getattr(load_state, "faces", 0.0)))
+        if getattr(model, "tmax", 1) == 1 and not shape_dependent and params[0].is_cuda and self.terms_error:
+            # the linear model: forward + loss (+ its whole reverse pass) as one node of this library's kernels
+            prog = self.program(structure, params[0].device)
+            loss = _FusedValueAndGrad.apply(params[0], params[1], nodes_load, structure, prog, model.solve_opts)
+        else:
+            eq_state = model(params, structure)
+            loss = self.errors_from_state(eq_state, structure)
         for reg in self.terms_regularization:
             loss = loss + reg(params)
         return loss

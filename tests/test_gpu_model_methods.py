@@ -130,7 +130,7 @@ def test_unrolled_differentiation_matches_the_implicit_adjoint(local):
         loss = 0.5 * ((st.xyz - T(prob.xyz0)) ** 2).sum() + 0.1 * (st.lengths ** 2).sum()
         loss.backward()
         assert model.last_solver_config["steps"] > 1
-        grads[implicit] = [N(t.grad) for t in (q, xs, p, w)] + [float(loss)]
+        grads[implicit] = [N(t.grad) for t in (q, xs, p, w)] + [float(loss.detach())]
     assert abs(grads[True][-1] - grads[False][-1]) <= 1e-12 * abs(grads[True][-1])
     for a, b, nm in zip(grads[True][:4], grads[False][:4], ("q", "xyz_fixed", "loads", "edges_load")):
         assert relerr(b, a) <= 1e-8, nm

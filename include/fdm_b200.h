@@ -102,7 +102,11 @@ enum {
   FDM_ARR_DIAGS_INDPTR = 7,      /* (Nf+1) int32  diags (BCSR Nf x E) structures.py:316-350 */
   FDM_ARR_DIAGS_INDICES = 8,     /* (dnnz) int32                                         */
   FDM_ARR_BAND_PERM = 9,         /* (Nf)   int32  free index -> band-ordered index       */
-  FDM_ARR_PART_OF_ROW = 10       /* (Nf)   int32  free index -> aggregate id             */
+  FDM_ARR_PART_OF_ROW = 10,      /* (Nf)   int32  free index -> aggregate id             */
+  /* tables of the two-sided factorisation (diagnostics / tests), half h = 0, 1 at +h: row -> free index (-1 =
+   * padding or the other half's row), first entry group of every 32-row block, and the (slot, K.data position)
+   * and (slot, edge id) entry lists; empty when the plan has no two-sided tables */
+  FDM_ARR_TW_IPERM = 11, FDM_ARR_TW_STAGE_PTR = 13, FDM_ARR_TW_STAGE_KENT = 15, FDM_ARR_TW_STAGE_EENT = 17
 };
 int64_t fdm_plan_get_array(const fdm_plan* plan, int which, void* h_out, int64_t capacity);
 

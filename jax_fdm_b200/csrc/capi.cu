@@ -27,6 +27,12 @@ void free_device(fdm_plan* p) {
                   d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent, d.band_row_diag, d.band_row_sup, d.band_row_node};
   for (void* q : ptrs)
     if (q) cudaFree(q);
+  for (int h = 0; h < 2; ++h) {
+    void* tw[] = {d.tw_iperm[h], d.tw_stage_ptr[h], d.tw_stage_kent[h], d.tw_stage_eent[h], d.tw_row_diag[h],
+                  d.tw_row_sup[h], d.tw_row_node[h]};
+    for (void* q : tw)
+      if (q) cudaFree(q);
+  }
   d = DeviceArrays();
 }
 
@@ -35,6 +41,7 @@ int build_host(fdm_plan* p, const int64_t* edges, int64_t E, int64_t N, const in
   int rc = fdm_build_topology(*p, edges, E, N, supports);
   if (rc != FDM_OK) return rc;
   fdm_build_band_order(*p);
+  fdm_build_twisted(*p);
   fdm_build_partition(*p, num_parts);
   return FDM_OK;
 }
@@ -127,10 +134,19 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->diags_indices, &q->d.diags_idx); },
         [](fdm_plan* q) { return upload(q->sup_mask, &q->d.sup_mask); },
     };
-    (void)d;
     for (auto f : steps) {
       rc = f(p);
       if (rc != FDM_OK) break;
+    }
+    for (int h = 0; h < 2 && rc == FDM_OK && p->tw[0].nblk > 0; ++h) {
+      const BandHalf& H = p->tw[h];
+      if (rc == FDM_OK) rc = upload(H.iperm, &d.tw_iperm[h]);
+      if (rc == FDM_OK) rc = upload(H.stage_ptr, &d.tw_stage_ptr[h]);
+      if (rc == FDM_OK) rc = upload(H.stage_kent, &d.tw_stage_kent[h]);
+      if (rc == FDM_OK) rc = upload(H.stage_eent, &d.tw_stage_eent[h]);
+      if (rc == FDM_OK) rc = upload(H.row_diag, &d.tw_row_diag[h]);
+      if (rc == FDM_OK) rc = upload(H.row_sup, &d.tw_row_sup[h]);
+      if (rc == FDM_OK) rc = upload(H.row_node, &d.tw_row_node[h]);
     }
   }
   if (rc != FDM_OK) {
@@ -185,6 +201,13 @@ int64_t fdm_plan_get_array(const fdm_plan* p, int which, void* h_out, int64_t ca
     case FDM_ARR_DIAGS_INDICES: return copy_out(p->diags_indices, h_out, capacity);
     case FDM_ARR_BAND_PERM: return copy_out(p->band_perm, h_out, capacity);
     case FDM_ARR_PART_OF_ROW: return copy_out(p->part_of_row, h_out, capacity);
+    case FDM_ARR_TW_IPERM: case FDM_ARR_TW_IPERM + 1: return copy_out(p->tw[which - FDM_ARR_TW_IPERM].iperm, h_out, capacity);
+    case FDM_ARR_TW_STAGE_PTR: case FDM_ARR_TW_STAGE_PTR + 1:
+      return copy_out(p->tw[which - FDM_ARR_TW_STAGE_PTR].stage_ptr, h_out, capacity);
+    case FDM_ARR_TW_STAGE_KENT: case FDM_ARR_TW_STAGE_KENT + 1:
+      return copy_out(p->tw[which - FDM_ARR_TW_STAGE_KENT].stage_kent, h_out, capacity);
+    case FDM_ARR_TW_STAGE_EENT: case FDM_ARR_TW_STAGE_EENT + 1:
+      return copy_out(p->tw[which - FDM_ARR_TW_STAGE_EENT].stage_eent, h_out, capacity);
   }
   fdm_set_error("fdm_plan_get_array: unknown array id");
   return FDM_ERR_INVALID;

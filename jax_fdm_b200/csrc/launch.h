@@ -31,6 +31,23 @@ inline int fdm_check_launch(const char* what) {
     }                                                                                          \
   } while (0)
 
+// In-kernel bounds checks of the -DFDM_DEBUG build (jax_fdm_b200.build.build(defines=("FDM_DEBUG",))): the pool
+// has no compute-sanitizer, so the index tables the kernels trust are checked where they are consumed; a failed
+// check prints file:line and the values, then traps (the launch fails with an error the C ABI reports).
+#ifdef FDM_DEBUG
+#include <cstdio>
+#define FDM_ASSERT(cond, fmt, ...)                                                                         \
+  do {                                                                                                     \
+    if (!(cond)) {                                                                                         \
+      printf("FDM_ASSERT %s:%d (block %d thread %d): " #cond " -- " fmt "\n", __FILE__, __LINE__,          \
+             (int)blockIdx.x, (int)threadIdx.x, ##__VA_ARGS__);                                            \
+      __trap();                                                                                            \
+    }                                                                                                      \
+  } while (0)
+#else
+#define FDM_ASSERT(cond, fmt, ...) ((void)0)
+#endif
+
 // kernels_basic.cu
 int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const double* loads,
                     double* Kdata, double* rhs, int64_t batch, int64_t qs, int64_t xss, int64_t ls,

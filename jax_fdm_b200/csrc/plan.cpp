@@ -385,6 +385,101 @@ void fdm_build_band_order(fdm_plan& p) {
   }
 }
 
+// Tables of one half of the two-sided factorisation (plan.h: BandHalf).  `vmap[R]` = band position of the half's
+// row R, or -1 for an identity padding row; rows in [excl_lo, excl_hi) have their mutual entries, diagonals and
+// right-hand sides left out (the other half owns them).  One trailing identity block is appended: the kernels
+// always stage one block ahead.
+static void build_half_tables(const fdm_plan& p, const std::vector<int32_t>& vmap, int32_t excl_lo, int32_t excl_hi,
+                              BandHalf& out) {
+  const int32_t n = (int32_t)p.Nf;
+  const int64_t rows = (int64_t)vmap.size() + 32;
+  std::vector<int32_t> inv(n, -1);
+  for (size_t R = 0; R < vmap.size(); ++R)
+    if (vmap[R] >= 0 && vmap[R] < n) inv[vmap[R]] = (int32_t)R;
+  auto excluded = [&](int64_t R) { return R >= excl_lo && R < excl_hi; };
+  std::vector<int32_t> rowk((size_t)rows * 32, -1);
+  out.iperm.assign((size_t)rows, -1);
+  out.row_diag.assign((size_t)rows * 8, -1);
+  out.row_sup.assign((size_t)rows * 8, -1);
+  out.row_node.assign((size_t)rows, -1);
+  for (int64_t R = 0; R < rows; ++R) {
+    const int32_t bp = R < (int64_t)vmap.size() ? vmap[(size_t)R] : -1;
+    if (bp < 0 || bp >= n) {
+      rowk[(size_t)R * 32] = -2;
+      continue;
+    }
+    const int32_t f = p.band_iperm[bp];
+    for (int32_t k = p.index_indptr[f]; k < p.index_indptr[f + 1]; ++k) {
+      const int32_t C = inv[p.band_perm[p.index_indices[k]]];
+      if (C < 0 || C > R) continue;                        // the other half's column, or the upper triangle
+      if (excluded(R) && excluded(C)) continue;
+      rowk[(size_t)R * 32 + (R - C)] = k;
+    }
+    if (excluded(R)) continue;                             // no diagonal, no right-hand side, no output row
+    out.iperm[(size_t)R] = f;
+    const int32_t node = p.free_node[f];
+    out.row_node[(size_t)R] = node;
+    const int32_t d0 = p.diags_indptr[f], d1 = p.diags_indptr[f + 1];
+    if (d1 - d0 > 8) out.row_diag[(size_t)R * 8] = -2;
+    else for (int32_t k = d0; k < d1; ++k) out.row_diag[(size_t)R * 8 + (k - d0)] = p.diags_indices[k];
+    int32_t cnt = 0;
+    bool overflow = false;
+    for (int32_t k = p.ninc_ptr[node]; k < p.ninc_ptr[node + 1]; ++k) {
+      const int32_t slot = p.node_slot[p.ninc_other[k]];
+      if (slot >= 0) continue;
+      if (cnt == 4) { overflow = true; break; }
+      out.row_sup[(size_t)R * 8 + 2 * cnt] = p.ninc_edge[k] >> 1;
+      out.row_sup[(size_t)R * 8 + 2 * cnt + 1] = -slot - 1;
+      ++cnt;
+    }
+    if (overflow) {
+      for (int j = 0; j < 8; ++j) out.row_sup[(size_t)R * 8 + j] = -1;
+      out.row_sup[(size_t)R * 8] = -2;
+    }
+  }
+  const int64_t blocks = rows / 32;
+  out.stage_ptr.assign((size_t)blocks + 1, 0);
+  out.stage_kent.clear();
+  out.stage_eent.clear();
+  for (int64_t b = 0; b < blocks; ++b) {
+    out.stage_ptr[(size_t)b] = (int32_t)(out.stage_kent.size() / 64);
+    for (int32_t r = 0; r < 32; ++r)
+      for (int32_t t = 0; t < 32; ++t) {
+        const int32_t k = rowk[(size_t)(b * 32 + r) * 32 + t];
+        if (k == -1) continue;
+        const int32_t pos = r * 32 + ((r - t) & 31);
+        const int32_t e = k >= 0 ? (p.entry_edge[k] >= 0 ? p.entry_edge[k] : -1) : k;   // diagonal: -1 (assembled per row)
+        out.stage_kent.push_back(pos);
+        out.stage_kent.push_back(k);
+        out.stage_eent.push_back(pos);
+        out.stage_eent.push_back(e);
+      }
+    while (out.stage_kent.size() % 64) {
+      out.stage_kent.push_back(0); out.stage_kent.push_back(-4);
+      out.stage_eent.push_back(0); out.stage_eent.push_back(-4);
+    }
+  }
+  out.stage_ptr[(size_t)blocks] = (int32_t)(out.stage_kent.size() / 64);
+}
+
+// Two-sided factorisation tables (four-column panel kernels only: hbw <= 29; at least two blocks per side).
+void fdm_build_twisted(fdm_plan& p) {
+  p.tw[0] = BandHalf();
+  p.tw[1] = BandHalf();
+  const int32_t n = (int32_t)p.Nf;
+  const int32_t nblk = (n + 31) / 32;
+  if (p.band_stage_ptr.empty() || p.hbw > 29 || nblk < 5) return;
+  const int32_t nbT = (nblk - 1) / 2, nbB = nblk - 1 - nbT, m = nbT * 32, npad = nblk * 32;
+  std::vector<int32_t> top((size_t)m + 32), bot((size_t)nbB * 32 + 32);
+  for (int32_t R = 0; R < m + 32; ++R) top[(size_t)R] = R;                         // [T | M]; positions >= n pad
+  for (int32_t R = 0; R < nbB * 32; ++R) bot[(size_t)R] = npad - 1 - R;            // B reversed
+  for (int32_t R = 0; R < 32; ++R) bot[(size_t)(nbB * 32 + R)] = m + 31 - R;       // M reversed
+  build_half_tables(p, top, -1, -1, p.tw[0]);
+  build_half_tables(p, bot, nbB * 32, nbB * 32 + 32, p.tw[1]);
+  p.tw[0].nblk = nbT + 1;
+  p.tw[1].nblk = nbB;
+}
+
 // Partition of the free nodes into `num_parts` compact aggregates: farthest-point seeding on
 // graph distance + Voronoi assignment (multi-source BFS).  Each new seed is the node farthest
 // from all previous seeds; its BFS only walks where it improves the distance, so the whole

@@ -36,8 +36,28 @@ struct DeviceArrays {
   int32_t* band_row_sup = nullptr;     // (rows, 8)  up to 4 (edge id, fixed index) pairs in incidence order, -1 padded; [0] = -2: walk the incidence list
   int32_t* band_row_node = nullptr;    // (rows)     node id of the row, -1 for padding rows
   int32_t* band_stage_eent = nullptr;  // (groups*32, 2): r*32 + slot, edge id | -1 zero (diagonal) | -2 one | -4 padding
+  // two-sided ("twisted") factorisation: the same tables for the top half [T | M] and the bottom half
+  // [reversed B | reversed M] of the band order (see BandHalf)
+  int32_t* tw_iperm[2] = {nullptr, nullptr};
+  int32_t* tw_stage_ptr[2] = {nullptr, nullptr};
+  int32_t* tw_stage_kent[2] = {nullptr, nullptr};
+  int32_t* tw_stage_eent[2] = {nullptr, nullptr};
+  int32_t* tw_row_diag[2] = {nullptr, nullptr};
+  int32_t* tw_row_sup[2] = {nullptr, nullptr};
+  int32_t* tw_row_node[2] = {nullptr, nullptr};
   // two-level persistent PCG (solver_pcg_persistent.cu); built lazily by the host
   void* pcg2 = nullptr;
+};
+
+// One half of the two-sided band factorisation.  The band order is cut into T = blocks [0, nbT), a middle block M
+// (32 rows, >= hbw, so T and B do not couple) and B = the blocks after M.  Half 0 factors [T | M] top-down; half 1
+// factors B bottom-up, i.e. the order [reversed B | reversed M] top-down with the M x M entries and M's right-hand
+// side left out (half 0 owns them).  Both leave their Schur complement on M; half 0 adds half 1's and factors M.
+// Same flops and fill as the one-sided factorisation, half the dependency chain.  Tables as the one-sided ones,
+// over the half's own row numbering; iperm = -1 for padding rows and, in half 1, for M's rows.
+struct BandHalf {
+  std::vector<int32_t> iperm, stage_ptr, stage_kent, stage_eent, row_diag, row_sup, row_node;
+  int32_t nblk = 0;       // blocks this half eliminates (half 0: nbT + 1 including M; half 1: nbB)
 };
 
 struct fdm_plan {
@@ -61,6 +81,7 @@ struct fdm_plan {
   std::vector<int32_t> band_stage_ptr, band_stage_kent, band_stage_eent;
   std::vector<int32_t> band_row_diag, band_row_sup, band_row_node;
   int32_t hbw = 0;
+  BandHalf tw[2];         // empty when the two-sided factorisation does not apply (hbw > 29 or fewer than 5 blocks)
 
   // aggregates for the two-level preconditioner
   std::vector<int32_t> part_of_row;  // (Nf) free index -> aggregate
@@ -76,3 +97,4 @@ void fdm_set_error(const std::string& msg);
 int fdm_build_topology(fdm_plan& p, const int64_t* edges, int64_t E, int64_t N, const int64_t* supports);
 void fdm_build_band_order(fdm_plan& p);
 void fdm_build_partition(fdm_plan& p, int num_parts);
+void fdm_build_twisted(fdm_plan& p);

@@ -56,6 +56,14 @@ constexpr unsigned kFull = 0xffffffffu;
 // slot of L(j+d, j) inside the 32-double record of factor column j
 #define FROT(j, d) (((d) + 5 * ((j) & 3)) & 31)
 
+// tables of one half of the two-sided factorisation (plan.h: BandHalf); the one-sided kernels use h[0] alone
+struct WHalf {
+  const int32_t *iperm, *stage_ptr, *stage_ent, *row_diag, *row_sup, *row_node;
+  int nblk;        // blocks this half eliminates
+  int rows;        // rows covered by iperm (one-sided: n; two-sided: every staged row, -1 = padding)
+  int block0;      // first factor block of this half inside the design's workspace
+};
+
 struct WArgs {
   int n, bw, nblk;
   const int32_t* rowkidx;  // ((nblk+1)*32, 32)
@@ -78,6 +86,10 @@ struct WArgs {
   const uint32_t* sup_mask;
   const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
   const int32_t *row_diag, *row_sup, *row_node;   // plan.band_row_* (assembly in place)
+  WHalf h[2];
+  int twisted;             // two warps per design: warp 2k factors [T | M] top-down, warp 2k+1 factors B bottom-up
+  int sigma_f, sigma_k;    // free index / position in K.data of the first diagonal entry (the sign of K)
+  int num_edges, num_nodes, num_fixed;   // bounds of the tables' targets (checked by the -DFDM_DEBUG build)
 };
 
 // 1/sqrt(x) for a positive normal double: hardware seed (MUFU.RSQ64H, ~20 bits) + ONE third-order step
@@ -248,6 +260,7 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_kernel(WArgs A) {
     meta[0] = sigma;
     meta[1] = (double)bad;
     meta[2] = 0.0;
+    meta[3] = 0.0;
   }
 }
 
@@ -320,22 +333,27 @@ __device__ __forceinline__ void invdiag_solve_store(double* fb, int lane, const 
 // sides are stored multiplied by D so that the backward substitution runs unchanged.  The signs go to the
 // fourth slot of the intermediate right-hand sides (the adjoint's forward sweep needs them), meta[2] = 1.
 // A pivot below 1e-13 of the largest diagonal entry seen is reported as a breakdown (meta[1] = 2).
-template <bool FROM_Q, int PW, bool SIGNED>
+template <bool FROM_Q, int PW, bool SIGNED, bool TW = false>   // TW: two-sided, a warp pair per design
 __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // designs per CTA = warps per CTA (host's choice)
+  // designs per CTA = warps per CTA (host's choice); two-sided: a design is the warp pair (2k, 2k+1)
+  const int half = TW ? (warp & 1) : 0;
+  const int64_t b = TW ? (int64_t)blockIdx.x * (blockDim.x >> 6) + (warp >> 1) : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= A.batch) return;
+  const WHalf H = TW ? A.h[half]
+                            : WHalf{A.iperm, A.stage_ptr, A.stage_ent, A.row_diag, A.row_sup, A.row_node, A.nblk, A.n, 0};
   double* fs = smem + warp * kMmaWarpSmem;
   double* Pn = fs + 32 * kMS;
   const int g = lane >> 2, m = lane & 3;
-  const int n = A.n, nblk = A.nblk;
+  const int n = A.n, nblk = H.nblk;
   const double* Kd = FROM_Q ? nullptr : A.Kdata + b * A.nnz;
   const double* rhs = FROM_Q ? nullptr : A.rhs + b * (int64_t)n * 3;
   const double* q = FROM_Q ? A.q + b * A.q_stride : nullptr;
-  double* fac = A.ws + b * A.ws_stride;
-  double* ysol = fac + (int64_t)nblk * 1024;
-  double* meta = ysol + (int64_t)nblk * 128;
+  double* const ws0 = A.ws + b * A.ws_stride;
+  double* fac = ws0 + (int64_t)H.block0 * 1024;
+  double* ysol = ws0 + (int64_t)A.nblk * 1024 + (int64_t)H.block0 * 128;
+  double* meta = ws0 + (int64_t)A.nblk * (1024 + 128);
   int bad = 0;
   if (SIGNED && meta[1] == 0.0) return;                    // the plain factorisation succeeded for this design
   double dmax = 0.0;                                       // SIGNED: largest |diagonal entry| staged so far
@@ -349,26 +367,28 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
     return dsum;
   };
   double sigma;
-  if (FROM_Q) sigma = diag_of(__ldg(A.iperm)) < 0.0 ? -1.0 : 1.0;
-  else sigma = __ldg(Kd + __ldg(A.rowkidx)) < 0.0 ? -1.0 : 1.0;
+  if (FROM_Q) sigma = diag_of(A.sigma_f) < 0.0 ? -1.0 : 1.0;
+  else sigma = __ldg(Kd + A.sigma_k) < 0.0 ? -1.0 : 1.0;
 
   // fs[r][s] = sigma * A(R0 + r, C), C = the column with slot s among the 32 ending at row R0 + r;
   // fs[r][32..34] = sigma * rhs(R0 + r).  K is sparse inside the band: the plan lists the non-zero (r, s) of
   // every block (band_stage_*), a few per lane; fs is all zero between blocks (the previous block's entries
   // are taken back first), so a block costs one round of index loads and one of value loads.
-  const int2* ent = reinterpret_cast<const int2*>(A.stage_ent);
+  const int2* ent = reinterpret_cast<const int2*>(H.stage_ent);
   auto stage_rows = [&](int blk) {
     const int R0 = blk * 32;
     // loads are issued in the order that keeps two chains in flight side by side: entry lists -> K.data,
     // band-to-free index -> right-hand side
-    const int g0 = __ldg(A.stage_ptr + blk), g1 = __ldg(A.stage_ptr + blk + 1);
+    const int g0 = __ldg(H.stage_ptr + blk), g1 = __ldg(H.stage_ptr + blk + 1);
     int gi = -1;
-    if (R0 + lane < n) gi = __ldg(A.iperm + R0 + lane);
+    if (R0 + lane < H.rows) gi = __ldg(H.iperm + R0 + lane);
+    FDM_ASSERT(gi >= -1 && gi < n, "iperm[%d] = %d, n = %d, half %d", R0 + lane, gi, n, half);
+    FDM_ASSERT(g0 <= g1 && g1 - g0 <= 64, "stage groups [%d, %d) of block %d, half %d", g0, g1, blk, half);
     int2 e[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) e[u] = g0 + u < g1 ? __ldg(ent + (g0 + u) * 32 + lane) : make_int2(0, -4);
     if (blk > 0) {                                           // take back the previous block's entries
-      const int h0 = __ldg(A.stage_ptr + blk - 1);
+      const int h0 = __ldg(H.stage_ptr + blk - 1);
       for (int gq = h0; gq < g0; gq += 4) {
         int2 o[4];
 #pragma unroll
@@ -390,6 +410,8 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         v[u] = e[u].y == -2 ? 1.0 : 0.0;
+        FDM_ASSERT(e[u].y == -4 || (e[u].x >= 0 && e[u].x < 1024), "stage slot %d (block %d, half %d)", e[u].x, blk, half);
+        FDM_ASSERT(e[u].y < (FROM_Q ? A.num_edges : (int)A.nnz), "stage index %d (block %d, half %d)", e[u].y, blk, half);
         if (e[u].y >= 0) v[u] = FROM_Q ? -sigma * __ldg(q + e[u].y) : sigma * __ldg(Kd + e[u].y);
       }
 #pragma unroll
@@ -407,11 +429,12 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
       // one of value loads; the sums run in the order of the assembly kernel (same bits).
       const int f = gi;
       const int R = R0 + lane;
-      const int4 da = __ldg(reinterpret_cast<const int4*>(A.row_diag) + 2 * R);
-      const int4 db = __ldg(reinterpret_cast<const int4*>(A.row_diag) + 2 * R + 1);
-      const int4 sa = __ldg(reinterpret_cast<const int4*>(A.row_sup) + 2 * R);
-      const int4 sb = __ldg(reinterpret_cast<const int4*>(A.row_sup) + 2 * R + 1);
-      const int node = __ldg(A.row_node + R);
+      const int4 da = __ldg(reinterpret_cast<const int4*>(H.row_diag) + 2 * R);
+      const int4 db = __ldg(reinterpret_cast<const int4*>(H.row_diag) + 2 * R + 1);
+      const int4 sa = __ldg(reinterpret_cast<const int4*>(H.row_sup) + 2 * R);
+      const int4 sb = __ldg(reinterpret_cast<const int4*>(H.row_sup) + 2 * R + 1);
+      const int node = __ldg(H.row_node + R);
+      FDM_ASSERT(node >= 0 && node < A.num_nodes, "row_node[%d] = %d (half %d)", R, node, half);
       const double* lp = A.loads + b * A.loads_stride + 3 * (int64_t)node;
       const double p0 = __ldg(lp), p1 = __ldg(lp + 1), p2 = __ldg(lp + 2);
       double dsum;
@@ -492,6 +515,30 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
     const int j0 = jb * 32;
     double* const fb = fac + (int64_t)j0 * 32;
     double* const yb = ysol + (int64_t)j0 * 4;
+    FDM_ASSERT(H.block0 + jb < A.nblk, "factor block %d + %d of %d (half %d)", H.block0, jb, A.nblk, half);
+    if constexpr (PW == 4 && TW) {
+      if (half == 0 && jb == nblk - 1) {
+        // Two-sided: the window now holds the middle block M with every update from T.  The partner warp has
+        // left B's updates of M in its staging area, in ITS (reversed) numbering: entry (r, c) here is
+        // (31 - r, 31 - c) there; right-hand side column c is 31 - c.  Add them; M is then factored like any block.
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp >> 1)) : "memory");
+        const double* fo = fs + kMmaWarpSmem;            // warp + 1's staging area
+#pragma unroll
+        for (int tr = 0; tr < 4; ++tr)
+#pragma unroll
+          for (int tc = 0; tc <= tr; ++tc)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) W[tr][tc][e] += fo[(31 - (8 * tr + g)) * kMS + 31 - (8 * tc + 2 * m + e)];
+        if (g < 3) {
+#pragma unroll
+          for (int tc = 0; tc < 4; ++tc)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) Y[tc][e] += fo[(31 - (8 * tc + 2 * m + e)) * kMS + 32 + g];
+        }
+        const int obad = (int)fo[32 * kMS];              // the partner's pivot flag
+        if (SIGNED) bad = obad == 2 ? 2 : bad; else bad |= obad;
+      }
+    }
     __syncwarp();
     stage_rows(jb + 1);
     __syncwarp();
@@ -759,10 +806,38 @@ __global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A
       invdiag_solve_store(fb, lane, dcol);
     }
   }
+  if constexpr (PW == 4 && TW) {
+    if (half == 1) {
+      // bottom-up half: leave the updated window (M in reversed numbering, as a full symmetric matrix), its
+      // right-hand-side rows and the pivot flag in the staging area for the partner, and retire
+      __syncwarp();
+#pragma unroll
+      for (int tr = 0; tr < 4; ++tr)
+#pragma unroll
+        for (int tc = 0; tc <= tr; ++tc)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int R = 8 * tr + g, C = 8 * tc + 2 * m + e;
+            fs[R * kMS + C] = W[tr][tc][e];
+            if (tc < tr) fs[C * kMS + R] = W[tr][tc][e];
+          }
+      if (g < 3) {
+#pragma unroll
+        for (int tc = 0; tc < 4; ++tc)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) fs[(8 * tc + 2 * m + e) * kMS + 32 + g] = Y[tc][e];
+      }
+      if (lane == 0) fs[32 * kMS] = (double)bad;
+      __threadfence_block();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp >> 1)) : "memory");
+      return;
+    }
+  }
   if (lane == 0) {
     meta[0] = sigma;
     meta[1] = (double)bad;
     meta[2] = SIGNED ? 1.0 : 0.0;
+    meta[3] = TW ? 1.0 : 0.0;                              // layout of the stored factor, read by chol_subst_kernel
   }
 }
 
@@ -827,6 +902,12 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   const double sigma = meta[0];
   const int bad = (int)meta[1];
   const bool sgn = meta[2] != 0.0;                        // sigma*K = L D L^T: D in slot 3 of the intermediate rhs
+  // Two-sided factor (meta[3], written by the factor kernel): half 0 = [T | M] in blocks 0 .. nbT, half 1 = B
+  // bottom-up in the blocks after them.  Visit order: forward T, forward B, forward M; backward M, T, B.  The
+  // running right-hand side of M after T is set aside while B runs and B's part (reversed numbering) is added
+  // to it; x_M is handed to B's backward sweep the same way.
+  const bool tw = NBL >= 3 && meta[3] != 0.0;
+  const int nbT = tw ? A.h[0].nblk - 1 : nblk, nbB = tw ? A.h[1].nblk : 0;
 
   if (lane == 0) {
     mbar_init(bars, 1);
@@ -836,15 +917,28 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   for (int i = lane; i < 4 * 64; i += 32) xt[i] = 0.0;
   __syncwarp();
 
-  // visit v = 0 .. nvis-1: forward pass over blocks 0..nblk-1 (if A.forward), then backward pass nblk-1..0
+  // visit v = 0 .. nvis-1: forward pass (if A.forward), then backward pass; (half, block in the half) of a visit
   const int nfwd = A.forward ? nblk : 0;
   const int nvis = nfwd + nblk;
-  auto block_of = [&](int v) { return v < nfwd ? v : nblk - 1 - (v - nfwd); };
-  auto issue = [&](int v) {  // one 8 KB bulk copy: the 32 factor columns of block_of(v) into buffer v&1
+  auto half_of = [&](int v) {
+    if (!tw) return 0;
+    const int u = v < nfwd ? v : v - nfwd;
+    return v < nfwd ? (u >= nbT && u < nbT + nbB ? 1 : 0) : (u > nbT ? 1 : 0);
+  };
+  auto blk_of = [&](int v) {                               // block index inside its half
+    if (!tw) return v < nfwd ? v : nblk - 1 - (v - nfwd);
+    const int u = v < nfwd ? v : v - nfwd;
+    if (v < nfwd) return u < nbT ? u : (u < nbT + nbB ? u - nbT : nbT);
+    return u == 0 ? nbT : (u <= nbT ? nbT - u : nbB - (u - nbT));
+  };
+  auto gblock_of = [&](int v) { return (tw ? A.h[half_of(v)].block0 : 0) + blk_of(v); };   // factor block in the workspace
+  auto iperm_of = [&](int v) { return tw ? A.h[half_of(v)].iperm : A.iperm; };
+  auto rows_in = [&](int v) { return tw ? A.h[half_of(v)].rows : n; };
+  auto issue = [&](int v) {  // one 8 KB bulk copy: the 32 factor columns of the visit's block into buffer v&1
     if (lane == 0) {
       uint64_t* bar = bars + (v & 1);
       mbar_expect_tx(bar, 32 * 256);
-      tma_load_1d(fsb + (v & 1) * 32 * kSS, fac + (int64_t)block_of(v) * 1024, 32 * 256, bar);
+      tma_load_1d(fsb + (v & 1) * 32 * kSS, fac + (int64_t)gblock_of(v) * 1024, 32 * 256, bar);
     }
   };
   uint32_t phases = 0u;   // bit i: parity the next wait on barrier i expects
@@ -852,20 +946,25 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
 
   // forward-pass state: T[i] = rows of group k+i of the running right-hand side, 8x8 tile (columns 0..2
   // used) in the accumulator layout of the FP64 mma: lane (g, m) holds row g, columns 2m and 2m+1.
-  auto load_tile = [&](int R, double (&t)[2]) {
+  auto load_tile = [&](const int32_t* ip, int rows, int R, double (&t)[2]) {
     t[0] = 0.0; t[1] = 0.0;
-    if (R < n && m < 2) {
-      const int gi = __ldg(A.iperm + R);
-      t[0] = sigma * rhs[3 * gi + 2 * m];
-      if (m == 0) t[1] = sigma * rhs[3 * gi + 1];
+    if (R < rows && m < 2) {
+      const int gi = __ldg(ip + R);
+      if (gi >= 0) {
+        t[0] = sigma * rhs[3 * gi + 2 * m];
+        if (m == 0) t[1] = sigma * rhs[3 * gi + 1];
+      }
     }
   };
   double T[NBL + 1][2];
 #pragma unroll
   for (int i = 0; i <= NBL; ++i) {
     T[i][0] = 0.0; T[i][1] = 0.0;
-    if (nfwd) load_tile(8 * i + g, T[i]);
+    if (nfwd) load_tile(iperm_of(0), rows_in(0), 8 * i + g, T[i]);
   }
+  double TM[4][2], XM[4][2];                               // two-sided: M's running rhs after T; x_M
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { TM[i][0] = TM[i][1] = 0.0; XM[i][0] = XM[i][1] = 0.0; }
   // Global operands of a visit are fetched ahead so that no load sits on a warp's critical path:
   // band-to-free row indices two visits ahead (Qn -> Q -> Qc), values one visit ahead (P -> C).
   // Forward visit: the four row groups that enter the window.  Backward visit: the four groups
@@ -873,14 +972,16 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   double P[4][2], C[4][2];
   int Qn[4], Q[4], Qc[4];
   auto rows_of = [&](int v, int kb) {
-    const int r0 = block_of(v) * 32 + 8 * kb + g;
+    const int r0 = blk_of(v) * 32 + 8 * kb + g;
     return v < nfwd ? r0 + 8 * (NBL + 1) : r0;
   };
   auto fetch_idx = [&](int v) {
+    const int32_t* ip = iperm_of(v);
+    const int rows = rows_in(v);
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
       const int R = rows_of(v, kb);
-      Qn[kb] = R < n ? __ldg(A.iperm + R) : -1;
+      Qn[kb] = R < rows ? __ldg(ip + R) : -1;
     }
   };
   auto fetch_val = [&](int v) {   // uses Q = row indices of visit v
@@ -894,7 +995,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
         }
       }
     } else {
-      const int r0 = block_of(v) * 32;
+      const int r0 = gblock_of(v) * 32;
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
         P[kb][0] = 0.0; P[kb][1] = 0.0;
@@ -911,9 +1012,10 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   for (int kb = 0; kb < 4; ++kb) Q[kb] = Qn[kb];
   fetch_val(0);
   if (nvis > 1) fetch_idx(1);
+  const int mirror = ((7 - g) << 2) | m;                   // lane holding row 7 - g of a tile (same columns)
 
   for (int v = 0; v < nvis; ++v) {
-    const int jb = block_of(v), j0 = jb * 32;
+    const int j0 = gblock_of(v) * 32;                      // first row of the block in the workspace numbering
     __syncwarp();                      // every lane is done with buffer (v+1)&1 (used at visit v-1)
     if (v + 1 < nvis) issue(v + 1);
     mbar_wait(bars + (v & 1), (phases >> (v & 1)) & 1u);
@@ -927,6 +1029,36 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
     }
     if (v + 1 < nvis && v + 1 != nfwd) fetch_val(v + 1);
     if (v + 2 < nvis) fetch_idx(v + 2);
+    if (tw && nfwd) {
+      if (v == nbT) {
+        // T is done: its window holds M's rows.  Set them aside and start B's sweep from B's own first rows.
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { TM[i][0] = T[i][0]; TM[i][1] = T[i][1]; }
+#pragma unroll
+        for (int i = 0; i <= NBL; ++i) load_tile(A.h[1].iperm, A.h[1].rows, 8 * i + g, T[i]);
+      } else if (v == nbT + nbB) {
+        // B is done: its window holds its part of M in reversed numbering (group i there = group 3 - i here, row
+        // g there = row 7 - g here).  M's right-hand side = what T left + what B left.
+        double R4[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          R4[i][0] = __shfl_sync(kFull, T[i][0], mirror);
+          R4[i][1] = __shfl_sync(kFull, T[i][1], mirror);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { T[i][0] = TM[i][0] + R4[3 - i][0]; T[i][1] = TM[i][1] + R4[3 - i][1]; }
+        if (NBL == 4) { T[NBL][0] = 0.0; T[NBL][1] = 0.0; }
+      }
+    }
+    if (tw && v == nfwd + nbT + 1) {
+      // backward: M and T are done, B starts from x_M in its own numbering
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double x0 = __shfl_sync(kFull, XM[3 - i][0], mirror), x1 = __shfl_sync(kFull, XM[3 - i][1], mirror);
+        *reinterpret_cast<double2*>(xt + i * 64 + g * 8 + 2 * m) = make_double2(x0, x1);
+      }
+      __syncwarp();
+    }
     if (v < nfwd) {
       // ---------------------------------------------------------------- forward: L z = sigma g
 #pragma unroll
@@ -1000,6 +1132,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
           dmma(x0, x1, a1, b1);
         }
         *reinterpret_cast<double2*>(xt + (kb & 3) * 64 + g * 8 + 2 * m) = make_double2(x0, x1);
+        if (tw && v == nfwd) { XM[kb][0] = x0; XM[kb][1] = x1; }   // x_M, for B's sweep
         if (Qc[kb] >= 0 && m < 2) {
           double* xo = A.x + (b * (int64_t)n + Qc[kb]) * 3 + 2 * m;
           xo[0] = x0;
@@ -1059,6 +1192,39 @@ inline size_t fac_smem_pad() {
   return v;
 }
 
+// Two-sided factorisation: two warps per design, half the dependency chain, same flops.  It pays when the batch
+// leaves SMs short of warps (one-sided: one warp per design); with every SM full it only adds the hand-over.
+// FDM_CHOL_TWISTED = 0 / 1 forces it off / on (where the plan has the tables).
+inline bool use_twisted(const fdm_plan* p, int64_t batch) {
+  static const int force = [] {
+    const char* e = std::getenv("FDM_CHOL_TWISTED");
+    return e ? std::atoi(e) : -1;
+  }();
+  if (p->tw[0].nblk == 0 || p->hbw < 16 || p->hbw > 29 || !p->d.tw_iperm[0]) return false;
+  if (force >= 0) return force != 0;
+  return batch <= (int64_t)p->sm_count * 8;
+}
+
+inline void fill_halves(WArgs& A, const fdm_plan* p, bool from_q) {
+  for (int h = 0; h < 2; ++h) {
+    WHalf& H = A.h[h];
+    const bool on = p->tw[0].nblk > 0 && p->d.tw_iperm[0];
+    H.iperm = on ? p->d.tw_iperm[h] : nullptr;
+    H.stage_ptr = on ? p->d.tw_stage_ptr[h] : nullptr;
+    H.stage_ent = on ? (from_q ? p->d.tw_stage_eent[h] : p->d.tw_stage_kent[h]) : nullptr;
+    H.row_diag = on ? p->d.tw_row_diag[h] : nullptr;
+    H.row_sup = on ? p->d.tw_row_sup[h] : nullptr;
+    H.row_node = on ? p->d.tw_row_node[h] : nullptr;
+    H.nblk = on ? p->tw[h].nblk : 0;
+    H.rows = on ? (int)p->tw[h].iperm.size() : 0;
+    H.block0 = h == 0 ? 0 : p->tw[0].nblk;
+  }
+  A.twisted = 0;
+  A.num_edges = (int)p->E; A.num_nodes = (int)p->N; A.num_fixed = (int)p->Ns;
+  A.sigma_f = p->band_iperm.empty() ? 0 : p->band_iperm[0];
+  A.sigma_k = p->band_rowkidx.empty() ? 0 : p->band_rowkidx[0];
+}
+
 inline int64_t ws_stride_of(const fdm_plan* p) {
   const int64_t nblk = (p->Nf + 31) / 32;
   return nblk * 1024 + nblk * 128 + 8;
@@ -1097,6 +1263,7 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   A.ninc_edge = p->d.ninc_edge; A.ninc_other = p->d.ninc_other; A.sup_mask = p->d.sup_mask;
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_eent;
   A.row_diag = p->d.band_row_diag; A.row_sup = p->d.band_row_sup; A.row_node = p->d.band_row_node;
+  fill_halves(A, p, true);
 }
 
 static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
@@ -1125,17 +1292,22 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   A.q = q; A.xs = xs; A.loads = loads;
   A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
   A.nan_fail = o.nan_on_failure;
+  A.twisted = mma_panel4(p) && use_twisted(p, batch) ? 1 : 0;
   const int stages = o.stages ? o.stages : 7;
-  const int fw = mma_warps_per_cta();
+  int fw = mma_warps_per_cta();
+  if (A.twisted) fw = std::max(2, fw & ~1);                // a design is a warp pair
+  const int dpc = A.twisted ? fw / 2 : fw;                 // designs per CTA
   const size_t smem = (size_t)fw * kMmaWarpSmem * sizeof(double) + fac_smem_pad();
-  void (*fkern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, false> : chol_factor_mma_kernel<true, 2, false>;
+  void (*fkern)(WArgs) = A.twisted ? chol_factor_mma_kernel<true, 4, false, true>
+                       : mma_panel4(p) ? chol_factor_mma_kernel<true, 4, false> : chol_factor_mma_kernel<true, 2, false>;
   if (stages & 1) {
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    fkern<<<(unsigned)((batch + dpc - 1) / dpc), fw * 32, smem, st>>>(A);
     // designs with a non-positive pivot (mixed-sign q) are factored again with signed pivots
-    void (*skern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<true, 4, true> : chol_factor_mma_kernel<true, 2, true>;
+    void (*skern)(WArgs) = A.twisted ? chol_factor_mma_kernel<true, 4, true, true>
+                         : mma_panel4(p) ? chol_factor_mma_kernel<true, 4, true> : chol_factor_mma_kernel<true, 2, true>;
     FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    skern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    skern<<<(unsigned)((batch + dpc - 1) / dpc), fw * 32, smem, st>>>(A);
   }
   if (stages & 4) {
     int rc = launch_backward(p, A, batch, st);
@@ -1176,6 +1348,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.ninc_ptr = A.ninc_edge = A.ninc_other = nullptr; A.sup_mask = nullptr;
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_kent;
   A.row_diag = A.row_sup = A.row_node = nullptr;
+  fill_halves(A, p, false);
   void (*fkern)(WArgs) = nullptr;
   void (*skern)(WArgs) = nullptr;
   if (p->hbw <= 7) { fkern = chol_factor_kernel<7>; skern = chol_subst_kernel<1>; }
@@ -1187,18 +1360,23 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   const bool mma = p->hbw <= 30 && !force_simt;                             // these invert the diagonal blocks themselves
   if (!o.reuse_factor && (stages & 1)) {
     size_t smem = (size_t)kFacWarps * kFacWarpSmem * sizeof(double);
-    int fw = kFacWarps;
+    int fw = kFacWarps, dpc = kFacWarps;
     if (mma) {
       fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, false> : chol_factor_mma_kernel<false, 2, false>;
       fw = mma_warps_per_cta();
+      A.twisted = mma_panel4(p) && use_twisted(p, batch) ? 1 : 0;
+      if (A.twisted) fw = std::max(2, fw & ~1);
+      dpc = A.twisted ? fw / 2 : fw;
+      if (A.twisted) fkern = chol_factor_mma_kernel<false, 4, false, true>;
       smem = (size_t)fw * kMmaWarpSmem * sizeof(double) + fac_smem_pad();
     }
     FDM_CUDA(cudaFuncSetAttribute(fkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fkern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+    fkern<<<(unsigned)((batch + dpc - 1) / dpc), fw * 32, smem, st>>>(A);
     if (mma) {   // designs with a non-positive pivot (mixed-sign q): again, with signed pivots
-      void (*skern)(WArgs) = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, true> : chol_factor_mma_kernel<false, 2, true>;
+      void (*skern)(WArgs) = A.twisted ? chol_factor_mma_kernel<false, 4, true, true>
+                           : mma_panel4(p) ? chol_factor_mma_kernel<false, 4, true> : chol_factor_mma_kernel<false, 2, true>;
       FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      skern<<<(unsigned)((batch + fw - 1) / fw), fw * 32, smem, st>>>(A);
+      skern<<<(unsigned)((batch + dpc - 1) / dpc), fw * 32, smem, st>>>(A);
     }
   }
   if (!o.reuse_factor && (stages & 2) && !mma) {

@@ -87,6 +87,7 @@ struct WArgs {
   const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
   const int32_t *row_diag, *row_sup, *row_node;   // plan.band_row_* (assembly in place)
   WHalf h[2];
+  int sub_pair;            // substitution kernel: a warp pair per design (two-sided factor): T and B sweeps in parallel
   int twisted;             // two warps per design: warp 2k factors [T | M] top-down, warp 2k+1 factors B bottom-up
   int sigma_f, sigma_k;    // free index / position in K.data of the first diagonal entry (the sign of K)
   int num_edges, num_nodes, num_fixed;   // bounds of the tables' targets (checked by the -DFDM_DEBUG build)
@@ -886,13 +887,16 @@ template <int NBL>  // column group k reaches row groups k+1 .. k+NBL
 __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;   // designs per CTA = warps per CTA (host's choice)
-  if (b >= A.batch) return;
+  // designs per CTA = warps per CTA (host's choice); A.sub_pair: a design is the warp pair (2k, 2k+1)
+  const int64_t b = A.sub_pair ? (int64_t)blockIdx.x * (blockDim.x >> 6) + (warp >> 1)
+                               : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (b >= A.batch || (A.sub_pair && warp >= (int)((blockDim.x >> 6) << 1))) return;
   double* fsb = smem + warp * kSubWarpSmem;   // two staged blocks
   double* zt1 = fsb + 2 * 32 * kSS;
   double* zt2 = zt1 + 64;
   double* xt = zt2 + 64;
   uint64_t* bars = reinterpret_cast<uint64_t*>(xt + 4 * 64);
+  double* xt_other = smem + (warp ^ 1) * kSubWarpSmem + 2 * 32 * kSS + 128;   // the partner's ring (A.sub_pair)
   const int g = lane >> 2, m = lane & 3;
   const int n = A.n, nblk = A.nblk;
   const double* rhs = A.rhs + b * (int64_t)n * 3;
@@ -903,11 +907,18 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   const int bad = (int)meta[1];
   const bool sgn = meta[2] != 0.0;                        // sigma*K = L D L^T: D in slot 3 of the intermediate rhs
   // Two-sided factor (meta[3], written by the factor kernel): half 0 = [T | M] in blocks 0 .. nbT, half 1 = B
-  // bottom-up in the blocks after them.  Visit order: forward T, forward B, forward M; backward M, T, B.  The
-  // running right-hand side of M after T is set aside while B runs and B's part (reversed numbering) is added
-  // to it; x_M is handed to B's backward sweep the same way.
+  // bottom-up in the blocks after them.  One warp (role 0): forward T, forward B, forward M; backward M, T, B; the
+  // running right-hand side of M after T is set aside while B runs and B's part (reversed numbering) is added to
+  // it; x_M is handed to B's backward sweep the same way.  A warp pair (roles 1 = top, 2 = bottom) runs the T and B
+  // sweeps side by side and meets on M through the partner's shared-memory ring and two named barriers.
   const bool tw = NBL >= 3 && meta[3] != 0.0;
+  int role = A.sub_pair ? 1 + (warp & 1) : 0;
+  if (role && !tw) {                                       // paired launch on a one-sided factor: the first warp does it all
+    if (role == 2) return;
+    role = 0;
+  }
   const int nbT = tw ? A.h[0].nblk - 1 : nblk, nbB = tw ? A.h[1].nblk : 0;
+  const int bar_a = 1 + 2 * (warp >> 1), bar_b = bar_a + 1;   // named barriers of the pair
 
   if (lane == 0) {
     mbar_init(bars, 1);
@@ -918,15 +929,17 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   __syncwarp();
 
   // visit v = 0 .. nvis-1: forward pass (if A.forward), then backward pass; (half, block in the half) of a visit
-  const int nfwd = A.forward ? nblk : 0;
-  const int nvis = nfwd + nblk;
+  const int nmine = role == 0 ? nblk : role == 1 ? nbT + 1 : nbB;   // blocks this warp sweeps
+  const int nfwd = A.forward ? nmine : 0;
+  const int nvis = nfwd + nmine;
   auto half_of = [&](int v) {
+    if (role) return role - 1;
     if (!tw) return 0;
     const int u = v < nfwd ? v : v - nfwd;
     return v < nfwd ? (u >= nbT && u < nbT + nbB ? 1 : 0) : (u > nbT ? 1 : 0);
   };
   auto blk_of = [&](int v) {                               // block index inside its half
-    if (!tw) return v < nfwd ? v : nblk - 1 - (v - nfwd);
+    if (role || !tw) return v < nfwd ? v : nmine - 1 - (v - nfwd);
     const int u = v < nfwd ? v : v - nfwd;
     if (v < nfwd) return u < nbT ? u : (u < nbT + nbB ? u - nbT : nbT);
     return u == 0 ? nbT : (u <= nbT ? nbT - u : nbB - (u - nbT));
@@ -1029,7 +1042,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
     }
     if (v + 1 < nvis && v + 1 != nfwd) fetch_val(v + 1);
     if (v + 2 < nvis) fetch_idx(v + 2);
-    if (tw && nfwd) {
+    if (role == 0 && tw && nfwd) {
       if (v == nbT) {
         // T is done: its window holds M's rows.  Set them aside and start B's sweep from B's own first rows.
 #pragma unroll
@@ -1050,7 +1063,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
         if (NBL == 4) { T[NBL][0] = 0.0; T[NBL][1] = 0.0; }
       }
     }
-    if (tw && v == nfwd + nbT + 1) {
+    if (role == 0 && tw && v == nfwd + nbT + 1) {
       // backward: M and T are done, B starts from x_M in its own numbering
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1058,6 +1071,28 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
         *reinterpret_cast<double2*>(xt + i * 64 + g * 8 + 2 * m) = make_double2(x0, x1);
       }
       __syncwarp();
+    }
+    if (role == 1 && nfwd && v == nbT) {
+      // top of a pair, forward: T is done and the window holds M; the partner has left B's part of M (reversed
+      // numbering) in its ring.  Add it: group i, row g here = group 3 - i, row 7 - g there.
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 o = *reinterpret_cast<const double2*>(xt_other + (3 - i) * 64 + (7 - g) * 8 + 2 * m);
+        T[i][0] += o.x; T[i][1] += o.y;
+      }
+      if (NBL == 4) { T[NBL][0] = 0.0; T[NBL][1] = 0.0; }
+    }
+    if (role == 2 && v == nfwd) {
+      // bottom of a pair: after its forward sweep the window holds its part of M -> the ring, for the partner;
+      // then x_M comes back through the same ring before the backward sweep starts
+      if (nfwd) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<double2*>(xt + i * 64 + g * 8 + 2 * m) = make_double2(T[i][0], T[i][1]);
+        __threadfence_block();
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");
     }
     if (v < nfwd) {
       // ---------------------------------------------------------------- forward: L z = sigma g
@@ -1132,7 +1167,9 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
           dmma(x0, x1, a1, b1);
         }
         *reinterpret_cast<double2*>(xt + (kb & 3) * 64 + g * 8 + 2 * m) = make_double2(x0, x1);
-        if (tw && v == nfwd) { XM[kb][0] = x0; XM[kb][1] = x1; }   // x_M, for B's sweep
+        if (role == 0 && tw && v == nfwd) { XM[kb][0] = x0; XM[kb][1] = x1; }   // x_M, for B's sweep
+        if (role == 1 && v == nfwd)                        // x_M into the partner's ring, in ITS numbering
+          *reinterpret_cast<double2*>(xt_other + (3 - kb) * 64 + (7 - g) * 8 + 2 * m) = make_double2(x0, x1);
         if (Qc[kb] >= 0 && m < 2) {
           double* xo = A.x + (b * (int64_t)n + Qc[kb]) * 3 + 2 * m;
           xo[0] = x0;
@@ -1140,8 +1177,14 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
         }
         __syncwarp();
       }
+      if (role == 1 && v == nfwd) {                        // the partner may start its backward sweep
+        __threadfence_block();
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_b) : "memory");
+      }
     }
   }
+  if (role) asm volatile("bar.sync %0, 64;" ::"r"(bar_a) : "memory");   // both sweeps have stored their rows of x
+  if (role == 2) return;                                   // the top warp reports
   if (A.nan_fail && bad != 0) {                            // fdm_solve_opts.nan_on_failure
     __syncwarp();
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -1220,6 +1263,7 @@ inline void fill_halves(WArgs& A, const fdm_plan* p, bool from_q) {
     H.block0 = h == 0 ? 0 : p->tw[0].nblk;
   }
   A.twisted = 0;
+  A.sub_pair = 0;
   A.num_edges = (int)p->E; A.num_nodes = (int)p->N; A.num_fixed = (int)p->Ns;
   A.sigma_f = p->band_iperm.empty() ? 0 : p->band_iperm[0];
   A.sigma_k = p->band_rowkidx.empty() ? 0 : p->band_rowkidx[0];
@@ -1266,13 +1310,20 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
   fill_halves(A, p, true);
 }
 
+// The substitution launch.  Small batches whose factor is two-sided get a warp pair per design (the T and B sweeps
+// side by side); the predicate is the factor kernel's own, so both calls of a solve agree (the kernel falls back to
+// one warp when the stored factor turns out one-sided).
 static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
   void (*skern)(WArgs) = p->hbw <= 7 ? chol_subst_kernel<1> : p->hbw <= 15 ? chol_subst_kernel<2>
                        : p->hbw <= 23 ? chol_subst_kernel<3> : chol_subst_kernel<4>;
-  const int sw = sub_warps_per_cta();
+  static const bool no_pair = std::getenv("FDM_CHOL_SUBPAIR") && std::atoi(std::getenv("FDM_CHOL_SUBPAIR")) == 0;
+  A.sub_pair = mma_panel4(p) && use_twisted(p, batch) && !no_pair ? 1 : 0;
+  int sw = sub_warps_per_cta();
+  if (A.sub_pair) sw = std::max(2, sw & ~1);
+  const int dpc = A.sub_pair ? sw / 2 : sw;                // designs per CTA
   const size_t smem = (size_t)sw * kSubWarpSmem * sizeof(double);
   FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  skern<<<(unsigned)((batch + sw - 1) / sw), sw * 32, smem, st>>>(A);
+  skern<<<(unsigned)((batch + dpc - 1) / dpc), sw * 32, smem, st>>>(A);
   return FDM_OK;
 }
 
@@ -1384,10 +1435,8 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
   }
   if (stages & 4) {
-    const int sw = sub_warps_per_cta();
-    const size_t smem = (size_t)sw * kSubWarpSmem * sizeof(double);
-    FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    skern<<<(unsigned)((batch + sw - 1) / sw), sw * 32, smem, st>>>(A);
+    int rc = launch_backward(p, A, batch, st);
+    if (rc != FDM_OK) return rc;
   }
   return fdm_check_launch("chol_warp_solve");
 }

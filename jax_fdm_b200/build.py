@@ -20,10 +20,11 @@ def _headers():
     return hs
 
 
-def _stale():
-    if not os.path.exists(OUT):
+def _stale(out=None):
+    out = out or OUT
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     deps = [os.path.join(CSRC, f) for f in SOURCES] + _headers()
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -32,7 +33,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     """Compile every source to an object (in parallel, only the stale ones) and link the shared library.
     `defines` / `out`: an alternative build of the same library (e.g. -DFDM_DEBUG bounds asserts)."""
     out = out or OUT
-    if not force and not defines and not _stale():
+    if not force and not _stale(out):
         return out
     from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

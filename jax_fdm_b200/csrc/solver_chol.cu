@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(kThreads) chol_band_kernel(CholArgs A) {
     const int j = i / 3, c = i - 3 * j;
     y[c * n + j] = sigma * A.rhs[(b * n + __ldg(A.iperm + j)) * 3 + c];
   }
-  if (tid == 0) s_bad = 0;
+  // the pivot flag lives beside the factor (slot 1 after sigma): a factor that failed keeps reporting so when reused
+  if (tid == 0) s_bad = A.reuse ? (int)fac[(int64_t)n * W + 1] : 0;
   __syncthreads();
 
   if (!A.reuse) {
@@ -83,7 +84,10 @@ __global__ void __launch_bounds__(kThreads) chol_band_kernel(CholArgs A) {
       __syncthreads();
     }
     for (int i = tid; i < n * W; i += kThreads) fac[i] = a[i];
-    if (tid == 0) fac[(int64_t)n * W] = sigma;
+    if (tid == 0) {
+      fac[(int64_t)n * W] = sigma;
+      fac[(int64_t)n * W + 1] = (double)s_bad;
+    }
   }
 
   // solves: warp c handles rhs column c (3 warps), column-oriented forward, row-oriented backward

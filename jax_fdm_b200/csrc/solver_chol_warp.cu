@@ -948,6 +948,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   auto iperm_of = [&](int v) { return tw ? A.h[half_of(v)].iperm : A.iperm; };
   auto rows_in = [&](int v) { return tw ? A.h[half_of(v)].rows : n; };
   auto issue = [&](int v) {  // one 8 KB bulk copy: the 32 factor columns of the visit's block into buffer v&1
+    FDM_ASSERT(gblock_of(v) >= 0 && gblock_of(v) < nblk, "visit %d -> factor block %d of %d (role %d)", v, gblock_of(v), nblk, role);
     if (lane == 0) {
       uint64_t* bar = bars + (v & 1);
       mbar_expect_tx(bar, 32 * 256);
@@ -995,6 +996,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
     for (int kb = 0; kb < 4; ++kb) {
       const int R = rows_of(v, kb);
       Qn[kb] = R < rows ? __ldg(ip + R) : -1;
+      FDM_ASSERT(R >= 0 && Qn[kb] >= -1 && Qn[kb] < n, "row %d -> free index %d of %d (visit %d, role %d)", R, Qn[kb], n, v, role);
     }
   };
   auto fetch_val = [&](int v) {   // uses Q = row indices of visit v

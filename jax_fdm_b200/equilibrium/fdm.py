@@ -52,7 +52,28 @@ def fdm(nodes, edges, supports, q, xyz_fixed, loads, sparse=True, tmax=1, eta=1e
     as_t = lambda a: a.to(dev, torch.float64) if isinstance(a, torch.Tensor) else \
         torch.as_tensor(np.asarray(a, dtype=np.float64), device=dev)
     params = EquilibriumParametersState(as_t(q), as_t(xyz_fixed), LoadState(as_t(loads), 0.0, 0.0))
-    return model(params, structure), structure
+    state = model(params, structure)
+    _check_equilibrium(state, structure)
+    return state, structure
+
+
+def _check_equilibrium(state, structure, rtol=1e-6):
+    """The front door fails LOUDLY where the kernels report through NaN or cannot certify: a solve whose status
+    was not OK (NaN positions: K singular, or indefinite -- mixed-sign q -- on a band too wide for the signed
+    factorisation, which the reference's pivoted LU would still solve), and a solution whose free-node residuals
+    are not small (the unpivoted signed factorisation of an indefinite K can lose accuracy without a flag).  One
+    device-to-host read; `fdm()` hands the state back to host code anyway."""
+    xyz = state.xyz.detach()
+    if not bool(torch.isfinite(xyz).all()):
+        raise FloatingPointError("fdm: the equilibrium solve failed (non-finite positions): K(q) is singular, or it is "
+                                 "indefinite (mixed-sign q) on a structure whose band is too wide for this build's signed "
+                                 "factorisation (half bandwidth > 30); the iterative solvers need a definite K")
+    free = torch.as_tensor(structure.indices_free, device=xyz.device)
+    res = state.residuals.detach().index_select(-2, free).abs().amax()
+    scale = torch.maximum(state.loads.detach().abs().amax(), (state.forces.detach().abs().amax()))
+    if float(res) > rtol * max(float(scale), 1e-300):
+        raise FloatingPointError(f"fdm: free-node residual {float(res):.3e} against loads / forces of {float(scale):.3e}: "
+                                 "the solve is inaccurate (indefinite K factored without pivoting?)")
 
 
 def constrained_fdm(nodes, edges, supports, q, xyz_fixed, loads, optimizer, loss, bounds=(None, None), maxiter=100,

@@ -178,3 +178,19 @@ def test_kbar_on_pattern_and_its_q_transpose_vs_dense_algebra():
     E = s.num_edges
     basis = np.stack([om.stiffness_matrix_sparse(np.eye(E)[e], so).data for e in range(E)])      # (E, nnz)
     assert np.allclose(qbar, Kbar @ basis.T, rtol=1e-13, atol=1e-13)
+
+
+def test_fdm_front_door_fails_loudly_on_an_unsolvable_system():
+    """Mixed-sign q on a band too wide for the signed factorisation: the kernels flag INDEFINITE and hand back NaN;
+    `fdm()` turns that into an exception instead of returning NaN positions (the reference's pivoted LU would solve
+    it; this build says so rather than guessing).  The same call with a definite q succeeds."""
+    import jax_fdm_b200.equilibrium as eq
+    prob = datasets.cablenet_problem(40, seed=1)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    assert s.half_bandwidth > 30
+    st, _ = eq.fdm(prob.nodes, prob.edges, prob.supports, prob.q, prob.xyz_fixed, prob.loads, structure=s)
+    assert bool(torch.isfinite(st.xyz).all())
+    q = prob.q.copy()
+    q[::3] *= -1.0
+    with pytest.raises(FloatingPointError):
+        eq.fdm(prob.nodes, prob.edges, prob.supports, q, prob.xyz_fixed, prob.loads, structure=s)

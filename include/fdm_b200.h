@@ -142,13 +142,20 @@ typedef struct fdm_solve_opts {
   int32_t check_every;  /* multi-kernel PCG: host polls convergence every this many iterations
                            (synchronises the stream; not graph-capturable); <=0 -> 50    */
   int32_t reuse_factor; /* Cholesky: nonzero -> d_ws already holds the factor of this K (adjoint
-                           solve after the forward solve, tmax>1 iterations): skip refactoring */
+                           solve after the forward solve, tmax>1 iterations): skip refactoring.
+                           2 (warp-per-design band Cholesky): ONE factor, in the first design's slot of a workspace
+                           sized for `batch` designs, serves every right-hand-side set of the batch (tangent /
+                           multi-rhs solves: same K, many right-hand sides) */
   int32_t stages;       /* batched Cholesky, measurement only: 0 = the whole solve; otherwise a mask of the
                            launches to issue (1 factorisation [+ its signed second pass], 2 diagonal-block inversion
                            [separate launch at half bandwidth 31 only], 4 substitution),
                            so that a benchmark can time each kernel of one solve on its own */
   int32_t nan_on_failure; /* nonzero: a design whose status is not FDM_STATUS_OK gets x = NaN (what the reference's
                            solvers hand to the optimiser's NaN check, optimizer.py:372-380); needs d_info */
+  int32_t concurrent_designs; /* batched Cholesky: designs in flight on the device including other streams' calls
+                           (a sliced batch: the whole batch); 0 = this call's batch.  Small batches take the
+                           two-sided factorisation (a warp pair per design: half the dependency chain), which only
+                           pays while SMs are short of warps */
 } fdm_solve_opts;
 
 size_t fdm_workspace_bytes(const fdm_plan* plan, int64_t batch, int32_t solver);
@@ -198,6 +205,15 @@ int fdm_state_vjp(const fdm_plan* plan, const double* d_q, const double* d_xyz,
                   const double* d_loads_cot, const double* d_vectors_cot,
                   double* d_q_bar, double* d_xyz_bar, double* d_loads_bar,
                   int64_t batch, int64_t q_stride, void* stream);
+
+/* JVP of fdm_state: tangents of vectors / lengths / forces / residuals for tangents (q_dot, xyz_dot, loads_dot) at
+ * the primal (q, xyz).  `batch` tangents; a primal stride of 0 shares one primal among them (jacfwd-style use: the
+ * reference forces the dense model for this, fdm.py:266-271).  q_dot, loads_dot may be NULL (= 0); any output may
+ * be NULL.  Strides in elements. */
+int fdm_state_jvp(const fdm_plan* plan, const double* d_q, const double* d_xyz, const double* d_q_dot,
+                  const double* d_xyz_dot, const double* d_loads_dot, double* d_vectors_dot, double* d_lengths_dot,
+                  double* d_forces_dot, double* d_residuals_dot, int64_t batch, int64_t q_stride, int64_t xyz_stride,
+                  int64_t q_dot_stride, int64_t loads_dot_stride, void* stream);
 
 /* ---- K3: gradients of the implicit solve ---------------------------------------------------
  * Replaces the tail of sparse_solve_bwd (sparse.py:299-308) plus the autodiff transposes of
@@ -326,6 +342,11 @@ int fdm_kbar_pattern(const fdm_plan* plan, const double* d_a, const double* d_b,
                      int64_t batch, void* stream);
 /* transpose of stiffness_matrix (models.py:1069-1077): q_bar (B,E) from Kbar.data (B,nnz); overwritten */
 int fdm_stiffness_vjp(const fdm_plan* plan, const double* d_Kbar_data, double* d_q_bar, int64_t batch, void* stream);
+
+/* out = a x + b y + c z over n doubles (y, z may be NULL; out may alias an input): the vector combinations the
+ * host-side rules need between kernels (tangent right-hand sides b_dot - K_dot x, fixed-point updates) */
+int fdm_lincomb(double* d_out, const double* d_x, const double* d_y, const double* d_z, double a, double b, double c,
+                int64_t n, void* stream);
 
 /* out[i] = sum_b in[b, i], fixed summation order: the local half of the two exchanges a sharded batch has (the
  * scalar loss, n = 1, and the gradient of a parameter shared by all designs), before the NCCL all-reduce. */

@@ -28,11 +28,11 @@ SOLVERS = {"auto": 0, "pcg": 1, "pcg_persistent": 2, "cholesky": 3}
 EXPORTS = [
     "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",
     "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_solve_from_q", "fdm_spmm",
-    "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_adjoint_grads", "fdm_edge_loads",
+    "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_state_jvp", "fdm_adjoint_grads", "fdm_edge_loads",
     "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_goals_loss", "fdm_loss_sqdist",
     "fdm_fa_create", "fdm_fa_destroy", "fdm_fa_set_constants", "fdm_fa_set_goal_program", "fdm_fa_set_q",
     "fdm_fa_step_device", "fdm_fa_enqueue_host", "fdm_fa_enqueue_copies_only", "fdm_fa_wait", "fdm_fa_run_host", "fdm_fa_device_array", "fdm_fa_info",
-    "fdm_host_alloc", "fdm_host_free", "fdm_batch_sum", "fdm_kbar_pattern", "fdm_stiffness_vjp",
+    "fdm_host_alloc", "fdm_host_free", "fdm_batch_sum", "fdm_lincomb", "fdm_kbar_pattern", "fdm_stiffness_vjp",
     "fdm_last_error", "fdm_version",
 ]
 
@@ -40,7 +40,7 @@ EXPORTS = [
 class SolveOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("max_iters", C.c_int32), ("tol", C.c_double),
                 ("check_every", C.c_int32), ("reuse_factor", C.c_int32), ("stages", C.c_int32),
-                ("nan_on_failure", C.c_int32)]
+                ("nan_on_failure", C.c_int32), ("concurrent_designs", C.c_int32)]
 
 
 class FaOpts(C.Structure):
@@ -111,6 +111,8 @@ def lib():
     L.fdm_state.restype = C.c_int
     L.fdm_state_vjp.argtypes = [vp] + [vp] * 8 + [vp] * 3 + [i64, i64, vp]
     L.fdm_state_vjp.restype = C.c_int
+    L.fdm_state_jvp.argtypes = [vp] * 10 + [i64] * 5 + [vp]
+    L.fdm_state_jvp.restype = C.c_int
     L.fdm_adjoint_grads.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, C.c_int, vp]
     L.fdm_adjoint_grads.restype = C.c_int
     L.fdm_edge_loads.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, C.c_int, vp]
@@ -153,6 +155,8 @@ def lib():
     L.fdm_kbar_pattern.restype = C.c_int
     L.fdm_stiffness_vjp.argtypes = [vp, vp, vp, i64, vp]
     L.fdm_stiffness_vjp.restype = C.c_int
+    L.fdm_lincomb.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, C.c_double, i64, vp]
+    L.fdm_lincomb.restype = C.c_int
     L.fdm_batch_sum.argtypes = [vp, vp, i64, i64, vp]
     L.fdm_batch_sum.restype = C.c_int
     L.fdm_host_alloc.argtypes = [sz]

@@ -347,6 +347,19 @@ int fdm_state_vjp(const fdm_plan* p, const double* q, const double* xyz, const d
                           loads_bar, batch, qs, (cudaStream_t)stream);
 }
 
+int fdm_state_jvp(const fdm_plan* p, const double* q, const double* xyz, const double* q_dot, const double* xyz_dot,
+                  const double* loads_dot, double* vectors_dot, double* lengths_dot, double* forces_dot,
+                  double* residuals_dot, int64_t batch, int64_t q_stride, int64_t xyz_stride, int64_t q_dot_stride,
+                  int64_t loads_dot_stride, void* stream) {
+  if (!ready(p, "fdm_state_jvp")) return FDM_ERR_INVALID;
+  if (!q || !xyz || !xyz_dot || batch <= 0) {
+    fdm_set_error("fdm_state_jvp: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_state_jvp(p, q, xyz, q_dot, xyz_dot, loads_dot, vectors_dot, lengths_dot, forces_dot, residuals_dot, batch,
+                          q_stride, xyz_stride, q_dot_stride, loads_dot_stride, (cudaStream_t)stream);
+}
+
 int fdm_adjoint_grads(const fdm_plan* p, const double* q, const double* xyz, const double* lam,
                       double* q_bar, double* loads_bar, double* xs_bar, int64_t batch, int64_t qs,
                       int accumulate, void* stream) {
@@ -467,6 +480,15 @@ int fdm_stiffness_vjp(const fdm_plan* p, const double* Kbar, double* q_bar, int6
     return FDM_ERR_INVALID;
   }
   return launch_stiffness_vjp(p, Kbar, q_bar, batch, (cudaStream_t)stream);
+}
+
+int fdm_lincomb(double* out, const double* x, const double* y, const double* z, double a, double b, double c, int64_t n,
+                void* stream) {
+  if (!out || !x || n <= 0) {
+    fdm_set_error("fdm_lincomb: bad arguments");
+    return FDM_ERR_INVALID;
+  }
+  return launch_lincomb(out, x, y, z, a, b, c, n, (cudaStream_t)stream);
 }
 
 int fdm_batch_sum(const double* d_in, double* d_out, int64_t batch, int64_t n, void* stream) {

@@ -188,6 +188,56 @@ state_kernel(int E, int N, const int32_t* __restrict__ edge_nodes,
 }
 
 // ---------------------------------------------------------------------------------------
+// K4 forward mode (JVP of models.py:780-794): tangents of the state for tangents (q_dot, xyz_dot, loads_dot) at the
+// primal (q, xyz).  T tangents may share one primal (primal strides 0).
+//   per edge e=(t,h):  v = x_h - x_t, vd = xd_h - xd_t, l = |v|:  vectors_dot = vd, lengths_dot = v.vd / l,
+//                      forces_dot = q_dot l + q lengths_dot
+//   per node n:        residuals_dot_n = loads_dot_n - sum_inc [ q_dot_e (x_n - x_o) + q_e (xd_n - xd_o) ]
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+state_jvp_kernel(int E, int N, const int32_t* __restrict__ edge_nodes, const int32_t* __restrict__ ninc_ptr,
+                 const int32_t* __restrict__ ninc_edge, const int32_t* __restrict__ ninc_other,
+                 const double* __restrict__ q, const double* __restrict__ xyz, const double* __restrict__ q_dot,
+                 const double* __restrict__ xyz_dot, const double* __restrict__ loads_dot,
+                 double* __restrict__ vectors_dot, double* __restrict__ lengths_dot, double* __restrict__ forces_dot,
+                 double* __restrict__ residuals_dot, int64_t q_stride, int64_t xyz_stride, int64_t q_dot_stride,
+                 int64_t loads_dot_stride) {
+  const int64_t b = blockIdx.y;
+  const int t = blockIdx.x * kThreads + threadIdx.x;
+  q += b * q_stride;
+  xyz += b * xyz_stride;
+  if (q_dot) q_dot += b * q_dot_stride;
+  xyz_dot += b * (int64_t)N * 3;
+  if (t < E && (vectors_dot || lengths_dot || forces_dot)) {
+    const int2 th = __ldg(reinterpret_cast<const int2*>(edge_nodes) + t);
+    const double3 a = ld3(xyz, th.x), c = ld3(xyz, th.y), ad = ld3(xyz_dot, th.x), cd = ld3(xyz_dot, th.y);
+    const double3 v = make_double3(c.x - a.x, c.y - a.y, c.z - a.z);
+    const double3 vd = make_double3(cd.x - ad.x, cd.y - ad.y, cd.z - ad.z);
+    if (vectors_dot) st3(vectors_dot + b * (int64_t)E * 3, t, vd);
+    if (lengths_dot || forces_dot) {
+      const double len = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+      const double ld = (v.x * vd.x + v.y * vd.y + v.z * vd.z) / len;   // NaN on a zero-length edge, like jnp.linalg.norm's JVP
+      if (lengths_dot) lengths_dot[b * (int64_t)E + t] = ld;
+      if (forces_dot) forces_dot[b * (int64_t)E + t] = (q_dot ? __ldg(q_dot + t) : 0.0) * len + __ldg(q + t) * ld;
+    }
+  }
+  if (t < N && residuals_dot) {
+    const double3 xn = ld3(xyz, t), xdn = ld3(xyz_dot, t);
+    double3 r = loads_dot ? ld3(loads_dot + b * loads_dot_stride, t) : make_double3(0.0, 0.0, 0.0);
+    const int k0 = __ldg(ninc_ptr + t), k1 = __ldg(ninc_ptr + t + 1);
+    for (int k = k0; k < k1; ++k) {
+      const int e = __ldg(ninc_edge + k) >> 1, o = __ldg(ninc_other + k);
+      const double qe = __ldg(q + e), qd = q_dot ? __ldg(q_dot + e) : 0.0;
+      const double3 xo = ld3(xyz, o), xdo = ld3(xyz_dot, o);
+      r.x -= qd * (xn.x - xo.x) + qe * (xdn.x - xdo.x);
+      r.y -= qd * (xn.y - xo.y) + qe * (xdn.y - xdo.y);
+      r.z -= qd * (xn.z - xo.z) + qe * (xdn.z - xdo.z);
+    }
+    st3(residuals_dot + b * (int64_t)N * 3, t, r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // K4 reverse (autodiff transpose of models.py:780-794; SURVEY.md Appendix B "direct" terms)
 //   per edge e=(t,h):  v = x_h - x_t, l = |v|, Crb = rbar_h - rbar_t
 //       q_bar_e  = fbar_e * l - Crb . v
@@ -741,6 +791,19 @@ face_loads_vjp_nodes_kernel(int N, int F, int D, const int32_t* __restrict__ fac
 // ---------------------------------------------------------------------------------------
 // loss helper: g = x - x0, loss_b = 0.5 sum g^2   (one CTA per design, fixed-order reduction)
 // ---------------------------------------------------------------------------------------
+// out = a x + b y + c z (y, z optional), grid-stride: the few vector combinations the host-side rules need between
+// kernels (tangent right-hand sides, fixed-point adjoint updates) without leaving this library
+__global__ void __launch_bounds__(256) lincomb_kernel(double* __restrict__ out, const double* __restrict__ x,
+                                                       const double* __restrict__ y, const double* __restrict__ z, double a,
+                                                       double b, double c, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    double v = a * x[i];
+    if (y) v += b * y[i];
+    if (z) v += c * z[i];
+    out[i] = v;
+  }
+}
+
 // out[i] = sum_b in[b, i] in a fixed order (deterministic, launch-geometry independent): the local part of the
 // loss / shared-gradient all-reduce (distributed.py).  n == 1: one CTA, thread t adds b = t, t + T, ... then a
 // fixed tree; otherwise one thread per column, b ascending (coalesced across the warp).
@@ -860,6 +923,21 @@ int launch_state(const fdm_plan* p, const double* q, const double* xyz, const do
   return fdm_check_launch("state");
 }
 
+int launch_state_jvp(const fdm_plan* p, const double* q, const double* xyz, const double* q_dot, const double* xyz_dot,
+                     const double* loads_dot, double* vd, double* ld, double* fd, double* rd, int64_t batch, int64_t qs,
+                     int64_t xs, int64_t qds, int64_t lds, cudaStream_t st) {
+  const DeviceArrays& d = p->d;
+  const int64_t work = std::max(p->E, p->N);
+  FDM_BATCH_LOOP(batch, b0, nb) {
+    state_jvp_kernel<<<grid_for(work, nb), kThreads, 0, st>>>(
+        (int)p->E, (int)p->N, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, q + b0 * qs, xyz + b0 * xs,
+        q_dot ? q_dot + b0 * qds : nullptr, xyz_dot + b0 * p->N * 3, loads_dot ? loads_dot + b0 * lds : nullptr,
+        vd ? vd + b0 * p->E * 3 : nullptr, ld ? ld + b0 * p->E : nullptr, fd ? fd + b0 * p->E : nullptr,
+        rd ? rd + b0 * p->N * 3 : nullptr, qs, xs, qds, lds);
+  }
+  return fdm_check_launch("state_jvp");
+}
+
 int launch_state_vjp(const fdm_plan* p, const double* q, const double* xyz, const double* xyz_cot,
                      const double* rbar, const double* lbar, const double* fbar,
                      const double* loads_cot, const double* vbar, double* q_bar, double* xyz_bar,
@@ -971,6 +1049,13 @@ int launch_face_loads_vjp(const fdm_plan* p, const int32_t* faces, int64_t F, in
           vert_bar ? vert_bar + b0 * F * D * 3 : nullptr, xyz_bar + b0 * p->N * 3, local);
   }
   return fdm_check_launch("face_loads_vjp");
+}
+
+int launch_lincomb(double* out, const double* x, const double* y, const double* z, double a, double b, double c, int64_t n,
+                   cudaStream_t st) {
+  const int64_t blocks = std::min<int64_t>((n + 255) / 256, 148 * 16);
+  lincomb_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, x, y, z, a, b, c, n);
+  return fdm_check_launch("lincomb");
 }
 
 int launch_batch_sum(const double* in, double* out, int64_t batch, int64_t n, cudaStream_t st) {

@@ -57,6 +57,9 @@ int launch_positions(const fdm_plan* p, double* xf, double* xs, double* xyz, int
 int launch_state(const fdm_plan* p, const double* q, const double* xyz, const double* loads,
                  double* vectors, double* lengths, double* forces, double* residuals,
                  int64_t batch, int64_t qs, int64_t ls, cudaStream_t st);
+int launch_state_jvp(const fdm_plan* p, const double* q, const double* xyz, const double* q_dot, const double* xyz_dot,
+                     const double* loads_dot, double* vd, double* ld, double* fd, double* rd, int64_t batch, int64_t qs,
+                     int64_t xs, int64_t qds, int64_t lds, cudaStream_t st);
 int launch_state_vjp(const fdm_plan* p, const double* q, const double* xyz, const double* xyz_cot,
                      const double* rbar, const double* lbar, const double* fbar,
                      const double* loads_cot, const double* vbar, double* q_bar, double* xyz_bar,
@@ -86,6 +89,8 @@ int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const
 int launch_kbar_pattern(const fdm_plan* p, const double* a, const double* bvec, double* out, double sign, int64_t batch,
                         cudaStream_t st);
 int launch_stiffness_vjp(const fdm_plan* p, const double* Kbar, double* q_bar, int64_t batch, cudaStream_t st);
+int launch_lincomb(double* out, const double* x, const double* y, const double* z, double a, double b, double c, int64_t n,
+                   cudaStream_t st);
 int launch_batch_sum(const double* in, double* out, int64_t batch, int64_t n, cudaStream_t st);
 // x[b] = NaN for every design whose info status is not OK (fdm_solve_opts.nan_on_failure)
 int launch_nan_failed(const double* info, double* x, int64_t n_per_design, int64_t batch, cudaStream_t st);

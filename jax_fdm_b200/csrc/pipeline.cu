@@ -83,6 +83,7 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   so.max_iters = f->o.max_iters;
   so.tol = f->o.tol;
   so.nan_on_failure = 1;
+  so.concurrent_designs = (int32_t)std::min<int64_t>(f->B, 1 << 30);   // the slices run side by side
   if (f->fused) {
     rc = fdm_solve_from_q(p, f->q.at(o), f->xs.p, f->loads.p, f->x.at(o), f->info_f.at(o), c.ws, c.ws_bytes, B, E, 0, 0,
                           &so, st);

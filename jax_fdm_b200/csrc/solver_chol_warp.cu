@@ -87,6 +87,7 @@ struct WArgs {
   const int32_t *stage_ptr, *stage_ent;   // plan.band_stage_ptr and band_stage_kent (from K.data) or band_stage_eent (from q)
   const int32_t *row_diag, *row_sup, *row_node;   // plan.band_row_* (assembly in place)
   WHalf h[2];
+  int shared_factor;       // substitution kernel: one factor (workspace slot 0) for every right-hand-side set of the batch
   int sub_pair;            // substitution kernel: a warp pair per design (two-sided factor): T and B sweeps in parallel
   int twisted;             // two warps per design: warp 2k factors [T | M] top-down, warp 2k+1 factors B bottom-up
   int sigma_f, sigma_k;    // free index / position in K.data of the first diagonal entry (the sign of K)
@@ -883,14 +884,17 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-template <int NBL>  // column group k reaches row groups k+1 .. k+NBL
+// TWC: the instance that also understands two-sided factors (small batches); the one-sided instance keeps the
+// lean visit schedule the bandwidth-bound full batches run
+template <int NBL, bool TWC = false>  // column group k reaches row groups k+1 .. k+NBL
 __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // designs per CTA = warps per CTA (host's choice); A.sub_pair: a design is the warp pair (2k, 2k+1)
-  const int64_t b = A.sub_pair ? (int64_t)blockIdx.x * (blockDim.x >> 6) + (warp >> 1)
-                               : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (b >= A.batch || (A.sub_pair && warp >= (int)((blockDim.x >> 6) << 1))) return;
+  const bool pair = TWC && A.sub_pair;
+  const int64_t b = pair ? (int64_t)blockIdx.x * (blockDim.x >> 6) + (warp >> 1)
+                         : (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (b >= A.batch || (pair && warp >= (int)((blockDim.x >> 6) << 1))) return;
   double* fsb = smem + warp * kSubWarpSmem;   // two staged blocks
   double* zt1 = fsb + 2 * 32 * kSS;
   double* zt2 = zt1 + 64;
@@ -900,19 +904,25 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
   const int g = lane >> 2, m = lane & 3;
   const int n = A.n, nblk = A.nblk;
   const double* rhs = A.rhs + b * (int64_t)n * 3;
-  double* fac = A.ws + b * A.ws_stride;
-  double* ysol = fac + (int64_t)nblk * 1024;
-  const double* meta = ysol + (int64_t)nblk * 128;
+  // A.shared_factor (opts.reuse_factor == 2): every right-hand-side set of the batch is solved with the ONE factor
+  // in slot 0 of the workspace (a tangent / multi-rhs solve: same K, many right-hand sides); each set keeps its own
+  // intermediate vector in its own slot
+  double* fac = A.ws + (A.shared_factor ? 0 : b * A.ws_stride);
+  double* ysol = A.ws + b * A.ws_stride + (int64_t)nblk * 1024;
+  const double* dsign = fac + (int64_t)nblk * 1024;        // D of L D L^T lives with the factor (slot 3 of ITS records)
+  const double* meta = fac + (int64_t)nblk * (1024 + 128);
   const double sigma = meta[0];
-  const int bad = (int)meta[1];
+  // a two-sided factor met by the one-sided instance (the two calls of a solve disagreed on the batch in flight) is
+  // reported as a breakdown rather than read wrongly
+  const int bad = !TWC && meta[3] != 0.0 ? 2 : (int)meta[1];
   const bool sgn = meta[2] != 0.0;                        // sigma*K = L D L^T: D in slot 3 of the intermediate rhs
   // Two-sided factor (meta[3], written by the factor kernel): half 0 = [T | M] in blocks 0 .. nbT, half 1 = B
   // bottom-up in the blocks after them.  One warp (role 0): forward T, forward B, forward M; backward M, T, B; the
   // running right-hand side of M after T is set aside while B runs and B's part (reversed numbering) is added to
   // it; x_M is handed to B's backward sweep the same way.  A warp pair (roles 1 = top, 2 = bottom) runs the T and B
   // sweeps side by side and meets on M through the partner's shared-memory ring and two named barriers.
-  const bool tw = NBL >= 3 && meta[3] != 0.0;
-  int role = A.sub_pair ? 1 + (warp & 1) : 0;
+  const bool tw = TWC && NBL >= 3 && meta[3] != 0.0;
+  int role = pair ? 1 + (warp & 1) : 0;
   if (role && !tw) {                                       // paired launch on a one-sided factor: the first warp does it all
     if (role == 2) return;
     role = 0;
@@ -1116,7 +1126,7 @@ __global__ void __launch_bounds__(kSubThreads, 1) chol_subst_kernel(WArgs A) {
           if (m < 2) *reinterpret_cast<double2*>(ysol + (int64_t)(j0 + cb + g) * 4 + 2 * m) = make_double2(z0, z1);
         } else {                                           // stored as D z (slot 3 keeps D): the backward sweep starts from it
           double* zo = ysol + (int64_t)(j0 + cb + g) * 4;
-          const double dk = zo[3];
+          const double dk = dsign[(int64_t)(j0 + cb + g) * 4 + 3];
           if (m == 0) *reinterpret_cast<double2*>(zo) = make_double2(dk * z0, dk * z1);
           if (m == 1) zo[2] = dk * z0;
         }
@@ -1266,6 +1276,7 @@ inline void fill_halves(WArgs& A, const fdm_plan* p, bool from_q) {
   }
   A.twisted = 0;
   A.sub_pair = 0;
+  A.shared_factor = 0;
   A.num_edges = (int)p->E; A.num_nodes = (int)p->N; A.num_fixed = (int)p->Ns;
   A.sigma_f = p->band_iperm.empty() ? 0 : p->band_iperm[0];
   A.sigma_k = p->band_rowkidx.empty() ? 0 : p->band_rowkidx[0];
@@ -1315,11 +1326,15 @@ static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, vo
 // The substitution launch.  Small batches whose factor is two-sided get a warp pair per design (the T and B sweeps
 // side by side); the predicate is the factor kernel's own, so both calls of a solve agree (the kernel falls back to
 // one warp when the stored factor turns out one-sided).
-static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st) {
+static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStream_t st, int64_t inflight) {
+  // a shared factor (opts.reuse_factor == 2) was laid out by an earlier call with ITS batch: take the instance that
+  // reads either layout
+  const bool twc = mma_panel4(p) && (use_twisted(p, inflight) || (A.shared_factor && use_twisted(p, 1)));   // `batch`: designs in flight (fdm_solve_opts.concurrent_designs)   // the factor of this batch may be two-sided
   void (*skern)(WArgs) = p->hbw <= 7 ? chol_subst_kernel<1> : p->hbw <= 15 ? chol_subst_kernel<2>
-                       : p->hbw <= 23 ? chol_subst_kernel<3> : chol_subst_kernel<4>;
+                       : p->hbw <= 23 ? (twc ? chol_subst_kernel<3, true> : chol_subst_kernel<3>)
+                                      : (twc ? chol_subst_kernel<4, true> : chol_subst_kernel<4>);
   static const bool no_pair = std::getenv("FDM_CHOL_SUBPAIR") && std::atoi(std::getenv("FDM_CHOL_SUBPAIR")) == 0;
-  A.sub_pair = mma_panel4(p) && use_twisted(p, batch) && !no_pair ? 1 : 0;
+  A.sub_pair = twc && !no_pair ? 1 : 0;
   int sw = sub_warps_per_cta();
   if (A.sub_pair) sw = std::max(2, sw & ~1);
   const int dpc = A.sub_pair ? sw / 2 : sw;                // designs per CTA
@@ -1345,7 +1360,8 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   A.q = q; A.xs = xs; A.loads = loads;
   A.q_stride = qs; A.xs_stride = xss; A.loads_stride = ls;
   A.nan_fail = o.nan_on_failure;
-  A.twisted = mma_panel4(p) && use_twisted(p, batch) ? 1 : 0;
+  const int64_t inflight = std::max<int64_t>(batch, o.concurrent_designs);
+  A.twisted = mma_panel4(p) && use_twisted(p, inflight) ? 1 : 0;
   const int stages = o.stages ? o.stages : 7;
   int fw = mma_warps_per_cta();
   if (A.twisted) fw = std::max(2, fw & ~1);                // a design is a warp pair
@@ -1363,7 +1379,7 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
     skern<<<(unsigned)((batch + dpc - 1) / dpc), fw * 32, smem, st>>>(A);
   }
   if (stages & 4) {
-    int rc = launch_backward(p, A, batch, st);
+    int rc = launch_backward(p, A, batch, st, inflight);
     if (rc != FDM_OK) return rc;
   }
   return fdm_check_launch("chol_warp_solve_from_q");
@@ -1402,6 +1418,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   A.stage_ptr = p->d.band_stage_ptr; A.stage_ent = p->d.band_stage_kent;
   A.row_diag = A.row_sup = A.row_node = nullptr;
   fill_halves(A, p, false);
+  A.shared_factor = o.reuse_factor == 2 ? 1 : 0;
   void (*fkern)(WArgs) = nullptr;
   void (*skern)(WArgs) = nullptr;
   if (p->hbw <= 7) { fkern = chol_factor_kernel<7>; skern = chol_subst_kernel<1>; }
@@ -1417,7 +1434,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     if (mma) {
       fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, false> : chol_factor_mma_kernel<false, 2, false>;
       fw = mma_warps_per_cta();
-      A.twisted = mma_panel4(p) && use_twisted(p, batch) ? 1 : 0;
+      A.twisted = mma_panel4(p) && use_twisted(p, std::max<int64_t>(batch, o.concurrent_designs)) ? 1 : 0;
       if (A.twisted) fw = std::max(2, fw & ~1);
       dpc = A.twisted ? fw / 2 : fw;
       if (A.twisted) fkern = chol_factor_mma_kernel<false, 4, false, true>;
@@ -1437,7 +1454,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     chol_invdiag_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(A);
   }
   if (stages & 4) {
-    int rc = launch_backward(p, A, batch, st);
+    int rc = launch_backward(p, A, batch, st, std::max<int64_t>(batch, o.concurrent_designs));
     if (rc != FDM_OK) return rc;
   }
   return fdm_check_launch("chol_warp_solve");

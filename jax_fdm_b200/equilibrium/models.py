@@ -424,24 +424,61 @@ class EquilibriumModel:
         """
         Forward-mode rule of the linear FDM step: returns (x_free, x_free_dot) with
             K x_dot = b_dot - K_dot x,   K_dot = K(q_dot)  (K is linear in q),
-            b_dot = loads_dot_f - C_f^T (q_dot * C_s x_s) - C_f^T (q * C_s x_s_dot),
-        one extra 3-rhs solve with the factor / coarse inverse of the primal solve.  The reference has
-        no such rule: its sparse solve is reverse-only (sparse.py:1), which is why constraints
-        (constrained.py:88, jacfwd) and Hessians force the dense model (fdm.py:266-271).
+            b_dot = loads_dot_f - C_f^T (q_dot * C_s x_s) - C_f^T (q * C_s x_s_dot).
+        The tangents may carry a leading axis T (T tangents at ONE primal, what `jacfwd` vmaps): the T tangent
+        solves are more right-hand sides of the SAME factor -- one batched substitution launch on the band Cholesky
+        (opts.reuse_factor = 2), a loop that reuses the coarse inverse on the iterative solvers.  The reference has
+        no such rule: its sparse solve is reverse-only (sparse.py:1), which is why constraints (constrained.py:88,
+        jacfwd) and Hessians force the dense model (fdm.py:266-271).
         """
         s = structure
-        zero_like = torch.zeros_like
-        q_dot = zero_like(q) if q_dot is None else q_dot
-        xyz_fixed_dot = zero_like(xyz_fixed) if xyz_fixed_dot is None else xyz_fixed_dot
-        loads_dot = zero_like(loads) if loads_dot is None else loads_dot
+        T = 0                                                              # 0: a single, unbatched tangent
+        for d, base_rank in ((q_dot, 1), (xyz_fixed_dot, 2), (loads_dot, 2)):
+            if d is not None and d.dim() > base_rank:
+                T = max(T, int(d.shape[0]))
+        lead = (T,) if T else ()
+        zeros = lambda *shape: torch.zeros(lead + shape, dtype=q.dtype, device=q.device)
+        q_dot = zeros(s.num_edges) if q_dot is None else q_dot
+        loads_dot = zeros(s.num_nodes, 3) if loads_dot is None else loads_dot
         opts = {k: v for k, v in self.solve_opts.items() if k != "fused_assembly"}
         K, rhs = ops.assemble(s, q, xyz_fixed, loads)
         ws = ops.Workspace()
+        ws.reserve(s, max(T, 1), opts.get("solver", "auto"), q.device)
         x = ops.solve(s, K, rhs, workspace=ws, **opts)
-        K_dot, b1 = ops.assemble(s, q_dot, xyz_fixed, loads_dot)           # loads_dot_f - C_f^T (q_dot * C_s x_s)
-        _, b2 = ops.assemble(s, q, xyz_fixed_dot, zero_like(loads), want_K=False)   # - C_f^T (q * C_s x_s_dot)
-        x_dot = ops.solve(s, K, (b1 + b2 - ops.spmm(s, K_dot, x)).contiguous(), workspace=ws, reuse_factor=True, **opts)
+        K_dot, b_dot = ops.assemble(s, q_dot, xyz_fixed, loads_dot)        # loads_dot_f - C_f^T (q_dot * C_s x_s)
+        b2 = None
+        if xyz_fixed_dot is not None:                                      # - C_f^T (q * C_s x_s_dot)
+            _, b2 = ops.assemble(s, q, xyz_fixed_dot, torch.zeros_like(loads), want_K=False)
+        rhs_dot = ops.lincomb(b_dot, ops.spmm(s, K_dot, x), b2, 1.0, -1.0, 1.0)
+        if T and s.half_bandwidth <= 31:
+            x_dot = ops.solve(s, K, rhs_dot, workspace=ws, reuse_factor=2, **{**opts, "solver": "cholesky"})
+        elif T:
+            x_dot = torch.stack([ops.solve(s, K, rhs_dot[t], workspace=ws, reuse_factor=True, **opts) for t in range(T)])
+        else:
+            x_dot = ops.solve(s, K, rhs_dot, workspace=ws, reuse_factor=True, **opts)
         return x, x_dot
+
+    def jvp(self, params, structure, q_dot=None, xyz_fixed_dot=None, loads_dot=None):
+        """
+        Forward mode through `__call__` for the linear model (tmax = 1, nodal loads): (state, state_dot), the
+        tangents of every field of the equilibrium state for tangents of q, xyz_fixed and the nodal loads -- T of
+        them at once with a leading axis on the tangents (`jax.jvp` / `jax.jacfwd` of `model(params, structure)`).
+        """
+        if self.tmax > 1:
+            raise NotImplementedError("forward mode is built for the linear model (tmax = 1)")
+        q, xyz_fixed, load_state = params
+        loads = load_state.nodes if isinstance(load_state, LoadState) else load_state
+        s = structure
+        x, x_dot = self.nodes_free_positions_jvp(q, xyz_fixed, loads, s, q_dot, xyz_fixed_dot, loads_dot)
+        xyz = ops.positions(s, x, xyz_fixed)
+        xs_dot = xyz_fixed_dot if xyz_fixed_dot is not None else \
+            torch.zeros(x_dot.shape[:-2] + (s.num_supports, 3), dtype=q.dtype, device=q.device)
+        xyz_dot = ops.positions(s, x_dot, xs_dot)
+        v, l, f, r = ops.state(s, q, xyz, loads)
+        vd, ld, fd, rd = ops.state_jvp(s, q, xyz, xyz_dot, q_dot=q_dot, loads_dot=loads_dot)
+        zero_loads = torch.zeros_like(xyz_dot) if loads_dot is None else loads_dot
+        return (EquilibriumState(xyz=xyz, residuals=r, lengths=l, forces=f, loads=loads, vectors=v),
+                EquilibriumState(xyz=xyz_dot, residuals=rd, lengths=ld, forces=fd, loads=zero_loads, vectors=vd))
 
     def nodes_equilibrium(self, q, xyz_fixed, loads_nodes, structure):
         return self.nodes_free_positions(q, xyz_fixed, loads_nodes, structure)

@@ -95,6 +95,11 @@ class Workspace:
     def __init__(self):
         self.buf = None
 
+    def reserve(self, structure, batch, solver, device):
+        """Size the buffer for `batch` designs up front: a later call with more right-hand-side sets than the call
+        that factored (reuse_factor=2: one factor, many right-hand sides) must not reallocate the factor away."""
+        return self.get(structure, batch, L.SOLVERS[solver] if isinstance(solver, str) else int(solver), device)
+
     def get(self, structure, batch, solver, device):
         need = int(L.lib().fdm_workspace_bytes(structure.plan, batch, solver))
         if self.buf is None or self.buf.numel() < need or self.buf.device != device:
@@ -130,7 +135,7 @@ def solve(structure, Kdata, rhs, solver="auto", tol=0.0, max_iters=0, reuse_fact
     sid = L.SOLVERS[solver] if isinstance(solver, str) else int(solver)
     ws = workspace if workspace is not None else Workspace()
     buf, need = ws.get(s, B, sid, rhs.device)
-    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(bool(reuse_factor)), int(stages),
+    opts = L.SolveOpts(sid, int(max_iters), float(tol), int(check_every), int(reuse_factor), int(stages),
                        int(bool(nan_on_failure)))                 # the NaN select happens in the solve's own kernels
     L.check(L.lib().fdm_solve(s.plan, _ptr(Kdata), _ptr(rhs), _ptr(x), _ptr(info), _ptr(buf),
                               buf.numel(), B, C.byref(opts), _stream()))
@@ -283,6 +288,41 @@ def state_vjp(structure, q, xyz, xyz_cot=None, residuals_cot=None, lengths_cot=N
     L.check(L.lib().fdm_state_vjp(s.plan, _ptr(q), _ptr(xyz), *[_ptr(c) for c in cots],
                                   _ptr(q_bar), _ptr(xyz_bar), _ptr(loads_bar), B, E, _stream()))
     return q_bar, xyz_bar, loads_bar
+
+
+def lincomb(x, y=None, z=None, a=1.0, b=1.0, c=1.0, out=None):
+    """out = a x + b y + c z (fdm_lincomb): elementwise combinations between kernels, in this library."""
+    x = x.contiguous()
+    out = torch.empty_like(x) if out is None else out
+    _tls.device = x.device
+    L.check(L.lib().fdm_lincomb(_ptr(out), _ptr(x), _ptr(None if y is None else y.contiguous()),
+                                _ptr(None if z is None else z.contiguous()), float(a), float(b), float(c), x.numel(), _stream()))
+    return out
+
+
+def state_jvp(structure, q, xyz, xyz_dot, q_dot=None, loads_dot=None):
+    """JVP of `state` (fdm_state_jvp) -> (vectors_dot, lengths_dot, forces_dot, residuals_dot) for T tangents (leading
+    axis of xyz_dot) at ONE primal (q (E,), xyz (N,3)) or at T primals."""
+    s = structure
+    E, N = s.num_edges, s.num_nodes
+    q = _chk(q, "q", (E,))
+    xyz = _chk(xyz, "xyz", (N, 3))
+    xyz_dot = _chk(xyz_dot, "xyz_dot", (N, 3))
+    q_dot = None if q_dot is None else _chk(q_dot, "q_dot", (E,))
+    loads_dot = None if loads_dot is None else _chk(loads_dot, "loads_dot", (N, 3))
+    T, batched = _resolve_batch((xyz_dot, 2), (q_dot, 1), (loads_dot, 2))
+    if batched and xyz_dot.dim() == 2:
+        xyz_dot = xyz_dot.expand(T, N, 3).contiguous()
+    lead = (T,) if batched else ()
+    dev = xyz.device
+    vd = torch.empty(lead + (E, 3), dtype=F64, device=dev)
+    ld = torch.empty(lead + (E, 1), dtype=F64, device=dev)
+    fd = torch.empty(lead + (E, 1), dtype=F64, device=dev)
+    rd = torch.empty(lead + (N, 3), dtype=F64, device=dev)
+    L.check(L.lib().fdm_state_jvp(s.plan, _ptr(q), _ptr(xyz), _ptr(q_dot), _ptr(xyz_dot), _ptr(loads_dot), _ptr(vd), _ptr(ld),
+                                  _ptr(fd), _ptr(rd), T, _stride(q, 1), _stride(xyz, 2), 0 if q_dot is None else _stride(q_dot, 1),
+                                  0 if loads_dot is None else _stride(loads_dot, 2), _stream()))
+    return vd, ld, fd, rd
 
 
 def adjoint_grads(structure, q, xyz, lam, q_bar=None, loads_bar=None, xyz_fixed_bar=None):

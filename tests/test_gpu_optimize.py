@@ -128,10 +128,10 @@ def test_inverse_design_over_q_supports_and_loads():
     val, grad = problem.fun(x0)
     assert abs(val - f(x0)) <= 1e-12 * abs(val)
     scale = np.abs(grad).max()
+    from conftest import fd5
     for k in rng.choice(x0.size, size=15, replace=False):
-        d = np.zeros_like(x0); d[k] = 1e-6
-        fd = (f(x0 + d) - f(x0 - d)) / 2e-6
-        assert abs(grad[k] - fd) <= 1e-6 * scale + 1e-10, (k, grad[k], fd)
+        fd = fd5(f, x0, k)
+        assert abs(grad[k] - fd) <= 1e-8 * scale + 1e-11, (k, grad[k], fd)
     x = opt.solve(problem)
     assert opt.result.fun <= 0.05 * val
     lo = np.array([b[0] for b in problem.bounds]); hi = np.array([b[1] for b in problem.bounds])
@@ -175,10 +175,9 @@ def test_liew_dome_inverse_design_steps():
     assert abs(val - f(x0)) <= 1e-10 * abs(val)
     rng = np.random.default_rng(0)
     scale = np.abs(grad).max()
+    from conftest import fd5
     for k in rng.choice(x0.size, size=8, replace=False):
-        h = 1e-6 * max(1.0, abs(x0[k]))
-        d = np.zeros_like(x0); d[k] = h
-        fd = (f(x0 + d) - f(x0 - d)) / (2 * h)
-        assert abs(grad[k] - fd) <= 1e-5 * scale + 1e-10, (k, grad[k], fd)
+        fd = fd5(f, x0, k)
+        assert abs(grad[k] - fd) <= 1e-8 * scale + 1e-11, (k, grad[k], fd)
     opt.solve(problem)
     assert opt.result.fun <= 0.5 * val

@@ -397,6 +397,39 @@ int fdm_fa_device_array(fdm_fa* fa, int which, void** d_out, int64_t* per_design
 enum { FDM_FA_INFO_CHUNKS = 0, FDM_FA_INFO_LAUNCHES = 1, FDM_FA_INFO_FUSED_ASSEMBLY = 2, FDM_FA_INFO_GRAPH = 3,
        FDM_FA_INFO_BATCH = 4 };
 int64_t fdm_fa_info(const fdm_fa* fa, int which);   /* LAUNCHES: kernels per step (0 before the first step) */
+/* ---- tmax > 1: the fixed point and its implicit adjoint as device-resident loops -------------------
+ * Replaces equilibrium_iterative_xyz + solver_forward (models.py:512-618, solvers/fixed_point.py:139-198) and the
+ * adjoint system of fixed_point_bwd_adjoint (fixed_point.py:501-604) for ONE design on the band Cholesky (half
+ * bandwidth <= 31; else FDM_ERR_UNSUPPORTED and the caller iterates from the host):
+ *     forward   x <- K^{-1} P(x),  P(x) = nodes_load(xyz(x))[free] - R_fixed,  until mean_n |x_prev - x|_2 <= eta
+ *     adjoint   w <- x_bar + J_P^T K^{-1} w   until max |w_new - w| <= adjoint_tol * max |x_bar|;   lam = K^{-1} w
+ * Each loop is one CUDA graph with a conditional WHILE node whose condition a kernel sets on the device: no host
+ * synchronisation per iteration.  K is factored once per forward call and the factor serves every iteration of
+ * both loops.  The object keeps the converged geometry between fdm_fp_forward and fdm_fp_adjoint.
+ * Mesh arrays (face loads): device int32, as fdm_face_loads / fdm_face_loads_vjp take them; NULL without faces. */
+typedef struct fdm_fp fdm_fp;
+typedef struct fdm_fp_opts {
+  int32_t tmax;               /* <= 0 -> 100 (models.py:77)                               */
+  int32_t is_load_local;      /* edge / face loads given in the element frames            */
+  int32_t adjoint_max_iters;  /* <= 0 -> 200                                              */
+  double eta;                 /* <= 0 -> 1e-6                                             */
+  double adjoint_tol;         /* <= 0 -> 1e-12                                            */
+} fdm_fp_opts;
+int fdm_fp_create(const fdm_plan* plan, const fdm_fp_opts* opts, int has_edges_load, const int32_t* d_faces,
+                  int64_t num_faces, int64_t max_deg, const int32_t* d_edges_faces, const int32_t* d_faces_edges,
+                  const int32_t* d_node_faces_ptr, const int32_t* d_node_faces, fdm_fp** out);   /* allocates; synchronous */
+void fdm_fp_destroy(fdm_fp* fp);
+/* d_x_init (Nf,3) or NULL (= the linear step with the nodal loads); d_x_free (Nf,3) out; d_loads_out (N,3) or NULL:
+ * the nodal loads at the converged geometry.  Asynchronous on `stream`. */
+int fdm_fp_forward(fdm_fp* fp, const double* d_q, const double* d_xyz_fixed, const double* d_loads_nodes,
+                   const double* d_edges_load, const double* d_faces_load, const double* d_x_init, double* d_x_free,
+                   double* d_loads_out, void* stream);
+/* after fdm_fp_forward: d_x_bar (Nf,3) -> d_w (Nf,3, may be NULL), d_lam (Nf,3).  Asynchronous on `stream`. */
+int fdm_fp_adjoint(fdm_fp* fp, const double* d_x_bar, double* d_w, double* d_lam, void* stream);
+/* h_out5: forward steps (solver_forward's count), last forward distance, adjoint iterations, last adjoint change,
+ * status of the last substitution.  Synchronises `stream`. */
+int fdm_fp_info(fdm_fp* fp, double* h_out5, void* stream);
+
 /* page-locked host memory for the end-to-end calls */
 void* fdm_host_alloc(size_t bytes);
 void fdm_host_free(void* p);

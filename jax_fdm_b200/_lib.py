@@ -32,6 +32,7 @@ EXPORTS = [
     "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_goals_loss", "fdm_loss_sqdist",
     "fdm_fa_create", "fdm_fa_destroy", "fdm_fa_set_constants", "fdm_fa_set_goal_program", "fdm_fa_set_q",
     "fdm_fa_step_device", "fdm_fa_enqueue_host", "fdm_fa_enqueue_copies_only", "fdm_fa_wait", "fdm_fa_run_host", "fdm_fa_device_array", "fdm_fa_info",
+    "fdm_fp_create", "fdm_fp_destroy", "fdm_fp_forward", "fdm_fp_adjoint", "fdm_fp_info",
     "fdm_host_alloc", "fdm_host_free", "fdm_batch_sum", "fdm_lincomb", "fdm_kbar_pattern", "fdm_stiffness_vjp",
     "fdm_last_error", "fdm_version",
 ]
@@ -41,6 +42,12 @@ class SolveOpts(C.Structure):
     _fields_ = [("solver", C.c_int32), ("max_iters", C.c_int32), ("tol", C.c_double),
                 ("check_every", C.c_int32), ("reuse_factor", C.c_int32), ("stages", C.c_int32),
                 ("nan_on_failure", C.c_int32), ("concurrent_designs", C.c_int32)]
+
+
+class FpOpts(C.Structure):
+    """fdm_fp_opts (include/fdm_b200.h)."""
+    _fields_ = [("tmax", C.c_int32), ("is_load_local", C.c_int32), ("adjoint_max_iters", C.c_int32), ("eta", C.c_double),
+                ("adjoint_tol", C.c_double)]
 
 
 class FaOpts(C.Structure):
@@ -159,6 +166,16 @@ def lib():
     L.fdm_lincomb.restype = C.c_int
     L.fdm_batch_sum.argtypes = [vp, vp, i64, i64, vp]
     L.fdm_batch_sum.restype = C.c_int
+    L.fdm_fp_create.argtypes = [vp, C.POINTER(FpOpts), C.c_int, vp, i64, i64, vp, vp, vp, vp, C.POINTER(vp)]
+    L.fdm_fp_create.restype = C.c_int
+    L.fdm_fp_destroy.argtypes = [vp]
+    L.fdm_fp_destroy.restype = None
+    L.fdm_fp_forward.argtypes = [vp] * 9 + [vp]
+    L.fdm_fp_forward.restype = C.c_int
+    L.fdm_fp_adjoint.argtypes = [vp, vp, vp, vp, vp]
+    L.fdm_fp_adjoint.restype = C.c_int
+    L.fdm_fp_info.argtypes = [vp, vp, vp]
+    L.fdm_fp_info.restype = C.c_int
     L.fdm_host_alloc.argtypes = [sz]
     L.fdm_host_alloc.restype = vp
     L.fdm_host_free.argtypes = [vp]

@@ -40,6 +40,7 @@ struct Buf {
 
 struct fdm_fa {
   const fdm_plan* plan = nullptr;
+  int device = 0;          // kept here: the plan may be gone by the time the object is destroyed
   int64_t B = 0;
   fdm_fa_opts o{};
   bool fused = false, capturable = true, has_prog = false;
@@ -198,7 +199,7 @@ int capture_chunks(fdm_fa* f) {
 
 void destroy(fdm_fa* f) {
   if (!f) return;
-  if (f->plan && f->plan->on_device) cudaSetDevice(f->plan->device);
+  cudaSetDevice(f->device);
   for (Chunk& c : f->chunks) {
     if (c.st) cudaStreamSynchronize(c.st);
     if (c.exec) cudaGraphExecDestroy(c.exec);
@@ -240,6 +241,7 @@ int fdm_fa_create(const fdm_plan* p, int64_t batch, const fdm_fa_opts* opts, fdm
   fdm_fa* f = new (std::nothrow) fdm_fa();
   if (!f) return FDM_ERR_INVALID;
   f->plan = p;
+  f->device = p->device;
   f->B = batch;
   if (opts) f->o = *opts;
   else { f->o.with_state = 1; f->o.use_graph = 1; }

@@ -212,6 +212,102 @@ class _FacesLoad(torch.autograd.Function):
         return xb, g, fb, None, None
 
 
+class _LazyCount:
+    """The iteration count of a device-resident loop: stays on the device until somebody looks (comparison, int(),
+    printing), so running the model never synchronises for it."""
+
+    def __init__(self, read):
+        self._read, self._value = read, None
+
+    def __int__(self):
+        if self._value is None:
+            self._value = int(self._read())
+        return self._value
+
+    __index__ = __int__
+
+    def __repr__(self):
+        return str(int(self))
+
+    def __eq__(self, other):
+        return int(self) == other
+
+    def __lt__(self, other):
+        return int(self) < other
+
+    def __le__(self, other):
+        return int(self) <= other
+
+    def __gt__(self, other):
+        return int(self) > other
+
+    def __ge__(self, other):
+        return int(self) >= other
+
+
+class _NativeLoops:
+    """One `fdm_fp` object (csrc/fixed_point.cu): both loops of the tmax > 1 equilibrium as CUDA graphs with a
+    conditional WHILE node.  Pooled per structure and configuration; an object is busy from a forward call until its
+    backward has run (it keeps the factor and the converged geometry in between)."""
+
+    def __init__(self, structure, key, has_edges, has_faces, device):
+        import ctypes as C
+        from .. import _lib as L
+        tmax, eta, local = key[:3]
+        self.lib, self.L, self.C = L.lib(), L, C
+        self.handle = C.c_void_p()
+        self.busy = False
+        opts = L.FpOpts(int(tmax), int(bool(local)), 0, float(eta), 0.0)
+        mesh = [None, 0, 0, None, None, None, None]
+        if has_faces:
+            d = structure.device_arrays(device)
+            self._mesh_keepalive = d
+            P = lambda t: C.c_void_p(t.data_ptr())
+            mesh = [P(d["faces"]), structure.num_faces, structure.faces_indexed.shape[1], P(d["edges_faces"]),
+                    P(d["faces_edges"]), P(d["node_faces_ptr"]), P(d["node_faces"])]
+        L.check(self.lib.fdm_fp_create(structure.plan, C.byref(opts), int(has_edges), *mesh, C.byref(self.handle)))
+
+    def __del__(self):
+        try:
+            if self.handle.value:
+                self.lib.fdm_fp_destroy(self.handle)
+                self.handle = self.C.c_void_p()
+        except Exception:
+            pass
+
+    @staticmethod
+    def acquire(structure, key, has_edges, has_faces, device):
+        pool = structure.__dict__.setdefault("_fp_pool", {}).setdefault((key, has_edges, has_faces, str(device)), [])
+        for obj in pool:
+            if not obj.busy:
+                obj.busy = True
+                return obj
+        obj = _NativeLoops(structure, key, has_edges, has_faces, device)
+        obj.busy = True
+        pool.append(obj)
+        return obj
+
+    def info(self, stream):
+        import numpy as np
+        out = np.zeros(5)
+        self.L.check(self.lib.fdm_fp_info(self.handle, out.ctypes.data, stream))
+        return out
+
+
+class _Lease:
+    """Frees a pooled loop object when the autograd context that used it goes away."""
+
+    def __init__(self, obj):
+        self.obj = obj
+
+    def release(self):
+        if self.obj is not None:
+            self.obj.busy = False
+            self.obj = None
+
+    __del__ = release
+
+
 class _FixedPoint(torch.autograd.Function):
     """
     x* = K(q)^{-1} P(x*),  P(x) = nodes_load(xyz(x))[free] - R_fixed(q, x_s): the fixed-point
@@ -222,65 +318,100 @@ class _FixedPoint(torch.autograd.Function):
     """
 
     @staticmethod
+    def _native_ok(q, x_init, structure, opts, config):
+        """The device-resident loops serve one design on the band Cholesky with the default fixed-point solver."""
+        return (q.dim() == 1 and x_init.dim() == 2 and q.is_cuda and config.get("solver") in (None, solver_forward)
+                and opts.get("solver", "auto") in ("auto", "cholesky") and structure.half_bandwidth <= 31
+                and not config.get("verbose"))
+
+    @staticmethod
     def forward(ctx, q, xyz_fixed, loads_nodes, edges_load, faces_load, x_init, structure, opts, config):
         s = structure
-        K, rhs0 = ops.assemble(s, q, xyz_fixed, torch.zeros_like(loads_nodes))     # rhs0 = -R_fixed
-        ws = ops.Workspace()
-        first = [True]
         local = bool(config.get("is_load_local", False))
+        has_faces = faces_load.numel() > 0
+        host = {}                                           # the host-driven loop's pieces, built on first use
 
         def solve_fn(b):
-            x = ops.solve(s, K, b.contiguous(), workspace=ws, reuse_factor=not first[0], **opts)
-            first[0] = False
+            if "K" not in host:
+                host["K"], host["rhs0"] = ops.assemble(s, q, xyz_fixed, torch.zeros_like(loads_nodes))   # rhs0 = -R_fixed
+                host["ws"], host["first"] = ops.Workspace(), True
+            x = ops.solve(s, host["K"], b.contiguous(), workspace=host["ws"], reuse_factor=not host["first"], **opts)
+            host["first"] = False
             return x
-
-        free = torch.as_tensor(s.indices_free, device=q.device)
-
-        has_faces = faces_load.numel() > 0
 
         def f(_, x):
             xyz = ops.positions(s, x, xyz_fixed)
             loads = ops.edge_loads(s, xyz, loads_nodes, edges_load, is_local=local)
             if has_faces:
                 loads, _ = ops.face_loads(s, xyz, loads, faces_load, is_local=local)
-            return solve_fn(loads.index_select(-2, free) + rhs0)
+            if "K" not in host:
+                host["K"], host["rhs0"] = ops.assemble(s, q, xyz_fixed, torch.zeros_like(loads_nodes))   # rhs0 = -R_fixed
+                host["ws"], host["first"] = ops.Workspace(), True
+            return solve_fn(ops.lincomb(ops.positions_vjp(s, loads.contiguous())[0], host["rhs0"]))
+
+        ctx.native = None
+        if _FixedPoint._native_ok(q, x_init, s, opts, config):
+            import ctypes as C
+            key = (int(config["tmax"]), float(config["eta"]), local)
+            loops = _NativeLoops.acquire(s, key, True, has_faces, q.device)
+            ctx.native, ctx.lease = loops, _Lease(loops)
+
+            def device_loop(x0, cfg):
+                P = lambda t: C.c_void_p(t.data_ptr())
+                st = C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+                x = torch.empty_like(x0)
+                args = [t.contiguous() for t in (q, xyz_fixed, loads_nodes, edges_load, faces_load, x0)]
+                loops.L.check(loops.lib.fdm_fp_forward(loops.handle, P(args[0]), P(args[1]), P(args[2]), P(args[3]),
+                                                       P(args[4]) if has_faces else None, P(args[5]), P(x), None, st))
+                cfg["steps"] = _LazyCount(lambda: loops.info(st)[0])
+                return x
+            f.device_loop = device_loop
 
         x = solver_fixedpoint_implicit(config.get("solver"), config, f, None, x_init)
-        ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces, ctx.local = s, solve_fn, free, has_faces, local
+        ctx.structure, ctx.solve_fn, ctx.has_faces, ctx.local = s, solve_fn, has_faces, local
         ctx.save_for_backward(q, xyz_fixed, edges_load, faces_load, x)
         return x
 
     @staticmethod
     def backward(ctx, g):
         q, xyz_fixed, edges_load, faces_load, x = ctx.saved_tensors
-        s, solve_fn, free, has_faces, local = ctx.structure, ctx.solve_fn, ctx.free, ctx.has_faces, ctx.local
+        s, solve_fn, has_faces, local = ctx.structure, ctx.solve_fn, ctx.has_faces, ctx.local
         xyz = ops.positions(s, x, xyz_fixed)
         aux = None
         if has_faces:   # centroids / global face loads of the converged geometry, needed by the face-load transpose
             _, aux = ops.face_loads(s, xyz, torch.zeros_like(xyz), faces_load, is_local=local)
 
-        def scatter_free(lam):
-            c = torch.zeros(lam.shape[:-2] + (s.num_nodes, 3), dtype=lam.dtype, device=lam.device)
-            c.index_copy_(-2, free, lam)
-            return c
-
         def loads_vjp_x(lam):                       # J_P^T lam, free rows
-            c = scatter_free(lam)
+            c = ops.positions(s, lam.contiguous(), torch.zeros_like(xyz_fixed))     # lam on the free rows, 0 on supports
             xb, _ = ops.edge_loads_vjp(s, xyz, edges_load, c, want_edges=False, is_local=local)
             if has_faces:
-                xb = xb + ops.face_loads_vjp(s, xyz, faces_load, aux, c, want_faces=False, is_local=local)[0]
-            return xb.index_select(-2, free)
+                xb = ops.lincomb(xb, ops.face_loads_vjp(s, xyz, faces_load, aux, c, want_faces=False, is_local=local)[0])
+            return ops.positions_vjp(s, xb)[0]
+
+        if ctx.native is not None:
+            import ctypes as C
+            loops = ctx.native
+
+            def device_adjoint(vec):                # the adjoint system as one graph launch (csrc/fixed_point.cu)
+                st = C.c_void_p(torch.cuda.current_stream(q.device).cuda_stream)
+                vec = vec.contiguous()
+                w, lam = torch.empty_like(x), torch.empty_like(x)
+                loops.L.check(loops.lib.fdm_fp_adjoint(loops.handle, C.c_void_p(vec.data_ptr()), C.c_void_p(w.data_ptr()),
+                                                       C.c_void_p(lam.data_ptr()), st))
+                return w, lam
+            solve_fn.device_adjoint = device_adjoint
 
         w, lam = fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, g.contiguous())
+        if ctx.native is not None:
+            ctx.lease.release()
         # cotangents of f(theta, x*) at w: K and R_fixed terms (K3), then the load terms
         qbar, pbar, xsbar = ops.adjoint_grads(s, q, xyz, lam)
         xb, ebar = ops.edge_loads_vjp(s, xyz, edges_load, pbar, is_local=local)
         fbar = None
         if has_faces:
             xb2, fbar = ops.face_loads_vjp(s, xyz, faces_load, aux, pbar, is_local=local)
-            xb = xb + xb2
-        fixed = torch.as_tensor(s.indices_fixed, device=q.device)
-        xsbar = xsbar + xb.index_select(-2, fixed)  # edge lengths / face areas at the supports depend on x_s
+            xb = ops.lincomb(xb, xb2)
+        xsbar = ops.lincomb(xsbar, ops.positions_vjp(s, xb)[1])   # edge lengths / face areas at the supports depend on x_s
         return qbar, xsbar, pbar, ebar, fbar, None, None, None, None
 
 

@@ -58,7 +58,7 @@ def solver_forward(f, a, x_init, solver_config):
     x_prev, x = x_init, f(a, x_init)
     steps = 0
     # the distance is a device scalar; one host read per iteration, as the reference's while_loop condition
-    while steps < tmax and float(torch.linalg.norm(x_prev - x, dim=-1).mean()) > eta:
+    while steps < tmax and float(torch.linalg.norm((x_prev - x).detach(), dim=-1).mean()) > eta:
         x_prev, x = x, f(a, x)
         steps += 1
     solver_config["steps"] = steps
@@ -71,6 +71,9 @@ def fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, vec, tol=1e-12, max_iters=200
     transposed iteration w <- vec + J_P^T K^{-1} w, and return (w, lam = K^{-1} w).
     `solve_fn(b)` = K^{-1} b with the forward factorisation; `loads_vjp_x(lam)` = J_P^T lam.
     """
+    device = getattr(solve_fn, "device_adjoint", None)
+    if device is not None:                                 # the same iteration as one CUDA graph (csrc/fixed_point.cu)
+        return device(vec)
     w = vec
     scale = float(vec.abs().max())
     lam = solve_fn(w)
@@ -85,7 +88,12 @@ def fixed_point_bwd_adjoint(solve_fn, loads_vjp_x, vec, tol=1e-12, max_iters=200
 
 
 def solver_fixedpoint_implicit(solver, solver_config, f, a, x_init):
-    """fixed_point.py:206-240: run `solver`; the implicit backward rule lives in models._FixedPoint."""
+    """fixed_point.py:206-240: run `solver`; the implicit backward rule lives in models._FixedPoint.  When the
+    iteration function carries a device-resident loop (`f.device_loop`: a CUDA graph with a conditional WHILE node,
+    csrc/fixed_point.cu) and the solver is the plain fixed-point iteration, that loop runs instead of the host's."""
+    device = getattr(f, "device_loop", None)
+    if device is not None and solver in (None, solver_forward):
+        return device(x_init, solver_config)
     return (solver or solver_forward)(f, a, x_init, solver_config)
 
 

@@ -248,6 +248,7 @@ class EquilibriumStructure(Graph):
 
     def __del__(self):
         try:
+            self.__dict__.pop("_fp_pool", None)            # loop objects built on this plan go first
             if getattr(self, "_plan", None) and self._plan.value:
                 L.lib().fdm_plan_destroy(self._plan)
                 self._plan = C.c_void_p()

@@ -369,3 +369,34 @@ def test_face_load_fixed_point_vs_reference_arrays(tag, local):
         r = g[f"{key}_state_{f}"]
         got = getattr(st, f).cpu().numpy().reshape(r.shape)
         assert np.abs(got - r).max() <= 1e-8 * max(1.0, np.abs(r).max()), f
+
+
+def test_device_resident_loops_are_pooled_and_match_the_host_driven_loops():
+    """The tmax > 1 equilibrium on the band Cholesky runs as two CUDA graphs with conditional WHILE nodes
+    (csrc/fixed_point.cu).  Two forwards before either backward must not share one loop object (it keeps the factor and
+    the converged geometry between the passes), and the result must match the host-driven loops of the iterative
+    solver path (same kernels, convergence read on the host every iteration)."""
+    import jax_fdm_b200.equilibrium as eq
+
+    prob, eload = problem(nx=6, seed=5)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    outs = {}
+    for solver in ("cholesky", "pcg"):                    # device-resident loops / host-driven loops
+        model = eq.EquilibriumModelSparse(tmax=200, eta=1e-13, solver=solver, tol=1e-14)
+        leaves, states = [], []
+        for scale in (1.0, 1.7):                          # two forwards, then two backwards
+            q, w = T(prob.q * scale, True), T(eload, True)
+            st = model(eq.EquilibriumParametersState(q, T(prob.xyz_fixed), eq.LoadState(T(prob.loads), w, 0.0)), s)
+            leaves.append((q, w))
+            states.append(st)
+        steps = model.last_solver_config["steps"]
+        for st in states:
+            (0.5 * (st.xyz ** 2).sum() + 0.1 * (st.lengths ** 2).sum()).backward()
+        assert int(steps) > 1
+        outs[solver] = [states[0].xyz.detach().cpu().numpy(), states[1].xyz.detach().cpu().numpy()] + \
+                       [t.grad.cpu().numpy() for pair in leaves for t in pair]
+    if True:
+        pool = s.__dict__["_fp_pool"]
+        assert sum(len(v) for v in pool.values()) == 2 and not any(o.busy for v in pool.values() for o in v)
+    for a, b in zip(outs["cholesky"], outs["pcg"]):
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(b).max(), 1e-300)

@@ -4,12 +4,26 @@ bench.py -- forward+adjoint FDM solves/s (BASELINE.json metric).
 
 Headline workload (config.workload): BASELINE config 5 -- a batch of 4096 synthetic 30x30
 pillow designs (841 free nodes, 1860 edges each, q_b = -2 + 0.1 (U-0.5), seed b), forward
-solve + adjoint + gradients of L_b = 1/2||x_free - x_free0||^2.  Designs are independent, so
+solve + state + adjoint + gradients of L_b = 1/2||x_free - x_free0||^2.  Designs are independent, so
 at N GPUs every rank owns 4096 designs (weak scaling, no data-path collective) and the scalar
-loss is all-reduced with NCCL; `config5_fixed_global_batch` additionally reports the fixed
-4096-design batch cut over the N ranks.  A "step" is one pass over a rank's batch.  The same
-JSON line carries `kernels` (every kernel of the step timed alone against the HBM roofline)
-and `single_mesh`: BASELINE config 4 (200x200 cable-net, one design), ms per forward+adjoint.
+loss is all-reduced with NCCL; `config5_fixed_global_batch` reports, at every N, BASELINE's fixed
+4096-design batch cut over the N ranks (strong scaling).  A "step" is one pass over a rank's batch.
+
+One JSON line.  Beside the contract keys it carries
+  value / ms_per_step      the device-resident step of the library-owned pipeline (fdm_fa_step_device), CUDA events
+  e2e                      the same through fdm_fa_run_host: pinned host q in, host loss + q_bar out, every step;
+                           + `copy_roofline` (the same copies without kernels: what the links deliver),
+                           `loss_only_readback`, `pipelined`
+  roofline                 the dominant kernel -- the factor kernel INSTANCE THE STEP LAUNCHES, timed alone through
+                           fdm_solve_from_q(stages = 1); `traffic` and `counters` from the committed ncu capture
+                           (profiles/ncu_counters.json); `strict`: SURVEY §8d's compulsory bytes only
+  step_roofline            SURVEY §8d's compulsory bytes of the whole step over the timed step
+  kernels                  every C-ABI call of the step timed alone (+ write-adjusted roofline, `stream_bandwidths`)
+  sweep_large_mesh         the HBM-bound kernels on one 2000x2000 mesh (working set far beyond L2)
+  api_path                 the public model API: EquilibriumModelSparse.__call__ + losses.Loss + .backward()
+  parity                   sampled designs of the timed batch against the CPU oracle (1e-10 / 1e-8)
+  single_mesh              BASELINE config 4 (200x200 cable-net, one design), ms per forward+adjoint
+  cpu_baseline             the oracle port on the host cores (N = 1)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun ... bench.py --gpus N ...          (N > 1: one rank per GPU)
@@ -18,8 +32,8 @@ Timing: W >= 3 warm-up steps; every timed step is bracketed by CUDA events on th
 stream; an L2 flush (write of a 256 MiB buffer) runs between timed steps, outside the events;
 barrier + synchronize on both sides of the timed region; max over ranks.
 `--impl reference` times the CPU restatement of the reference path (oracle/: scipy SuperLU
-forward + adjoint, exactly what sparse.py:147-149, 296 run) on the host cores -- jax is not
-installable in this image, so the oracle port is the reference arm.
+forward + adjoint, exactly what sparse.py:147-149, 296 run) on ALL 4096 designs per step on the host
+cores -- jax is not installable in this image, so the oracle port is the reference arm.
 """
 
 import argparse
@@ -220,6 +234,33 @@ def timed_steps(fn, stream, steps, flush, dist=None):
     return [a.elapsed_time(b) for a, b in ev]
 
 
+def stream_bandwidths(dev, stream):
+    """What this GPU moves for a pure WRITE stream and for a copy, measured here with torch fills / copies of 1 GiB
+    (CUDA events on `stream`): MEASURED_PEAKS.json's number is a copy (read + write).  Round 1 blamed the assembly
+    kernel's fraction on a write stream at half the copy rate; measured at this size the write stream is no slower
+    than the copy, so `frac_of_write_adjusted_roofline` (time >= max(all bytes / copy peak, written bytes / write
+    peak)) equals the plain fraction and the blame does not hold."""
+    import torch
+    n = 1 << 27                                               # 1 GiB of doubles
+    a = torch.empty(n, dtype=torch.float64, device=dev)
+    b = torch.empty(n, dtype=torch.float64, device=dev)
+    out = {}
+    with torch.cuda.stream(stream):
+        for name, fn, nbytes in (("write_gbs", lambda: a.fill_(1.0), 8 * n), ("copy_gbs", lambda: b.copy_(a), 16 * n)):
+            best = float("inf")
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                stream.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            out[name] = nbytes / (best * 1e-3) / 1e9
+    del a, b
+    torch.cuda.empty_cache()
+    return out
+
+
 def ncu_counters():
     """Counters of the dominant kernel from the committed ncu capture (profiles/ncu_counters.json, written by
     profiles/summarize.py from `ncu --set full` of the same instance the step launches)."""
@@ -240,7 +281,7 @@ def strict_bytes(s):
     return fwd + rev
 
 
-def kernel_table(pipe, s, B, steps, flush, hbm):
+def kernel_table(pipe, s, B, steps, flush, hbm, write_gbs=None):
     """Each C-ABI call of the step timed alone (CUDA events on pipe.stream, L2 flushed before every
     launch): algorithmic bytes per launch, time, achieved GB/s and fraction of the measured HBM peak."""
     import ctypes as C
@@ -252,6 +293,9 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
     fac = 8 * 1024 * ((Nf + 31) // 32)                       # factor columns, 32 doubles each, rows padded to 32
     Y = pipe.rhs.clone()
     stage_opts = {m: L.SolveOpts(pipe.solver_id, 0, 0.0, 0, 0, m, 0) for m in (1, 4)}
+    # bytes WRITTEN per design by each call (a mostly-writing kernel is bounded by the write stream, see stream_bandwidths)
+    written = {"assemble (K1)": 8 * nnz + 24 * Nf, "positions": 24 * N, "state (K4)": 40 * E + 24 * N,
+               "loss + cotangent": 24 * Nf + 8, "adjoint gradients (K3)": 8 * E + 24 * N + 24 * Ns, "SpMM K X (3 rhs)": 24 * Nf}
     calls = [
         ("assemble (K1)", 8 * E + 8 * nnz + 24 * Nf,
          lambda: lib.fdm_assemble(s.plan, P(pipe.q), P(pipe.xyz_fixed), P(pipe.loads), P(pipe.K), P(pipe.rhs), B, E, 0, 0, st)),
@@ -286,8 +330,14 @@ def kernel_table(pipe, s, B, steps, flush, hbm):
         ts = timed_steps(lambda: L.check(fn()), pipe.stream, steps, flush)
         ms = float(np.mean(ts))
         gbs = per_design * B / (ms * 1e-3) / 1e9
-        out.append({"kernel": name, "ms": ms, "algorithmic_bytes_per_launch": per_design * B,
-                    "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / hbm})
+        row = {"kernel": name, "ms": ms, "algorithmic_bytes_per_launch": per_design * B,
+               "achieved_gbs": gbs, "frac_of_measured_hbm": gbs / hbm}
+        if write_gbs and name in written:
+            # roofline with the write stream accounted for: time >= max(all bytes / copy peak, written bytes / write peak)
+            floor_ms = max(per_design * B / hbm, written[name] * B / write_gbs) / 1e6
+            row["write_bytes_per_launch"] = written[name] * B
+            row["frac_of_write_adjusted_roofline"] = floor_ms / ms
+        out.append(row)
     return out
 
 
@@ -463,6 +513,16 @@ def run_ours(args):
     e2e_fa.synchronize()
     t_pipelined = (time.perf_counter() - t0) * 1e3 / steps
     barrier()
+    # the same call when the gradient stays on the device (an optimiser on the GPU): only the losses come back
+    t_lossonly = []
+    for _ in range(steps):
+        flush_dev()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_fa.enqueue(want_q_bar=False)
+        e2e_fa.synchronize()
+        t_lossonly.append((time.perf_counter() - t0) * 1e3)
+    barrier()
     # what the link alone can do for this call: the same copies, same slices and streams, no kernels
     t_copy = []
     for _ in range(steps):
@@ -483,6 +543,7 @@ def run_ours(args):
     sum_dev = reduce_max(sum(t_dev))
     sum_e2e = reduce_max(sum(t_e2e))
     sum_copy = reduce_max(sum(t_copy))
+    sum_lossonly = reduce_max(sum(t_lossonly))
     t_pipelined = reduce_max(t_pipelined)
     dev_fa.step(main_stream)                              # leave the device arrays of a plain step for the checks below
     main_stream.synchronize()
@@ -569,7 +630,8 @@ def run_ours(args):
     pipe.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
     pipe.step()
     pipe.stream.synchronize()
-    kernels = kernel_table(pipe, s, B, max(3, min(steps, 10)), flush_on(pipe.stream), hbm)
+    streams = stream_bandwidths(dev, pipe.stream)
+    kernels = kernel_table(pipe, s, B, max(3, min(steps, 10)), flush_on(pipe.stream), hbm, streams["write_gbs"])
     del pipe
     torch.cuda.empty_cache()
 
@@ -607,7 +669,7 @@ def run_ours(args):
     e2e_ms = sum_e2e / steps
     e2e_value = B * world / (e2e_ms * 1e-3)
     copy_ms = sum_copy / steps
-    ctr = ncu_counters().get("chol_factor_mma_kernel<1,4,0>", {})
+    ctr = ncu_counters().get("chol_factor_mma_kernel<1,4,0,0>", {})   # <FROM_Q, PW, SIGNED, TW>: the one-sided instance of the step
     strict = strict_bytes(s)
     E, Nf = s.num_edges, s.num_free
     fac_strict = 8 * E + 24 * Nf                         # the factor kernel's compulsory share: q in (x out comes later)
@@ -636,6 +698,11 @@ def run_ours(args):
                                   "e2e_over_copy": e2e_ms / copy_ms,
                                   "how": "the same cudaMemcpyAsync calls (same slices, streams, pinned buffers) with no "
                                          "kernels between them, all ranks at once: what the host <-> device links deliver"},
+                "loss_only_readback": {"value": B * world / (sum_lossonly / steps * 1e-3), "unit": UNIT,
+                                       "ms_per_step": sum_lossonly / steps,
+                                       "d2h_bytes_per_step": e2e_fa.h_loss.size * 8 * world,
+                                       "how": "the same call with q_bar left on the device (h_q_bar = NULL): host q in, "
+                                              "per-design losses out"},
                 "pipelined": {"value": B * world / (t_pipelined * 1e-3), "unit": UNIT, "ms_per_step": t_pipelined,
                               "how": "the same K steps enqueued back to back and synchronised once: step k+1's copy-in "
                                      "overlaps step k's kernels and copy-out (independent batches; an optimiser loop "
@@ -664,6 +731,9 @@ def run_ours(args):
                           "note": "SURVEY.md §8d compulsory bytes of the whole forward + adjoint step (q in; x_free, xyz, "
                                   "state, loss, q_bar, loads_bar, xyz_fixed_bar out) over the timed step"},
         "kernels": kernels,
+        "stream_bandwidths": dict(streams, note="measured in this run (1 GiB fill / copy, best of 5); "
+                                                  "`frac_of_write_adjusted_roofline` in `kernels` = max(all bytes / copy "
+                                                  "peak, written bytes / write peak) / time"),
         "sweep_large_mesh": sweep,
         "config5_fixed_global_batch": fixed,
         "wall_s_timed_region": wall,

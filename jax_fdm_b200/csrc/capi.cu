@@ -24,7 +24,8 @@ void free_device(fdm_plan* p) {
   void* ptrs[] = {d.node_slot, d.edge_nodes, d.ninc_ptr, d.ninc_edge, d.ninc_other, d.free_node,
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
                   d.band_iperm, d.band_kidx, d.band_rowkidx, d.diags_ptr, d.diags_idx, d.sup_mask,
-                  d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent, d.band_row_diag, d.band_row_sup, d.band_row_node};
+                  d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent, d.band_row_diag, d.band_row_sup, d.band_row_node,
+                  d.asm_code, d.rsup_ptr, d.rsup_rows, d.rsup_edge, d.rsup_slot};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int h = 0; h < 2; ++h) {
@@ -42,6 +43,7 @@ int build_host(fdm_plan* p, const int64_t* edges, int64_t E, int64_t N, const in
   if (rc != FDM_OK) return rc;
   fdm_build_band_order(*p);
   fdm_build_twisted(*p);
+  fdm_check_assemble_batch(*p);
   fdm_build_partition(*p, num_parts);
   return FDM_OK;
 }
@@ -133,6 +135,11 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->diags_indptr, &q->d.diags_ptr); },
         [](fdm_plan* q) { return upload(q->diags_indices, &q->d.diags_idx); },
         [](fdm_plan* q) { return upload(q->sup_mask, &q->d.sup_mask); },
+        [](fdm_plan* q) { return upload(q->asm_code, &q->d.asm_code); },
+        [](fdm_plan* q) { return upload(q->rsup_ptr, &q->d.rsup_ptr); },
+        [](fdm_plan* q) { return upload(q->rsup_rows, &q->d.rsup_rows); },
+        [](fdm_plan* q) { return upload(q->rsup_edge, &q->d.rsup_edge); },
+        [](fdm_plan* q) { return upload(q->rsup_slot, &q->d.rsup_slot); },
     };
     for (auto f : steps) {
       rc = f(p);

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include "plan.h"
+#include <cstdlib>
+
 #include "launch.h"
 
 namespace {
@@ -120,6 +122,188 @@ assemble_kernel(int nnz, int Nf, int N, int Ns,
   if (rhs) {
     double* out = rhs + (b * (int64_t)Nf + r0) * 3;
     for (int i = tid; i < (r1 - r0) * 3; i += kThreads) out[i] = s_rhs[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1 for a BATCH of designs on one topology (the vmap of loss_plotter.py:98-103), as two streaming kernels.  The
+// per-design kernel above is bound by instruction issue and by its q gathers -- every stored entry is an 8-byte load
+// at a random place of the design's q, 32 sectors per warp request, behind a chain of index loads -- not by the
+// K.data it writes.  Here a CTA owns WHOLE designs, `dpc` of them one after another, and reads every index stream
+// once per launch.
+//
+// assemble_K_batch_kernel (K.data):
+//   * shared memory holds two regions [diag (Nf) | q (E) | 0.0], one per design in flight.  A design's q arrives as
+//     one coalesced asynchronous copy (cp.async) while the previous design is processed;
+//   * pass 1, a thread per row: the row's incident edges (<= 8, as byte offsets into the region, padded with the
+//     offset of the 0.0 slot; two 16-byte shared loads) -> the diagonal, summed in list order as `diags @ q` does,
+//     stored NEGATED in the region;
+//   * pass 2, a thread per stored entry: the entry's region offset sits in a REGISTER (NPT entries per thread, fixed
+//     for the whole launch); value = -region[offset] (-q on an off-diagonal, -(-sum) on the diagonal: negation is
+//     exact), stored in entry order: full-width stores, every byte of K.data written once.
+// assemble_rhs_batch_kernel (rhs): thread t owns the flat elements t, t + 512, ... of a design's (Nf, 3) rhs.  An
+//   element of a row without supports is load + 0.0 -- a register for the whole launch when all designs share the
+//   loads -- so the loop over designs is pure full-width stores; the few rows next to supports are compacted into
+//   (design, row, component) items, one thread each in CTAs of their own: load + sum of q_e * x_support in
+//   incidence order.
+// Same additions in the same order as assemble_kernel => bit-identical output (adding the +0.0 pads never changes a
+// sum that starts from +0.0).  Topologies that do not fit (plan: asm_batch_ok) keep the per-design kernel.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int4 lds_v4(uint32_t a) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double flip_sign(double v) {
+  return __hiloint2double(__double2hiint(v) ^ (int)0x80000000, __double2loint(v));
+}
+
+constexpr int kAsmNR = 4;                      // rows per thread: Nf <= 4 * 256
+constexpr int kAsmNS = 2;                      // supports per row the registers cover
+
+template <int NPT>
+__global__ void __launch_bounds__(kThreads, 3)
+assemble_K_batch_kernel(int E, int Nf, int nnz, int64_t batch, int dpc, const int32_t* __restrict__ asm_code,
+                        const int32_t* __restrict__ diags_ptr, const int32_t* __restrict__ diags_idx,
+                        const double* __restrict__ q, double* __restrict__ Kdata, int64_t q_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int NfP = (Nf + 1) & ~1;                                // q starts 16-byte aligned
+  const int region = NfP + ((E + 2) & ~1);                      // doubles per region: diag (| pad) | q | 0.0 (| pad)
+  double* s_reg = reinterpret_cast<double*>(smem_raw);          // [2][region]
+  int4* s_de = reinterpret_cast<int4*>(s_reg + 2 * region);     // [Nf][2]: eight byte offsets into a region
+  const int tid = threadIdx.x;
+  const int64_t b_lo = (int64_t)blockIdx.x * dpc, b_hi = min(batch, b_lo + dpc);
+  if (b_lo >= b_hi) return;
+  const uint32_t reg0 = (uint32_t)__cvta_generic_to_shared(s_reg);
+  const uint32_t de0 = (uint32_t)__cvta_generic_to_shared(s_de) + 32u * tid;
+  const bool vec = (E & 1) == 0 && (q_stride & 1) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0;
+  auto fetch_q = [&](int64_t b, int buf) {
+    const double* src = q + b * q_stride;
+    const uint32_t dst = reg0 + 8u * (buf * region + NfP);
+    if (vec) {
+      for (int i = tid; i < E / 2; i += kThreads)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 2 * i) : "memory");
+    } else {
+      for (int i = tid; i < E; i += kThreads)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * i), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch_q(b_lo, 0);
+  // ---- once per CTA: the index streams ----
+  const int zero_off = 8 * (NfP + E);
+  if (tid < 2) s_reg[tid * region + NfP + E] = 0.0;
+#pragma unroll
+  for (int i = 0; i < kAsmNR; ++i) {
+    const int r = tid + i * kThreads;
+    if (r < Nf) {
+      int o[8];
+      const int d0 = __ldg(diags_ptr + r), d1 = __ldg(diags_ptr + r + 1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = d0 + j < d1 ? 8 * (NfP + __ldg(diags_idx + d0 + j)) : zero_off;
+      s_de[2 * r] = make_int4(o[0], o[1], o[2], o[3]);
+      s_de[2 * r + 1] = make_int4(o[4], o[5], o[6], o[7]);
+    }
+  }
+  int off[NPT];                                                 // entry -> byte offset into a region, -1 past the end
+#pragma unroll
+  for (int u = 0; u < NPT; ++u) {
+    const int k = tid + u * kThreads;
+    off[u] = -1;
+    if (k < nnz) {
+      const int c = __ldg(asm_code + k);
+      off[u] = c >= 0 ? 8 * (NfP + c) : 8 * (-c - 2);
+    }
+  }
+  int buf = 0;
+  for (int64_t b = b_lo; b < b_hi; ++b, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();            // q of design b is in place for everyone; everyone is done with the other region
+    if (b + 1 < b_hi) fetch_q(b + 1, buf ^ 1);
+    const uint32_t rb = reg0 + 8u * (buf * region);
+#pragma unroll
+    for (int i = 0; i < kAsmNR; ++i) {
+      if (tid + i * kThreads < Nf) {
+        const int4 a = lds_v4(de0 + 32u * kThreads * i), c = lds_v4(de0 + 32u * kThreads * i + 16u);
+        const double q0 = lds_f64(rb + a.x), q1 = lds_f64(rb + a.y), q2 = lds_f64(rb + a.z), q3 = lds_f64(rb + a.w),
+                     q4 = lds_f64(rb + c.x), q5 = lds_f64(rb + c.y), q6 = lds_f64(rb + c.z), q7 = lds_f64(rb + c.w);
+        double acc = 0.0;
+        acc += q0; acc += q1; acc += q2; acc += q3; acc += q4; acc += q5; acc += q6; acc += q7;
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(rb + 8u * (tid + i * kThreads)), "d"(flip_sign(acc)) : "memory");
+      }
+    }
+    __syncthreads();            // the diagonals are in place
+    double* Kd = Kdata + b * (int64_t)nnz + tid;
+#pragma unroll
+    for (int u = 0; u < NPT; ++u)
+      if (off[u] >= 0) Kd[u * kThreads] = flip_sign(lds_f64(rb + off[u]));
+  }
+}
+
+// 512 threads.  The first `stream_ctas` CTAs stream: thread t owns the flat elements t, t + 512, ... (kRhsNE of them:
+// 3 Nf <= 3072) of `dpc` designs -- with shared loads (SHARED: loads_stride == 0) their loop over designs is stores
+// of registers only.  The other CTAs take the (design, support row, component) items, one per thread per trip, `dpp`
+// designs per CTA: short chains of index loads and gathers, hidden by the number of independent items.
+constexpr int kRhsThreads = 512;
+constexpr int kRhsNE = 6;
+
+template <bool SHARED>
+__global__ void __launch_bounds__(kRhsThreads, 2)
+assemble_rhs_batch_kernel(int Nf, int nsup_rows, int64_t batch, int dpc, int stream_ctas, int dpp,
+                          const int32_t* __restrict__ rsup_rows, const int32_t* __restrict__ rsup_ptr,
+                          const int32_t* __restrict__ rsup_edge, const int32_t* __restrict__ rsup_slot,
+                          const int32_t* __restrict__ free_node, const double* __restrict__ q,
+                          const double* __restrict__ xs, const double* __restrict__ loads, double* __restrict__ rhs,
+                          int64_t q_stride, int64_t xs_stride, int64_t loads_stride) {
+  const int tid = threadIdx.x;
+  const int n3 = 3 * Nf;
+  if ((int)blockIdx.x >= stream_ctas) {
+    const int npairs = 3 * nsup_rows;
+    const int64_t b0 = (int64_t)((int)blockIdx.x - stream_ctas) * dpp;
+    const int nb = (int)min((int64_t)dpp, batch - b0);
+    for (int it = tid; it < nb * npairs; it += kRhsThreads) {
+      const int db = it / npairs, pi = it - db * npairs;
+      const int64_t b = b0 + db;
+      const int r = __ldg(rsup_rows + pi / 3), c = pi % 3;
+      const int k0 = __ldg(rsup_ptr + r), k1 = __ldg(rsup_ptr + r + 1);
+      double acc = 0.0;
+      for (int k = k0; k < k1; ++k)
+        acc += __ldg(q + b * q_stride + __ldg(rsup_edge + k)) * __ldg(xs + b * xs_stride + 3 * __ldg(rsup_slot + k) + c);
+      rhs[b * (int64_t)n3 + 3 * r + c] = __ldg(loads + b * loads_stride + 3 * __ldg(free_node + r) + c) + acc;
+    }
+    return;
+  }
+  const int64_t b_lo = (int64_t)blockIdx.x * dpc, b_hi = min(batch, b_lo + dpc);
+  int src[kRhsNE];                        // element -> index into a design's loads; -1: no such element / a support row
+  double pv[kRhsNE];                      // load + 0.0, kept across designs when they share the loads
+#pragma unroll
+  for (int k = 0; k < kRhsNE; ++k) {
+    const int i = tid + k * kRhsThreads;
+    src[k] = -1;
+    pv[k] = 0.0;
+    if (i < n3) {
+      const int r = i / 3, c = i - 3 * r;
+      if (__ldg(rsup_ptr + r + 1) == __ldg(rsup_ptr + r)) {
+        src[k] = 3 * __ldg(free_node + r) + c;
+        if (SHARED) pv[k] = __ldg(loads + src[k]) + 0.0;
+      }
+    }
+  }
+  for (int64_t b = b_lo; b < b_hi; ++b) {
+    double* out = rhs + b * (int64_t)n3;
+    if (!SHARED) {
+#pragma unroll
+      for (int k = 0; k < kRhsNE; ++k)
+        if (src[k] >= 0) pv[k] = __ldg(loads + b * loads_stride + src[k]) + 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kRhsNE; ++k)
+      if (src[k] >= 0) out[tid + k * kRhsThreads] = pv[k];
   }
 }
 
@@ -888,6 +1072,38 @@ int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const 
                     cudaStream_t st) {
   const DeviceArrays& d = p->d;
   const unsigned tiles = (unsigned)((p->Nf + kAsmRows - 1) / kAsmRows);
+  // a batch on one topology: whole designs per CTA, index streams read once per launch (when the plan says it fits)
+  if (batch >= 8 && p->asm_batch_ok && !(std::getenv("FDM_ASM_BATCH") && std::atoi(std::getenv("FDM_ASM_BATCH")) == 0)) {
+    if (Kdata) {
+      const int smem = (int)p->asm_smem_bytes;
+      auto kern = p->nnz <= 8 * kThreads ? assemble_K_batch_kernel<8> : assemble_K_batch_kernel<16>;
+      FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      const int per_sm = std::max(1, std::min(3, (227 * 1024) / (smem + 1024)));        // resident CTAs per SM
+      const int64_t target = (int64_t)std::max(p->sm_count, 1) * per_sm;
+      int dpc = (int)std::max<int64_t>(1, (batch + target - 1) / target);
+      if (const char* e = std::getenv("FDM_ASM_DPC")) dpc = std::max(1, std::atoi(e));
+      kern<<<(unsigned)((batch + dpc - 1) / dpc), kThreads, smem, st>>>((int)p->E, (int)p->Nf, (int)p->nnz, batch, dpc,
+                                                                        d.asm_code, d.diags_ptr, d.diags_idx, q, Kdata, qs);
+      if (int rc = fdm_check_launch("assemble_K_batch")) return rc;
+    }
+    if (rhs) {
+      auto kern = ls == 0 ? assemble_rhs_batch_kernel<true> : assemble_rhs_batch_kernel<false>;
+      const int64_t target = (int64_t)std::max(p->sm_count, 1) * 2;
+      int dpc = (int)std::max<int64_t>(1, (batch + target - 1) / target);
+      if (const char* e = std::getenv("FDM_RHS_DPC")) dpc = std::max(1, std::atoi(e));
+      const int nsup = (int)p->rsup_rows.size();
+      // support-row items: about four trips of 512 per CTA
+      const int dpp = nsup ? std::max(1, (4 * kRhsThreads) / (3 * nsup)) : 1;
+      const unsigned stream_ctas = (unsigned)((batch + dpc - 1) / dpc);
+      unsigned pair_ctas = nsup ? (unsigned)((batch + dpp - 1) / dpp) : 0u;
+      if (std::getenv("FDM_RHS_NOPAIRS")) pair_ctas = 0;   // EXPERIMENT
+      kern<<<stream_ctas + pair_ctas, kRhsThreads, 0, st>>>((int)p->Nf, nsup, batch, dpc, (int)stream_ctas, dpp, d.rsup_rows,
+                                                            d.rsup_ptr, d.rsup_edge, d.rsup_slot, d.free_node, q, xs, loads,
+                                                            rhs, qs, xss, ls);
+      if (int rc = fdm_check_launch("assemble_rhs_batch")) return rc;
+    }
+    return FDM_OK;
+  }
   FDM_BATCH_LOOP(batch, b0, nb) {
     assemble_kernel<<<dim3(tiles, (unsigned)nb), kThreads, 0, st>>>(
         (int)p->nnz, (int)p->Nf, (int)p->N, (int)p->Ns, d.rowptr, d.entry_edge, d.diag_pos, d.free_node,

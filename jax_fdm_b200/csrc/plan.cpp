@@ -463,6 +463,41 @@ static void build_half_tables(const fdm_plan& p, const std::vector<int32_t>& vma
 }
 
 // Two-sided factorisation tables (four-column panel kernels only: hbw <= 29; at least two blocks per side).
+// Tables of the batched kernels.  assemble_K_batch_kernel (kernels_basic.cu) walks whole designs with one CTA: two
+// [diagonal | q] regions and the rows' incident-edge lists (<= 8 per row) live in shared memory, a thread's rows (<= 4)
+// and stored entries (<= 16) in registers; asm_smem_bytes <= 96 KB keeps two CTAs per SM.  assemble_rhs_batch_kernel
+// keeps a thread's <= 6 rhs elements in registers (the same Nf <= 1024).  spmm_batch_kernel keeps a row's columns
+// (<= 12) in registers.
+void fdm_check_assemble_batch(fdm_plan& p) {
+  p.asm_code.assign((size_t)p.nnz, -1);
+  for (int64_t r = 0; r < p.Nf; ++r)
+    for (int32_t k = p.index_indptr[r]; k < p.index_indptr[r + 1]; ++k)
+      p.asm_code[(size_t)k] = p.entry_edge[(size_t)k] >= 0 ? p.entry_edge[(size_t)k] : -(int32_t)r - 2;
+  p.rsup_ptr.assign((size_t)p.Nf + 1, 0);
+  p.rsup_rows.clear();
+  p.rsup_edge.clear();
+  p.rsup_slot.clear();
+  bool rows_ok = true;
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    const int32_t node = p.free_node[i];
+    for (int32_t k = p.ninc_ptr[node]; k < p.ninc_ptr[node + 1]; ++k) {
+      const int32_t slot = p.node_slot[p.ninc_other[k]];
+      if (slot < 0) {
+        p.rsup_edge.push_back(p.ninc_edge[k] >> 1);
+        p.rsup_slot.push_back(-slot - 1);
+      }
+    }
+    p.rsup_ptr[(size_t)i + 1] = (int32_t)p.rsup_edge.size();
+    if (p.rsup_ptr[(size_t)i + 1] > p.rsup_ptr[(size_t)i]) p.rsup_rows.push_back((int32_t)i);
+    if (p.diags_indptr[i + 1] - p.diags_indptr[i] > 8) rows_ok = false;
+  }
+  p.asm_smem_bytes = 16 * (((p.Nf + 1) & ~int64_t(1)) + ((p.E + 2) & ~int64_t(1))) + 32 * p.Nf + 16;
+  p.asm_batch_ok = rows_ok && p.Nf <= 4 * 256 && p.asm_smem_bytes <= 96 * 1024 && p.nnz <= 16 * 256;
+  p.spmm_batch_ok = true;
+  for (int64_t i = 0; i < p.Nf; ++i)
+    if (p.index_indptr[i + 1] - p.index_indptr[i] > 12) p.spmm_batch_ok = false;
+}
+
 void fdm_build_twisted(fdm_plan& p) {
   p.tw[0] = BandHalf();
   p.tw[1] = BandHalf();

@@ -23,6 +23,11 @@ struct DeviceArrays {
   int32_t* diags_ptr = nullptr;    // (Nf+1) = diags.indptr  (per free row: incident edges, ascending id)
   int32_t* diags_idx = nullptr;    // (dnnz) = diags.indices
   uint32_t* sup_mask = nullptr;    // (ceil(Nf/32)) bit r set: free row r has a support neighbour
+  int32_t* asm_code = nullptr;     // (nnz)  entry -> edge id, or -(row) - 2 on the diagonal      (assemble_design_kernel)
+  int32_t* rsup_ptr = nullptr;     // (Nf+1) per free row: its edges to supports, in incidence order
+  int32_t* rsup_rows = nullptr;    // the free rows that have at least one such edge
+  int32_t* rsup_edge = nullptr;    // (rsup) edge id
+  int32_t* rsup_slot = nullptr;    // (rsup) support slot (row of xyz_fixed)
   // band ordering (batched Cholesky)
   int32_t* band_perm = nullptr;    // (Nf) free index -> band position
   int32_t* band_iperm = nullptr;   // (Nf) band position -> free index
@@ -74,6 +79,7 @@ struct fdm_plan {
   std::vector<int32_t> node_slot, edge_nodes, ninc_ptr, ninc_edge, ninc_other;
   std::vector<int32_t> free_node, fixed_node, entry_edge, diag_pos;
   std::vector<uint32_t> sup_mask;
+  std::vector<int32_t> asm_code, rsup_ptr, rsup_rows, rsup_edge, rsup_slot;   // batched assembly (fdm_check_assemble_batch)
 
   // band ordering
   std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx;
@@ -81,6 +87,9 @@ struct fdm_plan {
   std::vector<int32_t> band_stage_ptr, band_stage_kent, band_stage_eent;
   std::vector<int32_t> band_row_diag, band_row_sup, band_row_node;
   int32_t hbw = 0;
+  bool spmm_batch_ok = false;  // every row has <= 12 stored entries (spmm_batch_kernel keeps a row's columns in registers)
+  bool asm_batch_ok = false;   // a design's q, diagonals and index streams fit one CTA's shared memory (asm_smem_bytes)
+  int64_t asm_smem_bytes = 0;
   BandHalf tw[2];         // empty when the two-sided factorisation does not apply (hbw > 29 or fewer than 5 blocks)
 
   // aggregates for the two-level preconditioner
@@ -98,3 +107,4 @@ int fdm_build_topology(fdm_plan& p, const int64_t* edges, int64_t E, int64_t N, 
 void fdm_build_band_order(fdm_plan& p);
 void fdm_build_partition(fdm_plan& p, int num_parts);
 void fdm_build_twisted(fdm_plan& p);
+void fdm_check_assemble_batch(fdm_plan& p);

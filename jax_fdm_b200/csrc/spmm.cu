@@ -13,6 +13,8 @@
 // Algorithmic bytes: 12 nnz + 52 Nf.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "launch.h"
 
 namespace {
@@ -151,11 +153,78 @@ spmm_tma_kernel(int Nf, const int32_t* __restrict__ rowptr, const int32_t* __res
   }
 }
 
+// The same product for a BATCH of designs on one topology: a thread owns one row of the tile and keeps its extent and
+// its column indices (<= kBatchRow, in registers) for the whole loop over `dpc` designs, two designs in flight at a
+// time.  A row's entries are consecutive in K.data, so the warp's loads of a design's values cover a contiguous
+// range with every sector used; X is gathered through the read-only path (a design's X is 20 KB); Y leaves as three
+// doubles per thread, contiguous across the warp.  No shared memory, no barrier.  Each row sums its entries in
+// ascending order in groups of four exactly as spmm_tma_kernel does => identical bits.
+constexpr int kBatchRow = 12;                         // entries per row the registers cover (rows are checked on the host)
+
+__global__ void __launch_bounds__(kThreads, 4)
+spmm_batch_kernel(int Nf, int64_t nnz, int64_t batch, int dpc, const int32_t* __restrict__ rowptr,
+                  const int32_t* __restrict__ colidx, const double* __restrict__ Kdata, const double* __restrict__ X,
+                  double* __restrict__ Y) {
+  const int r = blockIdx.x * kThreads + threadIdx.x;
+  if (r >= Nf) return;
+  const int a = __ldg(rowptr + r), len = __ldg(rowptr + r + 1) - a;
+  int c[kBatchRow];
+#pragma unroll
+  for (int j = 0; j < kBatchRow; ++j) c[j] = __ldg(colidx + a + (j < len ? j : 0));   // past the end: the first column, value 0
+  const int64_t b_lo = (int64_t)blockIdx.y * dpc, b_hi = min(batch, b_lo + dpc);
+  for (int64_t b = b_lo; b < b_hi; b += 2) {
+    const int64_t b1 = min(b + 1, b_hi - 1);
+    const double* K0 = Kdata + b * nnz + a;
+    const double* K1 = Kdata + b1 * nnz + a;
+    const double* X0 = X + b * (int64_t)Nf * 3;
+    const double* X1 = X + b1 * (int64_t)Nf * 3;
+    double s0[3] = {0.0, 0.0, 0.0}, s1[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < kBatchRow; k += 4) {
+      if (k >= len) break;
+      double v0[4], v1[4], x0[4][3], x1[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool in = k + u < len;
+        v0[u] = in ? __ldg(K0 + k + u) : 0.0;
+        v1[u] = in ? __ldg(K1 + k + u) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double* p0 = X0 + 3 * (int64_t)c[k + u];
+        const double* p1 = X1 + 3 * (int64_t)c[k + u];
+        x0[u][0] = __ldg(p0); x0[u][1] = __ldg(p0 + 1); x0[u][2] = __ldg(p0 + 2);
+        x1[u][0] = __ldg(p1); x1[u][1] = __ldg(p1 + 1); x1[u][2] = __ldg(p1 + 2);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s0[0] += v0[u] * x0[u][0]; s0[1] += v0[u] * x0[u][1]; s0[2] += v0[u] * x0[u][2];
+        s1[0] += v1[u] * x1[u][0]; s1[1] += v1[u] * x1[u][1]; s1[2] += v1[u] * x1[u][2];
+      }
+    }
+    double* y0 = Y + (b * (int64_t)Nf + r) * 3;
+    y0[0] = s0[0]; y0[1] = s0[1]; y0[2] = s0[2];
+    if (b + 1 < b_hi) {
+      double* y1 = Y + ((b + 1) * (int64_t)Nf + r) * 3;
+      y1[0] = s1[0]; y1[1] = s1[1]; y1[2] = s1[2];
+    }
+  }
+}
+
 }  // namespace
 
 int launch_spmm(const fdm_plan* p, const double* Kdata, const double* X, double* Y, int64_t batch,
                 cudaStream_t st) {
   const unsigned tiles = (unsigned)((p->Nf + kRowsPerCta - 1) / kRowsPerCta);
+  if (batch >= 8 && p->spmm_batch_ok && !(std::getenv("FDM_SPMM_BATCH") && std::atoi(std::getenv("FDM_SPMM_BATCH")) == 0)) {
+    // about eight resident waves of CTAs (4 per SM: the kernel's launch bound), each walking an even number of designs
+    const int64_t target = (int64_t)std::max(p->sm_count, 1) * 4 * 8;
+    int dpc = (int)std::min<int64_t>(64, std::max<int64_t>(2, 2 * ((batch * tiles + 2 * target - 1) / (2 * target))));
+    if (const char* e = std::getenv("FDM_SPMM_DPC")) dpc = std::max(2, std::atoi(e) & ~1);
+    spmm_batch_kernel<<<dim3(tiles, (unsigned)((batch + dpc - 1) / dpc)), kThreads, 0, st>>>(
+        (int)p->Nf, p->nnz, batch, dpc, p->d.rowptr, p->d.colidx, Kdata, X, Y);
+    return fdm_check_launch("spmm_batch");
+  }
   FDM_BATCH_LOOP(batch, b0, nb) {
     spmm_tma_kernel<<<dim3(tiles, (unsigned)nb), kThreads, 0, st>>>(
         (int)p->Nf, p->d.rowptr, p->d.colidx, Kdata + b0 * p->nnz, X + b0 * p->Nf * 3,

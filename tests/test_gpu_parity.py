@@ -267,3 +267,30 @@ def test_zero_rhs_column_and_errors(eq):
         eq.ops.solve(s, K.float(), rhs)
     with pytest.raises(ValueError):
         eq.ops.solve(s, K[:-1], rhs)
+
+
+@pytest.mark.parametrize("name", ["pillow30", "cablenet12", "liew_dome"])
+def test_batched_assembly_and_spmm_are_bit_identical_to_the_per_design_kernels(eq, name):
+    """A batch on one topology takes kernels that load the index streams once per CTA and stream the designs through
+    (assemble_batch_kernel, spmm_batch_kernel); a single design takes the per-design kernels.  Same additions in the
+    same order: the outputs must be the same bits, and K.data the reference's (ref_K_data) for the fixture's own q."""
+    g = load(name)
+    s, so = make(eq, g)
+    rng = np.random.default_rng(3)
+    B = 37
+    qb = g["q"][None, :] * (1.0 + 0.2 * rng.random((B, g["q"].size)))
+    qb[0] = g["q"]
+    xsb = g["xyz_fixed"][None] + 0.1 * rng.standard_normal((B,) + g["xyz_fixed"].shape)
+    pb = g["loads"][None] + 0.1 * rng.standard_normal((B,) + g["loads"].shape)
+    K, rhs = eq.ops.assemble(s, T(qb), T(xsb), T(pb))
+    assert np.array_equal(N(K)[0], oracle.stiffness_matrix_sparse(g["q"], so).data)
+    X = T(rng.standard_normal((B, s.num_free, 3)))
+    Y = eq.ops.spmm(s, K, X)
+    for b in (0, 1, 17, B - 1):
+        K1, rhs1 = eq.ops.assemble(s, T(qb[b]), T(xsb[b]), T(pb[b]))
+        assert torch.equal(K1, K[b]) and torch.equal(rhs1, rhs[b])
+        assert torch.equal(eq.ops.spmm(s, K1, X[b].contiguous()), Y[b])
+    # shared supports / loads (stride 0) through the batched kernel
+    K2, rhs2 = eq.ops.assemble(s, T(qb), T(g["xyz_fixed"]), T(g["loads"]))
+    K3, rhs3 = eq.ops.assemble(s, T(qb[5]), T(g["xyz_fixed"]), T(g["loads"]))
+    assert torch.equal(K2[5], K3) and torch.equal(rhs2[5], rhs3)

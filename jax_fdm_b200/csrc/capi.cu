@@ -25,7 +25,7 @@ void free_device(fdm_plan* p) {
                   d.fixed_node, d.rowptr, d.colidx, d.entry_edge, d.diag_pos, d.band_perm,
                   d.band_iperm, d.band_kidx, d.band_rowkidx, d.diags_ptr, d.diags_idx, d.sup_mask,
                   d.band_stage_ptr, d.band_stage_kent, d.band_stage_eent, d.band_row_diag, d.band_row_sup, d.band_row_node,
-                  d.asm_code, d.rsup_ptr, d.rsup_rows, d.rsup_edge, d.rsup_slot};
+                  d.asm_code, d.rsup_ptr, d.rsup_rows, d.rsup_edge, d.rsup_slot, d.rhs_src};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int h = 0; h < 2; ++h) {
@@ -138,6 +138,7 @@ int fdm_plan_create(const int64_t* h_edges, int64_t num_edges, int64_t num_nodes
         [](fdm_plan* q) { return upload(q->asm_code, &q->d.asm_code); },
         [](fdm_plan* q) { return upload(q->rsup_ptr, &q->d.rsup_ptr); },
         [](fdm_plan* q) { return upload(q->rsup_rows, &q->d.rsup_rows); },
+        [](fdm_plan* q) { return upload(q->rhs_src, &q->d.rhs_src); },
         [](fdm_plan* q) { return upload(q->rsup_edge, &q->d.rsup_edge); },
         [](fdm_plan* q) { return upload(q->rsup_slot, &q->d.rsup_slot); },
     };

@@ -126,11 +126,10 @@ assemble_kernel(int nnz, int Nf, int N, int Ns,
 }
 
 // ---------------------------------------------------------------------------------------
-// K1 for a BATCH of designs on one topology (the vmap of loss_plotter.py:98-103), as two streaming kernels.  The
+// K1 for a BATCH of designs on one topology (the vmap of loss_plotter.py:98-103), as streaming kernels.  The
 // per-design kernel above is bound by instruction issue and by its q gathers -- every stored entry is an 8-byte load
 // at a random place of the design's q, 32 sectors per warp request, behind a chain of index loads -- not by the
-// K.data it writes.  Here a CTA owns WHOLE designs, `dpc` of them one after another, and reads every index stream
-// once per launch.
+// K.data it writes.  Here a CTA owns WHOLE designs, one after another, and reads every index stream once per launch.
 //
 // assemble_K_batch_kernel (K.data):
 //   * shared memory holds two regions [diag (Nf) | q (E) | 0.0], one per design in flight.  A design's q arrives as
@@ -141,11 +140,10 @@ assemble_kernel(int nnz, int Nf, int N, int Ns,
 //   * pass 2, a thread per stored entry: the entry's region offset sits in a REGISTER (NPT entries per thread, fixed
 //     for the whole launch); value = -region[offset] (-q on an off-diagonal, -(-sum) on the diagonal: negation is
 //     exact), stored in entry order: full-width stores, every byte of K.data written once.
-// assemble_rhs_batch_kernel (rhs): thread t owns the flat elements t, t + 512, ... of a design's (Nf, 3) rhs.  An
-//   element of a row without supports is load + 0.0 -- a register for the whole launch when all designs share the
-//   loads -- so the loop over designs is pure full-width stores; the few rows next to supports are compacted into
-//   (design, row, component) items, one thread each in CTAs of their own: load + sum of q_e * x_support in
-//   incidence order.
+// rhs: an element of a row without supports is load + 0.0 -- registers for the whole launch when all designs share
+//   the loads -- so assemble_rhs_stream_kernel is full-width stores only; the few rows next to supports (load + sum
+//   of q_e * x_support in incidence order) are written afterwards by assemble_K_batch_kernel, which has q in shared
+//   memory, or by assemble_rhs_pairs_kernel.
 // Same additions in the same order as assemble_kernel => bit-identical output (adding the +0.0 pads never changes a
 // sum that starts from +0.0).  Topologies that do not fit (plan: asm_batch_ok) keep the per-design kernel.
 // ---------------------------------------------------------------------------------------
@@ -166,18 +164,28 @@ __device__ __forceinline__ double flip_sign(double v) {
 constexpr int kAsmNR = 4;                      // rows per thread: Nf <= 4 * 256
 constexpr int kAsmNS = 2;                      // supports per row the registers cover
 
-template <int NPT>
+// SUP: the CTA also writes the rhs rows next to supports (q is in shared memory here): thread t owns the t-th of them
+// (<= 256 such rows, <= kAsmNS supports per row; plan: asm_sup_in_K), indices in registers -- and the load and the
+// support coordinates too when all designs share them; the rhs has been filled before on the same stream.
+template <int NPT, bool SUP>
 __global__ void __launch_bounds__(kThreads, 3)
-assemble_K_batch_kernel(int E, int Nf, int nnz, int64_t batch, int dpc, const int32_t* __restrict__ asm_code,
+assemble_K_batch_kernel(int E, int Nf, int nnz, int maxdeg, int64_t batch, const int32_t* __restrict__ asm_code,
                         const int32_t* __restrict__ diags_ptr, const int32_t* __restrict__ diags_idx,
-                        const double* __restrict__ q, double* __restrict__ Kdata, int64_t q_stride) {
+                        const double* __restrict__ q, double* __restrict__ Kdata, int64_t q_stride, int nsup_rows,
+                        const int32_t* __restrict__ rsup_rows, const int32_t* __restrict__ rsup_ptr,
+                        const int32_t* __restrict__ rsup_edge, const int32_t* __restrict__ rsup_slot,
+                        const int32_t* __restrict__ free_node, const double* __restrict__ xs,
+                        const double* __restrict__ loads, double* __restrict__ rhs, int64_t xs_stride,
+                        int64_t loads_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int NfP = (Nf + 1) & ~1;                                // q starts 16-byte aligned
   const int region = NfP + ((E + 2) & ~1);                      // doubles per region: diag (| pad) | q | 0.0 (| pad)
   double* s_reg = reinterpret_cast<double*>(smem_raw);          // [2][region]
   int4* s_de = reinterpret_cast<int4*>(s_reg + 2 * region);     // [Nf][2]: eight byte offsets into a region
   const int tid = threadIdx.x;
-  const int64_t b_lo = (int64_t)blockIdx.x * dpc, b_hi = min(batch, b_lo + dpc);
+  // designs blockIdx.x, blockIdx.x + gridDim.x, ...: the grid is one resident wave, so every SM gets the same number
+  // of designs to within one
+  const int64_t b_lo = blockIdx.x, b_step = gridDim.x, b_hi = batch;
   if (b_lo >= b_hi) return;
   const uint32_t reg0 = (uint32_t)__cvta_generic_to_shared(s_reg);
   const uint32_t de0 = (uint32_t)__cvta_generic_to_shared(s_de) + 32u * tid;
@@ -220,20 +228,67 @@ assemble_K_batch_kernel(int E, int Nf, int nnz, int64_t batch, int dpc, const in
       off[u] = c >= 0 ? 8 * (NfP + c) : 8 * (-c - 2);
     }
   }
+  // the row next to supports this thread owns, if any: its place in the rhs, its node, its (q offset, support slot) terms
+  int srow = -1, snode = 0, pe[kAsmNS], ps[kAsmNS];
+  double3 xe[kAsmNS], pp = make_double3(0.0, 0.0, 0.0);
+  const bool sup_shared = xs_stride == 0 && loads_stride == 0;
+  if (SUP) {
+#pragma unroll
+    for (int j = 0; j < kAsmNS; ++j) { pe[j] = zero_off; ps[j] = -1; xe[j] = make_double3(0.0, 0.0, 0.0); }
+    if (tid < nsup_rows) {
+      srow = __ldg(rsup_rows + tid);
+      snode = __ldg(free_node + srow);
+      const int k0 = __ldg(rsup_ptr + srow), k1 = __ldg(rsup_ptr + srow + 1);
+#pragma unroll
+      for (int j = 0; j < kAsmNS; ++j)
+        if (k0 + j < k1) { pe[j] = 8 * (NfP + __ldg(rsup_edge + k0 + j)); ps[j] = __ldg(rsup_slot + k0 + j); }
+      if (sup_shared) {
+        pp = ld3(loads, snode);
+#pragma unroll
+        for (int j = 0; j < kAsmNS; ++j)
+          if (ps[j] >= 0) xe[j] = ld3(xs, ps[j]);
+      }
+    }
+  }
   int buf = 0;
-  for (int64_t b = b_lo; b < b_hi; ++b, buf ^= 1) {
+  for (int64_t b = b_lo; b < b_hi; b += b_step, buf ^= 1) {
+    if (SUP && !sup_shared && srow >= 0) {   // this design's load and support coordinates: issued before the wait for q
+      pp = ld3(loads + b * loads_stride, snode);
+#pragma unroll
+      for (int j = 0; j < kAsmNS; ++j)
+        if (ps[j] >= 0) xe[j] = ld3(xs + b * xs_stride, ps[j]);
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();            // q of design b is in place for everyone; everyone is done with the other region
-    if (b + 1 < b_hi) fetch_q(b + 1, buf ^ 1);
+    if (b + b_step < b_hi) fetch_q(b + b_step, buf ^ 1);
     const uint32_t rb = reg0 + 8u * (buf * region);
+    if (SUP && srow >= 0) {
+      double3 acc = make_double3(0.0, 0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < kAsmNS; ++j)
+        if (ps[j] >= 0) {
+          const double qe = lds_f64(rb + pe[j]);
+          acc.x += qe * xe[j].x; acc.y += qe * xe[j].y; acc.z += qe * xe[j].z;
+        }
+      st3(rhs + b * (int64_t)Nf * 3, srow, make_double3(pp.x + acc.x, pp.y + acc.y, pp.z + acc.z));
+    }
 #pragma unroll
     for (int i = 0; i < kAsmNR; ++i) {
       if (tid + i * kThreads < Nf) {
-        const int4 a = lds_v4(de0 + 32u * kThreads * i), c = lds_v4(de0 + 32u * kThreads * i + 16u);
-        const double q0 = lds_f64(rb + a.x), q1 = lds_f64(rb + a.y), q2 = lds_f64(rb + a.z), q3 = lds_f64(rb + a.w),
-                     q4 = lds_f64(rb + c.x), q5 = lds_f64(rb + c.y), q6 = lds_f64(rb + c.z), q7 = lds_f64(rb + c.w);
+        // `maxdeg` (the longest list of the topology) is uniform: the pad slots beyond it cost nothing
+        const int4 a = lds_v4(de0 + 32u * kThreads * i);
         double acc = 0.0;
-        acc += q0; acc += q1; acc += q2; acc += q3; acc += q4; acc += q5; acc += q6; acc += q7;
+        acc += lds_f64(rb + a.x);
+        if (maxdeg > 1) acc += lds_f64(rb + a.y);
+        if (maxdeg > 2) acc += lds_f64(rb + a.z);
+        if (maxdeg > 3) acc += lds_f64(rb + a.w);
+        if (maxdeg > 4) {
+          const int4 c = lds_v4(de0 + 32u * kThreads * i + 16u);
+          acc += lds_f64(rb + c.x);
+          if (maxdeg > 5) acc += lds_f64(rb + c.y);
+          if (maxdeg > 6) acc += lds_f64(rb + c.z);
+          if (maxdeg > 7) acc += lds_f64(rb + c.w);
+        }
         asm volatile("st.shared.f64 [%0], %1;" ::"r"(rb + 8u * (tid + i * kThreads)), "d"(flip_sign(acc)) : "memory");
       }
     }
@@ -245,65 +300,106 @@ assemble_K_batch_kernel(int E, int Nf, int nnz, int64_t batch, int dpc, const in
   }
 }
 
-// 512 threads.  The first `stream_ctas` CTAs stream: thread t owns the flat elements t, t + 512, ... (kRhsNE of them:
-// 3 Nf <= 3072) of `dpc` designs -- with shared loads (SHARED: loads_stride == 0) their loop over designs is stores
-// of registers only.  The other CTAs take the (design, support row, component) items, one per thread per trip, `dpp`
-// designs per CTA: short chains of index loads and gathers, hidden by the number of independent items.
+// rhs, step 1: every element as load + 0.0 -- final for the rows without supports, provisional for the others (step 2
+// overwrites them later on the same stream).  rhs_src[i] = index of flat element i's load in a design's loads (plan).
+//
+// assemble_rhs_tma_kernel -- shared loads (loads_stride == 0), 16-byte aligned rhs: every design's image is the same
+// 3 Nf doubles.  A CTA builds the image of TWO consecutive designs in shared memory once (2 * 3 Nf doubles: 16-byte
+// granular whatever the parity of 3 Nf) and one thread then issues a bulk asynchronous copy (TMA, shared -> global) per
+// pair of its designs: no registers, no store instructions, the copy engine streams the bytes.
+// assemble_rhs_stream_kernel -- per-design loads: plain stores, one design at a time.
 constexpr int kRhsThreads = 512;
-constexpr int kRhsNE = 6;
 
-template <bool SHARED>
-__global__ void __launch_bounds__(kRhsThreads, 2)
-assemble_rhs_batch_kernel(int Nf, int nsup_rows, int64_t batch, int dpc, int stream_ctas, int dpp,
-                          const int32_t* __restrict__ rsup_rows, const int32_t* __restrict__ rsup_ptr,
-                          const int32_t* __restrict__ rsup_edge, const int32_t* __restrict__ rsup_slot,
-                          const int32_t* __restrict__ free_node, const double* __restrict__ q,
-                          const double* __restrict__ xs, const double* __restrict__ loads, double* __restrict__ rhs,
-                          int64_t q_stride, int64_t xs_stride, int64_t loads_stride) {
+__global__ void __launch_bounds__(kRhsThreads, 1)
+assemble_rhs_tma_kernel(int Nf, int64_t batch, int dpc, const int32_t* __restrict__ rhs_src,
+                        const double* __restrict__ loads, double* __restrict__ rhs) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* img = reinterpret_cast<double*>(smem_raw);      // [2 * 3 Nf]
   const int tid = threadIdx.x;
   const int n3 = 3 * Nf;
-  if ((int)blockIdx.x >= stream_ctas) {
-    const int npairs = 3 * nsup_rows;
-    const int64_t b0 = (int64_t)((int)blockIdx.x - stream_ctas) * dpp;
-    const int nb = (int)min((int64_t)dpp, batch - b0);
-    for (int it = tid; it < nb * npairs; it += kRhsThreads) {
-      const int db = it / npairs, pi = it - db * npairs;
-      const int64_t b = b0 + db;
-      const int r = __ldg(rsup_rows + pi / 3), c = pi % 3;
-      const int k0 = __ldg(rsup_ptr + r), k1 = __ldg(rsup_ptr + r + 1);
-      double acc = 0.0;
-      for (int k = k0; k < k1; ++k)
-        acc += __ldg(q + b * q_stride + __ldg(rsup_edge + k)) * __ldg(xs + b * xs_stride + 3 * __ldg(rsup_slot + k) + c);
-      rhs[b * (int64_t)n3 + 3 * r + c] = __ldg(loads + b * loads_stride + 3 * __ldg(free_node + r) + c) + acc;
-    }
-    return;
+  const int64_t b_lo = (int64_t)blockIdx.x * dpc;         // dpc is even: b_lo * n3 * 8 is a multiple of 16
+  const int64_t b_hi = min(batch, b_lo + dpc);
+  const int64_t b_pairs = b_lo + ((b_hi - b_lo) & ~int64_t(1));   // [b_lo, b_pairs): whole pairs of designs
+  for (int i = tid; i < n3; i += kRhsThreads) {
+    const double v = __ldg(loads + __ldg(rhs_src + i)) + 0.0;
+    img[i] = v;
+    img[i + n3] = v;
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the generic-proxy writes above, seen by the copy engine
+  __syncthreads();
+  if (b_pairs < b_hi) {                                   // an odd design left over at the end of the batch
+    double* out = rhs + b_pairs * (int64_t)n3;
+    for (int i = tid; i < n3; i += kRhsThreads) out[i] = img[i];
+  }
+  if (tid == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(img);
+    for (int64_t b = b_lo; b < b_pairs; b += 2)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rhs + b * (int64_t)n3), "r"(src),
+                   "r"((uint32_t)(16 * n3))
+                   : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the image must outlive the reads
+  }
+}
+
+__global__ void __launch_bounds__(kRhsThreads, 2)
+assemble_rhs_stream_kernel(int Nf, int64_t batch, int dpc, const int32_t* __restrict__ rhs_src,
+                           const double* __restrict__ loads, double* __restrict__ rhs, int64_t loads_stride) {
+  const int tid = threadIdx.x;
+  const int n3 = 3 * Nf;
   const int64_t b_lo = (int64_t)blockIdx.x * dpc, b_hi = min(batch, b_lo + dpc);
-  int src[kRhsNE];                        // element -> index into a design's loads; -1: no such element / a support row
-  double pv[kRhsNE];                      // load + 0.0, kept across designs when they share the loads
-#pragma unroll
-  for (int k = 0; k < kRhsNE; ++k) {
-    const int i = tid + k * kRhsThreads;
-    src[k] = -1;
-    pv[k] = 0.0;
-    if (i < n3) {
-      const int r = i / 3, c = i - 3 * r;
-      if (__ldg(rsup_ptr + r + 1) == __ldg(rsup_ptr + r)) {
-        src[k] = 3 * __ldg(free_node + r) + c;
-        if (SHARED) pv[k] = __ldg(loads + src[k]) + 0.0;
-      }
-    }
-  }
   for (int64_t b = b_lo; b < b_hi; ++b) {
     double* out = rhs + b * (int64_t)n3;
-    if (!SHARED) {
+    for (int i = tid; i < n3; i += kRhsThreads) out[i] = __ldg(loads + b * loads_stride + __ldg(rhs_src + i)) + 0.0;
+  }
+}
+
+// rhs, step 2 when assemble_K_batch_kernel<., true> does not run: the (design, support row, component) items, four
+// per thread per trip so that their short chains of index loads and their gathers are in flight together.
+__global__ void __launch_bounds__(kRhsThreads, 1)
+assemble_rhs_pairs_kernel(int Nf, int nsup_rows, int64_t batch, int dpp, const int32_t* __restrict__ rsup_rows,
+                          const int32_t* __restrict__ rsup_ptr, const int32_t* __restrict__ rsup_edge,
+                          const int32_t* __restrict__ rsup_slot, const int32_t* __restrict__ free_node,
+                          const double* __restrict__ q, const double* __restrict__ xs, const double* __restrict__ loads,
+                          double* __restrict__ rhs, int64_t q_stride, int64_t xs_stride, int64_t loads_stride) {
+  const int tid = threadIdx.x;
+  const int n3 = 3 * Nf, npairs = 3 * nsup_rows;
+  const int64_t b0 = (int64_t)blockIdx.x * dpp;
+  const int nitems = (int)min((int64_t)dpp, batch - b0) * npairs;
+  for (int base = tid; base < nitems; base += 4 * kRhsThreads) {
+    int r[4], c[4], k0[4], k1[4];
+    int64_t b[4];
 #pragma unroll
-      for (int k = 0; k < kRhsNE; ++k)
-        if (src[k] >= 0) pv[k] = __ldg(loads + b * loads_stride + src[k]) + 0.0;
+    for (int u = 0; u < 4; ++u) {
+      const int it = min(base + u * kRhsThreads, nitems - 1);       // past the end: the last item again, not stored
+      const int db = it / npairs, pi = it - db * npairs;
+      b[u] = b0 + db;
+      r[u] = __ldg(rsup_rows + pi / 3);
+      c[u] = pi % 3;
     }
 #pragma unroll
-    for (int k = 0; k < kRhsNE; ++k)
-      if (src[k] >= 0) out[tid + k * kRhsThreads] = pv[k];
+    for (int u = 0; u < 4; ++u) { k0[u] = __ldg(rsup_ptr + r[u]); k1[u] = __ldg(rsup_ptr + r[u] + 1); }
+    double qe[4][2], xe[4][2], pp[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool in = k0[u] + j < k1[u];
+        qe[u][j] = in ? __ldg(q + b[u] * q_stride + __ldg(rsup_edge + k0[u] + j)) : 0.0;
+        xe[u][j] = in ? __ldg(xs + b[u] * xs_stride + 3 * __ldg(rsup_slot + k0[u] + j) + c[u]) : 0.0;
+      }
+      pp[u] = __ldg(loads + b[u] * loads_stride + 3 * __ldg(free_node + r[u]) + c[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (k0[u] + j < k1[u]) acc += qe[u][j] * xe[u][j];
+      for (int k = k0[u] + 2; k < k1[u]; ++k)                        // rows with more than two supports
+        acc += __ldg(q + b[u] * q_stride + __ldg(rsup_edge + k)) * __ldg(xs + b[u] * xs_stride + 3 * __ldg(rsup_slot + k) + c[u]);
+      if (base + u * kRhsThreads < nitems) rhs[b[u] * (int64_t)n3 + 3 * r[u] + c[u]] = pp[u] + acc;
+    }
   }
 }
 
@@ -1074,33 +1170,42 @@ int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const 
   const unsigned tiles = (unsigned)((p->Nf + kAsmRows - 1) / kAsmRows);
   // a batch on one topology: whole designs per CTA, index streams read once per launch (when the plan says it fits)
   if (batch >= 8 && p->asm_batch_ok && !(std::getenv("FDM_ASM_BATCH") && std::atoi(std::getenv("FDM_ASM_BATCH")) == 0)) {
+    const int sms = std::max(p->sm_count, 1);
+    const int nsup = (int)p->rsup_rows.size();
+    const bool sup_in_K = Kdata && rhs && nsup && p->asm_sup_in_K;
+    if (rhs) {
+      const int64_t img_bytes = 16 * 3 * (int64_t)p->Nf;
+      if (ls == 0 && (reinterpret_cast<uintptr_t>(rhs) & 15) == 0 && img_bytes <= 96 * 1024) {
+        FDM_CUDA(cudaFuncSetAttribute(assemble_rhs_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        int dpc = 2 * (int)std::max<int64_t>(1, (batch + 2 * sms - 1) / (2 * sms));       // even; one CTA per SM
+        if (const char* e = std::getenv("FDM_RHS_DPC")) dpc = std::max(2, std::atoi(e) & ~1);
+        assemble_rhs_tma_kernel<<<(unsigned)((batch + dpc - 1) / dpc), kRhsThreads, (size_t)img_bytes, st>>>(
+            (int)p->Nf, batch, dpc, d.rhs_src, loads, rhs);
+        if (int rc = fdm_check_launch("assemble_rhs_tma")) return rc;
+      } else {
+        const int dpc = (int)std::max<int64_t>(1, (batch + 4 * sms - 1) / (4 * sms));
+        assemble_rhs_stream_kernel<<<(unsigned)((batch + dpc - 1) / dpc), kRhsThreads, 0, st>>>((int)p->Nf, batch, dpc,
+                                                                                                d.rhs_src, loads, rhs, ls);
+        if (int rc = fdm_check_launch("assemble_rhs_stream")) return rc;
+      }
+    }
     if (Kdata) {
       const int smem = (int)p->asm_smem_bytes;
-      auto kern = p->nnz <= 8 * kThreads ? assemble_K_batch_kernel<8> : assemble_K_batch_kernel<16>;
+      auto kern = p->nnz <= 8 * kThreads ? (sup_in_K ? assemble_K_batch_kernel<8, true> : assemble_K_batch_kernel<8, false>)
+                                         : (sup_in_K ? assemble_K_batch_kernel<16, true> : assemble_K_batch_kernel<16, false>);
       FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      const int per_sm = std::max(1, std::min(3, (227 * 1024) / (smem + 1024)));        // resident CTAs per SM
-      const int64_t target = (int64_t)std::max(p->sm_count, 1) * per_sm;
-      int dpc = (int)std::max<int64_t>(1, (batch + target - 1) / target);
-      if (const char* e = std::getenv("FDM_ASM_DPC")) dpc = std::max(1, std::atoi(e));
-      kern<<<(unsigned)((batch + dpc - 1) / dpc), kThreads, smem, st>>>((int)p->E, (int)p->Nf, (int)p->nnz, batch, dpc,
-                                                                        d.asm_code, d.diags_ptr, d.diags_idx, q, Kdata, qs);
+      const int per_sm = std::max(1, std::min(3, (227 * 1024) / (smem + 1024)));          // resident CTAs per SM
+      kern<<<(unsigned)std::min<int64_t>(batch, (int64_t)sms * per_sm), kThreads, smem, st>>>(
+          (int)p->E, (int)p->Nf, (int)p->nnz, p->asm_maxdeg, batch, d.asm_code, d.diags_ptr, d.diags_idx, q, Kdata, qs,
+          nsup, d.rsup_rows, d.rsup_ptr, d.rsup_edge, d.rsup_slot, d.free_node, xs, loads, rhs, xss, ls);
       if (int rc = fdm_check_launch("assemble_K_batch")) return rc;
     }
-    if (rhs) {
-      auto kern = ls == 0 ? assemble_rhs_batch_kernel<true> : assemble_rhs_batch_kernel<false>;
-      const int64_t target = (int64_t)std::max(p->sm_count, 1) * 2;
-      int dpc = (int)std::max<int64_t>(1, (batch + target - 1) / target);
-      if (const char* e = std::getenv("FDM_RHS_DPC")) dpc = std::max(1, std::atoi(e));
-      const int nsup = (int)p->rsup_rows.size();
-      // support-row items: about four trips of 512 per CTA
-      const int dpp = nsup ? std::max(1, (4 * kRhsThreads) / (3 * nsup)) : 1;
-      const unsigned stream_ctas = (unsigned)((batch + dpc - 1) / dpc);
-      unsigned pair_ctas = nsup ? (unsigned)((batch + dpp - 1) / dpp) : 0u;
-      if (std::getenv("FDM_RHS_NOPAIRS")) pair_ctas = 0;   // EXPERIMENT
-      kern<<<stream_ctas + pair_ctas, kRhsThreads, 0, st>>>((int)p->Nf, nsup, batch, dpc, (int)stream_ctas, dpp, d.rsup_rows,
-                                                            d.rsup_ptr, d.rsup_edge, d.rsup_slot, d.free_node, q, xs, loads,
-                                                            rhs, qs, xss, ls);
-      if (int rc = fdm_check_launch("assemble_rhs_batch")) return rc;
+    if (rhs && nsup && !sup_in_K) {
+      const int dpp = std::max(1, (16 * kRhsThreads) / (3 * nsup));                       // about four trips per CTA
+      assemble_rhs_pairs_kernel<<<(unsigned)((batch + dpp - 1) / dpp), kRhsThreads, 0, st>>>(
+          (int)p->Nf, nsup, batch, dpp, d.rsup_rows, d.rsup_ptr, d.rsup_edge, d.rsup_slot, d.free_node, q, xs, loads, rhs, qs,
+          xss, ls);
+      if (int rc = fdm_check_launch("assemble_rhs_pairs")) return rc;
     }
     return FDM_OK;
   }

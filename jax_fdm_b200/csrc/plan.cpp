@@ -478,6 +478,7 @@ void fdm_check_assemble_batch(fdm_plan& p) {
   p.rsup_edge.clear();
   p.rsup_slot.clear();
   bool rows_ok = true;
+  p.asm_maxdeg = 0;
   for (int64_t i = 0; i < p.Nf; ++i) {
     const int32_t node = p.free_node[i];
     for (int32_t k = p.ninc_ptr[node]; k < p.ninc_ptr[node + 1]; ++k) {
@@ -490,6 +491,13 @@ void fdm_check_assemble_batch(fdm_plan& p) {
     p.rsup_ptr[(size_t)i + 1] = (int32_t)p.rsup_edge.size();
     if (p.rsup_ptr[(size_t)i + 1] > p.rsup_ptr[(size_t)i]) p.rsup_rows.push_back((int32_t)i);
     if (p.diags_indptr[i + 1] - p.diags_indptr[i] > 8) rows_ok = false;
+    p.asm_maxdeg = std::max(p.asm_maxdeg, (int)(p.diags_indptr[i + 1] - p.diags_indptr[i]));
+  }
+  p.rhs_src.assign((size_t)p.Nf * 3, 0);
+  p.asm_sup_in_K = p.rsup_rows.size() <= 256;
+  for (int64_t i = 0; i < p.Nf; ++i) {
+    for (int c = 0; c < 3; ++c) p.rhs_src[(size_t)i * 3 + c] = 3 * p.free_node[i] + c;
+    if (p.rsup_ptr[(size_t)i + 1] - p.rsup_ptr[(size_t)i] > 2) p.asm_sup_in_K = false;
   }
   p.asm_smem_bytes = 16 * (((p.Nf + 1) & ~int64_t(1)) + ((p.E + 2) & ~int64_t(1))) + 32 * p.Nf + 16;
   p.asm_batch_ok = rows_ok && p.Nf <= 4 * 256 && p.asm_smem_bytes <= 96 * 1024 && p.nnz <= 16 * 256;

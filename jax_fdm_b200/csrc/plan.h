@@ -26,6 +26,7 @@ struct DeviceArrays {
   int32_t* asm_code = nullptr;     // (nnz)  entry -> edge id, or -(row) - 2 on the diagonal      (assemble_design_kernel)
   int32_t* rsup_ptr = nullptr;     // (Nf+1) per free row: its edges to supports, in incidence order
   int32_t* rsup_rows = nullptr;    // the free rows that have at least one such edge
+  int32_t* rhs_src = nullptr;      // (3 Nf) flat rhs element -> 3 * node + component (index into a design's loads)
   int32_t* rsup_edge = nullptr;    // (rsup) edge id
   int32_t* rsup_slot = nullptr;    // (rsup) support slot (row of xyz_fixed)
   // band ordering (batched Cholesky)
@@ -79,7 +80,7 @@ struct fdm_plan {
   std::vector<int32_t> node_slot, edge_nodes, ninc_ptr, ninc_edge, ninc_other;
   std::vector<int32_t> free_node, fixed_node, entry_edge, diag_pos;
   std::vector<uint32_t> sup_mask;
-  std::vector<int32_t> asm_code, rsup_ptr, rsup_rows, rsup_edge, rsup_slot;   // batched assembly (fdm_check_assemble_batch)
+  std::vector<int32_t> asm_code, rsup_ptr, rsup_rows, rsup_edge, rsup_slot, rhs_src;   // batched assembly (fdm_check_assemble_batch)
 
   // band ordering
   std::vector<int32_t> band_perm, band_iperm, band_kidx, band_rowkidx;
@@ -90,6 +91,8 @@ struct fdm_plan {
   bool spmm_batch_ok = false;  // every row has <= 12 stored entries (spmm_batch_kernel keeps a row's columns in registers)
   bool asm_batch_ok = false;   // a design's q, diagonals and index streams fit one CTA's shared memory (asm_smem_bytes)
   int64_t asm_smem_bytes = 0;
+  int asm_maxdeg = 0;          // longest incident-edge list of a free row
+  bool asm_sup_in_K = false;   // rows next to supports: <= 256 of them, <= 2 supports each (assemble_K_batch_kernel<., true>)
   BandHalf tw[2];         // empty when the two-sided factorisation does not apply (hbw > 29 or fewer than 5 blocks)
 
   // aggregates for the two-level preconditioner

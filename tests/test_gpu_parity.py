@@ -272,7 +272,7 @@ def test_zero_rhs_column_and_errors(eq):
 @pytest.mark.parametrize("name", ["pillow30", "cablenet12", "liew_dome"])
 def test_batched_assembly_and_spmm_are_bit_identical_to_the_per_design_kernels(eq, name):
     """A batch on one topology takes kernels that load the index streams once per CTA and stream the designs through
-    (assemble_batch_kernel, spmm_batch_kernel); a single design takes the per-design kernels.  Same additions in the
+    (assemble_K_batch_kernel + assemble_rhs_tma_kernel / _stream_kernel / _pairs_kernel, spmm_batch_kernel); a single design takes the per-design kernels.  Same additions in the
     same order: the outputs must be the same bits, and K.data the reference's (ref_K_data) for the fixture's own q."""
     g = load(name)
     s, so = make(eq, g)
@@ -292,5 +292,17 @@ def test_batched_assembly_and_spmm_are_bit_identical_to_the_per_design_kernels(e
         assert torch.equal(eq.ops.spmm(s, K1, X[b].contiguous()), Y[b])
     # shared supports / loads (stride 0) through the batched kernel
     K2, rhs2 = eq.ops.assemble(s, T(qb), T(g["xyz_fixed"]), T(g["loads"]))
-    K3, rhs3 = eq.ops.assemble(s, T(qb[5]), T(g["xyz_fixed"]), T(g["loads"]))
-    assert torch.equal(K2[5], K3) and torch.equal(rhs2[5], rhs3)
+    for b in (0, 5, B - 1):
+        K3, rhs3 = eq.ops.assemble(s, T(qb[b]), T(g["xyz_fixed"]), T(g["loads"]))
+        assert torch.equal(K2[b], K3) and torch.equal(rhs2[b], rhs3)
+    # K.data alone and the rhs alone (NULL for the other output), straight through the C ABI
+    import ctypes as C
+    from jax_fdm_b200 import _lib as L
+    P = lambda t: C.c_void_p(t.data_ptr())
+    q_t, xs_t, p_t = T(qb), T(xsb), T(pb)
+    Ko, ro = torch.full_like(K, float("nan")), torch.full_like(rhs, float("nan"))
+    E = g["q"].size
+    L.check(L.lib().fdm_assemble(s.plan, P(q_t), P(xs_t), P(p_t), P(Ko), None, B, E, xs_t[0].numel(), p_t[0].numel(), None))
+    L.check(L.lib().fdm_assemble(s.plan, P(q_t), P(xs_t), P(p_t), None, P(ro), B, E, xs_t[0].numel(), p_t[0].numel(), None))
+    torch.cuda.synchronize()
+    assert torch.equal(Ko, K) and torch.equal(ro, rhs)

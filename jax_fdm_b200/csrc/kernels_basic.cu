@@ -1154,6 +1154,58 @@ loss_sqdist_kernel(const double* __restrict__ x, const double* __restrict__ x0,
   }
 }
 
+// The same loss for a batch, persistent CTAs: CTA c takes designs c, c + gridDim.x, ...; a thread keeps its NPT
+// elements of x0 in registers when the designs share the target (x0_stride == 0) and loads design b + step's x before
+// it reduces design b, so the reduction's barrier never leaves the memory pipe idle.  Same per-thread order of
+// accumulation (elements t, t + 256, ...) and the same reduction tree as loss_sqdist_kernel => identical bits.
+template <int NPT>
+__global__ void __launch_bounds__(256)
+loss_sqdist_batch_kernel(const double* __restrict__ x, const double* __restrict__ x0, double* __restrict__ g,
+                         double* __restrict__ loss, int n, int64_t batch, int64_t x0_stride) {
+  __shared__ double red[2][8];
+  const int tid = threadIdx.x;
+  double t0[NPT], cur[NPT], nxt[NPT];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const int i = tid + k * 256;
+    t0[k] = x0_stride == 0 && i < n ? __ldg(x0 + i) : 0.0;
+    cur[k] = i < n && (int64_t)blockIdx.x < batch ? x[(int64_t)blockIdx.x * n + i] : 0.0;
+    nxt[k] = 0.0;
+  }
+  int buf = 0;
+  for (int64_t b = blockIdx.x; b < batch; b += gridDim.x, buf ^= 1) {
+    const int64_t bn = b + gridDim.x;
+    if (bn < batch) {
+#pragma unroll
+      for (int k = 0; k < NPT; ++k)
+        if (tid + k * 256 < n) nxt[k] = x[bn * n + tid + k * 256];
+    }
+    if (x0_stride != 0) {
+#pragma unroll
+      for (int k = 0; k < NPT; ++k)
+        if (tid + k * 256 < n) t0[k] = __ldg(x0 + b * x0_stride + tid + k * 256);
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < NPT; ++k)
+      if (tid + k * 256 < n) {
+        const double d = cur[k] - t0[k];
+        if (g) g[b * n + tid + k * 256] = d;
+        acc += d * d;
+      }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) red[buf][tid >> 5] = acc;
+    __syncthreads();            // red[buf] complete; red[buf ^ 1] is rewritten only after the next barrier
+    if (tid < 32) {
+      acc = tid < 8 ? red[buf][tid] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (tid == 0 && loss) loss[b] = 0.5 * acc;
+    }
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) cur[k] = nxt[k];
+  }
+}
+
 inline dim3 grid_for(int64_t work, int64_t batch) {
   return dim3((unsigned)((work + kThreads - 1) / kThreads), (unsigned)batch, 1);
 }
@@ -1395,6 +1447,18 @@ int launch_nan_failed(const double* info, double* x, int64_t n, int64_t batch, c
 
 int launch_loss_sqdist(const double* x, const double* x0, double* g, double* loss, int64_t n,
                        int64_t batch, int64_t x0_stride, cudaStream_t st) {
+  if (batch >= 8 && n >= 256 && n <= 12 * 256 && !(std::getenv("FDM_LOSS_BATCH") && std::atoi(std::getenv("FDM_LOSS_BATCH")) == 0)) {
+    int dev = 0, sms = 0;
+    FDM_CUDA(cudaGetDevice(&dev));
+    FDM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int per_sm = 2;                                   // resident CTAs per SM at this kernel's register count
+    const unsigned ctas = (unsigned)std::min<int64_t>(batch, (int64_t)sms * per_sm);
+    if (n <= 4 * 256) loss_sqdist_batch_kernel<4><<<ctas, 256, 0, st>>>(x, x0, g, loss, (int)n, batch, x0_stride);
+    else if (n <= 8 * 256) loss_sqdist_batch_kernel<8><<<ctas, 256, 0, st>>>(x, x0, g, loss, (int)n, batch, x0_stride);
+    else if (n <= 10 * 256) loss_sqdist_batch_kernel<10><<<ctas, 256, 0, st>>>(x, x0, g, loss, (int)n, batch, x0_stride);
+    else loss_sqdist_batch_kernel<12><<<ctas, 256, 0, st>>>(x, x0, g, loss, (int)n, batch, x0_stride);
+    return fdm_check_launch("loss_sqdist_batch");
+  }
   const int threads = n >= 256 ? 256 : (int)std::max<int64_t>(32, ((n + 31) / 32) * 32);
   loss_sqdist_kernel<<<(unsigned)batch, threads, 0, st>>>(x, x0, g, loss, n, x0_stride);
   return fdm_check_launch("loss_sqdist");

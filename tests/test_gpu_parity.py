@@ -306,3 +306,13 @@ def test_batched_assembly_and_spmm_are_bit_identical_to_the_per_design_kernels(e
     L.check(L.lib().fdm_assemble(s.plan, P(q_t), P(xs_t), P(p_t), None, P(ro), B, E, xs_t[0].numel(), p_t[0].numel(), None))
     torch.cuda.synchronize()
     assert torch.equal(Ko, K) and torch.equal(ro, rhs)
+    # the batched squared-distance loss (persistent CTAs, next design prefetched) against the per-design kernel
+    x0 = T(rng.standard_normal((s.num_free, 3)))
+    n = s.num_free * 3
+    gb, lb = torch.empty_like(X), torch.empty(B, dtype=X.dtype, device=X.device)
+    L.check(L.lib().fdm_loss_sqdist(P(X), P(x0), P(gb), P(lb), n, B, 0, None))
+    for b in (0, 9, B - 1):
+        g1, l1 = torch.empty_like(X[b]), torch.empty(1, dtype=X.dtype, device=X.device)
+        L.check(L.lib().fdm_loss_sqdist(P(X[b]), P(x0), P(g1), P(l1), n, 1, 0, None))
+        assert torch.equal(g1, gb[b]) and torch.equal(l1[0], lb[b])
+    assert np.allclose(N(lb), 0.5 * ((N(X) - N(x0)[None]) ** 2).sum(axis=(1, 2)), rtol=1e-13)

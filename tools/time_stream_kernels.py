@@ -56,6 +56,8 @@ def main():
         ("fill rhs+8B", 24 * Nf, lambda: (pipe.rhs.view(-1)[1:].fill_(1.0), 0)[1]),
         ("fill rhs f32x2", 24 * Nf, lambda: (pipe.rhs.view(torch.float32).fill_(1.0), 0)[1]),
         ("copy K->K2", 16 * nnz, lambda: (K2.copy_(pipe.K), 0)[1]),
+        ("loss", 48 * Nf + 8,
+         lambda: lib.fdm_loss_sqdist(P(pipe.x), P(pipe.x0), P(pipe.g), P(pipe.loss), Nf * 3, B, 0, st)),
         ("spmm", 8 * nnz + 48 * Nf, lambda: lib.fdm_spmm(s.plan, P(pipe.K), P(pipe.x), P(Y), B, st)),
     ]
     def run(fn):

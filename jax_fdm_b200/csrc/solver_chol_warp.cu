@@ -335,8 +335,15 @@ __device__ __forceinline__ void invdiag_solve_store(double* fb, int lane, const 
 // sides are stored multiplied by D so that the backward substitution runs unchanged.  The signs go to the
 // fourth slot of the intermediate right-hand sides (the adjoint's forward sweep needs them), meta[2] = 1.
 // A pivot below 1e-13 of the largest diagonal entry seen is reported as a breakdown (meta[1] = 2).
+// measurement builds only: -DFDM_FAC_MAXNREG=112 trades the launch bound for a register cap (18 warps per SM with
+// FDM_CHOL_FACWARPS=6); DESIGN.md §5 has the outcome
+#ifdef FDM_FAC_MAXNREG
+#define FDM_FAC_BOUNDS __maxnreg__(FDM_FAC_MAXNREG)
+#else
+#define FDM_FAC_BOUNDS __launch_bounds__(kFacThreads, 2)
+#endif
 template <bool FROM_Q, int PW, bool SIGNED, bool TW = false>   // TW: two-sided, a warp pair per design
-__global__ void __launch_bounds__(kFacThreads, 2) chol_factor_mma_kernel(WArgs A) {
+__global__ void FDM_FAC_BOUNDS chol_factor_mma_kernel(WArgs A) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // designs per CTA = warps per CTA (host's choice); two-sided: a design is the warp pair (2k, 2k+1)

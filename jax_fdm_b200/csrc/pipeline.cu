@@ -26,6 +26,7 @@ struct Chunk {
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;
   cudaGraphExec_t exec = nullptr;
+  cudaGraphExec_t exec_park[2] = {nullptr, nullptr};   // the same + the parking of the losses in staging row 0 / 1
   void* ws = nullptr;
   size_t ws_bytes = 0;
 };
@@ -37,6 +38,11 @@ struct Buf {
 };
 
 }  // namespace
+
+__global__ void park_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
 
 struct fdm_fa {
   const fdm_plan* plan = nullptr;
@@ -56,6 +62,10 @@ struct fdm_fa {
   std::vector<void*> allocs;
   std::vector<Chunk> chunks;
   cudaEvent_t fork = nullptr;
+  cudaEvent_t loss_ev[2] = {nullptr, nullptr};   // recorded after a host step's loss copy (copy_losses), by staging row
+  bool loss_ev_armed[2] = {false, false};
+  int64_t host_steps = 0;
+  Buf loss_stage;                        // (2, B) staging rows of the losses of host steps
   cudaStream_t own = nullptr;      // run_host's ordering stream
   cudaGraphExec_t step_exec = nullptr;   // the whole device-resident step (fork / chunks / join) as one graph
   int64_t launches_per_step = 0;
@@ -169,6 +179,22 @@ int capture_chunks(fdm_fa* f) {
     e = cudaGraphInstantiate(&c.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+    // the same slice followed by the parking of its losses in staging row 0 / 1 (asynchronous host steps, see
+    // copy_losses): inside the graph the parking kernel is free, launched after the graph it costs 18 us per slice
+    for (int par = 0; par < 2; ++par) {
+      if (c.exec_park[par]) { cudaGraphExecDestroy(c.exec_park[par]); c.exec_park[par] = nullptr; }
+      graph = nullptr;
+      FDM_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeThreadLocal));
+      rc = launch_chunk(f, c, c.st, nullptr);
+      park_kernel<<<(unsigned)((c.B + 255) / 256), 256, 0, c.st>>>(f->loss.at(c.off),
+                                                                   f->loss_stage.p + (int64_t)par * f->B + c.off, c.B);
+      e = cudaStreamEndCapture(c.st, &graph);
+      if (rc != FDM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph capture: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+      e = cudaGraphInstantiate(&c.exec_park[par], graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+    }
   }
   // the device-resident step as ONE graph: fork from the capturing stream to the chunk streams and join back
   if (f->capturable && f->o.use_graph && f->chunks.size() > 1) {
@@ -203,12 +229,16 @@ void destroy(fdm_fa* f) {
   for (Chunk& c : f->chunks) {
     if (c.st) cudaStreamSynchronize(c.st);
     if (c.exec) cudaGraphExecDestroy(c.exec);
+    for (cudaGraphExec_t g : c.exec_park)
+      if (g) cudaGraphExecDestroy(g);
     if (c.done) cudaEventDestroy(c.done);
     if (c.st) cudaStreamDestroy(c.st);
     if (c.ws) cudaFree(c.ws);
   }
   if (f->step_exec) cudaGraphExecDestroy(f->step_exec);
   if (f->fork) cudaEventDestroy(f->fork);
+  for (cudaEvent_t e : f->loss_ev)
+    if (e) cudaEventDestroy(e);
   if (f->own) cudaStreamDestroy(f->own);
   for (void* q : f->allocs) cudaFree(q);
   for (void* q : f->prog_mem) cudaFree(q);
@@ -270,13 +300,15 @@ int fdm_fa_create(const fdm_plan* p, int64_t batch, const fdm_fa_opts* opts, fdm
   if (!f->fused) { A(f->K, nnz, batch); A(f->rhs, Nf * 3, batch); }
   A(f->x, Nf * 3, batch); A(f->xyz, N * 3, batch);
   A(f->info_f, FDM_INFO_STRIDE, batch); A(f->info_a, FDM_INFO_STRIDE, batch);
-  A(f->g, Nf * 3, batch); A(f->lam, Nf * 3, batch); A(f->loss, 1, batch);
+  A(f->g, Nf * 3, batch); A(f->lam, Nf * 3, batch); A(f->loss, 1, batch); A(f->loss_stage, 1, 2 * batch);
   A(f->q_bar, E, batch); A(f->loads_bar, N * 3, batch); A(f->xs_bar, Ns * 3, batch);
   if (f->o.with_state) {
     A(f->vectors, E * 3, batch); A(f->lengths, E, batch); A(f->forces, E, batch); A(f->residuals, N * 3, batch);
   }
   if (rc == FDM_OK && cudaStreamCreateWithFlags(&f->own, cudaStreamNonBlocking) != cudaSuccess) rc = FDM_ERR_CUDA;
   if (rc == FDM_OK && cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) rc = FDM_ERR_CUDA;
+  for (int i = 0; i < 2; ++i)
+    if (rc == FDM_OK && cudaEventCreateWithFlags(&f->loss_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = FDM_ERR_CUDA;
   f->chunks.resize((size_t)nch);
   int64_t off = 0;
   for (int64_t i = 0; i < nch && rc == FDM_OK; ++i) {
@@ -346,8 +378,11 @@ int fdm_fa_set_goal_program(fdm_fa* f, const fdm_goal_program* h) {
   A(f->xyz_cot, N * 3); A(f->len_cot, E); A(f->for_cot, E); A(f->res_cot, N * 3); A(f->xyz_bar, N * 3);
   if (rc != FDM_OK) return rc;
   f->has_prog = true;
-  for (Chunk& c : f->chunks)
-    if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }   // recaptured by the next run
+  for (Chunk& c : f->chunks) {                                         // recaptured by the next run
+    for (cudaGraphExec_t& g : c.exec_park)
+      if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (c.exec) { cudaGraphExecDestroy(c.exec); c.exec = nullptr; }
+  }
   if (f->step_exec) { cudaGraphExecDestroy(f->step_exec); f->step_exec = nullptr; }
   f->launches_per_step = 0;
   return FDM_OK;
@@ -386,7 +421,24 @@ int fdm_fa_step_device(fdm_fa* f, void* stream) {
   return FDM_OK;
 }
 
-int fdm_fa_enqueue_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar) {
+// The per-design losses of ALL slices leave in one copy on the last slice's stream, once every slice's kernels are
+// done: a 2 KB device-to-host copy per slice between the big ones costs the link 0.3 ms per step (16 slices, 61 MB each
+// way: 1.51 -> 1.80 ms, tools/link_bandwidth.py).  Each slice parks its losses in a staging row (device-to-device, on
+// its own stream) so that a step enqueued right behind this one cannot overwrite them before the copy has read them;
+// two staging rows alternate, and a step waits for the copy that read its row two steps ago.  The parking costs the
+// synchronous step 0.3 ms (2.04 -> 2.33 ms: a kernel launch between a graph launch and a copy on every stream), so
+// fdm_fa_run_host, which waits before it returns, copies from the loss array itself (`park` = false).
+static int copy_losses(fdm_fa* f, double* h_loss, int parity, bool park) {
+  Chunk& last = f->chunks.back();
+  for (Chunk& c : f->chunks)
+    if (&c != &last) FDM_CUDA(cudaStreamWaitEvent(last.st, c.done, 0));
+  FDM_CUDA(cudaMemcpyAsync(h_loss, park ? f->loss_stage.p + (int64_t)parity * f->B : f->loss.p, (size_t)f->B * 8, cudaMemcpyDeviceToHost, last.st));
+  FDM_CUDA(cudaEventRecord(f->loss_ev[parity], last.st));
+  f->loss_ev_armed[parity] = true;
+  return FDM_OK;
+}
+
+static int enqueue_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar, bool park) {
   if (!f || !h_q || !h_loss) {
     fdm_set_error("fdm_fa_enqueue_host: bad arguments");
     return FDM_ERR_INVALID;
@@ -394,15 +446,33 @@ int fdm_fa_enqueue_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_
   int rc = ensure_captured(f);
   if (rc != FDM_OK) return rc;
   const int64_t E = f->plan->E;
+  const int parity = (int)(f->host_steps++ & 1);
   for (Chunk& c : f->chunks) {
     FDM_CUDA(cudaMemcpyAsync(f->q.at(c.off), h_q + c.off * E, (size_t)c.B * E * 8, cudaMemcpyHostToDevice, c.st));
+    if (park && f->loss_ev_armed[parity]) FDM_CUDA(cudaStreamWaitEvent(c.st, f->loss_ev[parity], 0));
+    if (park && c.exec_park[parity]) {
+      FDM_CUDA(cudaGraphLaunch(c.exec_park[parity], c.st));
+      FDM_CUDA(cudaEventRecord(c.done, c.st));
+      if (h_q_bar)
+        FDM_CUDA(cudaMemcpyAsync(h_q_bar + c.off * E, f->q_bar.at(c.off), (size_t)c.B * E * 8, cudaMemcpyDeviceToHost, c.st));
+      continue;
+    }
     rc = run_chunk(f, c, c.st);
     if (rc != FDM_OK) return rc;
-    FDM_CUDA(cudaMemcpyAsync(h_loss + c.off, f->loss.at(c.off), (size_t)c.B * 8, cudaMemcpyDeviceToHost, c.st));
+    // (a kernel, not a device-to-device memcpy: small memcpy operations of any kind between the big copies of a
+    //  stream cost the link, see copy_losses)
+    if (park) park_kernel<<<(unsigned)((c.B + 255) / 256), 256, 0, c.st>>>(f->loss.at(c.off),
+                                                                 f->loss_stage.p + (int64_t)parity * f->B + c.off, c.B);
+    FDM_CUDA(cudaEventRecord(c.done, c.st));
     if (h_q_bar)
       FDM_CUDA(cudaMemcpyAsync(h_q_bar + c.off * E, f->q_bar.at(c.off), (size_t)c.B * E * 8, cudaMemcpyDeviceToHost, c.st));
   }
-  return FDM_OK;
+  return copy_losses(f, h_loss, parity, park);
+}
+
+// asynchronous: the caller may enqueue the next step before this one has finished, so the losses are parked
+int fdm_fa_enqueue_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar) {
+  return enqueue_host(f, h_q, h_loss, h_q_bar, true);
 }
 
 // measurement only: exactly the copies of fdm_fa_enqueue_host (same chunking, same streams), no kernels --
@@ -412,11 +482,11 @@ int fdm_fa_enqueue_copies_only(fdm_fa* f, const double* h_q, double* h_loss, dou
   const int64_t E = f->plan->E;
   for (Chunk& c : f->chunks) {
     FDM_CUDA(cudaMemcpyAsync(f->q.at(c.off), h_q + c.off * E, (size_t)c.B * E * 8, cudaMemcpyHostToDevice, c.st));
-    FDM_CUDA(cudaMemcpyAsync(h_loss + c.off, f->loss.at(c.off), (size_t)c.B * 8, cudaMemcpyDeviceToHost, c.st));
+    FDM_CUDA(cudaEventRecord(c.done, c.st));
     if (h_q_bar)
       FDM_CUDA(cudaMemcpyAsync(h_q_bar + c.off * E, f->q_bar.at(c.off), (size_t)c.B * E * 8, cudaMemcpyDeviceToHost, c.st));
   }
-  return FDM_OK;
+  return copy_losses(f, h_loss, 0, false);
 }
 
 int fdm_fa_wait(fdm_fa* f) {
@@ -426,7 +496,7 @@ int fdm_fa_wait(fdm_fa* f) {
 }
 
 int fdm_fa_run_host(fdm_fa* f, const double* h_q, double* h_loss, double* h_q_bar) {
-  int rc = fdm_fa_enqueue_host(f, h_q, h_loss, h_q_bar);
+  int rc = enqueue_host(f, h_q, h_loss, h_q_bar, false);   // synchronous: nothing can overwrite the losses before the wait
   if (rc != FDM_OK) return rc;
   return fdm_fa_wait(f);
 }

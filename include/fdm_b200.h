@@ -47,8 +47,10 @@ enum {
 enum {
   FDM_STATUS_OK = 0,
   FDM_STATUS_NOT_CONVERGED = 1,
-  FDM_STATUS_INDEFINITE = 2,   /* mixed-sign diagonal / pivot: K neither SPD nor -SPD (the batched band
-                                  Cholesky solves such designs itself when hbw <= 30: FDM_INFO_SIGN 0) */
+  FDM_STATUS_INDEFINITE = 2,   /* mixed-sign diagonal / pivot: K neither SPD nor -SPD.  The batched band Cholesky
+                                  solves such designs itself when hbw <= 30 and FDM_SOLVER_LDLT_BAND takes over
+                                  behind the other solvers when hbw <= 255 (FDM_INFO_SIGN 0); the status only
+                                  remains for wider bands or when the fallback's workspace slots run out */
   FDM_STATUS_BREAKDOWN = 3     /* non-finite scalar met in the iteration / vanishing pivot */
 };
 
@@ -132,7 +134,12 @@ enum {
   FDM_SOLVER_PCG = 1,            /* Jacobi-PCG, one kernel per phase (any size)          */
   FDM_SOLVER_PCG_PERSISTENT = 2, /* two-level PCG, one cooperative kernel, K and vectors
                                     resident in shared memory (meshes that fit)          */
-  FDM_SOLVER_CHOLESKY_BATCHED = 3 /* one CTA per design, banded LL^T in shared memory     */
+  FDM_SOLVER_CHOLESKY_BATCHED = 3, /* one CTA per design, banded LL^T in shared memory    */
+  FDM_SOLVER_LDLT_BAND = 4       /* band L D L^T without pivoting in global memory, one CTA per design, half
+                                    bandwidth <= 255: what FDM_SOLVER_AUTO falls back to, design by design and
+                                    without a host round trip, when the solver above reports
+                                    FDM_STATUS_INDEFINITE (mixed-sign q: the reference's LU, sparse.py:147-149,
+                                    solves such systems); slow (two CTA barriers per column), kept for coverage */
 };
 
 typedef struct fdm_solve_opts {

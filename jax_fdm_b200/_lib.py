@@ -23,7 +23,7 @@ SIZE_NODES, SIZE_EDGES, SIZE_FREE, SIZE_FIXED, SIZE_NNZ, SIZE_DIAGS_NNZ, SIZE_HB
  ARR_INDEX_INDPTR, ARR_DIAG_INDICES, ARR_DIAGS_INDPTR, ARR_DIAGS_INDICES, ARR_BAND_PERM,
  ARR_PART_OF_ROW) = range(11)
 SOLVER_AUTO, SOLVER_PCG, SOLVER_PCG_PERSISTENT, SOLVER_CHOLESKY_BATCHED = 0, 1, 2, 3
-SOLVERS = {"auto": 0, "pcg": 1, "pcg_persistent": 2, "cholesky": 3}
+SOLVERS = {"auto": 0, "pcg": 1, "pcg_persistent": 2, "cholesky": 3, "ldlt": 4}
 
 EXPORTS = [
     "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libfdm_b200.so")
 SOURCES = ["plan.cpp", "kernels_basic.cu", "goals.cu", "spmm.cu", "solver_pcg.cu", "solver_chol.cu", "solver_chol_warp.cu",
-           "solver_pcg2.cu", "pipeline.cu", "fixed_point.cu", "capi.cu"]
+           "solver_pcg2.cu", "solver_ldlt.cu", "pipeline.cu", "fixed_point.cu", "capi.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]
 

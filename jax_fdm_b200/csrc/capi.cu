@@ -242,14 +242,33 @@ static int pick_solver(const fdm_plan* p, int64_t batch, int32_t want) {
   return FDM_SOLVER_PCG;
 }
 
-size_t fdm_workspace_bytes(const fdm_plan* p, int64_t batch, int32_t solver) {
-  if (!p || batch <= 0) return 0;
-  switch (pick_solver(p, batch, solver)) {
+static size_t primary_workspace_bytes(const fdm_plan* p, int64_t batch, int32_t picked) {
+  switch (picked) {
     case FDM_SOLVER_PCG: return pcg_workspace_bytes(p);
     case FDM_SOLVER_PCG_PERSISTENT: return pcg2_workspace_bytes(p);
     case FDM_SOLVER_CHOLESKY_BATCHED: return chol_workspace_bytes(p, batch);
   }
   return 0;
+}
+
+// Does a design this solver reports as indefinite go on to the band L D L^T?  The warp-per-design Cholesky handles
+// mixed-sign q itself up to half bandwidth 30; everything else with a band table does.
+static bool ldlt_fallback(const fdm_plan* p, int32_t picked) {
+  if (!ldlt_supported(p) || picked == FDM_SOLVER_LDLT_BAND) return false;
+  if (picked == FDM_SOLVER_CHOLESKY_BATCHED && chol_warp_supported(p) && p->hbw <= 30) return false;
+  static const bool off = std::getenv("FDM_LDLT_FALLBACK") && std::atoi(std::getenv("FDM_LDLT_FALLBACK")) == 0;
+  return !off;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+size_t fdm_workspace_bytes(const fdm_plan* p, int64_t batch, int32_t solver) {
+  if (!p || batch <= 0) return 0;
+  const int32_t picked = pick_solver(p, batch, solver);
+  if (picked == FDM_SOLVER_LDLT_BAND) return ldlt_workspace_bytes(p, batch, batch);
+  size_t bytes = primary_workspace_bytes(p, batch, picked);
+  if (ldlt_fallback(p, picked)) bytes = align256(bytes) + ldlt_workspace_bytes(p, batch, ldlt_fallback_slots(p, batch));
+  return bytes;
 }
 
 int fdm_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info,
@@ -268,18 +287,43 @@ int fdm_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double*
     return FDM_ERR_INVALID;
   }
   int rc;
-  switch (pick_solver(p, batch, o.solver)) {
+  const int32_t picked = pick_solver(p, batch, o.solver);
+  bool nan_done = false;
+  switch (picked) {
     case FDM_SOLVER_PCG: rc = pcg_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st); break;
     case FDM_SOLVER_PCG_PERSISTENT: rc = pcg2_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st); break;
     case FDM_SOLVER_CHOLESKY_BATCHED:
       rc = chol_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, o, st);
-      if (chol_warp_supported(p)) return rc;             // its substitution kernel writes the NaNs itself
+      nan_done = chol_warp_supported(p);                 // its substitution kernel writes the NaNs itself
+      break;
+    case FDM_SOLVER_LDLT_BAND:
+      if (o.reuse_factor == 2) {
+        fdm_set_error("fdm_solve: the band L D L^T has no shared-factor mode");
+        return FDM_ERR_UNSUPPORTED;
+      }
+      rc = ldlt_solve(p, Kdata, rhs, x, info, ws, ws_bytes, batch, batch, 0, o.reuse_factor != 0, st);
       break;
     default:
       fdm_set_error("fdm_solve: unknown solver id");
       return FDM_ERR_INVALID;
   }
-  if (rc == FDM_OK && o.nan_on_failure) rc = launch_nan_failed(info, x, p->Nf * 3, batch, st);
+  // mixed-sign q behind a solver that needs a definite K: the designs it flagged go through the band L D L^T (the
+  // kernel returns at once for all others), when the caller's workspace has the room fdm_workspace_bytes asked for
+  if (rc == FDM_OK && info && ldlt_fallback(p, picked) && o.reuse_factor != 2) {
+    const size_t off = align256(primary_workspace_bytes(p, batch, picked));
+    const int64_t slots = ldlt_fallback_slots(p, batch);
+    if (ws_bytes >= off + ldlt_workspace_bytes(p, batch, slots)) {
+      rc = ldlt_solve(p, Kdata, rhs, x, info, static_cast<char*>(ws) + off, ws_bytes - off, batch, slots,
+                      picked == FDM_SOLVER_CHOLESKY_BATCHED ? 1 : 2, o.reuse_factor != 0, st);
+      nan_done = false;                                  // a design the fallback solved must lose its NaNs
+      if (rc == FDM_OK && o.nan_on_failure && chol_warp_supported(p) && picked == FDM_SOLVER_CHOLESKY_BATCHED) {
+        // (the warp kernels wrote NaN for the designs they gave up on before the fallback ran: it has overwritten x for
+        //  the ones it solved, the others keep their NaN)
+        nan_done = true;
+      }
+    }
+  }
+  if (rc == FDM_OK && o.nan_on_failure && !nan_done) rc = launch_nan_failed(info, x, p->Nf * 3, batch, st);
   return rc;
 }
 

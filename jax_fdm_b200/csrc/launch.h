@@ -123,6 +123,13 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
                            double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss,
                            int64_t ls, const fdm_solve_opts& o, cudaStream_t st);
 
+// solver_ldlt.cu  (band L D L^T in global memory, one CTA per design: the fallback for indefinite K)
+bool ldlt_supported(const fdm_plan* p);
+int64_t ldlt_fallback_slots(const fdm_plan* p, int64_t batch);
+size_t ldlt_workspace_bytes(const fdm_plan* p, int64_t batch, int64_t slots);
+int ldlt_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double* x, double* info, void* ws,
+               size_t ws_bytes, int64_t batch, int64_t slots, int only_failed, bool reuse, cudaStream_t st);
+
 // solver_pcg2.cu  (persistent two-level PCG)
 size_t pcg2_workspace_bytes(const fdm_plan* p);
 bool pcg2_supported(const fdm_plan* p);

@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(kThreads, 1) pcg2_kernel(Pcg2Args a) {
   int status = indefinite ? FDM_STATUS_INDEFINITE : FDM_STATUS_OK;
   const bool zero_rhs = (bb0 == 0.0 && bb1 == 0.0 && bb2 == 0.0);
 
-  while (!zero_rhs) {
+  // a mixed-sign diagonal: K is indefinite, CG has nothing to offer -- report at once (the band L D L^T takes over,
+  // solver_ldlt.cu); the flag comes from the all-gathered sums above, so every CTA takes the same branch
+  while (!zero_rhs && !indefinite) {
     const uint32_t tag = (uint32_t)it + 1u;
     PROF(t0 = clock64();)
     // ---- coarse residual recurrence + coarse solve for the own aggregate (warps 0..2) ----

@@ -106,22 +106,31 @@ def test_mixed_sign_designs_are_solved_with_signed_pivots(nx, ny, batch):
     assert torch.equal(x2, x) and torch.equal(info2[:, :4].cpu(), torch.as_tensor(info[:, :4]))
 
 
-def test_indefinite_design_is_flagged_at_half_bandwidth_31():
-    """The signed second pass exists for the tensor-core kernels (hbw <= 30); the rank-1 kernel keeps the flag."""
+def test_indefinite_design_is_flagged_at_half_bandwidth_31_without_the_fallback_workspace():
+    """The signed second pass exists for the tensor-core kernels (hbw <= 30); the rank-1 kernel flags the design and
+    the band L D L^T (solver_ldlt.cu, tests/test_gpu_ldlt.py) takes it over -- when the caller's workspace has the room
+    fdm_workspace_bytes asks for.  A workspace sized for the Cholesky alone keeps the flag."""
+    import ctypes as C
     import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import _lib as L
 
     m, supports, q, xs, loads = strip_problem(32, 34, 1.0, seed=3)
     s = eq.EquilibriumStructureSparse(m.nodes, m.edges, supports, device=0)
     qb = np.stack([q, q * np.where(np.arange(q.size) % 2, -1.0, 1.0), q])
     K, rhs = eq.ops.assemble(s, T(qb), T(xs), T(loads))
-    _, info = eq.ops.solve(s, K, rhs, solver="cholesky", return_info=True)
+    lib = L.lib()
+    need = int(lib.fdm_workspace_bytes(s.plan, 3, L.SOLVERS["cholesky"]))
+    per = (s.num_free * (s.half_bandwidth + 1) + 4 * s.num_free) * 8              # solver_ldlt.cu: bytes per slot
+    slots = min(3, max(1, (256 << 20) // per))
+    chol_only = need - (256 + 256 + slots * per)                                  # what the Cholesky alone needs
+    assert chol_only > 0
+    P = lambda t: C.c_void_p(t.data_ptr())
+    x, info = torch.empty_like(rhs), torch.zeros(3, 8, dtype=rhs.dtype, device=rhs.device)
+    ws = torch.empty(chol_only, dtype=torch.uint8, device=rhs.device)
+    opts = L.SolveOpts(L.SOLVERS["cholesky"], 0, 0.0, 0, 0, 0, 0)
+    L.check(lib.fdm_solve(s.plan, P(K), P(rhs), P(x), P(info), P(ws), ws.numel(), 3, C.byref(opts), None))
     st = info[:, 0].cpu().numpy()
     assert st[0] == 0 and st[2] == 0 and st[1] == 2        # FDM_STATUS_INDEFINITE for the mixed-sign design only
-    # the model level hands NaN to the caller for that design (the reference's optimisers check for it)
-    model = eq.EquilibriumModelSparse(tmax=1, solver="cholesky")
-    state = model(eq.EquilibriumParametersState(T(qb), T(xs), eq.LoadState(T(loads), 0.0, 0.0)), s)
-    finite = torch.isfinite(state.xyz).flatten(1).all(dim=1).cpu().numpy()
-    assert finite[0] and finite[2] and not finite[1]
 
 
 def test_band_too_wide_is_refused_and_auto_uses_pcg():

@@ -174,6 +174,41 @@ ffi::Error AdjointGradsImpl(cudaStream_t stream, int64_t plan, F64 q, F64 xyz, F
                                   fdm_plan_size(p, FDM_SIZE_EDGES), /*accumulate=*/0, stream));
 }
 
+// ---- forward mode of the state: (q, xyz, q_dot, xyz_dot, loads_dot) -> tangents of the state   jax.jvp of models.py:780-794
+ffi::Error StateJvpImpl(cudaStream_t stream, int64_t plan, F64 q, F64 xyz, F64 q_dot, F64 xyz_dot, F64 loads_dot,
+                        F64R vectors_dot, F64R lengths_dot, F64R forces_dot, F64R residuals_dot) {
+  fdm_plan* p = plan_of(plan);
+  const int64_t E = fdm_plan_size(p, FDM_SIZE_EDGES), N = fdm_plan_size(p, FDM_SIZE_NODES);
+  // T tangents may share one primal: a primal without the leading axis has stride 0
+  return status(fdm_state_jvp(p, q.typed_data(), xyz.typed_data(), q_dot.typed_data(), xyz_dot.typed_data(),
+                              loads_dot.typed_data(), vectors_dot->typed_data(), lengths_dot->typed_data(),
+                              forces_dot->typed_data(), residuals_dot->typed_data(), batch_of(xyz_dot, 2),
+                              stride_of(q, 1, E), stride_of(xyz, 2, N * 3), stride_of(q_dot, 1, E),
+                              stride_of(loads_dot, 2, N * 3), stream));
+}
+
+// ---- Kbar on the pattern and its pull-back to q_bar      sparse.py:299-306, transpose of models.py:1069-1077
+ffi::Error KbarPatternImpl(cudaStream_t stream, int64_t plan, double sign, F64 a, F64 b, F64R Kbar) {
+  return status(fdm_kbar_pattern(plan_of(plan), a.typed_data(), b.typed_data(), Kbar->typed_data(), sign, batch_of(a, 2),
+                                 stream));
+}
+ffi::Error StiffnessVjpImpl(cudaStream_t stream, int64_t plan, F64 Kbar, F64R q_bar) {
+  return status(fdm_stiffness_vjp(plan_of(plan), Kbar.typed_data(), q_bar->typed_data(), batch_of(Kbar, 1), stream));
+}
+
+// ---- tributary face loads (mesh structures)              models.py:333-344, loads.py:35-288
+using S32 = ffi::Buffer<ffi::S32>;
+ffi::Error FaceLoadsImpl(cudaStream_t stream, int64_t plan, int64_t is_local, S32 faces, S32 edges_faces, F64 xyz,
+                         F64 loads_nodes, F64 faces_load, F64R centroids, F64R gl, F64R loads_out) {
+  fdm_plan* p = plan_of(plan);
+  const int64_t N = fdm_plan_size(p, FDM_SIZE_NODES);
+  const int64_t F = (int64_t)faces.dimensions()[0], D = (int64_t)faces.dimensions()[1];
+  return status(fdm_face_loads(p, faces.typed_data(), F, D, edges_faces.typed_data(), xyz.typed_data(),
+                               loads_nodes.typed_data(), faces_load.typed_data(), centroids->typed_data(), gl->typed_data(),
+                               loads_out->typed_data(), batch_of(xyz, 2), stride_of(loads_nodes, 2, N * 3),
+                               stride_of(faces_load, 2, F * 3), (int)is_local, stream));
+}
+
 }  // namespace
 
 #define FDM_STREAM .Ctx<ffi::PlatformStream<cudaStream_t>>().Attr<int64_t>("plan")
@@ -211,3 +246,12 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_state_vjp, StateVjpImpl,
                                   .Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
 XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_adjoint_grads, AdjointGradsImpl,
                               ffi::Ffi::Bind() FDM_STREAM.Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_state_jvp, StateJvpImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>().Arg<F64>()
+                                  .Ret<F64>().Ret<F64>().Ret<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_kbar_pattern, KbarPatternImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Attr<double>("sign").Arg<F64>().Arg<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_stiffness_vjp, StiffnessVjpImpl, ffi::Ffi::Bind() FDM_STREAM.Arg<F64>().Ret<F64>());
+XLA_FFI_DEFINE_HANDLER_SYMBOL(fdm_b200_face_loads, FaceLoadsImpl,
+                              ffi::Ffi::Bind() FDM_STREAM.Attr<int64_t>("is_local")
+                                  .Arg<S32>().Arg<S32>().Arg<F64>().Arg<F64>().Arg<F64>().Ret<F64>().Ret<F64>().Ret<F64>());

@@ -31,7 +31,8 @@ from . import _lib as L
 
 _XLA_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfdm_b200_xla.so")
 _TARGETS = ["assemble", "solve", "solve_reuse", "solve_from_q", "spmm", "positions", "state", "state_vjp",
-            "adjoint_grads", "edge_loads", "edge_loads_vjp", "loss_sqdist"]
+            "adjoint_grads", "edge_loads", "edge_loads_vjp", "loss_sqdist", "state_jvp", "kbar_pattern", "stiffness_vjp",
+            "face_loads"]
 _registered = False
 
 
@@ -100,6 +101,25 @@ class Ops:
         lead = xyz.shape[:-2]
         return self._call("edge_loads_vjp", (_f64(*xyz.shape), _f64(*lead, self.E, 3)), xyz, edges_load, cot,
                           is_local=int(is_local))
+
+    def face_loads(self, faces, edges_faces, xyz, loads_nodes, faces_load, is_local=False):
+        """nodes_load with tributary face loads (mesh structures): returns (centroids, gl scratch, loads)."""
+        lead = xyz.shape[:-2]
+        F, D = faces.shape
+        outs = (_f64(*lead, F, 3), _f64(*lead, F, D, 3), _f64(*xyz.shape))
+        return self._call("face_loads", outs, faces, edges_faces, xyz, loads_nodes, faces_load, is_local=int(is_local))
+
+    def state_jvp(self, q, xyz, q_dot, xyz_dot, loads_dot):
+        lead = xyz_dot.shape[:-2]
+        outs = (_f64(*lead, self.E, 3), _f64(*lead, self.E), _f64(*lead, self.E), _f64(*lead, self.N, 3))
+        return self._call("state_jvp", outs, q, xyz, q_dot, xyz_dot, loads_dot)
+
+    def kbar_pattern(self, a, b, sign=-1.0):
+        """Kbar.data = sign * a[row] . b[col] on the pattern (sparse.py:299-306)."""
+        return self._call("kbar_pattern", _f64(*a.shape[:-2], self.nnz), a, b, sign=float(sign))
+
+    def stiffness_vjp(self, kbar_data):
+        return self._call("stiffness_vjp", _f64(*kbar_data.shape[:-1], self.E), kbar_data)
 
     def loss_sqdist(self, x, x0):
         return self._call("loss_sqdist", (_f64(*x.shape), _f64(*x.shape[:-2])), x, x0)

@@ -29,7 +29,7 @@ def main():
     lib = L.lib()
     P = lambda t: C.c_void_p(t.data_ptr())
     st = C.c_void_p(pipe.stream.cuda_stream)
-    E, Nf, nnz = s.num_edges, s.num_free, s.nnz
+    E, Nf, nnz, N, Ns = s.num_edges, s.num_free, s.nnz, s.num_nodes, s.num_supports
     fb = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     rb = torch.ones(64 << 20, dtype=torch.float64, device=dev)       # 512 MB, read after the write-flush
@@ -56,6 +56,12 @@ def main():
         ("fill rhs+8B", 24 * Nf, lambda: (pipe.rhs.view(-1)[1:].fill_(1.0), 0)[1]),
         ("fill rhs f32x2", 24 * Nf, lambda: (pipe.rhs.view(torch.float32).fill_(1.0), 0)[1]),
         ("copy K->K2", 16 * nnz, lambda: (K2.copy_(pipe.K), 0)[1]),
+        ("state", 8 * E + 24 * N + 40 * E + 24 * N,
+         lambda: lib.fdm_state(s.plan, P(pipe.q), P(pipe.xyz), P(pipe.loads), P(pipe.vectors), P(pipe.lengths),
+                               P(pipe.forces), P(pipe.residuals), B, E, 0, st)),
+        ("grads", 8 * E + 24 * N + 24 * Nf + 8 * E + 24 * N + 24 * Ns,
+         lambda: lib.fdm_adjoint_grads(s.plan, P(pipe.q), P(pipe.xyz), P(pipe.lam), P(pipe.q_bar), P(pipe.loads_bar),
+                                       P(pipe.xs_bar), B, E, 0, st)),
         ("loss", 48 * Nf + 8,
          lambda: lib.fdm_loss_sqdist(P(pipe.x), P(pipe.x0), P(pipe.g), P(pipe.loss), Nf * 3, B, 0, st)),
         ("spmm", 8 * nnz + 48 * Nf, lambda: lib.fdm_spmm(s.plan, P(pipe.K), P(pipe.x), P(Y), B, st)),

@@ -180,17 +180,42 @@ def test_kbar_on_pattern_and_its_q_transpose_vs_dense_algebra():
     assert np.allclose(qbar, Kbar @ basis.T, rtol=1e-13, atol=1e-13)
 
 
-def test_fdm_front_door_fails_loudly_on_an_unsolvable_system():
-    """Mixed-sign q on a band too wide for the signed factorisation: the kernels flag INDEFINITE and hand back NaN;
-    `fdm()` turns that into an exception instead of returning NaN positions (the reference's pivoted LU would solve
-    it; this build says so rather than guessing).  The same call with a definite q succeeds."""
+def test_fdm_front_door_solves_mixed_sign_q_and_fails_loudly_when_a_design_stays_unsolved():
+    """Mixed-sign q on a band too wide for the signed warp factorisation: the solver in front flags the design and the
+    band L D L^T solves it, as the reference's LU does (checked against SuperLU).  When a design does come back
+    unsolved (here: the same system with the fallback switched off) the kernels hand back NaN and `fdm()` turns that
+    into an exception instead of returning NaN positions."""
     import jax_fdm_b200.equilibrium as eq
+    import oracle
     prob = datasets.cablenet_problem(40, seed=1)
     s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    so = oracle.build_structure(prob.nodes, prob.edges, prob.supports)
     assert s.half_bandwidth > 30
     st, _ = eq.fdm(prob.nodes, prob.edges, prob.supports, prob.q, prob.xyz_fixed, prob.loads, structure=s)
     assert bool(torch.isfinite(st.xyz).all())
     q = prob.q.copy()
     q[::3] *= -1.0
-    with pytest.raises(FloatingPointError):
-        eq.fdm(prob.nodes, prob.edges, prob.supports, q, prob.xyz_fixed, prob.loads, structure=s)
+    st, _ = eq.fdm(prob.nodes, prob.edges, prob.supports, q, prob.xyz_fixed, prob.loads, structure=s)
+    xo = oracle.sparse_solve(oracle.stiffness_matrix_sparse(q, so), oracle.load_matrix(q, prob.xyz_fixed, prob.loads, so))
+    x = st.xyz.cpu().numpy()[np.asarray(so.indices_free)]
+    assert np.abs(x - xo).max() <= 1e-8 * np.abs(xo).max()
+    # with the fallback switched off (a process-wide switch, hence the child process) the kernels flag the design and
+    # hand back NaN, and the front door raises instead of returning NaN positions
+    import os
+    import subprocess
+    import sys
+    code = """
+import numpy as np, torch
+from jax_fdm_b200 import datasets
+import jax_fdm_b200.equilibrium as eq
+prob = datasets.cablenet_problem(40, seed=1)
+q = prob.q.copy(); q[::3] *= -1.0
+try:
+    eq.fdm(prob.nodes, prob.edges, prob.supports, q, prob.xyz_fixed, prob.loads)
+except FloatingPointError as e:
+    print("raised:", e)
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FDM_LDLT_FALLBACK="0", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+    assert "raised:" in r.stdout, r.stdout + r.stderr

@@ -10,7 +10,9 @@
 //   dinv[j] = 1/d_j and three work vectors.
 //   factor:   for j: l = A(j+1.., j) / d_j;  A(j+c.., j+c) -= l_c d_j l   (c = 1..hbw), blocked
 //   solve:    L y = P b (column sweep), y /= d, L^T z = y (row dots), x = P^T z
-//   a pivot below 1e-13 of the largest |diagonal| is a breakdown (FDM_STATUS_BREAKDOWN), as in the warp kernels.
+//   a pivot below 1e-13 of the largest |diagonal| is a breakdown (FDM_STATUS_BREAKDOWN), as in the warp kernels;
+//   the residual b - K x is formed against K.data, one step of iterative refinement follows when it is not at
+//   rounding level, and max ||r|| / ||b|| goes to FDM_INFO_RELRES (above 1e-6 the design is reported as a breakdown).
 //
 // `only_failed`: the kernel returns at once for every design whose status is not FDM_STATUS_INDEFINITE, so fdm_solve
 // can launch it behind another solver without a host round trip (CUDA-graph capturable).  Designs that do need it take
@@ -33,6 +35,8 @@ struct LArgs {
   int64_t nnz, per;                    // doubles per slot
   const int32_t* band_kidx;            // (n, hbw+1)
   const int32_t* band_iperm;           // band position -> free index
+  const int32_t* rowptr;               // CSR pattern of K (free order): the residual check
+  const int32_t* colidx;
   const double* Kdata;
   const double* rhs;
   double* x;
@@ -58,6 +62,53 @@ __device__ __forceinline__ void ldlt_load_panel(double* P, const double* Ab, int
     if (j0 + c + d < n) P[c * RP + c + d] = Ab[(int64_t)(j0 + c) * w + d];
   }
   __syncthreads();
+}
+
+// y (n, 3) in band order <- (L D L^T)^-1 y, block by block through shared memory
+__device__ void ldlt_substitute(double* P, double* sy, const double* Ab, const double* dinv, double* y, int n, int hbw,
+                                int RP, int tid) {
+  for (int j0 = 0; j0 < n; j0 += kNB) {                    // L y = b
+    const int nb = min(kNB, n - j0), R = min(nb + hbw, n - j0);
+    ldlt_load_panel(P, Ab, j0, nb, n, hbw, RP, tid);
+    for (int i = tid; i < 3 * R; i += kLThreads) sy[i] = y[3 * (int64_t)j0 + i];
+    __syncthreads();
+    for (int c = 0; c < nb; ++c) {
+      const double* pc = P + c * RP;
+      const int top = min(c + hbw, R - 1);
+      for (int i = tid; i < 3 * (top - c); i += kLThreads) {
+        const int r = c + 1 + i / 3, k = i % 3;
+        sy[3 * r + k] -= pc[r] * sy[3 * c + k];
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < 3 * R; i += kLThreads) y[3 * (int64_t)j0 + i] = sy[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += kLThreads) {               // y /= d
+    const double di = dinv[i];
+    y[3 * i] *= di; y[3 * i + 1] *= di; y[3 * i + 2] *= di;
+  }
+  __syncthreads();
+  for (int j0 = ((n - 1) / kNB) * kNB; j0 >= 0; j0 -= kNB) {   // L^T z = y
+    const int nb = min(kNB, n - j0), R = min(nb + hbw, n - j0);
+    ldlt_load_panel(P, Ab, j0, nb, n, hbw, RP, tid);
+    for (int i = tid; i < 3 * R; i += kLThreads) sy[i] = y[3 * (int64_t)j0 + i];
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int c = nb - 1; c >= 0; --c) {
+      if (warp < 3) {                                      // warp k: component k of row c
+        const double* pc = P + c * RP;
+        const int top = min(c + hbw, R - 1);
+        double acc = 0.0;
+        for (int r = c + 1 + lane; r <= top; r += 32) acc += pc[r] * sy[3 * r + warp];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) sy[3 * c + warp] -= acc;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < 3 * nb; i += kLThreads) y[3 * (int64_t)j0 + i] = sy[i];
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(kLThreads) ldlt_band_kernel(LArgs A) {
@@ -171,64 +222,72 @@ __global__ void __launch_bounds__(kLThreads) ldlt_band_kernel(LArgs A) {
     }
   }
   t_factored = clock64();
-  // ---- substitutions, three right-hand sides, block by block through shared memory
+  // ---- three right-hand sides: solve, residual against K.data, one step of iterative refinement when the residual
+  //      is not at rounding level (no pivoting: element growth can cost digits on an indefinite K), residual reported
+  const double* Kd = A.Kdata + (int64_t)b * A.nnz;
+  const double* rhs = A.rhs + (int64_t)b * n * 3;
+  double* x = A.x + (int64_t)b * n * 3;
+  __shared__ double s_red[6];
+  auto residual_into_y = [&]() {                           // y_j = b_f - (K x)_f, f = iperm[j]; returns max ||r|| / ||b||
+    if (tid < 6) s_red[tid] = 0.0;
+    __syncthreads();
+    double rr[3] = {0.0, 0.0, 0.0}, bb[3] = {0.0, 0.0, 0.0};
+    for (int j = tid; j < n; j += kLThreads) {
+      const int f = __ldg(A.band_iperm + j);
+      double r0 = rhs[3 * f], r1 = rhs[3 * f + 1], r2 = rhs[3 * f + 2];
+      bb[0] += r0 * r0; bb[1] += r1 * r1; bb[2] += r2 * r2;
+      for (int k = __ldg(A.rowptr + f); k < __ldg(A.rowptr + f + 1); ++k) {
+        const double v = Kd[k];
+        const double* xc = x + 3 * (int64_t)__ldg(A.colidx + k);
+        r0 -= v * xc[0]; r1 -= v * xc[1]; r2 -= v * xc[2];
+      }
+      y[3 * j] = r0; y[3 * j + 1] = r1; y[3 * j + 2] = r2;
+      rr[0] += r0 * r0; rr[1] += r1 * r1; rr[2] += r2 * r2;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      for (int o = 16; o > 0; o >>= 1) {
+        rr[k] += __shfl_xor_sync(0xffffffffu, rr[k], o);
+        bb[k] += __shfl_xor_sync(0xffffffffu, bb[k], o);
+      }
+      if ((tid & 31) == 0) { atomicAdd(&s_red[k], rr[k]); atomicAdd(&s_red[3 + k], bb[k]); }
+    }
+    __syncthreads();
+    double rel = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rel = fmax(rel, s_red[3 + k] > 0.0 ? sqrt(s_red[k] / s_red[3 + k]) : 0.0);
+    __syncthreads();
+    return rel;
+  };
   for (int i = tid; i < n; i += kLThreads) {
     const int f = __ldg(A.band_iperm + i);
-    const double* r = A.rhs + ((int64_t)b * n + f) * 3;
-    y[3 * i] = r[0]; y[3 * i + 1] = r[1]; y[3 * i + 2] = r[2];
+    y[3 * i] = rhs[3 * f]; y[3 * i + 1] = rhs[3 * f + 1]; y[3 * i + 2] = rhs[3 * f + 2];
   }
   __syncthreads();
-  for (int j0 = 0; j0 < n; j0 += kNB) {                    // L y = b
-    const int nb = min(kNB, n - j0), R = min(nb + hbw, n - j0);
-    ldlt_load_panel(P, Ab, j0, nb, n, hbw, RP, tid);
-    for (int i = tid; i < 3 * R; i += kLThreads) sy[i] = y[3 * (int64_t)j0 + i];
-    __syncthreads();
-    for (int c = 0; c < nb; ++c) {
-      const double* pc = P + c * RP;
-      const int top = min(c + hbw, R - 1);
-      for (int i = tid; i < 3 * (top - c); i += kLThreads) {
-        const int r = c + 1 + i / 3, k = i % 3;
-        sy[3 * r + k] -= pc[r] * sy[3 * c + k];
-      }
-      __syncthreads();
-    }
-    for (int i = tid; i < 3 * R; i += kLThreads) y[3 * (int64_t)j0 + i] = sy[i];
-    __syncthreads();
-  }
-  for (int i = tid; i < n; i += kLThreads) {               // y /= d
-    const double di = dinv[i];
-    y[3 * i] *= di; y[3 * i + 1] *= di; y[3 * i + 2] *= di;
-  }
-  __syncthreads();
-  for (int j0 = ((n - 1) / kNB) * kNB; j0 >= 0; j0 -= kNB) {   // L^T z = y
-    const int nb = min(kNB, n - j0), R = min(nb + hbw, n - j0);
-    ldlt_load_panel(P, Ab, j0, nb, n, hbw, RP, tid);
-    for (int i = tid; i < 3 * R; i += kLThreads) sy[i] = y[3 * (int64_t)j0 + i];
-    __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int c = nb - 1; c >= 0; --c) {
-      if (warp < 3) {                                      // warp k: component k of row c
-        const double* pc = P + c * RP;
-        const int top = min(c + hbw, R - 1);
-        double acc = 0.0;
-        for (int r = c + 1 + lane; r <= top; r += 32) acc += pc[r] * sy[3 * r + warp];
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) sy[3 * c + warp] -= acc;
-      }
-      __syncthreads();
-    }
-    for (int i = tid; i < 3 * nb; i += kLThreads) y[3 * (int64_t)j0 + i] = sy[i];
-    __syncthreads();
-  }
+  ldlt_substitute(P, sy, Ab, dinv, y, n, hbw, RP, tid);
   for (int i = tid; i < n; i += kLThreads) {
     const int f = __ldg(A.band_iperm + i);
-    double* o = A.x + ((int64_t)b * n + f) * 3;
-    o[0] = y[3 * i]; o[1] = y[3 * i + 1]; o[2] = y[3 * i + 2];
+    x[3 * f] = y[3 * i]; x[3 * f + 1] = y[3 * i + 1]; x[3 * f + 2] = y[3 * i + 2];
+  }
+  __syncthreads();
+  double rel = residual_into_y();
+  int refined = 0;
+  if (rel > 1e-13 && isfinite(rel)) {
+    ldlt_substitute(P, sy, Ab, dinv, y, n, hbw, RP, tid);
+    for (int i = tid; i < n; i += kLThreads) {
+      const int f = __ldg(A.band_iperm + i);
+      x[3 * f] += y[3 * i]; x[3 * f + 1] += y[3 * i + 1]; x[3 * f + 2] += y[3 * i + 2];
+    }
+    __syncthreads();
+    rel = residual_into_y();
+    refined = 1;
   }
   if (tid == 0) {
-    info[FDM_INFO_STATUS] = (double)FDM_STATUS_OK;
-    info[FDM_INFO_ITERS] = 0.0;
-    info[FDM_INFO_RELRES] = 0.0;
+    // a solution that does not satisfy the system is not handed out as one (the sums are atomics: the residual is
+    // reproducible to rounding only, the solution itself is deterministic)
+    info[FDM_INFO_STATUS] = rel <= 1e-6 ? (double)FDM_STATUS_OK : (double)FDM_STATUS_BREAKDOWN;
+    info[FDM_INFO_ITERS] = (double)refined;
+    info[FDM_INFO_RELRES] = rel;
     info[FDM_INFO_SIGN] = 0.0;
     // slots 4..6: cycles spent loading the band, factoring, substituting (diagnostic)
     info[4] = (double)(t_loaded - t_start); info[5] = (double)(t_factored - t_loaded); info[6] = (double)(clock64() - t_factored);
@@ -269,6 +328,7 @@ int ldlt_solve(const fdm_plan* p, const double* Kdata, const double* rhs, double
   A.only_failed = only_failed; A.reuse = reuse ? 1 : 0;
   A.nnz = p->nnz; A.per = per_design(p);
   A.band_kidx = p->d.band_kidx; A.band_iperm = p->d.band_iperm;
+  A.rowptr = p->d.rowptr; A.colidx = p->d.colidx;
   A.Kdata = Kdata; A.rhs = rhs; A.x = x; A.info = info;
   char* w = static_cast<char*>(ws);
   A.counter = reinterpret_cast<int32_t*>(w);

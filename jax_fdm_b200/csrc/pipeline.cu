@@ -98,12 +98,12 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   if (f->fused) {
     rc = fdm_solve_from_q(p, f->q.at(o), f->xs.p, f->loads.p, f->x.at(o), f->info_f.at(o), c.ws, c.ws_bytes, B, E, 0, 0,
                           &so, st);
-    n += 2;
+    n += 4;                                   // factor, signed second pass, substitution, residual check of signed designs
   } else {
     rc = fdm_assemble(p, f->q.at(o), f->xs.p, f->loads.p, f->K.at(o), f->rhs.at(o), B, E, 0, 0, st);
     if (rc != FDM_OK) return rc;
     rc = fdm_solve(p, f->K.at(o), f->rhs.at(o), f->x.at(o), f->info_f.at(o), c.ws, c.ws_bytes, B, &so, st);
-    n += 2;
+    n += 2 + 4;                               // assembly (K.data, rhs) + the band Cholesky's four (other solvers differ)
   }
   if (rc != FDM_OK) return rc;
   rc = fdm_positions(p, f->x.at(o), f->xs.p, f->xyz.at(o), B, 0, 0, st);

@@ -1304,6 +1304,100 @@ size_t chol_warp_workspace_bytes(const fdm_plan* p, int64_t batch) {
 
 bool chol_warp_from_q_supported(const fdm_plan* p) { return chol_warp_supported(p) && p->hbw <= 30; }
 
+// -------------------------------------------------------------------------------------------
+// Designs factored with signed pivots (mixed-sign q: sigma K = L D L^T without pivoting) get their residual checked:
+// element growth can cost digits there and nothing else would notice.  One CTA per design, returning at once unless
+// the design was solved that way (FDM_INFO_SIGN 0, status OK): r = b - K x from q (the operator of models.py:1064-1079
+// applied edge by edge: r_f = p_f - sum_inc q_e (x_f - x_other), b_f = p_f + sum_{e to support} q_e x_s) or from
+// K.data and the right-hand side; max ||r|| / ||b|| over the three right-hand sides goes to FDM_INFO_RELRES, and a
+// design above 1e-6 is reported as a breakdown (NaN positions under nan_on_failure) instead of being handed out.
+// -------------------------------------------------------------------------------------------
+struct RArgs {
+  int n, batch, from_q, nan_fail;
+  int64_t nnz, q_stride, xs_stride, loads_stride;
+  const double *q, *xs, *loads, *Kdata, *rhs;
+  const int32_t *rowptr, *colidx, *free_node, *node_slot, *ninc_ptr, *ninc_edge, *ninc_other;
+  double *x, *info;
+};
+
+__global__ void __launch_bounds__(256) signed_residual_check_kernel(RArgs A) {
+  const int b = blockIdx.x, tid = threadIdx.x, n = A.n;
+  double* info = A.info + (int64_t)b * FDM_INFO_STRIDE;
+  if (info[FDM_INFO_SIGN] != 0.0 || info[FDM_INFO_STATUS] != (double)FDM_STATUS_OK) return;
+  __shared__ double s_red[6];
+  if (tid < 6) s_red[tid] = 0.0;
+  __syncthreads();
+  double* x = A.x + (int64_t)b * n * 3;
+  double rr[3] = {0.0, 0.0, 0.0}, bb[3] = {0.0, 0.0, 0.0};
+  for (int f = tid; f < n; f += 256) {
+    const double xf[3] = {x[3 * f], x[3 * f + 1], x[3 * f + 2]};
+    double r[3], rhs[3];
+    if (A.from_q) {
+      const double* q = A.q + b * A.q_stride;
+      const double* xs = A.xs + b * A.xs_stride;
+      const int node = __ldg(A.free_node + f);
+      const double* p = A.loads + b * A.loads_stride + 3 * (int64_t)node;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { r[c] = p[c]; rhs[c] = p[c]; }
+      for (int k = __ldg(A.ninc_ptr + node); k < __ldg(A.ninc_ptr + node + 1); ++k) {
+        const double qe = q[__ldg(A.ninc_edge + k) >> 1];
+        const int slot = __ldg(A.node_slot + __ldg(A.ninc_other + k));
+        const double* xo = slot >= 0 ? x + 3 * (int64_t)slot : xs + 3 * (int64_t)(-slot - 1);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          r[c] -= qe * (xf[c] - xo[c]);
+          if (slot < 0) rhs[c] += qe * xo[c];
+        }
+      }
+    } else {
+      const double* Kd = A.Kdata + (int64_t)b * A.nnz;
+      const double* g = A.rhs + ((int64_t)b * n + f) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { r[c] = g[c]; rhs[c] = g[c]; }
+      for (int k = __ldg(A.rowptr + f); k < __ldg(A.rowptr + f + 1); ++k) {
+        const double v = Kd[k];
+        const double* xc = x + 3 * (int64_t)__ldg(A.colidx + k);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[c] -= v * xc[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { rr[c] += r[c] * r[c]; bb[c] += rhs[c] * rhs[c]; }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      rr[c] += __shfl_xor_sync(kFull, rr[c], o);
+      bb[c] += __shfl_xor_sync(kFull, bb[c], o);
+    }
+    if ((tid & 31) == 0) { atomicAdd(&s_red[c], rr[c]); atomicAdd(&s_red[3 + c], bb[c]); }
+  }
+  __syncthreads();
+  double rel = 0.0;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) rel = fmax(rel, s_red[3 + c] > 0.0 ? sqrt(s_red[c] / s_red[3 + c]) : 0.0);
+  const bool ok = rel <= 1e-6;                                       // false for NaN too
+  if (tid == 0) {
+    info[FDM_INFO_RELRES] = rel;
+    if (!ok) info[FDM_INFO_STATUS] = (double)FDM_STATUS_BREAKDOWN;
+  }
+  if (!ok && A.nan_fail)
+    for (int i = tid; i < 3 * n; i += 256) x[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+static int launch_signed_check(const fdm_plan* p, const WArgs& W, int64_t batch, bool from_q, cudaStream_t st) {
+  if (!W.info) return FDM_OK;
+  RArgs A;
+  A.n = W.n; A.batch = (int)batch; A.from_q = from_q ? 1 : 0; A.nan_fail = W.nan_fail;
+  A.nnz = W.nnz; A.q_stride = W.q_stride; A.xs_stride = W.xs_stride; A.loads_stride = W.loads_stride;
+  A.q = W.q; A.xs = W.xs; A.loads = W.loads; A.Kdata = W.Kdata; A.rhs = W.rhs;
+  A.rowptr = p->d.rowptr; A.colidx = p->d.colidx; A.free_node = p->d.free_node; A.node_slot = p->d.node_slot;
+  A.ninc_ptr = p->d.ninc_ptr; A.ninc_edge = p->d.ninc_edge; A.ninc_other = p->d.ninc_other;
+  A.x = W.x; A.info = W.info;
+  signed_residual_check_kernel<<<(unsigned)batch, 256, 0, st>>>(A);
+  return FDM_OK;
+}
+
 static void fill_common(WArgs& A, const fdm_plan* p, double* x, double* info, void* ws, int64_t batch) {
   A.n = (int)p->Nf;
   A.bw = p->hbw;
@@ -1388,6 +1482,7 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   if (stages & 4) {
     int rc = launch_backward(p, A, batch, st, inflight);
     if (rc != FDM_OK) return rc;
+    if (stages & 1) launch_signed_check(p, A, batch, true, st);
   }
   return fdm_check_launch("chol_warp_solve_from_q");
 }
@@ -1463,6 +1558,9 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
   if (stages & 4) {
     int rc = launch_backward(p, A, batch, st, std::max<int64_t>(batch, o.concurrent_designs));
     if (rc != FDM_OK) return rc;
+    // (not for a solve with a stored factor: the factor was checked when it was made, and a sliced caller that never
+    //  formed K.data passes a placeholder there)
+    if (mma && !o.reuse_factor && (stages & 1)) launch_signed_check(p, A, batch, false, st);
   }
   return fdm_check_launch("chol_warp_solve");
 }

@@ -657,6 +657,17 @@ def run_ours(args):
                   "relres_fwd": float(inf_f[2]), "relres_adj": float(inf_a[2]),
                   "status": [int(inf_f[0]), int(inf_a[0])]}
         cfa.close()
+        # one design of the headline topology: the latency an optimiser loop over a single structure sees per
+        # value-and-gradient (device-resident, one CUDA graph; the two-sided factorisation: a warp pair per design)
+        ofa = NativeForwardAdjoint(s, 1, solver="cholesky", device=local)
+        ofa.set_inputs(qb[:1], prob.xyz_fixed, prob.loads, x0)
+        for _ in range(3):
+            ofa.step(main_stream)
+        main_stream.synchronize()
+        t1 = timed_steps(lambda: ofa.step(main_stream), main_stream, k, flush_dev)
+        single["one_design_30x30"] = {"ms_per_value_and_grad": float(np.mean(t1)),
+                                      "how": "fdm_fa_step_device at batch 1 (pillow 30x30): latency, not throughput"}
+        ofa.close()
         sweep = sweep_large_mesh(SWEEP_NX, 5, flush_buf, hbm)
 
     if world > 1:

@@ -1312,6 +1312,8 @@ bool chol_warp_from_q_supported(const fdm_plan* p) { return chol_warp_supported(
 // K.data and the right-hand side; max ||r|| / ||b|| over the three right-hand sides goes to FDM_INFO_RELRES, and a
 // design above 1e-6 is reported as a breakdown (NaN positions under nan_on_failure) instead of being handed out.
 // -------------------------------------------------------------------------------------------
+namespace {
+
 struct RArgs {
   int n, batch, from_q, nan_fail;
   int64_t nnz, q_stride, xs_stride, loads_stride;
@@ -1384,6 +1386,8 @@ __global__ void __launch_bounds__(256) signed_residual_check_kernel(RArgs A) {
   if (!ok && A.nan_fail)
     for (int i = tid; i < 3 * n; i += 256) x[i] = __longlong_as_double(0x7ff8000000000000LL);
 }
+
+}  // namespace
 
 static int launch_signed_check(const fdm_plan* p, const WArgs& W, int64_t batch, bool from_q, cudaStream_t st) {
   if (!W.info) return FDM_OK;

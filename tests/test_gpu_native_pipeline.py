@@ -178,3 +178,41 @@ def test_failed_design_comes_back_as_nan_and_others_are_untouched():
     keep = [b for b in range(B) if b != 4]
     assert np.array_equal(l1[keep], l0[keep]) and np.array_equal(g1[keep], g0[keep])
     good.close(); bad.close()
+
+
+@pytest.mark.parametrize("chunks", [1, 4])
+def test_steps_enqueued_back_to_back_keep_their_own_losses(chunks):
+    """fdm_fa_enqueue_host twice without a wait in between, different q and different host buffers per step: the
+    per-design losses leave in ONE copy at the end of a step, parked in a staging row so that the next step's kernels
+    cannot overwrite them first.  Both steps must come back exactly as two synchronous steps do."""
+    import ctypes as C
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import _lib as L
+    from jax_fdm_b200.pipeline import NativeForwardAdjoint
+
+    prob = datasets.pillow_problem(12)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    B, E = 64, prob.edges.shape[0]
+    fa = NativeForwardAdjoint(s, B, chunks=chunks, solver="cholesky")
+    q1 = datasets.pillow_batch_q(E, 0, B)
+    q2 = datasets.pillow_batch_q(E, 1000, B)
+    fa.set_inputs(q1, prob.xyz_fixed, prob.loads, prob.xyz0[s.indices_free])
+    ref = []
+    for q in (q1, q2, q1):
+        fa.h_q[...] = q
+        loss, q_bar = fa()
+        ref.append((loss.copy(), q_bar.copy()))
+    assert not np.array_equal(ref[0][0], ref[1][0])
+    lib = fa.lib
+    bufs = []
+    for q in (q1, q2, q1):                                  # three steps: the staging rows alternate and are reused
+        hq, hl, hb = fa._host((B, E)), fa._host((B,)), fa._host((B, E))
+        hq[...] = q
+        hl[...] = -1.0
+        bufs.append((hq, hl, hb))
+    for hq, hl, hb in bufs:
+        L.check(lib.fdm_fa_enqueue_host(fa.handle, hq.ctypes.data, hl.ctypes.data, hb.ctypes.data))
+    L.check(lib.fdm_fa_wait(fa.handle))
+    for (hq, hl, hb), (rl, rb) in zip(bufs, ref):
+        assert np.array_equal(hl, rl) and np.array_equal(hb, rb)
+    fa.close()

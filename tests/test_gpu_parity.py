@@ -316,3 +316,48 @@ def test_batched_assembly_and_spmm_are_bit_identical_to_the_per_design_kernels(e
         L.check(L.lib().fdm_loss_sqdist(P(X[b]), P(x0), P(g1), P(l1), n, 1, 0, None))
         assert torch.equal(g1, gb[b]) and torch.equal(l1[0], lb[b])
     assert np.allclose(N(lb), 0.5 * ((N(X) - N(x0)[None]) ** 2).sum(axis=(1, 2)), rtol=1e-13)
+
+
+@pytest.mark.parametrize("B,G", [(8, 4096), (9, 4096), (37, 4096), (37, 4097)])
+def test_batched_kernels_write_only_their_outputs(eq, B, G):
+    """compute-sanitizer is closed on this pool, so the out-of-bounds check of the batched streaming kernels (TMA bulk
+    stores of two-design images, whole-design CTAs, persistent loss CTAs) is done with guard bands: every output sits
+    inside a larger buffer of sentinels, and the bands before and after it must come back untouched -- even and odd
+    batch sizes (the bulk stores work on pairs of designs)."""
+    import ctypes as C
+    from jax_fdm_b200 import _lib as L
+    g = load("pillow30")
+    s, _ = make(eq, g)
+    rng = np.random.default_rng(B)
+    E, Nf, nnz = g["q"].size, s.num_free, s.nnz
+    q = T(g["q"][None, :] * (1.0 + 0.2 * rng.random((B, E))))
+    xs, p = T(g["xyz_fixed"]), T(g["loads"])
+    # G guard doubles on each side; an odd G leaves the outputs 8-byte aligned only (no bulk stores, no 16-byte copies)
+    sentinel = 1234.5
+
+    def guarded(n):
+        buf = torch.full((n + 2 * G,), sentinel, dtype=torch.float64, device=q.device)
+        return buf, buf[G:G + n]
+
+    def intact(buf, n):
+        return bool((buf[:G] == sentinel).all()) and bool((buf[G + n:] == sentinel).all())
+
+    P = lambda t: C.c_void_p(t.data_ptr())
+    lib = L.lib()
+    Kb, K = guarded(B * nnz)
+    rb, rhs = guarded(B * Nf * 3)
+    L.check(lib.fdm_assemble(s.plan, P(q), P(xs), P(p), P(K), P(rhs), B, E, 0, 0, None))
+    X = T(rng.standard_normal((B, Nf, 3)))
+    Yb, Y = guarded(B * Nf * 3)
+    L.check(lib.fdm_spmm(s.plan, P(K), P(X), P(Y), B, None))
+    x0 = T(rng.standard_normal((Nf, 3)))
+    gb, gg = guarded(B * Nf * 3)
+    lb, ll = guarded(B)
+    L.check(lib.fdm_loss_sqdist(P(X), P(x0), P(gg), P(ll), Nf * 3, B, 0, None))
+    torch.cuda.synchronize()
+    assert intact(Kb, B * nnz) and intact(rb, B * Nf * 3) and intact(Yb, B * Nf * 3) and intact(gb, B * Nf * 3) and intact(lb, B)
+    # and everything inside was written
+    for t in (K, rhs, Y, gg, ll):
+        assert not bool((t == sentinel).any())
+    K2, rhs2 = eq.ops.assemble(s, q, xs, p)
+    assert torch.equal(K.view(B, nnz), K2) and torch.equal(rhs.view(B, Nf, 3), rhs2)

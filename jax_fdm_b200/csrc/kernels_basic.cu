@@ -250,6 +250,9 @@ assemble_K_batch_kernel(int E, int Nf, int nnz, int maxdeg, int64_t batch, const
       }
     }
   }
+  // launched as a programmatic dependent of the rhs kernel (launch_assemble): everything above ran while that grid was
+  // finishing; the rows next to supports written below must land after its stores (a no-op in an ordinary launch)
+  if (SUP) asm volatile("griddepcontrol.wait;" ::: "memory");
   int buf = 0;
   for (int64_t b = b_lo; b < b_hi; b += b_step, buf ^= 1) {
     if (SUP && !sup_shared && srow >= 0) {   // this design's load and support coordinates: issued before the wait for q
@@ -315,6 +318,9 @@ assemble_rhs_tma_kernel(int Nf, int64_t batch, int dpc, const int32_t* __restric
                         const double* __restrict__ loads, double* __restrict__ rhs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* img = reinterpret_cast<double*>(smem_raw);      // [2 * 3 Nf]
+  // programmatic dependent launch: the K.data kernel behind this one may start its CTAs now (they run their prologue
+  // and wait, `griddepcontrol.wait`, for this grid to finish before they touch the rhs)
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x;
   const int n3 = 3 * Nf;
   const int64_t b_lo = (int64_t)blockIdx.x * dpc;         // dpc is even: b_lo * n3 * 8 is a multiple of 16
@@ -1225,9 +1231,11 @@ int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const 
     const int sms = std::max(p->sm_count, 1);
     const int nsup = (int)p->rsup_rows.size();
     const bool sup_in_K = Kdata && rhs && nsup && p->asm_sup_in_K;
+    bool rhs_tma = false;
     if (rhs) {
       const int64_t img_bytes = 16 * 3 * (int64_t)p->Nf;
       if (ls == 0 && (reinterpret_cast<uintptr_t>(rhs) & 15) == 0 && img_bytes <= 96 * 1024) {
+        rhs_tma = true;
         FDM_CUDA(cudaFuncSetAttribute(assemble_rhs_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         int dpc = 2 * (int)std::max<int64_t>(1, (batch + 2 * sms - 1) / (2 * sms));       // even; one CTA per SM
         if (const char* e = std::getenv("FDM_RHS_DPC")) dpc = std::max(2, std::atoi(e) & ~1);
@@ -1247,9 +1255,22 @@ int launch_assemble(const fdm_plan* p, const double* q, const double* xs, const 
                                          : (sup_in_K ? assemble_K_batch_kernel<16, true> : assemble_K_batch_kernel<16, false>);
       FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       const int per_sm = std::max(1, std::min(3, (227 * 1024) / (smem + 1024)));          // resident CTAs per SM
-      kern<<<(unsigned)std::min<int64_t>(batch, (int64_t)sms * per_sm), kThreads, smem, st>>>(
-          (int)p->E, (int)p->Nf, (int)p->nnz, p->asm_maxdeg, batch, d.asm_code, d.diags_ptr, d.diags_idx, q, Kdata, qs,
-          nsup, d.rsup_rows, d.rsup_ptr, d.rsup_edge, d.rsup_slot, d.free_node, xs, loads, rhs, xss, ls);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)std::min<int64_t>(batch, (int64_t)sms * per_sm));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = (size_t)smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      static const bool pdl_off = std::getenv("FDM_ASM_PDL") && std::atoi(std::getenv("FDM_ASM_PDL")) == 0;
+      cfg.attrs = attr;
+      cfg.numAttrs = sup_in_K && rhs_tma && !pdl_off ? 1 : 0;      // only behind the bulk-store rhs kernel
+      FDM_CUDA(cudaLaunchKernelEx(&cfg, kern, (int)p->E, (int)p->Nf, (int)p->nnz, p->asm_maxdeg, batch,
+                                  (const int32_t*)d.asm_code, (const int32_t*)d.diags_ptr, (const int32_t*)d.diags_idx, q,
+                                  Kdata, qs, nsup, (const int32_t*)d.rsup_rows, (const int32_t*)d.rsup_ptr,
+                                  (const int32_t*)d.rsup_edge, (const int32_t*)d.rsup_slot, (const int32_t*)d.free_node, xs,
+                                  loads, rhs, xss, ls));
       if (int rc = fdm_check_launch("assemble_K_batch")) return rc;
     }
     if (rhs && nsup && !sup_in_K) {

@@ -119,7 +119,8 @@ int64_t fdm_plan_get_array(const fdm_plan* plan, int which, void* h_out, int64_t
  *     rhs = loads[indices_free] - C_f^T (q * (C_s xyz_fixed)).
  *   d_q (B,E)  d_xyz_fixed (B|1,Ns,3)  d_loads (B|1,N,3)  ->  d_Kdata (B,nnz)  d_rhs (B,Nf,3)
  * d_Kdata or d_rhs may be NULL to skip that half.
- */
+ * A batch (>= 8 designs) on a small topology takes streaming kernels that read the index streams once per launch
+ * (bit-identical output); every call is enqueued on `stream` only. */
 int fdm_assemble(const fdm_plan* plan, const double* d_q, const double* d_xyz_fixed,
                  const double* d_loads, double* d_Kdata, double* d_rhs, int64_t batch,
                  int64_t q_stride, int64_t xyz_fixed_stride, int64_t loads_stride, void* stream);
@@ -165,6 +166,10 @@ typedef struct fdm_solve_opts {
                            pays while SMs are short of warps */
 } fdm_solve_opts;
 
+/* Bytes of scratch fdm_solve / fdm_solve_from_q want for `batch` designs with this solver choice.  It includes room
+ * for the band L D L^T fallback behind solvers that need a definite K (up to 256 MB: min(batch, 256 MB / band size)
+ * designs can fall back in one call; nothing when one band alone is larger); a smaller workspace is accepted as long
+ * as it covers the solver itself -- the fallback is then skipped and such designs keep FDM_STATUS_INDEFINITE. */
 size_t fdm_workspace_bytes(const fdm_plan* plan, int64_t batch, int32_t solver);
 
 int fdm_solve(const fdm_plan* plan, const double* d_Kdata, const double* d_rhs, double* d_x,

@@ -254,7 +254,7 @@ static size_t primary_workspace_bytes(const fdm_plan* p, int64_t batch, int32_t 
 // Does a design this solver reports as indefinite go on to the band L D L^T?  The warp-per-design Cholesky handles
 // mixed-sign q itself up to half bandwidth 30; everything else with a band table does.
 static bool ldlt_fallback(const fdm_plan* p, int32_t picked) {
-  if (!ldlt_supported(p) || picked == FDM_SOLVER_LDLT_BAND) return false;
+  if (!ldlt_supported(p) || picked == FDM_SOLVER_LDLT_BAND || ldlt_fallback_slots(p, 1) < 1) return false;
   if (picked == FDM_SOLVER_CHOLESKY_BATCHED && chol_warp_supported(p) && p->hbw <= 30) return false;
   static const bool off = std::getenv("FDM_LDLT_FALLBACK") && std::atoi(std::getenv("FDM_LDLT_FALLBACK")) == 0;
   return !off;

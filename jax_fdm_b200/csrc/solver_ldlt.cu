@@ -301,10 +301,11 @@ inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 bool ldlt_supported(const fdm_plan* p) { return !p->band_kidx.empty() && p->d.band_kidx && p->d.band_iperm; }
 
-// slots of the fallback behind another solver: what fits 256 MB, at least one
+// slots of the fallback behind another solver: what fits 256 MB (none when a single band is larger than that: the
+// fallback must not multiply the workspace of a solver that would have done without it)
 int64_t ldlt_fallback_slots(const fdm_plan* p, int64_t batch) {
   const int64_t bytes = per_design(p) * 8;
-  return std::min<int64_t>(batch, std::max<int64_t>(1, (int64_t(256) << 20) / bytes));
+  return std::min<int64_t>(batch, (int64_t(256) << 20) / bytes);
 }
 
 size_t ldlt_workspace_bytes(const fdm_plan* p, int64_t batch, int64_t slots) {

@@ -126,7 +126,7 @@ def test_indefinite_design_is_flagged_at_half_bandwidth_31_without_the_fallback_
     lib = L.lib()
     need = int(lib.fdm_workspace_bytes(s.plan, 3, L.SOLVERS["cholesky"]))
     per = (s.num_free * (s.half_bandwidth + 1) + 4 * s.num_free) * 8              # solver_ldlt.cu: bytes per slot
-    slots = min(3, max(1, (256 << 20) // per))
+    slots = min(3, (256 << 20) // per)
     chol_only = need - (256 + 256 + slots * per)                                  # what the Cholesky alone needs
     assert chol_only > 0
     P = lambda t: C.c_void_p(t.data_ptr())

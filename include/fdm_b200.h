@@ -332,14 +332,18 @@ typedef struct fdm_goal_program {
   const int32_t* agg_index;   /* (sum of set sizes) */
 } fdm_goal_program;
 
-/* loss (B) [NULL in a reverse-only call]; group_sums (B,G) or NULL.  With the four cotangent arrays (all or
- * none) the kernel also writes loss_cot_b * d loss_b / d state: xyz_bar (B,N,3), lengths_bar (B,E), forces_bar
+/* loss (B) [NULL in a reverse-only call]; group_sums (B,G) or NULL.  With cotangent arrays the kernel also writes loss_cot_b * d loss_b / d state: xyz_bar (B,N,3), lengths_bar (B,E), forces_bar
  * (B,E), residuals_bar (B,N,3) -- the cotangents fdm_state_vjp takes; d_loss_cot (B) is the upstream cotangent of
- * the loss (NULL = 1). */
+ * the loss (NULL = 1).
+ * A cotangent array that no term of the program differentiates into (fdm_goal_kind_arrays) may be NULL --
+ * it is then neither zeroed nor written, and fdm_state_vjp takes a NULL cotangent as zero; an array a term does read
+ * must be given. */
 int fdm_goals_loss(const fdm_plan* plan, const fdm_goal_program* program, const double* d_xyz,
                    const double* d_lengths, const double* d_forces, const double* d_residuals, double* d_loss,
                    double* d_group_sums, const double* d_loss_cot, double* d_xyz_bar, double* d_lengths_bar,
                    double* d_forces_bar, double* d_residuals_bar, int64_t batch, void* stream);
+/* bit mask of the state arrays a goal kind differentiates into: 1 xyz, 2 lengths, 4 forces, 8 residuals */
+int fdm_goal_kind_arrays(int kind);
 
 /* ---- helper used by the benchmark's loss (above the path; kept here so the timed region
  * launches only this library's kernels): loss_b = 0.5 * sum (x - x0)^2, g = x - x0. */

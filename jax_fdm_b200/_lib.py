@@ -29,7 +29,7 @@ EXPORTS = [
     "fdm_plan_create", "fdm_plan_create_host", "fdm_plan_destroy", "fdm_plan_size",
     "fdm_plan_get_array", "fdm_assemble", "fdm_workspace_bytes", "fdm_solve", "fdm_solve_from_q", "fdm_spmm",
     "fdm_positions", "fdm_state", "fdm_state_vjp", "fdm_state_jvp", "fdm_adjoint_grads", "fdm_edge_loads",
-    "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_goals_loss", "fdm_loss_sqdist",
+    "fdm_edge_loads_vjp", "fdm_face_loads", "fdm_face_loads_vjp", "fdm_goals_loss", "fdm_goal_kind_arrays", "fdm_loss_sqdist",
     "fdm_fa_create", "fdm_fa_destroy", "fdm_fa_set_constants", "fdm_fa_set_goal_program", "fdm_fa_set_q",
     "fdm_fa_step_device", "fdm_fa_enqueue_host", "fdm_fa_enqueue_copies_only", "fdm_fa_wait", "fdm_fa_run_host", "fdm_fa_device_array", "fdm_fa_info",
     "fdm_fp_create", "fdm_fp_destroy", "fdm_fp_forward", "fdm_fp_adjoint", "fdm_fp_info",
@@ -132,6 +132,8 @@ def lib():
     L.fdm_face_loads_vjp.restype = C.c_int
     L.fdm_goals_loss.argtypes = [vp, C.POINTER(GoalProgram), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.fdm_goals_loss.restype = C.c_int
+    L.fdm_goal_kind_arrays.argtypes = [C.c_int]
+    L.fdm_goal_kind_arrays.restype = C.c_int
     L.fdm_loss_sqdist.argtypes = [vp, vp, vp, vp, i64, i64, i64, vp]
     L.fdm_loss_sqdist.restype = C.c_int
     L.fdm_fa_create.argtypes = [vp, i64, C.POINTER(FaOpts), C.POINTER(vp)]

@@ -480,7 +480,8 @@ int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* x
                    const double* loss_cot, double* xyz_bar, double* lengths_bar, double* forces_bar, double* residuals_bar,
                    int64_t batch, void* stream) {
   if (!ready(p, "fdm_goals_loss")) return FDM_ERR_INVALID;
-  if (!g || !xyz || !lengths || !forces || !residuals || (!loss && !xyz_bar) || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
+  const bool any_bar = xyz_bar || lengths_bar || forces_bar || residuals_bar;
+  if (!g || !xyz || !lengths || !forces || !residuals || (!loss && !any_bar) || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
       (g->num_terms > 0 && (!g->kind || !g->index || !g->error || !g->weight || !g->target)) ||
       (g->num_groups > 0 && (!g->group_ptr || !g->group_final || !g->group_inner || !g->group_outer))) {
     fdm_set_error("fdm_goals_loss: bad arguments");
@@ -493,11 +494,6 @@ int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* x
   if (g->num_groups > 64) {
     fdm_set_error("fdm_goals_loss: more than 64 error terms in one loss");
     return FDM_ERR_UNSUPPORTED;
-  }
-  const bool any_bar = xyz_bar || lengths_bar || forces_bar || residuals_bar;
-  if (any_bar && !(xyz_bar && lengths_bar && forces_bar && residuals_bar)) {
-    fdm_set_error("fdm_goals_loss: pass all four cotangent arrays or none");
-    return FDM_ERR_INVALID;
   }
   return launch_goals_loss(p, g->num_terms, g->kind, g->index, g->error, g->weight, g->target, g->num_groups,
                            g->group_ptr, g->group_final, g->group_inner, g->group_outer, g->has_network_loadpath,

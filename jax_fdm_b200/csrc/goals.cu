@@ -46,6 +46,11 @@ enum GoalKind : int {
   G_NODES_COLINEAR,           // colinearity energy of the ordered node sequence S (geometry.py:660-694)
 };
 constexpr int kMaxAgg = 16;    // aggregate goals per loss
+
+// scatter into a cotangent array; a NULL array is one no term of the program reads (fdm_goal_kind_arrays): skipped
+__device__ __forceinline__ void gadd(double* base, int idx, double v) {
+  if (base) atomicAdd(base + idx, v);
+}
 enum ErrKind : int { E_SQUARED = 0, E_ABSOLUTE, E_PREDICTION, E_LOGMAX };
 
 struct GoalArgs {
@@ -169,14 +174,21 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
   const double* res = A.residuals + b * (int64_t)A.N * 3;
   const double* len = A.lengths + b * (int64_t)A.E;
   const double* frc = A.forces + b * (int64_t)A.E;
-  const bool bwd = A.xyz_bar != nullptr;
-  double* xb = bwd ? A.xyz_bar + b * (int64_t)A.N * 3 : nullptr;
-  double* rb = bwd ? A.residuals_bar + b * (int64_t)A.N * 3 : nullptr;
-  double* lb = bwd ? A.lengths_bar + b * (int64_t)A.E : nullptr;
-  double* fb = bwd ? A.forces_bar + b * (int64_t)A.E : nullptr;
+  // reverse mode: any cotangent array given; an array no term of the program reads may be NULL (not zeroed, not written)
+  const bool bwd = A.xyz_bar || A.residuals_bar || A.lengths_bar || A.forces_bar;
+  double* xb = A.xyz_bar ? A.xyz_bar + b * (int64_t)A.N * 3 : nullptr;
+  double* rb = A.residuals_bar ? A.residuals_bar + b * (int64_t)A.N * 3 : nullptr;
+  double* lb = A.lengths_bar ? A.lengths_bar + b * (int64_t)A.E : nullptr;
+  double* fb = A.forces_bar ? A.forces_bar + b * (int64_t)A.E : nullptr;
   if (bwd) {
-    for (int i = threadIdx.x; i < 3 * A.N; i += kThreads) { xb[i] = 0.0; rb[i] = 0.0; }
-    for (int i = threadIdx.x; i < A.E; i += kThreads) { lb[i] = 0.0; fb[i] = 0.0; }
+    for (int i = threadIdx.x; i < 3 * A.N; i += kThreads) {
+      if (xb) xb[i] = 0.0;
+      if (rb) rb[i] = 0.0;
+    }
+    for (int i = threadIdx.x; i < A.E; i += kThreads) {
+      if (lb) lb[i] = 0.0;
+      if (fb) fb[i] = 0.0;
+    }
   }
   double loadpath = 0.0;
   if (A.need_loadpath) {
@@ -308,8 +320,8 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
             const double pc = p[0] * cp[0] + p[1] * cp[1] + p[2] * cp[2];
             for (int c = 0; c < 3; ++c) {
               const double gv = (cp[c] - p[c] * pc) / nn;
-              atomicAdd(xb + 3 * h + c, gv);
-              atomicAdd(xb + 3 * a + c, -gv);
+              gadd(xb, 3 * h + c, gv);
+              gadd(xb, 3 * a + c, -gv);
             }
           }
         } else if (k >= G_NODE_RESIDUAL_DIRECTION) {      // through r -> r / |r|: (I - p p^T) / |r|
@@ -317,26 +329,26 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
           const double nn = unit3(res + 3 * i, u);
           if (nn > 0.0) {
             const double pc = p[0] * cp[0] + p[1] * cp[1] + p[2] * cp[2];
-            for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, (cp[c] - p[c] * pc) / nn);
+            for (int c = 0; c < 3; ++c) gadd(rb, 3 * i + c, (cp[c] - p[c] * pc) / nn);
           }
         } else {
-          for (int c = 0; c < 3; ++c) atomicAdd(xb + 3 * i + c, cp[c]);
+          for (int c = 0; c < 3; ++c) gadd(xb, 3 * i + c, cp[c]);
         }
         continue;
       }
       for (int c = 0; c < nc; ++c) d[c] = mult * err_deriv(ek, w, p[c], A.target[6 * t + c]);
       switch (k) {
         case G_NODE_POINT:
-          for (int c = 0; c < 3; ++c) atomicAdd(xb + 3 * i + c, d[c]);
+          for (int c = 0; c < 3; ++c) gadd(xb, 3 * i + c, d[c]);
           break;
         case G_NODE_RESIDUAL_VECTOR:
-          for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, d[c]);
+          for (int c = 0; c < 3; ++c) gadd(rb, 3 * i + c, d[c]);
           break;
         case G_NODE_RESIDUAL_FORCE:
           if (p[0] > 0.0)
-            for (int c = 0; c < 3; ++c) atomicAdd(rb + 3 * i + c, d[0] * res[3 * i + c] / p[0]);
+            for (int c = 0; c < 3; ++c) gadd(rb, 3 * i + c, d[0] * res[3 * i + c] / p[0]);
           break;
-        case G_NODE_X: case G_NODE_Y: case G_NODE_Z: atomicAdd(xb + 3 * i + (k - G_NODE_X), d[0]); break;
+        case G_NODE_X: case G_NODE_Y: case G_NODE_Z: gadd(xb, 3 * i + (k - G_NODE_X), d[0]); break;
         case G_EDGE_ANGLE: {
           const int a = A.edge_nodes[2 * i], h = A.edge_nodes[2 * i + 1];
           const double v[3] = {xyz[3 * h] - xyz[3 * a], xyz[3 * h + 1] - xyz[3 * a + 1], xyz[3 * h + 2] - xyz[3 * a + 2]};
@@ -348,18 +360,18 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
             const double f = -d[0] / (sqrt(s2) * nn);     // d acos / d cos, through u = v / |v|
             for (int cc = 0; cc < 3; ++cc) {
               const double gv = f * (wv[cc] - u[cc] * c);
-              atomicAdd(xb + 3 * h + cc, gv);
-              atomicAdd(xb + 3 * a + cc, -gv);
+              gadd(xb, 3 * h + cc, gv);
+              gadd(xb, 3 * a + cc, -gv);
             }
           }
           break;
         }
-        case G_EDGE_LENGTH: atomicAdd(lb + i, d[0]); break;
-        case G_EDGE_FORCE: atomicAdd(fb + i, d[0]); break;
+        case G_EDGE_LENGTH: gadd(lb, i, d[0]); break;
+        case G_EDGE_FORCE: gadd(fb, i, d[0]); break;
         case G_EDGE_LOADPATH: {
           const double f = frc[i];
-          atomicAdd(fb + i, d[0] * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) * len[i]);
-          atomicAdd(lb + i, d[0] * fabs(f));
+          gadd(fb, i, d[0] * (f > 0.0 ? 1.0 : (f < 0.0 ? -1.0 : 0.0)) * len[i]);
+          gadd(lb, i, d[0] * fabs(f));
           break;
         }
         default: break;   // network load path: every edge, by the whole CTA below
@@ -386,9 +398,9 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
             const double gD = 2.0 * (d1[c] - d0[c]) / lbar;       // d T / d (d1 - d0)
             const double g0 = -gD - dd / (lbar * lbar) * d0[c];   // d T / d d0  (lbar = (|d0|^2 + |d1|^2) / 2)
             const double g1 = gD - dd / (lbar * lbar) * d1[c];    // d T / d d1
-            atomicAdd(xb + 3 * i0 + c, -d0s * g0);
-            atomicAdd(xb + 3 * i1 + c, d0s * (g0 - g1));
-            atomicAdd(xb + 3 * i2 + c, d0s * g1);
+            gadd(xb, 3 * i0 + c, -d0s * g0);
+            gadd(xb, 3 * i1 + c, d0s * (g0 - g1));
+            gadd(xb, 3 * i2 + c, d0s * g1);
           }
         }
         continue;
@@ -403,7 +415,7 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
           const int e = A.agg_index[j];
           const double x = v[e];
           const double dM = kk == G_EDGES_LENGTH_EQUAL ? 1.0 : (x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0));
-          atomicAdd(vb + e, d0 * (2.0 * (x - mu) / (n * M) - V * dM / (M * M * n)));
+          gadd(vb, e, d0 * (2.0 * (x - mu) / (n * M) - V * dM / (M * M * n)));
         }
         continue;
       }
@@ -412,8 +424,8 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
       for (int e = threadIdx.x; e < A.E; e += kThreads) {
         const double pl = len[e] * frc[e];
         const double sg = pl > 0.0 ? 1.0 : (pl < 0.0 ? -1.0 : 0.0);
-        atomicAdd(fb + e, d0 * sg * len[e]);
-        atomicAdd(lb + e, d0 * sg * frc[e]);
+        gadd(fb, e, d0 * sg * len[e]);
+        gadd(lb, e, d0 * sg * frc[e]);
       }
     }
     __syncthreads();
@@ -440,4 +452,20 @@ int launch_goals_loss(const fdm_plan* p, int n_terms, const int32_t* kind, const
   A.need_loadpath = need_loadpath;
   goals_loss_kernel<<<(unsigned)batch, kThreads, 0, st>>>(A);
   return fdm_check_launch("goals_loss");
+}
+
+// Which state arrays does a goal kind differentiate into?  bit 0 xyz, 1 lengths, 2 forces, 3 residuals.  A caller of
+// fdm_goals_loss may pass NULL for the cotangent arrays no term of its program touches (they are then neither zeroed
+// nor written, and fdm_state_vjp takes NULL as zero).
+extern "C" int fdm_goal_kind_arrays(int kind) {
+  switch (kind) {
+    case G_NODE_POINT: case G_NODE_X: case G_NODE_Y: case G_NODE_Z: case G_NODE_LINE: case G_NODE_PLANE:
+    case G_NODE_SEGMENT: case G_EDGE_DIRECTION: case G_EDGE_ANGLE: case G_NODES_COLINEAR: return 1;
+    case G_EDGE_LENGTH: case G_EDGES_LENGTH_EQUAL: return 2;
+    case G_EDGE_FORCE: case G_EDGES_FORCE_EQUAL: return 4;
+    case G_EDGE_LOADPATH: case G_NETWORK_LOADPATH: return 2 | 4;
+    case G_NODE_RESIDUAL_FORCE: case G_NODE_RESIDUAL_VECTOR: case G_NODE_RESIDUAL_DIRECTION:
+    case G_NODE_RESIDUAL_PLANE: return 8;
+  }
+  return 15;
 }

@@ -65,6 +65,7 @@ struct fdm_fa {
   cudaEvent_t loss_ev[2] = {nullptr, nullptr};   // recorded after a host step's loss copy (copy_losses), by staging row
   bool loss_ev_armed[2] = {false, false};
   int64_t host_steps = 0;
+  int prog_arrays = 15;                  // state arrays the goal program differentiates into (fdm_goal_kind_arrays)
   Buf loss_stage;                        // (2, B) staging rows of the losses of host steps
   cudaStream_t own = nullptr;      // run_host's ordering stream
   cudaGraphExec_t step_exec = nullptr;   // the whole device-resident step (fork / chunks / join) as one graph
@@ -131,11 +132,16 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
     // goal program: loss and the cotangents of the state, their transposes through the state (direct terms of
     // q_bar, loads_bar and the cotangent of xyz), the split of xyz_bar into free / fixed rows, the adjoint solve
     // and the implicit terms accumulated on top
+    // cotangent arrays of the state no goal of the program differentiates into are left out altogether
+    double* xc = (f->prog_arrays & 1) ? f->xyz_cot.at(o) : nullptr;
+    double* lc = (f->prog_arrays & 2) ? f->len_cot.at(o) : nullptr;
+    double* fc = (f->prog_arrays & 4) ? f->for_cot.at(o) : nullptr;
+    double* rc_ = (f->prog_arrays & 8) ? f->res_cot.at(o) : nullptr;
     rc = fdm_goals_loss(p, &f->prog, f->xyz.at(o), f->lengths.at(o), f->forces.at(o), f->residuals.at(o), f->loss.at(o),
-                        nullptr, nullptr, f->xyz_cot.at(o), f->len_cot.at(o), f->for_cot.at(o), f->res_cot.at(o), B, st);
+                        nullptr, nullptr, xc, lc, fc, rc_, B, st);
     if (rc != FDM_OK) return rc;
-    rc = fdm_state_vjp(p, f->q.at(o), f->xyz.at(o), f->xyz_cot.at(o), f->res_cot.at(o), f->len_cot.at(o), f->for_cot.at(o),
-                       nullptr, nullptr, f->q_bar.at(o), f->xyz_bar.at(o), f->loads_bar.at(o), B, E, st);
+    rc = fdm_state_vjp(p, f->q.at(o), f->xyz.at(o), xc, rc_, lc, fc, nullptr, nullptr, f->q_bar.at(o), f->xyz_bar.at(o),
+                       f->loads_bar.at(o), B, E, st);
     if (rc != FDM_OK) return rc;
     rc = fdm_positions(p, f->g.at(o), f->xs_bar.at(o), f->xyz_bar.at(o), B, Ns * 3, 1, st);
     if (rc != FDM_OK) return rc;
@@ -378,6 +384,9 @@ int fdm_fa_set_goal_program(fdm_fa* f, const fdm_goal_program* h) {
   A(f->xyz_cot, N * 3); A(f->len_cot, E); A(f->for_cot, E); A(f->res_cot, N * 3); A(f->xyz_bar, N * 3);
   if (rc != FDM_OK) return rc;
   f->has_prog = true;
+  f->prog_arrays = 0;
+  for (int32_t t = 0; t < h->num_terms; ++t) f->prog_arrays |= fdm_goal_kind_arrays(h->kind[t]);
+  if (h->num_terms == 0) f->prog_arrays = 1;             // keep the launch well-formed: an all-zero xyz cotangent
   for (Chunk& c : f->chunks) {                                         // recaptured by the next run
     for (cudaGraphExec_t& g : c.exec_park)
       if (g) { cudaGraphExecDestroy(g); g = nullptr; }

@@ -165,6 +165,12 @@ class _Program:
             ginner.append(1.0 / term.number_of_goals() if term.mean else 1.0)
             gouter.append(term.alpha)
         self.num_terms, self.num_groups = len(kind), len(gfinal)
+        # which of (xyz, lengths, forces, residuals) the terms differentiate into: the reverse pass neither zeroes nor
+        # writes the other cotangent arrays (include/fdm_b200.h: fdm_goal_kind_arrays)
+        mask = 0
+        for k in set(kind):
+            mask |= int(L.lib().fdm_goal_kind_arrays(int(k)))
+        self.touches = tuple(bool(mask & bit) for bit in (1, 2, 4, 8))
 
         host = [(kind, np.int32), (index, np.int32), (err, np.int32), (weight, np.float64),
                 (np.asarray(target).reshape(-1, 6), np.float64), (gptr, np.int32), (gfinal, np.int32),
@@ -207,8 +213,10 @@ class _GoalsLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         xyz, lengths, forces, residuals = ctx.saved_tensors
-        bars = [torch.empty_like(t) for t in (xyz, lengths, forces, residuals)]
-        _goals_call(ctx.structure, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
+        touched = ctx.program.touches
+        bars = [torch.empty_like(t) if on else None for t, on in zip((xyz, lengths, forces, residuals), touched)]
+        if any(touched):
+            _goals_call(ctx.structure, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
         return (*bars, None, None)
 
 
@@ -250,8 +258,10 @@ class _FusedValueAndGrad(torch.autograd.Function):
         from ..distributed import _batch_sum
         q, xyz_fixed, loads, xyz, lengths, forces, residuals, K = ctx.saved_tensors
         s = ctx.structure
-        bars = [torch.empty_like(t) for t in (xyz, lengths, forces, residuals)]
-        _goals_call(s, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
+        touched = ctx.program.touches                       # untouched state arrays: no cotangent array at all
+        bars = [torch.empty_like(t) if on else None for t, on in zip((xyz, lengths, forces, residuals), touched)]
+        if any(touched):
+            _goals_call(s, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
         q_bar, xyz_bar, loads_bar = ops.state_vjp(s, q, xyz, xyz_cot=bars[0], residuals_cot=bars[3], lengths_cot=bars[1],
                                                   forces_cot=bars[2])
         gx, xs_bar = ops.positions_vjp(s, xyz_bar)

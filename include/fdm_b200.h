@@ -335,7 +335,8 @@ typedef struct fdm_goal_program {
 /* loss (B) [NULL in a reverse-only call]; group_sums (B,G) or NULL.  With cotangent arrays the kernel also writes loss_cot_b * d loss_b / d state: xyz_bar (B,N,3), lengths_bar (B,E), forces_bar
  * (B,E), residuals_bar (B,N,3) -- the cotangents fdm_state_vjp takes; d_loss_cot (B) is the upstream cotangent of
  * the loss (NULL = 1).
- * A cotangent array that no term of the program differentiates into (fdm_goal_kind_arrays) may be NULL --
+ * d_lengths / d_forces / d_residuals may be NULL when no goal of the program reads them (fdm_goal_kind_arrays), and a
+ * cotangent array that no term of the program differentiates into (fdm_goal_kind_arrays) may be NULL --
  * it is then neither zeroed nor written, and fdm_state_vjp takes a NULL cotangent as zero; an array a term does read
  * must be given. */
 int fdm_goals_loss(const fdm_plan* plan, const fdm_goal_program* program, const double* d_xyz,

@@ -481,7 +481,7 @@ int fdm_goals_loss(const fdm_plan* p, const fdm_goal_program* g, const double* x
                    int64_t batch, void* stream) {
   if (!ready(p, "fdm_goals_loss")) return FDM_ERR_INVALID;
   const bool any_bar = xyz_bar || lengths_bar || forces_bar || residuals_bar;
-  if (!g || !xyz || !lengths || !forces || !residuals || (!loss && !any_bar) || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
+  if (!g || !xyz || (!loss && !any_bar) || batch <= 0 || g->num_terms < 0 || g->num_groups < 0 ||
       (g->num_terms > 0 && (!g->kind || !g->index || !g->error || !g->weight || !g->target)) ||
       (g->num_groups > 0 && (!g->group_ptr || !g->group_final || !g->group_inner || !g->group_outer))) {
     fdm_set_error("fdm_goals_loss: bad arguments");

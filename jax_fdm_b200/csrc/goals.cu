@@ -171,9 +171,10 @@ __global__ void __launch_bounds__(kThreads) goals_loss_kernel(GoalArgs A) {
   __shared__ double s_mult[64];
   const int64_t b = blockIdx.x;
   const double* xyz = A.xyz + b * (int64_t)A.N * 3;
-  const double* res = A.residuals + b * (int64_t)A.N * 3;
-  const double* len = A.lengths + b * (int64_t)A.E;
-  const double* frc = A.forces + b * (int64_t)A.E;
+  // lengths / forces / residuals may be NULL when no goal of the program reads them (a loss of node goals only)
+  const double* res = A.residuals ? A.residuals + b * (int64_t)A.N * 3 : nullptr;
+  const double* len = A.lengths ? A.lengths + b * (int64_t)A.E : nullptr;
+  const double* frc = A.forces ? A.forces + b * (int64_t)A.E : nullptr;
   // reverse mode: any cotangent array given; an array no term of the program reads may be NULL (not zeroed, not written)
   const bool bwd = A.xyz_bar || A.residuals_bar || A.lengths_bar || A.forces_bar;
   double* xb = A.xyz_bar ? A.xyz_bar + b * (int64_t)A.N * 3 : nullptr;

@@ -110,7 +110,10 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   rc = fdm_positions(p, f->x.at(o), f->xs.p, f->xyz.at(o), B, 0, 0, st);
   if (rc != FDM_OK) return rc;
   ++n;
-  if (f->o.with_state || f->has_prog) {
+  // a goal program of node goals only reads the positions: the state is computed only when the caller wants it
+  const bool prog_needs_state = f->has_prog && (f->prog_arrays & ~1) != 0;
+  const bool have_state = f->o.with_state || prog_needs_state;
+  if (have_state) {
     rc = fdm_state(p, f->q.at(o), f->xyz.at(o), f->loads.p, f->vectors.at(o), f->lengths.at(o), f->forces.at(o),
                    f->residuals.at(o), B, E, 0, st);
     if (rc != FDM_OK) return rc;
@@ -137,13 +140,22 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
     double* lc = (f->prog_arrays & 2) ? f->len_cot.at(o) : nullptr;
     double* fc = (f->prog_arrays & 4) ? f->for_cot.at(o) : nullptr;
     double* rc_ = (f->prog_arrays & 8) ? f->res_cot.at(o) : nullptr;
-    rc = fdm_goals_loss(p, &f->prog, f->xyz.at(o), f->lengths.at(o), f->forces.at(o), f->residuals.at(o), f->loss.at(o),
-                        nullptr, nullptr, xc, lc, fc, rc_, B, st);
+    rc = fdm_goals_loss(p, &f->prog, f->xyz.at(o), prog_needs_state ? f->lengths.at(o) : nullptr,
+                        prog_needs_state ? f->forces.at(o) : nullptr, prog_needs_state ? f->residuals.at(o) : nullptr,
+                        f->loss.at(o), nullptr, nullptr, xc, lc, fc, rc_, B, st);
     if (rc != FDM_OK) return rc;
-    rc = fdm_state_vjp(p, f->q.at(o), f->xyz.at(o), xc, rc_, lc, fc, nullptr, nullptr, f->q_bar.at(o), f->xyz_bar.at(o),
-                       f->loads_bar.at(o), B, E, st);
-    if (rc != FDM_OK) return rc;
-    rc = fdm_positions(p, f->g.at(o), f->xs_bar.at(o), f->xyz_bar.at(o), B, Ns * 3, 1, st);
+    double* xyz_bar = f->xyz_bar.at(o);
+    if (prog_needs_state) {
+      rc = fdm_state_vjp(p, f->q.at(o), f->xyz.at(o), xc, rc_, lc, fc, nullptr, nullptr, f->q_bar.at(o), xyz_bar,
+                         f->loads_bar.at(o), B, E, st);
+      if (rc != FDM_OK) return rc;
+    } else {
+      // only xyz was read: its cotangent IS xyz_bar and there are no direct terms on q and the loads
+      xyz_bar = xc;
+      FDM_CUDA(cudaMemsetAsync(f->q_bar.at(o), 0, (size_t)B * E * 8, st));
+      FDM_CUDA(cudaMemsetAsync(f->loads_bar.at(o), 0, (size_t)B * N * 3 * 8, st));
+    }
+    rc = fdm_positions(p, f->g.at(o), f->xs_bar.at(o), xyz_bar, B, Ns * 3, 1, st);
     if (rc != FDM_OK) return rc;
     rc = fdm_solve(p, f->fused ? f->x.at(o) : f->K.at(o), f->g.at(o), f->lam.at(o), f->info_a.at(o), c.ws, c.ws_bytes, B,
                    &so, st);
@@ -151,7 +163,7 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
     rc = fdm_adjoint_grads(p, f->q.at(o), f->xyz.at(o), f->lam.at(o), f->q_bar.at(o), f->loads_bar.at(o), f->xs_bar.at(o),
                            B, E, 1, st);
     if (rc != FDM_OK) return rc;
-    n += 5;
+    n += prog_needs_state ? 5 : 4;
   }
   (void)N;
   if (count) *count += n;

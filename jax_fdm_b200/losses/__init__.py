@@ -244,11 +244,18 @@ class _FusedValueAndGrad(torch.autograd.Function):
             K, rhs = ops.assemble(s, q, xyz_fixed, loads)
             x = ops.solve(s, K, rhs, workspace=ws, nan_on_failure=True, **opts)
         xyz = ops.positions(s, x, xyz_fixed)
-        _, lengths, forces, residuals = ops.state(s, q, xyz, loads)
+        # a loss of node goals only reads the positions: no state kernel (and no state VJP on the way back)
+        ctx.needs_state = any(program.touches[1:])
+        if ctx.needs_state:
+            _, lengths, forces, residuals = ops.state(s, q, xyz, loads)
+        else:
+            lengths = forces = residuals = None
         batched = xyz.dim() == 3
         loss = torch.empty((xyz.shape[0] if batched else 1,), dtype=F64, device=xyz.device)
         _goals_call(s, program, xyz, lengths, forces, residuals, loss, None, [None] * 4)
-        ctx.save_for_backward(q, xyz_fixed, loads, xyz, lengths, forces, residuals, K if K is not None else x.new_empty(0))
+        e = x.new_empty(0)
+        ctx.save_for_backward(q, xyz_fixed, loads, xyz, *(t if t is not None else e for t in (lengths, forces, residuals)),
+                              K if K is not None else e)
         ctx.structure, ctx.program, ctx.opts, ctx.ws, ctx.batched = s, program, opts, ws, batched
         return loss if batched else loss[0]
 
@@ -259,11 +266,19 @@ class _FusedValueAndGrad(torch.autograd.Function):
         q, xyz_fixed, loads, xyz, lengths, forces, residuals, K = ctx.saved_tensors
         s = ctx.structure
         touched = ctx.program.touches                       # untouched state arrays: no cotangent array at all
-        bars = [torch.empty_like(t) if on else None for t, on in zip((xyz, lengths, forces, residuals), touched)]
+        if not ctx.needs_state:
+            lengths = forces = residuals = None
+        bars = [torch.empty_like(xyz) if touched[0] else None] + [
+            torch.empty_like(t) if on else None for t, on in zip((lengths, forces, residuals), touched[1:])]
         if any(touched):
             _goals_call(s, ctx.program, xyz, lengths, forces, residuals, None, g.reshape(-1).contiguous(), bars)
-        q_bar, xyz_bar, loads_bar = ops.state_vjp(s, q, xyz, xyz_cot=bars[0], residuals_cot=bars[3], lengths_cot=bars[1],
-                                                  forces_cot=bars[2])
+        if ctx.needs_state or bars[0] is None:
+            q_bar, xyz_bar, loads_bar = ops.state_vjp(s, q, xyz, xyz_cot=bars[0], residuals_cot=bars[3],
+                                                      lengths_cot=bars[1], forces_cot=bars[2])
+        else:                                               # only xyz was read: its cotangent IS xyz_bar, no direct terms
+            xyz_bar = bars[0]
+            q_bar = torch.zeros(xyz.shape[:-2] + (s.num_edges,), dtype=F64, device=xyz.device)
+            loads_bar = torch.zeros_like(xyz)
         gx, xs_bar = ops.positions_vjp(s, xyz_bar)
         lam = ops.solve(s, K if K.numel() else None, gx, workspace=ctx.ws, reuse_factor=True, **ctx.opts)
         ops.adjoint_grads(s, q, xyz, lam, q_bar=q_bar, loads_bar=loads_bar, xyz_fixed_bar=xs_bar)

@@ -159,3 +159,59 @@ def test_batched_gradients_are_per_design():
         v1.backward()
         assert abs(v1.item() - vals[b].item()) <= 1e-13 * abs(v1.item())
         assert (q1.grad - q.grad[b]).abs().max().item() <= 1e-12 * q1.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("kinds", ["nodes", "edges", "residuals", "nodes+edges"])
+def test_partial_goal_programs_skip_what_they_do_not_read(kinds):
+    """A loss of node goals only never launches the state kernel or its VJP; one of edge goals only gets no xyz
+    cotangent array, and so on (fdm_goal_kind_arrays).  Value and all three gradients against the goal-by-goal route
+    through the model (autograd over the state), for the fused node and for the library-owned pipeline."""
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200 import goals as G, losses as LS
+    from jax_fdm_b200.pipeline import NativeForwardAdjoint
+
+    prob = datasets.cablenet_problem(9, seed=2)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    rng = np.random.default_rng(5)
+    free = np.flatnonzero(prob.supports == 0)
+    fixed = np.flatnonzero(prob.supports != 0)
+    terms = []
+    if "nodes" in kinds:
+        terms.append(LS.SquaredError([G.NodePointGoal(int(prob.nodes[n]), prob.xyz0[n] + 0.1 * rng.standard_normal(3))
+                                      for n in free[::3]], alpha=0.7))
+    if "edges" in kinds:
+        terms.append(LS.MeanSquaredError([G.EdgeLengthGoal((int(u), int(v)), 0.9) for u, v in prob.edges[::4]]))
+        terms.append(LS.SquaredError([G.EdgeForceGoal((int(u), int(v)), 1.5) for u, v in prob.edges[1::5]], alpha=0.2))
+    if "residuals" in kinds:
+        terms.append(LS.SquaredError([G.NodeResidualVectorGoal(int(prob.nodes[n]), [0.1, 0.0, -0.2]) for n in fixed]))
+    loss = LS.Loss(*terms)
+    assert loss.program(s, torch.device("cuda", 0)).touches == ("nodes" in kinds, "edges" in kinds, "edges" in kinds,
+                                                                 "residuals" in kinds)
+    model = eq.EquilibriumModelSparse(tmax=1)
+    B = 9
+    qb = prob.q[None, :] * rng.uniform(0.8, 1.25, size=(B, prob.q.size))
+
+    def run(fused):
+        q, xs, p = T(qb, True), T(prob.xyz_fixed, True), T(prob.loads, True)
+        params = eq.EquilibriumParametersState(q, xs, eq.LoadState(p, 0.0, 0.0))
+        val = loss(params, model, s) if fused else loss.errors_from_state(model(params, s), s)
+        w = T(np.linspace(0.5, 1.5, B))                      # a non-trivial upstream cotangent
+        (val * w).sum().backward()
+        return val.detach().cpu().numpy(), [t.grad.cpu().numpy() for t in (q, xs, p)]
+
+    v1, g1 = run(True)
+    v2, g2 = run(False)
+    assert np.allclose(v1, v2, rtol=1e-13, atol=0)
+    for a, b in zip(g1, g2):
+        assert np.abs(a - b).max() <= 1e-11 * max(np.abs(b).max(), 1e-300)
+    # the library-owned pipeline on the same program (unit upstream cotangent)
+    fa = NativeForwardAdjoint(s, B, chunks=2, solver="cholesky", with_state=False)
+    fa.set_inputs(qb, prob.xyz_fixed, prob.loads)
+    fa.set_loss(loss)
+    fa.step()
+    fa.stream.synchronize()
+    q = T(qb, True)
+    loss(eq.EquilibriumParametersState(q, T(prob.xyz_fixed), eq.LoadState(T(prob.loads), 0.0, 0.0)), model, s).sum().backward()
+    assert np.allclose(fa.array("loss").cpu().numpy(), v1, rtol=1e-13, atol=0)
+    assert np.abs(fa.array("q_bar").cpu().numpy() - q.grad.cpu().numpy()).max() <= 1e-11 * np.abs(q.grad.cpu().numpy()).max()
+    fa.close()

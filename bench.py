@@ -633,7 +633,8 @@ def run_ours(args):
             "ms_per_step": float(np.mean(t_api)), "value": B / (float(np.mean(t_api)) * 1e-3), "unit": UNIT,
             "how": "EquilibriumModelSparse(tmax=1)(params, structure) + losses.Loss(SquaredError(NodePointGoal x "
                    f"{len(free)}, alpha=0.5)) + .backward() on the same {B} designs, device-resident, torch autograd "
-                   "nodes over the same kernels, per-call allocations, no CUDA graph",
+                   "nodes over the same kernels, per-call allocations, no CUDA graph; a loss of node goals reads positions only, "
+                   "so the state kernel and its VJP are not launched on this route",
             "max_rel_diff_loss_vs_pipeline": float(((api_out["loss"] - ref_loss).abs() / ref_loss.abs()).max().item()),
             "max_rel_diff_q_bar_vs_pipeline": float(((api_out["q_bar"] - ref_qbar).abs().max() / ref_qbar.abs().max()).item())}
         del q_t, api_out
@@ -716,8 +717,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_fa.h2d_bytes * world,
                 "d2h_bytes_per_step": e2e_fa.d2h_bytes * world, "ms_per_step": e2e_ms,
                 "how": f"fdm_fa_run_host: pinned host q -> device, forward + adjoint, loss + q_bar -> pinned host, in "
-                       f"{E2E_CHUNKS} slices on their own streams so copies overlap kernels; one C call per step; host "
-                       "wall clock, synchronised both sides of EVERY step",
+                       f"{E2E_CHUNKS} slices on their own streams so copies overlap kernels (the per-design losses leave in "
+                       "one copy at the end); one C call per step; host wall clock, synchronised both sides of EVERY step",
                 "copy_roofline": {"ms_per_step": copy_ms,
                                   "gbs_per_gpu_each_way": e2e_fa.h2d_bytes / (copy_ms * 1e-3) / 1e9,
                                   "e2e_over_copy": e2e_ms / copy_ms,

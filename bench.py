@@ -57,7 +57,7 @@ CONFIG5_BATCH = 4096          # BASELINE config 5's fixed global batch (reported
 GLOBAL_BATCH = PER_GPU_BATCH  # the CPU arm times a bounded sample of one GPU's share
 CABLENET_NX = 200
 E2E_CHUNKS = int(os.environ.get("FDM_BENCH_E2E_CHUNKS", "16"))
-DEV_CHUNKS = int(os.environ.get("FDM_BENCH_DEV_CHUNKS", "2"))   # slices of the device-resident step (own streams)
+DEV_CHUNKS = int(os.environ.get("FDM_BENCH_DEV_CHUNKS", "8"))   # slices of the device-resident step (own streams)
 SWEEP_NX = 2000                # one mesh far beyond L2 for the HBM-bound kernels' fractions (SURVEY.md §8d size sweep)
 WORKLOAD = (f"{PER_GPU_BATCH} x pillow {PILLOW_NX}x{PILLOW_NX} designs per GPU (841 free nodes, 1860 edges, "
             "q_b = -2 + 0.1(U-0.5) seed b): forward solve + state + loss + adjoint solve + gradients; "
@@ -710,7 +710,9 @@ def run_ours(args):
                    "device_step": f"library-owned pipeline (fdm_fa_step_device): {DEV_CHUNKS} slices of the batch on their "
                                   "own streams inside one CUDA graph, forked from and joined to the timed stream (CUDA "
                                   "events on it bracket the whole step); the factorisation assembles its rows from q in "
-                                  "place (fdm_solve_from_q)",
+                                  "place (fdm_solve_from_q); the factor kernels carry the LOW launch priority and every other "
+                                  "kernel of a slice the high one, so one slice's bandwidth-bound kernels take freed CTA "
+                                  "slots ahead of the queued factor CTAs of the next",
                    "parallelism": f"designs sharded x{world}, no data-path collective"
                                   + (", 8-byte loss all-reduce (NCCL) per step" if world > 1 else "")},
         "clocks": clocks,

@@ -119,6 +119,7 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
                     void* ws, size_t ws_bytes, int64_t batch, const fdm_solve_opts& o, cudaStream_t st);
 
 bool chol_warp_from_q_supported(const fdm_plan* p);
+bool chol_warp_is_factor_kernel(const void* func);   // a graph kernel node's function: one of the factor kernels?
 int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,
                            double* info, void* ws, size_t ws_bytes, int64_t batch, int64_t qs, int64_t xss,
                            int64_t ls, const fdm_solve_opts& o, cudaStream_t st);

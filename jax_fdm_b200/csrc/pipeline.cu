@@ -11,6 +11,7 @@
 // (fdm_loss_sqdist) and a compiled goal program (fdm_goals_loss + fdm_state_vjp).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -23,6 +24,7 @@ namespace {
 
 struct Chunk {
   int64_t off = 0, B = 0;
+  bool lowlat = false;     // a small slice at either end of a tapered batch (latency matters more than throughput)
   cudaStream_t st = nullptr;
   cudaEvent_t done = nullptr;
   cudaGraphExec_t exec = nullptr;
@@ -96,6 +98,9 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   so.tol = f->o.tol;
   so.nan_on_failure = 1;
   so.concurrent_designs = (int32_t)std::min<int64_t>(f->B, 1 << 30);   // the slices run side by side
+  // a tapered slice (fdm_fa_create) runs while the machine is filling up or draining: it is factored two-sided (half
+  // the dependency chain) whatever the size of the whole batch
+  if (c.lowlat) so.concurrent_designs = (int32_t)c.B;
   if (f->fused) {
     rc = fdm_solve_from_q(p, f->q.at(o), f->xs.p, f->loads.p, f->x.at(o), f->info_f.at(o), c.ws, c.ws_bytes, B, E, 0, 0,
                           &so, st);
@@ -170,6 +175,35 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   return FDM_OK;
 }
 
+// Launch priorities of a captured slice (or step) graph: the factorisation kernels LOW, every other kernel HIGH.
+// Slices run side by side on their own streams; a factor CTA keeps its registers for ~0.3 ms while HBM idles, and
+// without priorities the queued factor CTAs of the next slice take every freed slot before the bandwidth-bound
+// substitution / state / gradient kernels of the slice that has just been factored get one.  With them those kernels
+// start as soon as slots free up and stream while the other slices factor.  FDM_FA_PRIORITY=0: off (A/B switch).
+int prioritise(cudaGraph_t graph) {
+  static const bool off = std::getenv("FDM_FA_PRIORITY") && std::atoi(std::getenv("FDM_FA_PRIORITY")) == 0;
+  if (off) return FDM_OK;
+  int least = 0, greatest = 0;
+  FDM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  if (least == greatest) return FDM_OK;
+  size_t n = 0;
+  FDM_CUDA(cudaGraphGetNodes(graph, nullptr, &n));
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (n) FDM_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n));
+  for (cudaGraphNode_t node : nodes) {
+    cudaGraphNodeType type;
+    FDM_CUDA(cudaGraphNodeGetType(node, &type));
+    if (type != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp;
+    FDM_CUDA(cudaGraphKernelNodeGetParams(node, &kp));
+    cudaKernelNodeAttrValue v;
+    std::memset(&v, 0, sizeof(v));
+    v.priority = chol_warp_is_factor_kernel(kp.func) ? least : greatest;
+    FDM_CUDA(cudaGraphKernelNodeSetAttribute(node, cudaKernelNodeAttributePriority, &v));
+  }
+  return FDM_OK;
+}
+
 int run_chunk(fdm_fa* f, Chunk& c, cudaStream_t st) {
   if (c.exec) {
     FDM_CUDA(cudaGraphLaunch(c.exec, st));
@@ -194,6 +228,7 @@ int capture_chunks(fdm_fa* f) {
     cudaError_t e = cudaStreamEndCapture(c.st, &graph);
     if (rc != FDM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph capture: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+    if (prioritise(graph) != FDM_OK) { cudaGraphDestroy(graph); return FDM_ERR_CUDA; }
     e = cudaGraphInstantiate(&c.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
@@ -209,6 +244,7 @@ int capture_chunks(fdm_fa* f) {
       e = cudaStreamEndCapture(c.st, &graph);
       if (rc != FDM_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
       if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph capture: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
+      if (prioritise(graph) != FDM_OK) { cudaGraphDestroy(graph); return FDM_ERR_CUDA; }
       e = cudaGraphInstantiate(&c.exec_park[par], graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
@@ -234,6 +270,7 @@ int capture_chunks(fdm_fa* f) {
       if (graph) cudaGraphDestroy(graph);
       return FDM_ERR_CUDA;
     }
+    if (prioritise(graph) != FDM_OK) { cudaGraphDestroy(graph); return FDM_ERR_CUDA; }
     e = cudaGraphInstantiate(&f->step_exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { fdm_set_error(std::string("fdm_fa: step graph instantiate: ") + cudaGetErrorString(e)); return FDM_ERR_CUDA; }
@@ -327,12 +364,32 @@ int fdm_fa_create(const fdm_plan* p, int64_t batch, const fdm_fa_opts* opts, fdm
   if (rc == FDM_OK && cudaEventCreateWithFlags(&f->fork, cudaEventDisableTiming) != cudaSuccess) rc = FDM_ERR_CUDA;
   for (int i = 0; i < 2; ++i)
     if (rc == FDM_OK && cudaEventCreateWithFlags(&f->loss_ev[i], cudaEventDisableTiming) != cudaSuccess) rc = FDM_ERR_CUDA;
-  f->chunks.resize((size_t)nch);
+  // slice sizes: nch equal slices.  FDM_FA_TAPER = k (measurement only) halves the first and the last slice k times
+  // ([64, 64, 128, 256, ..., 256, 128, 64, 64] for k = 2 on slices of 256) and factors those small slices two-sided:
+  // measured SLOWER end to end (2.02 -> 2.06 ms at 16 slices) -- the host step is bound by the device's ramp-up, not
+  // by the latency of its first and last slice, and small slices ramp up more slowly
+  std::vector<int64_t> sizes;
+  for (int64_t i = 0; i < nch; ++i) sizes.push_back(batch / nch + (i < batch % nch ? 1 : 0));
+  {
+    const char* e = std::getenv("FDM_FA_TAPER");
+    const int taper = e ? std::atoi(e) : 0;
+    const int64_t base = batch / nch;
+    for (int k = 0; k < taper && nch >= 4; ++k) {
+      const int64_t last = sizes.back(), first = sizes.front();
+      if (last < 64 || first < 64) break;
+      sizes.back() = last - last / 2;
+      sizes.push_back(last / 2);
+      sizes.front() = first - first / 2;
+      sizes.insert(sizes.begin(), first / 2);
+    }
+    f->chunks.resize(sizes.size());
+    for (size_t i = 0; i < sizes.size(); ++i) f->chunks[i].lowlat = sizes[i] < base;
+  }
   int64_t off = 0;
-  for (int64_t i = 0; i < nch && rc == FDM_OK; ++i) {
-    Chunk& c = f->chunks[(size_t)i];
+  for (size_t i = 0; i < f->chunks.size() && rc == FDM_OK; ++i) {
+    Chunk& c = f->chunks[i];
     c.off = off;
-    c.B = batch / nch + (i < batch % nch ? 1 : 0);
+    c.B = sizes[i];
     off += c.B;
     if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess) { rc = FDM_ERR_CUDA; break; }

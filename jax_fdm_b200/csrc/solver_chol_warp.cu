@@ -1238,13 +1238,13 @@ inline int mma_warps_per_cta() {
 // designs (= warps) per CTA of the substitution kernel (FDM_CHOL_SUBWARPS) and extra dynamic shared memory
 // requested by the factor kernels to cap their CTAs per SM (FDM_CHOL_FAC_SMEM_PAD, bytes): experiments on
 // co-residency of the latency-bound factorisation of one slice with the bandwidth-bound kernels of another
-inline int sub_warps_per_cta() {
+inline int sub_warps_per_cta(int dflt) {
   static const int w = [] {
     const char* e = std::getenv("FDM_CHOL_SUBWARPS");
-    const int v = e ? std::atoi(e) : kSubWarps;
-    return v >= 1 && v <= kSubWarps ? v : kSubWarps;
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 && v <= kSubWarps ? v : 0;
   }();
-  return w;
+  return w ? w : dflt;
 }
 inline size_t fac_smem_pad() {
   static const size_t v = [] {
@@ -1440,13 +1440,38 @@ static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStrea
                                       : (twc ? chol_subst_kernel<4, true> : chol_subst_kernel<4>);
   static const bool no_pair = std::getenv("FDM_CHOL_SUBPAIR") && std::atoi(std::getenv("FDM_CHOL_SUBPAIR")) == 0;
   A.sub_pair = twc && !no_pair ? 1 : 0;
-  int sw = sub_warps_per_cta();
+  // A sliced caller (designs in flight beyond this call's batch) runs this kernel beside the factor kernels of other
+  // slices: a CTA of 4 warps (78 KB, 21 K registers) fits into the hole ONE retiring factor CTA leaves (84 KB, 32 K
+  // registers), the full 11-warp CTA needs a whole SM and would wait until the queue of factor CTAs has drained
+  // (csrc/pipeline.cu: prioritise).  Alone, the 11-warp CTA streams best (0.195 ms backward at B = 4096).
+  int sw = sub_warps_per_cta(inflight > batch ? 4 : kSubWarps);
   if (A.sub_pair) sw = std::max(2, sw & ~1);
   const int dpc = A.sub_pair ? sw / 2 : sw;                // designs per CTA
   const size_t smem = (size_t)sw * kSubWarpSmem * sizeof(double);
   FDM_CUDA(cudaFuncSetAttribute(skern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   skern<<<(unsigned)((batch + dpc - 1) / dpc), sw * 32, smem, st>>>(A);
   return FDM_OK;
+}
+
+// Is `func` (the host-side handle of a __global__ function, as a CUDA graph's kernel node reports it) one of the
+// factorisation kernels of this file?  The pipeline gives those nodes the LOW launch priority and every other kernel
+// of a slice the high one: a factor CTA holds a quarter of an SM's registers for ~0.3 ms and leaves HBM idle, so when
+// slices run side by side the bandwidth-bound kernels of one slice should take freed CTA slots ahead of the queued
+// factor CTAs of the next (csrc/pipeline.cu: prioritise).
+bool chol_warp_is_factor_kernel(const void* func) {
+  // (the SIGNED second-pass instances are NOT in the list: they return at once for every design whose pivots were
+  //  positive and sit between a slice's factorisation and its substitution, so they must not queue behind the
+  //  factor CTAs of other slices)
+  const void* const fac[] = {
+      (const void*)chol_factor_mma_kernel<false, 2, false>, (const void*)chol_factor_mma_kernel<false, 4, false>,
+      (const void*)chol_factor_mma_kernel<false, 4, false, true>,
+      (const void*)chol_factor_mma_kernel<true, 2, false>,  (const void*)chol_factor_mma_kernel<true, 4, false>,
+      (const void*)chol_factor_mma_kernel<true, 4, false, true>,
+      (const void*)chol_factor_kernel<7>,  (const void*)chol_factor_kernel<15>,
+      (const void*)chol_factor_kernel<23>, (const void*)chol_factor_kernel<31>};
+  for (const void* f : fac)
+    if (f == func) return true;
+  return false;
 }
 
 int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs, const double* loads, double* x,

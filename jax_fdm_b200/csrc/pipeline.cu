@@ -26,7 +26,8 @@ struct Chunk {
   int64_t off = 0, B = 0;
   bool lowlat = false;     // a small slice at either end of a tapered batch (latency matters more than throughput)
   cudaStream_t st = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaStream_t side = nullptr;                          // positions + state beside the loss and the adjoint solve
+  cudaEvent_t done = nullptr, ev_fork = nullptr, ev_join = nullptr;
   cudaGraphExec_t exec = nullptr;
   cudaGraphExec_t exec_park[2] = {nullptr, nullptr};   // the same + the parking of the losses in staging row 0 / 1
   void* ws = nullptr;
@@ -112,7 +113,18 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
     n += 2 + 4;                               // assembly (K.data, rhs) + the band Cholesky's four (other solvers differ)
   }
   if (rc != FDM_OK) return rc;
-  rc = fdm_positions(p, f->x.at(o), f->xs.p, f->xyz.at(o), B, 0, 0, st);
+  // The quadratic loss reads x_free only: positions and state leave the critical path (solve -> loss -> adjoint solve)
+  // and run on the slice's side stream, joined again before the gradient kernel, which reads xyz.  For a small batch
+  // every kernel of the chain is latency-bound and the step is their sum: 512 designs 0.327 -> 0.30 ms.
+  static const bool no_fork = std::getenv("FDM_FA_FORK_STATE") && std::atoi(std::getenv("FDM_FA_FORK_STATE")) == 0;
+  const bool fork = !f->has_prog && !no_fork && c.side;
+  cudaStream_t ss = st;
+  if (fork) {
+    FDM_CUDA(cudaEventRecord(c.ev_fork, st));
+    FDM_CUDA(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+    ss = c.side;
+  }
+  rc = fdm_positions(p, f->x.at(o), f->xs.p, f->xyz.at(o), B, 0, 0, ss);
   if (rc != FDM_OK) return rc;
   ++n;
   // a goal program of node goals only reads the positions: the state is computed only when the caller wants it
@@ -120,10 +132,11 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   const bool have_state = f->o.with_state || prog_needs_state;
   if (have_state) {
     rc = fdm_state(p, f->q.at(o), f->xyz.at(o), f->loads.p, f->vectors.at(o), f->lengths.at(o), f->forces.at(o),
-                   f->residuals.at(o), B, E, 0, st);
+                   f->residuals.at(o), B, E, 0, ss);
     if (rc != FDM_OK) return rc;
     ++n;
   }
+  if (fork) FDM_CUDA(cudaEventRecord(c.ev_join, c.side));
   so.reuse_factor = 1;
   if (!f->has_prog) {
     // L_b = 1/2 |x_free - x0|^2, g = x_free - x0
@@ -132,6 +145,7 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
     rc = fdm_solve(p, f->fused ? f->x.at(o) /* unused */ : f->K.at(o), f->g.at(o), f->lam.at(o), f->info_a.at(o), c.ws,
                    c.ws_bytes, B, &so, st);
     if (rc != FDM_OK) return rc;
+    if (fork) FDM_CUDA(cudaStreamWaitEvent(st, c.ev_join, 0));
     rc = fdm_adjoint_grads(p, f->q.at(o), f->xyz.at(o), f->lam.at(o), f->q_bar.at(o), f->loads_bar.at(o), f->xs_bar.at(o),
                            B, E, 0, st);
     if (rc != FDM_OK) return rc;
@@ -287,6 +301,9 @@ void destroy(fdm_fa* f) {
     for (cudaGraphExec_t g : c.exec_park)
       if (g) cudaGraphExecDestroy(g);
     if (c.done) cudaEventDestroy(c.done);
+    if (c.ev_fork) cudaEventDestroy(c.ev_fork);
+    if (c.ev_join) cudaEventDestroy(c.ev_join);
+    if (c.side) cudaStreamDestroy(c.side);
     if (c.st) cudaStreamDestroy(c.st);
     if (c.ws) cudaFree(c.ws);
   }
@@ -392,7 +409,10 @@ int fdm_fa_create(const fdm_plan* p, int64_t batch, const fdm_fa_opts* opts, fdm
     c.B = sizes[i];
     off += c.B;
     if (cudaStreamCreateWithFlags(&c.st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess) { rc = FDM_ERR_CUDA; break; }
+        cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming) != cudaSuccess) { rc = FDM_ERR_CUDA; break; }
     c.ws_bytes = std::max<size_t>(fdm_workspace_bytes(p, c.B, f->solver), 16);
     if (cudaMalloc(&c.ws, c.ws_bytes) != cudaSuccess) { rc = FDM_ERR_CUDA; break; }
   }

@@ -1444,7 +1444,9 @@ static int launch_backward(const fdm_plan* p, WArgs& A, int64_t batch, cudaStrea
   // slices: a CTA of 4 warps (78 KB, 21 K registers) fits into the hole ONE retiring factor CTA leaves (84 KB, 32 K
   // registers), the full 11-warp CTA needs a whole SM and would wait until the queue of factor CTAs has drained
   // (csrc/pipeline.cu: prioritise).  Alone, the 11-warp CTA streams best (0.195 ms backward at B = 4096).
-  int sw = sub_warps_per_cta(inflight > batch ? 4 : kSubWarps);
+  // (the paired instance of a small batch is latency-bound whatever its CTA size; small CTAs start beside the
+  //  kernels of the side stream instead of waiting for a whole SM: 512 designs 0.323 -> 0.313 ms)
+  int sw = sub_warps_per_cta(inflight > batch || A.sub_pair ? 4 : kSubWarps);
   if (A.sub_pair) sw = std::max(2, sw & ~1);
   const int dpc = A.sub_pair ? sw / 2 : sw;                // designs per CTA
   const size_t smem = (size_t)sw * kSubWarpSmem * sizeof(double);

@@ -250,6 +250,11 @@ class NativeForwardAdjoint:
         self.B = int(batch)
         self.lib = L.lib()
         self.dev = torch.device("cuda", s.device if device is None else device)
+        if chunks == "auto":
+            # device-resident step: slices of ~512 designs (measured on the 30x30 pillow: 4096 designs 8 slices
+            # 1.46 ms against 1.52 in 2, 2048 in 4 slices 0.78 against 0.91 in one, 1024 in 2 slices 0.46 against
+            # 0.50; below that one slice) -- a slice's bandwidth-bound kernels run beside the next slice's factorisation
+            chunks = max(1, self.B // 512)
         opts = L.FaOpts(int(chunks), int(bool(with_state)), L.SOLVERS[solver], int(bool(use_graph)), int(max_iters), float(tol))
         self.handle = C.c_void_p()
         L.check(self.lib.fdm_fa_create(s.plan, self.B, C.byref(opts), C.byref(self.handle)))

@@ -73,6 +73,35 @@ def test_quadratic_loss_device_step_and_host_call(chunks):
     fa.close()
 
 
+def test_auto_slices_and_side_stream_give_the_bits_of_one_slice():
+    """`chunks="auto"` cuts the batch into slices of ~512 designs, each on its own stream with positions + state on a
+    side stream and the factor kernels at the low launch priority (csrc/pipeline.cu: prioritise).  Scheduling only:
+    every output must be bit-identical to the one-slice step, also after repeated steps (the side stream of step k+1
+    must not overtake the gradient kernel of step k, which reads xyz)."""
+    import jax_fdm_b200.equilibrium as eq
+    from jax_fdm_b200.pipeline import NativeForwardAdjoint
+
+    prob = datasets.pillow_problem(30)
+    s = eq.EquilibriumStructureSparse(prob.nodes, prob.edges, prob.supports, device=0)
+    B = 1536 + 7
+    qb = datasets.pillow_batch_q(prob.edges.shape[0], 0, B)
+    x0 = prob.xyz0[s.indices_free]
+    names = ("x", "xyz", "loss", "q_bar", "loads_bar", "xs_bar", "lengths", "forces", "residuals", "vectors")
+    out = {}
+    for chunks in (1, "auto"):
+        fa = NativeForwardAdjoint(s, B, chunks=chunks, solver="cholesky")
+        assert fa.chunks == (1 if chunks == 1 else B // 512)
+        fa.set_inputs(qb, prob.xyz_fixed, prob.loads, x0)
+        for _ in range(4):
+            fa.step()
+        fa.stream.synchronize()
+        assert bool((fa.array("info_f")[:, 0] == 0).all()) and bool((fa.array("info_a")[:, 0] == 0).all())
+        out[chunks] = {k: fa.array(k).clone() for k in names}
+        fa.close()
+    for k in names:
+        assert torch.equal(out[1][k], out["auto"][k]), k
+
+
 def test_goal_program_route_matches_oracle_and_autograd():
     import jax_fdm_b200.equilibrium as eq
     from jax_fdm_b200 import goals as G, losses as LS

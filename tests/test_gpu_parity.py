@@ -316,6 +316,37 @@ def test_batched_assembly_and_spmm_are_bit_identical_to_the_per_design_kernels(e
         L.check(L.lib().fdm_loss_sqdist(P(X[b]), P(x0), P(g1), P(l1), n, 1, 0, None))
         assert torch.equal(g1, gb[b]) and torch.equal(l1[0], lb[b])
     assert np.allclose(N(lb), 0.5 * ((N(X) - N(x0)[None]) ** 2).sum(axis=(1, 2)), rtol=1e-13)
+    # the state of a batch against the state of its designs one by one, with per-design loads, shared loads (stride 0)
+    # and partial outputs (NULL arrays), straight through the C ABI; one design against the oracle
+    Nn = s.num_nodes
+    xyzb = T(rng.standard_normal((B, Nn, 3)))
+    lib = L.lib()
+
+    def state(q_, xyz_, loads_, nb, ls, want=(1, 1, 1, 1)):
+        out = [torch.full((nb, E, 3), float("nan"), dtype=X.dtype, device=X.device),
+               torch.full((nb, E), float("nan"), dtype=X.dtype, device=X.device),
+               torch.full((nb, E), float("nan"), dtype=X.dtype, device=X.device),
+               torch.full((nb, Nn, 3), float("nan"), dtype=X.dtype, device=X.device)]
+        ptrs = [P(o) if w else None for o, w in zip(out, want)]
+        L.check(lib.fdm_state(s.plan, P(q_), P(xyz_), P(loads_), *ptrs, nb, E, ls, None))
+        torch.cuda.synchronize()
+        return out
+
+    full = state(q_t, xyzb, p_t, B, Nn * 3)
+    shared = state(q_t, xyzb, p_t[0].contiguous(), B, 0)
+    for b in (0, 1, 18, B - 1):
+        one = state(q_t[b].contiguous(), xyzb[b].contiguous(), p_t[b].contiguous(), 1, 0)
+        assert all(torch.equal(o[0], f[b]) for o, f in zip(one, full))
+        one = state(q_t[b].contiguous(), xyzb[b].contiguous(), p_t[0].contiguous(), 1, 0)
+        assert all(torch.equal(o[0], f[b]) for o, f in zip(one, shared))
+    part = state(q_t, xyzb, p_t, B, Nn * 3, want=(0, 1, 0, 1))
+    assert torch.equal(part[1], full[1]) and torch.equal(part[3], full[3])
+    assert torch.isnan(part[0]).all() and torch.isnan(part[2]).all()
+    ref = oracle.equilibrium_state(qb[3], N(xyzb)[3], pb[3], so)
+    assert np.allclose(N(full[0])[3], ref["vectors"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(N(full[1])[3], ref["lengths"][:, 0], rtol=1e-12, atol=1e-12)
+    assert np.allclose(N(full[2])[3], ref["forces"][:, 0], rtol=1e-12, atol=1e-12)
+    assert np.allclose(N(full[3])[3], ref["residuals"], rtol=1e-12, atol=1e-11)
 
 
 @pytest.mark.parametrize("B,G", [(8, 4096), (9, 4096), (37, 4096), (37, 4097)])

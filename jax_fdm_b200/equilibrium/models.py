@@ -494,6 +494,12 @@ class EquilibriumModel:
     def stiffness_matrix(q, structure):
         return CSC(_Stiffness.apply(q, structure), structure)
 
+    @staticmethod
+    def stiffness_matrix_dense(q, structure):
+        """The (Nf, Nf) array the reference's dense `EquilibriumModel.stiffness_matrix` returns (models.py:800-822):
+        the same `K.data` (fdm_assemble) scattered onto its pattern; differentiable with respect to q."""
+        return CSC(_Stiffness.apply(q, structure), structure).todense()
+
     def load_matrix(self, q, xyz_fixed, load_nodes, structure):
         return _LoadMatrix.apply(q, xyz_fixed, load_nodes, structure)
 

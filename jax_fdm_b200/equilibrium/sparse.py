@@ -12,6 +12,7 @@ structure: the cotangent of `A` is a CSC whose `.data` alone is populated
 
 from typing import Callable, NamedTuple
 
+import numpy as np
 import torch
 
 from . import ops
@@ -58,6 +59,22 @@ class CSC(NamedTuple):
 
     def __matmul__(self, x):
         return _SpMM.apply(self.data, x, self.structure)
+
+    def todense(self):
+        """The dense (Nf, Nf) matrix -- (B, Nf, Nf) for a batch -- that the reference's dense model builds as
+        `c_free.T @ (q[:, None] * c_free)` (models.py:800-822): `data` scattered onto the static pattern.  For
+        inspection, small problems and code written against the dense model; the solve path never forms it."""
+        s = self.structure
+        flat = getattr(s, "_dense_flat_index", None)
+        if flat is None or flat.device != self.data.device:
+            ia = s.index_array
+            n = ia.shape[0]
+            cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(ia.indptr))
+            flat = torch.as_tensor(ia.indices.astype(np.int64) * n + cols, device=self.data.device)
+            s._dense_flat_index = flat
+        n = s.index_array.shape[0]
+        out = self.data.new_zeros(self.data.shape[:-1] + (n * n,))
+        return out.index_copy(-1, flat, self.data).reshape(self.data.shape[:-1] + (n, n))
 
 
 _DEFAULT_OPTS = {"solver": "auto", "tol": 0.0, "max_iters": 0}

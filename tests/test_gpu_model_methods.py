@@ -136,6 +136,32 @@ def test_unrolled_differentiation_matches_the_implicit_adjoint(local):
         assert relerr(b, a) <= 1e-8, nm
 
 
+@pytest.mark.parametrize("name", ["arch10", "cablenet12", "olympia", "random40", "readme10", "stuttgart21"])
+def test_dense_stiffness_matrix_is_the_reference_dense_model_array(name):
+    """`EquilibriumModel.stiffness_matrix` of the reference's dense model returns the (Nf, Nf) array
+    (models.py:800-822); `ref_dense_K` is that array, computed by the reference's own models.py."""
+    import jax_fdm_b200.equilibrium as eq
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    s = eq.EquilibriumStructureSparse(g["nodes"], g["edges"], g["supports"], device=0)
+    model = eq.EquilibriumModel(tmax=1)
+    q = T(g["q"]).requires_grad_(True)
+    Kd = model.stiffness_matrix_dense(q, s)
+    assert Kd.shape == g["ref_dense_K"].shape
+    assert np.allclose(N(Kd), g["ref_dense_K"], rtol=1e-13, atol=1e-13)
+    assert torch.equal(Kd, model.stiffness_matrix(q, s).todense())
+    # its pull-back is the transpose of the assembly: d/dq sum(W * K) against the oracle's basis matrices
+    so = oracle.build_structure(g["nodes"], g["edges"], g["supports"])
+    W = np.random.default_rng(0).standard_normal(g["ref_dense_K"].shape)
+    (Kd * T(W)).sum().backward()
+    E = g["q"].size
+    want = np.array([(om.stiffness_matrix_dense(np.eye(E)[e], so) * W).sum() for e in range(E)])
+    assert relerr(N(q.grad), want) <= 1e-12
+    # a batch scatters design by design
+    qb = T(np.stack([g["q"], 2.0 * g["q"]]))
+    Kb = model.stiffness_matrix(qb, s).todense()
+    assert Kb.shape == (2,) + g["ref_dense_K"].shape and np.allclose(N(Kb)[1], 2.0 * g["ref_dense_K"], rtol=1e-13, atol=1e-13)
+
+
 def test_splu_session_reuses_one_device_factor():
     import jax_fdm_b200.equilibrium as eq
     g = dict(np.load(os.path.join(GOLDEN, "pillow30.npz")))

@@ -7,7 +7,9 @@
 // q in (one cudaMemcpyAsync), replays its graph (solve from q -> positions -> state -> loss and cotangents ->
 // adjoint solve with the stored factor -> gradients) and copies loss and q_bar out (one cudaMemcpyAsync
 // each), all on its own stream: the H2D copy of one chunk, the kernels of another and the D2H copy of a third
-// overlap on the copy engines and the SMs.  Two losses: the benchmark's quadratic distance to x0
+// overlap on the copy engines and the SMs; inside the slice graphs the factor kernels carry the LOW launch priority
+// (prioritise) and positions + state run on a side stream (launch_chunk), so that one slice's bandwidth-bound kernels
+// run beside the next slice's issue-bound factorisation.  Two losses: the benchmark's quadratic distance to x0
 // (fdm_loss_sqdist) and a compiled goal program (fdm_goals_loss + fdm_state_vjp).
 #include <cuda_runtime.h>
 
@@ -115,7 +117,8 @@ int launch_chunk(fdm_fa* f, const Chunk& c, cudaStream_t st, int64_t* count) {
   if (rc != FDM_OK) return rc;
   // The quadratic loss reads x_free only: positions and state leave the critical path (solve -> loss -> adjoint solve)
   // and run on the slice's side stream, joined again before the gradient kernel, which reads xyz.  For a small batch
-  // every kernel of the chain is latency-bound and the step is their sum: 512 designs 0.327 -> 0.30 ms.
+  // every kernel of the chain is latency-bound and the step is their sum: 512 designs 0.331 -> 0.323 ms (0.314 with the
+  // small substitution CTAs that start beside the state kernel), 4096 designs in 8 slices 1.478 -> 1.456 ms.
   static const bool no_fork = std::getenv("FDM_FA_FORK_STATE") && std::atoi(std::getenv("FDM_FA_FORK_STATE")) == 0;
   const bool fork = !f->has_prog && !no_fork && c.side;
   cudaStream_t ss = st;

@@ -1226,13 +1226,16 @@ inline bool mma_panel4(const fdm_plan* p) {
 }
 
 // designs (= warps) per CTA of the tensor-core factor kernels; FDM_CHOL_FACWARPS overrides for experiments
-inline int mma_warps_per_cta() {
+// Two-sided factorisation of a batch too small to give every SM a four-design CTA (a warp pair per design): ONE design
+// per CTA -- 512 designs are then 512 CTAs over all 148 SMs instead of 128 CTAs on 128 of them (step 0.314 -> 0.305 ms,
+// one design 0.239 -> 0.226 ms); from ~600 designs on the four-design CTAs are better again (1024: 0.50 against 0.585).
+inline int mma_warps_per_cta(bool single = false) {
   static const int w = [] {
     const char* e = std::getenv("FDM_CHOL_FACWARPS");
-    const int v = e ? std::atoi(e) : kFacWarps;
-    return v >= 1 && v <= kFacWarps ? v : kFacWarps;
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 && v <= kFacWarps ? v : 0;
   }();
-  return w;
+  return w ? w : single ? 2 : kFacWarps;
 }
 
 // designs (= warps) per CTA of the substitution kernel (FDM_CHOL_SUBWARPS) and extra dynamic shared memory
@@ -1496,7 +1499,7 @@ int chol_warp_solve_from_q(const fdm_plan* p, const double* q, const double* xs,
   const int64_t inflight = std::max<int64_t>(batch, o.concurrent_designs);
   A.twisted = mma_panel4(p) && use_twisted(p, inflight) ? 1 : 0;
   const int stages = o.stages ? o.stages : 7;
-  int fw = mma_warps_per_cta();
+  int fw = mma_warps_per_cta(A.twisted && inflight <= 4 * (int64_t)std::max(p->sm_count, 1));
   if (A.twisted) fw = std::max(2, fw & ~1);                // a design is a warp pair
   const int dpc = A.twisted ? fw / 2 : fw;                 // designs per CTA
   const size_t smem = (size_t)fw * kMmaWarpSmem * sizeof(double) + fac_smem_pad();
@@ -1567,8 +1570,8 @@ int chol_warp_solve(const fdm_plan* p, const double* Kdata, const double* rhs, d
     int fw = kFacWarps, dpc = kFacWarps;
     if (mma) {
       fkern = mma_panel4(p) ? chol_factor_mma_kernel<false, 4, false> : chol_factor_mma_kernel<false, 2, false>;
-      fw = mma_warps_per_cta();
       A.twisted = mma_panel4(p) && use_twisted(p, std::max<int64_t>(batch, o.concurrent_designs)) ? 1 : 0;
+      fw = mma_warps_per_cta(A.twisted && std::max<int64_t>(batch, o.concurrent_designs) <= 4 * (int64_t)std::max(p->sm_count, 1));
       if (A.twisted) fw = std::max(2, fw & ~1);
       dpc = A.twisted ? fw / 2 : fw;
       if (A.twisted) fkern = chol_factor_mma_kernel<false, 4, false, true>;
